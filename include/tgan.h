@@ -1,0 +1,232 @@
+/* tgan.h -- C ABI of libtgan.so: the B200 (sm_100a) Triple-GAN training hot path.
+ *
+ * The reference (Wenyuan-Vincent-Li/Tensorflow-Implementation-of-Triple-GAN) has no FFI layer: every
+ * numerical call goes Python -> TensorFlow op.  Each entry point below replaces the TensorFlow op(s)
+ * at the cited reference call sites (file:line relative to the reference repository root); the Python
+ * mirror of the reference operator surface (tgan/nn.py, tgan/model_base.py) binds them with ctypes.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.  Every function returns 0 on success, non-zero on
+ *     error; tgan_last_error() returns a thread-local message.  No exception crosses the ABI.
+ *   - All pointers are DEVICE pointers owned by the caller (incl. workspaces); no entry point
+ *     allocates, frees or synchronises.  Every op is asynchronous on `stream` (a cudaStream_t passed
+ *     as void*), and is CUDA-graph capturable.
+ *   - Activations are NHWC, conv filters HWIO [kh,kw,Cin,Cout], transposed-conv filters
+ *     [kh,kw,Cout,Cin], dense [in,out] -- the TF variable layouts.  `ld*` = row (pixel) stride in elements.
+ *   - dtype codes: TGAN_F32 = 0, TGAN_BF16 = 1.  Parameters, statistics, gradients of parameters and
+ *     loss scalars are always fp32.
+ *   - There is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef TGAN_H_
+#define TGAN_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TGAN_F32 0
+#define TGAN_BF16 1
+
+/* activation codes for the fused epilogues */
+#define TGAN_ACT_NONE 0
+#define TGAN_ACT_RELU 1      /* tf.nn.relu          Good_GAN_cifar10.py:41,47,52 */
+#define TGAN_ACT_LRELU 2     /* leakyReLu a=0.2     Good_GAN_cifar10.py:19-27; tf.nn.leaky_relu Good_GAN.py:99 */
+#define TGAN_ACT_TANH 3      /* tf.nn.tanh          Good_GAN_cifar10.py:57 */
+#define TGAN_ACT_SIGMOID 4   /* tf.nn.sigmoid       Good_GAN_cifar10.py:99, Good_GAN.py:32 */
+#define TGAN_ACT_SOFTPLUS 5  /* tf.nn.softplus      Good_GAN.py:22,27 */
+
+const char* tgan_last_error(void);
+int tgan_version(void);
+/* number of kernels libtgan has launched in this process since the last reset (bench.py gpu_launches) */
+int64_t tgan_launch_count(void);
+void tgan_launch_count_reset(void);
+
+/* ---------------------------------------------------------------- dense contractions (fp32 SIMT) --
+ * C[M,N] = alpha * op(A) * op(B) + beta * C, row-major fp32.  Replaces tf.matmul / tf.layers.dense
+ * (nn.py:553, modle_base.py:40,67) and, with tgan_im2col / tgan_col2im, tf.nn.conv2d and
+ * tf.nn.conv2d_transpose and their gradients (nn.py:504; modle_base.py:102,149,161,250) in the
+ * fp32 parity mode and for the skinny layers (Cout in {1,3,10}).  splits > 1 = deterministic split-K:
+ * `ws` must hold splits*M*N floats. */
+int tgan_sgemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
+               const float* B, int ldb, float beta, float* C, int ldc, int splits, float* ws,
+               void* stream);
+
+/* col[(n,ho,wo),(r,s,c)] = x[n, ho*sh + r - pt, wo*sw + s - pl, c] (0 outside).  x has dtype `xdt`,
+ * pixel stride ldx; col is fp32 [N*Ho*Wo, kh*kw*C].  TF SAME/VALID geometry is the caller's pt/pl. */
+int tgan_im2col(const void* x, int xdt, int N, int H, int W, int C, int ldx, int kh, int kw, int sh,
+                int sw, int pt, int pl, int Ho, int Wo, float* col, void* stream);
+/* adjoint of tgan_im2col (gather form, deterministic): x[n,h,w,c] = sum of the col entries that read it.
+ * Writes dtype `xdt`; only channels [0,Cx) of the C channels in col are produced (label-concat slice). */
+int tgan_col2im(const float* col, int N, int H, int W, int C, int kh, int kw, int sh, int sw, int pt,
+                int pl, int Ho, int Wo, void* x, int xdt, int Cx, int ldx, void* stream);
+
+/* ---------------------------------------------------------------- implicit-GEMM tcgen05 path (bf16) --
+ * One tcgen05/TMEM/TMA kernel family.  A = activations gathered by shifted-window TMA loads (zero fill =
+ * TF padding), B = packed bf16 weights [T][Nout][Kpad], fp32 accumulation in TMEM.
+ *   out[n, oy*osy + ooy, ox*osx + oox, co] = sum_t sum_ci x[n, oy + dy[t], ox + dx[t], ci] * Wp[t][co][ci]
+ * for (oy,ox) on the [gh, gw] output grid.  Covers conv fprop / dgrad (stride 1), the four output-parity
+ * sub-convolutions of the 5x5/s2 transposed conv (modle_base.py:250) and plain GEMMs (gh=1, T=1).
+ * Replaces the same reference call sites as tgan_sgemm in the bf16 tensor-core mode. */
+typedef struct {
+  const void* x;       /* bf16 [N, H, W, ldx]                                  */
+  int N, H, W, C, ldx; /* C = contraction channels actually used (<= ldx)      */
+  const void* wp;      /* bf16 packed weights [T][Nout][Kpad], Kpad % 8 == 0   */
+  int T, Nout, Kpad;
+  int dy[25], dx[25];  /* tap offsets                                          */
+  int gh, gw;          /* output grid per image (tile = th x tw pixels)        */
+  void* out;           /* dtype odt, [N, OH, OW, ldo]                          */
+  int odt, OH, OW, ldo;
+  int osy, osx, ooy, oox; /* output placement (stride / offset)                */
+  int vh, vw;          /* number of valid grid rows/cols actually stored       */
+  const float* bias;   /* optional fp32 [Nout] added before the store          */
+  float* colsum;       /* optional fp32 [Nout]: += column sums of the stored fp32 values */
+  int act;             /* TGAN_ACT_* applied after bias (before store)         */
+  float alpha;
+} tgan_igemm_args;
+int tgan_igemm_bf16(const tgan_igemm_args* a, void* stream);
+
+/* wgrad on tensor cores: dW[t][co][ci] (+)= sum_{n,oy,ox} dz[n,oy,ox,co] * x[n, oy + dy[t], ox + dx[t], ci]
+ * (pixel dimension is the GEMM K; both operands are MN-major UMMA operands loaded by TMA).
+ * Writes fp32 partials with split-K over pixels followed by a deterministic reduce. */
+typedef struct {
+  const void* dz;      /* bf16 [N, gh, gw, lddz]                               */
+  int N, gh, gw, Cout, lddz;
+  const void* x;       /* bf16 [N, H, W, ldx]                                  */
+  int H, W, Cin, ldx;
+  int T; int dy[25], dx[25];
+  float* dw;           /* fp32 [T][Cout][Cin] (row-major), accumulate if beta != 0 */
+  float beta;
+  float* ws; int64_t ws_bytes;
+} tgan_wgrad_args;
+int tgan_wgrad_bf16(const tgan_wgrad_args* a, void* stream);
+int64_t tgan_wgrad_workspace_bytes(const tgan_wgrad_args* a);
+
+/* weight preparation for the tcgen05 path: W_eff fp32 (any of the TF layouts) -> bf16 [T][Nout][Kpad].
+ *   mode 0 (fprop):  src HWIO [T][Cin][Cout]      -> dst[t][co][ci]
+ *   mode 1 (dgrad):  src HWIO [T][Cin][Cout]      -> dst[T-1-t][ci][co]   (flipped taps, roles swapped)
+ *   mode 2 (deconv): src [T][Cout][Cin] tap subset `taps[nt]` -> dst[j][co][ci]
+ * K beyond the source extent is zero filled. */
+int tgan_pack_weight_bf16(const float* src, void* dst, int mode, int T, int Cin, int Cout, int Kpad,
+                          const int* taps_dev, int nt, void* stream);
+
+/* ---------------------------------------------------------------- weight normalisation ------------
+ * V viewed as [A, Co, B]; per output channel co: nrm = sqrt(sum_{a,b} V^2);
+ *   W = V * g[co] / nrm          (eps_mode 0: no epsilon, nn.py:554)
+ *   W = V * g[co] * rsqrt(max(nrm^2, 1e-12))  (eps_mode 1: tf.nn.l2_normalize, nn.py:502; modle_base.py:66,101,148)
+ * HWIO / [in,out]: A = kh*kw*Cin, B = 1.  Transposed-conv [kh,kw,Cout,Cin] (axes [0,1,3]): A = kh*kw, B = Cin. */
+int tgan_weightnorm_fwd(const float* V, const float* g, float* W, float* inv_norm, float* scale, int A, int Co,
+                        int B, int eps_mode, float* ws, void* stream);
+/* also writes scale[co] = g[co]*inv_norm[co]; W may be NULL (the tcgen05 path folds `scale` into
+ * tgan_pack_weight_bf16 instead).  ws: (2*TGAN_STATS_MAX_PARTS + 1)*Co floats.
+ * dg[co] (+)= <dW, V>*inv_norm ; dV (+)= (g*inv_norm) * (dW - V*inv_norm * <dW,V>*inv_norm)    */
+int tgan_weightnorm_bwd(const float* V, const float* g, const float* inv_norm, const float* dW, float* dV,
+                        float* dg, int A, int Co, int B, float beta, float* ws, void* stream);
+
+/* ---------------------------------------------------------------- per-channel statistics ----------
+ * x [rows, C] (dtype xdt, contiguous): sum[c] = sum_r x, sumsq[c] = sum_r x^2 (sumsq may be NULL).
+ * Deterministic two-stage reduction; ws must hold 2*TGAN_STATS_MAX_PARTS*C floats. */
+#define TGAN_STATS_MAX_PARTS 256
+int tgan_channel_stats(const void* x, int xdt, int64_t rows, int C, float* sum, float* sumsq, float* ws,
+                       void* stream);
+
+/* mean-only batch norm, training branch (nn.py:172-183): given sum[c] over `rows`,
+ *   mean = sum/rows ; shift[c] = b[c] - mean ; pop_mean = pop_mean*decay + mean*(1-decay). */
+int tgan_mobn_finalize(const float* sum, int64_t rows, int C, const float* b, float* pop_mean, float decay,
+                       float* shift, void* stream);
+/* testing branch (nn.py:170-171): shift = b - pop_mean */
+int tgan_mobn_eval_shift(const float* b, const float* pop_mean, int C, float* shift, void* stream);
+
+/* tf.contrib.layers.batch_norm training statistics (modle_base.py:229-237):
+ *   mean, rstd = rsqrt(var_biased + eps); scale = gamma*rstd; shift = beta - mean*scale;
+ *   moving_mean/variance <- decay-EMA (variance uses the unbiased estimate). */
+int tgan_bn_finalize(const float* sum, const float* sumsq, int64_t rows, int C, const float* gamma,
+                     const float* beta, float eps, float decay, float* moving_mean, float* moving_var,
+                     float* mean, float* rstd, float* scale, float* shift, void* stream);
+int tgan_bn_eval_affine(const float* gamma, const float* beta, const float* moving_mean,
+                        const float* moving_var, float eps, int C, float* scale, float* shift, void* stream);
+
+/* y = act(x*scale[c] + shift[c]) ; scale/shift may be NULL (1 / 0).  x [rows,C] dtype xdt -> y dtype ydt.
+ * The one fused epilogue: bias + nonlinearity (nn.py:508,517), mean-only-BN apply + lrelu (nn.py:183,517),
+ * BN apply (modle_base.py:230), tanh/sigmoid heads. */
+int tgan_affine_act(const void* x, int xdt, void* y, int ydt, int64_t rows, int C, const float* scale,
+                    const float* shift, int act, float alpha, void* stream);
+/* du = dy * act'(.) computed from the activation OUTPUT y; also per-channel partial sums of du
+ * (-> bias gradient / mean-only-BN backward).  colsum[c] = sum_r du (deterministic, ws as channel_stats). */
+int tgan_act_bwd(const void* dy, int dydt, const void* y, int ydt, void* du, int dudt, int64_t rows, int C,
+                 int act, float alpha, float* colsum, float* ws, void* stream);
+/* mean-only BN backward: dz = du - colsum[c]/rows */
+int tgan_sub_channel_mean(const void* du, int dudt, void* dz, int dzdt, int64_t rows, int C,
+                          const float* colsum, void* stream);
+/* BN backward: s1[c] = sum dy, s2[c] = sum dy*xhat, then dx = scale*(dy - s1/M - xhat*s2/M);
+ * dgamma (+)= s2, dbeta (+)= s1. */
+int tgan_bn_bwd(const void* dy, int dydt, const void* x, int xdt, void* dx, int dxdt, int64_t rows, int C,
+                const float* mean, const float* rstd, const float* gamma, float* dgamma, float* dbeta,
+                float beta_acc, float* ws, void* stream);
+
+/* ---------------------------------------------------------------- pointwise layers ----------------
+ * Gaussian noise (modle_base.py:193-202; Good_GAN_cifar10.py:29-31): y = x + std * n,
+ * n = noise[i] if noise != NULL (parity mode, fp32 standard normal) else Philox4x32-10(seed,stream_id,*counter). */
+int tgan_add_noise(const void* x, int xdt, void* y, int ydt, int64_t n, float std, const float* noise,
+                   uint64_t seed, uint64_t stream_id, const uint64_t* counter, void* stream);
+/* inverted dropout (tf.layers.dropout, modle_base.py:190; Good_GAN_cifar10.py:124,143):
+ * y = x * keep / (1-rate).  gen != 0: draw keep from Philox and WRITE mask; gen == 0: READ mask (uint8 0/1). */
+int tgan_dropout(const void* x, int xdt, void* y, int ydt, uint8_t* mask, int64_t n, float rate, int gen,
+                 uint64_t seed, uint64_t stream_id, const uint64_t* counter, void* stream);
+/* 2x2/s2 max pool on even extents (tf.nn.max_pool SAME, Good_GAN_cifar10.py:123,142; max_pooling2d(2,2)
+ * Good_GAN.py:223): writes the winner index (first max, row-major window order) for the backward. */
+int tgan_maxpool2_fwd(const void* x, int dt, void* y, uint8_t* idx, int N, int H, int W, int C, void* stream);
+int tgan_maxpool2_bwd(const void* dy, int dt, const uint8_t* idx, void* dx, int N, int H, int W, int C,
+                      void* stream);
+/* global pooling over H*W: mode 0 = max (max_pooling2d(6,1) 'avg_pool_0', Good_GAN_cifar10.py:163),
+ * mode 1 = mean (average_pooling2d(8,1) :94; reduce_mean([1,2]) Good_GAN.py:157,243,295). */
+int tgan_global_pool_fwd(const void* x, int xdt, void* y, int ydt, uint8_t* idx, int N, int HW, int C,
+                         int mode, void* stream);
+int tgan_global_pool_bwd(const void* dy, int dydt, const uint8_t* idx, void* dx, int dxdt, int N, int HW,
+                         int C, int mode, void* stream);
+/* _conv_cond_concat / tf.concat([h, y], 1) (modle_base.py:239-244; Good_GAN_cifar10.py:38,97):
+ * out[r, 0:C] = x[r, 0:C]; out[r, C:C+K] = lab[r / rows_per_sample, 0:K]; out[r, C+K:ldo] = 0. */
+int tgan_concat_label(const void* x, int xdt, int64_t rows, int C, int ldx, const float* lab, int K,
+                      int rows_per_sample, void* out, int odt, int ldo, void* stream);
+/* strided channel slice / cast: dst[r, 0:C] = src[r, 0:C] */
+int tgan_copy_channels(const void* src, int sdt, int lds, void* dst, int ddt, int ldd, int64_t rows, int C,
+                       void* stream);
+/* y (+)= x elementwise (gradient accumulation), fp32 or bf16 */
+int tgan_accumulate(void* y, const void* x, int dt, int64_t n, void* stream);
+int tgan_fill_f32(float* p, float v, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------- pseudo-labels -------------------
+ * tf.argmax(axis=1) -> int64 (lowest index wins ties; NaN never wins over a number) and
+ * tf.one_hot(depth=K) fp32 (Good_GAN_cifar10.py:232,237,259,270; Good_GAN.py:447,451,458,468). */
+int tgan_argmax_onehot(const float* logits, int N, int K, int64_t* idx, float* onehot, void* stream);
+
+/* ---------------------------------------------------------------- losses (train_base.py:113-154) --
+ * d_loss = CE(1,dr) + .5 CE(0,df) + .5 CE(0,du)  and its dlogits (train_base.py:123-126). */
+int tgan_loss_d(const float* dr, int nr, const float* df, int nf, const float* du, int nu, float* loss,
+                float* g_dr, float* g_df, float* g_du, void* stream);
+/* g_loss = .5 CE(1,df) (train_base.py:128) */
+int tgan_loss_g(const float* df, int nf, float* loss, float* g_df, void* stream);
+/* c_loss (train_base.py:130-152) with its four dlogits; c_rep / g_rep may be NULL (non-cifar10).
+ * lambdas = device float[2] {lambda_1, lambda_2}. */
+int tgan_loss_c(const float* c_real, const float* y_l_c, int n_real, const float* c_unl, const float* c_rep,
+                const float* d_unl_logits, int n_unl, const float* c_fake, const float* y_g, int n_fake,
+                int K, const float* lambdas, float* loss, float* g_real, float* g_unl, float* g_rep,
+                float* g_fake, void* stream);
+
+/* ---------------------------------------------------------------- optimiser -----------------------
+ * tf.train.AdamOptimizer kernel form (train_base.py:91-97; Train_goodGAN.py:85-94) over one flat buffer:
+ *   a = lr*sqrt(1-b2^t)/(1-b1^t); m += (g-m)(1-b1); v += (g^2-v)(1-b2); theta -= a*m/(sqrt(v)+eps)
+ * state = device float[3] {lr, beta1_power, beta2_power}; grad is multiplied by grad_scale first
+ * (1/world_size after the NCCL sum).  If ema != NULL also applies tf.train.ExponentialMovingAverage
+ * (Train_goodGAN.py:101-103): ema -= (ema - theta)*(1-ema_decay). */
+int tgan_adam(float* theta, float* m, float* v, const float* grad, int64_t n, const float* state,
+              float beta1, float beta2, float eps, float grad_scale, float* ema, float ema_decay,
+              void* stream);
+/* beta1_power *= beta1, beta2_power *= beta2 (TF's _finish) */
+int tgan_adam_advance(float* state, float beta1, float beta2, void* stream);
+/* Philox counter bump once per step: *counter += inc */
+int tgan_counter_advance(uint64_t* counter, uint64_t inc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TGAN_H_ */

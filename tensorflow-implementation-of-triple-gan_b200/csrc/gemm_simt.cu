@@ -1,0 +1,180 @@
+// gemm_simt.cu -- fp32 CUDA-core GEMM + im2col / col2im.
+// The fp32 parity path of every dense contraction (tf.nn.conv2d nn.py:504, tf.nn.conv2d_transpose
+// modle_base.py:149,250, tf.matmul nn.py:553) and the production path of the skinny layers
+// (Cout in {1,3,10}) where a 128-wide UMMA tile would be >90% padding.
+#include "common.cuh"
+
+namespace tgan {
+
+constexpr int BM = 64, BN = 64, BK = 16;
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A,
+                                                    int lda, const float* __restrict__ B, int ldb, float beta,
+                                                    float* __restrict__ C, int ldc, int kper, float* __restrict__ ws) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kbeg = blockIdx.z * kper, kend = min(K, kbeg + kper);
+  const int tx = tid % 16, ty = tid / 16;
+  float acc[4][4] = {};
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int m, k;
+      if (!TA) { k = tid % 16; m = tid / 16 + i * 16; } else { m = tid % 64; k = tid / 64 + i * 4; }
+      int gm = m0 + m, gk = k0 + k;
+      float v = 0.f;
+      if (gm < M && gk < kend) v = TA ? A[(int64_t)gk * lda + gm] : A[(int64_t)gm * lda + gk];
+      As[k][m] = v;
+      int n, kb;
+      if (!TB) { n = tid % 64; kb = tid / 64 + i * 4; } else { kb = tid % 16; n = tid / 16 + i * 16; }
+      int gn = n0 + n, gkb = k0 + kb;
+      float w = 0.f;
+      if (gn < N && gkb < kend) w = TB ? B[(int64_t)gn * ldb + gkb] : B[(int64_t)gkb * ldb + gn];
+      Bs[kb][n] = w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[4], b[4];
+      float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      a[0] = av.x; a[1] = av.y; a[2] = av.z; a[3] = av.w;
+      b[0] = bv.x; b[1] = bv.y; b[2] = bv.z; b[3] = bv.w;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      if (ws) {
+        ws[((int64_t)blockIdx.z * M + gm) * N + gn] = acc[i][j];
+      } else {
+        float* c = C + (int64_t)gm * ldc + gn;
+        *c = alpha * acc[i][j] + (beta != 0.f ? beta * (*c) : 0.f);
+      }
+    }
+  }
+}
+
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, int M, int N, float alpha, float beta,
+                                     float* __restrict__ C, int ldc) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)M * N) return;
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += ws[(int64_t)z * M * N + i];
+  int m = (int)(i / N), n = (int)(i % N);
+  float* c = C + (int64_t)m * ldc + n;
+  *c = alpha * s + (beta != 0.f ? beta * (*c) : 0.f);
+}
+
+template <typename T>
+__global__ void im2col_kernel(const T* __restrict__ x, int N, int H, int W, int C, int ldx, int kh, int kw, int sh,
+                              int sw, int pt, int pl, int Ho, int Wo, float* __restrict__ col, int64_t total) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int c = (int)(i % C);
+  int64_t t = i / C;
+  int s = (int)(t % kw); t /= kw;
+  int r = (int)(t % kh); t /= kh;
+  int wo = (int)(t % Wo); t /= Wo;
+  int ho = (int)(t % Ho);
+  int n = (int)(t / Ho);
+  int hi = ho * sh + r - pt, wi = wo * sw + s - pl;
+  float v = 0.f;
+  if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = ldf<T>(x, ((int64_t)(n * H + hi) * W + wi) * ldx + c);
+  col[i] = v;
+}
+
+template <typename T>
+__global__ void col2im_kernel(const float* __restrict__ col, int N, int H, int W, int C, int kh, int kw, int sh,
+                              int sw, int pt, int pl, int Ho, int Wo, T* __restrict__ x, int Cx, int ldx,
+                              int64_t total) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int c = (int)(i % Cx);
+  int64_t t = i / Cx;
+  int w = (int)(t % W); t /= W;
+  int h = (int)(t % H);
+  int n = (int)(t / H);
+  float acc = 0.f;
+  for (int r = 0; r < kh; ++r) {
+    int hh = h + pt - r;
+    if (hh < 0 || hh % sh) continue;
+    int ho = hh / sh;
+    if (ho >= Ho) continue;
+    for (int s = 0; s < kw; ++s) {
+      int ww = w + pl - s;
+      if (ww < 0 || ww % sw) continue;
+      int wo = ww / sw;
+      if (wo >= Wo) continue;
+      acc += col[(((int64_t)(n * Ho + ho) * Wo + wo) * (kh * kw) + r * kw + s) * C + c];
+    }
+  }
+  stf<T>(x, ((int64_t)(n * H + h) * W + w) * ldx + c, acc);
+}
+
+}  // namespace tgan
+
+using namespace tgan;
+
+extern "C" int tgan_sgemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
+                          const float* B, int ldb, float beta, float* C, int ldc, int splits, float* ws,
+                          void* stream) {
+  TGAN_CHECK_ARG(M > 0 && N > 0 && K > 0, "sgemm: empty problem %d %d %d", M, N, K);
+  TGAN_CHECK_ARG(A && B && C, "sgemm: null pointer");
+  if (splits < 1) splits = 1;
+  TGAN_CHECK_ARG(splits == 1 || ws, "sgemm: split-K needs a workspace");
+  int kper = ((ceil_div(K, splits) + BK - 1) / BK) * BK;
+  splits = ceil_div(K, kper);
+  dim3 grid(ceil_div(N, BN), ceil_div(M, BM), splits);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* w = splits > 1 ? ws : nullptr;
+#define L(TA, TB) sgemm_kernel<TA, TB><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, kper, w)
+  if (!transA && !transB) L(false, false);
+  else if (!transA && transB) L(false, true);
+  else if (transA && !transB) L(true, false);
+  else L(true, true);
+#undef L
+  TGAN_LAUNCHED();
+  if (splits > 1) {
+    int64_t tot = (int64_t)M * N;
+    splitk_reduce_kernel<<<ceil_div(tot, 256), 256, 0, st>>>(ws, splits, M, N, alpha, beta, C, ldc);
+    TGAN_LAUNCHED();
+  }
+  return 0;
+}
+
+extern "C" int tgan_im2col(const void* x, int xdt, int N, int H, int W, int C, int ldx, int kh, int kw, int sh,
+                           int sw, int pt, int pl, int Ho, int Wo, float* col, void* stream) {
+  TGAN_CHECK_ARG(x && col, "im2col: null pointer");
+  int64_t total = (int64_t)N * Ho * Wo * kh * kw * C;
+  TGAN_CHECK_ARG(total > 0, "im2col: empty");
+  TGAN_DISPATCH_1(xdt, T, (im2col_kernel<T><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                              (const T*)x, N, H, W, C, ldx, kh, kw, sh, sw, pt, pl, Ho, Wo, col, total)));
+  TGAN_LAUNCHED();
+  return 0;
+}
+
+extern "C" int tgan_col2im(const float* col, int N, int H, int W, int C, int kh, int kw, int sh, int sw, int pt,
+                           int pl, int Ho, int Wo, void* x, int xdt, int Cx, int ldx, void* stream) {
+  TGAN_CHECK_ARG(x && col, "col2im: null pointer");
+  TGAN_CHECK_ARG(Cx <= C && Cx <= ldx, "col2im: bad channel slice");
+  int64_t total = (int64_t)N * H * W * Cx;
+  TGAN_CHECK_ARG(total > 0, "col2im: empty");
+  TGAN_DISPATCH_1(xdt, T, (col2im_kernel<T><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                              col, N, H, W, C, kh, kw, sh, sw, pt, pl, Ho, Wo, (T*)x, Cx, ldx, total)));
+  TGAN_LAUNCHED();
+  return 0;
+}

@@ -1,0 +1,547 @@
+// pointwise.cu -- HBM-bound elementwise / per-channel-reduction kernels of the Triple-GAN step:
+// mean-only BN and BN statistics + apply (nn.py:147-187; modle_base.py:229-237), fused
+// bias/activation epilogues, Gaussian noise, dropout, pooling, label concat, argmax/one-hot.
+// All kernels are vectorised (4 elements / thread) when the channel count allows, coalesced along the
+// NHWC channel axis, and reduce with shared memory + a deterministic second stage (no atomics).
+#include "common.cuh"
+#include "colreduce.cuh"
+
+namespace tgan {
+
+template <typename T, int VEC>
+struct StatsF {
+  const T* x; int C;
+  __device__ void operator()(int64_t r, int c0, float (&v)[2][VEC]) const {
+    if constexpr (VEC == 4) {
+      float t[4]; ld4<T>(x, r * C + c0, t);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { v[0][j] = t[j]; v[1][j] = t[j] * t[j]; }
+    } else {
+      float t = ldf<T>(x, r * C + c0); v[0][0] = t; v[1][0] = t * t;
+    }
+  }
+};
+
+template <typename TDY, typename TY, typename TDU, int VEC>
+struct ActBwdF {
+  const TDY* dy; const TY* y; TDU* du; int C; int act; float alpha;
+  __device__ void operator()(int64_t r, int c0, float (&v)[1][VEC]) const {
+    if constexpr (VEC == 4) {
+      float a[4], b[4], o[4];
+      ld4<TDY>(dy, r * C + c0, a); ld4<TY>(y, r * C + c0, b);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { o[j] = a[j] * act_grad_from_y(b[j], act, alpha); v[0][j] = o[j]; }
+      st4<TDU>(du, r * C + c0, o);
+    } else {
+      float o = ldf<TDY>(dy, r * C + c0) * act_grad_from_y(ldf<TY>(y, r * C + c0), act, alpha);
+      v[0][0] = o; stf<TDU>(du, r * C + c0, o);
+    }
+  }
+};
+
+template <typename TDY, typename TX, int VEC>
+struct BnBwdStatsF {
+  const TDY* dy; const TX* x; const float* mean; const float* rstd; int C;
+  __device__ void operator()(int64_t r, int c0, float (&v)[2][VEC]) const {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float d = ldf<TDY>(dy, r * C + c0 + j);
+      float xh = (ldf<TX>(x, r * C + c0 + j) - mean[c0 + j]) * rstd[c0 + j];
+      v[0][j] = d; v[1][j] = d * xh;
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// finalize kernels (tiny, one thread per channel)
+// ------------------------------------------------------------------------------------------------
+__global__ void mobn_finalize_kernel(const float* sum, float inv_rows, int C, const float* b, float* pop_mean,
+                                     float decay, float* shift) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float m = sum[c] * inv_rows;
+  shift[c] = (b ? b[c] : 0.f) - m;
+  if (pop_mean) pop_mean[c] = pop_mean[c] * decay + m * (1.f - decay);
+}
+__global__ void mobn_eval_kernel(const float* b, const float* pop_mean, int C, float* shift) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) shift[c] = (b ? b[c] : 0.f) - pop_mean[c];
+}
+__global__ void bn_finalize_kernel(const float* sum, const float* sumsq, float rows, int C, const float* gamma,
+                                   const float* beta, float eps, float decay, float* mm, float* mv, float* mean,
+                                   float* rstd, float* scale, float* shift) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mu = sum[c] / rows;
+  float var = fmaxf(sumsq[c] / rows - mu * mu, 0.f);
+  float rs = rsqrtf(var + eps);
+  mean[c] = mu; rstd[c] = rs;
+  float sc = gamma[c] * rs;
+  scale[c] = sc; shift[c] = beta[c] - mu * sc;
+  if (mm) mm[c] = mm[c] * decay + mu * (1.f - decay);
+  if (mv) mv[c] = mv[c] * decay + var * (rows / fmaxf(rows - 1.f, 1.f)) * (1.f - decay);
+}
+__global__ void bn_eval_kernel(const float* gamma, const float* beta, const float* mm, const float* mv, float eps,
+                               int C, float* scale, float* shift) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float sc = gamma[c] * rsqrtf(mv[c] + eps);
+  scale[c] = sc; shift[c] = beta[c] - mm[c] * sc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// elementwise kernels over [rows, C]
+// ------------------------------------------------------------------------------------------------
+template <typename TX, typename TY, int VEC>
+__global__ void affine_act_kernel(const TX* __restrict__ x, TY* __restrict__ y, int64_t nvec, int C,
+                                  const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                                  float alpha) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t e = i * VEC;
+    int c = (int)(e % C);
+    if constexpr (VEC == 4) {
+      float v[4]; ld4<TX>(x, e, v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        v[j] = act_fwd(v[j] * (scale ? scale[c + j] : 1.f) + (shift ? shift[c + j] : 0.f), act, alpha);
+      st4<TY>(y, e, v);
+    } else {
+      float v = ldf<TX>(x, e);
+      stf<TY>(y, e, act_fwd(v * (scale ? scale[c] : 1.f) + (shift ? shift[c] : 0.f), act, alpha));
+    }
+  }
+}
+
+template <typename TA, typename TB, int VEC>
+__global__ void sub_mean_kernel(const TA* __restrict__ du, TB* __restrict__ dz, int64_t nvec, int C,
+                                const float* __restrict__ colsum, float inv_rows) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t e = i * VEC;
+    int c = (int)(e % C);
+    if constexpr (VEC == 4) {
+      float v[4]; ld4<TA>(du, e, v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] -= colsum[c + j] * inv_rows;
+      st4<TB>(dz, e, v);
+    } else {
+      stf<TB>(dz, e, ldf<TA>(du, e) - colsum[c] * inv_rows);
+    }
+  }
+}
+
+template <typename TDY, typename TX, typename TDX>
+__global__ void bn_bwd_apply_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, TDX* __restrict__ dx,
+                                    int64_t n, int C, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                    const float* __restrict__ gamma, const float* __restrict__ s1,
+                                    const float* __restrict__ s2, float inv_rows) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    float xh = (ldf<TX>(x, i) - mean[c]) * rstd[c];
+    float d = ldf<TDY>(dy, i);
+    stf<TDX>(dx, i, gamma[c] * rstd[c] * (d - s1[c] * inv_rows - xh * s2[c] * inv_rows));
+  }
+}
+__global__ void add_to_kernel(float* dst, const float* src, int n, float beta) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (beta != 0.f ? beta * dst[i] : 0.f) + src[i];
+}
+
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
+  float u1 = ((a >> 8) + 1) * (1.0f / 16777216.0f);  // (0,1]
+  float u2 = u32_to_unit(b);
+  float r = sqrtf(-2.f * logf(u1));
+  float s, c;
+  sincospif(2.f * u2, &s, &c);
+  n0 = r * c; n1 = r * s;
+}
+
+template <typename TX, typename TY>
+__global__ void add_noise_kernel(const TX* __restrict__ x, TY* __restrict__ y, int64_t n, float std,
+                                 const float* __restrict__ noise, uint64_t seed, uint64_t stream_id,
+                                 const uint64_t* __restrict__ counter) {
+  int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 elements
+  int64_t e = q * 4;
+  if (e >= n) return;
+  float z[4];
+  if (noise) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) z[j] = (e + j < n) ? noise[e + j] : 0.f;
+  } else {
+    uint64_t ctr = counter ? *counter : 0;
+    uint4 r = Philox(seed)((uint64_t)q, stream_id + (ctr << 20));
+    box_muller(r.x, r.y, z[0], z[1]);
+    box_muller(r.z, r.w, z[2], z[3]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (e + j < n) stf<TY>(y, e + j, ldf<TX>(x, e + j) + std * z[j]);
+}
+
+template <typename TX, typename TY>
+__global__ void dropout_kernel(const TX* __restrict__ x, TY* __restrict__ y, uint8_t* __restrict__ mask, int64_t n,
+                               float rate, float scale, int gen, uint64_t seed, uint64_t stream_id,
+                               const uint64_t* __restrict__ counter) {
+  int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t e = q * 4;
+  if (e >= n) return;
+  uint8_t k[4];
+  if (gen) {
+    uint64_t ctr = counter ? *counter : 0;
+    uint4 r = Philox(seed)((uint64_t)q, stream_id + (ctr << 20));
+    k[0] = u32_to_unit(r.x) >= rate; k[1] = u32_to_unit(r.y) >= rate;
+    k[2] = u32_to_unit(r.z) >= rate; k[3] = u32_to_unit(r.w) >= rate;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) k[j] = (e + j < n) ? mask[e + j] : 0;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (e + j < n) {
+      if (gen) mask[e + j] = k[j];
+      stf<TY>(y, e + j, k[j] ? ldf<TX>(x, e + j) * scale : 0.f);
+    }
+  }
+}
+
+template <typename T>
+__global__ void maxpool2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint8_t* __restrict__ idx, int N,
+                                    int H, int W, int C, int64_t total) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int c = (int)(i % C);
+  int64_t t = i / C;
+  int Wo = W / 2, Ho = H / 2;
+  int wo = (int)(t % Wo); t /= Wo;
+  int ho = (int)(t % Ho);
+  int n = (int)(t / Ho);
+  const T* p = x + ((int64_t)(n * H + 2 * ho) * W + 2 * wo) * C + c;
+  float v0 = ldf<T>(p, 0), v1 = ldf<T>(p, C), v2 = ldf<T>(p, (int64_t)W * C), v3 = ldf<T>(p, (int64_t)W * C + C);
+  float m = v0; int k = 0;
+  if (v1 > m) { m = v1; k = 1; }
+  if (v2 > m) { m = v2; k = 2; }
+  if (v3 > m) { m = v3; k = 3; }
+  stf<T>(y, i, m);
+  idx[i] = (uint8_t)k;
+}
+template <typename T>
+__global__ void maxpool2_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ idx, T* __restrict__ dx,
+                                    int N, int H, int W, int C, int64_t total) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int c = (int)(i % C);
+  int64_t t = i / C;
+  int Wo = W / 2, Ho = H / 2;
+  int wo = (int)(t % Wo); t /= Wo;
+  int ho = (int)(t % Ho);
+  int n = (int)(t / Ho);
+  T* p = dx + ((int64_t)(n * H + 2 * ho) * W + 2 * wo) * C + c;
+  float d = ldf<T>(dy, i);
+  int k = idx[i];
+  stf<T>(p, 0, k == 0 ? d : 0.f);
+  stf<T>(p, C, k == 1 ? d : 0.f);
+  stf<T>(p, (int64_t)W * C, k == 2 ? d : 0.f);
+  stf<T>(p, (int64_t)W * C + C, k == 3 ? d : 0.f);
+}
+
+template <typename TX, typename TY>
+__global__ void global_pool_fwd_kernel(const TX* __restrict__ x, TY* __restrict__ y, uint8_t* __restrict__ idx,
+                                       int N, int HW, int C, int mode) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  int c = i % C, n = i / C;
+  const TX* p = x + (int64_t)n * HW * C + c;
+  if (mode == 0) {
+    float m = ldf<TX>(p, 0); int k = 0;
+    for (int j = 1; j < HW; ++j) { float v = ldf<TX>(p, (int64_t)j * C); if (v > m) { m = v; k = j; } }
+    stf<TY>(y, i, m);
+    if (idx) idx[i] = (uint8_t)k;
+  } else {
+    float s = 0.f;
+    for (int j = 0; j < HW; ++j) s += ldf<TX>(p, (int64_t)j * C);
+    stf<TY>(y, i, s / HW);
+  }
+}
+template <typename TDY, typename TDX>
+__global__ void global_pool_bwd_kernel(const TDY* __restrict__ dy, const uint8_t* __restrict__ idx,
+                                       TDX* __restrict__ dx, int N, int HW, int C, int mode, int64_t total) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int c = (int)(i % C);
+  int64_t t = i / C;
+  int j = (int)(t % HW);
+  int n = (int)(t / HW);
+  float d = ldf<TDY>(dy, (int64_t)n * C + c);
+  float v = mode == 0 ? (idx[n * C + c] == j ? d : 0.f) : d / HW;
+  stf<TDX>(dx, i, v);
+}
+
+template <typename TX, typename TO>
+__global__ void concat_label_kernel(const TX* __restrict__ x, int64_t rows, int C, int ldx,
+                                    const float* __restrict__ lab, int K, int rps, TO* __restrict__ out, int ldo,
+                                    int64_t total) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int j = (int)(i % ldo);
+  int64_t r = i / ldo;
+  float v = 0.f;
+  if (j < C) v = ldf<TX>(x, r * ldx + j);
+  else if (j < C + K) v = lab[(r / rps) * K + (j - C)];
+  stf<TO>(out, i, v);
+}
+template <typename TS, typename TD>
+__global__ void copy_channels_kernel(const TS* __restrict__ src, int lds, TD* __restrict__ dst, int ldd, int C,
+                                     int64_t total) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int j = (int)(i % C);
+  int64_t r = i / C;
+  stf<TD>(dst, r * ldd + j, ldf<TS>(src, r * lds + j));
+}
+template <typename T>
+__global__ void accumulate_kernel(T* __restrict__ y, const T* __restrict__ x, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    stf<T>(y, i, ldf<T>(y, i) + ldf<T>(x, i));
+}
+__global__ void fill_kernel(float* p, float v, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = v;
+}
+
+__global__ void argmax_onehot_kernel(const float* __restrict__ logits, int N, int K, int64_t* __restrict__ idx,
+                                     float* __restrict__ onehot) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float* p = logits + (int64_t)n * K;
+  int best = 0;
+  float m = p[0];
+  // strict '>' keeps the lowest index on ties; a NaN candidate never replaces a number, and a NaN
+  // incumbent is replaced by the first number that follows (NaN > x is false, so handle it explicitly).
+  for (int k = 1; k < K; ++k) {
+    float v = p[k];
+    if (v > m || (m != m && v == v)) { m = v; best = k; }
+  }
+  if (idx) idx[n] = best;
+  if (onehot)
+    for (int k = 0; k < K; ++k) onehot[(int64_t)n * K + k] = (k == best) ? 1.f : 0.f;
+}
+
+static inline int grid_for(int64_t n, int block = 256) {
+  int64_t g = (n + block - 1) / block;
+  int64_t cap = 148 * 16;
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace tgan
+
+using namespace tgan;
+
+#define DISPATCH_2(d1, T1, d2, T2, ...) TGAN_DISPATCH_1(d1, T1, TGAN_DISPATCH_1(d2, T2, __VA_ARGS__))
+
+extern "C" int tgan_channel_stats(const void* x, int xdt, int64_t rows, int C, float* sum, float* sumsq, float* ws,
+                                  void* stream) {
+  TGAN_CHECK_ARG(x && sum && ws && rows > 0 && C > 0, "channel_stats: bad args");
+  bool v = (C % 4 == 0) && aligned16(x);
+  TGAN_DISPATCH_1(xdt, T, {
+    StatsF<T, 1> f1{(const T*)x, C};
+    StatsF<T, 4> f4{(const T*)x, C};
+    return run_colreduce<2>(f1, f4, v, rows, C, sum, sumsq, 0.f, ws, (cudaStream_t)stream);
+  });
+  return 0;
+}
+
+extern "C" int tgan_mobn_finalize(const float* sum, int64_t rows, int C, const float* b, float* pop_mean, float decay,
+                                  float* shift, void* stream) {
+  TGAN_CHECK_ARG(sum && shift && rows > 0, "mobn_finalize: bad args");
+  mobn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(sum, 1.0f / (float)rows, C, b, pop_mean,
+                                                                           decay, shift);
+  TGAN_LAUNCHED();
+  return 0;
+}
+extern "C" int tgan_mobn_eval_shift(const float* b, const float* pop_mean, int C, float* shift, void* stream) {
+  TGAN_CHECK_ARG(pop_mean && shift, "mobn_eval_shift: bad args");
+  mobn_eval_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(b, pop_mean, C, shift);
+  TGAN_LAUNCHED();
+  return 0;
+}
+extern "C" int tgan_bn_finalize(const float* sum, const float* sumsq, int64_t rows, int C, const float* gamma,
+                                const float* beta, float eps, float decay, float* moving_mean, float* moving_var,
+                                float* mean, float* rstd, float* scale, float* shift, void* stream) {
+  TGAN_CHECK_ARG(sum && sumsq && gamma && beta && mean && rstd && scale && shift, "bn_finalize: bad args");
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(sum, sumsq, (float)rows, C, gamma, beta, eps,
+                                                                         decay, moving_mean, moving_var, mean, rstd,
+                                                                         scale, shift);
+  TGAN_LAUNCHED();
+  return 0;
+}
+extern "C" int tgan_bn_eval_affine(const float* gamma, const float* beta, const float* moving_mean,
+                                   const float* moving_var, float eps, int C, float* scale, float* shift,
+                                   void* stream) {
+  bn_eval_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(gamma, beta, moving_mean, moving_var, eps, C,
+                                                                     scale, shift);
+  TGAN_LAUNCHED();
+  return 0;
+}
+
+extern "C" int tgan_affine_act(const void* x, int xdt, void* y, int ydt, int64_t rows, int C, const float* scale,
+                               const float* shift, int act, float alpha, void* stream) {
+  TGAN_CHECK_ARG(x && y && rows > 0 && C > 0, "affine_act: bad args");
+  int64_t n = rows * C;
+  bool v = (C % 4 == 0) && aligned16(x) && aligned16(y);
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_2(xdt, TX, ydt, TY, {
+    if (v) affine_act_kernel<TX, TY, 4><<<grid_for(n / 4), 256, 0, st>>>((const TX*)x, (TY*)y, n / 4, C, scale, shift, act, alpha);
+    else affine_act_kernel<TX, TY, 1><<<grid_for(n), 256, 0, st>>>((const TX*)x, (TY*)y, n, C, scale, shift, act, alpha);
+  });
+  TGAN_LAUNCHED();
+  return 0;
+}
+
+extern "C" int tgan_act_bwd(const void* dy, int dydt, const void* y, int ydt, void* du, int dudt, int64_t rows, int C,
+                            int act, float alpha, float* colsum, float* ws, void* stream) {
+  TGAN_CHECK_ARG(dy && y && du && ws && rows > 0 && C > 0, "act_bwd: bad args");
+  bool v = (C % 4 == 0) && aligned16(dy) && aligned16(y) && aligned16(du);
+  TGAN_DISPATCH_1(dydt, TDY, TGAN_DISPATCH_1(ydt, TY, TGAN_DISPATCH_1(dudt, TDU, {
+    ActBwdF<TDY, TY, TDU, 1> f1{(const TDY*)dy, (const TY*)y, (TDU*)du, C, act, alpha};
+    ActBwdF<TDY, TY, TDU, 4> f4{(const TDY*)dy, (const TY*)y, (TDU*)du, C, act, alpha};
+    return run_colreduce<1>(f1, f4, v, rows, C, colsum, nullptr, 0.f, ws, (cudaStream_t)stream);
+  })));
+  return 0;
+}
+
+extern "C" int tgan_sub_channel_mean(const void* du, int dudt, void* dz, int dzdt, int64_t rows, int C,
+                                     const float* colsum, void* stream) {
+  TGAN_CHECK_ARG(du && dz && colsum && rows > 0, "sub_channel_mean: bad args");
+  int64_t n = rows * C;
+  bool v = (C % 4 == 0) && aligned16(du) && aligned16(dz);
+  cudaStream_t st = (cudaStream_t)stream;
+  float inv = 1.0f / (float)rows;
+  DISPATCH_2(dudt, TA, dzdt, TB, {
+    if (v) sub_mean_kernel<TA, TB, 4><<<grid_for(n / 4), 256, 0, st>>>((const TA*)du, (TB*)dz, n / 4, C, colsum, inv);
+    else sub_mean_kernel<TA, TB, 1><<<grid_for(n), 256, 0, st>>>((const TA*)du, (TB*)dz, n, C, colsum, inv);
+  });
+  TGAN_LAUNCHED();
+  return 0;
+}
+
+extern "C" int tgan_bn_bwd(const void* dy, int dydt, const void* x, int xdt, void* dx, int dxdt, int64_t rows, int C,
+                           const float* mean, const float* rstd, const float* gamma, float* dgamma, float* dbeta,
+                           float beta_acc, float* ws, void* stream) {
+  TGAN_CHECK_ARG(dy && x && dx && mean && rstd && gamma && ws && rows > 0, "bn_bwd: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  // ws layout: [partials: 2*MAX_PARTS*C][s1: C][s2: C]
+  float* s1 = ws + (int64_t)2 * TGAN_STATS_MAX_PARTS * C;
+  float* s2 = s1 + C;
+  DISPATCH_2(dydt, TDY, xdt, TX, {
+    BnBwdStatsF<TDY, TX, 1> f1{(const TDY*)dy, (const TX*)x, mean, rstd, C};
+    BnBwdStatsF<TDY, TX, 4> f4{(const TDY*)dy, (const TX*)x, mean, rstd, C};
+    int rc = run_colreduce<2>(f1, f4, C % 4 == 0, rows, C, s1, s2, 0.f, ws, st);
+    if (rc) return rc;
+  });
+  int64_t n = rows * C;
+  TGAN_DISPATCH_1(dydt, TDY, TGAN_DISPATCH_1(xdt, TX, TGAN_DISPATCH_1(dxdt, TDX, {
+    bn_bwd_apply_kernel<TDY, TX, TDX><<<grid_for(n), 256, 0, st>>>((const TDY*)dy, (const TX*)x, (TDX*)dx, n, C, mean,
+                                                                   rstd, gamma, s1, s2, 1.0f / (float)rows);
+  })));
+  TGAN_LAUNCHED();
+  if (dbeta) { add_to_kernel<<<ceil_div(C, 128), 128, 0, st>>>(dbeta, s1, C, beta_acc); TGAN_LAUNCHED(); }
+  if (dgamma) { add_to_kernel<<<ceil_div(C, 128), 128, 0, st>>>(dgamma, s2, C, beta_acc); TGAN_LAUNCHED(); }
+  return 0;
+}
+
+extern "C" int tgan_add_noise(const void* x, int xdt, void* y, int ydt, int64_t n, float std, const float* noise,
+                              uint64_t seed, uint64_t stream_id, const uint64_t* counter, void* stream) {
+  TGAN_CHECK_ARG(x && y && n > 0, "add_noise: bad args");
+  int64_t q = (n + 3) / 4;
+  DISPATCH_2(xdt, TX, ydt, TY, (add_noise_kernel<TX, TY><<<ceil_div(q, 256), 256, 0, (cudaStream_t)stream>>>(
+                                   (const TX*)x, (TY*)y, n, std, noise, seed, stream_id, counter)));
+  TGAN_LAUNCHED();
+  return 0;
+}
+
+extern "C" int tgan_dropout(const void* x, int xdt, void* y, int ydt, uint8_t* mask, int64_t n, float rate, int gen,
+                            uint64_t seed, uint64_t stream_id, const uint64_t* counter, void* stream) {
+  TGAN_CHECK_ARG(x && y && mask && n > 0 && rate >= 0.f && rate < 1.f, "dropout: bad args");
+  int64_t q = (n + 3) / 4;
+  DISPATCH_2(xdt, TX, ydt, TY, (dropout_kernel<TX, TY><<<ceil_div(q, 256), 256, 0, (cudaStream_t)stream>>>(
+                                   (const TX*)x, (TY*)y, mask, n, rate, 1.0f / (1.0f - rate), gen, seed, stream_id,
+                                   counter)));
+  TGAN_LAUNCHED();
+  return 0;
+}
+
+extern "C" int tgan_maxpool2_fwd(const void* x, int dt, void* y, uint8_t* idx, int N, int H, int W, int C,
+                                 void* stream) {
+  TGAN_CHECK_ARG(x && y && idx && H % 2 == 0 && W % 2 == 0, "maxpool2_fwd: bad args (even extents only)");
+  int64_t total = (int64_t)N * (H / 2) * (W / 2) * C;
+  TGAN_DISPATCH_1(dt, T, (maxpool2_fwd_kernel<T><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                             (const T*)x, (T*)y, idx, N, H, W, C, total)));
+  TGAN_LAUNCHED();
+  return 0;
+}
+extern "C" int tgan_maxpool2_bwd(const void* dy, int dt, const uint8_t* idx, void* dx, int N, int H, int W, int C,
+                                 void* stream) {
+  TGAN_CHECK_ARG(dy && dx && idx && H % 2 == 0 && W % 2 == 0, "maxpool2_bwd: bad args");
+  int64_t total = (int64_t)N * (H / 2) * (W / 2) * C;
+  TGAN_DISPATCH_1(dt, T, (maxpool2_bwd_kernel<T><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                             (const T*)dy, idx, (T*)dx, N, H, W, C, total)));
+  TGAN_LAUNCHED();
+  return 0;
+}
+
+extern "C" int tgan_global_pool_fwd(const void* x, int xdt, void* y, int ydt, uint8_t* idx, int N, int HW, int C,
+                                    int mode, void* stream) {
+  TGAN_CHECK_ARG(x && y && HW > 0 && HW <= 256, "global_pool_fwd: bad args");
+  TGAN_CHECK_ARG(mode == 1 || idx, "global_pool_fwd: max mode needs idx");
+  DISPATCH_2(xdt, TX, ydt, TY, (global_pool_fwd_kernel<TX, TY><<<ceil_div((int64_t)N * C, 128), 128, 0,
+                                                                 (cudaStream_t)stream>>>((const TX*)x, (TY*)y, idx, N,
+                                                                                         HW, C, mode)));
+  TGAN_LAUNCHED();
+  return 0;
+}
+extern "C" int tgan_global_pool_bwd(const void* dy, int dydt, const uint8_t* idx, void* dx, int dxdt, int N, int HW,
+                                    int C, int mode, void* stream) {
+  TGAN_CHECK_ARG(dy && dx, "global_pool_bwd: bad args");
+  int64_t total = (int64_t)N * HW * C;
+  DISPATCH_2(dydt, TDY, dxdt, TDX, (global_pool_bwd_kernel<TDY, TDX><<<ceil_div(total, 256), 256, 0,
+                                                                     (cudaStream_t)stream>>>(
+                                       (const TDY*)dy, idx, (TDX*)dx, N, HW, C, mode, total)));
+  TGAN_LAUNCHED();
+  return 0;
+}
+
+extern "C" int tgan_concat_label(const void* x, int xdt, int64_t rows, int C, int ldx, const float* lab, int K,
+                                 int rows_per_sample, void* out, int odt, int ldo, void* stream) {
+  TGAN_CHECK_ARG(x && lab && out && ldo >= C + K && rows_per_sample > 0, "concat_label: bad args");
+  int64_t total = rows * ldo;
+  DISPATCH_2(xdt, TX, odt, TO, (concat_label_kernel<TX, TO><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                                   (const TX*)x, rows, C, ldx, lab, K, rows_per_sample, (TO*)out, ldo, total)));
+  TGAN_LAUNCHED();
+  return 0;
+}
+extern "C" int tgan_copy_channels(const void* src, int sdt, int lds, void* dst, int ddt, int ldd, int64_t rows, int C,
+                                  void* stream) {
+  TGAN_CHECK_ARG(src && dst && lds >= C && ldd >= C, "copy_channels: bad args");
+  int64_t total = rows * C;
+  DISPATCH_2(sdt, TS, ddt, TD, (copy_channels_kernel<TS, TD><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                                   (const TS*)src, lds, (TD*)dst, ldd, C, total)));
+  TGAN_LAUNCHED();
+  return 0;
+}
+extern "C" int tgan_accumulate(void* y, const void* x, int dt, int64_t n, void* stream) {
+  TGAN_CHECK_ARG(y && x && n > 0, "accumulate: bad args");
+  TGAN_DISPATCH_1(dt, T, (accumulate_kernel<T><<<grid_for(n), 256, 0, (cudaStream_t)stream>>>((T*)y, (const T*)x, n)));
+  TGAN_LAUNCHED();
+  return 0;
+}
+extern "C" int tgan_fill_f32(float* p, float v, int64_t n, void* stream) {
+  TGAN_CHECK_ARG(p && n > 0, "fill: bad args");
+  fill_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(p, v, n);
+  TGAN_LAUNCHED();
+  return 0;
+}
+extern "C" int tgan_argmax_onehot(const float* logits, int N, int K, int64_t* idx, float* onehot, void* stream) {
+  TGAN_CHECK_ARG(logits && N > 0 && K > 0, "argmax_onehot: bad args");
+  argmax_onehot_kernel<<<ceil_div(N, 128), 128, 0, (cudaStream_t)stream>>>(logits, N, K, idx, onehot);
+  TGAN_LAUNCHED();
+  return 0;
+}

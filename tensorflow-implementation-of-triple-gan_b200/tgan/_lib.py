@@ -1,0 +1,90 @@
+"""ctypes binding of libtgan.so (the sm_100a CUDA library behind the C ABI in include/tgan.h).
+
+The prototypes are parsed from include/tgan.h so that the header is the single source of truth.
+There is NO fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+import re
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_HEADER = os.path.normpath(os.path.join(_PKG, '..', '..', 'include', 'tgan.h'))
+_SO = os.path.join(_PKG, 'libtgan.so')
+
+_CT = {'int': ctypes.c_int, 'float': ctypes.c_float, 'int64_t': ctypes.c_int64, 'uint64_t': ctypes.c_uint64,
+       'void': None}
+
+
+def parse_header(path=_HEADER):
+    """-> {name: (restype, [argtypes])} for every `tgan_*` prototype declared in the header."""
+    src = open(path).read()
+    src = re.sub(r'/\*.*?\*/', ' ', src, flags=re.S)
+    src = re.sub(r'^\s*#.*$', ' ', src, flags=re.M)
+    src = re.sub(r'typedef\s+struct\s*\{.*?\}\s*\w+\s*;', ' ', src, flags=re.S)
+    protos = {}
+    for m in re.finditer(r'([\w][\w\s\*]*?)\b(tgan_\w+)\s*\(([^)]*)\)\s*;', src):
+        ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()
+        if '*' in ret:
+            restype = ctypes.c_char_p if 'char' in ret else ctypes.c_void_p
+        else:
+            restype = _CT[ret.replace('const', '').strip()]
+        argtypes = []
+        if args and args != 'void':
+            for a in args.split(','):
+                a = a.strip()
+                if '*' in a:
+                    argtypes.append(ctypes.c_void_p)
+                else:
+                    t = a.replace('const', '').split()[0]
+                    argtypes.append(_CT[t])
+        protos[name] = (restype, argtypes)
+    return protos
+
+
+class TganIgemmArgs(ctypes.Structure):
+    _fields_ = [('x', ctypes.c_void_p), ('N', ctypes.c_int), ('H', ctypes.c_int), ('W', ctypes.c_int),
+                ('C', ctypes.c_int), ('ldx', ctypes.c_int), ('wp', ctypes.c_void_p), ('T', ctypes.c_int),
+                ('Nout', ctypes.c_int), ('Kpad', ctypes.c_int), ('dy', ctypes.c_int * 25), ('dx', ctypes.c_int * 25),
+                ('gh', ctypes.c_int), ('gw', ctypes.c_int), ('out', ctypes.c_void_p), ('odt', ctypes.c_int),
+                ('OH', ctypes.c_int), ('OW', ctypes.c_int), ('ldo', ctypes.c_int), ('osy', ctypes.c_int),
+                ('osx', ctypes.c_int), ('ooy', ctypes.c_int), ('oox', ctypes.c_int), ('vh', ctypes.c_int),
+                ('vw', ctypes.c_int), ('bias', ctypes.c_void_p), ('colsum', ctypes.c_void_p), ('act', ctypes.c_int),
+                ('alpha', ctypes.c_float)]
+
+
+class TganWgradArgs(ctypes.Structure):
+    _fields_ = [('dz', ctypes.c_void_p), ('N', ctypes.c_int), ('gh', ctypes.c_int), ('gw', ctypes.c_int),
+                ('Cout', ctypes.c_int), ('lddz', ctypes.c_int), ('x', ctypes.c_void_p), ('H', ctypes.c_int),
+                ('W', ctypes.c_int), ('Cin', ctypes.c_int), ('ldx', ctypes.c_int), ('T', ctypes.c_int),
+                ('dy', ctypes.c_int * 25), ('dx', ctypes.c_int * 25), ('dw', ctypes.c_void_p),
+                ('beta', ctypes.c_float), ('ws', ctypes.c_void_p), ('ws_bytes', ctypes.c_int64)]
+
+
+_lib = None
+
+
+def load():
+    """Load libtgan.so or fail loudly (no CPU / eager fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        raise RuntimeError('libtgan.so not found at %s -- build it with `python -c "import __graft_entry__ as g; '
+                           'g.build()"` (or `make -C tensorflow-implementation-of-triple-gan_b200/csrc`). '
+                           'There is no fallback path.' % _SO)
+    lib = ctypes.CDLL(_SO)
+    for name, (restype, argtypes) in parse_header().items():
+        fn = getattr(lib, name)      # AttributeError here == header/library mismatch: fail loudly
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError('libtgan: ' + load().tgan_last_error().decode())
+
+
+def call(name, *args):
+    check(getattr(load(), name)(*args))

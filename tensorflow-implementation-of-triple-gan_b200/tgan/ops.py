@@ -1,0 +1,688 @@
+"""Differentiable ops of the Triple-GAN path on `Var`s, each a thin orchestration of C-ABI calls
+(include/tgan.h).  Forward launches the sm_100a kernels and pushes a backward closure on the tape.
+No torch compute op is used on the data path (torch only allocates memory / provides the stream).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .core import BF16, F32, Var, add_grad, ctx, dt_code
+
+ACT = {'none': 0, 'relu': 1, 'lrelu': 2, 'tanh': 3, 'sigmoid': 4, 'softplus': 5}
+STATS_PARTS = 256
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _new(shape, dtype=None):
+    return torch.empty(tuple(int(s) for s in shape), dtype=dtype or ctx.act_dtype, device=ctx.device)
+
+
+def _zeros(shape, dtype=torch.float32):
+    t = _new(shape, dtype)
+    if dtype == torch.float32:
+        _lib.call('tgan_fill_f32', _p(t), 0.0, t.numel(), _st())
+    else:
+        t.zero_()
+    return t
+
+
+def _on():
+    return ctx.tape is not None
+
+
+def _out_dtype(C):
+    """Skinny outputs (logits, RGB images) stay fp32 even in bf16 mode: they feed the loss kernels /
+    leave the network."""
+    return torch.float32 if C < 16 else ctx.act_dtype
+
+
+def same_pad(n, k, s):
+    out = -(-n // s)
+    tot = max((out - 1) * s + k - n, 0)
+    return out, tot // 2
+
+
+def accumulate_(y, x):
+    assert y.dtype == x.dtype and y.numel() == x.numel()
+    _lib.call('tgan_accumulate', _p(y), _p(x), dt_code(y), y.numel(), _st())
+
+
+def _to_f32(t, rows, C, ld):
+    """[rows, ld] (any dtype, logical C) -> contiguous fp32 [rows, C]"""
+    if t.dtype == torch.float32 and ld == C:
+        return t
+    o = _new((rows, C), torch.float32)
+    _lib.call('tgan_copy_channels', _p(t), dt_code(t), ld, _p(o), F32, C, rows, C, _st())
+    return o
+
+
+def _cast(t, dtype):
+    if t.dtype == dtype:
+        return t
+    o = _new(t.shape, dtype)
+    n = t.numel()
+    _lib.call('tgan_copy_channels', _p(t), dt_code(t), n, _p(o), dt_code(o), n, 1, n, _st())
+    return o
+
+
+# ----------------------------------------------------------------------------------------------
+# weights: plain variables and weight-normalised (V, g) pairs
+# ----------------------------------------------------------------------------------------------
+
+
+class PlainWeight:
+    """A tf.layers kernel used as is (modle_base.py:40,161,250)."""
+
+    def __init__(self, param):
+        self.param = param
+        self.scale = None
+
+    @property
+    def requires_grad(self):
+        return self.param.requires_grad
+
+    @property
+    def key(self):
+        return self.param
+
+    def value(self):
+        return self.param.data
+
+    def grad_target(self):
+        return self.param.grad
+
+
+class WNWeight:
+    """W = g * V/||V|| per output channel (nn.py:502,554; modle_base.py:66,101,148).  V is viewed as
+    [A, Co, B].  The effective weight is computed once per optimiser version and shared by every call
+    in a phase; dW accumulates over the calls and ONE weight-norm backward runs per phase."""
+
+    def __init__(self, V, g, A, Co, B, eps_mode):
+        self.V, self.g, self.A, self.Co, self.B, self.eps_mode = V, g, A, Co, B, eps_mode
+
+    @property
+    def requires_grad(self):
+        return self.V.requires_grad or self.g.requires_grad
+
+    @property
+    def key(self):
+        return self.V
+
+    def _c(self):
+        c = self.V.cache
+        if c.get('version') != ctx.store.version:
+            c.clear()
+            c['version'] = ctx.store.version
+            c['W'] = _new(self.V.shape, torch.float32)
+            c['inv'] = _new((self.Co,), torch.float32)
+            c['scale'] = _new((self.Co,), torch.float32)
+            _lib.call('tgan_weightnorm_fwd', _p(self.V.data), _p(self.g.data), _p(c['W']), _p(c['inv']),
+                      _p(c['scale']), self.A, self.Co, self.B, self.eps_mode, _p(ctx.ws()), _st())
+        return c
+
+    def value(self):
+        return self._c()['W']
+
+    def grad_target(self):
+        c, tape = self._c(), ctx.tape
+        if c.get('tape') is not tape:
+            c['tape'] = tape
+            c['dW'] = _zeros(self.V.shape)
+            V, g, me = self.V, self.g, self
+
+            def post():
+                _lib.call('tgan_weightnorm_bwd', _p(V.data), _p(g.data), _p(c['inv']), _p(c['dW']), _p(V.grad),
+                          _p(g.grad), me.A, me.Co, me.B, 1.0, _p(ctx.ws()), _st())
+                c['tape'] = None
+            tape.post.append(post)
+        return c['dW']
+
+
+# ----------------------------------------------------------------------------------------------
+# dense contractions.  fp32 mode / skinny layers: im2col + SIMT GEMM.  bf16 mode: tcgen05 (tc.py).
+# ----------------------------------------------------------------------------------------------
+
+
+def _sgemm(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, beta=0.0, alpha=1.0):
+    tiles = -(-M // 64) * -(-N // 64)
+    splits = 1
+    if tiles < 148 and K >= 2048:
+        splits = max(1, min(64, (2 * 148) // tiles, K // 512))
+    ws = ctx.ws()
+    if splits > 1 and splits * M * N > ws.numel():
+        splits = max(1, ws.numel() // (M * N))
+    _lib.call('tgan_sgemm', ta, tb, M, N, K, alpha, _p(A), lda, _p(B), ldb, beta, _p(C), ldc, splits, _p(ws), _st())
+
+
+def _im2col(x, N, H, W, C, ld, kh, kw, s, pt, pl, Ho, Wo):
+    col = _new((N * Ho * Wo, kh * kw * C), torch.float32)
+    _lib.call('tgan_im2col', _p(x), dt_code(x), N, H, W, C, ld, kh, kw, s, s, pt, pl, Ho, Wo, _p(col), _st())
+    return col
+
+
+def conv2d(x, w, kh, kw, stride=1, padding='SAME'):
+    """tf.nn.conv2d (NHWC x HWIO).  x may be 2-D [rows, C] with kh = kw = 1 (tf.matmul)."""
+    Cout = w.key.shape[-1]
+    C = x.C
+    if len(x.shape) == 2:
+        N, H, W = x.shape[0], 1, 1
+        assert kh == 1 and kw == 1
+    else:
+        N, H, W = x.shape[0], x.shape[1], x.shape[2]
+    if padding.upper() == 'SAME':
+        Ho, pt = same_pad(H, kh, stride)
+        Wo, pl = same_pad(W, kw, stride)
+    else:
+        Ho, pt, Wo, pl = (H - kh) // stride + 1, 0, (W - kw) // stride + 1, 0
+    oshape = (N, Cout) if len(x.shape) == 2 else (N, Ho, Wo, Cout)
+    rg = _on() and (x.requires_grad or w.requires_grad)
+    if ctx.building:
+        return Var(None, oshape, requires_grad=rg)
+    from . import tc
+    geom = dict(N=N, H=H, W=W, C=C, kh=kh, kw=kw, s=stride, pt=pt, pl=pl, Ho=Ho, Wo=Wo, Cout=Cout)
+    use_tc = ctx.math == 'bf16' and tc.conv_eligible(geom, x)
+    rows = N * Ho * Wo
+    K = kh * kw * C
+    direct = (kh == 1 and kw == 1 and stride == 1 and pt == 0 and pl == 0)
+    if use_tc:
+        z = tc.conv_fwd(x, w, geom)
+    else:
+        xd = x.data
+        Wt = w.value()
+        if direct:
+            a = _to_f32(xd, rows, C, x.ld)
+            lda = C
+        else:
+            a = _im2col(xd, N, H, W, C, x.ld, kh, kw, stride, pt, pl, Ho, Wo)
+            lda = K
+        z = _new((rows, Cout), torch.float32)
+        _sgemm(0, 0, rows, Cout, K, a, lda, Wt, Cout, z, Cout)
+        del a
+    out = Var(z.view(oshape), oshape, requires_grad=rg)
+    if rg:
+        tape = ctx.tape
+
+        def bwd():
+            if out.grad is None:
+                return
+            dz = out.grad
+            if use_tc:
+                tc.conv_bwd(x, w, geom, dz)
+                return
+            dzf = _to_f32(dz, rows, Cout, Cout)
+            Wt = w.value()
+            if w.requires_grad:
+                if direct:
+                    a, lda = _to_f32(x.data, rows, C, x.ld), C
+                else:
+                    a, lda = _im2col(x.data, N, H, W, C, x.ld, kh, kw, stride, pt, pl, Ho, Wo), K
+                _sgemm(1, 0, K, Cout, rows, a, lda, dzf, Cout, w.grad_target(), Cout, beta=1.0)
+                del a
+            if x.requires_grad:
+                dcol = _new((rows, K), torch.float32)
+                _sgemm(0, 1, rows, K, Cout, dzf, Cout, Wt, Cout, dcol, K)
+                if direct:
+                    dx = dcol if x.data.dtype == torch.float32 else _cast(dcol, x.data.dtype)
+                    dx = dx.view(x.shape)
+                else:
+                    dx = _new(x.shape, x.data.dtype)
+                    _lib.call('tgan_col2im', _p(dcol), N, H, W, C, kh, kw, stride, stride, pt, pl, Ho, Wo, _p(dx),
+                              dt_code(dx), C, C, _st())
+                add_grad(x, dx)
+        tape.nodes.append(bwd)
+    return out
+
+
+def conv2d_transpose(x, w, kh, kw, stride=2):
+    """tf.nn.conv2d_transpose 'SAME' (modle_base.py:149,250); filter [kh,kw,Cout,Cin]."""
+    Cout, Cin = w.key.shape[2], w.key.shape[3]
+    N, h, wd = x.shape[0], x.shape[1], x.shape[2]
+    assert x.C == Cin
+    Ho, Wo = h * stride, wd * stride
+    _, pt = same_pad(Ho, kh, stride)
+    _, pl = same_pad(Wo, kw, stride)
+    oshape = (N, Ho, Wo, Cout)
+    rg = _on() and (x.requires_grad or w.requires_grad)
+    if ctx.building:
+        return Var(None, oshape, requires_grad=rg)
+    from . import tc
+    geom = dict(N=N, h=h, w=wd, Cin=Cin, Cout=Cout, kh=kh, kw=kw, s=stride, pt=pt, pl=pl, Ho=Ho, Wo=Wo)
+    use_tc = ctx.math == 'bf16' and tc.deconv_eligible(geom, x)
+    rows, KK = N * h * wd, kh * kw * Cout
+    if use_tc:
+        y = tc.deconv_fwd(x, w, geom)
+    else:
+        xf = _to_f32(x.data, rows, Cin, x.ld)
+        dcol = _new((rows, KK), torch.float32)
+        _sgemm(0, 1, rows, KK, Cin, xf, Cin, w.value(), Cin, dcol, KK)
+        y = _new(oshape, _out_dtype(Cout) if ctx.math == 'bf16' else torch.float32)
+        _lib.call('tgan_col2im', _p(dcol), N, Ho, Wo, Cout, kh, kw, stride, stride, pt, pl, h, wd, _p(y), dt_code(y),
+                  Cout, Cout, _st())
+        del dcol
+    out = Var(y, oshape, requires_grad=rg)
+    if rg:
+        def bwd():
+            if out.grad is None:
+                return
+            dy = out.grad
+            if use_tc:
+                tc.deconv_bwd(x, w, geom, dy)
+                return
+            col = _im2col(dy, N, Ho, Wo, Cout, Cout, kh, kw, stride, pt, pl, h, wd)      # [rows, KK]
+            if w.requires_grad:
+                xf = _to_f32(x.data, rows, Cin, x.ld)
+                _sgemm(1, 0, KK, Cin, rows, col, KK, xf, Cin, w.grad_target(), Cin, beta=1.0)
+            if x.requires_grad:
+                dxf = _new((rows, Cin), torch.float32)
+                _sgemm(0, 0, rows, Cin, KK, col, KK, w.value(), Cin, dxf, Cin)
+                add_grad(x, _cast(dxf, x.data.dtype).view(x.shape))
+        ctx.tape.nodes.append(bwd)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# epilogues: bias / mean-only BN / BN, fused with the nonlinearity
+# ----------------------------------------------------------------------------------------------
+
+
+def _affine_act(x, rows, C, scale, shift, act, alpha, out_dtype):
+    y = _new(x.shape, out_dtype)
+    _lib.call('tgan_affine_act', _p(x), dt_code(x), _p(y), dt_code(y), rows, C, _p(scale), _p(shift), act, alpha,
+              _st())
+    return y
+
+
+def _colsum_into(param_grad, colsum):
+    accumulate_(param_grad.view(-1), colsum.view(-1))
+
+
+def bias_act(z, b, act='none', alpha=0.2):
+    """y = act(z + b)  (tf.nn.bias_add + nonlinearity: nn.py:508,517; tf.layers bias)."""
+    a = ACT[act]
+    C, rows = z.C, z.rows
+    rg = _on() and (z.requires_grad or (b is not None and b.requires_grad))
+    if ctx.building:
+        return Var(None, z.shape, requires_grad=rg)
+    y = _affine_act(z.data, rows, C, None, None if b is None else b.data, a, alpha, _out_dtype(C))
+    out = Var(y, z.shape, requires_grad=rg)
+    if rg:
+        def bwd():
+            if out.grad is None:
+                return
+            dy = out.grad
+            need_db = b is not None and b.requires_grad
+            if a == 0:
+                du = dy
+                if need_db:
+                    cs = _new((C,), torch.float32)
+                    _lib.call('tgan_channel_stats', _p(dy), dt_code(dy), rows, C, _p(cs), None, _p(ctx.ws()), _st())
+                    _colsum_into(b.grad, cs)
+            else:
+                du = _new(z.shape, z.data.dtype)
+                cs = _new((C,), torch.float32)
+                _lib.call('tgan_act_bwd', _p(dy), dt_code(dy), _p(out.data), dt_code(out.data), _p(du), dt_code(du),
+                          rows, C, a, alpha, _p(cs), _p(ctx.ws()), _st())
+                if need_db:
+                    _colsum_into(b.grad, cs)
+            if z.requires_grad:
+                add_grad(z, du if du.dtype == z.data.dtype else _cast(du, z.data.dtype))
+        ctx.tape.nodes.append(bwd)
+    return out
+
+
+def lazy_bias(z, b):
+    """Defers `z + b` so that a following activation fuses into ONE epilogue kernel
+    (tf.layers.dense / conv2d return value followed by tf.nn.relu / leakyReLu in the builders)."""
+    v = Var(None, z.shape, requires_grad=_on() and (z.requires_grad or b.requires_grad))
+    v._lazy = (z, b)
+    return v
+
+
+def _materialize(v):
+    z, b = v._lazy
+    y = bias_act(z, b, 'none')
+    v._lazy = None
+    if ctx.building:
+        return
+    v._data = y.data
+    if y.requires_grad:
+        def bwd():
+            if v.grad is not None:
+                add_grad(y, v.grad)
+        ctx.tape.nodes.append(bwd)
+
+
+def activation(x, act, alpha=0.2):
+    """tf.nn.relu / leaky_relu / tanh / sigmoid / softplus; fuses a pending bias."""
+    if x._data is None and x._lazy is not None:
+        z, b = x._lazy
+        return bias_act(z, b, act, alpha)
+    return bias_act(x, None, act, alpha)
+
+
+def mobn_act(z, b, pop_mean, train, act='none', alpha=0.2, decay=0.9):
+    """mean_only_batch_norm_impl + nonlinearity (nn.py:147-187, :517).
+    train: y = act(z - mean_{rows}(z) + b), pop_mean <- decay*pop_mean + (1-decay)*mean
+    eval : y = act(z - pop_mean + b)."""
+    a = ACT[act]
+    C, rows = z.C, z.rows
+    rg = _on() and (z.requires_grad or b.requires_grad)
+    if ctx.building:
+        return Var(None, z.shape, requires_grad=rg)
+    shift = _new((C,), torch.float32)
+    if train:
+        s = _new((C,), torch.float32)
+        _lib.call('tgan_channel_stats', _p(z.data), dt_code(z.data), rows, C, _p(s), None, _p(ctx.ws()), _st())
+        _lib.call('tgan_mobn_finalize', _p(s), rows, C, _p(b.data), _p(pop_mean.data), decay, _p(shift), _st())
+    else:
+        _lib.call('tgan_mobn_eval_shift', _p(b.data), _p(pop_mean.data), C, _p(shift), _st())
+    y = _affine_act(z.data, rows, C, None, shift, a, alpha, _out_dtype(C))
+    out = Var(y, z.shape, requires_grad=rg)
+    if rg:
+        def bwd():
+            if out.grad is None:
+                return
+            dy = out.grad
+            du = _new(z.shape, z.data.dtype)
+            cs = _new((C,), torch.float32)
+            _lib.call('tgan_act_bwd', _p(dy), dt_code(dy), _p(out.data), dt_code(out.data), _p(du), dt_code(du), rows,
+                      C, a, alpha, _p(cs), _p(ctx.ws()), _st())
+            if b.requires_grad:
+                _colsum_into(b.grad, cs)
+            if z.requires_grad:
+                if train:
+                    _lib.call('tgan_sub_channel_mean', _p(du), dt_code(du), _p(du), dt_code(du), rows, C, _p(cs), _st())
+                add_grad(z, du)
+        ctx.tape.nodes.append(bwd)
+    return out
+
+
+def batch_norm(x, gamma, beta, mm, mv, train, eps=1e-5, decay=0.9):
+    """tf.contrib.layers.batch_norm(scale=True, updates_collections=None) (modle_base.py:229-237)."""
+    C, rows = x.C, x.rows
+    rg = _on() and (x.requires_grad or gamma.requires_grad or beta.requires_grad)
+    if ctx.building:
+        return Var(None, x.shape, requires_grad=rg)
+    xd = x.data
+    scale, shift = _new((C,), torch.float32), _new((C,), torch.float32)
+    mean, rstd = _new((C,), torch.float32), _new((C,), torch.float32)
+    if train:
+        s, ss = _new((C,), torch.float32), _new((C,), torch.float32)
+        _lib.call('tgan_channel_stats', _p(xd), dt_code(xd), rows, C, _p(s), _p(ss), _p(ctx.ws()), _st())
+        _lib.call('tgan_bn_finalize', _p(s), _p(ss), rows, C, _p(gamma.data), _p(beta.data), eps, decay,
+                  None if mm is None else _p(mm.data), None if mv is None else _p(mv.data), _p(mean), _p(rstd), _p(scale), _p(shift), _st())
+    else:
+        _lib.call('tgan_bn_eval_affine', _p(gamma.data), _p(beta.data), _p(mm.data), _p(mv.data), eps, C, _p(scale),
+                  _p(shift), _st())
+    y = _affine_act(xd, rows, C, scale, shift, 0, 0.0, _out_dtype(C))
+    out = Var(y, x.shape, requires_grad=rg)
+    if rg:
+        def bwd():
+            if out.grad is None:
+                return
+            dy = out.grad
+            if not train:
+                if x.requires_grad:
+                    add_grad(x, _affine_act(dy, rows, C, scale, None, 0, 0.0, xd.dtype))
+                return
+            dx = _new(x.shape, xd.dtype)
+            _lib.call('tgan_bn_bwd', _p(dy), dt_code(dy), _p(xd), dt_code(xd), _p(dx), dt_code(dx), rows, C, _p(mean),
+                      _p(rstd), _p(gamma.data), _p(gamma.grad) if gamma.requires_grad else None,
+                      _p(beta.grad) if beta.requires_grad else None, 1.0, _p(ctx.ws()), _st())
+            if x.requires_grad:
+                add_grad(x, dx)
+        ctx.tape.nodes.append(bwd)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# pointwise layers
+# ----------------------------------------------------------------------------------------------
+
+
+def add_noise(x, std, tag):
+    """x + N(0, std) (modle_base.py:193-202; Good_GAN_cifar10.py:29-31).  Active in eval too."""
+    rg = _on() and x.requires_grad
+    if ctx.building:
+        return Var(None, x.shape, requires_grad=rg)
+    xd = x.data
+    n = xd.numel()
+    y = _new(x.shape)
+    rng = ctx.rng
+    if rng.injected:
+        noise = rng.normal(tag, x.shape)
+        _lib.call('tgan_add_noise', _p(xd), dt_code(xd), _p(y), dt_code(y), n, std, _p(noise), 0, 0, None, _st())
+    else:
+        _lib.call('tgan_add_noise', _p(xd), dt_code(xd), _p(y), dt_code(y), n, std, None, rng.seed,
+                  rng.stream_id(tag), _p(rng.counter()), _st())
+    out = Var(y, x.shape, requires_grad=rg)
+    if rg:
+        def bwd():
+            if out.grad is not None:
+                add_grad(x, out.grad if out.grad.dtype == xd.dtype else _cast(out.grad, xd.dtype))
+        ctx.tape.nodes.append(bwd)
+    return out
+
+
+def dropout(x, rate, tag, training=True):
+    """tf.layers.dropout (modle_base.py:190-191; Good_GAN_cifar10.py:124,143)."""
+    if not training:
+        return x
+    rg = _on() and x.requires_grad
+    if ctx.building:
+        return Var(None, x.shape, requires_grad=rg)
+    xd = x.data
+    n = xd.numel()
+    y = _new(x.shape)
+    rng = ctx.rng
+    if rng.injected:
+        mask = rng.keep_mask(tag, x.shape, rate)
+        _lib.call('tgan_dropout', _p(xd), dt_code(xd), _p(y), dt_code(y), _p(mask), n, rate, 0, 0, 0, None, _st())
+    else:
+        mask = _new(x.shape, torch.uint8)
+        _lib.call('tgan_dropout', _p(xd), dt_code(xd), _p(y), dt_code(y), _p(mask), n, rate, 1, rng.seed,
+                  rng.stream_id(tag), _p(rng.counter()), _st())
+    out = Var(y, x.shape, requires_grad=rg)
+    if rg:
+        def bwd():
+            if out.grad is None:
+                return
+            dx = _new(x.shape, xd.dtype)
+            _lib.call('tgan_dropout', _p(out.grad), dt_code(out.grad), _p(dx), dt_code(dx), _p(mask), n, rate, 0, 0, 0,
+                      None, _st())
+            add_grad(x, dx)
+        ctx.tape.nodes.append(bwd)
+    return out
+
+
+def max_pool2(x):
+    """2x2/s2 max pool (Good_GAN_cifar10.py:123,142; Good_GAN.py:223,233,264,279)."""
+    N, H, W, C = x.shape
+    oshape = (N, H // 2, W // 2, C)
+    rg = _on() and x.requires_grad
+    if ctx.building:
+        return Var(None, oshape, requires_grad=rg)
+    xd = x.data
+    y, idx = _new(oshape, xd.dtype), _new(oshape, torch.uint8)
+    _lib.call('tgan_maxpool2_fwd', _p(xd), dt_code(xd), _p(y), _p(idx), N, H, W, C, _st())
+    out = Var(y, oshape, requires_grad=rg)
+    if rg:
+        def bwd():
+            if out.grad is None:
+                return
+            dx = _new(x.shape, xd.dtype)
+            _lib.call('tgan_maxpool2_bwd', _p(out.grad), dt_code(out.grad), _p(idx), _p(dx), N, H, W, C, _st())
+            add_grad(x, dx)
+        ctx.tape.nodes.append(bwd)
+    return out
+
+
+def global_pool(x, mode):
+    """mode 'max': tf.layers.max_pooling2d(pool=H) ('avg_pool_0', Good_GAN_cifar10.py:163);
+    mode 'mean': average_pooling2d(8,1) (:94) / reduce_mean([1,2]) (Good_GAN.py:157,243,295)."""
+    N, H, W, C = x.shape
+    m = 0 if mode == 'max' else 1
+    rg = _on() and x.requires_grad
+    if ctx.building:
+        return Var(None, (N, C), requires_grad=rg)
+    xd = x.data
+    y = _new((N, C), xd.dtype)
+    idx = _new((N, C), torch.uint8) if m == 0 else None
+    _lib.call('tgan_global_pool_fwd', _p(xd), dt_code(xd), _p(y), dt_code(y), _p(idx), N, H * W, C, m, _st())
+    out = Var(y, (N, C), requires_grad=rg)
+    if rg:
+        def bwd():
+            if out.grad is None:
+                return
+            dx = _new(x.shape, xd.dtype)
+            _lib.call('tgan_global_pool_bwd', _p(out.grad), dt_code(out.grad), _p(idx), _p(dx), dt_code(dx), N, H * W,
+                      C, m, _st())
+            add_grad(x, dx)
+        ctx.tape.nodes.append(bwd)
+    return out
+
+
+def concat_label(x, y):
+    """_conv_cond_concat (modle_base.py:239-244) and tf.concat([h, y], 1): appends the K label
+    channels.  The result is padded to a multiple of 8 channels (16-byte pixel stride for TMA); the
+    pad is zero and invisible to consumers (they use the logical C)."""
+    K = y.shape[-1]
+    C = x.C
+    ld = (C + K + 7) // 8 * 8 if ctx.math == 'bf16' else C + K
+    oshape = tuple(x.shape[:-1]) + (C + K,)
+    rows = x.rows
+    rps = rows // x.shape[0]
+    rg = _on() and x.requires_grad
+    if ctx.building:
+        return Var(None, oshape, ld=ld, requires_grad=rg)
+    xd = x.data
+    lab = y.data if isinstance(y, Var) else y
+    assert lab.dtype == torch.float32
+    o = _new(tuple(x.shape[:-1]) + (ld,))
+    _lib.call('tgan_concat_label', _p(xd), dt_code(xd), rows, C, x.ld, _p(lab), K, rps, _p(o), dt_code(o), ld, _st())
+    out = Var(o, oshape, ld=ld, requires_grad=rg)
+    if rg:
+        def bwd():
+            if out.grad is None:
+                return
+            g = out.grad          # [rows, C+K] contiguous (producers write logical channels densely)
+            dx = _new(x.shape, xd.dtype)
+            _lib.call('tgan_copy_channels', _p(g), dt_code(g), C + K, _p(dx), dt_code(dx), C, rows, C, _st())
+            add_grad(x, dx)
+        ctx.tape.nodes.append(bwd)
+    return out
+
+
+def reshape(x, shape):
+    shape = list(shape)
+    if -1 in shape:
+        known = int(np.prod([s for s in shape if s != -1]))
+        shape[shape.index(-1)] = int(np.prod(x.shape)) // known
+    shape = tuple(int(s) for s in shape)
+    assert x.ld == x.C, 'reshape of a channel-padded tensor'
+    rg = _on() and x.requires_grad
+    if ctx.building:
+        return Var(None, shape, requires_grad=rg)
+    out = Var(x.data.view(shape), shape, requires_grad=rg)
+    if rg:
+        def bwd():
+            if out.grad is not None:
+                add_grad(x, out.grad.view(x.shape))
+        ctx.tape.nodes.append(bwd)
+    return out
+
+
+def constant(t, dtype=torch.float32):
+    """Host/device tensor or ndarray -> Var (no gradient)."""
+    if ctx.building:
+        return Var(None, tuple(np.shape(t)))
+    if isinstance(t, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(t))
+    return Var(t.to(ctx.device, dtype).contiguous(), tuple(t.shape))
+
+
+# ----------------------------------------------------------------------------------------------
+# pseudo-labels and losses
+# ----------------------------------------------------------------------------------------------
+
+
+def argmax_onehot(logits, depth):
+    """tf.argmax(axis=1) + tf.one_hot(depth) (Good_GAN_cifar10.py:232,259): (int64 idx, fp32 one-hot)."""
+    N, K = logits.shape
+    if ctx.building:
+        return Var(None, (N,)), Var(None, (N, depth))
+    assert K == depth and logits.data.dtype == torch.float32
+    idx, oh = _new((N,), torch.int64), _new((N, depth), torch.float32)
+    _lib.call('tgan_argmax_onehot', _p(logits.data), N, K, _p(idx), _p(oh), _st())
+    return Var(idx, (N,)), Var(oh, (N, depth))
+
+
+class Loss:
+    """A scalar loss left on the device + the closed-form dlogits computed by the same kernel."""
+
+    def __init__(self, value, pairs):
+        self.value = value          # fp32 [1] device tensor
+        self._pairs = pairs         # [(logits Var, dlogits tensor)]
+
+    def seed(self):
+        for v, g in self._pairs:
+            if v is not None and v.requires_grad:
+                add_grad(v, g)
+
+    def item(self):
+        return float(self.value.item())
+
+
+def _f32logits(v):
+    assert v.data.dtype == torch.float32 and v.ld == v.C, 'loss kernels take fp32 logits'
+    return v.data
+
+
+def loss_d(dr, df, du):
+    """train_base.py:123-126."""
+    if ctx.building:
+        return Loss(None, [])
+    val = _new((1,), torch.float32)
+    g = [_new(v.shape, torch.float32) for v in (dr, df, du)]
+    _lib.call('tgan_loss_d', _p(_f32logits(dr)), dr.rows, _p(_f32logits(df)), df.rows, _p(_f32logits(du)), du.rows,
+              _p(val), _p(g[0]), _p(g[1]), _p(g[2]), _st())
+    return Loss(val, list(zip((dr, df, du), g)))
+
+
+def loss_g(df):
+    """train_base.py:128."""
+    if ctx.building:
+        return Loss(None, [])
+    val, g = _new((1,), torch.float32), _new(df.shape, torch.float32)
+    _lib.call('tgan_loss_g', _p(_f32logits(df)), df.rows, _p(val), _p(g), _st())
+    return Loss(val, [(df, g)])
+
+
+def loss_c(c_real, y_l_c, c_unl, c_rep, d_unl_logits, c_fake, y_g, lambdas):
+    """train_base.py:130-152.  lambdas: device fp32 [2] = {lambda_1, lambda_2}."""
+    if ctx.building:
+        return Loss(None, [])
+    K = c_real.shape[1]
+    val = _new((1,), torch.float32)
+    g_real, g_unl, g_fake = (_new(v.shape, torch.float32) for v in (c_real, c_unl, c_fake))
+    g_rep = _new(c_rep.shape, torch.float32) if c_rep is not None else None
+    _lib.call('tgan_loss_c', _p(_f32logits(c_real)), _p(y_l_c.data), c_real.rows, _p(_f32logits(c_unl)),
+              None if c_rep is None else _p(_f32logits(c_rep)), _p(_f32logits(d_unl_logits)), c_unl.rows,
+              _p(_f32logits(c_fake)), _p(y_g.data), c_fake.rows, K, _p(lambdas), _p(val), _p(g_real), _p(g_unl),
+              _p(g_rep), _p(g_fake), _st())
+    return Loss(val, [(c_real, g_real), (c_unl, g_unl), (c_rep, g_rep), (c_fake, g_fake)])
+
+
+def backward(loss):
+    """tf.gradients(loss, var_list) for the ops recorded on the current tape."""
+    loss.seed()
+    ctx.tape.backward()

@@ -1,0 +1,247 @@
+"""Train: the Triple-GAN training step of the reference's Training/Train_goodGAN.py (class Train :26-454)
+on the sm_100a path.
+
+What is mirrored: graph construction `_build_train_graph` (:400-426), variable partition by name
+substring + three Adam optimisers + EMA over the classifier (:78-103), and the D -> G -> C step
+(:249-276) with the per-`sess.run` pruning TF applies: each phase executes only the
+passes its loss depends on, draws fresh noise per pass, and updates only its own `var_list`.
+Epoch bookkeeping, summaries, checkpoints and the tf.data pipeline are out of scope.
+
+Data parallelism (new; the reference is single-GPU): one process per GPU, each rank runs the full
+per-rank batch tuple, the flat fp32 gradient buffer of the phase's network is all-reduced (NCCL, sum)
+and 1/world is folded into the fused Adam kernel.
+"""
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .core import VariableStore, building, ctx, no_grad, recording
+from .train_base import AdamOptimizer, Train_base
+
+INPUT_NAMES = ('z_g', 'y_g', 'x_l_c', 'y_l_c', 'x_l_d', 'y_l_d', 'x_u_d', 'x_u_c')
+
+
+class ExponentialMovingAverage:
+    """tf.train.ExponentialMovingAverage(decay).apply(c_vars) (Train_goodGAN.py:101-103): shadow buffer
+    updated by the fused Adam kernel; no debias, no num_updates."""
+
+    def __init__(self, decay):
+        self.decay = decay
+        self.shadow = None
+        self._fb = None
+
+    def bind(self, fb):
+        self._fb = fb
+        self.shadow = fb['theta'].clone()
+
+    def average(self, param):
+        i = self._fb['params'].index(param)
+        o = self._fb['offsets'][i]
+        return self.shadow[o:o + param.size].view(param.shape)
+
+
+class Train(Train_base):
+    def __init__(self, config, log_dir=None, save_dir=None, **kwargs):
+        super(Train, self).__init__()
+        self.config = config
+        self.comments = kwargs.get('comments', '')
+        self.store = VariableStore(seed=kwargs.get('seed', 1234))
+        self.model = None
+        self.graph = None
+        self.world = 1
+        self.pg = None
+        self.last_losses = None
+
+    # ------------------------------------------------------------------ graph construction --------
+    def input_shapes(self):
+        c = self.config
+        img = list(c.IMAGE_DIM)
+        return dict(z_g=[c.BATCH_SIZE_G, c.Z_DIM], y_g=[c.BATCH_SIZE_G, c.NUM_CLASSES],
+                    x_l_c=[c.BATCH_SIZE_L_C] + img, y_l_c=[c.BATCH_SIZE_L_C, c.NUM_CLASSES],
+                    x_l_d=[c.BATCH_SIZE_L_D] + img, y_l_d=[c.BATCH_SIZE_L_D, c.NUM_CLASSES],
+                    x_u_d=[c.BATCH_SIZE_U_D] + img, x_u_c=[c.BATCH_SIZE_U_C] + img)
+
+    def _build_train_graph(self, Model):
+        """Train_goodGAN.py:400-426: placeholders -> Model(config).forward_pass(...).  Runs in shape-only
+        mode: creates every variable under its TF name, launches nothing (works without a GPU)."""
+        ctx.store = self.store
+        self.model = Model(self.config)
+        with building(), no_grad():
+            ph = {k: ops.Var(None, tuple(v)) for k, v in self.input_shapes().items()}
+            G, D, C = self.model.forward_pass(ph['z_g'], ph['y_g'], ph['x_l_c'], ph['y_l_c'], ph['x_l_d'],
+                                              ph['y_l_d'], ph['x_u_d'], ph['x_u_c'], True)
+        t_vars = self.store.trainable()
+        self.g_vars = [v for v in t_vars if 'good_generator' in v.name]
+        self.d_vars = [v for v in t_vars if 'discriminator' in v.name]
+        self.c_vars = [v for v in t_vars if 'classifier' in v.name]
+        return ph, G, D, C, self.model
+
+    def initialize(self, init=None):
+        """global_variables_initializer (Train_goodGAN.py:154-156) or injected values
+        (`init=(P, S)` numpy dicts keyed by TF names), then the optimisers of :85-103."""
+        if self.model is None:
+            raise RuntimeError('call _build_train_graph(Model) first')
+        if init is not None:
+            self.store.load_numpy(*init)
+        self.store.finalize(ctx.device)
+        c = self.config
+        self.d_optimizer = self._Adam_optimizer(lr=c.LEARNING_RATE, beta1=c.BETA1)
+        self.g_optimizer = self._Adam_optimizer(lr=c.LEARNING_RATE, beta1=c.BETA1)
+        self.c_optimizer = self._Adam_optimizer(lr=c.CLA_LEARNINIG_RATE, beta1=0.5)
+        self.ema = ExponentialMovingAverage(decay=0.9999)
+        self.ema.bind(self.store.flat['classifier'])
+        self.lambdas = torch.zeros(2, dtype=torch.float32, device=ctx.device)
+        self._lam = (None, None)
+        self.inputs = {k: torch.zeros(tuple(v), dtype=torch.float32, device=ctx.device)
+                       for k, v in self.input_shapes().items()}
+        # everything a CUDA-graph replay must NOT re-initialise is created here, outside any capture
+        for o in (self.d_optimizer, self.g_optimizer, self.c_optimizer):
+            o._state()
+        self.loss_buf = torch.zeros(3, dtype=torch.float32, device=ctx.device)
+        ctx.ws()
+        if not ctx.rng.injected:
+            ctx.rng.counter()
+        if c.DATA_NAME == 'cifar10' and hasattr(self.model, '_whitener'):
+            self.model._whitener()._upload()
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size()
+        return self
+
+    # ------------------------------------------------------------------ one step ------------------
+    def _set_scalars(self, lambda_1, lambda_2, lr, cla_lr):
+        if (lambda_1, lambda_2) != self._lam:
+            self._lam = (lambda_1, lambda_2)
+            _lib.call('tgan_fill_f32', self.lambdas.data_ptr(), float(lambda_1), 1, ops._st())
+            _lib.call('tgan_fill_f32', self.lambdas.data_ptr() + 4, float(lambda_2), 1, ops._st())
+        if lr is not None:
+            self.d_optimizer.set_lr(lr)
+            self.g_optimizer.set_lr(lr)
+        if cla_lr is not None:
+            self.c_optimizer.set_lr(cla_lr)
+
+    def _begin(self, group, var_list):
+        for p in self.store.vars.values():
+            p.requires_grad = False
+        for p in var_list:
+            p.requires_grad = True
+        fb = self.store.flat[group]
+        _lib.call('tgan_fill_f32', fb['grad'].data_ptr(), 0.0, fb['n'], ops._st())
+        return fb
+
+    def _apply(self, fb, opt, ema=None):
+        scale = 1.0
+        if self.world > 1:
+            torch.distributed.all_reduce(fb['grad'], group=self.pg)      # NCCL sum over NVLink
+            scale = 1.0 / self.world
+        opt.apply_flat(fb, scale, ema.shadow if ema is not None else None, ema.decay if ema is not None else 0.0)
+        self.store.bump()
+
+    def _pre(self):
+        m = self.model
+        if self.config.DATA_NAME == 'cifar10' and hasattr(m, '_whitener'):
+            return m._whitener().apply
+        return lambda t: t
+
+    def _step_impl(self, train=True):
+        m, c = self.model, self.config
+        v = {k: ops.Var(t, tuple(t.shape)) for k, t in self.inputs.items()}
+        pre, K = self._pre(), c.NUM_CLASSES
+        cif = c.DATA_NAME == 'cifar10' and hasattr(m, '_whitener')
+        # ---- phase D: sess.run([d_solver, d_loss]) (:267) ----
+        with no_grad():
+            c_unl_d, _ = m.classifier(pre(v['x_u_d']), train, reuse=True, tag='D/C_unl_d')
+            c_unl, _ = m.classifier(pre(v['x_u_c']), train, reuse=True, tag='D/C_unl')
+            idx_d, oh_d = ops.argmax_onehot(c_unl_d, K)
+            idx_u, oh_u = ops.argmax_onehot(c_unl, K)
+            G = m.good_generator(v['z_g'], v['y_g'], reuse=True, tag='D/G')
+        from .good_gan_cifar10 import concat_batch
+        fb = self._begin('discriminator', self.d_vars)
+        with recording():
+            X_P, Y_P = concat_batch([v['x_l_d'], v['x_u_d']]), concat_batch([v['y_l_d'], oh_d])
+            _, dr = m.discriminator(X_P, Y_P, reuse=True, tag='D/D_real')
+            _, df = m.discriminator(G, v['y_g'], reuse=True, tag='D/D_fake')
+            _, du = m.discriminator(v['x_u_c'], oh_u, reuse=True, tag='D/D_unl')
+            d_loss = ops.loss_d(dr, df, du)
+            ops.backward(d_loss)
+        self._apply(fb, self.d_optimizer)
+        self.aux = dict(idx_unl_d=idx_d, idx_unl=idx_u, G_phaseD=G, d_logits=(dr, df, du))
+        # ---- phase G: sess.run([g_solver, g_loss]) (:270) ----
+        fb = self._begin('good_generator', self.g_vars)
+        with recording():
+            G = m.good_generator(v['z_g'], v['y_g'], reuse=True, tag='G/G')
+            _, df = m.discriminator(G, v['y_g'], reuse=True, tag='G/D_fake')
+            g_loss = ops.loss_g(df)
+            ops.backward(g_loss)
+        self._apply(fb, self.g_optimizer)
+        # ---- phase C: sess.run([c_solver, c_loss]) (:275) ----
+        fb = self._begin('classifier', self.c_vars)
+        with recording():
+            c_real, _ = m.classifier(pre(v['x_l_c']), train, reuse=True, tag='C/C_real')
+            c_unl, _ = m.classifier(pre(v['x_u_c']), train, reuse=True, tag='C/C_unl')
+            c_rep = m.classifier(pre(v['x_u_c']), train, reuse=True, tag='C/C_unl_rep')[0] if cif else None
+            with no_grad():
+                G = m.good_generator(v['z_g'], v['y_g'], reuse=True, tag='C/G')
+                _, oh_u = ops.argmax_onehot(c_unl, K)
+                _, du = m.discriminator(v['x_u_c'], oh_u, reuse=True, tag='C/D_unl')
+            c_fake, _ = m.classifier(pre(G), train, reuse=True, tag='C/C_fake')
+            c_loss = ops.loss_c(c_real, v['y_l_c'], c_unl, c_rep, du, c_fake, v['y_g'], self.lambdas)
+            ops.backward(c_loss)
+        self._apply(fb, self.c_optimizer, self.ema)
+        self.aux['c_logits'] = (c_real, c_unl, c_fake, c_rep)
+        if not ctx.rng.injected:
+            _lib.call('tgan_counter_advance', ctx.rng.counter().data_ptr(), 1, ops._st())
+        for i, l in enumerate((d_loss, g_loss, c_loss)):
+            _lib.call('tgan_copy_channels', l.value.data_ptr(), 0, 1, self.loss_buf.data_ptr() + 4 * i, 0, 1, 1, 1,
+                      ops._st())
+        return d_loss, g_loss, c_loss
+
+    def load_batch(self, batch):
+        """Copy one step's inputs (numpy / CPU / device tensors) into the static device buffers."""
+        for k in INPUT_NAMES:
+            t = batch[k]
+            if isinstance(t, np.ndarray):
+                t = torch.from_numpy(t)
+            self.inputs[k].copy_(t.reshape(self.inputs[k].shape), non_blocking=True)
+
+    def step(self, batch=None, lambda_1=None, lambda_2=0.0, lr=None, cla_lr=None, train=True):
+        """One training iteration (Train_goodGAN.py:249-276).  Returns the device tensor
+        [d_loss, g_loss, c_loss] (values before each phase's update); no host synchronisation."""
+        ctx.store = self.store
+        if batch is not None:
+            self.load_batch(batch)
+        lam1 = self.config.FAKE_G_LAMBDA if lambda_1 is None else lambda_1
+        self._set_scalars(lam1, lambda_2, lr, cla_lr)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step_impl(train)
+        return self.loss_buf
+
+    def capture(self, warmup=3):
+        """Capture the whole three-phase step into one CUDA graph (the step is a few hundred small
+        launches, SURVEY.md §7 'Launch-bound regime').  Inputs are read from the static buffers."""
+        assert not ctx.rng.injected, 'graph capture needs the in-kernel Philox RNG'
+        ctx.store = self.store
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._step_impl(True)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        n0 = _lib.load().tgan_launch_count()
+        with torch.cuda.graph(g):
+            self._step_impl(True)
+        self.launches_per_step = _lib.load().tgan_launch_count() - n0
+        self.graph = g
+        return g
+
+    # ------------------------------------------------------------------ epoch driver (next) -------
+    def schedule(self, epoch, start_epoch=0):
+        """lambda_1 / lambda_2 / lr schedule of Train_goodGAN.py:165-177 for (1-based) `epoch`."""
+        c = self.config
+        lam1 = c.FAKE_G_LAMBDA if (start_epoch + epoch) > 200 else 0.
+        lam2 = (0.5 if epoch > 67 else 0) if c.DATA_NAME == 'cifar10' else 0.0
+        n = max(0, start_epoch + epoch - 299)
+        return lam1, lam2, c.LEARNING_RATE * 0.995 ** n, c.CLA_LEARNINIG_RATE * 0.99 ** n
