@@ -63,7 +63,7 @@ int tgan_col2im(const float* col, int N, int H, int W, int C, int kh, int kw, in
 /* ---------------------------------------------------------------- implicit-GEMM tcgen05 path (bf16) --
  * One tcgen05/TMEM/TMA kernel family.  A = activations gathered by shifted-window TMA loads (zero fill =
  * TF padding), B = packed bf16 weights [T][Nout][Kpad], fp32 accumulation in TMEM.
- *   out[n, oy*osy + ooy, ox*osx + oox, co] = sum_t sum_ci x[n, oy + dy[t], ox + dx[t], ci] * Wp[t][co][ci]
+ *   out[n, oy*osy + ooy, ox*osx + oox, co] = sum_t sum_ci x[n, oy*sy + dy[t], ox*sx + dx[t], ci] * Wp[t][co][ci]
  * for (oy,ox) on the [gh, gw] output grid.  Covers conv fprop / dgrad (stride 1), the four output-parity
  * sub-convolutions of the 5x5/s2 transposed conv (modle_base.py:250) and plain GEMMs (gh=1, T=1).
  * Replaces the same reference call sites as tgan_sgemm in the bf16 tensor-core mode. */
@@ -74,6 +74,7 @@ typedef struct {
   int T, Nout, Kpad;
   int dy[25], dx[25];  /* tap offsets                                          */
   int gh, gw;          /* output grid per image (tile = th x tw pixels)        */
+  int sy, sx;          /* input traversal stride: x[n, oy*sy + dy, ox*sx + dx]  (conv stride; 0 = 1) */
   void* out;           /* dtype odt, [N, OH, OW, ldo]                          */
   int odt, OH, OW, ldo;
   int osy, osx, ooy, oox; /* output placement (stride / offset)                */
@@ -93,21 +94,22 @@ typedef struct {
   int N, gh, gw, Cout, lddz;
   const void* x;       /* bf16 [N, H, W, ldx]                                  */
   int H, W, Cin, ldx;
+  int sy, sx;          /* x traversal stride (0 = 1): x[n, oy*sy + dy[t], ox*sx + dx[t], ci] */
   int T; int dy[25], dx[25];
-  float* dw;           /* fp32 [T][Cout][Cin] (row-major), accumulate if beta != 0 */
+  float* dw;           /* fp32, element (t, co, ci) at dw[t*dw_st + co*dw_sco + ci*dw_sci]; dw = beta*dw + sum */
+  int64_t dw_st, dw_sco, dw_sci;
   float beta;
   float* ws; int64_t ws_bytes;
 } tgan_wgrad_args;
 int tgan_wgrad_bf16(const tgan_wgrad_args* a, void* stream);
 int64_t tgan_wgrad_workspace_bytes(const tgan_wgrad_args* a);
 
-/* weight preparation for the tcgen05 path: W_eff fp32 (any of the TF layouts) -> bf16 [T][Nout][Kpad].
- *   mode 0 (fprop):  src HWIO [T][Cin][Cout]      -> dst[t][co][ci]
- *   mode 1 (dgrad):  src HWIO [T][Cin][Cout]      -> dst[T-1-t][ci][co]   (flipped taps, roles swapped)
- *   mode 2 (deconv): src [T][Cout][Cin] tap subset `taps[nt]` -> dst[j][co][ci]
- * K beyond the source extent is zero filled. */
-int tgan_pack_weight_bf16(const float* src, void* dst, int mode, int T, int Cin, int Cout, int Kpad,
-                          const int* taps_dev, int nt, void* stream);
+/* weight preparation for the tcgen05 path: fp32 weights (any TF layout, addressed by strides) ->
+ * bf16 K-major [T][Nrows][Kpad]:  dst[t][n][k] = k < K ? src[taps[t]*st + n*sn + k*sk] : 0
+ * (taps_dev = NULL -> identity).  fprop HWIO: Nrows=Cout,K=Cin,sn=1,sk=Cout; dgrad HWIO: Nrows=Cin,K=Cout,
+ * sn=Cout,sk=1; transposed-conv [T][Cout][Cin]: Nrows=Cout,K=Cin,sn=Cin,sk=1. */
+int tgan_pack_weight_bf16(const float* src, void* dst, int T, int Nrows, int K, int Kpad, int64_t st, int64_t sn,
+                          int64_t sk, const int* taps_dev, void* stream);
 
 /* ---------------------------------------------------------------- weight normalisation ------------
  * V viewed as [A, Co, B]; per output channel co: nrm = sqrt(sum_{a,b} V^2);

@@ -679,7 +679,7 @@ class OracleTrainer:
         _, du = m.discriminator(b['x_u_c'], oh_u, rng, 'D/D_unl')
         d_loss = d_loss_fn(dr, df, du)
         gd = self._grads(d_loss, self.d_vars)
-        self.last_aux['D'] = dict(idx_unl_d=idx_d, idx_unl=idx_u, G=G, logits=(dr.detach(), df.detach(), du.detach()))
+        self.last_aux['D'] = dict(idx_unl_d=idx_d, idx_unl=idx_u, G=G, c_unl_d=c_unl_d, c_unl=c_unl, logits=(dr.detach(), df.detach(), du.detach()))
         if update:
             self.opt_d.apply(self.P, gd, lr)
         # ---- phase G (:270) ----

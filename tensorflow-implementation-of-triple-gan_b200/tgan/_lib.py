@@ -45,7 +45,8 @@ class TganIgemmArgs(ctypes.Structure):
     _fields_ = [('x', ctypes.c_void_p), ('N', ctypes.c_int), ('H', ctypes.c_int), ('W', ctypes.c_int),
                 ('C', ctypes.c_int), ('ldx', ctypes.c_int), ('wp', ctypes.c_void_p), ('T', ctypes.c_int),
                 ('Nout', ctypes.c_int), ('Kpad', ctypes.c_int), ('dy', ctypes.c_int * 25), ('dx', ctypes.c_int * 25),
-                ('gh', ctypes.c_int), ('gw', ctypes.c_int), ('out', ctypes.c_void_p), ('odt', ctypes.c_int),
+                ('gh', ctypes.c_int), ('gw', ctypes.c_int), ('sy', ctypes.c_int), ('sx', ctypes.c_int),
+                ('out', ctypes.c_void_p), ('odt', ctypes.c_int),
                 ('OH', ctypes.c_int), ('OW', ctypes.c_int), ('ldo', ctypes.c_int), ('osy', ctypes.c_int),
                 ('osx', ctypes.c_int), ('ooy', ctypes.c_int), ('oox', ctypes.c_int), ('vh', ctypes.c_int),
                 ('vw', ctypes.c_int), ('bias', ctypes.c_void_p), ('colsum', ctypes.c_void_p), ('act', ctypes.c_int),
@@ -55,8 +56,10 @@ class TganIgemmArgs(ctypes.Structure):
 class TganWgradArgs(ctypes.Structure):
     _fields_ = [('dz', ctypes.c_void_p), ('N', ctypes.c_int), ('gh', ctypes.c_int), ('gw', ctypes.c_int),
                 ('Cout', ctypes.c_int), ('lddz', ctypes.c_int), ('x', ctypes.c_void_p), ('H', ctypes.c_int),
-                ('W', ctypes.c_int), ('Cin', ctypes.c_int), ('ldx', ctypes.c_int), ('T', ctypes.c_int),
+                ('W', ctypes.c_int), ('Cin', ctypes.c_int), ('ldx', ctypes.c_int), ('sy', ctypes.c_int), ('sx', ctypes.c_int),
+                ('T', ctypes.c_int),
                 ('dy', ctypes.c_int * 25), ('dx', ctypes.c_int * 25), ('dw', ctypes.c_void_p),
+                ('dw_st', ctypes.c_int64), ('dw_sco', ctypes.c_int64), ('dw_sci', ctypes.c_int64),
                 ('beta', ctypes.c_float), ('ws', ctypes.c_void_p), ('ws_bytes', ctypes.c_int64)]
 
 

@@ -35,7 +35,7 @@ class Context:
         self.store = None
         self.rng = None
         self._ws = None
-        self.ws_floats = 24 * 1024 * 1024
+        self.ws_floats = 64 * 1024 * 1024
 
     @property
     def act_dtype(self):

@@ -1,31 +1,218 @@
 """bf16 tensor-core (tcgen05 / TMEM / TMA) routing of the dense contractions.
 
-`ops.conv2d` / `ops.conv2d_transpose` call in here when ctx.math == 'bf16'.  A layer is eligible when the
-implicit-GEMM kernel's tiling covers it (stride 1, 128-pixel tiles that align with image rows, >= 16
-output channels); everything else (Cout in {1,3,10}, stride-2 convs) stays on the fp32 SIMT path.
+`ops.conv2d` / `ops.conv2d_transpose` call in here when ctx.math == 'bf16'.  Every contraction is expressed
+as a list of taps (dy, dx) over shifted, optionally strided windows of an NHWC bf16 tensor:
+
+  conv fprop        x window (oy*s + r - pt, ox*s + c - pl)                         -> tgan_igemm_bf16
+  conv dgrad s=1    dz window (y + pt - r, x + pl - c), weights with roles swapped  -> tgan_igemm_bf16
+  conv dgrad s=2    4 output-parity classes of the transposed conv                  -> 4 x tgan_igemm_bf16
+  conv wgrad        pixel axis = GEMM K, MN-major operands                          -> tgan_wgrad_bf16
+  deconv fprop      4 output-parity classes (5x5/s2: 4/6/6/9 taps)                  -> 4 x tgan_igemm_bf16
+  deconv dgrad      strided forward conv of dy                                      -> tgan_igemm_bf16
+  deconv wgrad      wgrad with operand roles exchanged                              -> tgan_wgrad_bf16
+  dense / NiN / ZCA 1 tap, H = 1                                                    -> same kernels
+
+Skinny layers (Cout < 16: RGB output, logits, D head) stay on the fp32 SIMT path.
 """
-from .core import ctx  # noqa: F401
+import ctypes
+
+import torch
+
+from . import _lib
+from .core import BF16, ctx, dt_code
 
 
-def conv_eligible(geom, x):
-    return False
+def _st():
+    return torch.cuda.current_stream().cuda_stream
 
 
-def deconv_eligible(geom, x):
-    return False
+def _new(shape, dtype):
+    return torch.empty(tuple(int(s) for s in shape), dtype=dtype, device=ctx.device)
 
 
-def conv_fwd(x, w, geom):
-    raise NotImplementedError
+def _bf16_padded(t, rows, C, ld):
+    """-> (bf16 tensor [rows, ld8], ld8) with ld8 % 8 == 0 and zero padding (TMA needs 16-byte pixel strides)."""
+    if t.dtype == torch.bfloat16 and ld % 8 == 0:
+        return t, ld
+    ld8 = (C + 7) // 8 * 8
+    o = _new((rows, ld8), torch.bfloat16)
+    _lib.call('tgan_concat_label', t.data_ptr(), dt_code(t), rows, C, ld, t.data_ptr(), 0, 1, o.data_ptr(), BF16, ld8,
+              _st())
+    return o, ld8
 
 
-def conv_bwd(x, w, geom, dz):
-    raise NotImplementedError
+def _wcache(w):
+    c = w.key.cache.setdefault('tc', {})
+    if c.get('version') != ctx.store.version:
+        c.clear()
+        c['version'] = ctx.store.version
+    return c
 
 
-def deconv_fwd(x, w, geom):
-    raise NotImplementedError
+_taps_dev = {}
 
 
-def deconv_bwd(x, w, geom, dy):
-    raise NotImplementedError
+def _taps_tensor(taps):
+    key = tuple(taps)
+    if key not in _taps_dev:
+        _taps_dev[key] = torch.tensor(list(taps), dtype=torch.int32, device=ctx.device)
+    return _taps_dev[key]
+
+
+def _pack(w, key, T, Nrows, K, st, sn, sk, taps=None):
+    """Packed bf16 K-major weights [T][Nrows][Kpad], cached per optimiser version."""
+    c = _wcache(w)
+    if key not in c:
+        Kpad = (K + 7) // 8 * 8
+        dst = _new((T, Nrows, Kpad), torch.bfloat16)
+        tp = None if taps is None else _taps_tensor(taps).data_ptr()
+        _lib.call('tgan_pack_weight_bf16', w.value().data_ptr(), dst.data_ptr(), T, Nrows, K, Kpad, st, sn, sk, tp,
+                  _st())
+        c[key] = (dst, Kpad)
+    return c[key]
+
+
+def _igemm(x, N, H, W, C, ldx, wp, Kpad, taps, Nout, gh, gw, out, OH, OW, ldo, s=1, os_=1, oo=(0, 0), vh=0, vw=0):
+    a = _lib.TganIgemmArgs()
+    a.x, a.N, a.H, a.W, a.C, a.ldx = x.data_ptr(), N, H, W, C, ldx
+    a.wp, a.T, a.Nout, a.Kpad = wp.data_ptr(), len(taps), Nout, Kpad
+    for i, (dy, dx) in enumerate(taps):
+        a.dy[i], a.dx[i] = dy, dx
+    a.gh, a.gw, a.sy, a.sx = gh, gw, s, s
+    a.out, a.odt, a.OH, a.OW, a.ldo = out.data_ptr(), dt_code(out), OH, OW, ldo
+    a.osy, a.osx, a.ooy, a.oox, a.vh, a.vw = os_, os_, oo[0], oo[1], vh, vw
+    a.bias, a.colsum, a.act, a.alpha = None, None, 0, 1.0
+    _lib.call('tgan_igemm_bf16', ctypes.byref(a), _st())
+
+
+def _wgrad(dz, N, gh, gw, Cout, lddz, x, H, W, Cin, ldx, taps, s, dw, st, sco, sci):
+    a = _lib.TganWgradArgs()
+    a.dz, a.N, a.gh, a.gw, a.Cout, a.lddz = dz.data_ptr(), N, gh, gw, Cout, lddz
+    a.x, a.H, a.W, a.Cin, a.ldx, a.sy, a.sx = x.data_ptr(), H, W, Cin, ldx, s, s
+    a.T = len(taps)
+    for i, (dy, dx) in enumerate(taps):
+        a.dy[i], a.dx[i] = dy, dx
+    a.dw, a.dw_st, a.dw_sco, a.dw_sci, a.beta = dw.data_ptr(), st, sco, sci, 1.0
+    ws = ctx.ws()
+    a.ws, a.ws_bytes = ws.data_ptr(), ws.numel() * 4
+    _lib.call('tgan_wgrad_bf16', ctypes.byref(a), _st())
+
+
+# ------------------------------------------------------------------------------------------------
+# convolution (tf.nn.conv2d) and dense (tf.matmul)
+# ------------------------------------------------------------------------------------------------
+
+
+def conv_eligible(g, x):
+    return g['Cout'] >= 16 and g['kh'] * g['kw'] <= 25 and g['s'] in (1, 2) and g['Cout'] % 8 == 0 and \
+        (g['s'] == 1 or (g['H'] % 2 == 0 and g['W'] % 2 == 0))
+
+
+def _flat(g):
+    """1x1/s1 convs and dense layers are plain GEMMs: view the pixels as one row of length rows."""
+    if g['kh'] == 1 and g['kw'] == 1 and g['s'] == 1:
+        rows = g['N'] * g['H'] * g['W']
+        return dict(g, N=1, H=1, W=rows, Ho=1, Wo=rows)
+    return g
+
+
+def conv_fwd(x, w, g):
+    gf = _flat(g)
+    C, Cout, kh, kw = g['C'], g['Cout'], g['kh'], g['kw']
+    xd, ld = _bf16_padded(x.data, x.rows, C, x.ld)
+    g['_x'] = (xd, ld)
+    wp, Kpad = _pack(w, 'fprop', kh * kw, Cout, C, C * Cout, 1, Cout)
+    taps = [(r - g['pt'], c - g['pl']) for r in range(kh) for c in range(kw)]
+    z = _new((g['N'] * g['Ho'] * g['Wo'], Cout), torch.bfloat16)
+    _igemm(xd, gf['N'], gf['H'], gf['W'], C, ld, wp, Kpad, taps, Cout, gf['Ho'], gf['Wo'], z, gf['Ho'], gf['Wo'], Cout,
+           s=g['s'])
+    return z
+
+
+def conv_bwd(x, w, g, dz):
+    from .core import add_grad
+    gf = _flat(g)
+    C, Cout, kh, kw, s, pt, pl = g['C'], g['Cout'], g['kh'], g['kw'], g['s'], g['pt'], g['pl']
+    rows = g['N'] * g['Ho'] * g['Wo']
+    dzb, _ = _bf16_padded(dz, rows, Cout, Cout)
+    if w.requires_grad:
+        xd, ld = g.get('_x') or _bf16_padded(x.data, x.rows, C, x.ld)
+        taps = [(r - pt, c - pl) for r in range(kh) for c in range(kw)]
+        # HWIO gradient: element (t, co, ci) lives at t*C*Cout + ci*Cout + co
+        _wgrad(dzb, gf['N'], gf['Ho'], gf['Wo'], Cout, Cout, xd, gf['H'], gf['W'], C, ld, taps, s, w.grad_target(),
+               C * Cout, 1, Cout)
+    if x.requires_grad:
+        dx = _new(x.shape, x.data.dtype if x.data.dtype == torch.bfloat16 else torch.float32)
+        wp, Kpad = None, None
+        if s == 1:
+            wp, Kpad = _pack(w, 'dgrad', kh * kw, C, Cout, C * Cout, Cout, 1)
+            taps = [(pt - r, pl - c) for r in range(kh) for c in range(kw)]
+            _igemm(dzb, gf['N'], gf['Ho'], gf['Wo'], Cout, Cout, wp, Kpad, taps, C, gf['H'], gf['W'], dx, gf['H'],
+                   gf['W'], C)
+        else:
+            # input-gradient of a stride-2 conv = transposed conv: one launch per output parity class
+            for py in range(2):
+                for px in range(2):
+                    rs = [r for r in range(kh) if (py + pt - r) % 2 == 0]
+                    cs = [c for c in range(kw) if (px + pl - c) % 2 == 0]
+                    if not rs or not cs:
+                        continue
+                    sel = [r * kw + c for r in rs for c in cs]
+                    taps = [((py + pt - r) // 2, (px + pl - c) // 2) for r in rs for c in cs]
+                    wp, Kpad = _pack(w, ('dgrad2', py, px), len(sel), C, Cout, C * Cout, Cout, 1, sel)
+                    _igemm(dzb, g['N'], g['Ho'], g['Wo'], Cout, Cout, wp, Kpad, taps, C, g['H'] // 2, g['W'] // 2, dx,
+                           g['H'], g['W'], C, os_=2, oo=(py, px))
+        add_grad(x, dx if dx.dtype == x.data.dtype else dx.to(x.data.dtype))
+    g.pop('_x', None)
+
+
+# ------------------------------------------------------------------------------------------------
+# transposed convolution (tf.nn.conv2d_transpose 'SAME', stride 2)
+# ------------------------------------------------------------------------------------------------
+
+
+def deconv_eligible(g, x):
+    return g['Cout'] >= 16 and g['Cout'] % 8 == 0 and g['s'] == 2 and g['kh'] * g['kw'] <= 25
+
+
+def _parity_classes(g):
+    kh, kw, pt, pl = g['kh'], g['kw'], g['pt'], g['pl']
+    for py in range(2):
+        for px in range(2):
+            rs = [r for r in range(kh) if (py + pt - r) % 2 == 0]
+            cs = [c for c in range(kw) if (px + pl - c) % 2 == 0]
+            if rs and cs:
+                yield py, px, [r * kw + c for r in rs for c in cs], \
+                    [((py + pt - r) // 2, (px + pl - c) // 2) for r in rs for c in cs]
+
+
+def deconv_fwd(x, w, g):
+    Cin, Cout = g['Cin'], g['Cout']
+    xd, ld = _bf16_padded(x.data, x.rows, Cin, x.ld)
+    g['_x'] = (xd, ld)
+    y = _new((g['N'], g['Ho'], g['Wo'], Cout), torch.bfloat16)
+    for py, px, sel, taps in _parity_classes(g):
+        wp, Kpad = _pack(w, ('dfwd', py, px), len(sel), Cout, Cin, Cout * Cin, Cin, 1, sel)
+        _igemm(xd, g['N'], g['h'], g['w'], Cin, ld, wp, Kpad, taps, Cout, g['h'], g['w'], y, g['Ho'], g['Wo'], Cout,
+               os_=2, oo=(py, px))
+    return y
+
+
+def deconv_bwd(x, w, g, dy):
+    from .core import add_grad
+    Cin, Cout, kh, kw, pt, pl = g['Cin'], g['Cout'], g['kh'], g['kw'], g['pt'], g['pl']
+    dyb, _ = _bf16_padded(dy, g['N'] * g['Ho'] * g['Wo'], Cout, Cout)
+    taps = [(r - pt, c - pl) for r in range(kh) for c in range(kw)]
+    if w.requires_grad:
+        xd, ld = g.get('_x') or _bf16_padded(x.data, x.rows, Cin, x.ld)
+        # roles exchanged: M side = x channels (ci), N side = strided dy window (co);
+        # filter layout [t][co][ci]: kernel's (t, "co"=ci, "ci"=co) -> t*Cout*Cin + co*Cin + ci
+        _wgrad(xd, g['N'], g['h'], g['w'], Cin, ld, dyb, g['Ho'], g['Wo'], Cout, Cout, taps, 2, w.grad_target(),
+               Cout * Cin, 1, Cin)
+    if x.requires_grad:
+        wp, Kpad = _pack(w, 'ddgrad', kh * kw, Cin, Cout, Cout * Cin, 1, Cin)
+        dx = _new(x.shape, torch.bfloat16)
+        _igemm(dyb, g['N'], g['Ho'], g['Wo'], Cout, Cout, wp, Kpad, taps, Cin, g['h'], g['w'], dx, g['h'], g['w'], Cin,
+               s=2)
+        add_grad(x, dx if dx.dtype == x.data.dtype else dx.to(x.data.dtype))
+    g.pop('_x', None)

@@ -229,8 +229,8 @@ def test_pools_concat_dropout_noise():
         out = ops.max_pool2(xv)
         fwd = tnp(out.data)
         run_bwd(out, gy)
-    assert relerr(fwd, yt.detach().numpy()) == 0
-    assert relerr(tnp(xv.grad), xt.grad.numpy()) == 0
+    assert relerr(fwd, yt.detach().numpy()) < 1e-6
+    assert relerr(tnp(xv.grad), xt.grad.numpy()) < 1e-6
     for mode in ('max', 'mean'):
         x6 = rng.standard_normal((4, 6, 6, 10))
         xt = T(x6, True)
@@ -250,10 +250,10 @@ def test_pools_concat_dropout_noise():
     with core.recording():
         xv = var(x, True)
         out = ops.concat_label(xv, var(y))
-        assert relerr(out.numpy(), ref) == 0
+        assert relerr(out.numpy(), ref) < 1e-6
         gy = rng.standard_normal(ref.shape)
         run_bwd(out, gy)
-    assert relerr(tnp(xv.grad), gy[..., :6].astype(np.float32)) == 0
+    assert relerr(tnp(xv.grad), gy[..., :6].astype(np.float32)) < 1e-6
     # injected dropout / noise reproduce the oracle's draws exactly
     r = O.TagRNG(11)
     ctx = setup('fp32', injected=r)
