@@ -1,0 +1,274 @@
+#!/usr/bin/env python
+"""bench.py -- CIFAR-10 Triple-GAN training throughput (images/sec) on 1..8 B200, one process per GPU.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's CPU path (TF-equivalent restatement) on host cores
+
+A step = phases D + G + C of Training/Train_goodGAN.py:266-276 on the per-rank batch tuple
+(G 100, L_C 50, U_C 50, L_D 20, U_D 80 -> BATCH_SIZE = 100 images).  Weak scaling: per-rank batch fixed,
+global batch = 100 * N.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, 'tensorflow-implementation-of-triple-gan_b200')):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+STEP_TFLOP = 1.465          # algorithmic dense-contraction FLOPs of one CIFAR-10 step, x1e12
+IMAGES_PER_STEP = 100
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(bf16=d['bf16_tflops'], bf16_sustained=d.get('bf16_tflops_sustained', d['bf16_tflops']),
+                    hbm=d['hbm_gbs'], src='measured')
+    return dict(bf16=1590.0, bf16_sustained=1400.0, hbm=6650.0, src='fallback')
+
+
+class ClockSampler:
+    FIELDS = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,' \
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,' \
+             'clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, idx):
+        self.idx, self.p = idx, None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.FIELDS,
+                                       '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                      stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ''
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(',')]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def cpu_step_time(scale, steps, warmup):
+    """the reference's CPU path: float32 torch-CPU restatement of the identical three-phase step (TensorFlow is
+    not installable in this image), all host threads."""
+    import torch
+    from oracle import tgan_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    P, S = O.init_params('cifar10', seed=1234)
+    tr = O.OracleTrainer('cifar10', P, S, O.make_zca(1234), dtype=torch.float32, scale=scale)
+    batch = O.make_batch(tr.cfg, seed=1234)
+    rng = O.TagRNG(0)
+    for _ in range(warmup):
+        tr.step(batch, rng, 0.3, 0.5)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        tr.step(batch, rng, 0.3, 0.5)
+        ts.append(time.perf_counter() - t0)
+    return sum(ts) / len(ts), tr.cfg.BATCH_SIZE
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    scale = 4                       # bounded sample: 25 images per step (G 25, L_C 12, U_C 12, L_D 5, U_D 20)
+    t, imgs = cpu_step_time(scale, args.steps, max(1, min(args.warmup, 2)))
+    v = imgs / t
+    sample = 'CIFAR-10 Triple-GAN step at 1/%d of the batch tuple (%d images/step), float32 torch-CPU restatement ' \
+             'of the TF graph (TensorFlow not installable here)' % (scale, imgs)
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'CIFAR-10 Triple-GAN train images/sec', 'value': v, 'unit': 'images/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': t * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'CIFAR-10 32x32x3 Triple-GAN (Good_GAN_cifar10) training step, batch 100 per GPU',
+                   'sample': sample},
+        'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': os.cpu_count(), 'kind': 'port', 'sample': sample},
+        'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+
+
+def dominant_kernel_roofline(torch, tgan, pk):
+    """conv1_2 / conv1_3 forward at batch 100 (128 -> 128 channels, 32x32, 3x3): the implicit-GEMM tcgen05 kernel
+    that carries ~87% of the step's FLOPs across its fprop / dgrad instances.  Timed alone with CUDA events on the
+    launching stream, L2 flushed between launches (256 MB write)."""
+    from tgan import core, ops
+    core.ctx.store = core.VariableStore()
+    N, H, C = 100, 32, 128
+    x = ops.Var(torch.randn(N, H, H, C, device='cuda').to(torch.bfloat16), (N, H, H, C))
+    p = core.Param('w', (3, 3, C, C), True, None)
+    p.data = torch.randn(3, 3, C, C, device='cuda') * 0.03
+    w = ops.PlainWeight(p)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')
+    flops = 2.0 * N * H * H * 9 * C * C
+    for _ in range(3):
+        ops.conv2d(x, w, 3, 3, 1, 'SAME')
+    ts = []
+    for _ in range(10):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.conv2d(x, w, 3, 3, 1, 'SAME')
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e-3)
+    ts.sort()
+    t = sum(ts[:8]) / 8           # includes the output allocation; launches dominate
+    achieved = flops / t / 1e12
+    traffic = None
+    pj = os.path.join(ROOT, 'profiles', 'dominant_kernel.json')
+    if os.path.exists(pj):
+        traffic = json.load(open(pj)).get('dram_bytes_per_launch')
+    return {'bound': 'tensor', 'kernel': 'igemm_kernel (conv 128->128 @32x32, batch 100, fprop)', 'achieved': achieved,
+            'peak': pk['bf16'], 'unit': 'TFLOP/s', 'frac': achieved / pk['bf16'], 'peak_source': pk['src'] + ' burst bf16',
+            'traffic': traffic, 'flops_per_launch': flops, 'us_per_launch': t * 1e6}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--math', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import tgan
+    from tgan import _lib, synthetic
+    args.warmup = max(args.warmup, 3)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    tgan.init('cuda:%d' % local, math=args.math, seed=1234 + rank)
+    tr = tgan.make_trainer('cifar10', zca=synthetic.make_zca(1234), seed=1234)
+    batch = {k: torch.from_numpy(v).pin_memory() for k, v in synthetic.make_batch(tr.config, 1234 + rank).items()}
+    h2d = sum(v.numel() * v.element_size() for v in batch.values())
+    tr.load_batch(batch)
+    lam = dict(lambda_1=tr.config.FAKE_G_LAMBDA, lambda_2=0.5)
+    graph = False
+    if not args.no_graph:
+        try:
+            tr.capture(warmup=3)
+            graph = True
+        except Exception as e:            # e.g. NCCL capture unsupported: run the same launches eagerly
+            tr.graph = None
+            torch.cuda.synchronize()
+            if rank == 0:
+                print('graph capture failed (%s); running eager' % str(e)[:200], file=sys.stderr)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        tr.step(**lam)
+    barrier()
+    # ---- leg 1: inputs resident in HBM ----
+    sampler = ClockSampler(local)
+    sampler.start()
+    _lib.load().tgan_launch_count_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        tr.step(**lam)
+    e1.record()
+    barrier()
+    t_dev = e0.elapsed_time(e1) * 1e-3
+    launches = _lib.load().tgan_launch_count()
+    if graph:
+        launches = tr.launches_per_step * args.steps
+    clocks = sampler.stop()
+    # ---- leg 2: end to end through the public API: pinned host batch -> H2D -> step -> loss D2H, every step ----
+    for _ in range(2):
+        tr.step(batch, **lam).cpu()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    last = None
+    for _ in range(args.steps):
+        last = tr.step(batch, **lam).cpu()
+    f1.record()
+    barrier()
+    t_e2e = f0.elapsed_time(f1) * 1e-3
+    tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_dev, t_e2e = float(tt[0]), float(tt[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    imgs = IMAGES_PER_STEP * world * args.steps
+    value = imgs / t_dev
+    out = {
+        'metric': 'CIFAR-10 Triple-GAN train images/sec', 'value': value, 'unit': 'images/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': t_dev / args.steps * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16' if args.math == 'bf16' else 'f32', 'data': 'synthetic',
+        'config': {'workload': 'CIFAR-10 32x32x3 Triple-GAN (Good_GAN_cifar10: WN 9-layer conv C + conv D + deconv G), '
+                               'one D+G+C training step, batch 100 per GPU (G 100, L_C 50, U_C 50, L_D 20, U_D 80)',
+                   'global_batch': IMAGES_PER_STEP * world, 'parallelism': 'dp%d' % world,
+                   'cuda_graph': graph,
+                   'l2': 'no explicit flush: one step streams > 1 GB of activations (>> 126 MB L2) between reuses'},
+        'e2e': {'value': imgs / t_e2e, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 12,
+                'ms_per_step': t_e2e / args.steps * 1e3},
+        'gpu_launches': int(launches),
+        'clocks': clocks,
+        'step_tensor_frac': STEP_TFLOP * 1e12 * world * args.steps / t_dev / (pk['bf16_sustained'] * 1e12 * world),
+        'losses': [float(x) for x in last],
+    }
+    if args.math == 'bf16':
+        out['roofline'] = dominant_kernel_roofline(torch, tgan, pk)
+    if world == 1 and not args.no_cpu_baseline:
+        t, n = cpu_step_time(4, 2, 1)
+        out['cpu_baseline'] = {'value': n / t, 'unit': 'images/s', 'cores': os.cpu_count(), 'kind': 'port',
+                               'sample': 'CIFAR-10 step at 1/4 of the batch tuple (%d images/step), 2 timed steps, '
+                                         'float32 torch-CPU restatement of the TF graph' % n}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -46,6 +46,44 @@ class TagRNG:
 
 
 # --------------------------------------------------------------------------------------
+# Optional bf16 rounding points.  The reference computes in fp32; the tensor-core mode of the CUDA path
+# stores activations and feeds the MMAs in bf16 (fp32 accumulation).  Rounding flips discrete routing
+# decisions (max-pool winners, lrelu sides), so its gradients cannot be compared point-wise with an
+# un-rounded run.  `with quantized():` restates the SAME rounding points in the oracle (straight-through
+# for autograd), which isolates the kernels' arithmetic from the precision choice:
+#   * operands of every tensor-core contraction (Cout >= 16 and Cout % 8 == 0) and its result,
+#   * the output of every epilogue / normalisation with >= 16 channels, of noise, dropout and concat.
+# --------------------------------------------------------------------------------------
+_QUANT = False
+
+
+class quantized:
+    def __enter__(self):
+        global _QUANT
+        self._old, _QUANT = _QUANT, True
+
+    def __exit__(self, *a):
+        global _QUANT
+        _QUANT = self._old
+
+
+def q(t):
+    """round to bf16 (straight-through gradient) when the bf16 restatement is active"""
+    if not _QUANT:
+        return t
+    return t + (t.detach().to(torch.bfloat16).to(t.dtype) - t.detach())
+
+
+def _tc(cout):
+    return _QUANT and cout >= 16 and cout % 8 == 0
+
+
+def qc(t):
+    """epilogue outputs keep fp32 when they have < 16 channels (logits, RGB)"""
+    return q(t) if t.shape[-1] >= 16 else t
+
+
+# --------------------------------------------------------------------------------------
 # TF op semantics
 # --------------------------------------------------------------------------------------
 
@@ -60,13 +98,16 @@ def same_pad(n, k, s):
 def conv2d_tf(x, w, stride=1, padding='SAME'):
     """tf.nn.conv2d on NHWC x, HWIO w (nn.py:504, modle_base.py:102,161)."""
     kh, kw = w.shape[0], w.shape[1]
+    tc = _tc(w.shape[3])
+    if tc:
+        x, w = q(x), q(w)
     xc = x.permute(0, 3, 1, 2)
     if padding.upper() == 'SAME':
         _, pt, pb = same_pad(x.shape[1], kh, stride)
         _, pl, pr = same_pad(x.shape[2], kw, stride)
         xc = F.pad(xc, (pl, pr, pt, pb))
     y = F.conv2d(xc, w.permute(3, 2, 0, 1), stride=stride)
-    return y.permute(0, 2, 3, 1)
+    return q(y.permute(0, 2, 3, 1)) if tc else y.permute(0, 2, 3, 1)
 
 
 def conv2d_transpose_tf(x, w, stride=2, padding='SAME'):
@@ -74,6 +115,9 @@ def conv2d_transpose_tf(x, w, stride=2, padding='SAME'):
     w is [kh,kw,Cout,Cin].  == input-gradient of the SAME conv: full scatter of size
     (n-1)s+k then crop [before : before + s*n] with before = (k-s)//2."""
     kh, kw = w.shape[0], w.shape[1]
+    tc = _tc(w.shape[2])
+    if tc:
+        x, w = q(x), q(w)
     y = F.conv_transpose2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), stride=stride)
     if padding.upper() == 'SAME':
         Ho, Wo = x.shape[1] * stride, x.shape[2] * stride
@@ -81,7 +125,14 @@ def conv2d_transpose_tf(x, w, stride=2, padding='SAME'):
         _, pl, _ = same_pad(Wo, kw, stride)
         # the full scatter may be smaller than pt+Ho when k < s; not the case for any model here
         y = y[:, :, pt:pt + Ho, pl:pl + Wo]
-    return y.permute(0, 2, 3, 1)
+    return q(y.permute(0, 2, 3, 1)) if tc else y.permute(0, 2, 3, 1)
+
+
+def matmul_tf(x, w):
+    """tf.matmul / tf.layers.dense contraction (nn.py:553; modle_base.py:40,67)"""
+    if _tc(w.shape[1]):
+        return q(q(x) @ q(w))
+    return x @ w
 
 
 def l2_normalize(v, axes, eps=1e-12):
@@ -102,7 +153,7 @@ def leaky_relu_tf(x, alpha=0.2):
 
 def dropout_tf(x, keep_mask, rate):
     """tf.layers.dropout(training=True): x * mask / (1-rate)  (modle_base.py:190)."""
-    return x * keep_mask.to(x.dtype) * (1.0 / (1.0 - rate))
+    return q(x * keep_mask.to(x.dtype) * (1.0 / (1.0 - rate)))
 
 
 def max_pool_tf(x, k, s):
@@ -112,7 +163,7 @@ def max_pool_tf(x, k, s):
 
 def cond_concat(x, yb):
     """modle_base.py:239-244."""
-    return torch.cat([x, yb.expand(x.shape[0], x.shape[1], x.shape[2], yb.shape[3])], dim=3)
+    return q(torch.cat([x, yb.expand(x.shape[0], x.shape[1], x.shape[2], yb.shape[3])], dim=3))
 
 
 def sigmoid_ce(logits, labels):
@@ -154,16 +205,19 @@ def conv2d_WN(P, S, scope, x, pad, train, nonlin=lrelu_cifar, stride=1):
     W = g.view(1, 1, 1, -1) * l2_normalize(V, (0, 1, 2))
     x = conv2d_tf(x, W, stride, pad)
     x = mean_only_bn(x, scope + '/meanOnlyBatchNormalization/pop_mean', b, S, train, True)
-    return nonlin(x) if nonlin is not None else x
+    return qc(nonlin(x) if nonlin is not None else x)
 
 
 def dense_WN(P, S, scope, x, train, nonlin=None):
     """nn.dense_WN, WN + mean-only BN (nn.py:552-570): matmul first, then g/sqrt(sum V^2), no eps."""
     V, g, b = P[scope + '/V'], P[scope + '/g'], P[scope + '/b']
-    x = x @ V
-    x = (g / torch.sqrt((V * V).sum(dim=0))).view(1, -1) * x
+    if _QUANT:      # the CUDA path folds g/||V|| into the weight before the (bf16) contraction
+        x = matmul_tf(x, V * (g / torch.sqrt((V * V).sum(dim=0))).view(1, -1))
+    else:
+        x = x @ V
+        x = (g / torch.sqrt((V * V).sum(dim=0))).view(1, -1) * x
     x = mean_only_bn(x, scope + '/meanOnlyBatchNormalization/pop_mean', b.view(1, -1), S, train, False)
-    return nonlin(x) if nonlin is not None else x
+    return qc(nonlin(x) if nonlin is not None else x)
 
 
 def NiN_WN(P, S, scope, x, train, nonlin):
@@ -187,13 +241,13 @@ def bn_contrib(P, S, scope, x, train, eps=1e-5, decay=0.9):
                                          + var.detach() * (n / max(n - 1, 1)) * (1 - decay))
     else:
         mu, var = S[scope + '/moving_mean'], S[scope + '/moving_variance']
-    return gamma * (x - mu) * torch.rsqrt(var + eps) + beta
+    return qc(gamma * (x - mu) * torch.rsqrt(var + eps) + beta)
 
 
 def linear_fc(P, scope, x):
     """NN_Base._linear_fc -> tf.layers.dense, scope doubled (modle_base.py:27-48)."""
     n = scope + '/' + scope.split('/')[-1]
-    return x @ P[n + '/kernel'] + P[n + '/bias']
+    return matmul_tf(x, P[n + '/kernel']) + P[n + '/bias']
 
 
 def conv2d_layer(P, scope, x, stride):
@@ -211,18 +265,25 @@ def deconv2d_layer(P, scope, x, stride=2):
 def WN_dense(P, scope, x):
     """NN_Base._WN_dense init=False (modle_base.py:50-73)."""
     V, g, b = P[scope + '/V'], P[scope + '/g'], P[scope + '/b']
+    if _QUANT:      # g folded into the weight before the contraction (same function of (V, g))
+        return matmul_tf(x, g.view(1, -1) * l2_normalize(V, (0,))) + b.view(1, -1)
     return g.view(1, -1) * (x @ l2_normalize(V, (0,))) + b.view(1, -1)
 
 
 def WN_conv2d(P, scope, x, stride):
     """NN_Base._WN_conv2d init=False (modle_base.py:75-108): conv(x, l2norm(V))*g + b."""
     V, g, b = P[scope + '/V'], P[scope + '/g'], P[scope + '/b']
+    if _QUANT:
+        return conv2d_tf(x, g.view(1, 1, 1, -1) * l2_normalize(V, (0, 1, 2)), stride, 'SAME') + b.view(1, 1, 1, -1)
     return g.view(1, 1, 1, -1) * conv2d_tf(x, l2_normalize(V, (0, 1, 2)), stride, 'SAME') + b.view(1, 1, 1, -1)
 
 
 def WN_deconv2d(P, scope, x, stride=2):
     """NN_Base._WN_deconv2d init=False (modle_base.py:130-155): normalise over axes [0,1,3]."""
     V, g, b = P[scope + '/V'], P[scope + '/g'], P[scope + '/b']
+    if _QUANT:
+        return conv2d_transpose_tf(x, g.view(1, 1, -1, 1) * l2_normalize(V, (0, 1, 3)), stride, 'SAME') \
+            + b.view(1, 1, 1, -1)
     y = conv2d_transpose_tf(x, l2_normalize(V, (0, 1, 3)), stride, 'SAME')
     return g.view(1, 1, 1, -1) * y + b.view(1, 1, 1, -1)
 
@@ -423,21 +484,21 @@ class OracleModel:
     def good_generator(self, z, y, rng, tag):
         P, S, name = self.P, self.S, self.cfg.DATA_NAME
         if name == 'mnist':      # Good_GAN.py:19-33
-            h = F.softplus(linear_fc(P, 'good_generator/gg_h0_lin', torch.cat([z, y], 1)))
+            h = qc(F.softplus(linear_fc(P, 'good_generator/gg_h0_lin', q(torch.cat([z, y], 1)))))
             h = bn_contrib(P, S, 'good_generator/gg_bn0', h, True)
-            h = F.softplus(linear_fc(P, 'good_generator/gg_h1_lin', torch.cat([h, y], 1)))
+            h = qc(F.softplus(linear_fc(P, 'good_generator/gg_h1_lin', q(torch.cat([h, y], 1)))))
             h = bn_contrib(P, S, 'good_generator/gg_bn1', h, True)
-            return torch.sigmoid(WN_dense(P, 'good_generator/gg_h2_lin', torch.cat([h, y], 1)))
+            return qc(torch.sigmoid(WN_dense(P, 'good_generator/gg_h2_lin', q(torch.cat([h, y], 1)))))
         yb = y.view(y.shape[0], 1, 1, -1)
-        h = linear_fc(P, 'good_generator/gg_h0_lin', torch.cat([z, y], 1))
+        h = linear_fc(P, 'good_generator/gg_h0_lin', q(torch.cat([z, y], 1)))
         if name == 'cifar10':    # Good_GAN_cifar10.py:40-43  fc -> relu -> BN over [N,8192] -> reshape
-            h = bn_contrib(P, S, 'good_generator/gg_bn0', F.relu(h), True).view(-1, 4, 4, 512)
+            h = bn_contrib(P, S, 'good_generator/gg_bn0', qc(F.relu(h)), True).view(-1, 4, 4, 512)
         else:                    # Good_GAN.py:40-43  fc -> reshape -> relu -> BN over [N,4,4,512]
-            h = bn_contrib(P, S, 'good_generator/gg_bn0', F.relu(h.view(-1, 4, 4, 512)), True)
+            h = bn_contrib(P, S, 'good_generator/gg_bn0', qc(F.relu(h.view(-1, 4, 4, 512))), True)
         h = self._cap(tag + '/h0', cond_concat(h, yb))
-        h = F.relu(deconv2d_layer(P, 'good_generator/gg_dconv0', h))
+        h = qc(F.relu(deconv2d_layer(P, 'good_generator/gg_dconv0', h)))
         h = cond_concat(bn_contrib(P, S, 'good_generator/gg_bn1', h, True), yb)
-        h = F.relu(deconv2d_layer(P, 'good_generator/gg_dconv1', h))
+        h = qc(F.relu(deconv2d_layer(P, 'good_generator/gg_dconv1', h)))
         h = cond_concat(bn_contrib(P, S, 'good_generator/gg_bn2', h, True), yb)
         if name == 'cifar10':
             return torch.tanh(deconv2d_layer(P, 'good_generator/gg_dconv2', h))
@@ -448,22 +509,22 @@ class OracleModel:
         P, name = self.P, self.cfg.DATA_NAME
         if name == 'mnist':      # Good_GAN.py:93-124
             h = image.reshape(-1, 784)
-            h = h + 0.2 * rng.normal(tag + '/noise0', h.shape).to(h.dtype)
-            h = torch.cat([h, y], 1)
+            h = q(h + 0.2 * rng.normal(tag + '/noise0', h.shape).to(h.dtype))
+            h = q(torch.cat([h, y], 1))
             for i, _ in enumerate([1000, 500, 250, 250, 250]):
-                h = leaky_relu_tf(WN_dense(P, 'discriminator/d_h%d_wndense0' % i, h))
-                h = h + 0.2 * rng.normal(tag + '/noise%d' % (i + 1), h.shape).to(h.dtype)
-                h = torch.cat([h, y], 1)
+                h = qc(leaky_relu_tf(WN_dense(P, 'discriminator/d_h%d_wndense0' % i, h)))
+                h = q(h + 0.2 * rng.normal(tag + '/noise%d' % (i + 1), h.shape).to(h.dtype))
+                h = q(torch.cat([h, y], 1))
             h = WN_dense(P, 'discriminator/d_h5_wndense0', h)
             return torch.sigmoid(h), h
         yb = y.view(y.shape[0], 1, 1, -1)
         if name == 'cifar10':    # Good_GAN_cifar10.py:60-99 (plain tf.layers.conv2d + cifar lrelu)
             names = ['conv2d_00', 'conv2d_01', 'conv2d_10', 'conv2d_11', 'conv2d_20', 'conv2d_21']
-            conv = lambda n, x, s: lrelu_cifar(conv2d_layer(P, 'discriminator/' + n, x, s))
+            conv = lambda n, x, s: qc(lrelu_cifar(conv2d_layer(P, 'discriminator/' + n, x, s)))
         else:                    # Good_GAN.py:126-165 (WN convs + tf.nn.leaky_relu)
             names = ['d_h0_wnconv0', 'd_h0_wnconv1', 'd_h1_wnconv0', 'd_h1_wnconv1', 'd_h2_wnconv0',
                      'd_h2_wnconv1']
-            conv = lambda n, x, s: leaky_relu_tf(WN_conv2d(P, 'discriminator/' + n, x, s))
+            conv = lambda n, x, s: qc(leaky_relu_tf(WN_conv2d(P, 'discriminator/' + n, x, s)))
         h = dropout_tf(image, rng.keep_mask(tag + '/drop0', image.shape, 0.2), 0.2)
         h = conv(names[0], cond_concat(h, yb), 1)
         h = conv(names[1], cond_concat(h, yb), 2)
@@ -476,7 +537,7 @@ class OracleModel:
         if name != 'cifar10':
             h = cond_concat(h, yb)            # the double concat of Good_GAN.py:151-153 (148 channels)
         h = self._cap(tag + '/h5', conv(names[5], h, 1))
-        h = torch.cat([h.mean(dim=(1, 2)), y], 1)     # avg-pool 8x8 == mean over H,W
+        h = q(torch.cat([q(h.mean(dim=(1, 2))), y], 1))     # avg-pool 8x8 == mean over H,W
         if name == 'cifar10':
             h = linear_fc(P, 'discriminator/lin', h)
         else:
@@ -488,7 +549,7 @@ class OracleModel:
         P, S, name = self.P, self.S, self.cfg.DATA_NAME
         if name == 'cifar10':    # Good_GAN_cifar10.py:101-174
             x = inp.reshape(-1, 32, 32, 3)
-            x = x + 0.15 * rng.normal(tag + '/noise', x.shape).to(x.dtype)
+            x = q(x + 0.15 * rng.normal(tag + '/noise', x.shape).to(x.dtype))
             for n in ['conv1_1', 'conv1_2', 'conv1_3']:
                 x = self._cap(tag + '/' + n, conv2d_WN(P, S, 'classifier/' + n, x, 'SAME', train))
             x = max_pool_tf(x, 2, 2)
@@ -507,10 +568,10 @@ class OracleModel:
             return dense_WN(P, S, 'classifier/output_dense', x, train, None), inter
         # Good_GAN.py:216-247 (mnist) / :249-299 (svhn): conv(bias) -> leaky_relu -> BN
         blk = lambda c, b, x: bn_contrib(P, S, 'classifier/' + b,
-                                         leaky_relu_tf(conv2d_layer(P, 'classifier/' + c, x, 1)), train)
+                                         qc(leaky_relu_tf(conv2d_layer(P, 'classifier/' + c, x, 1))), train)
         if name == 'mnist':
             x = inp.reshape(-1, 28, 28, 1)
-            x = x + 0.3 * rng.normal(tag + '/noise', x.shape).to(x.dtype)
+            x = q(x + 0.3 * rng.normal(tag + '/noise', x.shape).to(x.dtype))
             x = max_pool_tf(blk('c_h0_conv0', 'c_h0_bn0', x), 2, 2)
             if train:
                 x = dropout_tf(x, rng.keep_mask(tag + '/drop1', x.shape, 0.5), 0.5)
@@ -537,14 +598,16 @@ class OracleModel:
             for i in range(2):   # NN_Base._nin (modle_base.py:204-209)
                 s = x.shape
                 h = WN_dense(P, 'classifier/c_h2_nin%d' % i, x.reshape(-1, s[-1])).reshape(s[0], s[1], s[2], -1)
-                x = bn_contrib(P, S, 'classifier/c_h2_bn%d' % (i + 1), leaky_relu_tf(h), train)
-        fm = x.mean(dim=(1, 2))
+                x = bn_contrib(P, S, 'classifier/c_h2_bn%d' % (i + 1), qc(leaky_relu_tf(h)), train)
+        fm = q(x.mean(dim=(1, 2)))
         h = linear_fc(P, 'classifier/c_h2_lin', fm)
         return bn_contrib(P, S, 'classifier/c_h3_bn0', h, train), fm
 
     def zca_apply(self, x):
         """cifar10_ZCA.apply (Good_GAN_cifar10.py:294-299)."""
         mean, mat = self.zca
+        if _QUANT:      # CUDA path: x @ mat on the tensor cores, -(mean @ mat) rides in the epilogue
+            return qc(matmul_tf(x.reshape(x.shape[0], -1), mat) - mean @ mat).reshape(x.shape)
         return ((x.reshape(x.shape[0], -1) - mean) @ mat).reshape(x.shape)
 
     def forward_pass(self, z_g, y_g, x_l_c, y_l_c, x_l_d, y_l_d, x_u_d, x_u_c, train, rng, tag='F'):

@@ -40,6 +40,11 @@ CASES = [
     dict(N=2, H=32, W=32, Cin=3, Cout=128, k=3, s=1, pad='SAME'),     # conv1_1: K = 3 channels
     dict(N=4, H=28, W=28, Cin=32, Cout=64, k=3, s=1, pad='SAME'),     # MNIST extent (not a power of two)
     dict(N=300, H=1, W=1, Cin=110, Cout=136, k=1, s=1, pad='SAME'),   # dense (tf.matmul)
+    dict(N=2, H=16, W=16, Cin=256, Cout=256, k=3, s=1, pad='SAME'),   # conv2_2: Cin 256 -> wgrad N tile 256
+    dict(N=3, H=8, W=8, Cin=256, Cout=512, k=3, s=1, pad='VALID'),    # conv3 at its real channel counts
+    dict(N=16, H=6, W=6, Cin=512, Cout=256, k=1, s=1, pad='SAME'),    # NiN1
+    dict(N=16, H=6, W=6, Cin=256, Cout=128, k=1, s=1, pad='SAME'),    # NiN2
+    dict(N=16, H=1, W=1, Cin=110, Cout=8192, k=1, s=1, pad='SAME'),   # G fc 110 -> 8192 (32 N-tiles)
 ]
 
 
