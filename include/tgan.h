@@ -86,7 +86,7 @@ typedef struct {
 } tgan_igemm_args;
 int tgan_igemm_bf16(const tgan_igemm_args* a, void* stream);
 
-/* wgrad on tensor cores: dW[t][co][ci] (+)= sum_{n,oy,ox} dz[n,oy,ox,co] * x[n, oy + dy[t], ox + dx[t], ci]
+/* wgrad on tensor cores: dW[t][ci][co] (+)= sum_{n,oy,ox} dz[n,oy,ox,co] * x[n, oy + dy[t], ox + dx[t], ci]
  * (pixel dimension is the GEMM K; both operands are MN-major UMMA operands loaded by TMA).
  * Writes fp32 partials with split-K over pixels followed by a deterministic reduce. */
 typedef struct {
@@ -96,8 +96,8 @@ typedef struct {
   int H, W, Cin, ldx;
   int sy, sx;          /* x traversal stride (0 = 1): x[n, oy*sy + dy[t], ox*sx + dx[t], ci] */
   int T; int dy[25], dx[25];
-  float* dw;           /* fp32, element (t, co, ci) at dw[t*dw_st + co*dw_sco + ci*dw_sci]; dw = beta*dw + sum */
-  int64_t dw_st, dw_sco, dw_sci;
+  float* dw;           /* fp32 [T][Cin][Cout] (== HWIO for a conv; == [kh,kw,Cout,Cin] of a transposed conv when
+                          the operand roles are exchanged); dw = beta*dw + sum */
   float beta;
   float* ws; int64_t ws_bytes;
 } tgan_wgrad_args;

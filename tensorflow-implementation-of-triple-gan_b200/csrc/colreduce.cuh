@@ -47,19 +47,35 @@ __global__ void __launch_bounds__(32 * RY) colreduce_kernel(F f, int64_t rows, i
   }
 }
 
-// out[a][c] = beta*out[a][c] + sum_p partials[p][a][c]
+// out[a][c] = beta*out[a][c] + sum_p partials[p][a][c].  (32 channels x 8 part-lanes) per CTA: the partial
+// loads of one channel are spread over 8 threads and issued back to back (MLP), then folded in a fixed order.
 template <int NACC>
-__global__ void colreduce_final_kernel(const float* __restrict__ partials, int parts, int C, float* o0, float* o1,
-                                       float beta) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+__global__ void __launch_bounds__(32 * RY) colreduce_final_kernel(const float* __restrict__ partials, int parts, int C,
+                                                                  float* o0, float* o1, float beta) {
+  __shared__ float sm[RY][NACC][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float acc[NACC];
 #pragma unroll
-  for (int a = 0; a < NACC; ++a) {
-    float* o = a == 0 ? o0 : o1;
-    if (!o) continue;
-    float s = 0.f;
-    for (int p = 0; p < parts; ++p) s += partials[((int64_t)p * NACC + a) * C + c];
-    o[c] = (beta != 0.f ? beta * o[c] : 0.f) + s;
+  for (int a = 0; a < NACC; ++a) acc[a] = 0.f;
+  if (c < C) {
+    for (int p = threadIdx.y; p < parts; p += RY) {
+#pragma unroll
+      for (int a = 0; a < NACC; ++a) acc[a] += partials[((int64_t)p * NACC + a) * C + c];
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < NACC; ++a) sm[threadIdx.y][a][threadIdx.x] = acc[a];
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) {
+      float* o = a == 0 ? o0 : o1;
+      if (!o) continue;
+      float s = 0.f;
+#pragma unroll
+      for (int y = 0; y < RY; ++y) s += sm[y][a][threadIdx.x];
+      o[c] = (beta != 0.f ? beta * o[c] : 0.f) + s;
+    }
   }
 }
 
@@ -82,7 +98,7 @@ static int run_colreduce(F1 f1, F4 f4, bool vec_ok, int64_t rows, int C, float* 
   if (vec_ok) colreduce_kernel<NACC, 4, F4><<<grid, block, 0, st>>>(f4, rows, C, ws);
   else colreduce_kernel<NACC, 1, F1><<<grid, block, 0, st>>>(f1, rows, C, ws);
   TGAN_LAUNCHED();
-  colreduce_final_kernel<NACC><<<ceil_div(C, 128), 128, 0, st>>>(ws, parts, C, o0, o1, beta);
+  colreduce_final_kernel<NACC><<<ceil_div(C, 32), dim3(32, RY), 0, st>>>(ws, parts, C, o0, o1, beta);
   TGAN_LAUNCHED();
   return 0;
 }

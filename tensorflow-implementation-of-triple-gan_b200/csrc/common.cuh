@@ -67,6 +67,35 @@ template <> __device__ __forceinline__ void st4<bf16>(bf16* p, int64_t i, const 
   *reinterpret_cast<uint2*>(p + i) = t;
 }
 
+// compile-time activation (elementwise kernels are instantiated per activation so that no predicated-off
+// transcendental code is issued)
+template <int ACT> __device__ __forceinline__ float act_fwd_t(float u, float alpha) {
+  if constexpr (ACT == TGAN_ACT_RELU) return u > 0.f ? u : 0.f;
+  else if constexpr (ACT == TGAN_ACT_LRELU) return u > 0.f ? u : alpha * u;
+  else if constexpr (ACT == TGAN_ACT_TANH) return tanhf(u);
+  else if constexpr (ACT == TGAN_ACT_SIGMOID) return 1.f / (1.f + expf(-u));
+  else if constexpr (ACT == TGAN_ACT_SOFTPLUS) return u > 20.f ? u : log1pf(expf(u));
+  else return u;
+}
+template <int ACT> __device__ __forceinline__ float act_grad_from_y_t(float y, float alpha) {
+  if constexpr (ACT == TGAN_ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  else if constexpr (ACT == TGAN_ACT_LRELU) return y > 0.f ? 1.f : (y < 0.f ? alpha : 0.f);
+  else if constexpr (ACT == TGAN_ACT_TANH) return 1.f - y * y;
+  else if constexpr (ACT == TGAN_ACT_SIGMOID) return y * (1.f - y);
+  else if constexpr (ACT == TGAN_ACT_SOFTPLUS) return 1.f - expf(-y);
+  else return 1.f;
+}
+#define TGAN_DISPATCH_ACT(act, A, ...)                                        \
+  switch (act) {                                                               \
+    case TGAN_ACT_NONE: { constexpr int A = TGAN_ACT_NONE; __VA_ARGS__; } break;         \
+    case TGAN_ACT_RELU: { constexpr int A = TGAN_ACT_RELU; __VA_ARGS__; } break;         \
+    case TGAN_ACT_LRELU: { constexpr int A = TGAN_ACT_LRELU; __VA_ARGS__; } break;       \
+    case TGAN_ACT_TANH: { constexpr int A = TGAN_ACT_TANH; __VA_ARGS__; } break;         \
+    case TGAN_ACT_SIGMOID: { constexpr int A = TGAN_ACT_SIGMOID; __VA_ARGS__; } break;   \
+    case TGAN_ACT_SOFTPLUS: { constexpr int A = TGAN_ACT_SOFTPLUS; __VA_ARGS__; } break; \
+    default: tgan::set_error("bad activation %d", (int)(act)); return 1;      \
+  }
+
 __device__ __forceinline__ float act_fwd(float u, int act, float alpha) {
   switch (act) {
     case TGAN_ACT_RELU: return u > 0.f ? u : 0.f;

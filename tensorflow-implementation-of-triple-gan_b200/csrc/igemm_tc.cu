@@ -13,6 +13,7 @@
 //                    split-K over pixel tiles + deterministic second-stage reduction.
 //
 // Roofline: tensor pipe (bf16 in, fp32 accumulate).  Algorithmic FLOPs per launch = 2 * pixels * T * C * Nout.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -59,10 +60,19 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* d
 // implicit-GEMM kernel
 // ------------------------------------------------------------------------------------------------
 constexpr int IG_THREADS = 192;          // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
-constexpr int A_STAGE_BYTES = 128 * 128; // 128 pixels x 64 bf16
+constexpr int W_STAGE_BYTES = 128 * 128; // 128 output channels x 64 bf16 (UMMA A operand, M = 128)
+constexpr int P_TILE_BYTES = 128 * 128;  // 128 pixels x 64 bf16
+constexpr int IG_NPIX = 256;             // pixels per CTA tile = UMMA N (two 128-pixel TMA boxes)
+constexpr int IG_STAGE_BYTES = W_STAGE_BYTES + 2 * P_TILE_BYTES;
+constexpr int IG_STAGES = 4;
 
+// Orientation: D[co, pixel] = W[co, k] * X[pixel, k]^T.  The OUTPUT CHANNELS are the UMMA M dimension (TMEM lanes) and
+// 256 PIXELS are the UMMA N dimension: measured on B200, one cta_group::1 tcgen05.mma (M=128, K=16, smem operands)
+// retires every ~82 ns for any N <= 256, so only N = 256 instructions reach the tensor-pipe rate; with the pixels on N
+// every layer (Cout = 32 ... 512) issues full-width MMAs, and per-channel epilogue work (bias, column sums for the
+// batch-norm statistics) is per-THREAD state instead of cross-lane reductions.
 struct IgParams {
-  int N, th, tw, nb, tiles_y, tiles_x, m_tiles, n_tiles, BN, T, kchunks, klast, stages, sy, sx;
+  int N, th, tw, nb, ltw, lppi, tiles_y, tiles_x, m_tiles, pp_tiles, ct_tiles, T, kchunks, klast, sy, sx;
   int dy[25], dx[25];
   void* out;
   int odt, OH, OW, ldo, osy, osx, ooy, oox, vh, vw, Nout;
@@ -70,161 +80,193 @@ struct IgParams {
   float* colsum;
   int act;
   float alpha;
+  int dbg;   // experiments only (TGAN_IGEMM_DBG): 1 skip activation loads, 2 skip weight loads, 4 skip stores
 };
 
+// Store one chunk of 32 consecutive tile pixels for this thread's output channel.  TW = min(tile width, 32) is a
+// compile-time constant so that every pixel's offset is `segment base + constant * pixel step`: the epilogue warps
+// run alone on their scheduler (no latency hiding), so per-element dependent integer chains would dominate the tile.
+template <int TW, typename TO>
+__device__ __forceinline__ void ig_store_chunk(const IgParams& p, TO* __restrict__ out, const float (&v)[32], int pbase,
+                                               int tx, int ty, int ng, int co, bool cvalid, float& csum) {
+  const int ppi = p.th * p.tw;
+  const int pstep = p.osx * p.ldo;
+#pragma unroll
+  for (int sgm = 0; sgm < 32 / TW; ++sgm) {
+    const int pix = pbase + sgm * TW;
+    const int nl = pix >> p.lppi, rem = pix & (ppi - 1);
+    const int oy = ty * p.th + (rem >> p.ltw), ox0 = tx * p.tw + (rem & (p.tw - 1)), n = ng * p.nb + nl;
+    const bool rowok = cvalid && (n < p.N) && (oy < p.vh);
+    const int base = ((n * p.OH + (oy * p.osy + p.ooy)) * p.OW + (ox0 * p.osx + p.oox)) * p.ldo + co;
+    const int lim = p.vw - ox0;          // pixel jc is inside the valid width iff jc < lim
+#pragma unroll
+    for (int jc = 0; jc < TW; ++jc) {
+      const bool ok = rowok && (jc < lim);
+      const float x = v[sgm * TW + jc];
+      if (p.colsum) csum += ok ? x : 0.f;
+      if (ok) {
+        if constexpr (sizeof(TO) == 2) out[base + jc * pstep] = __float2bfloat16_rn(x);
+        else out[base + jc * pstep] = x;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(IG_THREADS, 1)
-igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
              const __grid_constant__ IgParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int stages = p.stages, BN = p.BN;
-  const uint32_t b_stage_bytes = (uint32_t)BN * 128u;
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + (size_t)stages * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)stages * b_stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)IG_STAGES * IG_STAGE_BYTES);
   uint64_t* full = bars;
-  uint64_t* empty = bars + stages;
-  uint64_t* tfull = bars + 2 * stages;
+  uint64_t* empty = bars + IG_STAGES;
+  uint64_t* tfull = bars + 2 * IG_STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tmem_cols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < IG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
     fence_barrier_init();
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
   }
-  if (warp == 0) { tmem_alloc(tmem_slot, tmem_cols); tmem_relinquish(); }
+  if (warp == 0) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }   // 2 accumulators x 256 fp32 columns
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int total_tiles = p.pp_tiles * p.ct_tiles;
   const int ksteps = p.T * p.kchunks;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
 
+  // Producer and MMA-issuer warps run their loops with ALL 32 lanes (warp-uniform control flow keeps addresses and
+  // descriptors in uniform registers); only the TMA / tcgen05 instructions themselves are issued by one elected lane.
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
-        const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, ng = mt / (p.tiles_x * p.tiles_y);
-        const int x0 = tx * p.tw * p.sx, y0 = ty * p.th * p.sy, n0 = ng * p.nb;
-        for (int t = 0; t < p.T; ++t) {
-          for (int kc = 0; kc < p.kchunks; ++kc) {
-            mbar_wait(&empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full[stage], A_STAGE_BYTES + b_stage_bytes);
-            tma_load_4d(sA + (size_t)stage * A_STAGE_BYTES, &tmA, &full[stage], kc * 64, x0 + p.dx[t], y0 + p.dy[t], n0);
-            tma_load_3d(sB + (size_t)stage * b_stage_bytes, &tmB, &full[stage], kc * 64, nt * BN, t);
-            if (++stage == stages) { stage = 0; phase ^= 1; }
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int ct = tile % p.ct_tiles, pp = tile / p.ct_tiles;
+      int x0[2], y0[2], n0[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int mt = 2 * pp + h;       // mt >= m_tiles -> image index >= N -> the box is zero-filled
+        x0[h] = (mt % p.tiles_x) * p.tw * p.sx;
+        y0[h] = ((mt / p.tiles_x) % p.tiles_y) * p.th * p.sy;
+        n0[h] = (mt / tiles_per_img) * p.nb;
+      }
+      for (int t = 0; t < p.T; ++t) {
+        const int ddx = p.dx[t], ddy = p.dy[t];
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (elect_one()) {
+            uint8_t* s = smem + (size_t)stage * IG_STAGE_BYTES;
+            mbar_arrive_expect_tx(&full[stage], ((p.dbg & 2) ? 0u : (uint32_t)W_STAGE_BYTES) + ((p.dbg & 1) ? 0u : 2u * P_TILE_BYTES));
+            if (!(p.dbg & 2)) tma_load_3d(s, &tmW, &full[stage], kc * 64, ct * 128, t);
+            if (!(p.dbg & 1)) {
+              tma_load_4d(s + W_STAGE_BYTES, &tmX, &full[stage], kc * 64, x0[0] + ddx, y0[0] + ddy, n0[0]);
+              tma_load_4d(s + W_STAGE_BYTES + P_TILE_BYTES, &tmX, &full[stage], kc * 64, x0[1] + ddx, y0[1] + ddy, n0[1]);
+            }
           }
+          __syncwarp();
+          if (++stage == IG_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
-      int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t accphase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty[acc], accphase ^ 1);
+    const uint32_t idesc = umma_idesc_bf16(128, IG_NPIX, 0, 0);
+    // K-major SWIZZLE_128B descriptor: LBO field 1 (unused), SBO = 1024 B (8 rows), version 1, layout 2
+    const uint64_t desc_hi = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+    const uint32_t s_base = smem_u32(smem) >> 4;
+    int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t accphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[acc], accphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * IG_NPIX);
+      int kc = 0;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int ks = 0; ks < ksteps; ++ks) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const int nk = ((ks % p.kchunks) == p.kchunks - 1) ? p.klast : 4;
-          const uint32_t a_addr = smem_u32(sA + (size_t)stage * A_STAGE_BYTES);
-          const uint32_t b_addr = smem_u32(sB + (size_t)stage * b_stage_bytes);
-          for (int k = 0; k < nk; ++k) {
-            // K-major SWIZZLE_128B: 8-row groups 1024 B apart; a K step of 16 bf16 = +32 B inside the atom
-            umma_bf16(d_tmem, umma_smem_desc(a_addr + k * 32, 16, 1024), umma_smem_desc(b_addr + k * 32, 16, 1024),
-                      idesc, (ks | k) ? 1u : 0u);
+        const uint32_t a_lo = s_base + (uint32_t)stage * (IG_STAGE_BYTES >> 4);
+        const uint32_t b_lo = a_lo + (W_STAGE_BYTES >> 4);
+        const bool last = (++kc == p.kchunks);
+        if (last) kc = 0;
+        if (elect_one()) {
+          // a K step of 16 bf16 = +32 B inside the 128 B swizzle atom = +2 in the (>>4) start-address field
+          if (!last || p.klast == 4) {
+            umma_bf16(d_tmem, desc_hi | (uint64_t)(a_lo + 0), desc_hi | (uint64_t)(b_lo + 0), idesc, ks ? 1u : 0u);
+            umma_bf16(d_tmem, desc_hi | (uint64_t)(a_lo + 2), desc_hi | (uint64_t)(b_lo + 2), idesc, 1u);
+            umma_bf16(d_tmem, desc_hi | (uint64_t)(a_lo + 4), desc_hi | (uint64_t)(b_lo + 4), idesc, 1u);
+            umma_bf16(d_tmem, desc_hi | (uint64_t)(a_lo + 6), desc_hi | (uint64_t)(b_lo + 6), idesc, 1u);
+          } else {
+            for (int k = 0; k < p.klast; ++k)
+              umma_bf16(d_tmem, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc, (ks | k) ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);          // smem slot reusable once these MMAs retire
-          if (++stage == stages) { stage = 0; phase ^= 1; }
+          umma_commit(&empty[stage]);                     // smem slot reusable once these MMAs retire
+          if (ks == ksteps - 1) umma_commit(&tfull[acc]); // accumulator complete -> epilogue
         }
-        umma_commit(&tfull[acc]);              // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; accphase ^= 1; }
+        __syncwarp();
+        if (++stage == IG_STAGES) { stage = 0; phase ^= 1; }
       }
+      if (++acc == 2) { acc = 0; accphase ^= 1; }
     }
   } else {
-    // ---- epilogue: TMEM -> registers -> (bias, activation, column sums) -> global ----
+    // ---- epilogue: thread = one output channel (TMEM lane), 32 consecutive pixels per tcgen05.ld ----
     const int q = warp & 3;                    // TMEM lane quadrant this warp may access
-    const int row = q * 32 + lane;
-    const int pix_per_img = p.th * p.tw;
+    const int ppi = p.th * p.tw;               // pixels per image inside a 128-pixel tile (power of two)
     int acc = 0; uint32_t accphase = 0;
-    const bool vec_ok = (p.odt == TGAN_BF16) ? ((p.ldo % 8 == 0) && (p.Nout % 8 == 0)) : ((p.ldo % 4 == 0) && (p.Nout % 4 == 0));
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
-      const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, ng = mt / (p.tiles_x * p.tiles_y);
-      const int nl = row / pix_per_img, rem = row % pix_per_img;
-      const int oy = ty * p.th + rem / p.tw, ox = tx * p.tw + rem % p.tw, n = ng * p.nb + nl;
-      const bool rvalid = (n < p.N) && (oy < p.vh) && (ox < p.vw);
-      const int64_t poff = rvalid ? (((int64_t)n * p.OH + (oy * p.osy + p.ooy)) * p.OW + (ox * p.osx + p.oox)) * p.ldo : 0;
+      const int ct = tile % p.ct_tiles, pp = tile / p.ct_tiles;
+      const int co = ct * 128 + q * 32 + lane;
+      const bool cvalid = co < p.Nout;
+      const float bias = (p.bias && cvalid) ? p.bias[co] : 0.f;
+      float csum = 0.f;
       mbar_wait(&tfull[acc], accphase);
       tc_fence_after();
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        const int colbase = nt * BN + c0;
-        if (colbase >= p.Nout) break;
+      for (int c0 = 0; c0 < IG_NPIX; c0 += 32) {
+        const int mt = 2 * pp + (c0 >> 7);
+        if (mt >= p.m_tiles) break;
+        const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, ng = mt / tiles_per_img;
         uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * IG_NPIX + c0), r);
         tmem_ld_wait();
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(r[j]) * p.alpha;
-          const int col = colbase + j;
-          if (p.bias && col < p.Nout) x += p.bias[col];
-          v[j] = act_fwd(x, p.act, 0.2f);
-        }
-        if (p.colsum) {
-          float mine = 0.f;
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha + bias;
+        // optional stages sit behind warp-uniform branches (no predicated-off transcendental code in the hot path)
+        if (p.act == TGAN_ACT_LRELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float s = warp_sum(rvalid ? v[j] : 0.f);
-            if (lane == j) mine = s;
-          }
-          if (colbase + lane < p.Nout) atomicAdd(&p.colsum[colbase + lane], mine);
+          for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
+        } else if (p.act == TGAN_ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (p.act != TGAN_ACT_NONE) {
+#pragma unroll 1
+          for (int j = 0; j < 32; ++j) v[j] = act_fwd(v[j], p.act, 0.2f);
         }
-        if (rvalid) {
+        const int pbase = c0 & 127;
+        if (!(p.dbg & 4)) {
           if (p.odt == TGAN_BF16) {
-            bf16* o = reinterpret_cast<bf16*>(p.out) + poff + colbase;
-            if (vec_ok) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                if (colbase + g * 8 < p.Nout) {
-                  uint4 u;
-                  __nv_bfloat162 h0 = __floats2bfloat162_rn(v[g * 8 + 0], v[g * 8 + 1]);
-                  __nv_bfloat162 h1 = __floats2bfloat162_rn(v[g * 8 + 2], v[g * 8 + 3]);
-                  __nv_bfloat162 h2 = __floats2bfloat162_rn(v[g * 8 + 4], v[g * 8 + 5]);
-                  __nv_bfloat162 h3 = __floats2bfloat162_rn(v[g * 8 + 6], v[g * 8 + 7]);
-                  u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-                  u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-                  *reinterpret_cast<uint4*>(o + g * 8) = u;
-                }
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (colbase + j < p.Nout) o[j] = __float2bfloat16_rn(v[j]);
+            bf16* o = reinterpret_cast<bf16*>(p.out);
+            switch (p.ltw) {
+              case 2: ig_store_chunk<4>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum); break;
+              case 3: ig_store_chunk<8>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum); break;
+              case 4: ig_store_chunk<16>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum); break;
+              default: ig_store_chunk<32>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum); break;
             }
           } else {
-            float* o = reinterpret_cast<float*>(p.out) + poff + colbase;
-            if (vec_ok) {
-#pragma unroll
-              for (int g = 0; g < 8; ++g)
-                if (colbase + g * 4 < p.Nout)
-                  *reinterpret_cast<float4*>(o + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (colbase + j < p.Nout) o[j] = v[j];
+            float* o = reinterpret_cast<float*>(p.out);
+            switch (p.ltw) {
+              case 2: ig_store_chunk<4>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum); break;
+              case 3: ig_store_chunk<8>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum); break;
+              case 4: ig_store_chunk<16>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum); break;
+              default: ig_store_chunk<32>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum); break;
             }
           }
         }
       }
+      if (p.colsum && cvalid) atomicAdd(&p.colsum[co], csum);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -233,7 +275,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -246,7 +288,7 @@ struct WgParams {
   int N, bh, bw, bn, ptiles_y, ptiles_x, p_tiles;   // pixel tiling (K axis)
   int co_tiles, ci_tiles, BNc, tg, tap_groups, T, splits, stages, sy, sx;
   int dy[25], dx[25];
-  float* ws;            // [splits][T][Cout][Cin]
+  float* ws;            // [splits][T][Cin][Cout]
   int Cout, Cin;
 };
 
@@ -290,12 +332,12 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ C
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int pt = pt0; pt < pt1; ++pt) {
-        const int tx = pt % p.ptiles_x, ty = (pt / p.ptiles_x) % p.ptiles_y, ng = pt / (p.ptiles_x * p.ptiles_y);
-        const int ox0 = tx * p.bw, oy0 = ty * p.bh, n0 = ng * p.bn;
-        mbar_wait(&empty[stage], phase ^ 1);
+    int stage = 0; uint32_t phase = 0;
+    for (int pt = pt0; pt < pt1; ++pt) {
+      const int tx = pt % p.ptiles_x, ty = (pt / p.ptiles_x) % p.ptiles_y, ng = pt / (p.ptiles_x * p.ptiles_y);
+      const int ox0 = tx * p.bw, oy0 = ty * p.bh, n0 = ng * p.bn;
+      mbar_wait(&empty[stage], phase ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&full[stage], (uint32_t)(2 + nt * nbB) * WG_BOX_BYTES);   // exact: last group may be short
         uint8_t* s = smem + (size_t)stage * stage_bytes;
         tma_load_4d(s, &tmDz, &full[stage], cot * 128, ox0, oy0, n0);
@@ -304,33 +346,38 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ C
           for (int bb = 0; bb < nbB; ++bb)
             tma_load_4d(s + (size_t)(2 + j * nbB + bb) * WG_BOX_BYTES, &tmX, &full[stage], cit * p.BNc + bb * 64,
                         ox0 * p.sx + p.dx[t0 + j], oy0 * p.sy + p.dy[t0 + j], n0);
-        if (++stage == stages) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == stages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, p.BNc, 1, 1);
-      int stage = 0; uint32_t phase = 0;
-      bool first = true;
-      for (int pt = pt0; pt < pt1; ++pt) {
-        mbar_wait(&full[stage], phase);
-        tc_fence_after();
-        const uint32_t s = smem_u32(smem + (size_t)stage * stage_bytes);
-        for (int j = 0; j < nt; ++j) {
-          const uint32_t b_addr = s + (uint32_t)(2 + j * nbB) * WG_BOX_BYTES;
-#pragma unroll
-          for (int k = 0; k < WG_KP / 16; ++k) {
-            // MN-major SWIZZLE_128B: LBO = distance between 64-channel boxes, SBO = 8 pixel rows = 1024 B;
-            // a K step of 16 pixels = 2 row groups = +2048 B
-            umma_bf16(tmem_base + (uint32_t)(j * p.BNc), umma_smem_desc(s + k * 2048, WG_BOX_BYTES, 1024),
-                      umma_smem_desc(b_addr + k * 2048, WG_BOX_BYTES, 1024), idesc, (first && k == 0) ? 0u : 1u);
-          }
+    const int span = max(1, 256 / p.BNc);
+    const uint32_t idesc = umma_idesc_bf16(128, span * p.BNc, 1, 1);
+    // MN-major SWIZZLE_128B: LBO = distance between 64-channel boxes, SBO = 8 pixel rows = 1024 B
+    const uint64_t desc_hi = ((uint64_t)(WG_BOX_BYTES >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+    const uint32_t s_base = smem_u32(smem) >> 4;
+    int stage = 0; uint32_t phase = 0;
+    for (int pt = pt0; pt < pt1; ++pt) {
+      mbar_wait(&full[stage], phase);
+      tc_fence_after();
+      const uint32_t s = s_base + (uint32_t)stage * (stage_bytes >> 4);
+      if (elect_one()) {
+        // consecutive taps are consecutive 64-channel boxes in smem and consecutive column blocks in TMEM, so one
+        // MMA spans `span` taps: N = span*BNc <= 256 (an MMA costs the same ~82 ns for any N <= 256)
+        for (int j = 0; j < nt; j += span) {
+          const int sp = min(span, nt - j);
+          const uint32_t b_lo = s + (uint32_t)(2 + j * nbB) * (WG_BOX_BYTES >> 4);
+          const uint32_t d = tmem_base + (uint32_t)(j * p.BNc);
+          const uint32_t id = sp == span ? idesc : umma_idesc_bf16(128, sp * p.BNc, 1, 1);
+          // a K step of 16 pixels = 2 row groups = +2048 B = +128 in the (>>4) start-address field
+          umma_bf16(d, desc_hi | (uint64_t)(s + 0), desc_hi | (uint64_t)(b_lo + 0), id, pt > pt0 ? 1u : 0u);
+          umma_bf16(d, desc_hi | (uint64_t)(s + 128), desc_hi | (uint64_t)(b_lo + 128), id, 1u);
         }
-        first = false;
         umma_commit(&empty[stage]);
-        if (++stage == stages) { stage = 0; phase ^= 1; }
+        if (pt == pt1 - 1) umma_commit(done);
       }
-      umma_commit(done);
+      __syncwarp();
+      if (++stage == stages) { stage = 0; phase ^= 1; }
     }
   } else {
     const int q = warp & 3;
@@ -352,9 +399,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ C
           for (int i = 0; i < 32; ++i) r[i] = 0u;
         }
         if (co < p.Cout) {
-          float* o = p.ws + (((int64_t)split * p.T + (t0 + j)) * p.Cout + co) * p.Cin + ci0;
+          // partial layout [split][t][ci][co]: for a fixed ci the 32 lanes write 32 consecutive co (one 128 B line)
+          float* o = p.ws + (((int64_t)split * p.T + (t0 + j)) * p.Cin + ci0) * p.Cout + co;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) if (ci0 + i < p.Cin) o[i] = __uint_as_float(r[i]);
+          for (int i = 0; i < 32; ++i) if (ci0 + i < p.Cin) o[(int64_t)i * p.Cout] = __uint_as_float(r[i]);
         }
       }
     }
@@ -364,19 +412,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ C
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
 }
 
-// dst[t*st + co*sco + ci*sci] = beta*dst + sum_splits ws[s][t][co][ci]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int T, int Cout, int Cin,
-                                    float* __restrict__ dw, int64_t st, int64_t sco, int64_t sci, float beta) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t tot = (int64_t)T * Cout * Cin;
-  if (i >= tot) return;
-  float s = 0.f;
-  for (int z = 0; z < splits; ++z) s += ws[z * tot + i];
-  const int ci = (int)(i % Cin);
-  const int co = (int)((i / Cin) % Cout);
-  const int t = (int)(i / ((int64_t)Cin * Cout));
-  float* o = dw + t * st + co * sco + ci * sci;
-  *o = (beta != 0.f ? beta * (*o) : 0.f) + s;
+// dw[i] = beta*dw[i] + sum_splits ws[s][i]  (i over [T][Cin][Cout], same layout in and out -> fully coalesced)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int64_t tot, float* __restrict__ dw,
+                                    float beta) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += ws[z * tot + i];
+    dw[i] = (beta != 0.f ? beta * dw[i] : 0.f) + s;
+  }
 }
 
 // dst[t][n][k] (bf16, k < Kpad) = k < K ? src[tap(t)*st + n*sn + k*sk] : 0
@@ -394,7 +437,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, bf16* __restri
 
 static void pick_tile(int gh, int gw, int& th, int& tw, int& nb, int total) {
   if (gh == 1) { tw = total; th = 1; nb = 1; return; }
-  tw = 1; while (tw < gw && tw < total) tw <<= 1;
+  tw = 4; while (tw < gw && tw < total) tw <<= 1;   // >= 4: the epilogue is specialised for tile widths 4, 8, 16, >= 32
   th = 1; while (th < gh && th * tw < total) th <<= 1;
   nb = total / (tw * th);
 }
@@ -414,37 +457,38 @@ extern "C" int tgan_igemm_bf16(const tgan_igemm_args* a, void* stream) {
   const int sy = a->sy > 0 ? a->sy : 1, sx = a->sx > 0 ? a->sx : 1;
   pick_tile(a->gh, a->gw, p.th, p.tw, p.nb, 128);
   TGAN_CHECK_ARG(p.tw * sx <= 256 && p.th * sy <= 256, "igemm: strided box too large");
+  TGAN_CHECK_ARG(p.tw >= 4, "igemm: output grid narrower than 4 pixels is not supported");
+  TGAN_CHECK_ARG((int64_t)a->N * a->OH * a->OW * a->ldo < (1ll << 31), "igemm: output larger than 2^31 elements");
+  p.ltw = 0; while ((1 << p.ltw) < p.tw) ++p.ltw;
+  p.lppi = 0; while ((1 << p.lppi) < p.tw * p.th) ++p.lppi;
   p.N = a->N; p.sy = sy; p.sx = sx;
   p.tiles_y = ceil_div(a->gh, p.th); p.tiles_x = ceil_div(a->gw, p.tw);
   p.m_tiles = ceil_div(a->N, p.nb) * p.tiles_y * p.tiles_x;
-  p.BN = a->Nout <= 32 ? 32 : a->Nout <= 64 ? 64 : a->Nout <= 128 ? 128 : 256;
-  p.n_tiles = ceil_div(a->Nout, p.BN);
+  p.pp_tiles = ceil_div(p.m_tiles, 2);
+  p.ct_tiles = ceil_div(a->Nout, 128);
   p.T = a->T; p.kchunks = ceil_div(a->C, 64);
   p.klast = ceil_div(a->C - (p.kchunks - 1) * 64, 16);
   for (int t = 0; t < a->T; ++t) { p.dy[t] = a->dy[t]; p.dx[t] = a->dx[t]; }
   p.out = a->out; p.odt = a->odt; p.OH = a->OH; p.OW = a->OW; p.ldo = a->ldo;
   p.osy = a->osy > 0 ? a->osy : 1; p.osx = a->osx > 0 ? a->osx : 1; p.ooy = a->ooy; p.oox = a->oox;
   p.vh = a->vh > 0 ? a->vh : a->gh; p.vw = a->vw > 0 ? a->vw : a->gw; p.Nout = a->Nout;
+  { const char* e = getenv("TGAN_IGEMM_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.bias = a->bias; p.colsum = a->colsum; p.act = a->act; p.alpha = a->alpha == 0.f ? 1.f : a->alpha;
-  const size_t stage_bytes = A_STAGE_BYTES + (size_t)p.BN * 128;
-  int stages = (int)((232448 - 2048) / stage_bytes);
-  if (stages > 8) stages = 8;
-  p.stages = stages;
-  const size_t smem_bytes = 1024 + stages * stage_bytes + 256;
+  const size_t smem_bytes = 1024 + (size_t)IG_STAGES * IG_STAGE_BYTES + 256;
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmX, tmW;
   {
     uint64_t dims[4] = {(uint64_t)a->C, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->N};
     uint64_t str[3] = {(uint64_t)a->ldx * 2, (uint64_t)a->W * a->ldx * 2, (uint64_t)a->H * a->W * a->ldx * 2};
     uint32_t box[4] = {64, (uint32_t)(p.tw * sx), (uint32_t)(p.th * sy), (uint32_t)p.nb};
     uint32_t es[4] = {1, (uint32_t)sx, (uint32_t)sy, 1};
-    if (make_tmap_bf16(&tmA, a->x, 4, dims, str, box, es)) return 1;
+    if (make_tmap_bf16(&tmX, a->x, 4, dims, str, box, es)) return 1;
   }
   {
     uint64_t dims[3] = {(uint64_t)a->Kpad, (uint64_t)a->Nout, (uint64_t)a->T};
     uint64_t str[2] = {(uint64_t)a->Kpad * 2, (uint64_t)a->Nout * a->Kpad * 2};
-    uint32_t box[3] = {64, (uint32_t)p.BN, 1};
-    if (make_tmap_bf16(&tmB, a->wp, 3, dims, str, box, nullptr)) return 1;
+    uint32_t box[3] = {64, 128, 1};
+    if (make_tmap_bf16(&tmW, a->wp, 3, dims, str, box, nullptr)) return 1;
   }
   static bool attr_set = false;
   if (!attr_set) {
@@ -452,9 +496,9 @@ extern "C" int tgan_igemm_bf16(const tgan_igemm_args* a, void* stream) {
     TGAN_CHECK_ARG(e == cudaSuccess, "igemm: cannot set max dynamic smem: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int total = p.m_tiles * p.n_tiles;
+  const int total = p.pp_tiles * p.ct_tiles;
   const int grid = total < 148 ? total : 148;
-  igemm_kernel<<<grid, IG_THREADS, smem_bytes, (cudaStream_t)stream>>>(tmA, tmB, p);
+  igemm_kernel<<<grid, IG_THREADS, smem_bytes, (cudaStream_t)stream>>>(tmX, tmW, p);
   TGAN_LAUNCHED();
   return 0;
 }
@@ -536,8 +580,9 @@ extern "C" int tgan_wgrad_bf16(const tgan_wgrad_args* a, void* stream) {
   wgrad_kernel<<<grid, IG_THREADS, smem_bytes, (cudaStream_t)stream>>>(tmDz, tmX, p);
   TGAN_LAUNCHED();
   const int64_t tot = (int64_t)a->T * a->Cout * a->Cin;
-  wgrad_reduce_kernel<<<ceil_div(tot, 256), 256, 0, (cudaStream_t)stream>>>(a->ws, p.splits, a->T, a->Cout, a->Cin,
-                                                                          a->dw, a->dw_st, a->dw_sco, a->dw_sci, a->beta);
+  int rg = ceil_div(tot, 256);
+  if (rg > 148 * 8) rg = 148 * 8;
+  wgrad_reduce_kernel<<<rg, 256, 0, (cudaStream_t)stream>>>(a->ws, p.splits, tot, a->dw, a->beta);
   TGAN_LAUNCHED();
   return 0;
 }

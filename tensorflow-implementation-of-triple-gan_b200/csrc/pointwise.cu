@@ -22,18 +22,18 @@ struct StatsF {
   }
 };
 
-template <typename TDY, typename TY, typename TDU, int VEC>
+template <typename TDY, typename TY, typename TDU, int VEC, int ACT>
 struct ActBwdF {
-  const TDY* dy; const TY* y; TDU* du; int C; int act; float alpha;
+  const TDY* dy; const TY* y; TDU* du; int C; float alpha;
   __device__ void operator()(int64_t r, int c0, float (&v)[1][VEC]) const {
     if constexpr (VEC == 4) {
       float a[4], b[4], o[4];
       ld4<TDY>(dy, r * C + c0, a); ld4<TY>(y, r * C + c0, b);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { o[j] = a[j] * act_grad_from_y(b[j], act, alpha); v[0][j] = o[j]; }
+      for (int j = 0; j < 4; ++j) { o[j] = a[j] * act_grad_from_y_t<ACT>(b[j], alpha); v[0][j] = o[j]; }
       st4<TDU>(du, r * C + c0, o);
     } else {
-      float o = ldf<TDY>(dy, r * C + c0) * act_grad_from_y(ldf<TY>(y, r * C + c0), act, alpha);
+      float o = ldf<TDY>(dy, r * C + c0) * act_grad_from_y_t<ACT>(ldf<TY>(y, r * C + c0), alpha);
       v[0][0] = o; stf<TDU>(du, r * C + c0, o);
     }
   }
@@ -92,10 +92,9 @@ __global__ void bn_eval_kernel(const float* gamma, const float* beta, const floa
 // ------------------------------------------------------------------------------------------------
 // elementwise kernels over [rows, C]
 // ------------------------------------------------------------------------------------------------
-template <typename TX, typename TY, int VEC>
+template <typename TX, typename TY, int VEC, int ACT>
 __global__ void affine_act_kernel(const TX* __restrict__ x, TY* __restrict__ y, int64_t nvec, int C,
-                                  const float* __restrict__ scale, const float* __restrict__ shift, int act,
-                                  float alpha) {
+                                  const float* __restrict__ scale, const float* __restrict__ shift, float alpha) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t e = i * VEC;
     int c = (int)(e % C);
@@ -103,11 +102,11 @@ __global__ void affine_act_kernel(const TX* __restrict__ x, TY* __restrict__ y, 
       float v[4]; ld4<TX>(x, e, v);
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        v[j] = act_fwd(v[j] * (scale ? scale[c + j] : 1.f) + (shift ? shift[c + j] : 0.f), act, alpha);
+        v[j] = act_fwd_t<ACT>(v[j] * (scale ? scale[c + j] : 1.f) + (shift ? shift[c + j] : 0.f), alpha);
       st4<TY>(y, e, v);
     } else {
       float v = ldf<TX>(x, e);
-      stf<TY>(y, e, act_fwd(v * (scale ? scale[c] : 1.f) + (shift ? shift[c] : 0.f), act, alpha));
+      stf<TY>(y, e, act_fwd_t<ACT>(v * (scale ? scale[c] : 1.f) + (shift ? shift[c] : 0.f), alpha));
     }
   }
 }
@@ -389,8 +388,10 @@ extern "C" int tgan_affine_act(const void* x, int xdt, void* y, int ydt, int64_t
   bool v = (C % 4 == 0) && aligned16(x) && aligned16(y);
   cudaStream_t st = (cudaStream_t)stream;
   DISPATCH_2(xdt, TX, ydt, TY, {
-    if (v) affine_act_kernel<TX, TY, 4><<<grid_for(n / 4), 256, 0, st>>>((const TX*)x, (TY*)y, n / 4, C, scale, shift, act, alpha);
-    else affine_act_kernel<TX, TY, 1><<<grid_for(n), 256, 0, st>>>((const TX*)x, (TY*)y, n, C, scale, shift, act, alpha);
+    TGAN_DISPATCH_ACT(act, A, {
+      if (v) affine_act_kernel<TX, TY, 4, A><<<grid_for(n / 4), 256, 0, st>>>((const TX*)x, (TY*)y, n / 4, C, scale, shift, alpha);
+      else affine_act_kernel<TX, TY, 1, A><<<grid_for(n), 256, 0, st>>>((const TX*)x, (TY*)y, n, C, scale, shift, alpha);
+    });
   });
   TGAN_LAUNCHED();
   return 0;
@@ -401,9 +402,11 @@ extern "C" int tgan_act_bwd(const void* dy, int dydt, const void* y, int ydt, vo
   TGAN_CHECK_ARG(dy && y && du && ws && rows > 0 && C > 0, "act_bwd: bad args");
   bool v = (C % 4 == 0) && aligned16(dy) && aligned16(y) && aligned16(du);
   TGAN_DISPATCH_1(dydt, TDY, TGAN_DISPATCH_1(ydt, TY, TGAN_DISPATCH_1(dudt, TDU, {
-    ActBwdF<TDY, TY, TDU, 1> f1{(const TDY*)dy, (const TY*)y, (TDU*)du, C, act, alpha};
-    ActBwdF<TDY, TY, TDU, 4> f4{(const TDY*)dy, (const TY*)y, (TDU*)du, C, act, alpha};
-    return run_colreduce<1>(f1, f4, v, rows, C, colsum, nullptr, 0.f, ws, (cudaStream_t)stream);
+    TGAN_DISPATCH_ACT(act, A, {
+      ActBwdF<TDY, TY, TDU, 1, A> f1{(const TDY*)dy, (const TY*)y, (TDU*)du, C, alpha};
+      ActBwdF<TDY, TY, TDU, 4, A> f4{(const TDY*)dy, (const TY*)y, (TDU*)du, C, alpha};
+      return run_colreduce<1>(f1, f4, v, rows, C, colsum, nullptr, 0.f, ws, (cudaStream_t)stream);
+    });
   })));
   return 0;
 }

@@ -240,6 +240,7 @@ class VariableStore:
         self.np_rng = np.random.default_rng(seed)
         self.flat = {}          # group -> dict(theta, grad, m, v, ema, params)
         self.version = 0        # bumped on every optimiser step (invalidates weight-norm caches)
+        self.versions = {}      # per network: only the updated network's cached weights are rebuilt
         self.finalized = False
 
     # -- scopes --
@@ -328,8 +329,16 @@ class VariableStore:
     def to_numpy(self):
         return {n: self.vars[n].data.detach().cpu().numpy().copy() for n in self.order}
 
-    def bump(self):
+    def bump(self, group=None):
         self.version += 1
+        if group is None:
+            for k in list(self.versions) + list(self.GROUPS):
+                self.versions[k] = self.versions.get(k, 0) + 1
+        else:
+            self.versions[group] = self.versions.get(group, 0) + 1
+
+    def group_version(self, group):
+        return self.versions.get(group, 0)
 
 
 def variable_scope(name, reuse=None):

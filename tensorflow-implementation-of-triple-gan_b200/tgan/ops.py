@@ -119,9 +119,10 @@ class WNWeight:
 
     def _c(self):
         c = self.V.cache
-        if c.get('version') != ctx.store.version:
+        ver = ctx.store.group_version(self.V.group)
+        if c.get('version') != ver:
             c.clear()
-            c['version'] = ctx.store.version
+            c['version'] = ver
             c['W'] = _new(self.V.shape, torch.float32)
             c['inv'] = _new((self.Co,), torch.float32)
             c['scale'] = _new((self.Co,), torch.float32)

@@ -43,9 +43,10 @@ def _bf16_padded(t, rows, C, ld):
 
 def _wcache(w):
     c = w.key.cache.setdefault('tc', {})
-    if c.get('version') != ctx.store.version:
+    ver = ctx.store.group_version(w.key.group)
+    if c.get('version') != ver:
         c.clear()
-        c['version'] = ctx.store.version
+        c['version'] = ver
     return c
 
 
@@ -85,14 +86,14 @@ def _igemm(x, N, H, W, C, ldx, wp, Kpad, taps, Nout, gh, gw, out, OH, OW, ldo, s
     _lib.call('tgan_igemm_bf16', ctypes.byref(a), _st())
 
 
-def _wgrad(dz, N, gh, gw, Cout, lddz, x, H, W, Cin, ldx, taps, s, dw, st, sco, sci):
+def _wgrad(dz, N, gh, gw, Cout, lddz, x, H, W, Cin, ldx, taps, s, dw):
     a = _lib.TganWgradArgs()
     a.dz, a.N, a.gh, a.gw, a.Cout, a.lddz = dz.data_ptr(), N, gh, gw, Cout, lddz
     a.x, a.H, a.W, a.Cin, a.ldx, a.sy, a.sx = x.data_ptr(), H, W, Cin, ldx, s, s
     a.T = len(taps)
     for i, (dy, dx) in enumerate(taps):
         a.dy[i], a.dx[i] = dy, dx
-    a.dw, a.dw_st, a.dw_sco, a.dw_sci, a.beta = dw.data_ptr(), st, sco, sci, 1.0
+    a.dw, a.beta = dw.data_ptr(), 1.0
     ws = ctx.ws()
     a.ws, a.ws_bytes = ws.data_ptr(), ws.numel() * 4
     _lib.call('tgan_wgrad_bf16', ctypes.byref(a), _st())
@@ -138,9 +139,8 @@ def conv_bwd(x, w, g, dz):
     if w.requires_grad:
         xd, ld = g.get('_x') or _bf16_padded(x.data, x.rows, C, x.ld)
         taps = [(r - pt, c - pl) for r in range(kh) for c in range(kw)]
-        # HWIO gradient: element (t, co, ci) lives at t*C*Cout + ci*Cout + co
-        _wgrad(dzb, gf['N'], gf['Ho'], gf['Wo'], Cout, Cout, xd, gf['H'], gf['W'], C, ld, taps, s, w.grad_target(),
-               C * Cout, 1, Cout)
+        # the kernel writes [t][ci][co] == HWIO
+        _wgrad(dzb, gf['N'], gf['Ho'], gf['Wo'], Cout, Cout, xd, gf['H'], gf['W'], C, ld, taps, s, w.grad_target())
     if x.requires_grad:
         dx = _new(x.shape, x.data.dtype if x.data.dtype == torch.bfloat16 else torch.float32)
         wp, Kpad = None, None
@@ -205,10 +205,9 @@ def deconv_bwd(x, w, g, dy):
     taps = [(r - pt, c - pl) for r in range(kh) for c in range(kw)]
     if w.requires_grad:
         xd, ld = g.get('_x') or _bf16_padded(x.data, x.rows, Cin, x.ld)
-        # roles exchanged: M side = x channels (ci), N side = strided dy window (co);
-        # filter layout [t][co][ci]: kernel's (t, "co"=ci, "ci"=co) -> t*Cout*Cin + co*Cin + ci
-        _wgrad(xd, g['N'], g['h'], g['w'], Cin, ld, dyb, g['Ho'], g['Wo'], Cout, Cout, taps, 2, w.grad_target(),
-               Cout * Cin, 1, Cin)
+        # roles exchanged: M side = x channels (ci), N side = strided dy window (co); the kernel's
+        # [t][N-side][M-side] output is then exactly the filter layout [kh,kw,Cout,Cin]
+        _wgrad(xd, g['N'], g['h'], g['w'], Cin, ld, dyb, g['Ho'], g['Wo'], Cout, Cout, taps, 2, w.grad_target())
     if x.requires_grad:
         wp, Kpad = _pack(w, 'ddgrad', kh * kw, Cin, Cout, Cout * Cin, 1, Cin)
         dx = _new(x.shape, torch.bfloat16)

@@ -128,13 +128,13 @@ class Train(Train_base):
         _lib.call('tgan_fill_f32', fb['grad'].data_ptr(), 0.0, fb['n'], ops._st())
         return fb
 
-    def _apply(self, fb, opt, ema=None):
+    def _apply(self, fb, opt, ema=None, group=None):
         scale = 1.0
         if self.world > 1:
             torch.distributed.all_reduce(fb['grad'], group=self.pg)      # NCCL sum over NVLink
             scale = 1.0 / self.world
         opt.apply_flat(fb, scale, ema.shadow if ema is not None else None, ema.decay if ema is not None else 0.0)
-        self.store.bump()
+        self.store.bump(group)
 
     def _pre(self):
         m = self.model
@@ -163,7 +163,7 @@ class Train(Train_base):
             _, du = m.discriminator(v['x_u_c'], oh_u, reuse=True, tag='D/D_unl')
             d_loss = ops.loss_d(dr, df, du)
             ops.backward(d_loss)
-        self._apply(fb, self.d_optimizer)
+        self._apply(fb, self.d_optimizer, group='discriminator')
         self.aux = dict(idx_unl_d=idx_d, idx_unl=idx_u, G_phaseD=G, d_logits=(dr, df, du))
         # ---- phase G: sess.run([g_solver, g_loss]) (:270) ----
         fb = self._begin('good_generator', self.g_vars)
@@ -172,7 +172,7 @@ class Train(Train_base):
             _, df = m.discriminator(G, v['y_g'], reuse=True, tag='G/D_fake')
             g_loss = ops.loss_g(df)
             ops.backward(g_loss)
-        self._apply(fb, self.g_optimizer)
+        self._apply(fb, self.g_optimizer, group='good_generator')
         # ---- phase C: sess.run([c_solver, c_loss]) (:275) ----
         fb = self._begin('classifier', self.c_vars)
         with recording():
@@ -186,7 +186,7 @@ class Train(Train_base):
             c_fake, _ = m.classifier(pre(G), train, reuse=True, tag='C/C_fake')
             c_loss = ops.loss_c(c_real, v['y_l_c'], c_unl, c_rep, du, c_fake, v['y_g'], self.lambdas)
             ops.backward(c_loss)
-        self._apply(fb, self.c_optimizer, self.ema)
+        self._apply(fb, self.c_optimizer, self.ema, group='classifier')
         self.aux['c_logits'] = (c_real, c_unl, c_fake, c_rep)
         if not ctx.rng.injected:
             _lib.call('tgan_counter_advance', ctx.rng.counter().data_ptr(), 1, ops._st())

@@ -86,7 +86,17 @@ def _compare(orc, o32, tr, group, names, fn, logits_v, math, what):
           % (what, math, el, lfloor, worst, floor, rworst, rfloor, wn))
     assert el < max(tl, 3 * lfloor), (what, el, lfloor)
     if math == 'fp32':
-        assert worst < max(tg, 5 * floor), (what, wn, worst, floor)
+        # parameters whose exact gradient is identically zero (a bias in front of a batch-mean subtraction) carry
+        # pure cancellation noise whose size depends on the summation order: bound it at 2e-3 of the net's scale
+        zero = {n for n, r in ref.items() if np.abs(r).max() < 1e-6 * scale}
+        worst_nz = 0.0
+        for p, o in zip(fb['params'], fb['offsets']):
+            g = tnp(fb['grad'][o:o + p.size]).reshape(p.shape)
+            if p.name in zero:
+                assert np.abs(g).max() < 2e-3 * scale, (what, p.name, np.abs(g).max(), scale)
+            else:
+                worst_nz = max(worst_nz, np.abs(g - ref[p.name]).max() / den[p.name])
+        assert worst_nz < max(tg, 5 * floor), (what, wn, worst_nz, floor)
     else:
         assert rworst < max(tg, 2 * rfloor), (what, rworst, rfloor)
         assert worst < max(tg, 3 * floor), (what, wn, worst, floor)
@@ -147,9 +157,11 @@ def test_generator_discriminator_fwd_bwd(data_name, math):
         _, lv = tr.model.discriminator(Gv, ops.constant(y), reuse=True, tag='T/DG')
         lv.grad = torch.tensor(R, dtype=torch.float32).cuda()
         core.ctx.tape.backward()
-    with _ctx('fp32'):
-        Gt = orc.model.good_generator(torch.tensor(z, dtype=torch.float64), torch.tensor(y, dtype=torch.float64), rng, 'T/G')
-    eg = np.abs(Gv.numpy().reshape(Gt.shape) - Gt.detach().numpy()).max()
-    print('%s %s G image abs err %.2e' % (data_name, math, eg))
-    assert eg < (1e-4 if math == 'fp32' else 3e-2)
+    t64 = lambda a: torch.tensor(a, dtype=torch.float64)
+    Gt = orc.model.good_generator(t64(z), t64(y), rng, 'T/G').detach().numpy()
+    with _ctx(math):
+        Gq = orc.model.good_generator(t64(z), t64(y), rng, 'T/G').detach().numpy()
+    eg, gfloor = np.abs(Gv.numpy().reshape(Gt.shape) - Gt).max(), np.abs(Gq - Gt).max()
+    print('%s %s G image abs err %.2e (oracle floor at this precision %.2e)' % (data_name, math, eg, gfloor))
+    assert eg < (1e-4 if math == 'fp32' else max(3e-2, 2 * gfloor))
     _compare(orc, o32, tr, 'good_generator', orc.g_vars, fn_g, lv, math, data_name + ' G<-D')

@@ -108,8 +108,11 @@ def test_step_parity_bf16(data_name):
     """tensor-core mode: bf16 operands / activations, fp32 accumulation.  Stated tolerance (relative to
     max-abs), against the oracle restating the same bf16 rounding points (oracle.quantized): losses 2e-2,
     per-phase gradients 1.5e-1 of the phase's gradient scale after up to 10 bf16 layers forward and backward;
-    pseudo-labels exact where the oracle's top-2 logit margin exceeds 0.05."""
-    _run(data_name, 'bf16', steps=2, scale=10, tol_loss=2e-2, tol_grad=1.5e-1, margin0=0.05)
+    pseudo-labels exact where the oracle's top-2 logit margin exceeds 0.05.  One step only: Adam's first
+    update is lr*sign(g) per element, so bf16 gradient noise (20-30% rms on the deep classifier, see
+    test_gpu_nets.py) already moves a large share of the weights by 2*lr relative to the fp64 run; later steps
+    are compared as a trajectory band in test_loss_trajectory_20_steps."""
+    _run(data_name, 'bf16', steps=1, scale=10, tol_loss=2e-2, tol_grad=1.5e-1, margin0=0.05)
 
 
 def test_step_parity_fp32_cifar_lambdas_zero():
