@@ -103,6 +103,9 @@ typedef struct {
 } tgan_wgrad_args;
 int tgan_wgrad_bf16(const tgan_wgrad_args* a, void* stream);
 int64_t tgan_wgrad_workspace_bytes(const tgan_wgrad_args* a);
+/* sizeof() of the two argument structs, for binding-side layout checks */
+int tgan_sizeof_igemm_args(void);
+int tgan_sizeof_wgrad_args(void);
 
 /* weight preparation for the tcgen05 path: fp32 weights (any TF layout, addressed by strides) ->
  * bf16 K-major [T][Nrows][Kpad]:  dst[t][n][k] = k < K ? src[taps[t]*st + n*sn + k*sk] : 0

@@ -123,7 +123,8 @@ def conv2d_transpose_tf(x, w, stride=2, padding='SAME'):
         Ho, Wo = x.shape[1] * stride, x.shape[2] * stride
         _, pt, _ = same_pad(Ho, kh, stride)
         _, pl, _ = same_pad(Wo, kw, stride)
-        # the full scatter may be smaller than pt+Ho when k < s; not the case for any model here
+        # the full scatter (n-1)s+k is shorter than pt+s*n when k < s: the missing tail is zeros
+        y = F.pad(y, (0, max(0, pl + Wo - y.shape[3]), 0, max(0, pt + Ho - y.shape[2])))
         y = y[:, :, pt:pt + Ho, pl:pl + Wo]
     return q(y.permute(0, 2, 3, 1)) if tc else y.permute(0, 2, 3, 1)
 

@@ -539,6 +539,9 @@ static int wgrad_plan(const tgan_wgrad_args* a, WgParams& p) {
   return 0;
 }
 
+extern "C" int tgan_sizeof_igemm_args(void) { return (int)sizeof(tgan_igemm_args); }
+extern "C" int tgan_sizeof_wgrad_args(void) { return (int)sizeof(tgan_wgrad_args); }
+
 extern "C" int64_t tgan_wgrad_workspace_bytes(const tgan_wgrad_args* a) {
   WgParams p;
   if (!a || wgrad_plan(a, p)) return -1;

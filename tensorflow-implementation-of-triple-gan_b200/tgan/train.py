@@ -14,7 +14,7 @@ and 1/world is folded into the fused Adam kernel.
 import numpy as np
 import torch
 
-from . import _lib, ops
+from . import _lib, ddp, ops
 from .core import VariableStore, building, ctx, no_grad, recording
 from .train_base import AdamOptimizer, Train_base
 
@@ -103,8 +103,8 @@ class Train(Train_base):
             ctx.rng.counter()
         if c.DATA_NAME == 'cifar10' and hasattr(self.model, '_whitener'):
             self.model._whitener()._upload()
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            self.world = torch.distributed.get_world_size()
+        self.world = ddp.world_size()
+        ddp.broadcast_params(self.store, 0, self.pg)
         return self
 
     # ------------------------------------------------------------------ one step ------------------
@@ -129,10 +129,7 @@ class Train(Train_base):
         return fb
 
     def _apply(self, fb, opt, ema=None, group=None):
-        scale = 1.0
-        if self.world > 1:
-            torch.distributed.all_reduce(fb['grad'], group=self.pg)      # NCCL sum over NVLink
-            scale = 1.0 / self.world
+        scale = ddp.allreduce_grads(fb['grad'], self.pg)      # NCCL sum over NVLink; 1/world folded into Adam
         opt.apply_flat(fb, scale, ema.shadow if ema is not None else None, ema.decay if ema is not None else 0.0)
         self.store.bump(group)
 

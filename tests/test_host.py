@@ -1,0 +1,112 @@
+"""CPU: host-side logic of the product package -- graph construction in shape-only mode, TF variable naming and
+scope semantics, configs, schedules, and loud failure without a GPU."""
+import numpy as np
+import pytest
+
+import tgan
+from oracle import tgan_oracle as O
+from tgan import core, nn, ops
+
+
+@pytest.mark.parametrize('name,counts', [('cifar10', (327467, 5129201, 3121812)), ('svhn', (339436, 5113844, 3124254)),
+                                         ('mnist', (1561262, 714408, 279326))])
+def test_variable_inventory_matches_tf_names(name, counts):
+    tr = tgan.make_trainer(name, build_only=True)
+    P, S = O.init_params(name)
+    mine = {n: p.shape for n, p in tr.store.vars.items()}
+    ref = {k: tuple(v.shape) for k, v in list(P.items()) + list(S.items())}
+    assert mine == ref
+    assert set(n for n, p in tr.store.vars.items() if not p.trainable) == set(S)
+    got = tuple(sum(p.size for p in v) for v in (tr.d_vars, tr.g_vars, tr.c_vars))
+    assert got == counts        # D 327,467 / G 5,129,201 / C 3,121,812 for the CIFAR file
+    if name == 'cifar10':
+        assert 'classifier/NiN1/NiN1/V' in mine and 'good_generator/gg_h0_lin/gg_h0_lin/kernel' in mine
+        assert mine['good_generator/gg_dconv0/gg_dconv0/kernel'] == (5, 5, 256, 522)
+        assert mine['discriminator/conv2d_21/conv2d_21/kernel'] == (3, 3, 138, 128)
+
+
+def test_build_mode_shapes_of_forward_pass():
+    tr = tgan.Train(tgan.make_config('cifar10', ZCA=(np.zeros(3072), np.eye(3072))))
+    ph, G, D, C, model = tr._build_train_graph(tgan.Good_GAN_cifar10)
+    assert G.shape == (100, 32, 32, 3)
+    assert [d.shape for d in D[1::2]] == [(100, 1), (100, 1), (50, 1)]
+    assert [c.shape for c in C] == [(50, 10), (50, 10), (80, 10), (100, 10), (50, 10)]
+    tr2 = tgan.Train(tgan.make_config('mnist'))
+    _, G, D, C, _ = tr2._build_train_graph(tgan.Good_GAN)
+    assert G.shape == (100, 784) and len(C) == 4 and C[0].shape == (100, 10)
+
+
+def test_variable_scope_reuse_semantics():
+    store = core.VariableStore()
+    core.ctx.store = store
+    with core.building(), core.no_grad():
+        x = ops.Var(None, (4, 8, 8, 3))
+        with core.variable_scope('net'):
+            nn.conv2d_WN(x, 16, name='c1', use_weight_normalization=True, use_mean_only_batch_normalization=True)
+        assert set(store.vars) == {'net/c1/V', 'net/c1/b', 'net/c1/meanOnlyBatchNormalization/pop_mean', 'net/c1/g'}
+        with pytest.raises(ValueError):            # TF: "Variable net/c1/V already exists"
+            with core.variable_scope('net'):
+                nn.conv2d_WN(x, 16, name='c1', use_weight_normalization=True)
+        with core.variable_scope('net', reuse=True):
+            y = nn.conv2d_WN(x, 16, name='c1', use_weight_normalization=True, use_mean_only_batch_normalization=True)
+            assert y.shape == (4, 8, 8, 16)
+            with pytest.raises(ValueError):        # TF: "Variable net/c2/V does not exist"
+                nn.conv2d_WN(x, 16, name='c2', use_weight_normalization=True)
+            with pytest.raises(ValueError):        # shape mismatch on reuse
+                nn.conv2d_WN(x, 32, name='c1', use_weight_normalization=True)
+
+
+def test_nn_surface_shapes_and_scopes():
+    store = core.VariableStore()
+    core.ctx.store = store
+    with core.building(), core.no_grad():
+        x = ops.Var(None, (2, 8, 8, 6))
+        assert nn.conv2d_WN(x, 12, pad='VALID', name='a', use_weight_normalization=True).shape == (2, 6, 6, 12)
+        assert nn.conv2d_WN(x, 12, stride=[2, 2], name='b').shape == (2, 4, 4, 12)
+        assert nn.NiN_WN(x, 5, name='nin', use_weight_normalization=True,
+                         use_mean_only_batch_normalization=True).shape == (2, 8, 8, 5)
+        assert 'nin/nin/V' in store.vars and store.vars['nin/nin/V'].shape == (6, 5)
+        assert nn.dense_WN(ops.Var(None, (7, 6)), 3, name='d', use_weight_normalization=True).shape == (7, 3)
+        c = {}
+        assert nn.conv2d(x, 4, counters=c).shape == (2, 8, 8, 4) and 'conv2d_0/V' in store.vars
+        assert nn.deconv2d(x, 4, filter_size=[5, 5], stride=[2, 2], counters=c).shape == (2, 16, 16, 4)
+        assert store.vars['deconv2d_0/V'].shape == (5, 5, 4, 6)
+        assert nn.dense(ops.Var(None, (3, 6)), 9, counters=c).shape == (3, 9)
+        assert nn.nin(x, 7, counters=c).shape == (2, 8, 8, 7) and 'dense_1/V' in store.vars
+        assert nn._linear_fc(ops.Var(None, (3, 6)), 4, 'fc').shape == (3, 4) and 'fc/fc/kernel' in store.vars
+        assert nn._deconv2d(x, 3, name='dc').shape == (2, 16, 16, 3)
+        assert nn.batch_norm_contrib(x, 'bn', train=True).shape == (2, 8, 8, 6)
+        assert {'bn/beta', 'bn/gamma', 'bn/moving_mean', 'bn/moving_variance'} <= set(store.vars)
+        h = ops.concat_label(x, ops.Var(None, (2, 10)))
+        assert h.shape == (2, 8, 8, 16)
+
+
+def test_config_presets_and_schedule():
+    c = tgan.make_config('cifar10')
+    assert (c.BATCH_SIZE_G, c.BATCH_SIZE_L_C, c.BATCH_SIZE_U_C, c.BATCH_SIZE_L_D, c.BATCH_SIZE_U_D) == (100, 50, 50, 20, 80)
+    assert c.IMAGE_DIM == [32, 32, 3] and c.CLA_LEARNINIG_RATE == 3e-3 and c.FAKE_G_LAMBDA == 0.3 and c.BETA1 == 0.5
+    m = tgan.make_config('mnist')
+    assert m.BATCH_SIZE_L_C == 100 and m.IMAGE_DIM == [28, 28, 1] and m.LEARNING_RATE == 1e-3
+    with pytest.raises(ValueError):
+        tgan.make_config('prostate')
+    tr = tgan.Train(c)
+    assert tr.schedule(1) == (0.0, 0, 3e-4, 3e-3)              # Train_goodGAN.py:165-177
+    assert tr.schedule(68)[1] == 0.5 and tr.schedule(201)[0] == 0.3
+    l1, l2, lr, clr = tr.schedule(301)
+    assert abs(lr - 3e-4 * 0.995 ** 2) < 1e-12 and abs(clr - 3e-3 * 0.99 ** 2) < 1e-12
+
+
+def test_unknown_dataset_raises_like_the_reference():
+    class Cfg(tgan.Config):
+        DATA_NAME, NUM_CLASSES, MINIBATCH_DIS = 'prostate', 10, False
+    core.ctx.store = core.VariableStore()
+    with core.building(), pytest.raises(ValueError):
+        tgan.Good_GAN(Cfg()).good_generator(ops.Var(None, (2, 100)), ops.Var(None, (2, 10)))
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        tgan.init('cuda:0')
