@@ -122,24 +122,24 @@ int tgan_pack_weight_bf16(const float* src, void* dst, int T, int Nrows, int K, 
 int tgan_weightnorm_fwd(const float* V, const float* g, float* W, float* inv_norm, float* scale, int A, int Co,
                         int B, int eps_mode, float* ws, void* stream);
 /* also writes scale[co] = g[co]*inv_norm[co]; W may be NULL (the tcgen05 path folds `scale` into
- * tgan_pack_weight_bf16 instead).  ws: (2*TGAN_STATS_MAX_PARTS + 1)*Co floats.
+ * tgan_pack_weight_bf16 instead).  ws: (4*TGAN_STATS_MAX_PARTS + 1)*Co floats.
  * dg[co] (+)= <dW, V>*inv_norm ; dV (+)= (g*inv_norm) * (dW - V*inv_norm * <dW,V>*inv_norm)    */
 int tgan_weightnorm_bwd(const float* V, const float* g, const float* inv_norm, const float* dW, float* dV,
                         float* dg, int A, int Co, int B, float beta, float* ws, void* stream);
 
 /* ---------------------------------------------------------------- per-channel statistics ----------
- * x [rows, C] (dtype xdt, contiguous): sum[c] = sum_r x, sumsq[c] = sum_r x^2 (sumsq may be NULL).
- * Deterministic two-stage reduction; ws must hold 2*TGAN_STATS_MAX_PARTS*C floats. */
+ * x [rows, C] (dtype xdt, contiguous): sum[c] = beta*sum[c] + sum_r x, sumsq[c] likewise (sumsq may be NULL).
+ * One launch, deterministic (the last CTA folds the partials in a fixed order); ws: 4*TGAN_STATS_MAX_PARTS*C floats (fp64 partials). */
 #define TGAN_STATS_MAX_PARTS 256
-int tgan_channel_stats(const void* x, int xdt, int64_t rows, int C, float* sum, float* sumsq, float* ws,
+int tgan_channel_stats(const void* x, int xdt, int64_t rows, int C, float* sum, float* sumsq, float beta, float* ws,
                        void* stream);
 
-/* mean-only batch norm, training branch (nn.py:172-183): given sum[c] over `rows`,
- *   mean = sum/rows ; shift[c] = b[c] - mean ; pop_mean = pop_mean*decay + mean*(1-decay). */
-int tgan_mobn_finalize(const float* sum, int64_t rows, int C, const float* b, float* pop_mean, float decay,
-                       float* shift, void* stream);
-/* testing branch (nn.py:170-171): shift = b - pop_mean */
-int tgan_mobn_eval_shift(const float* b, const float* pop_mean, int C, float* shift, void* stream);
+/* mean-only batch norm (nn.py:147-187) fused with the nonlinearity (nn.py:517), one pass:
+ *   training: mean = sum[c]/rows (sum from tgan_channel_stats or from the tgan_igemm_bf16 epilogue);
+ *             y = act(x - mean + b);  pop_mean = pop_mean*decay + mean*(1-decay)        (nn.py:172-183)
+ *   testing : y = act(x - pop_mean + b)                                                 (nn.py:170-171) */
+int tgan_mobn_apply(const void* x, int xdt, void* y, int ydt, int64_t rows, int C, const float* sum, const float* b,
+                    float* pop_mean, float decay, int train, int act, float alpha, void* stream);
 
 /* tf.contrib.layers.batch_norm training statistics (modle_base.py:229-237):
  *   mean, rstd = rsqrt(var_biased + eps); scale = gamma*rstd; shift = beta - mean*scale;
@@ -156,9 +156,10 @@ int tgan_bn_eval_affine(const float* gamma, const float* beta, const float* movi
 int tgan_affine_act(const void* x, int xdt, void* y, int ydt, int64_t rows, int C, const float* scale,
                     const float* shift, int act, float alpha, void* stream);
 /* du = dy * act'(.) computed from the activation OUTPUT y; also per-channel partial sums of du
- * (-> bias gradient / mean-only-BN backward).  colsum[c] = sum_r du (deterministic, ws as channel_stats). */
+ * (-> bias gradient / mean-only-BN backward).  colsum[c] = sum_r du and grad_acc[c] += sum_r du (either may be
+ * NULL; deterministic, ws as channel_stats). */
 int tgan_act_bwd(const void* dy, int dydt, const void* y, int ydt, void* du, int dudt, int64_t rows, int C,
-                 int act, float alpha, float* colsum, float* ws, void* stream);
+                 int act, float alpha, float* colsum, float* grad_acc, float* ws, void* stream);
 /* mean-only BN backward: dz = du - colsum[c]/rows */
 int tgan_sub_channel_mean(const void* du, int dudt, void* dz, int dzdt, int64_t rows, int C,
                           const float* colsum, void* stream);

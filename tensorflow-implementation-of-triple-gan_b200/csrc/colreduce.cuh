@@ -1,109 +1,112 @@
-// colreduce.cuh -- deterministic per-channel (column) reductions over a [rows, C] matrix with an
-// optional fused elementwise output.  Stage 1: (32 channel lanes x 8 row lanes) CTAs, grid sized to
-// ~4 CTAs per SM, coalesced (vectorised x4) along the NHWC channel axis, shared-memory reduce across the
-// row lanes, one partial per CTA row-group.  Stage 2: one thread per channel sums the partials in a
-// fixed order (no atomics -> bit-reproducible statistics).
+// colreduce.cuh -- deterministic per-channel (column) reductions over a [rows, C] matrix with an optional fused
+// elementwise output, in ONE launch.  Each CTA owns 32 channels x a strided subset of the rows (256 threads:
+// 8 channel lanes x 4-wide vectors x 32 row lanes when C % 4 == 0, else 32 x 8), coalesced along the NHWC channel
+// axis, and publishes one partial per accumulator.  The last CTA of a channel block to finish (device-scope ticket)
+// folds the partials in a fixed order, so the statistics are bit-reproducible without a second kernel and without
+// floating-point atomics.  Accumulation is in fp64 end to end (registers, shared memory, partials): bias / beta
+// gradients behind a batch norm are sums of large terms that cancel almost exactly (sum of BN input-gradients is 0),
+// so fp32 summation noise would otherwise depend on the fold order at the 1e-2 level.
 #pragma once
 #include "common.cuh"
 
 namespace tgan {
 
-// ------------------------------------------------------------------------------------------------
-constexpr int RY = 8;  // row lanes per block
+__device__ unsigned int g_colreduce_ticket[1024];   // zero at load; the last CTA of every launch resets its slot
 
 template <int NACC, int VEC, typename F>
-__global__ void __launch_bounds__(32 * RY) colreduce_kernel(F f, int64_t rows, int C, float* __restrict__ partials) {
-  __shared__ float sm[RY][NACC][32 * VEC + 1];
-  const int c0 = (blockIdx.x * 32 + threadIdx.x) * VEC;
-  float acc[NACC][VEC];
+__global__ void __launch_bounds__(256) colreduce_kernel(F f, int64_t rows, int C, double* __restrict__ partials,
+                                                        float* o0, float* o1, float beta, float* acc0) {
+  constexpr int CL = VEC == 4 ? 8 : 32, RL = 256 / CL;
+  __shared__ double sm[RL][NACC][33];
+  __shared__ bool is_last;
+  const int t = threadIdx.x, tx = t % CL, ty = t / CL;
+  const int c0 = blockIdx.x * 32 + tx * VEC;
+  double acc[NACC][VEC];
 #pragma unroll
   for (int a = 0; a < NACC; ++a)
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) acc[a][j] = 0.f;
+    for (int j = 0; j < VEC; ++j) acc[a][j] = 0.0;
   if (c0 < C) {
-    for (int64_t r = (int64_t)blockIdx.y * RY + threadIdx.y; r < rows; r += (int64_t)gridDim.y * RY) {
+    for (int64_t r = (int64_t)blockIdx.y * RL + ty; r < rows; r += (int64_t)gridDim.y * RL) {
       float v[NACC][VEC];
       f(r, c0, v);
 #pragma unroll
       for (int a = 0; a < NACC; ++a)
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) acc[a][j] += v[a][j];
+        for (int j = 0; j < VEC; ++j) acc[a][j] += (double)v[a][j];
     }
   }
 #pragma unroll
   for (int a = 0; a < NACC; ++a)
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) sm[threadIdx.y][a][threadIdx.x * VEC + j] = acc[a][j];
+    for (int j = 0; j < VEC; ++j) sm[ty][a][tx * VEC + j] = acc[a][j];
   __syncthreads();
-  const int t = threadIdx.y * 32 + threadIdx.x;
-  for (int e = t; e < NACC * 32 * VEC; e += 32 * RY) {
-    int a = e / (32 * VEC), cc = e % (32 * VEC);
-    int c = blockIdx.x * 32 * VEC + cc;
-    if (c >= C) continue;
-    float s = 0.f;
+  if (t < 32 * NACC) {
+    const int a = t / 32, cc = t % 32, c = blockIdx.x * 32 + cc;
+    if (c < C) {
+      double s = 0.0;
 #pragma unroll
-    for (int y = 0; y < RY; ++y) s += sm[y][a][cc];
-    partials[((int64_t)blockIdx.y * NACC + a) * C + c] = s;
-  }
-}
-
-// out[a][c] = beta*out[a][c] + sum_p partials[p][a][c].  (32 channels x 8 part-lanes) per CTA: the partial
-// loads of one channel are spread over 8 threads and issued back to back (MLP), then folded in a fixed order.
-template <int NACC>
-__global__ void __launch_bounds__(32 * RY) colreduce_final_kernel(const float* __restrict__ partials, int parts, int C,
-                                                                  float* o0, float* o1, float beta) {
-  __shared__ float sm[RY][NACC][33];
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  float acc[NACC];
-#pragma unroll
-  for (int a = 0; a < NACC; ++a) acc[a] = 0.f;
-  if (c < C) {
-    for (int p = threadIdx.y; p < parts; p += RY) {
-#pragma unroll
-      for (int a = 0; a < NACC; ++a) acc[a] += partials[((int64_t)p * NACC + a) * C + c];
+      for (int y = 0; y < RL; ++y) s += sm[y][a][cc];
+      partials[((int64_t)blockIdx.y * NACC + a) * C + c] = s;
     }
   }
-#pragma unroll
-  for (int a = 0; a < NACC; ++a) sm[threadIdx.y][a][threadIdx.x] = acc[a];
+  __threadfence();
   __syncthreads();
-  if (threadIdx.y == 0 && c < C) {
+  if (t == 0) is_last = (atomicAdd(&g_colreduce_ticket[blockIdx.x], 1u) == gridDim.y - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // ---- last CTA of this channel block: fold gridDim.y partials (32 channels x 8 part lanes), fixed order ----
+  const int fc = t % 32, fl = t / 32, c = blockIdx.x * 32 + fc;
+  const int parts = gridDim.y;
+#pragma unroll
+  for (int a = 0; a < NACC; ++a) {
+    double s = 0.0;
+    if (c < C)
+      for (int p = fl; p < parts; p += 8) s += __ldcg(&partials[((int64_t)p * NACC + a) * C + c]);
+    sm[fl][a][fc] = s;
+  }
+  __syncthreads();
+  if (t < 32 && c < C) {
 #pragma unroll
     for (int a = 0; a < NACC; ++a) {
-      float* o = a == 0 ? o0 : o1;
-      if (!o) continue;
-      float s = 0.f;
+      double s = 0.0;
 #pragma unroll
-      for (int y = 0; y < RY; ++y) s += sm[y][a][threadIdx.x];
-      o[c] = (beta != 0.f ? beta * o[c] : 0.f) + s;
+      for (int y = 0; y < 8; ++y) s += sm[y][a][fc];
+      float* o = a == 0 ? o0 : o1;
+      if (o) o[c] = (float)((beta != 0.f ? (double)beta * o[c] : 0.0) + s);
+      if (a == 0 && acc0) acc0[c] = (float)((double)acc0[c] + s);
     }
   }
+  if (t == 0) g_colreduce_ticket[blockIdx.x] = 0;
 }
 
 static inline int pick_parts(int64_t rows, int C, int vec) {
-  int xblocks = ceil_div(C, 32 * vec);
+  const int rl = vec == 4 ? 32 : 8;
+  int xblocks = ceil_div(C, 32);
   int64_t want = (148 * 4 + xblocks - 1) / xblocks;           // ~4 CTAs per SM over the whole grid
-  int64_t maxp = (rows + RY * 4 - 1) / (RY * 4);              // >= 4 rows per thread
+  int64_t maxp = (rows + rl * 2 - 1) / (rl * 2);              // >= 2 rows per thread
   int64_t p = want < maxp ? want : maxp;
   if (p < 1) p = 1;
   if (p > TGAN_STATS_MAX_PARTS) p = TGAN_STATS_MAX_PARTS;
   return (int)p;
 }
 
+// out0/out1 = beta*out + column sums of accumulator 0/1 (either may be NULL); acc0 (optional) += sums of accumulator 0
 template <int NACC, typename F1, typename F4>
 static int run_colreduce(F1 f1, F4 f4, bool vec_ok, int64_t rows, int C, float* o0, float* o1, float beta, float* ws,
-                         cudaStream_t st) {
+                         cudaStream_t st, float* acc0 = nullptr) {
+  if (ceil_div(C, 32) > 1024) { set_error("colreduce: more than 32768 channels"); return 1; }
   int vec = vec_ok ? 4 : 1;
   int parts = pick_parts(rows, C, vec);
-  dim3 grid(ceil_div(C, 32 * vec), parts), block(32, RY);
-  if (vec_ok) colreduce_kernel<NACC, 4, F4><<<grid, block, 0, st>>>(f4, rows, C, ws);
-  else colreduce_kernel<NACC, 1, F1><<<grid, block, 0, st>>>(f1, rows, C, ws);
-  TGAN_LAUNCHED();
-  colreduce_final_kernel<NACC><<<ceil_div(C, 32), dim3(32, RY), 0, st>>>(ws, parts, C, o0, o1, beta);
+  dim3 grid(ceil_div(C, 32), parts);
+  double* wsd = reinterpret_cast<double*>(ws);       // fp64 partials: the first 4*MAX_PARTS*C floats of ws
+  if (vec_ok) colreduce_kernel<NACC, 4, F4><<<grid, 256, 0, st>>>(f4, rows, C, wsd, o0, o1, beta, acc0);
+  else colreduce_kernel<NACC, 1, F1><<<grid, 256, 0, st>>>(f1, rows, C, wsd, o0, o1, beta, acc0);
   TGAN_LAUNCHED();
   return 0;
 }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
-
 
 }  // namespace tgan

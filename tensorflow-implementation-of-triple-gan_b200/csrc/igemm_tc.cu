@@ -521,7 +521,7 @@ static int wgrad_plan(const tgan_wgrad_args* a, WgParams& p) {
   while (p.tg > 1 && (size_t)2 * (2 + p.tg * (p.BNc / 64)) * WG_BOX_BYTES > 200 * 1024) --p.tg;
   p.tap_groups = ceil_div(a->T, p.tg);
   const int base = p.co_tiles * p.ci_tiles * p.tap_groups;
-  int splits = (2 * 148 + base - 1) / base;
+  int splits = 148 / base;            // one wave of equal-work CTAs; fewer splits = fewer fp32 partials to fold
   if (splits > p.p_tiles) splits = p.p_tiles;
   if (splits < 1) splits = 1;
   // keep >= 8 pixel tiles per split so the pipeline prologue is amortised

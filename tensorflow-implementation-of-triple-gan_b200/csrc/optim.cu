@@ -134,7 +134,7 @@ extern "C" int tgan_weightnorm_fwd(const float* V, const float* g, float* W, flo
                                    int Co, int B, int eps_mode, float* ws, void* stream) {
   TGAN_CHECK_ARG(V && g && inv_norm && scale && ws && A > 0 && Co > 0 && B > 0, "weightnorm_fwd: bad args");
   cudaStream_t st = (cudaStream_t)stream;
-  float* ss = ws + (int64_t)2 * TGAN_STATS_MAX_PARTS * Co;
+  float* ss = ws + (int64_t)4 * TGAN_STATS_MAX_PARTS * Co;
   if (B == 1) {
     SumSqF<1> f1{V, Co};
     SumSqF<4> f4{V, Co};
@@ -158,7 +158,7 @@ extern "C" int tgan_weightnorm_bwd(const float* V, const float* g, const float* 
                                    float* dg, int A, int Co, int B, float beta, float* ws, void* stream) {
   TGAN_CHECK_ARG(V && g && inv_norm && dW && dV && dg && ws, "weightnorm_bwd: bad args");
   cudaStream_t st = (cudaStream_t)stream;
-  float* dot = ws + (int64_t)2 * TGAN_STATS_MAX_PARTS * Co;
+  float* dot = ws + (int64_t)4 * TGAN_STATS_MAX_PARTS * Co;
   if (B == 1) {
     DotF<1> f1{dW, V, Co};
     DotF<4> f4{dW, V, Co};

@@ -55,18 +55,6 @@ struct BnBwdStatsF {
 // ------------------------------------------------------------------------------------------------
 // finalize kernels (tiny, one thread per channel)
 // ------------------------------------------------------------------------------------------------
-__global__ void mobn_finalize_kernel(const float* sum, float inv_rows, int C, const float* b, float* pop_mean,
-                                     float decay, float* shift) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float m = sum[c] * inv_rows;
-  shift[c] = (b ? b[c] : 0.f) - m;
-  if (pop_mean) pop_mean[c] = pop_mean[c] * decay + m * (1.f - decay);
-}
-__global__ void mobn_eval_kernel(const float* b, const float* pop_mean, int C, float* shift) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < C) shift[c] = (b ? b[c] : 0.f) - pop_mean[c];
-}
 __global__ void bn_finalize_kernel(const float* sum, const float* sumsq, float rows, int C, const float* gamma,
                                    const float* beta, float eps, float decay, float* mm, float* mv, float* mean,
                                    float* rstd, float* scale, float* shift) {
@@ -108,6 +96,33 @@ __global__ void affine_act_kernel(const TX* __restrict__ x, TY* __restrict__ y, 
       float v = ldf<TX>(x, e);
       stf<TY>(y, e, act_fwd_t<ACT>(v * (scale ? scale[c] : 1.f) + (shift ? shift[c] : 0.f), alpha));
     }
+  }
+}
+
+// mean-only batch norm apply (nn.py:170-187) fused with the nonlinearity: shift = b - mean, mean = sum/rows in
+// training (and pop_mean <- decay*pop_mean + (1-decay)*mean, done by CTA 0) or pop_mean at test time.
+template <typename TX, typename TY, int VEC, int ACT>
+__global__ void mobn_apply_kernel(const TX* __restrict__ x, TY* __restrict__ y, int64_t nvec, int C,
+                                  const float* __restrict__ sum, float inv_rows, const float* __restrict__ b,
+                                  float* __restrict__ pop_mean, float decay, int train, float alpha) {
+  if (train && pop_mean && blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+      pop_mean[c] = pop_mean[c] * decay + sum[c] * inv_rows * (1.f - decay);
+  }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t e = i * VEC;
+    int c = (int)(e % C);
+    float v[VEC];
+    if constexpr (VEC == 4) ld4<TX>(x, e, *reinterpret_cast<float(*)[4]>(v));
+    else v[0] = ldf<TX>(x, e);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      // in training pop_mean is being rewritten by CTA 0, but it is not read here (sum is)
+      const float m = train ? sum[c + j] * inv_rows : pop_mean[c + j];
+      v[j] = act_fwd_t<ACT>(v[j] + (b ? b[c + j] : 0.f) - m, alpha);
+    }
+    if constexpr (VEC == 4) st4<TY>(y, e, *reinterpret_cast<float(*)[4]>(v));
+    else stf<TY>(y, e, v[0]);
   }
 }
 
@@ -336,29 +351,33 @@ using namespace tgan;
 
 #define DISPATCH_2(d1, T1, d2, T2, ...) TGAN_DISPATCH_1(d1, T1, TGAN_DISPATCH_1(d2, T2, __VA_ARGS__))
 
-extern "C" int tgan_channel_stats(const void* x, int xdt, int64_t rows, int C, float* sum, float* sumsq, float* ws,
-                                  void* stream) {
+extern "C" int tgan_channel_stats(const void* x, int xdt, int64_t rows, int C, float* sum, float* sumsq, float beta,
+                                  float* ws, void* stream) {
   TGAN_CHECK_ARG(x && sum && ws && rows > 0 && C > 0, "channel_stats: bad args");
   bool v = (C % 4 == 0) && aligned16(x);
   TGAN_DISPATCH_1(xdt, T, {
     StatsF<T, 1> f1{(const T*)x, C};
     StatsF<T, 4> f4{(const T*)x, C};
-    return run_colreduce<2>(f1, f4, v, rows, C, sum, sumsq, 0.f, ws, (cudaStream_t)stream);
+    return run_colreduce<2>(f1, f4, v, rows, C, sum, sumsq, beta, ws, (cudaStream_t)stream);
   });
   return 0;
 }
 
-extern "C" int tgan_mobn_finalize(const float* sum, int64_t rows, int C, const float* b, float* pop_mean, float decay,
-                                  float* shift, void* stream) {
-  TGAN_CHECK_ARG(sum && shift && rows > 0, "mobn_finalize: bad args");
-  mobn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(sum, 1.0f / (float)rows, C, b, pop_mean,
-                                                                           decay, shift);
-  TGAN_LAUNCHED();
-  return 0;
-}
-extern "C" int tgan_mobn_eval_shift(const float* b, const float* pop_mean, int C, float* shift, void* stream) {
-  TGAN_CHECK_ARG(pop_mean && shift, "mobn_eval_shift: bad args");
-  mobn_eval_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(b, pop_mean, C, shift);
+extern "C" int tgan_mobn_apply(const void* x, int xdt, void* y, int ydt, int64_t rows, int C, const float* sum,
+                               const float* b, float* pop_mean, float decay, int train, int act, float alpha,
+                               void* stream) {
+  TGAN_CHECK_ARG(x && y && rows > 0 && C > 0, "mobn_apply: bad args");
+  TGAN_CHECK_ARG(train ? sum != nullptr : pop_mean != nullptr, "mobn_apply: needs sum (train) or pop_mean (test)");
+  int64_t n = rows * C;
+  bool v = (C % 4 == 0) && aligned16(x) && aligned16(y);
+  cudaStream_t st = (cudaStream_t)stream;
+  const float inv = 1.0f / (float)rows;
+  DISPATCH_2(xdt, TX, ydt, TY, {
+    TGAN_DISPATCH_ACT(act, A, {
+      if (v) mobn_apply_kernel<TX, TY, 4, A><<<grid_for(n / 4), 256, 0, st>>>((const TX*)x, (TY*)y, n / 4, C, sum, inv, b, pop_mean, decay, train, alpha);
+      else mobn_apply_kernel<TX, TY, 1, A><<<grid_for(n), 256, 0, st>>>((const TX*)x, (TY*)y, n, C, sum, inv, b, pop_mean, decay, train, alpha);
+    });
+  });
   TGAN_LAUNCHED();
   return 0;
 }
@@ -398,14 +417,14 @@ extern "C" int tgan_affine_act(const void* x, int xdt, void* y, int ydt, int64_t
 }
 
 extern "C" int tgan_act_bwd(const void* dy, int dydt, const void* y, int ydt, void* du, int dudt, int64_t rows, int C,
-                            int act, float alpha, float* colsum, float* ws, void* stream) {
+                            int act, float alpha, float* colsum, float* grad_acc, float* ws, void* stream) {
   TGAN_CHECK_ARG(dy && y && du && ws && rows > 0 && C > 0, "act_bwd: bad args");
   bool v = (C % 4 == 0) && aligned16(dy) && aligned16(y) && aligned16(du);
   TGAN_DISPATCH_1(dydt, TDY, TGAN_DISPATCH_1(ydt, TY, TGAN_DISPATCH_1(dudt, TDU, {
     TGAN_DISPATCH_ACT(act, A, {
       ActBwdF<TDY, TY, TDU, 1, A> f1{(const TDY*)dy, (const TY*)y, (TDU*)du, C, alpha};
       ActBwdF<TDY, TY, TDU, 4, A> f4{(const TDY*)dy, (const TY*)y, (TDU*)du, C, alpha};
-      return run_colreduce<1>(f1, f4, v, rows, C, colsum, nullptr, 0.f, ws, (cudaStream_t)stream);
+      return run_colreduce<1>(f1, f4, v, rows, C, colsum, nullptr, 0.f, ws, (cudaStream_t)stream, grad_acc);
     });
   })));
   return 0;
@@ -432,7 +451,7 @@ extern "C" int tgan_bn_bwd(const void* dy, int dydt, const void* x, int xdt, voi
   TGAN_CHECK_ARG(dy && x && dx && mean && rstd && gamma && ws && rows > 0, "bn_bwd: bad args");
   cudaStream_t st = (cudaStream_t)stream;
   // ws layout: [partials: 2*MAX_PARTS*C][s1: C][s2: C]
-  float* s1 = ws + (int64_t)2 * TGAN_STATS_MAX_PARTS * C;
+  float* s1 = ws + (int64_t)4 * TGAN_STATS_MAX_PARTS * C;
   float* s2 = s1 + C;
   DISPATCH_2(dydt, TDY, xdt, TX, {
     BnBwdStatsF<TDY, TX, 1> f1{(const TDY*)dy, (const TX*)x, mean, rstd, C};

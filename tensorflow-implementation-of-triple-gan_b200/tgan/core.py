@@ -36,10 +36,19 @@ class Context:
         self.rng = None
         self._ws = None
         self.ws_floats = 64 * 1024 * 1024
+        self._arena = None          # zero-initialised fp32 scratch for epilogue-accumulated statistics
+        self.arena_floats = 256 * 1024
+        self.arena_off = 0
 
     @property
     def act_dtype(self):
         return torch.bfloat16 if self.math == 'bf16' else torch.float32
+
+    def arena(self):
+        if self._arena is None:
+            self._arena = torch.zeros(self.arena_floats, dtype=torch.float32, device=self.device)
+            self.arena_off = 0
+        return self._arena
 
     def ws(self):
         if self._ws is None:
@@ -62,6 +71,7 @@ def init(device='cuda:0', math='fp32', seed=1234):
     torch.cuda.set_device(ctx.device)
     ctx.math = math
     ctx._ws = None
+    ctx._arena = None
     ctx.rng = PhiloxSource(seed)
     return ctx
 
@@ -127,7 +137,7 @@ class InjectedSource:
 class Var:
     """An activation.  `data` is a contiguous device tensor [..., ld]; the logical shape is `shape`
     (last dim C <= ld; ld > C only for label-concatenated tensors padded for 16-byte TMA strides)."""
-    __slots__ = ('_data', 'shape', 'ld', 'grad', 'requires_grad', '_lazy', 'tag')
+    __slots__ = ('_data', 'shape', 'ld', 'grad', 'requires_grad', '_lazy', 'tag', 'aux')
 
     def __init__(self, data, shape=None, ld=None, requires_grad=False):
         self._data = data
@@ -137,6 +147,7 @@ class Var:
         self.requires_grad = requires_grad
         self._lazy = None          # pending fused epilogue: (z Var, bias Param)
         self.tag = None
+        self.aux = None            # e.g. {'colsum': per-channel sums accumulated by the producing GEMM epilogue}
 
     @property
     def data(self):

@@ -233,7 +233,8 @@ def conv2d_WN(x, num_filters, filter_size=[3, 3], pad='SAME', stride=[1, 1], non
                 z = ops.conv2d(x, ops.WNWeight(V, _tmp_param(np.ones(num_filters)), A, num_filters, 1, 1), kh, kw,
                                stride[0], pad)
                 return _data_init(z, init_scale, 1e-08, nonlinearity)
-            z = ops.conv2d(x, ops.WNWeight(V, g, A, num_filters, 1, 1), kh, kw, stride[0], pad)
+            z = ops.conv2d(x, ops.WNWeight(V, g, A, num_filters, 1, 1), kh, kw, stride[0], pad,
+                           colsum=bool(use_mean_only_batch_normalization))
             if use_mean_only_batch_normalization:
                 fa = _fused(nonlinearity)
                 if fa is not None:
@@ -264,7 +265,8 @@ def dense_WN(x, num_units, nonlinearity=None, init_scale=1., init=False, use_wei
                 z = ops.conv2d(x, ops.WNWeight(V, _tmp_param(np.ones(num_units)), cin, num_units, 1, 1), 1, 1)
                 return _data_init(z, init_scale, 1e-10, nonlinearity)
             # (x @ V) * g/sqrt(sum V^2): the same function of (V, g) as x @ (g V/||V||), no epsilon (nn.py:553-555)
-            z = ops.conv2d(x, ops.WNWeight(V, g, cin, num_units, 1, 0), 1, 1)
+            z = ops.conv2d(x, ops.WNWeight(V, g, cin, num_units, 1, 0), 1, 1,
+                           colsum=bool(use_mean_only_batch_normalization))
             if use_mean_only_batch_normalization:
                 fa = _fused(nonlinearity)
                 if fa is not None:

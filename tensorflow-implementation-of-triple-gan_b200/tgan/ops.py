@@ -35,6 +35,24 @@ def _zeros(shape, dtype=torch.float32):
     return t
 
 
+def arena_reset():
+    """Zero the statistics arena (one launch) -- called at the start of every phase of the step."""
+    a = ctx.arena()
+    _lib.call('tgan_fill_f32', _p(a), 0.0, a.numel(), _st())
+    ctx.arena_off = 0
+
+
+def arena_take(n):
+    """n zero-initialised floats that a GEMM epilogue may atomically accumulate into."""
+    a = ctx.arena()
+    n4 = (n + 3) // 4 * 4
+    if ctx.arena_off + n4 > a.numel():
+        arena_reset()
+    o = ctx.arena_off
+    ctx.arena_off += n4
+    return a[o:o + n]
+
+
 def _on():
     return ctx.tape is not None
 
@@ -170,7 +188,7 @@ def _im2col(x, N, H, W, C, ld, kh, kw, s, pt, pl, Ho, Wo):
     return col
 
 
-def conv2d(x, w, kh, kw, stride=1, padding='SAME'):
+def conv2d(x, w, kh, kw, stride=1, padding='SAME', colsum=False):
     """tf.nn.conv2d (NHWC x HWIO).  x may be 2-D [rows, C] with kh = kw = 1 (tf.matmul)."""
     Cout = w.key.shape[-1]
     C = x.C
@@ -194,8 +212,10 @@ def conv2d(x, w, kh, kw, stride=1, padding='SAME'):
     rows = N * Ho * Wo
     K = kh * kw * C
     direct = (kh == 1 and kw == 1 and stride == 1 and pt == 0 and pl == 0)
+    cs = None
     if use_tc:
-        z = tc.conv_fwd(x, w, geom)
+        cs = arena_take(Cout) if colsum else None
+        z = tc.conv_fwd(x, w, geom, cs)
     else:
         xd = x.data
         Wt = w.value()
@@ -209,6 +229,8 @@ def conv2d(x, w, kh, kw, stride=1, padding='SAME'):
         _sgemm(0, 0, rows, Cout, K, a, lda, Wt, Cout, z, Cout)
         del a
     out = Var(z.view(oshape), oshape, requires_grad=rg)
+    if cs is not None:
+        out.aux = {'colsum': cs}
     if rg:
         tape = ctx.tape
 
@@ -323,17 +345,13 @@ def bias_act(z, b, act='none', alpha=0.2):
             need_db = b is not None and b.requires_grad
             if a == 0:
                 du = dy
-                if need_db:
-                    cs = _new((C,), torch.float32)
-                    _lib.call('tgan_channel_stats', _p(dy), dt_code(dy), rows, C, _p(cs), None, _p(ctx.ws()), _st())
-                    _colsum_into(b.grad, cs)
+                if need_db:      # db += column sums of dy, accumulated in place by the reduction's last CTA
+                    _lib.call('tgan_channel_stats', _p(dy), dt_code(dy), rows, C, _p(b.grad), None, 1.0, _p(ctx.ws()),
+                              _st())
             else:
                 du = _new(z.shape, z.data.dtype)
-                cs = _new((C,), torch.float32)
                 _lib.call('tgan_act_bwd', _p(dy), dt_code(dy), _p(out.data), dt_code(out.data), _p(du), dt_code(du),
-                          rows, C, a, alpha, _p(cs), _p(ctx.ws()), _st())
-                if need_db:
-                    _colsum_into(b.grad, cs)
+                          rows, C, a, alpha, None, _p(b.grad) if need_db else None, _p(ctx.ws()), _st())
             if z.requires_grad:
                 add_grad(z, du if du.dtype == z.data.dtype else _cast(du, z.data.dtype))
         ctx.tape.nodes.append(bwd)
@@ -379,14 +397,15 @@ def mobn_act(z, b, pop_mean, train, act='none', alpha=0.2, decay=0.9):
     rg = _on() and (z.requires_grad or b.requires_grad)
     if ctx.building:
         return Var(None, z.shape, requires_grad=rg)
-    shift = _new((C,), torch.float32)
+    s = None
     if train:
-        s = _new((C,), torch.float32)
-        _lib.call('tgan_channel_stats', _p(z.data), dt_code(z.data), rows, C, _p(s), None, _p(ctx.ws()), _st())
-        _lib.call('tgan_mobn_finalize', _p(s), rows, C, _p(b.data), _p(pop_mean.data), decay, _p(shift), _st())
-    else:
-        _lib.call('tgan_mobn_eval_shift', _p(b.data), _p(pop_mean.data), C, _p(shift), _st())
-    y = _affine_act(z.data, rows, C, None, shift, a, alpha, _out_dtype(C))
+        s = z.aux.get('colsum') if z.aux else None      # accumulated by the tcgen05 GEMM epilogue
+        if s is None:
+            s = _new((C,), torch.float32)
+            _lib.call('tgan_channel_stats', _p(z.data), dt_code(z.data), rows, C, _p(s), None, 0.0, _p(ctx.ws()), _st())
+    y = _new(z.shape, _out_dtype(C))
+    _lib.call('tgan_mobn_apply', _p(z.data), dt_code(z.data), _p(y), dt_code(y), rows, C, _p(s), _p(b.data),
+              _p(pop_mean.data), decay, 1 if train else 0, a, alpha, _st())
     out = Var(y, z.shape, requires_grad=rg)
     if rg:
         def bwd():
@@ -396,9 +415,7 @@ def mobn_act(z, b, pop_mean, train, act='none', alpha=0.2, decay=0.9):
             du = _new(z.shape, z.data.dtype)
             cs = _new((C,), torch.float32)
             _lib.call('tgan_act_bwd', _p(dy), dt_code(dy), _p(out.data), dt_code(out.data), _p(du), dt_code(du), rows,
-                      C, a, alpha, _p(cs), _p(ctx.ws()), _st())
-            if b.requires_grad:
-                _colsum_into(b.grad, cs)
+                      C, a, alpha, _p(cs), _p(b.grad) if b.requires_grad else None, _p(ctx.ws()), _st())
             if z.requires_grad:
                 if train:
                     _lib.call('tgan_sub_channel_mean', _p(du), dt_code(du), _p(du), dt_code(du), rows, C, _p(cs), _st())
@@ -418,7 +435,7 @@ def batch_norm(x, gamma, beta, mm, mv, train, eps=1e-5, decay=0.9):
     mean, rstd = _new((C,), torch.float32), _new((C,), torch.float32)
     if train:
         s, ss = _new((C,), torch.float32), _new((C,), torch.float32)
-        _lib.call('tgan_channel_stats', _p(xd), dt_code(xd), rows, C, _p(s), _p(ss), _p(ctx.ws()), _st())
+        _lib.call('tgan_channel_stats', _p(xd), dt_code(xd), rows, C, _p(s), _p(ss), 0.0, _p(ctx.ws()), _st())
         _lib.call('tgan_bn_finalize', _p(s), _p(ss), rows, C, _p(gamma.data), _p(beta.data), eps, decay,
                   None if mm is None else _p(mm.data), None if mv is None else _p(mv.data), _p(mean), _p(rstd), _p(scale), _p(shift), _st())
     else:

@@ -73,7 +73,8 @@ def _pack(w, key, T, Nrows, K, st, sn, sk, taps=None):
     return c[key]
 
 
-def _igemm(x, N, H, W, C, ldx, wp, Kpad, taps, Nout, gh, gw, out, OH, OW, ldo, s=1, os_=1, oo=(0, 0), vh=0, vw=0):
+def _igemm(x, N, H, W, C, ldx, wp, Kpad, taps, Nout, gh, gw, out, OH, OW, ldo, s=1, os_=1, oo=(0, 0), vh=0, vw=0,
+           colsum=None):
     a = _lib.TganIgemmArgs()
     a.x, a.N, a.H, a.W, a.C, a.ldx = x.data_ptr(), N, H, W, C, ldx
     a.wp, a.T, a.Nout, a.Kpad = wp.data_ptr(), len(taps), Nout, Kpad
@@ -82,7 +83,7 @@ def _igemm(x, N, H, W, C, ldx, wp, Kpad, taps, Nout, gh, gw, out, OH, OW, ldo, s
     a.gh, a.gw, a.sy, a.sx = gh, gw, s, s
     a.out, a.odt, a.OH, a.OW, a.ldo = out.data_ptr(), dt_code(out), OH, OW, ldo
     a.osy, a.osx, a.ooy, a.oox, a.vh, a.vw = os_, os_, oo[0], oo[1], vh, vw
-    a.bias, a.colsum, a.act, a.alpha = None, None, 0, 1.0
+    a.bias, a.colsum, a.act, a.alpha = None, (None if colsum is None else colsum.data_ptr()), 0, 1.0
     _lib.call('tgan_igemm_bf16', ctypes.byref(a), _st())
 
 
@@ -117,7 +118,7 @@ def _flat(g):
     return g
 
 
-def conv_fwd(x, w, g):
+def conv_fwd(x, w, g, colsum=None):
     gf = _flat(g)
     C, Cout, kh, kw = g['C'], g['Cout'], g['kh'], g['kw']
     xd, ld = _bf16_padded(x.data, x.rows, C, x.ld)
@@ -126,7 +127,7 @@ def conv_fwd(x, w, g):
     taps = [(r - g['pt'], c - g['pl']) for r in range(kh) for c in range(kw)]
     z = _new((g['N'] * g['Ho'] * g['Wo'], Cout), torch.bfloat16)
     _igemm(xd, gf['N'], gf['H'], gf['W'], C, ld, wp, Kpad, taps, Cout, gf['Ho'], gf['Wo'], z, gf['Ho'], gf['Wo'], Cout,
-           s=g['s'])
+           s=g['s'], colsum=colsum)
     return z
 
 

@@ -99,6 +99,7 @@ class Train(Train_base):
             o._state()
         self.loss_buf = torch.zeros(3, dtype=torch.float32, device=ctx.device)
         ctx.ws()
+        ctx.arena()
         if not ctx.rng.injected:
             ctx.rng.counter()
         if c.DATA_NAME == 'cifar10' and hasattr(self.model, '_whitener'):
@@ -126,6 +127,7 @@ class Train(Train_base):
             p.requires_grad = True
         fb = self.store.flat[group]
         _lib.call('tgan_fill_f32', fb['grad'].data_ptr(), 0.0, fb['n'], ops._st())
+        ops.arena_reset()
         return fb
 
     def _apply(self, fb, opt, ema=None, group=None):
@@ -145,6 +147,7 @@ class Train(Train_base):
         pre, K = self._pre(), c.NUM_CLASSES
         cif = c.DATA_NAME == 'cifar10' and hasattr(m, '_whitener')
         # ---- phase D: sess.run([d_solver, d_loss]) (:267) ----
+        ops.arena_reset()
         with no_grad():
             c_unl_d, _ = m.classifier(pre(v['x_u_d']), train, reuse=True, tag='D/C_unl_d')
             c_unl, _ = m.classifier(pre(v['x_u_c']), train, reuse=True, tag='D/C_unl')

@@ -141,7 +141,7 @@ def test_weightnorm_conv_and_dense():
 
 
 @pytest.mark.parametrize('train', [True, False])
-@pytest.mark.parametrize('shape', [(4, 6, 6, 8), (7, 10), (3, 5, 5, 3)])
+@pytest.mark.parametrize('shape', [(4, 6, 6, 8), (7, 10), (3, 5, 5, 3), (16, 16, 16, 256)])
 def test_mobn_act(train, shape):
     from tgan import core, ops
     rng = np.random.default_rng(4)
@@ -165,7 +165,7 @@ def test_mobn_act(train, shape):
     assert relerr(tnp(ppm.data), S['pm'].numpy()) < TOL
 
 
-@pytest.mark.parametrize('shape', [(4, 6, 6, 8), (16, 12), (5, 4, 4, 3)])
+@pytest.mark.parametrize('shape', [(4, 6, 6, 8), (16, 12), (5, 4, 4, 3), (16, 8, 8, 128), (16, 32, 32, 128)])
 def test_batch_norm_train(shape):
     from tgan import core, ops
     rng = np.random.default_rng(5)
@@ -192,12 +192,13 @@ def test_batch_norm_train(shape):
     assert relerr(tnp(pmv.data), S['s/moving_variance'].numpy()) < 5e-5
 
 
+@pytest.mark.parametrize('shape', [(5, 4, 4, 12), (16, 8, 8, 128)])
 @pytest.mark.parametrize('act', ['none', 'relu', 'lrelu', 'tanh', 'sigmoid', 'softplus'])
-def test_bias_act(act):
+def test_bias_act(act, shape):
     from tgan import core, ops
     import torch.nn.functional as F
     rng = np.random.default_rng(6)
-    z, b = rng.standard_normal((5, 4, 4, 12)) * 2, rng.standard_normal(12)
+    z, b = rng.standard_normal(shape) * 2, rng.standard_normal(shape[-1])
     f = dict(none=lambda t: t, relu=F.relu, lrelu=O.lrelu_cifar, tanh=torch.tanh, sigmoid=torch.sigmoid,
              softplus=F.softplus)[act]
     zt, bt = T(z, True), T(b, True)
@@ -355,3 +356,25 @@ def test_adam_ema_multi_step():
         mine.apply_flat(fb, 0.25, ema, 0.9999)       # grad_scale = 1/world folds the DP average
     assert relerr(tnp(fb['theta'][:n]), P['w'].numpy()) < 1e-5
     assert relerr(tnp(ema[:n]), ema_ref.numpy()) < 1e-6
+
+
+@pytest.mark.parametrize('rows,C,dt', [(16384, 128, 'f32'), (16384, 128, 'bf16'), (4096, 512, 'f32'), (1024, 256, 'bf16'),
+                                       (102400, 128, 'bf16'), (1600, 8192, 'f32'), (1000, 10, 'f32'), (77, 3, 'f32')])
+def test_channel_stats_large(rows, C, dt):
+    """single-launch column reduction (last-CTA fold) at real activation sizes, incl. accumulate-in-place"""
+    from tgan import _lib
+    rng = np.random.default_rng(12)
+    x = (rng.standard_normal((rows, C)) + 0.3).astype(np.float32)
+    xt = torch.from_numpy(x).cuda()
+    if dt == 'bf16':
+        xt = xt.to(torch.bfloat16)
+        x = xt.float().cpu().numpy()
+    s = torch.full((C,), 5.0, device='cuda')
+    ss = torch.zeros(C, device='cuda')
+    ws = torch.empty(4 * 256 * C + 2 * C, device="cuda")
+    for beta in (0.0, 1.0):
+        _lib.call('tgan_channel_stats', xt.data_ptr(), 0 if dt == 'f32' else 1, rows, C, s.data_ptr(), ss.data_ptr(), beta,
+                  ws.data_ptr(), 0)
+    ref = x.astype(np.float64).sum(0)
+    assert relerr(tnp(s), 2 * ref) < 1e-5
+    assert relerr(tnp(ss), 2 * (x.astype(np.float64) ** 2).sum(0)) < 1e-5
