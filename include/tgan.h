@@ -80,7 +80,10 @@ typedef struct {
   int osy, osx, ooy, oox; /* output placement (stride / offset)                */
   int vh, vw;          /* number of valid grid rows/cols actually stored       */
   const float* bias;   /* optional fp32 [Nout] added before the store          */
-  float* colsum;       /* optional fp32 [Nout]: += column sums of the stored fp32 values */
+  float* colsum;       /* optional fp32 [nseg][Nout]: += per-channel sums of the stored values, per batch segment */
+  int nseg;            /* 0/1 = whole batch; up to 4 segments of consecutive images (several network calls grouped
+                          in one launch keep their own mean-only-BN statistics) */
+  int seg_end[4];      /* exclusive image index where segment i ends */
   int act;             /* TGAN_ACT_* applied after bias (before store)         */
   float alpha;
 } tgan_igemm_args;

@@ -78,6 +78,7 @@ struct IgParams {
   int odt, OH, OW, ldo, osy, osx, ooy, oox, vh, vw, Nout;
   const float* bias;
   float* colsum;
+  int nseg, seg_end[4];
   int act;
   float alpha;
   int dbg;   // experiments only (TGAN_IGEMM_DBG): 1 skip activation loads, 2 skip weight loads, 4 skip stores
@@ -88,7 +89,7 @@ struct IgParams {
 // run alone on their scheduler (no latency hiding), so per-element dependent integer chains would dominate the tile.
 template <int TW, typename TO>
 __device__ __forceinline__ void ig_store_chunk(const IgParams& p, TO* __restrict__ out, const float (&v)[32], int pbase,
-                                               int tx, int ty, int ng, int co, bool cvalid, float& csum) {
+                                               int tx, int ty, int ng, int co, bool cvalid, float (&csum)[4]) {
   const int ppi = p.th * p.tw;
   const int pstep = p.osx * p.ldo;
 #pragma unroll
@@ -99,11 +100,16 @@ __device__ __forceinline__ void ig_store_chunk(const IgParams& p, TO* __restrict
     const bool rowok = cvalid && (n < p.N) && (oy < p.vh);
     const int base = ((n * p.OH + (oy * p.osy + p.ooy)) * p.OW + (ox0 * p.osx + p.oox)) * p.ldo + co;
     const int lim = p.vw - ox0;          // pixel jc is inside the valid width iff jc < lim
+    const int sg = (n >= p.seg_end[0]) + (n >= p.seg_end[1]) + (n >= p.seg_end[2]);   // batch segment of this image
 #pragma unroll
     for (int jc = 0; jc < TW; ++jc) {
       const bool ok = rowok && (jc < lim);
       const float x = v[sgm * TW + jc];
-      if (p.colsum) csum += ok ? x : 0.f;
+      if (p.colsum) {
+        const float xs = ok ? x : 0.f;
+        csum[0] += sg == 0 ? xs : 0.f; csum[1] += sg == 1 ? xs : 0.f;
+        csum[2] += sg == 2 ? xs : 0.f; csum[3] += sg == 3 ? xs : 0.f;
+      }
       if (ok) {
         if constexpr (sizeof(TO) == 2) out[base + jc * pstep] = __float2bfloat16_rn(x);
         else out[base + jc * pstep] = x;
@@ -221,7 +227,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       const int co = ct * 128 + q * 32 + lane;
       const bool cvalid = co < p.Nout;
       const float bias = (p.bias && cvalid) ? p.bias[co] : 0.f;
-      float csum = 0.f;
+      float csum[4] = {0.f, 0.f, 0.f, 0.f};
       mbar_wait(&tfull[acc], accphase);
       tc_fence_after();
       for (int c0 = 0; c0 < IG_NPIX; c0 += 32) {
@@ -266,7 +272,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
           }
         }
       }
-      if (p.colsum && cvalid) atomicAdd(&p.colsum[co], csum);
+      if (p.colsum && cvalid) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          if (g < p.nseg && csum[g] != 0.f) atomicAdd(&p.colsum[g * p.Nout + co], csum[g]);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -473,6 +483,9 @@ extern "C" int tgan_igemm_bf16(const tgan_igemm_args* a, void* stream) {
   p.osy = a->osy > 0 ? a->osy : 1; p.osx = a->osx > 0 ? a->osx : 1; p.ooy = a->ooy; p.oox = a->oox;
   p.vh = a->vh > 0 ? a->vh : a->gh; p.vw = a->vw > 0 ? a->vw : a->gw; p.Nout = a->Nout;
   { const char* e = getenv("TGAN_IGEMM_DBG"); p.dbg = e ? atoi(e) : 0; }
+  p.nseg = a->nseg > 1 ? a->nseg : 1;
+  TGAN_CHECK_ARG(p.nseg <= 4, "igemm: at most 4 batch segments");
+  for (int i = 0; i < 4; ++i) p.seg_end[i] = (a->nseg > 1 && i < a->nseg - 1) ? a->seg_end[i] : 0x7fffffff;
   p.bias = a->bias; p.colsum = a->colsum; p.act = a->act; p.alpha = a->alpha == 0.f ? 1.f : a->alpha;
   const size_t smem_bytes = 1024 + (size_t)IG_STAGES * IG_STAGE_BYTES + 256;
 

@@ -49,7 +49,8 @@ class TganIgemmArgs(ctypes.Structure):
                 ('out', ctypes.c_void_p), ('odt', ctypes.c_int),
                 ('OH', ctypes.c_int), ('OW', ctypes.c_int), ('ldo', ctypes.c_int), ('osy', ctypes.c_int),
                 ('osx', ctypes.c_int), ('ooy', ctypes.c_int), ('oox', ctypes.c_int), ('vh', ctypes.c_int),
-                ('vw', ctypes.c_int), ('bias', ctypes.c_void_p), ('colsum', ctypes.c_void_p), ('act', ctypes.c_int),
+                ('vw', ctypes.c_int), ('bias', ctypes.c_void_p), ('colsum', ctypes.c_void_p), ('nseg', ctypes.c_int), ('seg_end', ctypes.c_int * 4),
+                ('act', ctypes.c_int),
                 ('alpha', ctypes.c_float)]
 
 

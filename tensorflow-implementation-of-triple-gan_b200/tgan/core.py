@@ -180,10 +180,16 @@ class Tape:
         self.post = []      # weight-norm backward hooks run once after all nodes
 
     def backward(self):
-        for fn in reversed(self.nodes):
-            fn()
-        for fn in self.post:
-            fn()
+        """Run the recorded closures in reverse, then the once-per-phase weight-norm backward hooks.  The tape is
+        made current for the duration, so it can be differentiated outside the `recording()` block that built it."""
+        old, ctx.tape = ctx.tape, self
+        try:
+            for fn in reversed(self.nodes):
+                fn()
+            for fn in self.post:
+                fn()
+        finally:
+            ctx.tape = old
         self.nodes, self.post = [], []
 
 

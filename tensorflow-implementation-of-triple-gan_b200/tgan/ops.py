@@ -53,6 +53,67 @@ def arena_take(n):
     return a[o:o + n]
 
 
+class TagList:
+    """RNG tags of several network calls grouped into one batch: [(tag, samples), ...].  `tags + '/noise'` appends
+    the suffix to every tag, so builder code written for one call works unchanged on a grouped batch."""
+
+    def __init__(self, items):
+        self.items = list(items)
+
+    def __add__(self, suffix):
+        return TagList([(t + suffix, n) for t, n in self.items])
+
+    def __str__(self):
+        return '|'.join(t for t, _ in self.items)
+
+
+def _segs(x):
+    return x.aux.get('segs') if x.aux else None
+
+
+def _prop(out, x):
+    """carry the batch segmentation (samples per grouped network call) from x to out"""
+    sg = _segs(x)
+    if sg is not None:
+        out.aux = dict(out.aux or {}, segs=sg)
+    return out
+
+
+def group_batch(vs, tags=None):
+    """Concatenate the inputs of several calls of the same network along the batch axis.  Per-sample work
+    (convolutions, pooling, dropout, noise) then runs once on the whole group, while batch statistics stay per call
+    (the segments).  No gradient flows to the inputs."""
+    shape = (sum(v.shape[0] for v in vs),) + tuple(vs[0].shape[1:])
+    if ctx.building:
+        out = Var(None, shape)
+    else:
+        t = torch.empty(shape, dtype=vs[0].data.dtype, device=ctx.device)
+        per, o, es = int(np.prod(shape[1:])), 0, t.element_size()
+        for v in vs:      # same elements per sample in any view ([N,28,28,1] vs [N,784]); dtype converted on the fly
+            assert v.ld == v.C and int(np.prod(v.shape[1:])) == per
+            n = v.shape[0] * per
+            _lib.call('tgan_copy_channels', _p(v.data), dt_code(v.data), n, t.data_ptr() + o * per * es, dt_code(t), n,
+                      1, n, _st())
+            o += v.shape[0]
+        out = Var(t, shape)
+    out.aux = {'segs': [v.shape[0] for v in vs]}
+    return out
+
+
+def _rng_normal(tag, shape):
+    rng = ctx.rng
+    if isinstance(tag, TagList):
+        return torch.cat([rng.normal(t, (n,) + tuple(shape[1:])) for t, n in tag.items], 0)
+    return rng.normal(tag, shape)
+
+
+def _rng_mask(tag, shape, rate):
+    rng = ctx.rng
+    if isinstance(tag, TagList):
+        return torch.cat([rng.keep_mask(t, (n,) + tuple(shape[1:]), rate) for t, n in tag.items], 0)
+    return rng.keep_mask(tag, shape, rate)
+
+
 def _on():
     return ctx.tape is not None
 
@@ -205,7 +266,7 @@ def conv2d(x, w, kh, kw, stride=1, padding='SAME', colsum=False):
     oshape = (N, Cout) if len(x.shape) == 2 else (N, Ho, Wo, Cout)
     rg = _on() and (x.requires_grad or w.requires_grad)
     if ctx.building:
-        return Var(None, oshape, requires_grad=rg)
+        return _prop(Var(None, oshape, requires_grad=rg), x)
     from . import tc
     geom = dict(N=N, H=H, W=W, C=C, kh=kh, kw=kw, s=stride, pt=pt, pl=pl, Ho=Ho, Wo=Wo, Cout=Cout)
     use_tc = ctx.math == 'bf16' and tc.conv_eligible(geom, x)
@@ -213,9 +274,11 @@ def conv2d(x, w, kh, kw, stride=1, padding='SAME', colsum=False):
     K = kh * kw * C
     direct = (kh == 1 and kw == 1 and stride == 1 and pt == 0 and pl == 0)
     cs = None
+    segs = _segs(x)
     if use_tc:
-        cs = arena_take(Cout) if colsum else None
-        z = tc.conv_fwd(x, w, geom, cs)
+        seg_ok = segs is None or (len(x.shape) == 4 and kh * kw > 1 and len(segs) <= 4)   # spatial convs: per-image segments
+        cs = arena_take(Cout * (len(segs) if segs else 1)) if (colsum and seg_ok) else None
+        z = tc.conv_fwd(x, w, geom, cs, segs if cs is not None else None)
     else:
         xd = x.data
         Wt = w.value()
@@ -228,9 +291,9 @@ def conv2d(x, w, kh, kw, stride=1, padding='SAME', colsum=False):
         z = _new((rows, Cout), torch.float32)
         _sgemm(0, 0, rows, Cout, K, a, lda, Wt, Cout, z, Cout)
         del a
-    out = Var(z.view(oshape), oshape, requires_grad=rg)
+    out = _prop(Var(z.view(oshape), oshape, requires_grad=rg), x)
     if cs is not None:
-        out.aux = {'colsum': cs}
+        out.aux = dict(out.aux or {}, colsum=cs)
     if rg:
         tape = ctx.tape
 
@@ -336,7 +399,7 @@ def bias_act(z, b, act='none', alpha=0.2):
     if ctx.building:
         return Var(None, z.shape, requires_grad=rg)
     y = _affine_act(z.data, rows, C, None, None if b is None else b.data, a, alpha, _out_dtype(C))
-    out = Var(y, z.shape, requires_grad=rg)
+    out = _prop(Var(y, z.shape, requires_grad=rg), z)
     if rg:
         def bwd():
             if out.grad is None:
@@ -391,34 +454,53 @@ def activation(x, act, alpha=0.2):
 def mobn_act(z, b, pop_mean, train, act='none', alpha=0.2, decay=0.9):
     """mean_only_batch_norm_impl + nonlinearity (nn.py:147-187, :517).
     train: y = act(z - mean_{rows}(z) + b), pop_mean <- decay*pop_mean + (1-decay)*mean
-    eval : y = act(z - pop_mean + b)."""
+    eval : y = act(z - pop_mean + b).
+    A grouped batch (ops.group_batch) keeps one mean per call: statistics, apply and their backward run per segment
+    of rows, everything else of the layer ran once on the whole group."""
     a = ACT[act]
     C, rows = z.C, z.rows
     rg = _on() and (z.requires_grad or b.requires_grad)
     if ctx.building:
-        return Var(None, z.shape, requires_grad=rg)
-    s = None
-    if train:
-        s = z.aux.get('colsum') if z.aux else None      # accumulated by the tcgen05 GEMM epilogue
-        if s is None:
-            s = _new((C,), torch.float32)
-            _lib.call('tgan_channel_stats', _p(z.data), dt_code(z.data), rows, C, _p(s), None, 0.0, _p(ctx.ws()), _st())
+        return _prop(Var(None, z.shape, requires_grad=rg), z)
+    segs = _segs(z) or [z.shape[0]]
+    rps = rows // sum(segs)                      # rows per sample
+    bounds, r0 = [], 0
+    for n in segs:
+        bounds.append((r0, n * rps))
+        r0 += n * rps
+    zd = z.data
+    ez = zd.element_size()
+    cs_all = z.aux.get('colsum') if z.aux else None      # [nseg, C] accumulated by the tcgen05 GEMM epilogue
     y = _new(z.shape, _out_dtype(C))
-    _lib.call('tgan_mobn_apply', _p(z.data), dt_code(z.data), _p(y), dt_code(y), rows, C, _p(s), _p(b.data),
-              _p(pop_mean.data), decay, 1 if train else 0, a, alpha, _st())
-    out = Var(y, z.shape, requires_grad=rg)
+    ey = y.element_size()
+    for i, (r0, nr) in enumerate(bounds):
+        s = None
+        if train:
+            if cs_all is not None:
+                s = cs_all[i * C:(i + 1) * C]
+            else:
+                s = _new((C,), torch.float32)
+                _lib.call('tgan_channel_stats', zd.data_ptr() + r0 * C * ez, dt_code(zd), nr, C, _p(s), None, 0.0,
+                          _p(ctx.ws()), _st())
+        _lib.call('tgan_mobn_apply', zd.data_ptr() + r0 * C * ez, dt_code(zd), y.data_ptr() + r0 * C * ey, dt_code(y), nr, C,
+                  _p(s), _p(b.data), _p(pop_mean.data), decay, 1 if train else 0, a, alpha, _st())
+    out = _prop(Var(y, z.shape, requires_grad=rg), z)
     if rg:
         def bwd():
             if out.grad is None:
                 return
             dy = out.grad
-            du = _new(z.shape, z.data.dtype)
-            cs = _new((C,), torch.float32)
-            _lib.call('tgan_act_bwd', _p(dy), dt_code(dy), _p(out.data), dt_code(out.data), _p(du), dt_code(du), rows,
-                      C, a, alpha, _p(cs), _p(b.grad) if b.requires_grad else None, _p(ctx.ws()), _st())
+            du = _new(z.shape, zd.dtype)
+            ed, eu = dy.element_size(), du.element_size()
+            for r0, nr in bounds:
+                cs = _new((C,), torch.float32)
+                _lib.call('tgan_act_bwd', dy.data_ptr() + r0 * C * ed, dt_code(dy), y.data_ptr() + r0 * C * ey, dt_code(y),
+                          du.data_ptr() + r0 * C * eu, dt_code(du), nr, C, a, alpha, _p(cs),
+                          _p(b.grad) if b.requires_grad else None, _p(ctx.ws()), _st())
+                if z.requires_grad and train:
+                    _lib.call('tgan_sub_channel_mean', du.data_ptr() + r0 * C * eu, dt_code(du), du.data_ptr() + r0 * C * eu,
+                              dt_code(du), nr, C, _p(cs), _st())
             if z.requires_grad:
-                if train:
-                    _lib.call('tgan_sub_channel_mean', _p(du), dt_code(du), _p(du), dt_code(du), rows, C, _p(cs), _st())
                 add_grad(z, du)
         ctx.tape.nodes.append(bwd)
     return out
@@ -477,12 +559,12 @@ def add_noise(x, std, tag):
     y = _new(x.shape)
     rng = ctx.rng
     if rng.injected:
-        noise = rng.normal(tag, x.shape)
+        noise = _rng_normal(tag, x.shape)
         _lib.call('tgan_add_noise', _p(xd), dt_code(xd), _p(y), dt_code(y), n, std, _p(noise), 0, 0, None, _st())
     else:
         _lib.call('tgan_add_noise', _p(xd), dt_code(xd), _p(y), dt_code(y), n, std, None, rng.seed,
-                  rng.stream_id(tag), _p(rng.counter()), _st())
-    out = Var(y, x.shape, requires_grad=rg)
+                  rng.stream_id(str(tag)), _p(rng.counter()), _st())
+    out = _prop(Var(y, x.shape, requires_grad=rg), x)
     if rg:
         def bwd():
             if out.grad is not None:
@@ -503,13 +585,13 @@ def dropout(x, rate, tag, training=True):
     y = _new(x.shape)
     rng = ctx.rng
     if rng.injected:
-        mask = rng.keep_mask(tag, x.shape, rate)
+        mask = _rng_mask(tag, x.shape, rate)
         _lib.call('tgan_dropout', _p(xd), dt_code(xd), _p(y), dt_code(y), _p(mask), n, rate, 0, 0, 0, None, _st())
     else:
         mask = _new(x.shape, torch.uint8)
         _lib.call('tgan_dropout', _p(xd), dt_code(xd), _p(y), dt_code(y), _p(mask), n, rate, 1, rng.seed,
-                  rng.stream_id(tag), _p(rng.counter()), _st())
-    out = Var(y, x.shape, requires_grad=rg)
+                  rng.stream_id(str(tag)), _p(rng.counter()), _st())
+    out = _prop(Var(y, x.shape, requires_grad=rg), x)
     if rg:
         def bwd():
             if out.grad is None:
@@ -532,7 +614,7 @@ def max_pool2(x):
     xd = x.data
     y, idx = _new(oshape, xd.dtype), _new(oshape, torch.uint8)
     _lib.call('tgan_maxpool2_fwd', _p(xd), dt_code(xd), _p(y), _p(idx), N, H, W, C, _st())
-    out = Var(y, oshape, requires_grad=rg)
+    out = _prop(Var(y, oshape, requires_grad=rg), x)
     if rg:
         def bwd():
             if out.grad is None:
@@ -556,7 +638,7 @@ def global_pool(x, mode):
     y = _new((N, C), xd.dtype)
     idx = _new((N, C), torch.uint8) if m == 0 else None
     _lib.call('tgan_global_pool_fwd', _p(xd), dt_code(xd), _p(y), dt_code(y), _p(idx), N, H * W, C, m, _st())
-    out = Var(y, (N, C), requires_grad=rg)
+    out = _prop(Var(y, (N, C), requires_grad=rg), x)
     if rg:
         def bwd():
             if out.grad is None:
@@ -610,7 +692,7 @@ def reshape(x, shape):
     rg = _on() and x.requires_grad
     if ctx.building:
         return Var(None, shape, requires_grad=rg)
-    out = Var(x.data.view(shape), shape, requires_grad=rg)
+    out = _prop(Var(x.data.view(shape), shape, requires_grad=rg), x)
     if rg:
         def bwd():
             if out.grad is not None:
@@ -698,6 +780,35 @@ def loss_c(c_real, y_l_c, c_unl, c_rep, d_unl_logits, c_fake, y_g, lambdas):
               _p(_f32logits(c_fake)), _p(y_g.data), c_fake.rows, K, _p(lambdas), _p(val), _p(g_real), _p(g_unl),
               _p(g_rep), _p(g_fake), _st())
     return Loss(val, [(c_real, g_real), (c_unl, g_unl), (c_rep, g_rep), (c_fake, g_fake)])
+
+
+def loss_d_grouped(logits, nr, nf, nu):
+    """d_loss on one grouped D pass: rows [0,nr) real, [nr,nr+nf) fake, [nr+nf, ...) unlabelled (train_base.py:123-126)"""
+    if ctx.building:
+        return Loss(None, [])
+    x = _f32logits(logits)
+    val, g = _new((1,), torch.float32), _new(logits.shape, torch.float32)
+    _lib.call('tgan_loss_d', x.data_ptr(), nr, x.data_ptr() + 4 * nr, nf, x.data_ptr() + 4 * (nr + nf), nu, _p(val),
+              g.data_ptr(), g.data_ptr() + 4 * nr, g.data_ptr() + 4 * (nr + nf), _st())
+    return Loss(val, [(logits, g)])
+
+
+def loss_c_grouped(logits, segs, has_rep, y_l_c, d_unl_logits, y_g, lambdas):
+    """c_loss on one grouped C pass with rows ordered [real | unl | (rep) | fake] (train_base.py:130-152)"""
+    if ctx.building:
+        return Loss(None, [])
+    K = logits.shape[1]
+    x = _f32logits(logits)
+    offs = [0]
+    for n in segs:
+        offs.append(offs[-1] + n)
+    val, g = _new((1,), torch.float32), _new(logits.shape, torch.float32)
+    at = lambda t, i: t.data_ptr() + 4 * K * offs[i]
+    i_fake = 3 if has_rep else 2
+    _lib.call('tgan_loss_c', at(x, 0), _p(y_l_c.data), segs[0], at(x, 1), at(x, 2) if has_rep else None,
+              _p(_f32logits(d_unl_logits)), segs[1], at(x, i_fake), _p(y_g.data), segs[i_fake], K, _p(lambdas), _p(val),
+              at(g, 0), at(g, 1), at(g, 2) if has_rep else None, at(g, i_fake), _st())
+    return Loss(val, [(logits, g)])
 
 
 def backward(loss):

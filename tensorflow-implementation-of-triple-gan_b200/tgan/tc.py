@@ -74,7 +74,7 @@ def _pack(w, key, T, Nrows, K, st, sn, sk, taps=None):
 
 
 def _igemm(x, N, H, W, C, ldx, wp, Kpad, taps, Nout, gh, gw, out, OH, OW, ldo, s=1, os_=1, oo=(0, 0), vh=0, vw=0,
-           colsum=None):
+           colsum=None, segs=None):
     a = _lib.TganIgemmArgs()
     a.x, a.N, a.H, a.W, a.C, a.ldx = x.data_ptr(), N, H, W, C, ldx
     a.wp, a.T, a.Nout, a.Kpad = wp.data_ptr(), len(taps), Nout, Kpad
@@ -84,6 +84,11 @@ def _igemm(x, N, H, W, C, ldx, wp, Kpad, taps, Nout, gh, gw, out, OH, OW, ldo, s
     a.out, a.odt, a.OH, a.OW, a.ldo = out.data_ptr(), dt_code(out), OH, OW, ldo
     a.osy, a.osx, a.ooy, a.oox, a.vh, a.vw = os_, os_, oo[0], oo[1], vh, vw
     a.bias, a.colsum, a.act, a.alpha = None, (None if colsum is None else colsum.data_ptr()), 0, 1.0
+    if segs and len(segs) > 1:
+        a.nseg, e = len(segs), 0
+        for i, n in enumerate(segs[:-1]):
+            e += n
+            a.seg_end[i] = e
     _lib.call('tgan_igemm_bf16', ctypes.byref(a), _st())
 
 
@@ -118,7 +123,7 @@ def _flat(g):
     return g
 
 
-def conv_fwd(x, w, g, colsum=None):
+def conv_fwd(x, w, g, colsum=None, segs=None):
     gf = _flat(g)
     C, Cout, kh, kw = g['C'], g['Cout'], g['kh'], g['kw']
     xd, ld = _bf16_padded(x.data, x.rows, C, x.ld)
@@ -127,7 +132,7 @@ def conv_fwd(x, w, g, colsum=None):
     taps = [(r - g['pt'], c - g['pl']) for r in range(kh) for c in range(kw)]
     z = _new((g['N'] * g['Ho'] * g['Wo'], Cout), torch.bfloat16)
     _igemm(xd, gf['N'], gf['H'], gf['W'], C, ld, wp, Kpad, taps, Cout, gf['Ho'], gf['Wo'], z, gf['Ho'], gf['Wo'], Cout,
-           s=g['s'], colsum=colsum)
+           s=g['s'], colsum=colsum, segs=(segs if gf is g else None))
     return z
 
 

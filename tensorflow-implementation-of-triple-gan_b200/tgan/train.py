@@ -108,6 +108,21 @@ class Train(Train_base):
         ddp.broadcast_params(self.store, 0, self.pg)
         return self
 
+    def load_state(self, P=None, S=None, adam=None):
+        """Overwrite parameters (P), state variables (S: pop_mean / BN moving statistics) and Adam slots
+        (adam = {network: (m, v)}), all dicts keyed by TF variable name.  Used for checkpoint import
+        (Training/Saver.py:14-66 names) and by the teacher-forced multi-step parity tests."""
+        self.store.load_numpy(P or {}, S or {})
+        for grp, (m, v) in (adam or {}).items():
+            fb = self.store.flat[grp]
+            for p, o in zip(fb['params'], fb['offsets']):
+                for slot, src in (('m', m), ('v', v)):
+                    if p.name in src:
+                        t = torch.as_tensor(np.asarray(src[p.name], np.float32)).reshape(-1)
+                        fb[slot][o:o + p.size].copy_(t)
+        self.store.bump()
+        return self
+
     # ------------------------------------------------------------------ one step ------------------
     def _set_scalars(self, lambda_1, lambda_2, lr, cla_lr):
         if (lambda_1, lambda_2) != self._lam:
@@ -142,52 +157,88 @@ class Train(Train_base):
         return lambda t: t
 
     def _step_impl(self, train=True):
+        """The three phases with TF's per-`sess.run` pruning, scheduled for the GPU:
+
+        * calls of the same network inside a phase are GROUPED into one batch (ops.group_batch): per-sample work
+          runs once on the group; batch statistics (mean-only BN) stay per call through the batch segments, so every
+          value equals the separate calls of the reference graph.  D has no batch statistics at all, so its three
+          phase-D calls are one pass over 250 samples.  (Models with tf.contrib batch_norm in C keep separate calls.)
+        * the generator forward of phase G is the phase-D forward: same weights G0, same z / y, no stochastic op, so
+          the tensors are identical; it is recorded once on its own tape and differentiated in phase G.
+        """
         m, c = self.model, self.config
         v = {k: ops.Var(t, tuple(t.shape)) for k, t in self.inputs.items()}
         pre, K = self._pre(), c.NUM_CLASSES
         cif = c.DATA_NAME == 'cifar10' and hasattr(m, '_whitener')
+        grouped_c = cif                      # mean-only-BN classifier: segment-aware ops
+        nLD, nUD, nUC, nG, nLC = (c.BATCH_SIZE_L_D, c.BATCH_SIZE_U_D, c.BATCH_SIZE_U_C, c.BATCH_SIZE_G, c.BATCH_SIZE_L_C)
+        TL = ops.TagList
         # ---- phase D: sess.run([d_solver, d_loss]) (:267) ----
         ops.arena_reset()
         with no_grad():
-            c_unl_d, _ = m.classifier(pre(v['x_u_d']), train, reuse=True, tag='D/C_unl_d')
-            c_unl, _ = m.classifier(pre(v['x_u_c']), train, reuse=True, tag='D/C_unl')
-            idx_d, oh_d = ops.argmax_onehot(c_unl_d, K)
-            idx_u, oh_u = ops.argmax_onehot(c_unl, K)
+            if grouped_c:
+                lg, _ = m.classifier(pre(ops.group_batch([v['x_u_d'], v['x_u_c']])), train, reuse=True,
+                                     tag=TL([('D/C_unl_d', nUD), ('D/C_unl', nUC)]))
+                idx, oh = ops.argmax_onehot(lg, K)
+                idx_d, idx_u = ops.Var(idx.data[:nUD], (nUD,)), ops.Var(idx.data[nUD:], (nUC,))
+                oh_d, oh_u = ops.Var(oh.data[:nUD], (nUD, K)), ops.Var(oh.data[nUD:], (nUC, K))
+            else:
+                c_unl_d, _ = m.classifier(pre(v['x_u_d']), train, reuse=True, tag='D/C_unl_d')
+                c_unl, _ = m.classifier(pre(v['x_u_c']), train, reuse=True, tag='D/C_unl')
+                idx_d, oh_d = ops.argmax_onehot(c_unl_d, K)
+                idx_u, oh_u = ops.argmax_onehot(c_unl, K)
+        for p in self.g_vars:                # record G(z, y) once, on its own tape, for phase G's backward
+            p.requires_grad = True
+        with recording() as tape_g:
             G = m.good_generator(v['z_g'], v['y_g'], reuse=True, tag='D/G')
-        from .good_gan_cifar10 import concat_batch
+        G_const = ops.Var(G.data, G.shape)   # phase D sees the generated images as constants (var_list = d_vars)
         fb = self._begin('discriminator', self.d_vars)
         with recording():
-            X_P, Y_P = concat_batch([v['x_l_d'], v['x_u_d']]), concat_batch([v['y_l_d'], oh_d])
-            _, dr = m.discriminator(X_P, Y_P, reuse=True, tag='D/D_real')
-            _, df = m.discriminator(G, v['y_g'], reuse=True, tag='D/D_fake')
-            _, du = m.discriminator(v['x_u_c'], oh_u, reuse=True, tag='D/D_unl')
-            d_loss = ops.loss_d(dr, df, du)
+            X = ops.group_batch([v['x_l_d'], v['x_u_d'], G_const, v['x_u_c']])
+            Y = ops.group_batch([v['y_l_d'], oh_d, v['y_g'], oh_u])
+            X.aux = None                     # D is per-sample: one plain batch of 250
+            _, dl = m.discriminator(X, Y, reuse=True, tag=TL([('D/D_real', nLD + nUD), ('D/D_fake', nG), ('D/D_unl', nUC)]))
+            d_loss = ops.loss_d_grouped(dl, nLD + nUD, nG, nUC)
             ops.backward(d_loss)
         self._apply(fb, self.d_optimizer, group='discriminator')
-        self.aux = dict(idx_unl_d=idx_d, idx_unl=idx_u, G_phaseD=G, d_logits=(dr, df, du))
+        self.aux = dict(idx_unl_d=idx_d, idx_unl=idx_u, G_phaseD=G, d_logits=dl)
         # ---- phase G: sess.run([g_solver, g_loss]) (:270) ----
         fb = self._begin('good_generator', self.g_vars)
-        with recording():
-            G = m.good_generator(v['z_g'], v['y_g'], reuse=True, tag='G/G')
+        with recording() as tape_d:
             _, df = m.discriminator(G, v['y_g'], reuse=True, tag='G/D_fake')
             g_loss = ops.loss_g(df)
-            ops.backward(g_loss)
+            g_loss.seed()
+            tape_d.backward()                # d g_loss / d G through D1 (dgrad only)
+        tape_g.backward()                    # ... and through the generator recorded in phase D
         self._apply(fb, self.g_optimizer, group='good_generator')
         # ---- phase C: sess.run([c_solver, c_loss]) (:275) ----
         fb = self._begin('classifier', self.c_vars)
+        with no_grad():
+            G = m.good_generator(v['z_g'], v['y_g'], reuse=True, tag='C/G')
         with recording():
-            c_real, _ = m.classifier(pre(v['x_l_c']), train, reuse=True, tag='C/C_real')
-            c_unl, _ = m.classifier(pre(v['x_u_c']), train, reuse=True, tag='C/C_unl')
-            c_rep = m.classifier(pre(v['x_u_c']), train, reuse=True, tag='C/C_unl_rep')[0] if cif else None
-            with no_grad():
-                G = m.good_generator(v['z_g'], v['y_g'], reuse=True, tag='C/G')
-                _, oh_u = ops.argmax_onehot(c_unl, K)
-                _, du = m.discriminator(v['x_u_c'], oh_u, reuse=True, tag='C/D_unl')
-            c_fake, _ = m.classifier(pre(G), train, reuse=True, tag='C/C_fake')
-            c_loss = ops.loss_c(c_real, v['y_l_c'], c_unl, c_rep, du, c_fake, v['y_g'], self.lambdas)
+            if grouped_c:
+                segs = [nLC, nUC, nUC, nG]
+                xs = ops.group_batch([v['x_l_c'], v['x_u_c'], v['x_u_c'], ops.Var(G.data, G.shape)])
+                lg, _ = m.classifier(pre(xs), train, reuse=True,
+                                     tag=TL([('C/C_real', nLC), ('C/C_unl', nUC), ('C/C_unl_rep', nUC), ('C/C_fake', nG)]))
+                c_unl_v = ops.Var(lg.data[nLC:nLC + nUC], (nUC, K))
+                with no_grad():
+                    _, oh_u = ops.argmax_onehot(c_unl_v, K)
+                    _, du = m.discriminator(v['x_u_c'], oh_u, reuse=True, tag='C/D_unl')
+                c_loss = ops.loss_c_grouped(lg, segs, True, v['y_l_c'], du, v['y_g'], self.lambdas)
+                self.aux['c_logits'] = lg
+            else:
+                c_real, _ = m.classifier(pre(v['x_l_c']), train, reuse=True, tag='C/C_real')
+                c_unl, _ = m.classifier(pre(v['x_u_c']), train, reuse=True, tag='C/C_unl')
+                c_rep = m.classifier(pre(v['x_u_c']), train, reuse=True, tag='C/C_unl_rep')[0] if cif else None
+                with no_grad():
+                    _, oh_u = ops.argmax_onehot(c_unl, K)
+                    _, du = m.discriminator(v['x_u_c'], oh_u, reuse=True, tag='C/D_unl')
+                c_fake, _ = m.classifier(pre(G), train, reuse=True, tag='C/C_fake')
+                c_loss = ops.loss_c(c_real, v['y_l_c'], c_unl, c_rep, du, c_fake, v['y_g'], self.lambdas)
+                self.aux['c_logits'] = (c_real, c_unl, c_fake, c_rep)
             ops.backward(c_loss)
         self._apply(fb, self.c_optimizer, self.ema, group='classifier')
-        self.aux['c_logits'] = (c_real, c_unl, c_fake, c_rep)
         if not ctx.rng.injected:
             _lib.call('tgan_counter_advance', ctx.rng.counter().data_ptr(), 1, ops._st())
         for i, l in enumerate((d_loss, g_loss, c_loss)):

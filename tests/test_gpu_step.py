@@ -17,6 +17,30 @@ from oracle import tgan_oracle as O                 # noqa: E402
 from util_gpu import relerr, tnp                    # noqa: E402
 
 
+def _teacher_force(orc, o32, tr):
+    """Start step k of all three runs from the float64 oracle's state after step k-1 (parameters, pop_mean / BN
+    moving statistics, Adam slots; the beta-power accumulators advance identically by construction).  Adam's
+    early updates are sign-like (|update| ~ lr once |g| >> eps), so an element whose exact gradient is zero moves
+    by +-lr on rounding noise alone -- in TF's own float32 run as much as here -- and free-running float32 and
+    float64 trajectories decorrelate within a few steps.  Teacher forcing makes every step an exact single-step
+    comparison with non-trivial Adam state; the free-running trajectory is checked as a band in
+    test_loss_trajectory_20_steps."""
+    npy = lambda d: {k: v.detach().numpy() for k, v in d.items()}
+    tr.load_state(npy(orc.P), npy(orc.S),
+                  {'discriminator': (npy(orc.opt_d.m), npy(orc.opt_d.v)),
+                   'good_generator': (npy(orc.opt_g.m), npy(orc.opt_g.v)),
+                   'classifier': (npy(orc.opt_c.m), npy(orc.opt_c.v))})
+    with torch.no_grad():
+        for k in orc.P:
+            o32.P[k].copy_(orc.P[k])
+        for k in orc.S:
+            o32.S[k].copy_(orc.S[k])
+        for a, b in ((o32.opt_d, orc.opt_d), (o32.opt_g, orc.opt_g), (o32.opt_c, orc.opt_c)):
+            for n in a.names:
+                a.m[n].copy_(b.m[n])
+                a.v[n].copy_(b.v[n])
+
+
 def _run(data_name, math, steps, scale, tol_loss, tol_grad, lambdas=(0.3, 0.5), margin0=1e-4):
     import tgan
     from tgan import core
@@ -32,32 +56,29 @@ def _run(data_name, math, steps, scale, tol_loss, tol_grad, lambdas=(0.3, 0.5), 
         rng = O.TagRNG(100 + step)
         core.ctx.rng = core.InjectedSource(rng)
         batch = O.make_batch(orc.cfg, seed=50 + step)
+        if step > 0:
+            _teacher_force(orc, o32, tr)
         ref = orc.step(batch, rng, lambdas[0], lambdas[1])
         # the oracle at the precision under test: float32, or float64 with the bf16 rounding points inserted
         with (O.quantized() if math == 'bf16' else contextlib.nullcontext()):
             ref32 = o32.step(batch, rng, lambdas[0], lambdas[1])
         got = tr.step(batch, lambda_1=lambdas[0], lambda_2=lambdas[1]).cpu().numpy()
-        # pseudo-labels: bit-exact wherever the oracle's top-2 logit margin exceeds the accumulated fp32
-        # drift (after the first Adam update the two fp32/fp64 trajectories differ by ~1e-5, so a
-        # near-tie may legitimately flip; on step 0 every sample is checked against margin 1e-4)
+        # pseudo-labels: bit-exact wherever the oracle's top-2 logit margin exceeds the single-step fp32 noise
+        # (every step starts from identical state, so the same margin holds on all steps)
         for key, lk in (('idx_unl_d', 'c_unl_d'), ('idx_unl', 'c_unl')):
             top2 = torch.topk(orc.last_aux['D'][lk], 2, dim=1).values
-            sure = ((top2[:, 0] - top2[:, 1]) > (margin0 if step == 0 else max(1e-2, margin0))).numpy()
+            sure = ((top2[:, 0] - top2[:, 1]) > margin0).numpy()
             mine, theirs = tr.aux[key].data.cpu().numpy(), orc.last_aux['D'][key].numpy()
             assert mine.dtype == np.int64
-            if step == 0:
-                assert np.array_equal(mine[sure], theirs[sure]), (step, key, mine, theirs)
-            # later steps: the fp32 and fp64 weights have drifted apart by +-lr on every noise-dominated element
-            # (see the loss bound below), so with 5-8 samples per call the labels are not comparable any more
+            assert np.array_equal(mine[sure], theirs[sure]), (step, key, mine, theirs)
         for i, nm in enumerate('dgc'):
             e = abs(got[i] - ref[i]) / max(1.0, abs(ref[i]))
             worst['loss_' + nm] = max(worst.get('loss_' + nm, 0), e)
-            # step 0: identical weights -> tight.  Later steps: Adam (eps 1e-8) turns fp32 rounding noise on
-            # exactly-zero gradients into +-lr moves, so the fp32 trajectory legitimately drifts; the bound
-            # is calibrated by the drift of the ORACLE's own float32 run against its float64 run.
+            # identical state at the start of every step -> the stated tolerance, or 4x the noise floor of the
+            # ORACLE's own run at the precision under test against its float64 run
             fl = abs(ref32[i] - ref[i]) / max(1.0, abs(ref[i]))
             worst['lfloor_' + nm] = max(worst.get('lfloor_' + nm, 0), fl)
-            assert e < max(tol_loss if step == 0 else 50 * tol_loss, 4 * fl), (step, nm, got[i], ref[i], ref32[i])
+            assert e < max(tol_loss, 4 * fl), (step, nm, got[i], ref[i], ref32[i])
         for grp, ph in (('discriminator', 'D'), ('good_generator', 'G'), ('classifier', 'C')):
             fb = tr.store.flat[grp]
             # error of one parameter's gradient, relative to max(|its own max|, 1e-3 * the phase's max):
@@ -75,8 +96,9 @@ def _run(data_name, math, steps, scale, tol_loss, tol_grad, lambdas=(0.3, 0.5), 
                 floor = max(floor, float(np.abs(o32.last_grads[ph][p.name].detach().double().numpy() - r).max() / den))
             worst['grad_' + ph] = max(worst.get('grad_' + ph, 0), max(errs.values()))
             worst['floor_' + ph] = max(worst.get('floor_' + ph, 0), floor)
-            # bound: the stated tolerance, or 5x the float32 noise floor the oracle itself shows
-            bad += [(step, n, e, floor) for n, e in errs.items() if e >= max(tol_grad, (5 if math == 'fp32' else 3) * floor)]
+            # bound: the stated tolerance, or 8x the float32 noise floor the oracle itself shows (the floor is one
+            # sample of summation-order noise: weight-norm `g` gradients are heavily cancelling sums)
+            bad += [(step, n, e, floor) for n, e in errs.items() if e >= max(tol_grad, (8 if math == 'fp32' else 3) * floor)]
         # bf16: per-parameter gradients are checked with fixed labels in test_gpu_nets.py (a pseudo-label that
         # flips on a sub-margin logit difference legitimately changes D's inputs); here: losses + labels
         assert math == 'bf16' or not bad, bad
@@ -90,10 +112,10 @@ def _run(data_name, math, steps, scale, tol_loss, tol_grad, lambdas=(0.3, 0.5), 
             lr = orc.cfg.CLA_LEARNINIG_RATE if grp == 'classifier' else orc.cfg.LEARNING_RATE
             d = np.abs(tnp(p.data) - orc.P[p.name].detach().numpy())
             m = resolved[p.name]
-            assert d.max() <= 10 * lr * steps, (p.name, d.max())
+            assert d.max() <= 10 * lr, (p.name, d.max())       # one update away from the forced state
             if m.any():      # calibrated by the oracle's own float32-vs-float64 parameter drift
                 fl = np.abs(o32.P[p.name].detach().double().numpy() - orc.P[p.name].detach().numpy())[m].max()
-                assert d[m].max() < max(0.1 * lr * steps, 4 * fl), (p.name, d[m].max(), fl)
+                assert d[m].max() < max(0.1 * lr, 4 * fl), (p.name, d[m].max(), fl)
     print(data_name, math, {k: '%.2e' % v for k, v in worst.items()})
     return worst
 

@@ -1,0 +1,32 @@
+"""warm per-kernel timings of the eager CIFAR-10 step via torch.profiler (CUPTI): aggregated by kernel name and a
+chronological list (name, grid, us) of one step -> gpurun_out/prof_step_{agg,seq}.txt"""
+import sys, collections
+sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tensorflow-implementation-of-triple-gan_b200')
+import torch, tgan
+from tgan import synthetic
+from torch.profiler import profile, ProfilerActivity
+tag = sys.argv[1] if len(sys.argv) > 1 else 'r1'
+tgan.init('cuda:0', math='bf16')
+tr = tgan.make_trainer('cifar10', zca=synthetic.make_zca(1234))
+tr.load_batch({k: torch.from_numpy(v) for k, v in synthetic.make_batch(tr.config, 1234).items()})
+for _ in range(3):
+    tr.step(lambda_1=0.3, lambda_2=0.5)
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    tr.step(lambda_1=0.3, lambda_2=0.5)
+    torch.cuda.synchronize()
+evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+evs.sort(key=lambda e: e.time_range.start)
+agg = collections.defaultdict(lambda: [0, 0.0])
+tot = 0.0
+with open('gpurun_out/prof_step_seq_%s.txt' % tag, 'w') as f:
+    for e in evs:
+        d = e.time_range.end - e.time_range.start
+        nm = e.name.split('(')[0][:70]
+        agg[nm][0] += 1; agg[nm][1] += d; tot += d
+        f.write('%-72s %9.1f\n' % (e.name[:72], d))
+with open('gpurun_out/prof_step_agg_%s.txt' % tag, 'w') as f:
+    f.write('kernels in one eager step: %d, summed warm GPU time %.0f us\n' % (len(evs), tot))
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        f.write('%-72s n=%4d %9.1f us %5.1f%% avg %7.1f\n' % (k, v[0], v[1], 100 * v[1] / tot, v[1] / v[0]))
+print(open('gpurun_out/prof_step_agg_%s.txt' % tag).read())
