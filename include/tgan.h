@@ -83,7 +83,7 @@ typedef struct {
   float* colsum;       /* optional fp32 [nseg][Nout]: += per-channel sums of the stored values, per batch segment */
   int nseg;            /* 0/1 = whole batch; up to 4 segments of consecutive images (several network calls grouped
                           in one launch keep their own mean-only-BN statistics) */
-  int seg_end[4];      /* exclusive image index where segment i ends */
+  int seg_end[4];      /* exclusive image index where segment i ends (plain GEMM, N == 1 && gh == 1: pixel index) */
   int act;             /* TGAN_ACT_* applied after bias (before store)         */
   float alpha;
 } tgan_igemm_args;
@@ -143,6 +143,23 @@ int tgan_channel_stats(const void* x, int xdt, int64_t rows, int C, float* sum, 
  *   testing : y = act(x - pop_mean + b)                                                 (nn.py:170-171) */
 int tgan_mobn_apply(const void* x, int xdt, void* y, int ydt, int64_t rows, int C, const float* sum, const float* b,
                     float* pop_mean, float decay, int train, int act, float alpha, void* stream);
+
+/* Segment-aware variants for GROUPED batches: several calls of one network (e.g. C(x_l), C(x_u), C(G(z)) of
+ * Good_GAN_cifar10.py:220-254) are concatenated along the batch axis and run as one pass; every call keeps its own
+ * batch mean.  nseg <= 4 segments of consecutive rows; r0,r1,r2 = exclusive end rows of segments 0..2 (the last
+ * segment ends at `rows`; unused values ignored).  bf16 tensors, C % 8 == 0 (16-byte vector accesses).
+ *   mobn_apply_seg: y = act(x - sums[seg]/rows_seg + b) (train) | act(x - pop_mean + b) (test); pop_mean is updated once
+ *                   per segment in call order (nn.py:176-183).  sums: fp32 [nseg][C].
+ *   act_bwd_seg:    du = dy * act'(y); colsums[seg][c] = sum_{rows in seg} du; grad_acc[c] += sum over all rows (db).
+ *   sub_channel_mean_seg: dz = du - colsums[seg]/rows_seg (the mean-subtraction's gradient, nn.py:179). */
+int tgan_mobn_apply_seg(const void* x, void* y, int64_t rows, int C, int nseg, int64_t r0, int64_t r1, int64_t r2,
+                        const float* sums, const float* b, float* pop_mean, float decay, int train, int act,
+                        float alpha, void* stream);
+int tgan_act_bwd_seg(const void* dy, int dydt, const void* y, int ydt, void* du, int dudt, int64_t rows, int C,
+                     int nseg, int64_t r0, int64_t r1, int64_t r2, int act, float alpha, float* colsums,
+                     float* grad_acc, float* ws, void* stream);
+int tgan_sub_channel_mean_seg(const void* du, void* dz, int64_t rows, int C, int nseg, int64_t r0, int64_t r1,
+                              int64_t r2, const float* colsums, void* stream);
 
 /* tf.contrib.layers.batch_norm training statistics (modle_base.py:229-237):
  *   mean, rstd = rsqrt(var_biased + eps); scale = gamma*rstd; shift = beta - mean*scale;

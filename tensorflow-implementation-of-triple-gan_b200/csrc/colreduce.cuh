@@ -15,7 +15,7 @@ __device__ unsigned int g_colreduce_ticket[1024];   // zero at load; the last CT
 
 template <int NACC, int VEC, typename F>
 __global__ void __launch_bounds__(256) colreduce_kernel(F f, int64_t rows, int C, double* __restrict__ partials,
-                                                        float* o0, float* o1, float beta, float* acc0) {
+                                                        float* o0, float* o1, float beta, float* acc0, int segmode) {
   constexpr int CL = VEC == 4 ? 8 : 32, RL = 256 / CL;
   __shared__ double sm[RL][NACC][33];
   __shared__ bool is_last;
@@ -68,15 +68,22 @@ __global__ void __launch_bounds__(256) colreduce_kernel(F f, int64_t rows, int C
   }
   __syncthreads();
   if (t < 32 && c < C) {
+    double tot = 0.0;
 #pragma unroll
     for (int a = 0; a < NACC; ++a) {
       double s = 0.0;
 #pragma unroll
       for (int y = 0; y < 8; ++y) s += sm[y][a][fc];
-      float* o = a == 0 ? o0 : o1;
-      if (o) o[c] = (float)((beta != 0.f ? (double)beta * o[c] : 0.0) + s);
-      if (a == 0 && acc0) acc0[c] = (float)((double)acc0[c] + s);
+      tot += s;
+      if (segmode) {            // accumulator a = batch segment a: o0 is [NACC][C]; acc0 += the sum over all segments
+        o0[a * C + c] = (float)s;
+      } else {
+        float* o = a == 0 ? o0 : o1;
+        if (o) o[c] = (float)((beta != 0.f ? (double)beta * o[c] : 0.0) + s);
+        if (a == 0 && acc0) acc0[c] = (float)((double)acc0[c] + s);
+      }
     }
+    if (segmode && acc0) acc0[c] = (float)((double)acc0[c] + tot);
   }
   if (t == 0) g_colreduce_ticket[blockIdx.x] = 0;
 }
@@ -95,14 +102,14 @@ static inline int pick_parts(int64_t rows, int C, int vec) {
 // out0/out1 = beta*out + column sums of accumulator 0/1 (either may be NULL); acc0 (optional) += sums of accumulator 0
 template <int NACC, typename F1, typename F4>
 static int run_colreduce(F1 f1, F4 f4, bool vec_ok, int64_t rows, int C, float* o0, float* o1, float beta, float* ws,
-                         cudaStream_t st, float* acc0 = nullptr) {
+                         cudaStream_t st, float* acc0 = nullptr, int segmode = 0) {
   if (ceil_div(C, 32) > 1024) { set_error("colreduce: more than 32768 channels"); return 1; }
   int vec = vec_ok ? 4 : 1;
   int parts = pick_parts(rows, C, vec);
   dim3 grid(ceil_div(C, 32), parts);
   double* wsd = reinterpret_cast<double*>(ws);       // fp64 partials: the first 4*MAX_PARTS*C floats of ws
-  if (vec_ok) colreduce_kernel<NACC, 4, F4><<<grid, 256, 0, st>>>(f4, rows, C, wsd, o0, o1, beta, acc0);
-  else colreduce_kernel<NACC, 1, F1><<<grid, 256, 0, st>>>(f1, rows, C, wsd, o0, o1, beta, acc0);
+  if (vec_ok) colreduce_kernel<NACC, 4, F4><<<grid, 256, 0, st>>>(f4, rows, C, wsd, o0, o1, beta, acc0, segmode);
+  else colreduce_kernel<NACC, 1, F1><<<grid, 256, 0, st>>>(f1, rows, C, wsd, o0, o1, beta, acc0, segmode);
   TGAN_LAUNCHED();
   return 0;
 }

@@ -37,7 +37,7 @@ PFN_tmapEncodeTiled get_tmap_encoder() {
 }
 
 int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box, const uint32_t* elem_strides) {
+                   const uint32_t* box, const uint32_t* elem_strides, bool swizzle128) {
   PFN_tmapEncodeTiled enc = get_tmap_encoder();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return 1; }
   cuuint64_t gd[5], gs[5];
@@ -45,7 +45,8 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* d
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = elem_strides ? elem_strides[i] : 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu %llu box %u %u %u %u", (int)r, rank,
@@ -65,6 +66,7 @@ constexpr int P_TILE_BYTES = 128 * 128;  // 128 pixels x 64 bf16
 constexpr int IG_NPIX = 256;             // pixels per CTA tile = UMMA N (two 128-pixel TMA boxes)
 constexpr int IG_STAGE_BYTES = W_STAGE_BYTES + 2 * P_TILE_BYTES;
 constexpr int IG_STAGES = 4;
+constexpr int IG_OUT_STAGE_BYTES = 128 * 256;   // epilogue staging: 128 pixels x 128 channels bf16 ([pixel][channel] rows)
 
 // Orientation: D[co, pixel] = W[co, k] * X[pixel, k]^T.  The OUTPUT CHANNELS are the UMMA M dimension (TMEM lanes) and
 // 256 PIXELS are the UMMA N dimension: measured on B200, one cta_group::1 tcgen05.mma (M=128, K=16, smem operands)
@@ -78,9 +80,10 @@ struct IgParams {
   int odt, OH, OW, ldo, osy, osx, ooy, oox, vh, vw, Nout;
   const float* bias;
   float* colsum;
-  int nseg, seg_end[4];
+  int nseg, seg_end[4], segflat;   // segflat: plain GEMM (one row of pixels) -> segments are pixel ranges
   int act;
   float alpha;
+  int tstore;   // 1: bf16 output staged in shared memory and written by TMA bulk-tensor stores
   int dbg;   // experiments only (TGAN_IGEMM_DBG): 1 skip activation loads, 2 skip weight loads, 4 skip stores
 };
 
@@ -107,8 +110,10 @@ __device__ __forceinline__ void ig_store_chunk(const IgParams& p, TO* __restrict
       const float x = v[sgm * TW + jc];
       if (p.colsum) {
         const float xs = ok ? x : 0.f;
-        csum[0] += sg == 0 ? xs : 0.f; csum[1] += sg == 1 ? xs : 0.f;
-        csum[2] += sg == 2 ? xs : 0.f; csum[3] += sg == 3 ? xs : 0.f;
+        const int ox = ox0 + jc;
+        const int sj = p.segflat ? (ox >= p.seg_end[0]) + (ox >= p.seg_end[1]) + (ox >= p.seg_end[2]) : sg;
+        csum[0] += sj == 0 ? xs : 0.f; csum[1] += sj == 1 ? xs : 0.f;
+        csum[2] += sj == 2 ? xs : 0.f; csum[3] += sj == 3 ? xs : 0.f;
       }
       if (ok) {
         if constexpr (sizeof(TO) == 2) out[base + jc * pstep] = __float2bfloat16_rn(x);
@@ -118,12 +123,46 @@ __device__ __forceinline__ void ig_store_chunk(const IgParams& p, TO* __restrict
   }
 }
 
+// Per-segment channel sums of one chunk of 32 tile pixels (TMA-store path: the store itself needs no geometry, the
+// statistics still must skip pixels outside the valid grid).  A run of TW pixels lies in one image row.
+template <int TW>
+__device__ __forceinline__ void ig_sum_chunk(const IgParams& p, const float (&v)[32], int pbase, int tx, int ty, int ng,
+                                             float (&csum)[4]) {
+  const int ppi = p.th * p.tw;
+#pragma unroll
+  for (int sgm = 0; sgm < 32 / TW; ++sgm) {
+    const int pix = pbase + sgm * TW;
+    const int nl = pix >> p.lppi, rem = pix & (ppi - 1);
+    const int oy = ty * p.th + (rem >> p.ltw), ox0 = tx * p.tw + (rem & (p.tw - 1)), n = ng * p.nb + nl;
+    const bool rowok = (n < p.N) && (oy < p.vh);
+    const int lim = rowok ? p.vw - ox0 : 0;
+    if (p.segflat) {      // segment boundaries fall inside a run of pixels: classify every pixel
+#pragma unroll
+      for (int jc = 0; jc < TW; ++jc) {
+        const int ox = ox0 + jc;
+        const float xs = (jc < lim) ? v[sgm * TW + jc] : 0.f;
+        const int sgj = (ox >= p.seg_end[0]) + (ox >= p.seg_end[1]) + (ox >= p.seg_end[2]);
+        csum[0] += sgj == 0 ? xs : 0.f; csum[1] += sgj == 1 ? xs : 0.f;
+        csum[2] += sgj == 2 ? xs : 0.f; csum[3] += sgj == 3 ? xs : 0.f;
+      }
+      continue;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int jc = 0; jc < TW; ++jc) s += (jc < lim) ? v[sgm * TW + jc] : 0.f;
+    const int sg = (n >= p.seg_end[0]) + (n >= p.seg_end[1]) + (n >= p.seg_end[2]);
+    csum[0] += sg == 0 ? s : 0.f; csum[1] += sg == 1 ? s : 0.f;
+    csum[2] += sg == 2 ? s : 0.f; csum[3] += sg == 3 ? s : 0.f;
+  }
+}
+
 __global__ void __launch_bounds__(IG_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-             const __grid_constant__ IgParams p) {
+             const __grid_constant__ CUtensorMap tmO, const __grid_constant__ IgParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)IG_STAGES * IG_STAGE_BYTES);
+  uint8_t* ostage = smem + (size_t)IG_STAGES * IG_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ostage + IG_OUT_STAGE_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + IG_STAGES;
   uint64_t* tfull = bars + 2 * IG_STAGES;
@@ -137,6 +176,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     fence_barrier_init();
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
+    if (p.tstore) tma_prefetch_desc(&tmO);
   }
   if (warp == 0) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }   // 2 accumulators x 256 fp32 columns
   tc_fence_before();
@@ -252,7 +292,33 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
           for (int j = 0; j < 32; ++j) v[j] = act_fwd(v[j], p.act, 0.2f);
         }
         const int pbase = c0 & 127;
-        if (!(p.dbg & 4)) {
+        if (p.tstore) {
+          // ---- staged path: [pixel][channel] rows in shared memory, one bulk-tensor store per 128-pixel half.  The
+          // store needs no geometry (TMA clips at the valid extents); 32 lanes write 32 consecutive channels = 64 B.
+          if (p.colsum) {
+            switch (p.ltw) {
+              case 2: ig_sum_chunk<4>(p, v, pbase, tx, ty, ng, csum); break;
+              case 3: ig_sum_chunk<8>(p, v, pbase, tx, ty, ng, csum); break;
+              case 4: ig_sum_chunk<16>(p, v, pbase, tx, ty, ng, csum); break;
+              default: ig_sum_chunk<32>(p, v, pbase, tx, ty, ng, csum); break;
+            }
+          }
+          if (pbase == 0) {       // the previous half's store must have finished reading the staging buffer
+            if (warp == 2 && lane == 0) bulk_wait_read0();
+            named_bar_sync(1, 128);
+          }
+          bf16* srow = reinterpret_cast<bf16*>(ostage) + (size_t)pbase * 128 + (q * 32 + lane);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) srow[j * 128] = __float2bfloat16_rn(v[j]);
+          if (pbase == 96) {
+            fence_proxy_async();
+            named_bar_sync(1, 128);
+            if (warp == 2 && lane == 0 && !(p.dbg & 4)) {
+              tma_store_4d(&tmO, ostage, ct * 128, tx * p.tw, ty * p.th, ng * p.nb);
+              bulk_commit();
+            }
+          }
+        } else if (!(p.dbg & 4)) {
           if (p.odt == TGAN_BF16) {
             bf16* o = reinterpret_cast<bf16*>(p.out);
             switch (p.ltw) {
@@ -282,6 +348,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       if (lane == 0) mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; accphase ^= 1; }
     }
+    if (p.tstore && warp == 2 && lane == 0) bulk_wait0();   // staging buffer must outlive the last store's read
   }
   tc_fence_before();
   __syncthreads();
@@ -486,10 +553,13 @@ extern "C" int tgan_igemm_bf16(const tgan_igemm_args* a, void* stream) {
   p.nseg = a->nseg > 1 ? a->nseg : 1;
   TGAN_CHECK_ARG(p.nseg <= 4, "igemm: at most 4 batch segments");
   for (int i = 0; i < 4; ++i) p.seg_end[i] = (a->nseg > 1 && i < a->nseg - 1) ? a->seg_end[i] : 0x7fffffff;
+  p.segflat = (a->nseg > 1 && a->N == 1 && a->gh == 1) ? 1 : 0;
   p.bias = a->bias; p.colsum = a->colsum; p.act = a->act; p.alpha = a->alpha == 0.f ? 1.f : a->alpha;
-  const size_t smem_bytes = 1024 + (size_t)IG_STAGES * IG_STAGE_BYTES + 256;
+  const size_t smem_bytes = 1024 + (size_t)IG_STAGES * IG_STAGE_BYTES + IG_OUT_STAGE_BYTES + 256;
+  p.tstore = (a->odt == TGAN_BF16 && a->ldo % 8 == 0 && ((uintptr_t)a->out & 15) == 0) ? 1 : 0;
+  { const char* e = getenv("TGAN_IGEMM_NO_TSTORE"); if (e && atoi(e)) p.tstore = 0; }
 
-  CUtensorMap tmX, tmW;
+  CUtensorMap tmX, tmW, tmO;
   {
     uint64_t dims[4] = {(uint64_t)a->C, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->N};
     uint64_t str[3] = {(uint64_t)a->ldx * 2, (uint64_t)a->W * a->ldx * 2, (uint64_t)a->H * a->W * a->ldx * 2};
@@ -503,6 +573,18 @@ extern "C" int tgan_igemm_bf16(const tgan_igemm_args* a, void* stream) {
     uint32_t box[3] = {64, 128, 1};
     if (make_tmap_bf16(&tmW, a->wp, 3, dims, str, box, nullptr)) return 1;
   }
+  if (p.tstore) {
+    // the valid output grid as a strided 4-D view [Nout, vw, vh, N] of out (parity-class placement = base offset +
+    // pixel strides); staging rows are dense [pixel][128 channels], so the map is not swizzled
+    const uint64_t ldo = (uint64_t)a->ldo;
+    uint64_t dims[4] = {(uint64_t)a->Nout, (uint64_t)p.vw, (uint64_t)p.vh, (uint64_t)a->N};
+    uint64_t str[3] = {(uint64_t)p.osx * ldo * 2, (uint64_t)p.osy * a->OW * ldo * 2, (uint64_t)a->OH * a->OW * ldo * 2};
+    uint32_t box[4] = {128, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.nb};
+    const char* base = (const char*)a->out + ((int64_t)p.ooy * a->OW + p.oox) * (int64_t)ldo * 2;
+    if (make_tmap_bf16(&tmO, base, 4, dims, str, box, nullptr, false)) return 1;
+  } else {
+    tmO = tmX;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
@@ -511,7 +593,7 @@ extern "C" int tgan_igemm_bf16(const tgan_igemm_args* a, void* stream) {
   }
   const int total = p.pp_tiles * p.ct_tiles;
   const int grid = total < 148 ? total : 148;
-  igemm_kernel<<<grid, IG_THREADS, smem_bytes, (cudaStream_t)stream>>>(tmX, tmW, p);
+  igemm_kernel<<<grid, IG_THREADS, smem_bytes, (cudaStream_t)stream>>>(tmX, tmW, tmO, p);
   TGAN_LAUNCHED();
   return 0;
 }

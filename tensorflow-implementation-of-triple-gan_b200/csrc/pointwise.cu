@@ -39,6 +39,38 @@ struct ActBwdF {
   }
 };
 
+// batch segments: several calls of one network grouped along the batch axis keep their own batch statistics
+struct Segs {
+  int n;
+  int64_t end[3];      // exclusive row index where segments 0..2 end (unused entries = INT64_MAX)
+  float inv_rows[4];
+  __device__ __forceinline__ int of(int64_t r) const { return (r >= end[0]) + (r >= end[1]) + (r >= end[2]); }
+};
+
+// du = dy * act'(y) with per-SEGMENT column sums (accumulator a = segment a)
+template <typename TDY, typename TY, typename TDU, int VEC, int ACT>
+struct ActBwdSegF {
+  const TDY* dy; const TY* y; TDU* du; int C; float alpha; Segs sg;
+  __device__ void operator()(int64_t r, int c0, float (&v)[4][VEC]) const {
+    const int s = sg.of(r);
+    float o[VEC];
+    if constexpr (VEC == 4) {
+      float a[4], b[4];
+      ld4<TDY>(dy, r * C + c0, a); ld4<TY>(y, r * C + c0, b);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = a[j] * act_grad_from_y_t<ACT>(b[j], alpha);
+      st4<TDU>(du, r * C + c0, *reinterpret_cast<float(*)[4]>(o));
+    } else {
+      o[0] = ldf<TDY>(dy, r * C + c0) * act_grad_from_y_t<ACT>(ldf<TY>(y, r * C + c0), alpha);
+      stf<TDU>(du, r * C + c0, o[0]);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) v[a][j] = (s == a) ? o[j] : 0.f;
+  }
+};
+
 template <typename TDY, typename TX, int VEC>
 struct BnBwdStatsF {
   const TDY* dy; const TX* x; const float* mean; const float* rstd; int C;
@@ -123,6 +155,74 @@ __global__ void mobn_apply_kernel(const TX* __restrict__ x, TY* __restrict__ y, 
     }
     if constexpr (VEC == 4) st4<TY>(y, e, *reinterpret_cast<float(*)[4]>(v));
     else stf<TY>(y, e, v[0]);
+  }
+}
+
+// 8 bf16 per thread (16-byte accesses)
+__device__ __forceinline__ void ld8(const bf16* p, int64_t i, float (&v)[8]) {
+  uint4 t = *reinterpret_cast<const uint4*>(p + i);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { v[2 * j] = __low2float(h[j]); v[2 * j + 1] = __high2float(h[j]); }
+}
+__device__ __forceinline__ void st8(bf16* p, int64_t i, const float (&v)[8]) {
+  uint4 t;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+  *reinterpret_cast<uint4*>(p + i) = t;
+}
+
+// Segment-aware mean-only batch norm apply + nonlinearity, whole grouped batch in one launch (bf16, C % 8 == 0):
+//   y = act(z - mean_seg + b),  mean_seg = sums[seg] / rows_seg   (training)   |   mean = pop_mean (test)
+// pop_mean is updated once per segment IN CALL ORDER (the reference runs the calls one after the other).
+template <int ACT>
+__global__ void mobn_apply_seg_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int64_t nvec, int C,
+                                      const float* __restrict__ sums, Segs sg, const float* __restrict__ b,
+                                      float* __restrict__ pop_mean, float decay, int train, float alpha) {
+  if (train && pop_mean && blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float pm = pop_mean[c];
+      for (int s = 0; s < sg.n; ++s) pm = pm * decay + sums[s * C + c] * sg.inv_rows[s] * (1.f - decay);
+      pop_mean[c] = pm;
+    }
+  }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = i * 8;
+    const int64_t r = e / C;
+    const int c = (int)(e - r * C);
+    const int s = sg.of(r);
+    float v[8];
+    ld8(x, e, v);
+    const float4* bp = reinterpret_cast<const float4*>(b + c);
+    const float4* mp = reinterpret_cast<const float4*>((train ? sums + (int64_t)s * C : pop_mean) + c);
+    const float sc = train ? sg.inv_rows[s] : 1.f;
+    float4 b0 = bp[0], b1 = bp[1], m0 = mp[0], m1 = mp[1];
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = act_fwd_t<ACT>(v[j] + bb[j] - mm[j] * sc, alpha);
+    st8(y, e, v);
+  }
+}
+
+// dz = du - colsums[seg] / rows_seg  (bf16, C % 8 == 0), in place allowed
+__global__ void sub_mean_seg_kernel(const bf16* __restrict__ du, bf16* __restrict__ dz, int64_t nvec, int C,
+                                    const float* __restrict__ colsums, Segs sg) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = i * 8;
+    const int64_t r = e / C;
+    const int c = (int)(e - r * C);
+    const int s = sg.of(r);
+    float v[8];
+    ld8(du, e, v);
+    const float4* mp = reinterpret_cast<const float4*>(colsums + (int64_t)s * C + c);
+    float4 m0 = mp[0], m1 = mp[1];
+    const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+    const float sc = sg.inv_rows[s];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] -= mm[j] * sc;
+    st8(dz, e, v);
   }
 }
 
@@ -381,6 +481,67 @@ extern "C" int tgan_mobn_apply(const void* x, int xdt, void* y, int ydt, int64_t
   TGAN_LAUNCHED();
   return 0;
 }
+static int make_segs(Segs& sg, int64_t rows, int nseg, int64_t r0, int64_t r1, int64_t r2) {
+  if (nseg < 1 || nseg > 4) { set_error("segments: nseg %d out of range [1,4]", nseg); return 1; }
+  const int64_t e[4] = {r0, r1, r2, rows};
+  int64_t prev = 0;
+  sg.n = nseg;
+  for (int i = 0; i < 4; ++i) {
+    const int64_t end = i < nseg - 1 ? e[i] : rows;
+    if (i < nseg && end <= prev) { set_error("segments: boundaries must be increasing and non-empty"); return 1; }
+    if (i < 3) sg.end[i] = i < nseg - 1 ? end : INT64_MAX;
+    sg.inv_rows[i] = i < nseg ? 1.0f / (float)(end - prev) : 0.f;
+    if (i < nseg) prev = end;
+  }
+  return 0;
+}
+
+extern "C" int tgan_mobn_apply_seg(const void* x, void* y, int64_t rows, int C, int nseg, int64_t r0, int64_t r1,
+                                   int64_t r2, const float* sums, const float* b, float* pop_mean, float decay,
+                                   int train, int act, float alpha, void* stream) {
+  TGAN_CHECK_ARG(x && y && b && rows > 0 && C > 0 && C % 8 == 0 && aligned16(x) && aligned16(y) && aligned16(b),
+                 "mobn_apply_seg: bf16 tensors with C %% 8 == 0 and 16-byte alignment only");
+  TGAN_CHECK_ARG(train ? (sums != nullptr && aligned16(sums)) : (pop_mean != nullptr && aligned16(pop_mean)),
+                 "mobn_apply_seg: needs sums (train) or pop_mean (test)");
+  Segs sg;
+  if (make_segs(sg, rows, nseg, r0, r1, r2)) return 1;
+  const int64_t nvec = rows * C / 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  TGAN_DISPATCH_ACT(act, A, (mobn_apply_seg_kernel<A><<<grid_for(nvec), 256, 0, st>>>(
+                                (const bf16*)x, (bf16*)y, nvec, C, sums, sg, b, pop_mean, decay, train, alpha)));
+  TGAN_LAUNCHED();
+  return 0;
+}
+
+extern "C" int tgan_act_bwd_seg(const void* dy, int dydt, const void* y, int ydt, void* du, int dudt, int64_t rows,
+                                int C, int nseg, int64_t r0, int64_t r1, int64_t r2, int act, float alpha,
+                                float* colsums, float* grad_acc, float* ws, void* stream) {
+  TGAN_CHECK_ARG(dy && y && du && ws && colsums && rows > 0 && C > 0, "act_bwd_seg: bad args");
+  Segs sg;
+  if (make_segs(sg, rows, nseg, r0, r1, r2)) return 1;
+  bool v = (C % 4 == 0) && aligned16(dy) && aligned16(y) && aligned16(du);
+  TGAN_DISPATCH_1(dydt, TDY, TGAN_DISPATCH_1(ydt, TY, TGAN_DISPATCH_1(dudt, TDU, {
+    TGAN_DISPATCH_ACT(act, A, {
+      ActBwdSegF<TDY, TY, TDU, 1, A> f1{(const TDY*)dy, (const TY*)y, (TDU*)du, C, alpha, sg};
+      ActBwdSegF<TDY, TY, TDU, 4, A> f4{(const TDY*)dy, (const TY*)y, (TDU*)du, C, alpha, sg};
+      return run_colreduce<4>(f1, f4, v, rows, C, colsums, nullptr, 0.f, ws, (cudaStream_t)stream, grad_acc, 1);
+    });
+  })));
+  return 0;
+}
+
+extern "C" int tgan_sub_channel_mean_seg(const void* du, void* dz, int64_t rows, int C, int nseg, int64_t r0,
+                                         int64_t r1, int64_t r2, const float* colsums, void* stream) {
+  TGAN_CHECK_ARG(du && dz && colsums && rows > 0 && C > 0 && C % 8 == 0 && aligned16(du) && aligned16(dz) &&
+                     aligned16(colsums), "sub_channel_mean_seg: bf16 tensors with C %% 8 == 0 and 16-byte alignment only");
+  Segs sg;
+  if (make_segs(sg, rows, nseg, r0, r1, r2)) return 1;
+  const int64_t nvec = rows * C / 8;
+  sub_mean_seg_kernel<<<grid_for(nvec), 256, 0, (cudaStream_t)stream>>>((const bf16*)du, (bf16*)dz, nvec, C, colsums, sg);
+  TGAN_LAUNCHED();
+  return 0;
+}
+
 extern "C" int tgan_bn_finalize(const float* sum, const float* sumsq, int64_t rows, int C, const float* gamma,
                                 const float* beta, float eps, float decay, float* moving_mean, float* moving_var,
                                 float* mean, float* rstd, float* scale, float* shift, void* stream) {

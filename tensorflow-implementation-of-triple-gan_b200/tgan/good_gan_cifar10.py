@@ -22,6 +22,8 @@ class Good_GAN_cifar10(model_base.NN_Base):
     def leakyReLu(self, x, alpha=0.2, name=None):
         return self._leakyReLu_impl(x, alpha)
 
+    leakyReLu.tgan_act = ('lrelu', 0.2)      # fusable into the producing layer's epilogue (nn._fused)
+
     def _leakyReLu_impl(self, x, alpha):
         # tf.nn.relu(x) - alpha * tf.nn.relu(-x)  (Good_GAN_cifar10.py:26-27)
         return ops.activation(x, 'lrelu', alpha)

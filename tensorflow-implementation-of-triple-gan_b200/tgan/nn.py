@@ -48,7 +48,7 @@ def _fused(nonlinearity):
     """-> (kind, alpha) if the callable is one of ours, else None."""
     if nonlinearity is None:
         return ('none', 0.0)
-    return getattr(nonlinearity, 'tgan_act', None)
+    return getattr(nonlinearity, 'tgan_act', None)      # bound methods forward attribute reads to their function
 
 
 def _tmp_param(value):

@@ -276,7 +276,7 @@ def conv2d(x, w, kh, kw, stride=1, padding='SAME', colsum=False):
     cs = None
     segs = _segs(x)
     if use_tc:
-        seg_ok = segs is None or (len(x.shape) == 4 and kh * kw > 1 and len(segs) <= 4)   # spatial convs: per-image segments
+        seg_ok = segs is None or len(segs) <= 4
         cs = arena_take(Cout * (len(segs) if segs else 1)) if (colsum and seg_ok) else None
         z = tc.conv_fwd(x, w, geom, cs, segs if cs is not None else None)
     else:
@@ -468,22 +468,37 @@ def mobn_act(z, b, pop_mean, train, act='none', alpha=0.2, decay=0.9):
     for n in segs:
         bounds.append((r0, n * rps))
         r0 += n * rps
+    ends = [b0 + nr for b0, nr in bounds[:-1]] + [0, 0, 0]
     zd = z.data
     ez = zd.element_size()
     cs_all = z.aux.get('colsum') if z.aux else None      # [nseg, C] accumulated by the tcgen05 GEMM epilogue
     y = _new(z.shape, _out_dtype(C))
     ey = y.element_size()
-    for i, (r0, nr) in enumerate(bounds):
-        s = None
-        if train:
-            if cs_all is not None:
-                s = cs_all[i * C:(i + 1) * C]
-            else:
-                s = _new((C,), torch.float32)
-                _lib.call('tgan_channel_stats', zd.data_ptr() + r0 * C * ez, dt_code(zd), nr, C, _p(s), None, 0.0,
-                          _p(ctx.ws()), _st())
-        _lib.call('tgan_mobn_apply', zd.data_ptr() + r0 * C * ez, dt_code(zd), y.data_ptr() + r0 * C * ey, dt_code(y), nr, C,
-                  _p(s), _p(b.data), _p(pop_mean.data), decay, 1 if train else 0, a, alpha, _st())
+    fused = zd.dtype == torch.bfloat16 and y.dtype == torch.bfloat16 and C % 8 == 0 and len(segs) <= 4
+
+    def seg_stats():
+        s_all = _new((len(segs), C), torch.float32)
+        for i, (b0, nr) in enumerate(bounds):
+            _lib.call('tgan_channel_stats', zd.data_ptr() + b0 * C * ez, dt_code(zd), nr, C, s_all.data_ptr() + 4 * i * C,
+                      None, 0.0, _p(ctx.ws()), _st())
+        return s_all
+
+    if fused:       # one launch for the whole grouped batch, nonlinearity included
+        sums = (cs_all if cs_all is not None else seg_stats()) if train else None
+        _lib.call('tgan_mobn_apply_seg', _p(zd), _p(y), rows, C, len(segs), ends[0], ends[1], ends[2], _p(sums),
+                  _p(b.data), _p(pop_mean.data), decay, 1 if train else 0, a, alpha, _st())
+    else:
+        for i, (b0, nr) in enumerate(bounds):
+            s = None
+            if train:
+                if cs_all is not None:
+                    s = cs_all[i * C:(i + 1) * C]
+                else:
+                    s = _new((C,), torch.float32)
+                    _lib.call('tgan_channel_stats', zd.data_ptr() + b0 * C * ez, dt_code(zd), nr, C, _p(s), None, 0.0,
+                              _p(ctx.ws()), _st())
+            _lib.call('tgan_mobn_apply', zd.data_ptr() + b0 * C * ez, dt_code(zd), y.data_ptr() + b0 * C * ey, dt_code(y),
+                      nr, C, _p(s), _p(b.data), _p(pop_mean.data), decay, 1 if train else 0, a, alpha, _st())
     out = _prop(Var(y, z.shape, requires_grad=rg), z)
     if rg:
         def bwd():
@@ -492,14 +507,23 @@ def mobn_act(z, b, pop_mean, train, act='none', alpha=0.2, decay=0.9):
             dy = out.grad
             du = _new(z.shape, zd.dtype)
             ed, eu = dy.element_size(), du.element_size()
-            for r0, nr in bounds:
-                cs = _new((C,), torch.float32)
-                _lib.call('tgan_act_bwd', dy.data_ptr() + r0 * C * ed, dt_code(dy), y.data_ptr() + r0 * C * ey, dt_code(y),
-                          du.data_ptr() + r0 * C * eu, dt_code(du), nr, C, a, alpha, _p(cs),
+            if fused:
+                cs = _new((4, C), torch.float32)
+                _lib.call('tgan_act_bwd_seg', _p(dy), dt_code(dy), _p(y), dt_code(y), _p(du), dt_code(du), rows, C,
+                          len(segs), ends[0], ends[1], ends[2], a, alpha, _p(cs),
                           _p(b.grad) if b.requires_grad else None, _p(ctx.ws()), _st())
                 if z.requires_grad and train:
-                    _lib.call('tgan_sub_channel_mean', du.data_ptr() + r0 * C * eu, dt_code(du), du.data_ptr() + r0 * C * eu,
-                              dt_code(du), nr, C, _p(cs), _st())
+                    _lib.call('tgan_sub_channel_mean_seg', _p(du), _p(du), rows, C, len(segs), ends[0], ends[1], ends[2],
+                              _p(cs), _st())
+            else:
+                for b0, nr in bounds:
+                    cs = _new((C,), torch.float32)
+                    _lib.call('tgan_act_bwd', dy.data_ptr() + b0 * C * ed, dt_code(dy), y.data_ptr() + b0 * C * ey,
+                              dt_code(y), du.data_ptr() + b0 * C * eu, dt_code(du), nr, C, a, alpha, _p(cs),
+                              _p(b.grad) if b.requires_grad else None, _p(ctx.ws()), _st())
+                    if z.requires_grad and train:
+                        _lib.call('tgan_sub_channel_mean', du.data_ptr() + b0 * C * eu, dt_code(du),
+                                  du.data_ptr() + b0 * C * eu, dt_code(du), nr, C, _p(cs), _st())
             if z.requires_grad:
                 add_grad(z, du)
         ctx.tape.nodes.append(bwd)

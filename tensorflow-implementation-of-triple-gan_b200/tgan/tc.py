@@ -131,8 +131,11 @@ def conv_fwd(x, w, g, colsum=None, segs=None):
     wp, Kpad = _pack(w, 'fprop', kh * kw, Cout, C, C * Cout, 1, Cout)
     taps = [(r - g['pt'], c - g['pl']) for r in range(kh) for c in range(kw)]
     z = _new((g['N'] * g['Ho'] * g['Wo'], Cout), torch.bfloat16)
+    if segs and gf is not g:          # plain GEMM: segments become ranges of rows
+        rps = (g['N'] * g['Ho'] * g['Wo']) // sum(segs)
+        segs = [n * rps for n in segs]
     _igemm(xd, gf['N'], gf['H'], gf['W'], C, ld, wp, Kpad, taps, Cout, gf['Ho'], gf['Wo'], z, gf['Ho'], gf['Wo'], Cout,
-           s=g['s'], colsum=colsum, segs=(segs if gf is g else None))
+           s=g['s'], colsum=colsum, segs=segs)
     return z
 
 

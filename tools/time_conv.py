@@ -30,3 +30,6 @@ run(100,16,256,256)
 run(100,16,128,256)
 run(100,8,256,512,pad='VALID')
 run(50,32,128,128)
+run(250,32,128,128)
+run(250,16,256,256)
+run(250,32,3,128)
