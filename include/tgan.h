@@ -180,6 +180,10 @@ int tgan_affine_act(const void* x, int xdt, void* y, int ydt, int64_t rows, int 
  * NULL; deterministic, ws as channel_stats). */
 int tgan_act_bwd(const void* dy, int dydt, const void* y, int ydt, void* du, int dudt, int64_t rows, int C,
                  int act, float alpha, float* colsum, float* grad_acc, float* ws, void* stream);
+/* same with y in a channel-padded buffer (row stride ldy >= C), e.g. a conv output written straight into its
+ * label-concatenated successor (modle_base.py:239-244) */
+int tgan_act_bwd_ld(const void* dy, int dydt, const void* y, int ydt, int ldy, void* du, int dudt, int64_t rows, int C,
+                    int act, float alpha, float* colsum, float* grad_acc, float* ws, void* stream);
 /* mean-only BN backward: dz = du - colsum[c]/rows */
 int tgan_sub_channel_mean(const void* du, int dudt, void* dz, int dzdt, int64_t rows, int C,
                           const float* colsum, void* stream);
@@ -213,6 +217,10 @@ int tgan_global_pool_bwd(const void* dy, int dydt, const uint8_t* idx, void* dx,
  * out[r, 0:C] = x[r, 0:C]; out[r, C:C+K] = lab[r / rows_per_sample, 0:K]; out[r, C+K:ldo] = 0. */
 int tgan_concat_label(const void* x, int xdt, int64_t rows, int C, int ldx, const float* lab, int K,
                       int rows_per_sample, void* out, int odt, int ldo, void* stream);
+/* label planes only: out[r, C + j] = j < K ? lab[r / rows_per_sample, j] : 0 for j in [0, ldo - C) -- used when the
+ * producing GEMM epilogue already wrote channels [0, C) of the concatenated tensor in place */
+int tgan_fill_label(const float* lab, int K, int rows_per_sample, void* out, int odt, int64_t rows, int C, int ldo,
+                    void* stream);
 /* strided channel slice / cast: dst[r, 0:C] = src[r, 0:C] */
 int tgan_copy_channels(const void* src, int sdt, int lds, void* dst, int ddt, int ldd, int64_t rows, int C,
                        void* stream);

@@ -280,16 +280,23 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha + bias;
-        // optional stages sit behind warp-uniform branches (no predicated-off transcendental code in the hot path)
+        // optional stages sit behind warp-uniform branches; every loop is fully unrolled so that v[] stays in registers
+        // (a single dynamically indexed access would move the whole array to local memory)
         if (p.act == TGAN_ACT_LRELU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
         } else if (p.act == TGAN_ACT_RELU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        } else if (p.act != TGAN_ACT_NONE) {
-#pragma unroll 1
-          for (int j = 0; j < 32; ++j) v[j] = act_fwd(v[j], p.act, 0.2f);
+        } else if (p.act == TGAN_ACT_TANH) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+        } else if (p.act == TGAN_ACT_SIGMOID) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
+        } else if (p.act == TGAN_ACT_SOFTPLUS) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = v[j] > 20.f ? v[j] : log1pf(expf(v[j]));
         }
         const int pbase = c0 & 127;
         if (p.tstore) {
@@ -348,7 +355,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       if (lane == 0) mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; accphase ^= 1; }
     }
-    if (p.tstore && warp == 2 && lane == 0) bulk_wait0();   // staging buffer must outlive the last store's read
+    if (p.tstore && warp == 2 && lane == 0) bulk_wait_read0();   // staging buffer must outlive the last store's read
   }
   tc_fence_before();
   __syncthreads();

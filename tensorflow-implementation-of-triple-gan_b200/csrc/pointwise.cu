@@ -24,16 +24,16 @@ struct StatsF {
 
 template <typename TDY, typename TY, typename TDU, int VEC, int ACT>
 struct ActBwdF {
-  const TDY* dy; const TY* y; TDU* du; int C; float alpha;
+  const TDY* dy; const TY* y; TDU* du; int C; float alpha; int ldy;      // y may live in a channel-padded buffer
   __device__ void operator()(int64_t r, int c0, float (&v)[1][VEC]) const {
     if constexpr (VEC == 4) {
       float a[4], b[4], o[4];
-      ld4<TDY>(dy, r * C + c0, a); ld4<TY>(y, r * C + c0, b);
+      ld4<TDY>(dy, r * C + c0, a); ld4<TY>(y, r * ldy + c0, b);
 #pragma unroll
       for (int j = 0; j < 4; ++j) { o[j] = a[j] * act_grad_from_y_t<ACT>(b[j], alpha); v[0][j] = o[j]; }
       st4<TDU>(du, r * C + c0, o);
     } else {
-      float o = ldf<TDY>(dy, r * C + c0) * act_grad_from_y_t<ACT>(ldf<TY>(y, r * C + c0), alpha);
+      float o = ldf<TDY>(dy, r * C + c0) * act_grad_from_y_t<ACT>(ldf<TY>(y, r * ldy + c0), alpha);
       v[0][0] = o; stf<TDU>(du, r * C + c0, o);
     }
   }
@@ -402,6 +402,18 @@ __global__ void concat_label_kernel(const TX* __restrict__ x, int64_t rows, int 
   else if (j < C + K) v = lab[(r / rps) * K + (j - C)];
   stf<TO>(out, i, v);
 }
+// out[r, C + j] = j < K ? lab[(r / rps) * K + j] : 0 for j in [0, ldo - C): the label planes (+ zero pad) of a tensor whose
+// first C channels were written in place by the producing GEMM epilogue
+template <typename TO>
+__global__ void fill_label_kernel(const float* __restrict__ lab, int K, int rps, TO* __restrict__ out, int C, int ldo,
+                                  int64_t total) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int w = ldo - C;
+  const int j = (int)(i % w);
+  const int64_t r = i / w;
+  stf<TO>(out, r * ldo + C + j, j < K ? lab[(r / rps) * K + j] : 0.f);
+}
 template <typename TS, typename TD>
 __global__ void copy_channels_kernel(const TS* __restrict__ src, int lds, TD* __restrict__ dst, int ldd, int C,
                                      int64_t total) {
@@ -579,12 +591,17 @@ extern "C" int tgan_affine_act(const void* x, int xdt, void* y, int ydt, int64_t
 
 extern "C" int tgan_act_bwd(const void* dy, int dydt, const void* y, int ydt, void* du, int dudt, int64_t rows, int C,
                             int act, float alpha, float* colsum, float* grad_acc, float* ws, void* stream) {
-  TGAN_CHECK_ARG(dy && y && du && ws && rows > 0 && C > 0, "act_bwd: bad args");
-  bool v = (C % 4 == 0) && aligned16(dy) && aligned16(y) && aligned16(du);
+  return tgan_act_bwd_ld(dy, dydt, y, ydt, C, du, dudt, rows, C, act, alpha, colsum, grad_acc, ws, stream);
+}
+extern "C" int tgan_act_bwd_ld(const void* dy, int dydt, const void* y, int ydt, int ldy, void* du, int dudt,
+                               int64_t rows, int C, int act, float alpha, float* colsum, float* grad_acc, float* ws,
+                               void* stream) {
+  TGAN_CHECK_ARG(dy && y && du && ws && rows > 0 && C > 0 && ldy >= C, "act_bwd: bad args");
+  bool v = (C % 4 == 0) && (ldy % 4 == 0) && aligned16(dy) && aligned16(y) && aligned16(du);
   TGAN_DISPATCH_1(dydt, TDY, TGAN_DISPATCH_1(ydt, TY, TGAN_DISPATCH_1(dudt, TDU, {
     TGAN_DISPATCH_ACT(act, A, {
-      ActBwdF<TDY, TY, TDU, 1, A> f1{(const TDY*)dy, (const TY*)y, (TDU*)du, C, alpha};
-      ActBwdF<TDY, TY, TDU, 4, A> f4{(const TDY*)dy, (const TY*)y, (TDU*)du, C, alpha};
+      ActBwdF<TDY, TY, TDU, 1, A> f1{(const TDY*)dy, (const TY*)y, (TDU*)du, C, alpha, ldy};
+      ActBwdF<TDY, TY, TDU, 4, A> f4{(const TDY*)dy, (const TY*)y, (TDU*)du, C, alpha, ldy};
       return run_colreduce<1>(f1, f4, v, rows, C, colsum, nullptr, 0.f, ws, (cudaStream_t)stream, grad_acc);
     });
   })));
@@ -698,6 +715,15 @@ extern "C" int tgan_concat_label(const void* x, int xdt, int64_t rows, int C, in
   int64_t total = rows * ldo;
   DISPATCH_2(xdt, TX, odt, TO, (concat_label_kernel<TX, TO><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
                                    (const TX*)x, rows, C, ldx, lab, K, rows_per_sample, (TO*)out, ldo, total)));
+  TGAN_LAUNCHED();
+  return 0;
+}
+extern "C" int tgan_fill_label(const float* lab, int K, int rows_per_sample, void* out, int odt, int64_t rows, int C,
+                               int ldo, void* stream) {
+  TGAN_CHECK_ARG(lab && out && ldo >= C + K && rows_per_sample > 0 && rows > 0, "fill_label: bad args");
+  int64_t total = rows * (ldo - C);
+  TGAN_DISPATCH_1(odt, TO, (fill_label_kernel<TO><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                               lab, K, rows_per_sample, (TO*)out, C, ldo, total)));
   TGAN_LAUNCHED();
   return 0;
 }

@@ -72,7 +72,7 @@ class Good_GAN(model_base.NN_Base):
                     h = self._add_noise(h, stddev=0.2, tag=tag + '/noise%d' % (i + 1))
                     h = ops.concat_label(h, y)
                 h5 = self._WN_dense(h, 1, 'd_h5_wndense0', init=False)
-                h5 = ops.bias_act(*h5._lazy, 'none')
+                h5 = ops.force(h5)
                 return _LazySigmoid(h5), h5
             # svhn :126-165 / cifar10 :167-206
             image = self._drop_out(image, 0.2, True, tag=tag + '/drop0')
@@ -110,7 +110,7 @@ class Good_GAN(model_base.NN_Base):
             if self.config.MINIBATCH_DIS:
                 raise NotImplementedError('MINIBATCH_DIS is off in every reference config (Train_goodGAN.py:511)')
             h3 = self._WN_dense(h3, 1, 'd_h3_wndense')
-            h3 = ops.bias_act(*h3._lazy, 'none')
+            h3 = ops.force(h3)
             return _LazySigmoid(h3), h3
 
     def classifier(self, image, train_ph, reuse=False, tag='C'):

@@ -91,7 +91,7 @@ class Good_GAN_cifar10(model_base.NN_Base):
             h3 = ops.global_pool(h2, 'mean')      # average_pooling2d(8, 1) + squeeze (:94-96)
             h3 = ops.concat_label(h3, y)
             h3 = self._linear_fc(h3, 1, 'lin', kernel_initializer=he_init)
-            h3 = ops.bias_act(*h3._lazy, 'none')      # logits are consumed as is: apply the pending bias now
+            h3 = ops.force(h3)      # logits are consumed as is: apply the pending bias now
         return _LazySigmoid(h3), h3
 
     def classifier(self, inp, is_training, init=False, reuse=False, getter=None, tag='C'):

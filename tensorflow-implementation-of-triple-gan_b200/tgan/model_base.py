@@ -112,10 +112,7 @@ class NN_Base(object):
         s = list(input.shape)
         x = ops.reshape(input, [int(np.prod(s[:-1])), s[-1]])
         x = self._WN_dense(x, num_units, name)
-        if x._lazy is not None:            # keep the pending bias fusable through the reshape
-            z, b = x._lazy
-            return ops.lazy_bias(ops.reshape(z, s[:-1] + [num_units]), b)
-        return ops.reshape(x, s[:-1] + [num_units])
+        return ops.reshape_pending(x, s[:-1] + [num_units])      # keeps the pending bias fusable through the reshape
 
     def _batch_norm_contrib(self, x, name, train=False):
         return nn.batch_norm_contrib(x, name, train, self._batch_norm_decay, self._batch_norm_epsilon)

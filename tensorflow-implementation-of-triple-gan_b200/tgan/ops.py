@@ -249,8 +249,39 @@ def _im2col(x, N, H, W, C, ld, kh, kw, s, pt, pl, Ho, Wo):
     return col
 
 
+class Deferred:
+    """A tensor-core contraction whose launch is deferred until its consumer is known, so that the bias, the
+    nonlinearity and the output row stride (a label-concatenated successor, modle_base.py:239-244) are fused into the
+    GEMM epilogue instead of running as separate passes over the activation."""
+    __slots__ = ('run', 'b', 'act', 'alpha')
+
+    def __init__(self, run):
+        self.run, self.b, self.act, self.alpha = run, None, 'none', 0.2
+
+
+def _deferred(v):
+    return v._data is None and isinstance(v._lazy, Deferred)
+
+
+def _epilogue_bwd(out, b, act, alpha):
+    """gradient through y = act(z + b) fused in a GEMM epilogue: returns dz (bf16 [rows, C]) and accumulates db"""
+    dy = out.grad
+    C, rows = out.C, out.rows
+    a = ACT[act]
+    need_db = b is not None and b.requires_grad
+    if a == 0:
+        if need_db:
+            _lib.call('tgan_channel_stats', _p(dy), dt_code(dy), rows, C, _p(b.grad), None, 1.0, _p(ctx.ws()), _st())
+        return dy
+    du = _new((rows, C), out.data.dtype)
+    _lib.call('tgan_act_bwd_ld', _p(dy), dt_code(dy), _p(out.data), dt_code(out.data), out.ld, _p(du), dt_code(du),
+              rows, C, a, alpha, None, _p(b.grad) if need_db else None, _p(ctx.ws()), _st())
+    return du
+
+
 def conv2d(x, w, kh, kw, stride=1, padding='SAME', colsum=False):
-    """tf.nn.conv2d (NHWC x HWIO).  x may be 2-D [rows, C] with kh = kw = 1 (tf.matmul)."""
+    """tf.nn.conv2d (NHWC x HWIO).  x may be 2-D [rows, C] with kh = kw = 1 (tf.matmul).  In tensor-core mode the
+    launch is deferred (see Deferred) unless the caller wants the epilogue's channel sums (mean-only BN)."""
     Cout = w.key.shape[-1]
     C = x.C
     if len(x.shape) == 2:
@@ -273,27 +304,44 @@ def conv2d(x, w, kh, kw, stride=1, padding='SAME', colsum=False):
     rows = N * Ho * Wo
     K = kh * kw * C
     direct = (kh == 1 and kw == 1 and stride == 1 and pt == 0 and pl == 0)
-    cs = None
     segs = _segs(x)
     if use_tc:
-        seg_ok = segs is None or len(segs) <= 4
-        cs = arena_take(Cout * (len(segs) if segs else 1)) if (colsum and seg_ok) else None
-        z = tc.conv_fwd(x, w, geom, cs, segs if cs is not None else None)
-    else:
-        xd = x.data
-        Wt = w.value()
-        if direct:
-            a = _to_f32(xd, rows, C, x.ld)
-            lda = C
+        tape = ctx.tape
+        out = _prop(Var(None, oshape, requires_grad=rg), x)
+
+        def run(b, act, alpha, out_ld):
+            ld = out_ld or Cout
+            cs = None
+            if colsum and (segs is None or len(segs) <= 4):
+                cs = arena_take(Cout * (len(segs) if segs else 1))
+            z = tc.conv_fwd(x, w, geom, cs, segs if cs is not None else None, bias=None if b is None else b.data,
+                            act=ACT[act], ldo=ld)
+            out._data, out.ld, out._lazy = z.view(tuple(out.shape[:-1]) + (ld,)), ld, None
+            if cs is not None:
+                out.aux = dict(out.aux or {}, colsum=cs)
+            if out.requires_grad and tape is not None:
+                def bwd():
+                    if out.grad is not None:
+                        tc.conv_bwd(x, w, geom, _epilogue_bwd(out, b, act, alpha))
+                tape.nodes.append(bwd)
+
+        if colsum:
+            run(None, 'none', 0.2, None)
         else:
-            a = _im2col(xd, N, H, W, C, x.ld, kh, kw, stride, pt, pl, Ho, Wo)
-            lda = K
-        z = _new((rows, Cout), torch.float32)
-        _sgemm(0, 0, rows, Cout, K, a, lda, Wt, Cout, z, Cout)
-        del a
+            out._lazy = Deferred(run)
+        return out
+    xd = x.data
+    Wt = w.value()
+    if direct:
+        a = _to_f32(xd, rows, C, x.ld)
+        lda = C
+    else:
+        a = _im2col(xd, N, H, W, C, x.ld, kh, kw, stride, pt, pl, Ho, Wo)
+        lda = K
+    z = _new((rows, Cout), torch.float32)
+    _sgemm(0, 0, rows, Cout, K, a, lda, Wt, Cout, z, Cout)
+    del a
     out = _prop(Var(z.view(oshape), oshape, requires_grad=rg), x)
-    if cs is not None:
-        out.aux = dict(out.aux or {}, colsum=cs)
     if rg:
         tape = ctx.tape
 
@@ -301,9 +349,6 @@ def conv2d(x, w, kh, kw, stride=1, padding='SAME', colsum=False):
             if out.grad is None:
                 return
             dz = out.grad
-            if use_tc:
-                tc.conv_bwd(x, w, geom, dz)
-                return
             dzf = _to_f32(dz, rows, Cout, Cout)
             Wt = w.value()
             if w.requires_grad:
@@ -345,24 +390,34 @@ def conv2d_transpose(x, w, kh, kw, stride=2):
     use_tc = ctx.math == 'bf16' and tc.deconv_eligible(geom, x)
     rows, KK = N * h * wd, kh * kw * Cout
     if use_tc:
-        y = tc.deconv_fwd(x, w, geom)
-    else:
-        xf = _to_f32(x.data, rows, Cin, x.ld)
-        dcol = _new((rows, KK), torch.float32)
-        _sgemm(0, 1, rows, KK, Cin, xf, Cin, w.value(), Cin, dcol, KK)
-        y = _new(oshape, _out_dtype(Cout) if ctx.math == 'bf16' else torch.float32)
-        _lib.call('tgan_col2im', _p(dcol), N, Ho, Wo, Cout, kh, kw, stride, stride, pt, pl, h, wd, _p(y), dt_code(y),
-                  Cout, Cout, _st())
-        del dcol
+        tape = ctx.tape
+        out = Var(None, oshape, requires_grad=rg)
+
+        def run(b, act, alpha, out_ld):
+            ld = out_ld or Cout
+            y = tc.deconv_fwd(x, w, geom, bias=None if b is None else b.data, act=ACT[act], ldo=ld)
+            out._data, out.ld, out._lazy = y.view(tuple(out.shape[:-1]) + (ld,)), ld, None
+            if out.requires_grad and tape is not None:
+                def bwd():
+                    if out.grad is not None:
+                        tc.deconv_bwd(x, w, geom, _epilogue_bwd(out, b, act, alpha))
+                tape.nodes.append(bwd)
+
+        out._lazy = Deferred(run)
+        return out
+    xf = _to_f32(x.data, rows, Cin, x.ld)
+    dcol = _new((rows, KK), torch.float32)
+    _sgemm(0, 1, rows, KK, Cin, xf, Cin, w.value(), Cin, dcol, KK)
+    y = _new(oshape, _out_dtype(Cout) if ctx.math == 'bf16' else torch.float32)
+    _lib.call('tgan_col2im', _p(dcol), N, Ho, Wo, Cout, kh, kw, stride, stride, pt, pl, h, wd, _p(y), dt_code(y),
+              Cout, Cout, _st())
+    del dcol
     out = Var(y, oshape, requires_grad=rg)
     if rg:
         def bwd():
             if out.grad is None:
                 return
             dy = out.grad
-            if use_tc:
-                tc.deconv_bwd(x, w, geom, dy)
-                return
             col = _im2col(dy, N, Ho, Wo, Cout, Cout, kh, kw, stride, pt, pl, h, wd)      # [rows, KK]
             if w.requires_grad:
                 xf = _to_f32(x.data, rows, Cin, x.ld)
@@ -422,14 +477,23 @@ def bias_act(z, b, act='none', alpha=0.2):
 
 
 def lazy_bias(z, b):
-    """Defers `z + b` so that a following activation fuses into ONE epilogue kernel
-    (tf.layers.dense / conv2d return value followed by tf.nn.relu / leakyReLu in the builders)."""
+    """Defers `z + b` so that a following activation fuses into ONE epilogue
+    (tf.layers.dense / conv2d return value followed by tf.nn.relu / leakyReLu in the builders): the epilogue of the
+    deferred tensor-core GEMM itself, or one bias+activation kernel behind an already computed z."""
+    if _deferred(z) and z._lazy.b is None and z._lazy.act == 'none':
+        z._lazy.b = b
+        z.requires_grad = z.requires_grad or (_on() and b.requires_grad)
+        return z
     v = Var(None, z.shape, requires_grad=_on() and (z.requires_grad or b.requires_grad))
     v._lazy = (z, b)
     return v
 
 
-def _materialize(v):
+def _materialize(v, out_ld=None):
+    if isinstance(v._lazy, Deferred):
+        d = v._lazy
+        d.run(d.b, d.act, d.alpha, out_ld)
+        return
     z, b = v._lazy
     y = bias_act(z, b, 'none')
     v._lazy = None
@@ -444,8 +508,11 @@ def _materialize(v):
 
 
 def activation(x, act, alpha=0.2):
-    """tf.nn.relu / leaky_relu / tanh / sigmoid / softplus; fuses a pending bias."""
-    if x._data is None and x._lazy is not None:
+    """tf.nn.relu / leaky_relu / tanh / sigmoid / softplus; fuses into a pending GEMM epilogue / pending bias."""
+    if _deferred(x) and x._lazy.act == 'none' and (act != 'lrelu' or abs(alpha - 0.2) < 1e-12):
+        x._lazy.act, x._lazy.alpha = act, alpha
+        return x
+    if x._data is None and isinstance(x._lazy, tuple):
         z, b = x._lazy
         return bias_act(z, b, act, alpha)
     return bias_act(x, None, act, alpha)
@@ -688,18 +755,27 @@ def concat_label(x, y):
     rg = _on() and x.requires_grad
     if ctx.building:
         return Var(None, oshape, ld=ld, requires_grad=rg)
-    xd = x.data
     lab = y.data if isinstance(y, Var) else y
     assert lab.dtype == torch.float32
-    o = _new(tuple(x.shape[:-1]) + (ld,))
-    _lib.call('tgan_concat_label', _p(xd), dt_code(xd), rows, C, x.ld, _p(lab), K, rps, _p(o), dt_code(o), ld, _st())
+    if _deferred(x) and ctx.math == 'bf16':
+        # the producing GEMM writes channels [0, C) straight into the concatenated buffer; only the label planes
+        # (and the zero pad) are filled here
+        _materialize(x, out_ld=ld)
+        o = x.data
+        _lib.call('tgan_fill_label', _p(lab), K, rps, _p(o), dt_code(o), rows, C, ld, _st())
+    else:
+        xd = x.data
+        o = _new(tuple(x.shape[:-1]) + (ld,))
+        _lib.call('tgan_concat_label', _p(xd), dt_code(xd), rows, C, x.ld, _p(lab), K, rps, _p(o), dt_code(o), ld, _st())
     out = Var(o, oshape, ld=ld, requires_grad=rg)
+    # tensor-core consumers compute the input gradient of the first C channels only and hand it to x directly
+    out.aux = {'concat_src': x, 'C0': C}
     if rg:
         def bwd():
             if out.grad is None:
                 return
             g = out.grad          # [rows, C+K] contiguous (producers write logical channels densely)
-            dx = _new(x.shape, xd.dtype)
+            dx = _new(x.shape, x.data.dtype)
             _lib.call('tgan_copy_channels', _p(g), dt_code(g), C + K, _p(dx), dt_code(dx), C, rows, C, _st())
             add_grad(x, dx)
         ctx.tape.nodes.append(bwd)
@@ -723,6 +799,28 @@ def reshape(x, shape):
                 add_grad(x, out.grad.view(x.shape))
         ctx.tape.nodes.append(bwd)
     return out
+
+
+def reshape_pending(x, shape):
+    """reshape that keeps a pending epilogue (deferred GEMM / pending bias) pending"""
+    shape = tuple(int(v) for v in shape)
+    if _deferred(x):
+        assert int(np.prod(shape)) == int(np.prod(x.shape))
+        x.shape = shape           # the launch views its output with the shape current at materialisation
+        return x
+    if x._data is None and isinstance(x._lazy, tuple):
+        z, b = x._lazy
+        return lazy_bias(reshape(z, shape), b)
+    return reshape(x, shape)
+
+
+def force(v):
+    """apply whatever is pending on v now (logits that are consumed as they are)"""
+    if v._data is None and isinstance(v._lazy, tuple):
+        return bias_act(*v._lazy, 'none')
+    if not ctx.building:
+        v.data
+    return v
 
 
 def constant(t, dtype=torch.float32):

@@ -74,7 +74,7 @@ def _pack(w, key, T, Nrows, K, st, sn, sk, taps=None):
 
 
 def _igemm(x, N, H, W, C, ldx, wp, Kpad, taps, Nout, gh, gw, out, OH, OW, ldo, s=1, os_=1, oo=(0, 0), vh=0, vw=0,
-           colsum=None, segs=None):
+           colsum=None, segs=None, bias=None, act=0):
     a = _lib.TganIgemmArgs()
     a.x, a.N, a.H, a.W, a.C, a.ldx = x.data_ptr(), N, H, W, C, ldx
     a.wp, a.T, a.Nout, a.Kpad = wp.data_ptr(), len(taps), Nout, Kpad
@@ -83,7 +83,8 @@ def _igemm(x, N, H, W, C, ldx, wp, Kpad, taps, Nout, gh, gw, out, OH, OW, ldo, s
     a.gh, a.gw, a.sy, a.sx = gh, gw, s, s
     a.out, a.odt, a.OH, a.OW, a.ldo = out.data_ptr(), dt_code(out), OH, OW, ldo
     a.osy, a.osx, a.ooy, a.oox, a.vh, a.vw = os_, os_, oo[0], oo[1], vh, vw
-    a.bias, a.colsum, a.act, a.alpha = None, (None if colsum is None else colsum.data_ptr()), 0, 1.0
+    a.bias, a.colsum = (None if bias is None else bias.data_ptr()), (None if colsum is None else colsum.data_ptr())
+    a.act, a.alpha = act, 1.0
     if segs and len(segs) > 1:
         a.nseg, e = len(segs), 0
         for i, n in enumerate(segs[:-1]):
@@ -123,20 +124,30 @@ def _flat(g):
     return g
 
 
-def conv_fwd(x, w, g, colsum=None, segs=None):
+def conv_fwd(x, w, g, colsum=None, segs=None, bias=None, act=0, ldo=None):
+    """-> bf16 [rows, ldo] with act(conv + bias) in channels [0, Cout) (ldo > Cout: the rest is left untouched)"""
     gf = _flat(g)
     C, Cout, kh, kw = g['C'], g['Cout'], g['kh'], g['kw']
     xd, ld = _bf16_padded(x.data, x.rows, C, x.ld)
     g['_x'] = (xd, ld)
     wp, Kpad = _pack(w, 'fprop', kh * kw, Cout, C, C * Cout, 1, Cout)
     taps = [(r - g['pt'], c - g['pl']) for r in range(kh) for c in range(kw)]
-    z = _new((g['N'] * g['Ho'] * g['Wo'], Cout), torch.bfloat16)
+    ldo = ldo or Cout
+    z = _new((g['N'] * g['Ho'] * g['Wo'], ldo), torch.bfloat16)
     if segs and gf is not g:          # plain GEMM: segments become ranges of rows
         rps = (g['N'] * g['Ho'] * g['Wo']) // sum(segs)
         segs = [n * rps for n in segs]
-    _igemm(xd, gf['N'], gf['H'], gf['W'], C, ld, wp, Kpad, taps, Cout, gf['Ho'], gf['Wo'], z, gf['Ho'], gf['Wo'], Cout,
-           s=g['s'], colsum=colsum, segs=segs)
+    _igemm(xd, gf['N'], gf['H'], gf['W'], C, ld, wp, Kpad, taps, Cout, gf['Ho'], gf['Wo'], z, gf['Ho'], gf['Wo'], ldo,
+           s=g['s'], colsum=colsum, segs=segs, bias=bias, act=act)
     return z
+
+
+def _grad_target(x, C):
+    """-> (Var that receives the input gradient, number of leading channels it covers)"""
+    src = x.aux.get('concat_src') if x.aux else None
+    if src is not None:
+        return src, x.aux['C0']
+    return x, C
 
 
 def conv_bwd(x, w, g, dz):
@@ -150,14 +161,16 @@ def conv_bwd(x, w, g, dz):
         taps = [(r - pt, c - pl) for r in range(kh) for c in range(kw)]
         # the kernel writes [t][ci][co] == HWIO
         _wgrad(dzb, gf['N'], gf['Ho'], gf['Wo'], Cout, Cout, xd, gf['H'], gf['W'], C, ld, taps, s, w.grad_target())
-    if x.requires_grad:
-        dx = _new(x.shape, x.data.dtype if x.data.dtype == torch.bfloat16 else torch.float32)
+    tgt, Cg = _grad_target(x, C)
+    if tgt.requires_grad:
+        # a label-concatenated input only needs the gradient of its first Cg channels: it goes to the concat's source
+        dx = _new(tuple(x.shape[:-1]) + (Cg,), tgt.data.dtype if tgt.data.dtype == torch.bfloat16 else torch.float32)
         wp, Kpad = None, None
         if s == 1:
-            wp, Kpad = _pack(w, 'dgrad', kh * kw, C, Cout, C * Cout, Cout, 1)
+            wp, Kpad = _pack(w, ('dgrad', Cg), kh * kw, Cg, Cout, C * Cout, Cout, 1)
             taps = [(pt - r, pl - c) for r in range(kh) for c in range(kw)]
-            _igemm(dzb, gf['N'], gf['Ho'], gf['Wo'], Cout, Cout, wp, Kpad, taps, C, gf['H'], gf['W'], dx, gf['H'],
-                   gf['W'], C)
+            _igemm(dzb, gf['N'], gf['Ho'], gf['Wo'], Cout, Cout, wp, Kpad, taps, Cg, gf['H'], gf['W'], dx, gf['H'],
+                   gf['W'], Cg)
         else:
             # input-gradient of a stride-2 conv = transposed conv: one launch per output parity class
             for py in range(2):
@@ -168,10 +181,10 @@ def conv_bwd(x, w, g, dz):
                         continue
                     sel = [r * kw + c for r in rs for c in cs]
                     taps = [((py + pt - r) // 2, (px + pl - c) // 2) for r in rs for c in cs]
-                    wp, Kpad = _pack(w, ('dgrad2', py, px), len(sel), C, Cout, C * Cout, Cout, 1, sel)
-                    _igemm(dzb, g['N'], g['Ho'], g['Wo'], Cout, Cout, wp, Kpad, taps, C, g['H'] // 2, g['W'] // 2, dx,
-                           g['H'], g['W'], C, os_=2, oo=(py, px))
-        add_grad(x, dx if dx.dtype == x.data.dtype else dx.to(x.data.dtype))
+                    wp, Kpad = _pack(w, ('dgrad2', py, px, Cg), len(sel), Cg, Cout, C * Cout, Cout, 1, sel)
+                    _igemm(dzb, g['N'], g['Ho'], g['Wo'], Cout, Cout, wp, Kpad, taps, Cg, g['H'] // 2, g['W'] // 2, dx,
+                           g['H'], g['W'], Cg, os_=2, oo=(py, px))
+        add_grad(tgt, dx if dx.dtype == tgt.data.dtype else dx.to(tgt.data.dtype))
     g.pop('_x', None)
 
 
@@ -195,15 +208,16 @@ def _parity_classes(g):
                     [((py + pt - r) // 2, (px + pl - c) // 2) for r in rs for c in cs]
 
 
-def deconv_fwd(x, w, g):
+def deconv_fwd(x, w, g, bias=None, act=0, ldo=None):
     Cin, Cout = g['Cin'], g['Cout']
     xd, ld = _bf16_padded(x.data, x.rows, Cin, x.ld)
     g['_x'] = (xd, ld)
-    y = _new((g['N'], g['Ho'], g['Wo'], Cout), torch.bfloat16)
+    ldo = ldo or Cout
+    y = _new((g['N'], g['Ho'], g['Wo'], ldo), torch.bfloat16)
     for py, px, sel, taps in _parity_classes(g):
         wp, Kpad = _pack(w, ('dfwd', py, px), len(sel), Cout, Cin, Cout * Cin, Cin, 1, sel)
-        _igemm(xd, g['N'], g['h'], g['w'], Cin, ld, wp, Kpad, taps, Cout, g['h'], g['w'], y, g['Ho'], g['Wo'], Cout,
-               os_=2, oo=(py, px))
+        _igemm(xd, g['N'], g['h'], g['w'], Cin, ld, wp, Kpad, taps, Cout, g['h'], g['w'], y, g['Ho'], g['Wo'], ldo,
+               os_=2, oo=(py, px), bias=bias, act=act)
     return y
 
 
@@ -217,10 +231,11 @@ def deconv_bwd(x, w, g, dy):
         # roles exchanged: M side = x channels (ci), N side = strided dy window (co); the kernel's
         # [t][N-side][M-side] output is then exactly the filter layout [kh,kw,Cout,Cin]
         _wgrad(xd, g['N'], g['h'], g['w'], Cin, ld, dyb, g['Ho'], g['Wo'], Cout, Cout, taps, 2, w.grad_target())
-    if x.requires_grad:
-        wp, Kpad = _pack(w, 'ddgrad', kh * kw, Cin, Cout, Cout * Cin, 1, Cin)
-        dx = _new(x.shape, torch.bfloat16)
-        _igemm(dyb, g['N'], g['Ho'], g['Wo'], Cout, Cout, wp, Kpad, taps, Cin, g['h'], g['w'], dx, g['h'], g['w'], Cin,
+    tgt, Cg = _grad_target(x, Cin)
+    if tgt.requires_grad:
+        wp, Kpad = _pack(w, ('ddgrad', Cg), kh * kw, Cg, Cout, Cout * Cin, 1, Cin)
+        dx = _new(tuple(x.shape[:-1]) + (Cg,), torch.bfloat16)
+        _igemm(dyb, g['N'], g['Ho'], g['Wo'], Cout, Cout, wp, Kpad, taps, Cg, g['h'], g['w'], dx, g['h'], g['w'], Cg,
                s=2)
-        add_grad(x, dx if dx.dtype == x.data.dtype else dx.to(x.data.dtype))
+        add_grad(tgt, dx if dx.dtype == tgt.data.dtype else dx.to(tgt.data.dtype))
     g.pop('_x', None)
