@@ -131,11 +131,11 @@ def dominant_kernel_roofline(torch, tgan, pk):
     st = torch.cuda.Stream()
     with torch.cuda.stream(st):
         for i in range(3):
-            ops.conv2d(xs[i], w, 3, 3, 1, 'SAME')
+            ops.conv2d(xs[i], w, 3, 3, 1, 'SAME').data      # .data launches the (deferred) contraction
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
-        keep = [ops.conv2d(xs[i % 8], w, 3, 3, 1, 'SAME') for i in range(R)]
+        keep = [ops.conv2d(xs[i % 8], w, 3, 3, 1, 'SAME').data for i in range(R)]
     g.replay()
     torch.cuda.synchronize()
     ts = []

@@ -86,6 +86,11 @@ typedef struct {
   int seg_end[4];      /* exclusive image index where segment i ends (plain GEMM, N == 1 && gh == 1: pixel index) */
   int act;             /* TGAN_ACT_* applied after bias (before store)         */
   float alpha;
+  int ncls;            /* 0/1 = one tap list.  2..4 = output classes run in ONE launch (the output-parity sub-convolutions
+                          of a stride-2 transposed conv / stride-2 input gradient): class c owns the next cls_T[c] entries
+                          of dy/dx/wp (sum = T) and writes at output offset (cls_ooy[c], cls_oox[c]) instead of (ooy, oox);
+                          list the classes with the most taps first */
+  int cls_T[4], cls_ooy[4], cls_oox[4];
 } tgan_igemm_args;
 int tgan_igemm_bf16(const tgan_igemm_args* a, void* stream);
 

@@ -84,6 +84,9 @@ struct IgParams {
   int act;
   float alpha;
   int tstore;   // 1: bf16 output staged in shared memory and written by TMA bulk-tensor stores
+  // output-parity classes of a strided transposed convolution, all in ONE launch: class c owns taps
+  // [ctap0[c], ctap0[c] + cT[c]) of dy/dx/the packed weights and writes at output offset (cooy[c], coox[c])
+  int ncls, cT[4], ctap0[4], cooy[4], coox[4];
   int dbg;   // experiments only (TGAN_IGEMM_DBG): 1 skip activation loads, 2 skip weight loads, 4 skip stores
 };
 
@@ -92,7 +95,8 @@ struct IgParams {
 // run alone on their scheduler (no latency hiding), so per-element dependent integer chains would dominate the tile.
 template <int TW, typename TO>
 __device__ __forceinline__ void ig_store_chunk(const IgParams& p, TO* __restrict__ out, const float (&v)[32], int pbase,
-                                               int tx, int ty, int ng, int co, bool cvalid, float (&csum)[4]) {
+                                               int tx, int ty, int ng, int co, bool cvalid, float (&csum)[4], int ooy,
+                                               int oox) {
   const int ppi = p.th * p.tw;
   const int pstep = p.osx * p.ldo;
 #pragma unroll
@@ -101,7 +105,7 @@ __device__ __forceinline__ void ig_store_chunk(const IgParams& p, TO* __restrict
     const int nl = pix >> p.lppi, rem = pix & (ppi - 1);
     const int oy = ty * p.th + (rem >> p.ltw), ox0 = tx * p.tw + (rem & (p.tw - 1)), n = ng * p.nb + nl;
     const bool rowok = cvalid && (n < p.N) && (oy < p.vh);
-    const int base = ((n * p.OH + (oy * p.osy + p.ooy)) * p.OW + (ox0 * p.osx + p.oox)) * p.ldo + co;
+    const int base = ((n * p.OH + (oy * p.osy + ooy)) * p.OW + (ox0 * p.osx + oox)) * p.ldo + co;
     const int lim = p.vw - ox0;          // pixel jc is inside the valid width iff jc < lim
     const int sg = (n >= p.seg_end[0]) + (n >= p.seg_end[1]) + (n >= p.seg_end[2]);   // batch segment of this image
 #pragma unroll
@@ -158,7 +162,9 @@ __device__ __forceinline__ void ig_sum_chunk(const IgParams& p, const float (&v)
 
 __global__ void __launch_bounds__(IG_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-             const __grid_constant__ CUtensorMap tmO, const __grid_constant__ IgParams p) {
+             const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
+             const __grid_constant__ CUtensorMap tmO2, const __grid_constant__ CUtensorMap tmO3,
+             const __grid_constant__ IgParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* ostage = smem + (size_t)IG_STAGES * IG_STAGE_BYTES;
@@ -176,7 +182,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     fence_barrier_init();
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
-    if (p.tstore) tma_prefetch_desc(&tmO);
+    if (p.tstore) tma_prefetch_desc(&tmO0);
   }
   if (warp == 0) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }   // 2 accumulators x 256 fp32 columns
   tc_fence_before();
@@ -184,8 +190,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.pp_tiles * p.ct_tiles;
-  const int ksteps = p.T * p.kchunks;
+  const int tiles_per_cls = p.pp_tiles * p.ct_tiles;
+  const int total_tiles = tiles_per_cls * p.ncls;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
 
   // Producer and MMA-issuer warps run their loops with ALL 32 lanes (warp-uniform control flow keeps addresses and
@@ -193,7 +199,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
   if (warp == 0) {
     int stage = 0; uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int ct = tile % p.ct_tiles, pp = tile / p.ct_tiles;
+      const int cls = tile / tiles_per_cls, tin = tile - cls * tiles_per_cls;
+      const int ct = tin % p.ct_tiles, pp = tin / p.ct_tiles;
+      const int tap0 = p.ctap0[cls], tap1 = tap0 + p.cT[cls];
       int x0[2], y0[2], n0[2];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -202,7 +210,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         y0[h] = ((mt / p.tiles_x) % p.tiles_y) * p.th * p.sy;
         n0[h] = (mt / tiles_per_img) * p.nb;
       }
-      for (int t = 0; t < p.T; ++t) {
+      for (int t = tap0; t < tap1; ++t) {
         const int ddx = p.dx[t], ddy = p.dy[t];
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait(&empty[stage], phase ^ 1);
@@ -227,6 +235,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     const uint32_t s_base = smem_u32(smem) >> 4;
     int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t accphase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int ksteps = p.cT[tile / tiles_per_cls] * p.kchunks;
       mbar_wait(&tempty[acc], accphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * IG_NPIX);
@@ -263,7 +272,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     const int ppi = p.th * p.tw;               // pixels per image inside a 128-pixel tile (power of two)
     int acc = 0; uint32_t accphase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int ct = tile % p.ct_tiles, pp = tile / p.ct_tiles;
+      const int cls = tile / tiles_per_cls, tin = tile - cls * tiles_per_cls;
+      const int ct = tin % p.ct_tiles, pp = tin / p.ct_tiles;
+      const CUtensorMap* tmO = cls == 0 ? &tmO0 : cls == 1 ? &tmO1 : cls == 2 ? &tmO2 : &tmO3;
       const int co = ct * 128 + q * 32 + lane;
       const bool cvalid = co < p.Nout;
       const float bias = (p.bias && cvalid) ? p.bias[co] : 0.f;
@@ -321,7 +332,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             fence_proxy_async();
             named_bar_sync(1, 128);
             if (warp == 2 && lane == 0 && !(p.dbg & 4)) {
-              tma_store_4d(&tmO, ostage, ct * 128, tx * p.tw, ty * p.th, ng * p.nb);
+              tma_store_4d(tmO, ostage, ct * 128, tx * p.tw, ty * p.th, ng * p.nb);
               bulk_commit();
             }
           }
@@ -329,18 +340,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
           if (p.odt == TGAN_BF16) {
             bf16* o = reinterpret_cast<bf16*>(p.out);
             switch (p.ltw) {
-              case 2: ig_store_chunk<4>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum); break;
-              case 3: ig_store_chunk<8>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum); break;
-              case 4: ig_store_chunk<16>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum); break;
-              default: ig_store_chunk<32>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum); break;
+              case 2: ig_store_chunk<4>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum, p.cooy[cls], p.coox[cls]); break;
+              case 3: ig_store_chunk<8>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum, p.cooy[cls], p.coox[cls]); break;
+              case 4: ig_store_chunk<16>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum, p.cooy[cls], p.coox[cls]); break;
+              default: ig_store_chunk<32>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum, p.cooy[cls], p.coox[cls]); break;
             }
           } else {
             float* o = reinterpret_cast<float*>(p.out);
             switch (p.ltw) {
-              case 2: ig_store_chunk<4>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum); break;
-              case 3: ig_store_chunk<8>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum); break;
-              case 4: ig_store_chunk<16>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum); break;
-              default: ig_store_chunk<32>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum); break;
+              case 2: ig_store_chunk<4>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum, p.cooy[cls], p.coox[cls]); break;
+              case 3: ig_store_chunk<8>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum, p.cooy[cls], p.coox[cls]); break;
+              case 4: ig_store_chunk<16>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum, p.cooy[cls], p.coox[cls]); break;
+              default: ig_store_chunk<32>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum, p.cooy[cls], p.coox[cls]); break;
             }
           }
         }
@@ -533,6 +544,7 @@ using namespace tgan;
 extern "C" int tgan_igemm_bf16(const tgan_igemm_args* a, void* stream) {
   TGAN_CHECK_ARG(a && a->x && a->wp && a->out, "igemm: null pointer");
   TGAN_CHECK_ARG(a->T >= 1 && a->T <= 25, "igemm: T out of range");
+  TGAN_CHECK_ARG(a->ncls >= 0 && a->ncls <= 4, "igemm: at most 4 output classes");
   TGAN_CHECK_ARG(a->ldx % 8 == 0 && a->Kpad % 8 == 0, "igemm: ldx (%d) and Kpad (%d) must be multiples of 8", a->ldx, a->Kpad);
   TGAN_CHECK_ARG(((uintptr_t)a->x & 15) == 0 && ((uintptr_t)a->wp & 15) == 0, "igemm: operands must be 16B aligned");
   TGAN_CHECK_ARG(a->C >= 1 && a->C <= a->Kpad && a->Nout >= 1, "igemm: bad channel counts");
@@ -566,7 +578,21 @@ extern "C" int tgan_igemm_bf16(const tgan_igemm_args* a, void* stream) {
   p.tstore = (a->odt == TGAN_BF16 && a->ldo % 8 == 0 && ((uintptr_t)a->out & 15) == 0) ? 1 : 0;
   { const char* e = getenv("TGAN_IGEMM_NO_TSTORE"); if (e && atoi(e)) p.tstore = 0; }
 
-  CUtensorMap tmX, tmW, tmO;
+  p.ncls = a->ncls > 1 ? a->ncls : 1;
+  if (a->ncls > 1) {
+    int t0 = 0;
+    for (int c = 0; c < p.ncls; ++c) {
+      TGAN_CHECK_ARG(a->cls_T[c] >= 1, "igemm: empty output class");
+      p.cT[c] = a->cls_T[c]; p.ctap0[c] = t0; p.cooy[c] = a->cls_ooy[c]; p.coox[c] = a->cls_oox[c];
+      t0 += a->cls_T[c];
+    }
+    TGAN_CHECK_ARG(t0 == a->T, "igemm: class tap counts must add up to T");
+    TGAN_CHECK_ARG(a->colsum == nullptr, "igemm: channel sums are not supported with output classes");
+  } else {
+    p.cT[0] = a->T; p.ctap0[0] = 0; p.cooy[0] = p.ooy; p.coox[0] = p.oox;
+  }
+
+  CUtensorMap tmX, tmW, tmO[4];
   {
     uint64_t dims[4] = {(uint64_t)a->C, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->N};
     uint64_t str[3] = {(uint64_t)a->ldx * 2, (uint64_t)a->W * a->ldx * 2, (uint64_t)a->H * a->W * a->ldx * 2};
@@ -580,17 +606,16 @@ extern "C" int tgan_igemm_bf16(const tgan_igemm_args* a, void* stream) {
     uint32_t box[3] = {64, 128, 1};
     if (make_tmap_bf16(&tmW, a->wp, 3, dims, str, box, nullptr)) return 1;
   }
-  if (p.tstore) {
+  for (int c = 0; c < 4; ++c) {
+    if (!p.tstore || c >= p.ncls) { tmO[c] = tmX; continue; }
     // the valid output grid as a strided 4-D view [Nout, vw, vh, N] of out (parity-class placement = base offset +
     // pixel strides); staging rows are dense [pixel][128 channels], so the map is not swizzled
     const uint64_t ldo = (uint64_t)a->ldo;
     uint64_t dims[4] = {(uint64_t)a->Nout, (uint64_t)p.vw, (uint64_t)p.vh, (uint64_t)a->N};
     uint64_t str[3] = {(uint64_t)p.osx * ldo * 2, (uint64_t)p.osy * a->OW * ldo * 2, (uint64_t)a->OH * a->OW * ldo * 2};
     uint32_t box[4] = {128, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.nb};
-    const char* base = (const char*)a->out + ((int64_t)p.ooy * a->OW + p.oox) * (int64_t)ldo * 2;
-    if (make_tmap_bf16(&tmO, base, 4, dims, str, box, nullptr, false)) return 1;
-  } else {
-    tmO = tmX;
+    const char* base = (const char*)a->out + ((int64_t)p.cooy[c] * a->OW + p.coox[c]) * (int64_t)ldo * 2;
+    if (make_tmap_bf16(&tmO[c], base, 4, dims, str, box, nullptr, false)) return 1;
   }
   static bool attr_set = false;
   if (!attr_set) {
@@ -598,9 +623,9 @@ extern "C" int tgan_igemm_bf16(const tgan_igemm_args* a, void* stream) {
     TGAN_CHECK_ARG(e == cudaSuccess, "igemm: cannot set max dynamic smem: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int total = p.pp_tiles * p.ct_tiles;
+  const int total = p.pp_tiles * p.ct_tiles * p.ncls;
   const int grid = total < 148 ? total : 148;
-  igemm_kernel<<<grid, IG_THREADS, smem_bytes, (cudaStream_t)stream>>>(tmX, tmW, tmO, p);
+  igemm_kernel<<<grid, IG_THREADS, smem_bytes, (cudaStream_t)stream>>>(tmX, tmW, tmO[0], tmO[1], tmO[2], tmO[3], p);
   TGAN_LAUNCHED();
   return 0;
 }

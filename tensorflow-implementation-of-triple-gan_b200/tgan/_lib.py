@@ -51,7 +51,8 @@ class TganIgemmArgs(ctypes.Structure):
                 ('osx', ctypes.c_int), ('ooy', ctypes.c_int), ('oox', ctypes.c_int), ('vh', ctypes.c_int),
                 ('vw', ctypes.c_int), ('bias', ctypes.c_void_p), ('colsum', ctypes.c_void_p), ('nseg', ctypes.c_int), ('seg_end', ctypes.c_int * 4),
                 ('act', ctypes.c_int),
-                ('alpha', ctypes.c_float)]
+                ('alpha', ctypes.c_float), ('ncls', ctypes.c_int), ('cls_T', ctypes.c_int * 4),
+                ('cls_ooy', ctypes.c_int * 4), ('cls_oox', ctypes.c_int * 4)]
 
 
 class TganWgradArgs(ctypes.Structure):

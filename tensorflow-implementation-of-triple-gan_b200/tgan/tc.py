@@ -74,7 +74,7 @@ def _pack(w, key, T, Nrows, K, st, sn, sk, taps=None):
 
 
 def _igemm(x, N, H, W, C, ldx, wp, Kpad, taps, Nout, gh, gw, out, OH, OW, ldo, s=1, os_=1, oo=(0, 0), vh=0, vw=0,
-           colsum=None, segs=None, bias=None, act=0):
+           colsum=None, segs=None, bias=None, act=0, classes=None):
     a = _lib.TganIgemmArgs()
     a.x, a.N, a.H, a.W, a.C, a.ldx = x.data_ptr(), N, H, W, C, ldx
     a.wp, a.T, a.Nout, a.Kpad = wp.data_ptr(), len(taps), Nout, Kpad
@@ -85,6 +85,10 @@ def _igemm(x, N, H, W, C, ldx, wp, Kpad, taps, Nout, gh, gw, out, OH, OW, ldo, s
     a.osy, a.osx, a.ooy, a.oox, a.vh, a.vw = os_, os_, oo[0], oo[1], vh, vw
     a.bias, a.colsum = (None if bias is None else bias.data_ptr()), (None if colsum is None else colsum.data_ptr())
     a.act, a.alpha = act, 1.0
+    if classes:      # [(taps in class, output row offset, output col offset)]: parity classes in one launch
+        a.ncls = len(classes)
+        for i, (tn, oy, ox) in enumerate(classes):
+            a.cls_T[i], a.cls_ooy[i], a.cls_oox[i] = tn, oy, ox
     if segs and len(segs) > 1:
         a.nseg, e = len(segs), 0
         for i, n in enumerate(segs[:-1]):
@@ -172,18 +176,22 @@ def conv_bwd(x, w, g, dz):
             _igemm(dzb, gf['N'], gf['Ho'], gf['Wo'], Cout, Cout, wp, Kpad, taps, Cg, gf['H'], gf['W'], dx, gf['H'],
                    gf['W'], Cg)
         else:
-            # input-gradient of a stride-2 conv = transposed conv: one launch per output parity class
+            # input-gradient of a stride-2 conv = transposed conv: its output-parity classes, heaviest first, in ONE launch
+            cl = []
             for py in range(2):
                 for px in range(2):
                     rs = [r for r in range(kh) if (py + pt - r) % 2 == 0]
                     cs = [c for c in range(kw) if (px + pl - c) % 2 == 0]
-                    if not rs or not cs:
-                        continue
-                    sel = [r * kw + c for r in rs for c in cs]
-                    taps = [((py + pt - r) // 2, (px + pl - c) // 2) for r in rs for c in cs]
-                    wp, Kpad = _pack(w, ('dgrad2', py, px, Cg), len(sel), Cg, Cout, C * Cout, Cout, 1, sel)
-                    _igemm(dzb, g['N'], g['Ho'], g['Wo'], Cout, Cout, wp, Kpad, taps, Cg, g['H'] // 2, g['W'] // 2, dx,
-                           g['H'], g['W'], Cg, os_=2, oo=(py, px))
+                    if rs and cs:
+                        cl.append((py, px, [r * kw + c for r in rs for c in cs],
+                                   [((py + pt - r) // 2, (px + pl - c) // 2) for r in rs for c in cs]))
+            assert len(cl) == 4, 'every output parity must receive a tap (else it would need an explicit zero fill)'
+            cl.sort(key=lambda c: -len(c[2]))
+            sel = [i for c in cl for i in c[2]]
+            taps = [t for c in cl for t in c[3]]
+            wp, Kpad = _pack(w, ('dgrad2', Cg), len(sel), Cg, Cout, C * Cout, Cout, 1, sel)
+            _igemm(dzb, g['N'], g['Ho'], g['Wo'], Cout, Cout, wp, Kpad, taps, Cg, g['H'] // 2, g['W'] // 2, dx,
+                   g['H'], g['W'], Cg, os_=2, classes=[(len(c[2]), c[0], c[1]) for c in cl])
         add_grad(tgt, dx if dx.dtype == tgt.data.dtype else dx.to(tgt.data.dtype))
     g.pop('_x', None)
 
@@ -214,10 +222,13 @@ def deconv_fwd(x, w, g, bias=None, act=0, ldo=None):
     g['_x'] = (xd, ld)
     ldo = ldo or Cout
     y = _new((g['N'], g['Ho'], g['Wo'], ldo), torch.bfloat16)
-    for py, px, sel, taps in _parity_classes(g):
-        wp, Kpad = _pack(w, ('dfwd', py, px), len(sel), Cout, Cin, Cout * Cin, Cin, 1, sel)
-        _igemm(xd, g['N'], g['h'], g['w'], Cin, ld, wp, Kpad, taps, Cout, g['h'], g['w'], y, g['Ho'], g['Wo'], ldo,
-               os_=2, oo=(py, px), bias=bias, act=act)
+    cl = sorted(_parity_classes(g), key=lambda c: -len(c[2]))      # heaviest class first, all in ONE launch
+    assert len(cl) == 4
+    sel = [i for c in cl for i in c[2]]
+    taps = [t for c in cl for t in c[3]]
+    wp, Kpad = _pack(w, 'dfwd', len(sel), Cout, Cin, Cout * Cin, Cin, 1, sel)
+    _igemm(xd, g['N'], g['h'], g['w'], Cin, ld, wp, Kpad, taps, Cout, g['h'], g['w'], y, g['Ho'], g['Wo'], ldo,
+           os_=2, bias=bias, act=act, classes=[(len(c[2]), c[0], c[1]) for c in cl])
     return y
 
 

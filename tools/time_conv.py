@@ -12,11 +12,11 @@ def run(N,H,C,Co,k=3,pad='SAME', reps=20):
     w = ops.PlainWeight(p)
     st = torch.cuda.Stream()
     with torch.cuda.stream(st):
-        for i in range(3): ops.conv2d(xs[i % nbuf], w, k,k,1,pad)
+        for i in range(3): ops.conv2d(xs[i % nbuf], w, k,k,1,pad).data
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
-        outs = [ops.conv2d(xs[i % nbuf], w, k,k,1,pad) for i in range(reps)]
+        outs = [ops.conv2d(xs[i % nbuf], w, k,k,1,pad).data for i in range(reps)]
     g.replay(); torch.cuda.synchronize()
     e0,e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); g.replay(); e1.record(); e1.synchronize()
