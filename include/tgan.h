@@ -122,6 +122,31 @@ int tgan_sizeof_wgrad_args(void);
 int tgan_pack_weight_bf16(const float* src, void* dst, int T, int Nrows, int K, int Kpad, int64_t st, int64_t sn,
                           int64_t sk, const int* taps_dev, void* stream);
 
+/* ---------------------------------------------------------------- multi-tensor weight preparation --
+ * One launch for every layer of a network (descriptor tables live in DEVICE memory; the pointers inside are device
+ * pointers, normally views into the flat per-network parameter / gradient buffers).
+ *   weightnorm_fwd_multi : inv_norm[co], scale[co] = g[co]*inv_norm[co] for each tensor (same maths as
+ *                          tgan_weightnorm_fwd, W is not materialised: tgan_pack_weight_multi folds `scale`)
+ *   weightnorm_bwd_multi : dg[co] += <dW,V>*inv ; dV += g*inv*(dW - V*inv^2*<dW,V>)   (accumulating)
+ *   pack_weight_multi    : tgan_pack_weight_bf16 for each entry, times scale[n] (scale_on = 1) or scale[k] (2)
+ * max_co = largest Co in the table (sizes the grid). */
+typedef struct {
+  const float* V; const float* g; float* inv_norm; float* scale;
+  const float* dW; float* dV; float* dg;      /* backward only */
+  int A, Co, B, eps_mode;
+} tgan_wn_desc;
+typedef struct {
+  const float* src; void* dst; const float* scale; const int* taps;
+  int64_t st, sn, sk;
+  int T, Nr, K, Kpad, scale_on, pad_;
+} tgan_pack_desc;
+int tgan_weightnorm_fwd_multi(const tgan_wn_desc* descs_dev, int n, int max_co, float* ws, void* stream);
+int tgan_weightnorm_bwd_multi(const tgan_wn_desc* descs_dev, int n, int max_co, float* ws, void* stream);
+int64_t tgan_weightnorm_bwd_multi_ws_floats(int n, int max_co);   /* size of ws (fwd and bwd) */
+int tgan_pack_weight_multi(const tgan_pack_desc* descs_dev, int n, void* stream);
+int tgan_sizeof_wn_desc(void);
+int tgan_sizeof_pack_desc(void);
+
 /* ---------------------------------------------------------------- weight normalisation ------------
  * V viewed as [A, Co, B]; per output channel co: nrm = sqrt(sum_{a,b} V^2);
  *   W = V * g[co] / nrm          (eps_mode 0: no epsilon, nn.py:554)

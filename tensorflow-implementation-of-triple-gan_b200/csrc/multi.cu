@@ -1,0 +1,186 @@
+// multi.cu -- multi-tensor weight preparation: ONE launch serves every layer of a network.
+//   * weight-norm forward  (inv_norm, scale = g * inv_norm per output channel)  nn.py:502,554; modle_base.py:66,101,148
+//   * weight-norm backward (dg, dV from the accumulated dW)                     SURVEY.md Appendix B
+//   * bf16 K-major operand packing for the tcgen05 path, weight-norm scale folded in
+// The per-layer descriptors live in a device table built once by the host (parameter pointers are views into the flat
+// per-network buffers, so they never change); blockIdx.y selects the tensor.  The step launches these three kernels
+// once per network and optimiser version instead of 3-5 small kernels per layer.
+#include "common.cuh"
+
+namespace tgan {
+
+__device__ __forceinline__ int64_t wn_idx(int a, int co, int b, int Co, int B) { return ((int64_t)a * Co + co) * B + b; }
+
+// 256 threads = 32 channels x 8 row lanes; deterministic shared-memory fold over the lanes
+__device__ __forceinline__ float fold8(float (*sm)[33], float v, int tx, int ty) {
+  sm[ty][tx] = v;
+  __syncthreads();
+  float s = 0.f;
+  if (ty == 0) {
+#pragma unroll
+    for (int y = 0; y < 8; ++y) s += sm[y][tx];
+    sm[0][tx] = s;
+  }
+  __syncthreads();
+  s = sm[0][tx];
+  __syncthreads();
+  return s;
+}
+
+constexpr int WN_SPLITS = 16;      // row ranges per tensor (CTAs along blockIdx.z)
+
+__global__ void __launch_bounds__(256) wn_fwd_part_kernel(const tgan_wn_desc* __restrict__ descs, float* __restrict__ part,
+                                                          int max_co) {
+  const tgan_wn_desc d = descs[blockIdx.y];
+  const int c0 = blockIdx.x * 32;
+  if (c0 >= d.Co) return;
+  __shared__ float sm[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, co = c0 + tx;
+  const int AB = d.A * d.B, per = (AB + WN_SPLITS - 1) / WN_SPLITS;
+  const int e0 = blockIdx.z * per, e1 = min(AB, e0 + per);
+  float s = 0.f;
+  if (co < d.Co)
+    for (int e = e0 + ty; e < e1; e += 8) {
+      const float v = d.V[wn_idx(e / d.B, co, e % d.B, d.Co, d.B)];
+      s += v * v;
+    }
+  s = fold8(sm, s, tx, ty);
+  if (ty == 0 && co < d.Co) part[((int64_t)blockIdx.y * WN_SPLITS + blockIdx.z) * max_co + co] = s;
+}
+__global__ void wn_fwd_final_kernel(const tgan_wn_desc* __restrict__ descs, const float* __restrict__ part, int max_co) {
+  const tgan_wn_desc d = descs[blockIdx.y];
+  const int co = blockIdx.x * blockDim.x + threadIdx.x;
+  if (co >= d.Co) return;
+  float s = 0.f;
+#pragma unroll
+  for (int z = 0; z < WN_SPLITS; ++z) s += part[((int64_t)blockIdx.y * WN_SPLITS + z) * max_co + co];
+  const float inv = d.eps_mode ? rsqrtf(fmaxf(s, 1e-12f)) : 1.0f / sqrtf(s);
+  d.inv_norm[co] = inv;
+  d.scale[co] = d.g[co] * inv;
+}
+
+// dg[co] += <dW,V>*inv ; dV += g*inv*(dW - V*inv^2*<dW,V>).  Two kernels so that the rows of a tensor are spread over
+// WN_SPLITS CTAs: (1) partial dots per row range, (2) fold the partials in a fixed order and apply over the same range.
+__global__ void __launch_bounds__(256) wn_bwd_dot_kernel(const tgan_wn_desc* __restrict__ descs, float* __restrict__ part,
+                                                         int max_co) {
+  const tgan_wn_desc d = descs[blockIdx.y];
+  const int c0 = blockIdx.x * 32;
+  if (c0 >= d.Co) return;
+  __shared__ float sm[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, co = c0 + tx;
+  const int AB = d.A * d.B, per = (AB + WN_SPLITS - 1) / WN_SPLITS;
+  const int e0 = blockIdx.z * per, e1 = min(AB, e0 + per);
+  float s = 0.f;
+  if (co < d.Co)
+    for (int e = e0 + ty; e < e1; e += 8) {
+      const int64_t i = wn_idx(e / d.B, co, e % d.B, d.Co, d.B);
+      s += d.dW[i] * d.V[i];
+    }
+  s = fold8(sm, s, tx, ty);
+  if (ty == 0 && co < d.Co) part[((int64_t)blockIdx.y * WN_SPLITS + blockIdx.z) * max_co + co] = s;
+}
+
+__global__ void __launch_bounds__(256) wn_bwd_apply_kernel(const tgan_wn_desc* __restrict__ descs,
+                                                           const float* __restrict__ part, int max_co) {
+  const tgan_wn_desc d = descs[blockIdx.y];
+  const int c0 = blockIdx.x * 32;
+  if (c0 >= d.Co) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, co = c0 + tx;
+  if (co >= d.Co) return;
+  float dot = 0.f;
+#pragma unroll
+  for (int z = 0; z < WN_SPLITS; ++z) dot += part[((int64_t)blockIdx.y * WN_SPLITS + z) * max_co + co];
+  const float inv = d.inv_norm[co], gi = d.g[co] * inv, k = inv * inv * dot;
+  if (ty == 0 && blockIdx.z == 0) d.dg[co] += dot * inv;
+  const int AB = d.A * d.B, per = (AB + WN_SPLITS - 1) / WN_SPLITS;
+  const int e0 = blockIdx.z * per, e1 = min(AB, e0 + per);
+  for (int e = e0 + ty; e < e1; e += 8) {
+    const int64_t i = wn_idx(e / d.B, co, e % d.B, d.Co, d.B);
+    d.dV[i] += gi * (d.dW[i] - d.V[i] * k);
+  }
+}
+
+// dst[t][n][k] (bf16, k < Kpad) = k < K ? src[taps[t]*st + n*sn + k*sk] * scale : 0, in 32x32 (n, k) tiles.  One of the
+// source strides is 1 in every layout the step uses; when it is the n stride the tile is transposed through shared
+// memory so that both the fp32 reads and the bf16 writes are coalesced.
+__global__ void __launch_bounds__(256) pack_multi_kernel(const tgan_pack_desc* __restrict__ descs) {
+  const tgan_pack_desc d = descs[blockIdx.y];
+  __shared__ float sm[32][33];
+  const int nbk = (d.Kpad + 31) / 32, nbn = (d.Nr + 31) / 32;
+  const int tiles = d.T * nbn * nbk;
+  bf16* dst = reinterpret_cast<bf16*>(d.dst);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const bool transpose = d.sk != 1 && d.sn == 1;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int kb = tile % nbk, nb = (tile / nbk) % nbn, t = tile / (nbk * nbn);
+    const int64_t base = (int64_t)(d.taps ? d.taps[t] : t) * d.st;
+    if (transpose) {
+      const int n = nb * 32 + tx;
+#pragma unroll
+      for (int j = ty; j < 32; j += 8) {
+        const int k = kb * 32 + j;
+        float v = 0.f;
+        if (k < d.K && n < d.Nr) {
+          v = d.src[base + n + k * d.sk];
+          if (d.scale_on == 1) v *= d.scale[n];
+          else if (d.scale_on == 2) v *= d.scale[k];
+        }
+        sm[j][tx] = v;
+      }
+      __syncthreads();
+      const int k = kb * 32 + tx;
+#pragma unroll
+      for (int j = ty; j < 32; j += 8) {
+        const int nn = nb * 32 + j;
+        if (nn < d.Nr && k < d.Kpad) dst[((int64_t)t * d.Nr + nn) * d.Kpad + k] = __float2bfloat16_rn(sm[tx][j]);
+      }
+      __syncthreads();
+    } else {
+      const int k = kb * 32 + tx;
+#pragma unroll
+      for (int j = ty; j < 32; j += 8) {
+        const int n = nb * 32 + j;
+        if (n >= d.Nr || k >= d.Kpad) continue;
+        float v = 0.f;
+        if (k < d.K) {
+          v = d.src[base + n * d.sn + k * d.sk];
+          if (d.scale_on == 1) v *= d.scale[n];
+          else if (d.scale_on == 2) v *= d.scale[k];
+        }
+        dst[((int64_t)t * d.Nr + n) * d.Kpad + k] = __float2bfloat16_rn(v);
+      }
+    }
+  }
+}
+
+}  // namespace tgan
+
+using namespace tgan;
+
+extern "C" int tgan_sizeof_wn_desc(void) { return (int)sizeof(tgan_wn_desc); }
+extern "C" int tgan_sizeof_pack_desc(void) { return (int)sizeof(tgan_pack_desc); }
+
+extern "C" int tgan_weightnorm_fwd_multi(const tgan_wn_desc* descs_dev, int n, int max_co, float* ws, void* stream) {
+  TGAN_CHECK_ARG(descs_dev && ws && n > 0 && max_co > 0, "weightnorm_fwd_multi: bad args");
+  wn_fwd_part_kernel<<<dim3(ceil_div(max_co, 32), n, WN_SPLITS), 256, 0, (cudaStream_t)stream>>>(descs_dev, ws, max_co);
+  TGAN_LAUNCHED();
+  wn_fwd_final_kernel<<<dim3(ceil_div(max_co, 128), n), 128, 0, (cudaStream_t)stream>>>(descs_dev, ws, max_co);
+  TGAN_LAUNCHED();
+  return 0;
+}
+extern "C" int64_t tgan_weightnorm_bwd_multi_ws_floats(int n, int max_co) { return (int64_t)n * WN_SPLITS * max_co; }
+extern "C" int tgan_weightnorm_bwd_multi(const tgan_wn_desc* descs_dev, int n, int max_co, float* ws, void* stream) {
+  TGAN_CHECK_ARG(descs_dev && ws && n > 0 && max_co > 0, "weightnorm_bwd_multi: bad args");
+  dim3 grid(ceil_div(max_co, 32), n, WN_SPLITS);
+  wn_bwd_dot_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(descs_dev, ws, max_co);
+  TGAN_LAUNCHED();
+  wn_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(descs_dev, ws, max_co);
+  TGAN_LAUNCHED();
+  return 0;
+}
+extern "C" int tgan_pack_weight_multi(const tgan_pack_desc* descs_dev, int n, void* stream) {
+  TGAN_CHECK_ARG(descs_dev && n > 0, "pack_weight_multi: bad args");
+  pack_multi_kernel<<<dim3(148 * 4, n), 256, 0, (cudaStream_t)stream>>>(descs_dev);
+  TGAN_LAUNCHED();
+  return 0;
+}

@@ -64,6 +64,19 @@ class TganWgradArgs(ctypes.Structure):
                 ('beta', ctypes.c_float), ('ws', ctypes.c_void_p), ('ws_bytes', ctypes.c_int64)]
 
 
+class TganWnDesc(ctypes.Structure):
+    _fields_ = [('V', ctypes.c_void_p), ('g', ctypes.c_void_p), ('inv_norm', ctypes.c_void_p), ('scale', ctypes.c_void_p),
+                ('dW', ctypes.c_void_p), ('dV', ctypes.c_void_p), ('dg', ctypes.c_void_p),
+                ('A', ctypes.c_int), ('Co', ctypes.c_int), ('B', ctypes.c_int), ('eps_mode', ctypes.c_int)]
+
+
+class TganPackDesc(ctypes.Structure):
+    _fields_ = [('src', ctypes.c_void_p), ('dst', ctypes.c_void_p), ('scale', ctypes.c_void_p), ('taps', ctypes.c_void_p),
+                ('st', ctypes.c_int64), ('sn', ctypes.c_int64), ('sk', ctypes.c_int64),
+                ('T', ctypes.c_int), ('Nr', ctypes.c_int), ('K', ctypes.c_int), ('Kpad', ctypes.c_int),
+                ('scale_on', ctypes.c_int), ('pad_', ctypes.c_int)]
+
+
 _lib = None
 
 
@@ -81,6 +94,10 @@ def load():
         fn = getattr(lib, name)      # AttributeError here == header/library mismatch: fail loudly
         fn.restype = restype
         fn.argtypes = argtypes
+    for cls, fn in ((TganIgemmArgs, lib.tgan_sizeof_igemm_args), (TganWgradArgs, lib.tgan_sizeof_wgrad_args),
+                    (TganWnDesc, lib.tgan_sizeof_wn_desc), (TganPackDesc, lib.tgan_sizeof_pack_desc)):
+        if ctypes.sizeof(cls) != fn():
+            raise RuntimeError('libtgan: struct layout mismatch for %s (%d vs %d)' % (cls.__name__, ctypes.sizeof(cls), fn()))
     _lib = lib
     return lib
 

@@ -210,9 +210,13 @@ class WNWeight:
         return c
 
     def value(self):
+        """fp32 effective weight (CUDA-core GEMM paths; the tensor-core path folds the scale while packing)"""
         return self._c()['W']
 
     def grad_target(self):
+        if ctx.math == 'bf16':      # one zero-fill / one weight-norm backward launch for the whole network (prep.py)
+            from .prep import WNGroup
+            return WNGroup.of(self.V.group).grad_target(self, ctx.tape)
         c, tape = self._c(), ctx.tape
         if c.get('tape') is not tape:
             c['tape'] = tape

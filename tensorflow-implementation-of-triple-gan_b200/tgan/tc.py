@@ -61,16 +61,10 @@ def _taps_tensor(taps):
 
 
 def _pack(w, key, T, Nrows, K, st, sn, sk, taps=None):
-    """Packed bf16 K-major weights [T][Nrows][Kpad], cached per optimiser version."""
-    c = _wcache(w)
-    if key not in c:
-        Kpad = (K + 7) // 8 * 8
-        dst = _new((T, Nrows, Kpad), torch.bfloat16)
-        tp = None if taps is None else _taps_tensor(taps).data_ptr()
-        _lib.call('tgan_pack_weight_bf16', w.value().data_ptr(), dst.data_ptr(), T, Nrows, K, Kpad, st, sn, sk, tp,
-                  _st())
-        c[key] = (dst, Kpad)
-    return c[key]
+    """Packed bf16 K-major weights [T][Nrows][Kpad] for the current optimiser version.  All operands of a network are
+    (re)packed by one multi-tensor launch when its version changes (prep.PackGroup)."""
+    from .prep import PackGroup
+    return PackGroup.of(w.key.group).get(w, key, T, Nrows, K, st, sn, sk, None if taps is None else _taps_tensor(taps))
 
 
 def _igemm(x, N, H, W, C, ldx, wp, Kpad, taps, Nout, gh, gw, out, OH, OW, ldo, s=1, os_=1, oo=(0, 0), vh=0, vw=0,
