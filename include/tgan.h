@@ -55,6 +55,11 @@ int tgan_sgemm(int transA, int transB, int M, int N, int K, float alpha, const f
  * pixel stride ldx; col is fp32 [N*Ho*Wo, kh*kw*C].  TF SAME/VALID geometry is the caller's pt/pl. */
 int tgan_im2col(const void* x, int xdt, int N, int H, int W, int C, int ldx, int kh, int kw, int sh,
                 int sw, int pt, int pl, int Ho, int Wo, float* col, void* stream);
+/* bf16 im2col for the tensor-core path of convolutions with few input channels (conv1_1: 3 channels, D's first
+ * conv: 13): col is bf16 [N*Ho*Wo, ldc], ldc % 8 == 0, columns >= kh*kw*C are zero.  The convolution then runs as one
+ * plain tcgen05 GEMM with K = kh*kw*C instead of kh*kw narrow taps. */
+int tgan_im2col_bf16(const void* x, int xdt, int N, int H, int W, int C, int ldx, int kh, int kw, int sh, int sw, int pt,
+                     int pl, int Ho, int Wo, void* col, int ldc, void* stream);
 /* adjoint of tgan_im2col (gather form, deterministic): x[n,h,w,c] = sum of the col entries that read it.
  * Writes dtype `xdt`; only channels [0,Cx) of the C channels in col are produced (label-concat slice). */
 int tgan_col2im(const float* col, int N, int H, int W, int C, int kh, int kw, int sh, int sw, int pt,
@@ -108,6 +113,8 @@ typedef struct {
                           the operand roles are exchanged); dw = beta*dw + sum */
   float beta;
   float* ws; int64_t ws_bytes;
+  int cin_store;       /* T == 1 only: store the first cin_store rows of dw (0 = all Cin); the x operand may carry zero
+                          padding columns that dw has no room for */
 } tgan_wgrad_args;
 int tgan_wgrad_bf16(const tgan_wgrad_args* a, void* stream);
 int64_t tgan_wgrad_workspace_bytes(const tgan_wgrad_args* a);

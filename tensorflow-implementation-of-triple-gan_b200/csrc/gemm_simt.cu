@@ -97,6 +97,44 @@ __global__ void im2col_kernel(const T* __restrict__ x, int N, int H, int W, int 
   col[i] = v;
 }
 
+// bf16 variant feeding the tensor-core GEMM of small-Cin convolutions: col[row, k] for k = (r*kw + s)*C + c < K, zero for
+// K <= k < ldc (row stride padded to a multiple of 8 elements for TMA)
+// 128 output pixels per CTA: thread = pixel gathers its kh*kw*C window into a shared-memory row (odd word pitch: no bank
+// conflicts), then the CTA streams the [128, ldc] tile to global memory with 16-byte coalesced stores.
+template <typename T>
+__global__ void __launch_bounds__(128) im2col_bf16_kernel(const T* __restrict__ x, int N, int H, int W, int C, int ldx,
+                                                          int kh, int kw, int sh, int sw, int pt, int pl, int Ho, int Wo,
+                                                          bf16* __restrict__ col, int ldc, int64_t rows) {
+  extern __shared__ uint32_t im2col_sm[];
+  const int pitch = ldc / 2 + 1;                       // 32-bit words per row, odd (ldc % 8 == 0)
+  bf16* srow = reinterpret_cast<bf16*>(im2col_sm + (size_t)threadIdx.x * pitch);
+  const int64_t row0 = (int64_t)blockIdx.x * 128, row = row0 + threadIdx.x;
+  const int K = kh * kw * C;
+  if (row < rows) {
+    const int wo = (int)(row % Wo), ho = (int)((row / Wo) % Ho), n = (int)(row / ((int64_t)Wo * Ho));
+    int k = 0;
+    for (int r = 0; r < kh; ++r) {
+      const int hi = ho * sh + r - pt;
+      for (int s2 = 0; s2 < kw; ++s2) {
+        const int wi = wo * sw + s2 - pl;
+        const bool in = hi >= 0 && hi < H && wi >= 0 && wi < W;
+        const T* px = x + ((int64_t)(n * H + hi) * W + wi) * ldx;
+        for (int c = 0; c < C; ++c, ++k) srow[k] = __float2bfloat16_rn(in ? ldf<T>(px, c) : 0.f);
+      }
+    }
+    for (; k < ldc; ++k) srow[k] = __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+  const int cpr = ldc / 8;                             // 16-byte chunks per row
+  const int64_t nrows = rows - row0 < 128 ? rows - row0 : 128;
+  for (int j = threadIdx.x; j < (int)nrows * cpr; j += 128) {
+    const int rl = j / cpr, kk = (j - rl * cpr) * 4;   // word offset inside the row
+    const uint32_t* sp = im2col_sm + (size_t)rl * pitch + kk;
+    uint4 v = make_uint4(sp[0], sp[1], sp[2], sp[3]);
+    *reinterpret_cast<uint4*>(col + (row0 + rl) * ldc + kk * 2) = v;
+  }
+}
+
 template <typename T>
 __global__ void col2im_kernel(const float* __restrict__ col, int N, int H, int W, int C, int kh, int kw, int sh,
                               int sw, int pt, int pl, int Ho, int Wo, T* __restrict__ x, int Cx, int ldx,
@@ -163,6 +201,25 @@ extern "C" int tgan_im2col(const void* x, int xdt, int N, int H, int W, int C, i
   TGAN_CHECK_ARG(total > 0, "im2col: empty");
   TGAN_DISPATCH_1(xdt, T, (im2col_kernel<T><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
                               (const T*)x, N, H, W, C, ldx, kh, kw, sh, sw, pt, pl, Ho, Wo, col, total)));
+  TGAN_LAUNCHED();
+  return 0;
+}
+
+extern "C" int tgan_im2col_bf16(const void* x, int xdt, int N, int H, int W, int C, int ldx, int kh, int kw, int sh,
+                                int sw, int pt, int pl, int Ho, int Wo, void* col, int ldc, void* stream) {
+  TGAN_CHECK_ARG(x && col && ldc >= kh * kw * C && ldc % 8 == 0, "im2col_bf16: bad args");
+  const int64_t rows = (int64_t)N * Ho * Wo;
+  TGAN_CHECK_ARG(rows > 0 && ldc <= 512 && ((uintptr_t)col & 15) == 0, "im2col_bf16: empty / ldc > 512 / unaligned col");
+  const size_t smem = (size_t)128 * (ldc / 2 + 1) * 4;
+  TGAN_DISPATCH_1(xdt, T, {
+    static bool attr = false;
+    if (!attr && smem > 48 * 1024) {
+      cudaFuncSetAttribute(im2col_bf16_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024);
+      attr = true;
+    }
+    im2col_bf16_kernel<T><<<ceil_div(rows, 128), 128, smem, (cudaStream_t)stream>>>(
+        (const T*)x, N, H, W, C, ldx, kh, kw, sh, sw, pt, pl, Ho, Wo, (bf16*)col, ldc, rows);
+  });
   TGAN_LAUNCHED();
   return 0;
 }

@@ -508,9 +508,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ C
 }
 
 // dw[i] = beta*dw[i] + sum_splits ws[s][i]  (i over [T][Cin][Cout], same layout in and out -> fully coalesced)
-__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int64_t tot, float* __restrict__ dw,
-                                    float beta) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int64_t tot, int64_t tot_store,
+                                    float* __restrict__ dw, float beta) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot_store; i += (int64_t)gridDim.x * blockDim.x) {
     float s = 0.f;
     for (int z = 0; z < splits; ++z) s += ws[z * tot + i];
     dw[i] = (beta != 0.f ? beta * dw[i] : 0.f) + s;
@@ -710,9 +710,11 @@ extern "C" int tgan_wgrad_bf16(const tgan_wgrad_args* a, void* stream) {
   wgrad_kernel<<<grid, IG_THREADS, smem_bytes, (cudaStream_t)stream>>>(tmDz, tmX, p);
   TGAN_LAUNCHED();
   const int64_t tot = (int64_t)a->T * a->Cout * a->Cin;
-  int rg = ceil_div(tot, 256);
+  TGAN_CHECK_ARG(a->cin_store == 0 || (a->T == 1 && a->cin_store <= a->Cin), "wgrad: cin_store needs T == 1");
+  const int64_t tot_store = a->cin_store > 0 ? (int64_t)a->cin_store * a->Cout : tot;
+  int rg = ceil_div(tot_store, 256);
   if (rg > 148 * 8) rg = 148 * 8;
-  wgrad_reduce_kernel<<<rg, 256, 0, (cudaStream_t)stream>>>(a->ws, p.splits, tot, a->dw, a->beta);
+  wgrad_reduce_kernel<<<rg, 256, 0, (cudaStream_t)stream>>>(a->ws, p.splits, tot, tot_store, a->dw, a->beta);
   TGAN_LAUNCHED();
   return 0;
 }

@@ -61,7 +61,8 @@ class TganWgradArgs(ctypes.Structure):
                 ('W', ctypes.c_int), ('Cin', ctypes.c_int), ('ldx', ctypes.c_int), ('sy', ctypes.c_int), ('sx', ctypes.c_int),
                 ('T', ctypes.c_int),
                 ('dy', ctypes.c_int * 25), ('dx', ctypes.c_int * 25), ('dw', ctypes.c_void_p),
-                ('beta', ctypes.c_float), ('ws', ctypes.c_void_p), ('ws_bytes', ctypes.c_int64)]
+                ('beta', ctypes.c_float), ('ws', ctypes.c_void_p), ('ws_bytes', ctypes.c_int64),
+                ('cin_store', ctypes.c_int)]
 
 
 class TganWnDesc(ctypes.Structure):

@@ -91,14 +91,14 @@ def _igemm(x, N, H, W, C, ldx, wp, Kpad, taps, Nout, gh, gw, out, OH, OW, ldo, s
     _lib.call('tgan_igemm_bf16', ctypes.byref(a), _st())
 
 
-def _wgrad(dz, N, gh, gw, Cout, lddz, x, H, W, Cin, ldx, taps, s, dw):
+def _wgrad(dz, N, gh, gw, Cout, lddz, x, H, W, Cin, ldx, taps, s, dw, cin_store=0):
     a = _lib.TganWgradArgs()
     a.dz, a.N, a.gh, a.gw, a.Cout, a.lddz = dz.data_ptr(), N, gh, gw, Cout, lddz
     a.x, a.H, a.W, a.Cin, a.ldx, a.sy, a.sx = x.data_ptr(), H, W, Cin, ldx, s, s
     a.T = len(taps)
     for i, (dy, dx) in enumerate(taps):
         a.dy[i], a.dx[i] = dy, dx
-    a.dw, a.beta = dw.data_ptr(), 1.0
+    a.dw, a.beta, a.cin_store = dw.data_ptr(), 1.0, cin_store
     ws = ctx.ws()
     a.ws, a.ws_bytes = ws.data_ptr(), ws.numel() * 4
     _lib.call('tgan_wgrad_bf16', ctypes.byref(a), _st())
@@ -122,10 +122,40 @@ def _flat(g):
     return g
 
 
+def _small_cin(g):
+    """few input channels (conv1_1: 3, D's first conv: 13): per-tap TMA boxes would move 6-26 useful bytes per 128-byte
+    shared-memory row, so the taps are gathered once into a bf16 im2col matrix and the conv runs as one plain GEMM"""
+    return g['kh'] * g['kw'] > 1 and g['C'] <= 16
+
+
+def _im2col(x, g):
+    K = g['kh'] * g['kw'] * g['C']
+    Kc = (K + 7) // 8 * 8
+    rows = g['N'] * g['Ho'] * g['Wo']
+    col = _new((rows, Kc), torch.bfloat16)
+    xd = x.data
+    _lib.call('tgan_im2col_bf16', xd.data_ptr(), dt_code(xd), g['N'], g['H'], g['W'], g['C'], x.ld, g['kh'], g['kw'],
+              g['s'], g['s'], g['pt'], g['pl'], g['Ho'], g['Wo'], col.data_ptr(), Kc, _st())
+    return col, K, Kc
+
+
 def conv_fwd(x, w, g, colsum=None, segs=None, bias=None, act=0, ldo=None):
     """-> bf16 [rows, ldo] with act(conv + bias) in channels [0, Cout) (ldo > Cout: the rest is left untouched)"""
     gf = _flat(g)
     C, Cout, kh, kw = g['C'], g['Cout'], g['kh'], g['kw']
+    if _small_cin(g):
+        col, K, Kc = _im2col(x, g)
+        g['_col'] = (col, K, Kc)
+        rows = col.shape[0]
+        wp, Kpad = _pack(w, 'fprop_col', 1, Cout, K, 0, 1, Cout)      # HWIO flattened: k = (tap, ci) has stride Cout
+        assert Kpad == Kc
+        ldo = ldo or Cout
+        z = _new((rows, ldo), torch.bfloat16)
+        if segs:
+            segs = [n * (rows // sum(segs)) for n in segs]
+        _igemm(col, 1, 1, rows, K, Kc, wp, Kpad, [(0, 0)], Cout, 1, rows, z, 1, rows, ldo, colsum=colsum, segs=segs,
+               bias=bias, act=act)
+        return z
     xd, ld = _bf16_padded(x.data, x.rows, C, x.ld)
     g['_x'] = (xd, ld)
     wp, Kpad = _pack(w, 'fprop', kh * kw, Cout, C, C * Cout, 1, Cout)
@@ -154,7 +184,11 @@ def conv_bwd(x, w, g, dz):
     C, Cout, kh, kw, s, pt, pl = g['C'], g['Cout'], g['kh'], g['kw'], g['s'], g['pt'], g['pl']
     rows = g['N'] * g['Ho'] * g['Wo']
     dzb, _ = _bf16_padded(dz, rows, Cout, Cout)
-    if w.requires_grad:
+    if w.requires_grad and _small_cin(g):
+        col, K, Kc = g.get('_col') or _im2col(x, g)
+        # dW[(tap, ci), co] = col^T dz: a plain GEMM whose [Kc][Cout] result starts with the K rows of the HWIO gradient
+        _wgrad(dzb, 1, 1, rows, Cout, Cout, col, 1, rows, Kc, Kc, [(0, 0)], 1, w.grad_target(), cin_store=K)
+    elif w.requires_grad:
         xd, ld = g.get('_x') or _bf16_padded(x.data, x.rows, C, x.ld)
         taps = [(r - pt, c - pl) for r in range(kh) for c in range(kw)]
         # the kernel writes [t][ci][co] == HWIO
@@ -188,6 +222,7 @@ def conv_bwd(x, w, g, dz):
                    g['H'], g['W'], Cg, os_=2, classes=[(len(c[2]), c[0], c[1]) for c in cl])
         add_grad(tgt, dx if dx.dtype == tgt.data.dtype else dx.to(tgt.data.dtype))
     g.pop('_x', None)
+    g.pop('_col', None)
 
 
 # ------------------------------------------------------------------------------------------------
