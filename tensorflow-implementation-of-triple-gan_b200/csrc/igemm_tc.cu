@@ -60,7 +60,8 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* d
 // ------------------------------------------------------------------------------------------------
 // implicit-GEMM kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int IG_THREADS = 192;          // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int IG_THREADS = 320;          // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue (see below)
+constexpr int WG_THREADS = 192;          // wgrad: warp 0 producer, warp 1 issuer, warps 2-5 epilogue
 constexpr int W_STAGE_BYTES = 128 * 128; // 128 output channels x 64 bf16 (UMMA A operand, M = 128)
 constexpr int P_TILE_BYTES = 128 * 128;  // 128 pixels x 64 bf16
 constexpr int IG_NPIX = 256;             // pixels per CTA tile = UMMA N (two 128-pixel TMA boxes)
@@ -178,7 +179,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < IG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
     fence_barrier_init();
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
@@ -213,6 +214,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       for (int t = tap0; t < tap1; ++t) {
         const int ddx = p.dx[t], ddy = p.dy[t];
         for (int kc = 0; kc < p.kchunks; ++kc) {
+          if (p.dbg & 16) continue;
           mbar_wait(&empty[stage], phase ^ 1);
           if (elect_one()) {
             uint8_t* s = smem + (size_t)stage * IG_STAGE_BYTES;
@@ -241,7 +243,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * IG_NPIX);
       int kc = 0;
       for (int ks = 0; ks < ksteps; ++ks) {
-        mbar_wait(&full[stage], phase);
+        if (!(p.dbg & 16)) mbar_wait(&full[stage], phase);
         tc_fence_after();
         const uint32_t a_lo = s_base + (uint32_t)stage * (IG_STAGE_BYTES >> 4);
         const uint32_t b_lo = a_lo + (W_STAGE_BYTES >> 4);
@@ -267,9 +269,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       if (++acc == 2) { acc = 0; accphase ^= 1; }
     }
   } else {
-    // ---- epilogue: thread = one output channel (TMEM lane), 32 consecutive pixels per tcgen05.ld ----
+    // ---- epilogue: thread = one output channel (TMEM lane), 32 consecutive pixels per tcgen05.ld.  EIGHT warps: a
+    // warp runs alone on its scheduler, so the ~4 dependent instructions per element (convert, shared-memory store,
+    // statistics) of a 128 x 256 tile cost ~6 us with four warps -- more than the tile's MMAs.  Warps w and w+4 share a
+    // TMEM lane quadrant and split every 128-pixel box into two 64-pixel halves.
     const int q = warp & 3;                    // TMEM lane quadrant this warp may access
-    const int ppi = p.th * p.tw;               // pixels per image inside a 128-pixel tile (power of two)
+    const int g = (warp - 2) >> 2;             // which 64 pixels of each 128-pixel box
+    const bool plain = p.alpha == 1.f && p.bias == nullptr;
     int acc = 0; uint32_t accphase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int cls = tile / tiles_per_cls, tin = tile - cls * tiles_per_cls;
@@ -281,85 +287,93 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       float csum[4] = {0.f, 0.f, 0.f, 0.f};
       mbar_wait(&tfull[acc], accphase);
       tc_fence_after();
-      for (int c0 = 0; c0 < IG_NPIX; c0 += 32) {
-        const int mt = 2 * pp + (c0 >> 7);
-        if (mt >= p.m_tiles) break;
+      for (int h = 0; h < 2; ++h) {
+        const int mt = 2 * pp + h;
+        if (mt >= p.m_tiles || (p.dbg & 8)) break;
         const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, ng = mt / tiles_per_img;
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * IG_NPIX + c0), r);
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha + bias;
-        // optional stages sit behind warp-uniform branches; every loop is fully unrolled so that v[] stays in registers
-        // (a single dynamically indexed access would move the whole array to local memory)
-        if (p.act == TGAN_ACT_LRELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
-        } else if (p.act == TGAN_ACT_RELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        } else if (p.act == TGAN_ACT_TANH) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
-        } else if (p.act == TGAN_ACT_SIGMOID) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
-        } else if (p.act == TGAN_ACT_SOFTPLUS) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = v[j] > 20.f ? v[j] : log1pf(expf(v[j]));
+        if (p.tstore) {           // the previous box's store must have finished reading the staging buffer
+          if (warp == 2 && lane == 0) bulk_wait_read0();
+          named_bar_sync(1, 256);
         }
-        const int pbase = c0 & 127;
-        if (p.tstore) {
-          // ---- staged path: [pixel][channel] rows in shared memory, one bulk-tensor store per 128-pixel half.  The
-          // store needs no geometry (TMA clips at the valid extents); 32 lanes write 32 consecutive channels = 64 B.
-          if (p.colsum) {
-            switch (p.ltw) {
-              case 2: ig_sum_chunk<4>(p, v, pbase, tx, ty, ng, csum); break;
-              case 3: ig_sum_chunk<8>(p, v, pbase, tx, ty, ng, csum); break;
-              case 4: ig_sum_chunk<16>(p, v, pbase, tx, ty, ng, csum); break;
-              default: ig_sum_chunk<32>(p, v, pbase, tx, ty, ng, csum); break;
-            }
-          }
-          if (pbase == 0) {       // the previous half's store must have finished reading the staging buffer
-            if (warp == 2 && lane == 0) bulk_wait_read0();
-            named_bar_sync(1, 128);
-          }
-          bf16* srow = reinterpret_cast<bf16*>(ostage) + (size_t)pbase * 128 + (q * 32 + lane);
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          const int pbase = g * 64 + cc * 32;
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * IG_NPIX + h * 128 + pbase), r);
+          tmem_ld_wait();
+          float v[32];
+          if (plain) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) srow[j * 128] = __float2bfloat16_rn(v[j]);
-          if (pbase == 96) {
-            fence_proxy_async();
-            named_bar_sync(1, 128);
-            if (warp == 2 && lane == 0 && !(p.dbg & 4)) {
-              tma_store_4d(tmO, ostage, ct * 128, tx * p.tw, ty * p.th, ng * p.nb);
-              bulk_commit();
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha + bias;
+          }
+          // optional stages sit behind warp-uniform branches; every loop is fully unrolled so that v[] stays in registers
+          // (a single dynamically indexed access would move the whole array to local memory)
+          if (p.act == TGAN_ACT_LRELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
+          } else if (p.act == TGAN_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (p.act == TGAN_ACT_TANH) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+          } else if (p.act == TGAN_ACT_SIGMOID) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
+          } else if (p.act == TGAN_ACT_SOFTPLUS) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] > 20.f ? v[j] : log1pf(expf(v[j]));
+          }
+          if (p.tstore) {
+            // ---- staged path: [pixel][channel] rows in shared memory, one bulk-tensor store per 128-pixel box.  The
+            // store needs no geometry (TMA clips at the valid extents); 32 lanes write 32 consecutive channels = 64 B.
+            if (p.colsum) {
+              switch (p.ltw) {
+                case 2: ig_sum_chunk<4>(p, v, pbase, tx, ty, ng, csum); break;
+                case 3: ig_sum_chunk<8>(p, v, pbase, tx, ty, ng, csum); break;
+                case 4: ig_sum_chunk<16>(p, v, pbase, tx, ty, ng, csum); break;
+                default: ig_sum_chunk<32>(p, v, pbase, tx, ty, ng, csum); break;
+              }
+            }
+            bf16* srow = reinterpret_cast<bf16*>(ostage) + (size_t)pbase * 128 + (q * 32 + lane);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) srow[j * 128] = __float2bfloat16_rn(v[j]);
+          } else if (!(p.dbg & 4)) {
+            if (p.odt == TGAN_BF16) {
+              bf16* o = reinterpret_cast<bf16*>(p.out);
+              switch (p.ltw) {
+                case 2: ig_store_chunk<4>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum, p.cooy[cls], p.coox[cls]); break;
+                case 3: ig_store_chunk<8>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum, p.cooy[cls], p.coox[cls]); break;
+                case 4: ig_store_chunk<16>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum, p.cooy[cls], p.coox[cls]); break;
+                default: ig_store_chunk<32>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum, p.cooy[cls], p.coox[cls]); break;
+              }
+            } else {
+              float* o = reinterpret_cast<float*>(p.out);
+              switch (p.ltw) {
+                case 2: ig_store_chunk<4>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum, p.cooy[cls], p.coox[cls]); break;
+                case 3: ig_store_chunk<8>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum, p.cooy[cls], p.coox[cls]); break;
+                case 4: ig_store_chunk<16>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum, p.cooy[cls], p.coox[cls]); break;
+                default: ig_store_chunk<32>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum, p.cooy[cls], p.coox[cls]); break;
+              }
             }
           }
-        } else if (!(p.dbg & 4)) {
-          if (p.odt == TGAN_BF16) {
-            bf16* o = reinterpret_cast<bf16*>(p.out);
-            switch (p.ltw) {
-              case 2: ig_store_chunk<4>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum, p.cooy[cls], p.coox[cls]); break;
-              case 3: ig_store_chunk<8>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum, p.cooy[cls], p.coox[cls]); break;
-              case 4: ig_store_chunk<16>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum, p.cooy[cls], p.coox[cls]); break;
-              default: ig_store_chunk<32>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum, p.cooy[cls], p.coox[cls]); break;
-            }
-          } else {
-            float* o = reinterpret_cast<float*>(p.out);
-            switch (p.ltw) {
-              case 2: ig_store_chunk<4>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum, p.cooy[cls], p.coox[cls]); break;
-              case 3: ig_store_chunk<8>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum, p.cooy[cls], p.coox[cls]); break;
-              case 4: ig_store_chunk<16>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum, p.cooy[cls], p.coox[cls]); break;
-              default: ig_store_chunk<32>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum, p.cooy[cls], p.coox[cls]); break;
-            }
+        }
+        if (p.tstore) {
+          fence_proxy_async();
+          named_bar_sync(1, 256);
+          if (warp == 2 && lane == 0 && !(p.dbg & 4)) {
+            tma_store_4d(tmO, ostage, ct * 128, tx * p.tw, ty * p.th, ng * p.nb);
+            bulk_commit();
           }
         }
       }
       if (p.colsum && cvalid) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-          if (g < p.nseg && csum[g] != 0.f) atomicAdd(&p.colsum[g * p.Nout + co], csum[g]);
+        for (int gg = 0; gg < 4; ++gg)
+          if (gg < p.nseg && csum[gg] != 0.f) atomicAdd(&p.colsum[gg * p.Nout + co], csum[gg]);
       }
       tc_fence_before();
       __syncwarp();
@@ -387,7 +401,7 @@ struct WgParams {
   int Cout, Cin;
 };
 
-__global__ void __launch_bounds__(IG_THREADS, 1)
+__global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorMap tmX,
              const __grid_constant__ WgParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -707,7 +721,7 @@ extern "C" int tgan_wgrad_bf16(const tgan_wgrad_args* a, void* stream) {
   const size_t stage_bytes = (size_t)(2 + p.tg * (p.BNc / 64)) * WG_BOX_BYTES;
   const size_t smem_bytes = 1024 + p.stages * stage_bytes + 256;
   const int grid = p.co_tiles * p.ci_tiles * p.tap_groups * p.splits;
-  wgrad_kernel<<<grid, IG_THREADS, smem_bytes, (cudaStream_t)stream>>>(tmDz, tmX, p);
+  wgrad_kernel<<<grid, WG_THREADS, smem_bytes, (cudaStream_t)stream>>>(tmDz, tmX, p);
   TGAN_LAUNCHED();
   const int64_t tot = (int64_t)a->T * a->Cout * a->Cin;
   TGAN_CHECK_ARG(a->cin_store == 0 || (a->T == 1 && a->cin_store <= a->Cin), "wgrad: cin_store needs T == 1");

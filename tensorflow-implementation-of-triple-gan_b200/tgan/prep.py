@@ -50,7 +50,7 @@ class WNGroup:
         return g[group]
 
     def entry(self, w):
-        e = self.entries.get(id(w.V))
+        e = self.entries.get(w.V)
         if e is None:
             n = w.V.size
             off = None
@@ -62,7 +62,7 @@ class WNGroup:
             e = dict(w=w, inv=torch.empty(w.Co, dtype=torch.float32, device=ctx.device),
                      scale=torch.empty(w.Co, dtype=torch.float32, device=ctx.device), dW=dW.view(w.V.shape),
                      flat=off is not None)
-            self.entries[id(w.V)] = e
+            self.entries[w.V] = e
             self.table = None
             if self.version == ctx.store.group_version(self.group):      # the group was prepared without this tensor
                 self._launch('tgan_weightnorm_fwd_multi', [e])
@@ -143,7 +143,7 @@ class PackGroup:
         from .ops import WNWeight
         ver = ctx.store.group_version(self.group)
         wn = isinstance(w, WNWeight)
-        k = (id(w.key), key)
+        k = (w.key, key)      # keyed by the Param object itself (ids are recycled)
         e = self.entries.get(k)
         if e is None:
             Kpad = (K + 7) // 8 * 8
