@@ -244,6 +244,15 @@ int tgan_dropout(const void* x, int xdt, void* y, int ydt, uint8_t* mask, int64_
 int tgan_maxpool2_fwd(const void* x, int dt, void* y, uint8_t* idx, int N, int H, int W, int C, void* stream);
 int tgan_maxpool2_bwd(const void* dy, int dt, const uint8_t* idx, void* dx, int N, int H, int W, int C,
                       void* stream);
+/* 2x2/s2 max pool fused with the inverted dropout that follows it (Good_GAN_cifar10.py:123-124, 142-143): bf16 NHWC,
+ * C % 8 == 0.  y = keep ? max * 1/(1-rate) : 0;  code[N,H/2,W/2,C] = winner (bits 0-1, first maximum) | keep << 2.
+ * mask != NULL: keep flags supplied (parity mode); else Philox(seed, stream_id, *counter), the same draws as tgan_dropout
+ * for that stream; rate == 0: pool only.  bwd: dx[winner] = keep ? dy/(1-rate) : 0, zeros elsewhere. */
+int tgan_maxpool2_dropout_fwd(const void* x, void* y, uint8_t* code, int N, int H, int W, int C, float rate,
+                              const uint8_t* mask, uint64_t seed, uint64_t stream_id, const uint64_t* counter,
+                              void* stream);
+int tgan_maxpool2_dropout_bwd(const void* dy, const uint8_t* code, void* dx, int N, int H, int W, int C, float rate,
+                              void* stream);
 /* global pooling over H*W: mode 0 = max (max_pooling2d(6,1) 'avg_pool_0', Good_GAN_cifar10.py:163),
  * mode 1 = mean (average_pooling2d(8,1) :94; reduce_mean([1,2]) Good_GAN.py:157,243,295). */
 int tgan_global_pool_fwd(const void* x, int xdt, void* y, int ydt, uint8_t* idx, int N, int HW, int C,

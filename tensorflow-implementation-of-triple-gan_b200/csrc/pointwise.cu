@@ -357,6 +357,85 @@ __global__ void maxpool2_bwd_kernel(const T* __restrict__ dy, const uint8_t* __r
   stf<T>(p, (int64_t)W * C + C, k == 3 ? d : 0.f);
 }
 
+// 2x2/s2 max pool fused with the inverted dropout that follows it in the classifier (Good_GAN_cifar10.py:123-124,
+// 142-143): bf16, C % 8 == 0, one thread = 8 channels of one output pixel (16-byte accesses).  code = winner index
+// (2 bits, first maximum wins like tf.nn.max_pool's gradient) | keep << 2.  The Philox stream is the one the
+// stand-alone dropout kernel draws for the same tag (element groups of 4).
+__global__ void maxpool2_dropout_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, uint8_t* __restrict__ code,
+                                            int H, int W, int C, int64_t nvec, float rate, float scale,
+                                            const uint8_t* __restrict__ mask, uint64_t seed, uint64_t stream_id,
+                                            const uint64_t* __restrict__ counter) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nvec) return;
+  const int cv = C / 8, Wo = W / 2, Ho = H / 2;
+  const int c = (int)(i % cv) * 8;
+  int64_t t = i / cv;
+  const int wo = (int)(t % Wo); t /= Wo;
+  const int ho = (int)(t % Ho);
+  const int64_t n = t / Ho;
+  const int64_t p0 = ((n * H + 2 * ho) * W + 2 * wo) * C + c;
+  float a[4][8];
+  ld8(x, p0, a[0]); ld8(x, p0 + C, a[1]); ld8(x, p0 + (int64_t)W * C, a[2]); ld8(x, p0 + (int64_t)W * C + C, a[3]);
+  uint8_t keep[8];
+  const int64_t e = i * 8;                      // first output element of this thread
+  if (rate <= 0.f) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) keep[j] = 1;
+  } else if (mask) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) keep[j] = mask[e + j];
+  } else {
+    const uint64_t ctr = counter ? *counter : 0;
+    Philox ph(seed);
+    const uint4 r0 = ph((uint64_t)(e / 4), stream_id + (ctr << 20)), r1 = ph((uint64_t)(e / 4 + 1), stream_id + (ctr << 20));
+    const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) keep[j] = u32_to_unit(rr[j]) >= rate;
+  }
+  float o[8];
+  uint8_t cd[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float m = a[0][j]; int k = 0;
+    if (a[1][j] > m) { m = a[1][j]; k = 1; }
+    if (a[2][j] > m) { m = a[2][j]; k = 2; }
+    if (a[3][j] > m) { m = a[3][j]; k = 3; }
+    o[j] = keep[j] ? m * scale : 0.f;
+    cd[j] = (uint8_t)(k | (keep[j] << 2));
+  }
+  st8(y, e, o);
+  uint2 cw;
+  cw.x = cd[0] | (cd[1] << 8) | (cd[2] << 16) | ((uint32_t)cd[3] << 24);
+  cw.y = cd[4] | (cd[5] << 8) | (cd[6] << 16) | ((uint32_t)cd[7] << 24);
+  *reinterpret_cast<uint2*>(code + e) = cw;
+}
+__global__ void maxpool2_dropout_bwd_kernel(const bf16* __restrict__ dy, const uint8_t* __restrict__ code,
+                                            bf16* __restrict__ dx, int H, int W, int C, int64_t nvec, float scale) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nvec) return;
+  const int cv = C / 8, Wo = W / 2, Ho = H / 2;
+  const int c = (int)(i % cv) * 8;
+  int64_t t = i / cv;
+  const int wo = (int)(t % Wo); t /= Wo;
+  const int ho = (int)(t % Ho);
+  const int64_t n = t / Ho;
+  const int64_t p0 = ((n * H + 2 * ho) * W + 2 * wo) * C + c;
+  const int64_t e = i * 8;
+  float d[8];
+  ld8(dy, e, d);
+  const uint2 cw = *reinterpret_cast<const uint2*>(code + e);
+  const uint32_t cws[2] = {cw.x, cw.y};
+  float o[4][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t cd = (cws[j >> 2] >> (8 * (j & 3))) & 0xff;
+    const float g = (cd & 4) ? d[j] * scale : 0.f;
+    const int k = cd & 3;
+    o[0][j] = k == 0 ? g : 0.f; o[1][j] = k == 1 ? g : 0.f; o[2][j] = k == 2 ? g : 0.f; o[3][j] = k == 3 ? g : 0.f;
+  }
+  st8(dx, p0, o[0]); st8(dx, p0 + C, o[1]); st8(dx, p0 + (int64_t)W * C, o[2]); st8(dx, p0 + (int64_t)W * C + C, o[3]);
+}
+
 template <typename TX, typename TY>
 __global__ void global_pool_fwd_kernel(const TX* __restrict__ x, TY* __restrict__ y, uint8_t* __restrict__ idx,
                                        int N, int HW, int C, int mode) {
@@ -684,6 +763,29 @@ extern "C" int tgan_maxpool2_bwd(const void* dy, int dt, const uint8_t* idx, voi
   int64_t total = (int64_t)N * (H / 2) * (W / 2) * C;
   TGAN_DISPATCH_1(dt, T, (maxpool2_bwd_kernel<T><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
                              (const T*)dy, idx, (T*)dx, N, H, W, C, total)));
+  TGAN_LAUNCHED();
+  return 0;
+}
+
+extern "C" int tgan_maxpool2_dropout_fwd(const void* x, void* y, uint8_t* code, int N, int H, int W, int C, float rate,
+                                         const uint8_t* mask, uint64_t seed, uint64_t stream_id,
+                                         const uint64_t* counter, void* stream) {
+  TGAN_CHECK_ARG(x && y && code && H % 2 == 0 && W % 2 == 0 && C % 8 == 0 && rate >= 0.f && rate < 1.f && aligned16(x) &&
+                     aligned16(y) && ((uintptr_t)code & 7) == 0,
+                 "maxpool2_dropout_fwd: bf16, even extents, C %% 8 == 0, aligned buffers");
+  const int64_t nvec = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
+  maxpool2_dropout_fwd_kernel<<<ceil_div(nvec, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, (bf16*)y, code, H, W, C, nvec, rate, 1.0f / (1.0f - rate), mask, seed, stream_id, counter);
+  TGAN_LAUNCHED();
+  return 0;
+}
+extern "C" int tgan_maxpool2_dropout_bwd(const void* dy, const uint8_t* code, void* dx, int N, int H, int W, int C,
+                                         float rate, void* stream) {
+  TGAN_CHECK_ARG(dy && dx && code && H % 2 == 0 && W % 2 == 0 && C % 8 == 0 && aligned16(dy) && aligned16(dx),
+                 "maxpool2_dropout_bwd: bad args");
+  const int64_t nvec = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
+  maxpool2_dropout_bwd_kernel<<<ceil_div(nvec, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)dy, code, (bf16*)dx, H, W, C, nvec, 1.0f / (1.0f - rate));
   TGAN_LAUNCHED();
   return 0;
 }

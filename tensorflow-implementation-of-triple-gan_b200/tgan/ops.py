@@ -267,6 +267,15 @@ def _deferred(v):
     return v._data is None and isinstance(v._lazy, Deferred)
 
 
+class PoolDeferred:
+    """a 2x2 max pool waiting to learn whether a dropout follows (the classifier's max_pool -> dropout pairs run as one
+    kernel forward and one backward)"""
+    __slots__ = ('run',)
+
+    def __init__(self, run):
+        self.run = run
+
+
 def _epilogue_bwd(out, b, act, alpha):
     """gradient through y = act(z + b) fused in a GEMM epilogue: returns dz (bf16 [rows, C]) and accumulates db"""
     dy = out.grad
@@ -391,7 +400,7 @@ def conv2d_transpose(x, w, kh, kw, stride=2):
         return Var(None, oshape, requires_grad=rg)
     from . import tc
     geom = dict(N=N, h=h, w=wd, Cin=Cin, Cout=Cout, kh=kh, kw=kw, s=stride, pt=pt, pl=pl, Ho=Ho, Wo=Wo)
-    use_tc = ctx.math == 'bf16' and tc.deconv_eligible(geom, x)
+    use_tc = ctx.math == 'bf16' and tc.deconv_eligible(geom, x) and not (tc._skinny(geom) and isinstance(w, WNWeight))
     rows, KK = N * h * wd, kh * kw * Cout
     if use_tc:
         tape = ctx.tape
@@ -494,6 +503,9 @@ def lazy_bias(z, b):
 
 
 def _materialize(v, out_ld=None):
+    if isinstance(v._lazy, PoolDeferred):
+        v._lazy.run(0.0, None)
+        return
     if isinstance(v._lazy, Deferred):
         d = v._lazy
         d.run(d.b, d.act, d.alpha, out_ld)
@@ -675,6 +687,9 @@ def dropout(x, rate, tag, training=True):
     rg = _on() and x.requires_grad
     if ctx.building:
         return Var(None, x.shape, requires_grad=rg)
+    if x._data is None and isinstance(x._lazy, PoolDeferred):
+        x._lazy.run(rate, tag)           # fused into the pending max pool
+        return x
     xd = x.data
     n = xd.numel()
     y = _new(x.shape)
@@ -707,6 +722,34 @@ def max_pool2(x):
     if ctx.building:
         return Var(None, oshape, requires_grad=rg)
     xd = x.data
+    if ctx.math == 'bf16' and xd.dtype == torch.bfloat16 and C % 8 == 0 and x.ld == C:
+        out = _prop(Var(None, oshape, requires_grad=rg), x)
+        tape = ctx.tape
+
+        def run(rate, tag):
+            y, code = _new(oshape, torch.bfloat16), _new(oshape, torch.uint8)
+            rng = ctx.rng
+            if rate > 0 and rng.injected:
+                mask = _rng_mask(tag, oshape, rate)
+                _lib.call('tgan_maxpool2_dropout_fwd', _p(xd), _p(y), _p(code), N, H, W, C, rate, _p(mask), 0, 0, None, _st())
+            elif rate > 0:
+                _lib.call('tgan_maxpool2_dropout_fwd', _p(xd), _p(y), _p(code), N, H, W, C, rate, None, rng.seed,
+                          rng.stream_id(str(tag)), _p(rng.counter()), _st())
+            else:
+                _lib.call('tgan_maxpool2_dropout_fwd', _p(xd), _p(y), _p(code), N, H, W, C, 0.0, None, 0, 0, None, _st())
+            out._data, out._lazy = y, None
+            if out.requires_grad and tape is not None:
+                def bwd():
+                    if out.grad is None:
+                        return
+                    dx = _new(x.shape, torch.bfloat16)
+                    _lib.call('tgan_maxpool2_dropout_bwd', _p(_cast(out.grad, torch.bfloat16)), _p(code), _p(dx), N, H, W,
+                              C, rate, _st())
+                    add_grad(x, dx)
+                tape.nodes.append(bwd)
+
+        out._lazy = PoolDeferred(run)
+        return out
     y, idx = _new(oshape, xd.dtype), _new(oshape, torch.uint8)
     _lib.call('tgan_maxpool2_fwd', _p(xd), dt_code(xd), _p(y), _p(idx), N, H, W, C, _st())
     out = _prop(Var(y, oshape, requires_grad=rg), x)

@@ -231,7 +231,14 @@ def conv_bwd(x, w, g, dz):
 
 
 def deconv_eligible(g, x):
-    return g['Cout'] >= 16 and g['Cout'] % 8 == 0 and g['s'] == 2 and g['kh'] * g['kw'] <= 25
+    return (_skinny(g) or (g['Cout'] >= 16 and g['Cout'] % 8 == 0)) and g['s'] == 2 and g['kh'] * g['kw'] <= 25
+
+
+def _skinny(g):
+    """the generator's last layer: 3 output channels (Good_GAN_cifar10.py:56).  Forward: the same parity-class launch
+    into an 8-channel bf16 staging buffer, then a slice/convert to the fp32 image.  Backward: K per tap would be
+    3 channels, so dy is gathered into a bf16 im2col matrix once and both gradients are plain GEMMs."""
+    return g['Cout'] <= 8 and g['kh'] * g['kw'] * g['Cout'] <= 512
 
 
 def _parity_classes(g):
@@ -249,7 +256,8 @@ def deconv_fwd(x, w, g, bias=None, act=0, ldo=None):
     Cin, Cout = g['Cin'], g['Cout']
     xd, ld = _bf16_padded(x.data, x.rows, Cin, x.ld)
     g['_x'] = (xd, ld)
-    ldo = ldo or Cout
+    skinny = _skinny(g)
+    ldo = 8 if skinny else (ldo or Cout)
     y = _new((g['N'], g['Ho'], g['Wo'], ldo), torch.bfloat16)
     cl = sorted(_parity_classes(g), key=lambda c: -len(c[2]))      # heaviest class first, all in ONE launch
     assert len(cl) == 4
@@ -258,11 +266,41 @@ def deconv_fwd(x, w, g, bias=None, act=0, ldo=None):
     wp, Kpad = _pack(w, 'dfwd', len(sel), Cout, Cin, Cout * Cin, Cin, 1, sel)
     _igemm(xd, g['N'], g['h'], g['w'], Cin, ld, wp, Kpad, taps, Cout, g['h'], g['w'], y, g['Ho'], g['Wo'], ldo,
            os_=2, bias=bias, act=act, classes=[(len(c[2]), c[0], c[1]) for c in cl])
+    if skinny:
+        rows = g['N'] * g['Ho'] * g['Wo']
+        yf = _new((g['N'], g['Ho'], g['Wo'], Cout), torch.float32)
+        _lib.call('tgan_copy_channels', y.data_ptr(), BF16, ldo, yf.data_ptr(), 0, Cout, rows, Cout, _st())
+        return yf
     return y
+
+
+def _deconv_bwd_skinny(x, w, g, dy):
+    from .core import add_grad
+    Cin, Cout, kh, kw, pt, pl = g['Cin'], g['Cout'], g['kh'], g['kw'], g['pt'], g['pl']
+    rows_out, rows_in = g['N'] * g['Ho'] * g['Wo'], g['N'] * g['h'] * g['w']
+    dyb, ldy = _bf16_padded(dy, rows_out, Cout, Cout)
+    K = kh * kw * Cout
+    Kc = (K + 7) // 8 * 8
+    col = _new((rows_in, Kc), torch.bfloat16)      # col[(n,i,j), (r,c,co)] = dy[n, 2i + r - pt, 2j + c - pl, co]
+    _lib.call('tgan_im2col_bf16', dyb.data_ptr(), BF16, g['N'], g['Ho'], g['Wo'], Cout, ldy, kh, kw, 2, 2, pt, pl,
+              g['h'], g['w'], col.data_ptr(), Kc, _st())
+    if w.requires_grad:
+        xd, ld = g.get('_x') or _bf16_padded(x.data, x.rows, Cin, x.ld)
+        # dW[(r,c,co), ci] = col^T x: M side = x channels, N side = the im2col columns -> [K][Cin] == [kh,kw,Cout,Cin]
+        _wgrad(xd, 1, 1, rows_in, Cin, ld, col, 1, rows_in, Kc, Kc, [(0, 0)], 1, w.grad_target(), cin_store=K)
+    tgt, Cg = _grad_target(x, Cin)
+    if tgt.requires_grad:
+        wp, Kpad = _pack(w, ('ddgrad_col', Cg), 1, Cg, K, 0, 1, Cin)     # [ci][(r,c,co)]: k has stride Cin
+        dx = _new(tuple(x.shape[:-1]) + (Cg,), torch.bfloat16)
+        _igemm(col, 1, 1, rows_in, K, Kc, wp, Kpad, [(0, 0)], Cg, 1, rows_in, dx, 1, rows_in, Cg)
+        add_grad(tgt, dx if dx.dtype == tgt.data.dtype else dx.to(tgt.data.dtype))
+    g.pop('_x', None)
 
 
 def deconv_bwd(x, w, g, dy):
     from .core import add_grad
+    if _skinny(g):
+        return _deconv_bwd_skinny(x, w, g, dy)
     Cin, Cout, kh, kw, pt, pl = g['Cin'], g['Cout'], g['kh'], g['kw'], g['pt'], g['pl']
     dyb, _ = _bf16_padded(dy, g['N'] * g['Ho'] * g['Wo'], Cout, Cout)
     taps = [(r - pt, c - pl) for r in range(kh) for c in range(kw)]
