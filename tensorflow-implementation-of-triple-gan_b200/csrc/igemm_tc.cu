@@ -74,7 +74,24 @@ constexpr int IG_OUT_STAGE_BYTES = 128 * 256;   // epilogue staging: 128 pixels 
 // retires every ~82 ns for any N <= 256, so only N = 256 instructions reach the tensor-pipe rate; with the pixels on N
 // every layer (Cout = 32 ... 512) issues full-width MMAs, and per-channel epilogue work (bias, column sums for the
 // batch-norm statistics) is per-THREAD state instead of cross-lane reductions.
+// n / d for 0 <= n < 2^31 with a host-computed multiplier (a runtime integer division costs ~40 dependent instructions;
+// the tile loops of all three warp roles decode tile -> (class, channel tile, pixel tile, image, row, column))
+struct FastDiv {
+  uint32_t mul, shr, d;
+  __host__ void set(int denom) {
+    d = (uint32_t)denom;
+    uint32_t l = 0;
+    while ((1u << l) < d) ++l;
+    const uint32_t p = 31 + l;
+    mul = (uint32_t)((((uint64_t)1 << p) + d - 1) / d);
+    shr = p - 32;
+  }
+  __device__ __forceinline__ int div(int n) const { return d == 1 ? n : (int)(__umulhi((uint32_t)n, mul) >> shr); }
+  __device__ __forceinline__ void divmod(int n, int& q, int& r) const { q = div(n); r = n - q * (int)d; }
+};
+
 struct IgParams {
+  FastDiv d_tiles_x, d_tiles_y, d_tpi, d_ct, d_tpc;
   int N, th, tw, nb, ltw, lppi, tiles_y, tiles_x, m_tiles, pp_tiles, ct_tiles, T, kchunks, klast, sy, sx;
   int dy[25], dx[25];
   void* out;
@@ -88,7 +105,8 @@ struct IgParams {
   // output-parity classes of a strided transposed convolution, all in ONE launch: class c owns taps
   // [ctap0[c], ctap0[c] + cT[c]) of dy/dx/the packed weights and writes at output offset (cooy[c], coox[c])
   int ncls, cT[4], ctap0[4], cooy[4], coox[4];
-  int dbg;   // experiments only (TGAN_IGEMM_DBG): 1 skip activation loads, 2 skip weight loads, 4 skip stores
+  int dbg;   // experiments only (TGAN_IGEMM_DBG): 1 skip activation loads, 2 skip weight loads, 4 skip stores,
+             // 8 skip the epilogue body, 16 skip the smem-ring handshakes
 };
 
 // Store one chunk of 32 consecutive tile pixels for this thread's output channel.  TW = min(tile width, 32) is a
@@ -141,7 +159,10 @@ __device__ __forceinline__ void ig_sum_chunk(const IgParams& p, const float (&v)
     const int oy = ty * p.th + (rem >> p.ltw), ox0 = tx * p.tw + (rem & (p.tw - 1)), n = ng * p.nb + nl;
     const bool rowok = (n < p.N) && (oy < p.vh);
     const int lim = rowok ? p.vw - ox0 : 0;
-    if (p.segflat) {      // segment boundaries fall inside a run of pixels: classify every pixel
+    const int sga = (ox0 >= p.seg_end[0]) + (ox0 >= p.seg_end[1]) + (ox0 >= p.seg_end[2]);
+    const int oxl = ox0 + TW - 1;
+    const int sgb = (oxl >= p.seg_end[0]) + (oxl >= p.seg_end[1]) + (oxl >= p.seg_end[2]);
+    if (p.segflat && sga != sgb) {      // a segment boundary falls inside this run of pixels: classify every pixel
 #pragma unroll
       for (int jc = 0; jc < TW; ++jc) {
         const int ox = ox0 + jc;
@@ -155,7 +176,7 @@ __device__ __forceinline__ void ig_sum_chunk(const IgParams& p, const float (&v)
     float s = 0.f;
 #pragma unroll
     for (int jc = 0; jc < TW; ++jc) s += (jc < lim) ? v[sgm * TW + jc] : 0.f;
-    const int sg = (n >= p.seg_end[0]) + (n >= p.seg_end[1]) + (n >= p.seg_end[2]);
+    const int sg = p.segflat ? sga : (n >= p.seg_end[0]) + (n >= p.seg_end[1]) + (n >= p.seg_end[2]);
     csum[0] += sg == 0 ? s : 0.f; csum[1] += sg == 1 ? s : 0.f;
     csum[2] += sg == 2 ? s : 0.f; csum[3] += sg == 3 ? s : 0.f;
   }
@@ -167,7 +188,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
              const __grid_constant__ CUtensorMap tmO2, const __grid_constant__ CUtensorMap tmO3,
              const __grid_constant__ IgParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by OFFSET (pointer arithmetic on the __shared__ array keeps the address space, so the epilogue's
+  // staging stores compile to STS instead of generic stores)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* ostage = smem + (size_t)IG_STAGES * IG_STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ostage + IG_OUT_STAGE_BYTES);
   uint64_t* full = bars;
@@ -193,23 +216,26 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 
   const int tiles_per_cls = p.pp_tiles * p.ct_tiles;
   const int total_tiles = tiles_per_cls * p.ncls;
-  const int tiles_per_img = p.tiles_x * p.tiles_y;
 
   // Producer and MMA-issuer warps run their loops with ALL 32 lanes (warp-uniform control flow keeps addresses and
   // descriptors in uniform registers); only the TMA / tcgen05 instructions themselves are issued by one elected lane.
   if (warp == 0) {
     int stage = 0; uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int cls = tile / tiles_per_cls, tin = tile - cls * tiles_per_cls;
-      const int ct = tin % p.ct_tiles, pp = tin / p.ct_tiles;
+      int cls, tin, ct, pp;
+      p.d_tpc.divmod(tile, cls, tin);
+      p.d_ct.divmod(tin, pp, ct);
       const int tap0 = p.ctap0[cls], tap1 = tap0 + p.cT[cls];
       int x0[2], y0[2], n0[2];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int mt = 2 * pp + h;       // mt >= m_tiles -> image index >= N -> the box is zero-filled
-        x0[h] = (mt % p.tiles_x) * p.tw * p.sx;
-        y0[h] = ((mt / p.tiles_x) % p.tiles_y) * p.th * p.sy;
-        n0[h] = (mt / tiles_per_img) * p.nb;
+        int t2, txx, tyy, ngg;
+        p.d_tiles_x.divmod(mt, t2, txx);
+        p.d_tiles_y.divmod(t2, ngg, tyy);
+        x0[h] = txx * p.tw * p.sx;
+        y0[h] = tyy * p.th * p.sy;
+        n0[h] = ngg * p.nb;
       }
       for (int t = tap0; t < tap1; ++t) {
         const int ddx = p.dx[t], ddy = p.dy[t];
@@ -237,7 +263,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     const uint32_t s_base = smem_u32(smem) >> 4;
     int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t accphase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int ksteps = p.cT[tile / tiles_per_cls] * p.kchunks;
+      const int ksteps = p.cT[p.d_tpc.div(tile)] * p.kchunks;
       mbar_wait(&tempty[acc], accphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * IG_NPIX);
@@ -278,8 +304,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     const bool plain = p.alpha == 1.f && p.bias == nullptr;
     int acc = 0; uint32_t accphase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int cls = tile / tiles_per_cls, tin = tile - cls * tiles_per_cls;
-      const int ct = tin % p.ct_tiles, pp = tin / p.ct_tiles;
+      int cls, tin, ct, pp;
+      p.d_tpc.divmod(tile, cls, tin);
+      p.d_ct.divmod(tin, pp, ct);
       const CUtensorMap* tmO = cls == 0 ? &tmO0 : cls == 1 ? &tmO1 : cls == 2 ? &tmO2 : &tmO3;
       const int co = ct * 128 + q * 32 + lane;
       const bool cvalid = co < p.Nout;
@@ -290,7 +317,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       for (int h = 0; h < 2; ++h) {
         const int mt = 2 * pp + h;
         if (mt >= p.m_tiles || (p.dbg & 8)) break;
-        const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, ng = mt / tiles_per_img;
+        int t2, tx, ty, ng;
+        p.d_tiles_x.divmod(mt, t2, tx);
+        p.d_tiles_y.divmod(t2, ng, ty);
         if (p.tstore) {           // the previous box's store must have finished reading the staging buffer
           if (warp == 2 && lane == 0) bulk_wait_read0();
           named_bar_sync(1, 256);
@@ -405,7 +434,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorMap tmX,
              const __grid_constant__ WgParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by OFFSET (pointer arithmetic on the __shared__ array keeps the address space, so the epilogue's
+  // staging stores compile to STS instead of generic stores)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int stages = p.stages;
   const int nbB = p.BNc / 64;                                   // 64-channel boxes per tap operand
   const uint32_t stage_bytes = (uint32_t)(2 + p.tg * nbB) * WG_BOX_BYTES;
@@ -637,6 +668,8 @@ extern "C" int tgan_igemm_bf16(const tgan_igemm_args* a, void* stream) {
     TGAN_CHECK_ARG(e == cudaSuccess, "igemm: cannot set max dynamic smem: %s", cudaGetErrorString(e));
     attr_set = true;
   }
+  p.d_tiles_x.set(p.tiles_x); p.d_tiles_y.set(p.tiles_y); p.d_tpi.set(p.tiles_x * p.tiles_y);
+  p.d_ct.set(p.ct_tiles); p.d_tpc.set(p.pp_tiles * p.ct_tiles);
   const int total = p.pp_tiles * p.ct_tiles * p.ncls;
   const int grid = total < 148 ? total : 148;
   igemm_kernel<<<grid, IG_THREADS, smem_bytes, (cudaStream_t)stream>>>(tmX, tmW, tmO[0], tmO[1], tmO[2], tmO[3], p);
