@@ -109,16 +109,21 @@ struct IgParams {
              // 8 skip the epilogue body, 16 skip the smem-ring handshakes
 };
 
-// Store one chunk of 32 consecutive tile pixels for this thread's output channel.  TW = min(tile width, 32) is a
-// compile-time constant so that every pixel's offset is `segment base + constant * pixel step`: the epilogue warps
-// run alone on their scheduler (no latency hiding), so per-element dependent integer chains would dominate the tile.
-template <int TW, typename TO>
-__device__ __forceinline__ void ig_store_chunk(const IgParams& p, TO* __restrict__ out, const float (&v)[32], int pbase,
-                                               int tx, int ty, int ng, int co, bool cvalid, float (&csum)[4], int ooy,
-                                               int oox) {
+// Slow path of the epilogue, deliberately OUT OF LINE and not unrolled: rare activations (tanh / sigmoid / softplus) and
+// the direct global store used when the output cannot go through the TMA store (fp32 or a pixel stride that is not a
+// multiple of 16 bytes: RGB images, 3-channel input gradients).  Keeping it compact matters more than its speed: fully
+// unrolled it made the kernel ~300 KB of SASS and the hot epilogue stalled on instruction fetches.
+__device__ __noinline__ void ig_slow_chunk(const IgParams& p, float* v, int pbase, int tx, int ty, int ng, int co,
+                                           bool cvalid, float* csum, int ooy, int oox, int do_act, int do_store) {
+  if (do_act) {
+#pragma unroll 1
+    for (int j = 0; j < 32; ++j) v[j] = act_fwd(v[j], p.act, 0.2f);
+  }
+  if (!do_store) return;
   const int ppi = p.th * p.tw;
   const int pstep = p.osx * p.ldo;
-#pragma unroll
+  const int TW = p.tw < 32 ? p.tw : 32;
+#pragma unroll 1
   for (int sgm = 0; sgm < 32 / TW; ++sgm) {
     const int pix = pbase + sgm * TW;
     const int nl = pix >> p.lppi, rem = pix & (ppi - 1);
@@ -127,20 +132,18 @@ __device__ __forceinline__ void ig_store_chunk(const IgParams& p, TO* __restrict
     const int base = ((n * p.OH + (oy * p.osy + ooy)) * p.OW + (ox0 * p.osx + oox)) * p.ldo + co;
     const int lim = p.vw - ox0;          // pixel jc is inside the valid width iff jc < lim
     const int sg = (n >= p.seg_end[0]) + (n >= p.seg_end[1]) + (n >= p.seg_end[2]);   // batch segment of this image
-#pragma unroll
+#pragma unroll 1
     for (int jc = 0; jc < TW; ++jc) {
       const bool ok = rowok && (jc < lim);
       const float x = v[sgm * TW + jc];
-      if (p.colsum) {
-        const float xs = ok ? x : 0.f;
+      if (p.colsum && ok) {
         const int ox = ox0 + jc;
         const int sj = p.segflat ? (ox >= p.seg_end[0]) + (ox >= p.seg_end[1]) + (ox >= p.seg_end[2]) : sg;
-        csum[0] += sj == 0 ? xs : 0.f; csum[1] += sj == 1 ? xs : 0.f;
-        csum[2] += sj == 2 ? xs : 0.f; csum[3] += sj == 3 ? xs : 0.f;
+        csum[sj] += x;
       }
       if (ok) {
-        if constexpr (sizeof(TO) == 2) out[base + jc * pstep] = __float2bfloat16_rn(x);
-        else out[base + jc * pstep] = x;
+        if (p.odt == TGAN_BF16) reinterpret_cast<bf16*>(p.out)[base + jc * pstep] = __float2bfloat16_rn(x);
+        else reinterpret_cast<float*>(p.out)[base + jc * pstep] = x;
       }
     }
   }
@@ -346,15 +349,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
           } else if (p.act == TGAN_ACT_RELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          } else if (p.act == TGAN_ACT_TANH) {
+          } else if (p.act != TGAN_ACT_NONE) {
+            float tmp[32];            // a separate copy: taking v's address would move v to local memory on the hot path too
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
-          } else if (p.act == TGAN_ACT_SIGMOID) {
+            for (int j = 0; j < 32; ++j) tmp[j] = v[j];
+            ig_slow_chunk(p, tmp, pbase, tx, ty, ng, co, cvalid, csum, 0, 0, 1, 0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
-          } else if (p.act == TGAN_ACT_SOFTPLUS) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = v[j] > 20.f ? v[j] : log1pf(expf(v[j]));
+            for (int j = 0; j < 32; ++j) v[j] = tmp[j];
           }
           if (p.tstore) {
             // ---- staged path: [pixel][channel] rows in shared memory, one bulk-tensor store per 128-pixel box.  The
@@ -371,23 +372,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 #pragma unroll
             for (int j = 0; j < 32; ++j) srow[j * 128] = __float2bfloat16_rn(v[j]);
           } else if (!(p.dbg & 4)) {
-            if (p.odt == TGAN_BF16) {
-              bf16* o = reinterpret_cast<bf16*>(p.out);
-              switch (p.ltw) {
-                case 2: ig_store_chunk<4>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum, p.cooy[cls], p.coox[cls]); break;
-                case 3: ig_store_chunk<8>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum, p.cooy[cls], p.coox[cls]); break;
-                case 4: ig_store_chunk<16>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum, p.cooy[cls], p.coox[cls]); break;
-                default: ig_store_chunk<32>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum, p.cooy[cls], p.coox[cls]); break;
-              }
-            } else {
-              float* o = reinterpret_cast<float*>(p.out);
-              switch (p.ltw) {
-                case 2: ig_store_chunk<4>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum, p.cooy[cls], p.coox[cls]); break;
-                case 3: ig_store_chunk<8>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum, p.cooy[cls], p.coox[cls]); break;
-                case 4: ig_store_chunk<16>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum, p.cooy[cls], p.coox[cls]); break;
-                default: ig_store_chunk<32>(p, o, v, pbase, tx, ty, ng, co, cvalid, csum, p.cooy[cls], p.coox[cls]); break;
-              }
-            }
+            float tmp[32], cs2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 32; ++j) tmp[j] = v[j];
+            ig_slow_chunk(p, tmp, pbase, tx, ty, ng, co, cvalid, cs2, p.cooy[cls], p.coox[cls], 0, 1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) csum[j] += cs2[j];
           }
         }
         if (p.tstore) {

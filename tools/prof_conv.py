@@ -9,7 +9,7 @@ p = core.Param('w', (3,3,C,C), True, None); p.data = torch.randn(3,3,C,C, device
 for it in range(3):
     with core.recording():
         x = ops.Var(torch.randn(N,H,H,C, device='cuda').to(torch.bfloat16), (N,H,H,C), requires_grad=True)
-        y = ops.conv2d(x, ops.PlainWeight(p), 3,3,1,'SAME')
+        y = ops.conv2d(x, ops.PlainWeight(p), 3,3,1,'SAME'); y.data      # .data launches the deferred contraction
         y.grad = torch.randn(N,H,H,C, device='cuda').to(torch.bfloat16)
         core.ctx.tape.backward()
 torch.cuda.synchronize()
