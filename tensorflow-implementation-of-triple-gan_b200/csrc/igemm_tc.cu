@@ -68,6 +68,14 @@ constexpr int IG_NPIX = 256;             // pixels per CTA tile = UMMA N (two 12
 constexpr int IG_STAGE_BYTES = W_STAGE_BYTES + 2 * P_TILE_BYTES;
 constexpr int IG_STAGES = 4;
 constexpr int IG_OUT_STAGE_BYTES = 128 * 256;   // epilogue staging: 128 pixels x 128 channels bf16 ([pixel][channel] rows)
+// Row-halo mode (3x3 / stride-1 convolutions whose 256-pixel tile is a block of full-width rows of ONE image): for each
+// of the three column offsets dx ONE activation box of (rows + 2) x width pixels is loaded, and the three row taps dy are
+// row-shifted views of it (UMMA descriptor start address + dy * width * 128 B) -- 3 activation loads per K chunk instead
+// of 9.  Shared memory: HALO_A_SLOTS activation slots + HALO_W_SLOTS weight slots (one per tap) replace the 4-stage ring.
+constexpr int HALO_A_SLOT_BYTES = 40 * 1024;    // (8 + 2) rows x 32 pixels x 128 B is the largest box (32x32 images)
+constexpr int HALO_A_SLOTS = 3;
+constexpr int HALO_W_SLOTS = 4;
+static_assert(HALO_A_SLOTS * HALO_A_SLOT_BYTES + HALO_W_SLOTS * W_STAGE_BYTES <= IG_STAGES * IG_STAGE_BYTES, "halo rings fit");
 
 // Orientation: D[co, pixel] = W[co, k] * X[pixel, k]^T.  The OUTPUT CHANNELS are the UMMA M dimension (TMEM lanes) and
 // 256 PIXELS are the UMMA N dimension: measured on B200, one cta_group::1 tcgen05.mma (M=128, K=16, smem operands)
@@ -105,6 +113,7 @@ struct IgParams {
   // output-parity classes of a strided transposed convolution, all in ONE launch: class c owns taps
   // [ctap0[c], ctap0[c] + cT[c]) of dy/dx/the packed weights and writes at output offset (cooy[c], coox[c])
   int ncls, cT[4], ctap0[4], cooy[4], coox[4];
+  int halo, halo_rows, halo_dy0;   // row-halo mode: box rows (2*th + 2), smallest dy
   int dbg;   // experiments only (TGAN_IGEMM_DBG): 1 skip activation loads, 2 skip weight loads, 4 skip stores,
              // 8 skip the epilogue body, 16 skip the smem-ring handshakes
 };
@@ -115,8 +124,8 @@ struct IgParams {
 // unrolled it made the kernel ~300 KB of SASS and the hot epilogue stalled on instruction fetches.
 __device__ __noinline__ void ig_slow_chunk(const IgParams& p, float* v, int pbase, int tx, int ty, int ng, int co,
                                            bool cvalid, float* csum, int ooy, int oox, int do_act, int do_store) {
-  if (do_act) {
-#pragma unroll 1
+  if (do_act && cvalid) {      // lanes beyond Nout (125 of 128 for the generator's RGB layer) skip the transcendental
+#pragma unroll 4
     for (int j = 0; j < 32; ++j) v[j] = act_fwd(v[j], p.act, 0.2f);
   }
   if (!do_store) return;
@@ -187,7 +196,7 @@ __device__ __forceinline__ void ig_sum_chunk(const IgParams& p, const float (&v)
 
 __global__ void __launch_bounds__(IG_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-             const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
+             const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
              const __grid_constant__ CUtensorMap tmO2, const __grid_constant__ CUtensorMap tmO3,
              const __grid_constant__ IgParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -200,15 +209,22 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
   uint64_t* empty = bars + IG_STAGES;
   uint64_t* tfull = bars + 2 * IG_STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* fullA = tempty + 2;                 // row-halo mode rings
+  uint64_t* emptyA = fullA + HALO_A_SLOTS;
+  uint64_t* fullW = emptyA + HALO_A_SLOTS;
+  uint64_t* emptyW = fullW + HALO_W_SLOTS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(emptyW + HALO_W_SLOTS);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < IG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < HALO_A_SLOTS; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
+    for (int s = 0; s < HALO_W_SLOTS; ++s) { mbar_init(&fullW[s], 1); mbar_init(&emptyW[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
     fence_barrier_init();
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
+    if (p.halo) tma_prefetch_desc(&tmXh);
     if (p.tstore) tma_prefetch_desc(&tmO0);
   }
   if (warp == 0) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }   // 2 accumulators x 256 fp32 columns
@@ -222,7 +238,79 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 
   // Producer and MMA-issuer warps run their loops with ALL 32 lanes (warp-uniform control flow keeps addresses and
   // descriptors in uniform registers); only the TMA / tcgen05 instructions themselves are issued by one elected lane.
-  if (warp == 0) {
+  if (warp == 0 && p.halo) {
+    // ---- row-halo producer: per K chunk and column offset one activation box, then its three row taps' weights ----
+    uint8_t* wring = smem + HALO_A_SLOTS * HALO_A_SLOT_BYTES;
+    const uint32_t a_bytes = (uint32_t)p.halo_rows * p.tw * 128u;
+    int sa = 0, sw = 0; uint32_t pa = 0, pw = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int ct, pp, ty, ng;
+      p.d_ct.divmod(tile, pp, ct);
+      p.d_tiles_y.divmod(2 * pp, ng, ty);          // tiles_x == 1, nb == 1: box 2*pp starts the 256-pixel tile
+      const int y0 = ty * p.th + p.halo_dy0;
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        for (int c = 0; c < 3; ++c) {
+          mbar_wait(&emptyA[sa], pa ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&fullA[sa], (p.dbg & 1) ? 0u : a_bytes);
+            if (!(p.dbg & 1)) tma_load_4d(smem + (size_t)sa * HALO_A_SLOT_BYTES, &tmXh, &fullA[sa], kc * 64, p.dx[c], y0, ng);
+          }
+          __syncwarp();
+          if (++sa == HALO_A_SLOTS) { sa = 0; pa ^= 1; }
+          for (int r = 0; r < 3; ++r) {
+            mbar_wait(&emptyW[sw], pw ^ 1);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&fullW[sw], (p.dbg & 2) ? 0u : (uint32_t)W_STAGE_BYTES);
+              if (!(p.dbg & 2)) tma_load_3d(wring + (size_t)sw * W_STAGE_BYTES, &tmW, &fullW[sw], kc * 64, ct * 128, r * 3 + c);
+            }
+            __syncwarp();
+            if (++sw == HALO_W_SLOTS) { sw = 0; pw ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && p.halo) {
+    // ---- row-halo MMA issuer ----
+    const uint32_t idesc = umma_idesc_bf16(128, IG_NPIX, 0, 0);
+    const uint64_t desc_hi = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+    const uint32_t a_base = smem_u32(smem) >> 4;
+    const uint32_t w_base = a_base + ((HALO_A_SLOTS * HALO_A_SLOT_BYTES) >> 4);
+    int sa = 0, sw = 0; uint32_t pa = 0, pw = 0; int acc = 0; uint32_t accphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[acc], accphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * IG_NPIX);
+      uint32_t accum = 0;
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        const int nk = (kc == p.kchunks - 1) ? p.klast : 4;
+        for (int c = 0; c < 3; ++c) {
+          mbar_wait(&fullA[sa], pa);
+          const uint32_t x_lo = a_base + (uint32_t)sa * (HALO_A_SLOT_BYTES >> 4);
+          for (int r = 0; r < 3; ++r) {
+            mbar_wait(&fullW[sw], pw);
+            tc_fence_after();
+            const uint32_t a_lo = w_base + (uint32_t)sw * (W_STAGE_BYTES >> 4);
+            // the row tap dy = row-shifted view of the halo box: + (dy - dy0) * width pixel rows of 128 B
+            const uint32_t b_lo = x_lo + (uint32_t)((p.dy[r * 3] - p.halo_dy0) * p.tw * 8);
+            if (elect_one()) {
+              for (int k = 0; k < nk; ++k) {
+                umma_bf16(d_tmem, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc, accum);
+                accum = 1u;
+              }
+              umma_commit(&emptyW[sw]);
+              if (r == 2) umma_commit(&emptyA[sa]);
+              if (r == 2 && c == 2 && kc == p.kchunks - 1) umma_commit(&tfull[acc]);
+            }
+            accum = 1u;
+            __syncwarp();
+            if (++sw == HALO_W_SLOTS) { sw = 0; pw ^= 1; }
+          }
+          if (++sa == HALO_A_SLOTS) { sa = 0; pa ^= 1; }
+        }
+      }
+      if (++acc == 2) { acc = 0; accphase ^= 1; }
+    }
+  } else if (warp == 0) {
     int stage = 0; uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int cls, tin, ct, pp;
@@ -627,13 +715,35 @@ extern "C" int tgan_igemm_bf16(const tgan_igemm_args* a, void* stream) {
     p.cT[0] = a->T; p.ctap0[0] = 0; p.cooy[0] = p.ooy; p.coox[0] = p.oox;
   }
 
-  CUtensorMap tmX, tmW, tmO[4];
+  // row-halo eligibility: a full 3x3 tap grid (row-major, unit steps), stride 1, one class, full-width tiles of one image
+  // whose two 128-pixel boxes are vertically adjacent
+  p.halo = 0;
+  if (a->T == 9 && sy == 1 && sx == 1 && p.ncls == 1 && p.nb == 1 && p.tiles_x == 1 && p.tiles_y % 2 == 0 && p.tw >= 8 &&
+      (2 * p.th + 2) * p.tw * 128 <= HALO_A_SLOT_BYTES) {
+    bool grid = true;
+    const int sr = a->dy[3] - a->dy[0], sc = a->dx[1] - a->dx[0];
+    for (int t = 0; t < 9; ++t)
+      grid = grid && a->dy[t] == a->dy[0] + (t / 3) * sr && a->dx[t] == a->dx[0] + (t % 3) * sc;
+    if (grid && (sr == 1 || sr == -1) && (sc == 1 || sc == -1)) {
+      p.halo = 1;
+      p.halo_rows = 2 * p.th + 2;
+      p.halo_dy0 = sr == 1 ? a->dy[0] : a->dy[6];
+    }
+  }
+  { const char* e = getenv("TGAN_IGEMM_NO_HALO"); if (e && atoi(e)) p.halo = 0; }
+
+  CUtensorMap tmX, tmW, tmXh, tmO[4];
   {
     uint64_t dims[4] = {(uint64_t)a->C, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->N};
     uint64_t str[3] = {(uint64_t)a->ldx * 2, (uint64_t)a->W * a->ldx * 2, (uint64_t)a->H * a->W * a->ldx * 2};
     uint32_t box[4] = {64, (uint32_t)(p.tw * sx), (uint32_t)(p.th * sy), (uint32_t)p.nb};
     uint32_t es[4] = {1, (uint32_t)sx, (uint32_t)sy, 1};
     if (make_tmap_bf16(&tmX, a->x, 4, dims, str, box, es)) return 1;
+    tmXh = tmX;
+    if (p.halo) {
+      uint32_t hbox[4] = {64, (uint32_t)p.tw, (uint32_t)p.halo_rows, 1};
+      if (make_tmap_bf16(&tmXh, a->x, 4, dims, str, hbox, nullptr)) return 1;
+    }
   }
   {
     uint64_t dims[3] = {(uint64_t)a->Kpad, (uint64_t)a->Nout, (uint64_t)a->T};
@@ -662,7 +772,7 @@ extern "C" int tgan_igemm_bf16(const tgan_igemm_args* a, void* stream) {
   p.d_ct.set(p.ct_tiles); p.d_tpc.set(p.pp_tiles * p.ct_tiles);
   const int total = p.pp_tiles * p.ct_tiles * p.ncls;
   const int grid = total < 148 ? total : 148;
-  igemm_kernel<<<grid, IG_THREADS, smem_bytes, (cudaStream_t)stream>>>(tmX, tmW, tmO[0], tmO[1], tmO[2], tmO[3], p);
+  igemm_kernel<<<grid, IG_THREADS, smem_bytes, (cudaStream_t)stream>>>(tmX, tmW, tmXh, tmO[0], tmO[1], tmO[2], tmO[3], p);
   TGAN_LAUNCHED();
   return 0;
 }
