@@ -141,7 +141,7 @@ __device__ __noinline__ void ig_slow_chunk(const IgParams& p, float* v, int pbas
     const int base = ((n * p.OH + (oy * p.osy + ooy)) * p.OW + (ox0 * p.osx + oox)) * p.ldo + co;
     const int lim = p.vw - ox0;          // pixel jc is inside the valid width iff jc < lim
     const int sg = (n >= p.seg_end[0]) + (n >= p.seg_end[1]) + (n >= p.seg_end[2]);   // batch segment of this image
-#pragma unroll 1
+#pragma unroll 4
     for (int jc = 0; jc < TW; ++jc) {
       const bool ok = rowok && (jc < lim);
       const float x = v[sgm * TW + jc];
@@ -437,6 +437,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
           } else if (p.act == TGAN_ACT_RELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (p.act == TGAN_ACT_TANH && p.tstore) {
+            // bf16 output: 1 - 2/(e^2x + 1) with the fast exponential (abs. error ~1e-7, far below the bf16 rounding);
+            // fp32 outputs take the exact tanhf of the out-of-line path
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 1.f - __fdividef(2.f, __expf(2.f * v[j]) + 1.f);
+          } else if (p.act == TGAN_ACT_SIGMOID && p.tstore) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __fdividef(1.f, 1.f + __expf(-v[j]));
           } else if (p.act != TGAN_ACT_NONE) {
             float tmp[32];            // a separate copy: taking v's address would move v to local memory on the hot path too
 #pragma unroll

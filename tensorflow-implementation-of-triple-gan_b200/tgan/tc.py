@@ -196,13 +196,18 @@ def conv_bwd(x, w, g, dz):
     tgt, Cg = _grad_target(x, C)
     if tgt.requires_grad:
         # a label-concatenated input only needs the gradient of its first Cg channels: it goes to the concat's source
-        dx = _new(tuple(x.shape[:-1]) + (Cg,), tgt.data.dtype if tgt.data.dtype == torch.bfloat16 else torch.float32)
+        dxt = _new(tuple(x.shape[:-1]) + (Cg,), tgt.data.dtype if tgt.data.dtype == torch.bfloat16 else torch.float32)
+        # narrow / fp32 gradients (the RGB image: 3 channels) go through an 8-channel bf16 staging tensor so that the
+        # GEMM keeps its TMA-store epilogue, then one slice / convert
+        staged = Cg % 8 != 0 or dxt.dtype != torch.bfloat16
+        Cs = (Cg + 7) // 8 * 8
+        dx = _new(tuple(x.shape[:-1]) + (Cs,), torch.bfloat16) if staged else dxt
         wp, Kpad = None, None
         if s == 1:
             wp, Kpad = _pack(w, ('dgrad', Cg), kh * kw, Cg, Cout, C * Cout, Cout, 1)
             taps = [(pt - r, pl - c) for r in range(kh) for c in range(kw)]
             _igemm(dzb, gf['N'], gf['Ho'], gf['Wo'], Cout, Cout, wp, Kpad, taps, Cg, gf['H'], gf['W'], dx, gf['H'],
-                   gf['W'], Cg)
+                   gf['W'], Cs if staged else Cg)
         else:
             # input-gradient of a stride-2 conv = transposed conv: its output-parity classes, heaviest first, in ONE launch
             cl = []
@@ -219,8 +224,10 @@ def conv_bwd(x, w, g, dz):
             taps = [t for c in cl for t in c[3]]
             wp, Kpad = _pack(w, ('dgrad2', Cg), len(sel), Cg, Cout, C * Cout, Cout, 1, sel)
             _igemm(dzb, g['N'], g['Ho'], g['Wo'], Cout, Cout, wp, Kpad, taps, Cg, g['H'] // 2, g['W'] // 2, dx,
-                   g['H'], g['W'], Cg, os_=2, classes=[(len(c[2]), c[0], c[1]) for c in cl])
-        add_grad(tgt, dx if dx.dtype == tgt.data.dtype else dx.to(tgt.data.dtype))
+                   g['H'], g['W'], Cs if staged else Cg, os_=2, classes=[(len(c[2]), c[0], c[1]) for c in cl])
+        if staged:
+            _lib.call('tgan_copy_channels', dx.data_ptr(), BF16, Cs, dxt.data_ptr(), dt_code(dxt), Cg, x.rows, Cg, _st())
+        add_grad(tgt, dxt if dxt.dtype == tgt.data.dtype else dxt.to(tgt.data.dtype))
     g.pop('_x', None)
     g.pop('_col', None)
 
