@@ -514,6 +514,9 @@ struct WgParams {
   int dy[25], dx[25];
   float* ws;            // [splits][T][Cin][Cout]
   int Cout, Cin;
+  // row-halo mode (3x3 / stride 1, pixel tiles = kr full-width rows of one image): the tap group is one COLUMN offset dx,
+  // its x operand is ONE box of kr + 2 rows and the three row taps dy are row-shifted views of it
+  int halo, kp, xrows, dy0;     // pixels (GEMM K) per stage, pixel rows of the x box, smallest dy
 };
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
@@ -525,7 +528,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ C
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int stages = p.stages;
   const int nbB = p.BNc / 64;                                   // 64-channel boxes per tap operand
-  const uint32_t stage_bytes = (uint32_t)(2 + p.tg * nbB) * WG_BOX_BYTES;
+  const uint32_t dz_box = (uint32_t)p.kp * 128u, x_box = (uint32_t)p.xrows * 128u;
+  const uint32_t stage_bytes = 2u * dz_box + (uint32_t)((p.halo ? 1 : p.tg) * nbB) * x_box;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + stages;
@@ -540,7 +544,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ C
   const int split = b % p.splits; b /= p.splits;
   const int tgi = b % p.tap_groups; b /= p.tap_groups;
   const int cit = b % p.ci_tiles; const int cot = b / p.ci_tiles;
-  const int t0 = tgi * p.tg, nt = min(p.tg, p.T - t0);
+  const int t0 = p.halo ? tgi : tgi * p.tg, nt = p.halo ? 3 : min(p.tg, p.T - t0);   // halo: taps t0, t0 + 3, t0 + 6
+  const int tstep = p.halo ? 3 : 1;
   const int per = (p.p_tiles + p.splits - 1) / p.splits;
   const int pt0 = split * per, pt1 = min(p.p_tiles, pt0 + per);
 
@@ -564,14 +569,23 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ C
       const int ox0 = tx * p.bw, oy0 = ty * p.bh, n0 = ng * p.bn;
       mbar_wait(&empty[stage], phase ^ 1);
       if (elect_one()) {
-        mbar_arrive_expect_tx(&full[stage], (uint32_t)(2 + nt * nbB) * WG_BOX_BYTES);   // exact: last group may be short
         uint8_t* s = smem + (size_t)stage * stage_bytes;
-        tma_load_4d(s, &tmDz, &full[stage], cot * 128, ox0, oy0, n0);
-        tma_load_4d(s + WG_BOX_BYTES, &tmDz, &full[stage], cot * 128 + 64, ox0, oy0, n0);
-        for (int j = 0; j < nt; ++j)
+        if (p.halo) {
+          mbar_arrive_expect_tx(&full[stage], 2u * dz_box + (uint32_t)nbB * x_box);
+          tma_load_4d(s, &tmDz, &full[stage], cot * 128, ox0, oy0, n0);
+          tma_load_4d(s + dz_box, &tmDz, &full[stage], cot * 128 + 64, ox0, oy0, n0);
           for (int bb = 0; bb < nbB; ++bb)
-            tma_load_4d(s + (size_t)(2 + j * nbB + bb) * WG_BOX_BYTES, &tmX, &full[stage], cit * p.BNc + bb * 64,
-                        ox0 * p.sx + p.dx[t0 + j], oy0 * p.sy + p.dy[t0 + j], n0);
+            tma_load_4d(s + 2 * dz_box + (size_t)bb * x_box, &tmX, &full[stage], cit * p.BNc + bb * 64, ox0 + p.dx[t0],
+                        oy0 + p.dy0, n0);
+        } else {
+          mbar_arrive_expect_tx(&full[stage], (uint32_t)(2 + nt * nbB) * WG_BOX_BYTES);   // exact: last group may be short
+          tma_load_4d(s, &tmDz, &full[stage], cot * 128, ox0, oy0, n0);
+          tma_load_4d(s + WG_BOX_BYTES, &tmDz, &full[stage], cot * 128 + 64, ox0, oy0, n0);
+          for (int j = 0; j < nt; ++j)
+            for (int bb = 0; bb < nbB; ++bb)
+              tma_load_4d(s + (size_t)(2 + j * nbB + bb) * WG_BOX_BYTES, &tmX, &full[stage], cit * p.BNc + bb * 64,
+                          ox0 * p.sx + p.dx[t0 + j], oy0 * p.sy + p.dy[t0 + j], n0);
+        }
       }
       __syncwarp();
       if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -587,7 +601,23 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ C
       mbar_wait(&full[stage], phase);
       tc_fence_after();
       const uint32_t s = s_base + (uint32_t)stage * (stage_bytes >> 4);
-      if (elect_one()) {
+      if (p.halo) {
+        if (elect_one()) {
+          // A (dz): MN-major, LBO = dz box; B (x): MN-major, LBO = x box; row tap r = + (dy_r - dy0) * width pixel rows
+          const uint64_t hiA = ((uint64_t)(dz_box >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+          const uint64_t hiB = ((uint64_t)(x_box >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+          const uint32_t idh = umma_idesc_bf16(128, p.BNc, 1, 1);
+          const uint32_t xb = s + ((2u * dz_box) >> 4);
+          for (int ks = 0; ks < p.kp / 16; ++ks)
+            for (int r = 0; r < 3; ++r) {
+              const uint32_t b_lo = xb + (uint32_t)((p.dy[t0 + 3 * r] - p.dy0) * p.bw * 8) + (uint32_t)ks * 128u;
+              umma_bf16(tmem_base + (uint32_t)(r * p.BNc), hiA | (uint64_t)(s + (uint32_t)ks * 128u), hiB | (uint64_t)b_lo, idh,
+                        (pt > pt0 || ks > 0) ? 1u : 0u);
+            }
+          umma_commit(&empty[stage]);
+          if (pt == pt1 - 1) umma_commit(done);
+        }
+      } else if (elect_one()) {
         // consecutive taps are consecutive 64-channel boxes in smem and consecutive column blocks in TMEM, so one
         // MMA spans `span` taps: N = span*BNc <= 256 (an MMA costs the same ~82 ns for any N <= 256)
         for (int j = 0; j < nt; j += span) {
@@ -626,7 +656,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ C
         }
         if (co < p.Cout) {
           // partial layout [split][t][ci][co]: for a fixed ci the 32 lanes write 32 consecutive co (one 128 B line)
-          float* o = p.ws + (((int64_t)split * p.T + (t0 + j)) * p.Cin + ci0) * p.Cout + co;
+          float* o = p.ws + (((int64_t)split * p.T + (t0 + j * tstep)) * p.Cin + ci0) * p.Cout + co;
 #pragma unroll
           for (int i = 0; i < 32; ++i) if (ci0 + i < p.Cin) o[(int64_t)i * p.Cout] = __uint_as_float(r[i]);
         }
@@ -785,35 +815,64 @@ extern "C" int tgan_igemm_bf16(const tgan_igemm_args* a, void* stream) {
   return 0;
 }
 
+static size_t wg_stage_bytes(const WgParams& p) {
+  return (size_t)2 * p.kp * 128 + (size_t)((p.halo ? 1 : p.tg) * (p.BNc / 64)) * p.xrows * 128;
+}
+
 static int wgrad_plan(const tgan_wgrad_args* a, WgParams& p) {
   memset(&p, 0, sizeof(p));
   const int sy = a->sy > 0 ? a->sy : 1, sx = a->sx > 0 ? a->sx : 1;
   p.N = a->N; p.sy = sy; p.sx = sx; p.T = a->T; p.Cout = a->Cout; p.Cin = a->Cin;
-  pick_tile(a->gh, a->gw, p.bh, p.bw, p.bn, WG_KP);
+  // row-halo eligibility: full 3x3 tap grid in row-major order with unit steps, stride 1, width a power of two in
+  // [16, 128] that divides 128, height a multiple of the 128 / width rows of a pixel tile
+  p.halo = 0;
+  if (a->T == 9 && sy == 1 && sx == 1 && a->gw >= 16 && a->gw <= 128 && (a->gw & (a->gw - 1)) == 0 && a->W == a->gw &&
+      a->gh % (128 / a->gw) == 0 && a->Cin >= 64) {
+    bool grid = true;
+    const int sr = a->dy[3] - a->dy[0], sc = a->dx[1] - a->dx[0];
+    for (int t = 0; t < 9; ++t)
+      grid = grid && a->dy[t] == a->dy[0] + (t / 3) * sr && a->dx[t] == a->dx[0] + (t % 3) * sc;
+    if (grid && (sr == 1 || sr == -1) && (sc == 1 || sc == -1)) { p.halo = 1; p.dy0 = sr == 1 ? a->dy[0] : a->dy[6]; }
+  }
+  { const char* e = getenv("TGAN_WGRAD_NO_HALO"); if (e && atoi(e)) p.halo = 0; }
+  if (p.halo) {
+    p.kp = 128; p.bw = a->gw; p.bh = 128 / a->gw; p.bn = 1;
+    p.xrows = (p.bh + 2) * p.bw;
+  } else {
+    pick_tile(a->gh, a->gw, p.bh, p.bw, p.bn, WG_KP);
+    p.kp = WG_KP; p.xrows = WG_KP;
+  }
   if (p.bw * sx > 256 || p.bh * sy > 256) { set_error("wgrad: strided box too large"); return 1; }
   p.ptiles_y = ceil_div(a->gh, p.bh); p.ptiles_x = ceil_div(a->gw, p.bw);
   p.p_tiles = ceil_div(a->N, p.bn) * p.ptiles_y * p.ptiles_x;
   p.co_tiles = ceil_div(a->Cout, 128);
-  p.BNc = a->Cin <= 64 ? 64 : a->Cin <= 128 ? 128 : 256;
-  p.ci_tiles = ceil_div(a->Cin, p.BNc);
-  p.tg = 512 / p.BNc;
-  if (p.tg > a->T) p.tg = a->T;
-  p.tg = ceil_div(a->T, ceil_div(a->T, p.tg));     // balanced tap groups (T=9, max 4 -> 3+3+3)
-  // smem: stages * (2 + tg*BNc/64) boxes of 4 KB
-  while (p.tg > 1 && (size_t)2 * (2 + p.tg * (p.BNc / 64)) * WG_BOX_BYTES > 200 * 1024) --p.tg;
-  p.tap_groups = ceil_div(a->T, p.tg);
+  if (p.halo) {
+    p.BNc = a->Cin <= 64 ? 64 : 128;        // three row taps x BNc accumulator columns <= 512
+    p.ci_tiles = ceil_div(a->Cin, p.BNc);
+    p.tg = 3;
+    p.tap_groups = 3;                        // one per column offset
+  } else {
+    p.BNc = a->Cin <= 64 ? 64 : a->Cin <= 128 ? 128 : 256;
+    p.ci_tiles = ceil_div(a->Cin, p.BNc);
+    p.tg = 512 / p.BNc;
+    if (p.tg > a->T) p.tg = a->T;
+    p.tg = ceil_div(a->T, ceil_div(a->T, p.tg));     // balanced tap groups (T=9, max 4 -> 3+3+3)
+    // smem: stages * (2 + tg*BNc/64) boxes of 4 KB
+    while (p.tg > 1 && (size_t)2 * (2 + p.tg * (p.BNc / 64)) * WG_BOX_BYTES > 200 * 1024) --p.tg;
+    p.tap_groups = ceil_div(a->T, p.tg);
+  }
   const int base = p.co_tiles * p.ci_tiles * p.tap_groups;
   int splits = 148 / base;            // one wave of equal-work CTAs; fewer splits = fewer fp32 partials to fold
   if (splits > p.p_tiles) splits = p.p_tiles;
   if (splits < 1) splits = 1;
-  // keep >= 8 pixel tiles per split so the pipeline prologue is amortised
-  while (splits > 1 && p.p_tiles / splits < 8) --splits;
+  // keep >= 8 pixel tiles (2 of the 4x larger row-halo tiles) per split so the pipeline prologue is amortised
+  while (splits > 1 && p.p_tiles / splits < (p.halo ? 2 : 8)) --splits;
   if (a->ws_bytes > 0) {   // clamp to the caller's workspace
     const int64_t per_split = (int64_t)a->T * a->Cout * a->Cin * 4;
     while (splits > 1 && (int64_t)splits * per_split > a->ws_bytes) --splits;
   }
   p.splits = splits;
-  const size_t stage_bytes = (size_t)(2 + p.tg * (p.BNc / 64)) * WG_BOX_BYTES;
+  const size_t stage_bytes = wg_stage_bytes(p);
   int stages = (int)((232448 - 2048) / stage_bytes);
   if (stages > 8) stages = 8;
   p.stages = stages;
@@ -849,7 +908,7 @@ extern "C" int tgan_wgrad_bf16(const tgan_wgrad_args* a, void* stream) {
   {
     uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->N};
     uint64_t str[3] = {(uint64_t)a->ldx * 2, (uint64_t)a->W * a->ldx * 2, (uint64_t)a->H * a->W * a->ldx * 2};
-    uint32_t box[4] = {64, (uint32_t)(p.bw * p.sx), (uint32_t)(p.bh * p.sy), (uint32_t)p.bn};
+    uint32_t box[4] = {64, (uint32_t)(p.bw * p.sx), (uint32_t)((p.halo ? p.bh + 2 : p.bh) * p.sy), (uint32_t)p.bn};
     uint32_t es[4] = {1, (uint32_t)p.sx, (uint32_t)p.sy, 1};
     if (make_tmap_bf16(&tmX, a->x, 4, dims, str, box, es)) return 1;
   }
@@ -859,7 +918,7 @@ extern "C" int tgan_wgrad_bf16(const tgan_wgrad_args* a, void* stream) {
     TGAN_CHECK_ARG(e == cudaSuccess, "wgrad: cannot set max dynamic smem: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const size_t stage_bytes = (size_t)(2 + p.tg * (p.BNc / 64)) * WG_BOX_BYTES;
+  const size_t stage_bytes = wg_stage_bytes(p);
   const size_t smem_bytes = 1024 + p.stages * stage_bytes + 256;
   const int grid = p.co_tiles * p.ci_tiles * p.tap_groups * p.splits;
   wgrad_kernel<<<grid, WG_THREADS, smem_bytes, (cudaStream_t)stream>>>(tmDz, tmX, p);
