@@ -171,6 +171,7 @@ int tgan_weightnorm_bwd(const float* V, const float* g, const float* inv_norm, c
  * x [rows, C] (dtype xdt, contiguous): sum[c] = beta*sum[c] + sum_r x, sumsq[c] likewise (sumsq may be NULL).
  * One launch, deterministic (the last CTA folds the partials in a fixed order); ws: 4*TGAN_STATS_MAX_PARTS*C floats (fp64 partials). */
 #define TGAN_STATS_MAX_PARTS 256
+#define TGAN_ACT_BWD_SEG_PARTS 444   /* tgan_act_bwd_seg: ws must hold 4*TGAN_ACT_BWD_SEG_PARTS*C floats */
 int tgan_channel_stats(const void* x, int xdt, int64_t rows, int C, float* sum, float* sumsq, float beta, float* ws,
                        void* stream);
 

@@ -206,6 +206,94 @@ __global__ void mobn_apply_seg_kernel(const bf16* __restrict__ x, bf16* __restri
   }
 }
 
+// du = dy * act'(y) with per-segment column sums, bf16 with 16-byte accesses (the generic colreduce path moves 8 bytes per
+// thread and accumulates in fp64; this one is the backward of every mean-only-BN layer of the classifier and runs at HBM
+// speed).  256 threads = (C/8 channel groups) x (2048/C row lanes); each CTA walks a strided set of row blocks, folds
+// its row lanes through shared memory and writes one fp32 partial per (segment, channel); act_bwd_seg_fold_kernel adds
+// the partials of all CTAs in a fixed order in fp64 (deterministic).
+template <int ACT>
+__global__ void __launch_bounds__(256) act_bwd_seg_v8_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y,
+                                                             bf16* __restrict__ du, int64_t rows, int C, Segs sg,
+                                                             float alpha, float* __restrict__ partials) {
+  extern __shared__ float abs_sm[];              // [row lanes][4][C]; every thread owns its (lane, segment, 8 channels) slots
+  const int cg = C / 8, rl = 256 / cg;           // channel groups per row, row lanes per CTA
+  const int tc = threadIdx.x % cg, tr = threadIdx.x / cg;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) abs_sm[((size_t)tr * 4 + a) * C + tc * 8 + j] = 0.f;
+  // a CONTIGUOUS range of rows per CTA: the segment changes at most three times, so one accumulator set in registers is
+  // enough (flushed to the thread's shared-memory slot when the segment changes)
+  const int64_t per = ((rows + gridDim.x - 1) / gridDim.x + rl - 1) / rl * rl;
+  const int64_t rbeg = (int64_t)blockIdx.x * per, rend = rbeg + per < rows ? rbeg + per : rows;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  int cur = -1;
+  for (int64_t r0 = rbeg + tr; r0 < rend; r0 += 2 * rl) {
+    const int64_t r1 = r0 + rl;
+    float a0[8], b0[8], a1[8], b1[8];
+    ld8(dy, r0 * C + tc * 8, a0); ld8(y, r0 * C + tc * 8, b0);
+    if (r1 < rend) { ld8(dy, r1 * C + tc * 8, a1); ld8(y, r1 * C + tc * 8, b1); }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t r = u ? r1 : r0;
+      if (r >= rend) break;
+      const int s = sg.of(r);
+      if (s != cur) {
+        if (cur >= 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { abs_sm[((size_t)tr * 4 + cur) * C + tc * 8 + j] += acc[j]; acc[j] = 0.f; }
+        }
+        cur = s;
+      }
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[j] = (u ? a1[j] : a0[j]) * act_grad_from_y_t<ACT>(u ? b1[j] : b0[j], alpha);
+        acc[j] += o[j];
+      }
+      st8(du, r * C + tc * 8, o);
+    }
+  }
+  if (cur >= 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) abs_sm[((size_t)tr * 4 + cur) * C + tc * 8 + j] += acc[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * C; i += 256) {
+    float t = 0.f;
+    for (int l = 0; l < rl; ++l) t += abs_sm[(size_t)l * 4 * C + i];
+    partials[(size_t)blockIdx.x * 4 * C + i] = t;
+  }
+}
+// 256 threads = 32 channels x 8 part lanes; fixed summation order -> deterministic
+__global__ void __launch_bounds__(256) act_bwd_seg_fold_kernel(const float* __restrict__ partials, int nparts, int C,
+                                                               float* __restrict__ colsums, float* __restrict__ grad_acc) {
+  __shared__ double sm[8][4][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, c = blockIdx.x * 32 + tx;
+  double t[4] = {0.0, 0.0, 0.0, 0.0};
+  if (c < C)
+    for (int p = ty; p < nparts; p += 8)
+#pragma unroll
+      for (int a = 0; a < 4; ++a) t[a] += (double)partials[((size_t)p * 4 + a) * C + c];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) sm[ty][a][tx] = t[a];
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    double tot = 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      double u = 0.0;
+#pragma unroll
+      for (int l = 0; l < 8; ++l) u += sm[l][a][tx];
+      colsums[a * C + c] = (float)u;
+      tot += u;
+    }
+    if (grad_acc) grad_acc[c] = (float)((double)grad_acc[c] + tot);
+  }
+}
+
 // dz = du - colsums[seg] / rows_seg  (bf16, C % 8 == 0), in place allowed
 __global__ void sub_mean_seg_kernel(const bf16* __restrict__ du, bf16* __restrict__ dz, int64_t nvec, int C,
                                     const float* __restrict__ colsums, Segs sg) {
@@ -611,6 +699,18 @@ extern "C" int tgan_act_bwd_seg(const void* dy, int dydt, const void* y, int ydt
   Segs sg;
   if (make_segs(sg, rows, nseg, r0, r1, r2)) return 1;
   bool v = (C % 4 == 0) && aligned16(dy) && aligned16(y) && aligned16(du);
+  if (dydt == TGAN_BF16 && ydt == TGAN_BF16 && dudt == TGAN_BF16 && v && C % 8 == 0 && 2048 % C == 0 && C >= 64 &&
+      (act == TGAN_ACT_LRELU || act == TGAN_ACT_RELU || act == TGAN_ACT_NONE)) {
+    const int nparts = TGAN_ACT_BWD_SEG_PARTS;    // 3 CTAs per SM; ws holds nparts * 4 * C floats
+    const size_t smem = (size_t)(2048 / C) * 4 * C * sizeof(float);      // 32 KB
+    cudaStream_t st = (cudaStream_t)stream;
+    TGAN_DISPATCH_ACT(act, A, (act_bwd_seg_v8_kernel<A><<<nparts, 256, smem, st>>>(
+                                  (const bf16*)dy, (const bf16*)y, (bf16*)du, rows, C, sg, alpha, ws)));
+    TGAN_LAUNCHED();
+    act_bwd_seg_fold_kernel<<<ceil_div(C, 32), 256, 0, st>>>(ws, nparts, C, colsums, grad_acc);
+    TGAN_LAUNCHED();
+    return 0;
+  }
   TGAN_DISPATCH_1(dydt, TDY, TGAN_DISPATCH_1(ydt, TY, TGAN_DISPATCH_1(dudt, TDU, {
     TGAN_DISPATCH_ACT(act, A, {
       ActBwdSegF<TDY, TY, TDU, 1, A> f1{(const TDY*)dy, (const TY*)y, (TDU*)du, C, alpha, sg};
