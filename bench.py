@@ -22,7 +22,14 @@ for _p in (ROOT, os.path.join(ROOT, 'tensorflow-implementation-of-triple-gan_b20
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
-STEP_TFLOP = 1.465          # algorithmic dense-contraction FLOPs of one CIFAR-10 step, x1e12
+# algorithmic dense-contraction FLOPs of one step, x1e12; the default workload is the north-star one
+STEP_TFLOPS = {'cifar10': 1.465, 'svhn': 1.295, 'mnist': 0.0511}
+WORKLOADS = {
+    'cifar10': 'CIFAR-10 32x32x3 Triple-GAN (Good_GAN_cifar10: WN 9-layer conv C + conv D + deconv G), one D+G+C training '
+               'step, batch 100 per GPU (G 100, L_C 50, U_C 50, L_D 20, U_D 80)',
+    'svhn': 'SVHN 32x32x3 Triple-GAN (Good_GAN), one D+G+C training step, batch 100 per GPU',
+    'mnist': 'MNIST 28x28x1 Triple-GAN (Good_GAN), one D+G+C training step, batch 100 per GPU'}
+STEP_TFLOP = STEP_TFLOPS['cifar10']
 IMAGES_PER_STEP = 100
 
 
@@ -177,6 +184,8 @@ def main():
     ap.add_argument('--math', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='cifar10', choices=sorted(WORKLOADS),
+                    help='cifar10 = the north-star configuration; svhn / mnist = BASELINE.json configs[1] / configs[0]')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -195,7 +204,8 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     tgan.init('cuda:%d' % local, math=args.math, seed=1234 + rank)
-    tr = tgan.make_trainer('cifar10', zca=synthetic.make_zca(1234), seed=1234)
+    wl = args.workload
+    tr = tgan.make_trainer(wl, zca=synthetic.make_zca(1234) if wl == 'cifar10' else None, seed=1234)
     batch = {k: torch.from_numpy(v).pin_memory() for k, v in synthetic.make_batch(tr.config, 1234 + rank).items()}
     h2d = sum(v.numel() * v.element_size() for v in batch.values())
     tr.load_batch(batch)
@@ -259,11 +269,10 @@ def main():
     imgs = IMAGES_PER_STEP * world * args.steps
     value = imgs / t_dev
     out = {
-        'metric': 'CIFAR-10 Triple-GAN train images/sec', 'value': value, 'unit': 'images/s', 'n_gpus': world,
+        'metric': ('CIFAR-10' if wl == 'cifar10' else wl.upper()) + ' Triple-GAN train images/sec', 'value': value, 'unit': 'images/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': t_dev / args.steps * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16' if args.math == 'bf16' else 'f32', 'data': 'synthetic',
-        'config': {'workload': 'CIFAR-10 32x32x3 Triple-GAN (Good_GAN_cifar10: WN 9-layer conv C + conv D + deconv G), '
-                               'one D+G+C training step, batch 100 per GPU (G 100, L_C 50, U_C 50, L_D 20, U_D 80)',
+        'config': {'workload': WORKLOADS[wl],
                    'global_batch': IMAGES_PER_STEP * world, 'parallelism': 'dp%d' % world,
                    'cuda_graph': graph,
                    'l2': 'no explicit flush: one step streams > 1 GB of activations (>> 126 MB L2) between reuses'},
@@ -271,12 +280,12 @@ def main():
                 'ms_per_step': t_e2e / args.steps * 1e3},
         'gpu_launches': int(launches),
         'clocks': clocks,
-        'step_tensor_frac': STEP_TFLOP * 1e12 * world * args.steps / t_dev / (pk['bf16_sustained'] * 1e12 * world),
+        'step_tensor_frac': STEP_TFLOPS[wl] * 1e12 * world * args.steps / t_dev / (pk['bf16_sustained'] * 1e12 * world),
         'losses': [float(x) for x in last],
     }
     if args.math == 'bf16':
         out['roofline'] = dominant_kernel_roofline(torch, tgan, pk)
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and wl == 'cifar10':
         t, n = cpu_step_time(4, 2, 1)
         out['cpu_baseline'] = {'value': n / t, 'unit': 'images/s', 'cores': os.cpu_count(), 'kind': 'port',
                                'sample': 'CIFAR-10 step at 1/4 of the batch tuple (%d images/step), 2 timed steps, '
