@@ -114,6 +114,7 @@ struct IgParams {
   // [ctap0[c], ctap0[c] + cT[c]) of dy/dx/the packed weights and writes at output offset (cooy[c], coox[c])
   int ncls, cT[4], ctap0[4], cooy[4], coox[4];
   int halo, halo_rows, halo_dy0;   // row-halo mode: box rows (2*th + 2), smallest dy
+  int nbox;                        // 128-pixel boxes per tile: 2 (UMMA N = 256), or 1 when that leaves SMs without a tile
   int dbg;   // experiments only (TGAN_IGEMM_DBG): 1 skip activation loads, 2 skip weight loads, 4 skip stores,
              // 8 skip the epilogue body, 16 skip the smem-ring handshakes
 };
@@ -320,7 +321,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       int x0[2], y0[2], n0[2];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const int mt = 2 * pp + h;       // mt >= m_tiles -> image index >= N -> the box is zero-filled
+        const int mt = p.nbox * pp + h;  // mt >= m_tiles -> image index >= N -> the box is zero-filled
         int t2, txx, tyy, ngg;
         p.d_tiles_x.divmod(mt, t2, txx);
         p.d_tiles_y.divmod(t2, ngg, tyy);
@@ -335,11 +336,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
           mbar_wait(&empty[stage], phase ^ 1);
           if (elect_one()) {
             uint8_t* s = smem + (size_t)stage * IG_STAGE_BYTES;
-            mbar_arrive_expect_tx(&full[stage], ((p.dbg & 2) ? 0u : (uint32_t)W_STAGE_BYTES) + ((p.dbg & 1) ? 0u : 2u * P_TILE_BYTES));
+            mbar_arrive_expect_tx(&full[stage], ((p.dbg & 2) ? 0u : (uint32_t)W_STAGE_BYTES) +
+                                                    ((p.dbg & 1) ? 0u : (uint32_t)p.nbox * P_TILE_BYTES));
             if (!(p.dbg & 2)) tma_load_3d(s, &tmW, &full[stage], kc * 64, ct * 128, t);
             if (!(p.dbg & 1)) {
               tma_load_4d(s + W_STAGE_BYTES, &tmX, &full[stage], kc * 64, x0[0] + ddx, y0[0] + ddy, n0[0]);
-              tma_load_4d(s + W_STAGE_BYTES + P_TILE_BYTES, &tmX, &full[stage], kc * 64, x0[1] + ddx, y0[1] + ddy, n0[1]);
+              if (p.nbox == 2)
+                tma_load_4d(s + W_STAGE_BYTES + P_TILE_BYTES, &tmX, &full[stage], kc * 64, x0[1] + ddx, y0[1] + ddy, n0[1]);
             }
           }
           __syncwarp();
@@ -348,7 +351,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = umma_idesc_bf16(128, IG_NPIX, 0, 0);
+    const uint32_t idesc = umma_idesc_bf16(128, 128 * p.nbox, 0, 0);
     // K-major SWIZZLE_128B descriptor: LBO field 1 (unused), SBO = 1024 B (8 rows), version 1, layout 2
     const uint64_t desc_hi = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
     const uint32_t s_base = smem_u32(smem) >> 4;
@@ -405,8 +408,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       float csum[4] = {0.f, 0.f, 0.f, 0.f};
       mbar_wait(&tfull[acc], accphase);
       tc_fence_after();
-      for (int h = 0; h < 2; ++h) {
-        const int mt = 2 * pp + h;
+      for (int h = 0; h < p.nbox; ++h) {
+        const int mt = p.nbox * pp + h;
         if (mt >= p.m_tiles || (p.dbg & 8)) break;
         int t2, tx, ty, ng;
         p.d_tiles_x.divmod(mt, t2, tx);
@@ -721,6 +724,7 @@ extern "C" int tgan_igemm_bf16(const tgan_igemm_args* a, void* stream) {
   p.N = a->N; p.sy = sy; p.sx = sx;
   p.tiles_y = ceil_div(a->gh, p.th); p.tiles_x = ceil_div(a->gw, p.tw);
   p.m_tiles = ceil_div(a->N, p.nb) * p.tiles_y * p.tiles_x;
+  p.nbox = 2;
   p.pp_tiles = ceil_div(p.m_tiles, 2);
   p.ct_tiles = ceil_div(a->Nout, 128);
   p.T = a->T; p.kchunks = ceil_div(a->C, 64);
@@ -753,10 +757,13 @@ extern "C" int tgan_igemm_bf16(const tgan_igemm_args* a, void* stream) {
     p.cT[0] = a->T; p.ctap0[0] = 0; p.cooy[0] = p.ooy; p.coox[0] = p.oox;
   }
 
+  // small problems: with 256-pixel tiles fewer than 148 CTAs would have work, and an N = 128 MMA runs at the same rate
+  if (2 * p.pp_tiles * p.ct_tiles * p.ncls <= 148 && p.m_tiles > 1) { p.nbox = 1; p.pp_tiles = p.m_tiles; }   // still one wave
+  { const char* e = getenv("TGAN_IGEMM_NBOX"); if (e && atoi(e) == 2) { p.nbox = 2; p.pp_tiles = ceil_div(p.m_tiles, 2); } }
   // row-halo eligibility: a full 3x3 tap grid (row-major, unit steps), stride 1, one class, full-width tiles of one image
   // whose two 128-pixel boxes are vertically adjacent
   p.halo = 0;
-  if (a->T == 9 && sy == 1 && sx == 1 && p.ncls == 1 && p.nb == 1 && p.tiles_x == 1 && p.tiles_y % 2 == 0 && p.tw >= 8 &&
+  if (p.nbox == 2 && a->T == 9 && sy == 1 && sx == 1 && p.ncls == 1 && p.nb == 1 && p.tiles_x == 1 && p.tiles_y % 2 == 0 && p.tw >= 8 &&
       (2 * p.th + 2) * p.tw * 128 <= HALO_A_SLOT_BYTES) {
     bool grid = true;
     const int sr = a->dy[3] - a->dy[0], sc = a->dx[1] - a->dx[0];
