@@ -16,6 +16,7 @@ __device__ unsigned int g_colreduce_ticket[1024];   // zero at load; the last CT
 template <int NACC, int VEC, typename F>
 __global__ void __launch_bounds__(256) colreduce_kernel(F f, int64_t rows, int C, double* __restrict__ partials,
                                                         float* o0, float* o1, float beta, float* acc0, int segmode) {
+  pdl_entry();
   constexpr int CL = VEC == 4 ? 8 : 32, RL = 256 / CL;
   __shared__ double sm[RL][NACC][33];
   __shared__ bool is_last;
@@ -108,8 +109,8 @@ static int run_colreduce(F1 f1, F4 f4, bool vec_ok, int64_t rows, int C, float* 
   int parts = pick_parts(rows, C, vec);
   dim3 grid(ceil_div(C, 32), parts);
   double* wsd = reinterpret_cast<double*>(ws);       // fp64 partials: the first 4*MAX_PARTS*C floats of ws
-  if (vec_ok) colreduce_kernel<NACC, 4, F4><<<grid, 256, 0, st>>>(f4, rows, C, wsd, o0, o1, beta, acc0, segmode);
-  else colreduce_kernel<NACC, 1, F1><<<grid, 256, 0, st>>>(f1, rows, C, wsd, o0, o1, beta, acc0, segmode);
+  if (vec_ok) pdl_launch(colreduce_kernel<NACC, 4, F4>, grid, 256, 0, (cudaStream_t)(st), f4, rows, C, wsd, o0, o1, beta, acc0, segmode);
+  else pdl_launch(colreduce_kernel<NACC, 1, F1>, grid, 256, 0, (cudaStream_t)(st), f1, rows, C, wsd, o0, o1, beta, acc0, segmode);
   TGAN_LAUNCHED();
   return 0;
 }

@@ -35,6 +35,25 @@ extern std::atomic<int64_t> g_launches;
 
 typedef __nv_bfloat16 bf16;
 
+// Programmatic dependent launch: every kernel of the library is launched with the programmatic-stream-serialization
+// attribute and starts with pdl_entry(): it lets its successor begin launching (block scheduling, prologue) while this grid
+// is still running, then waits until its own predecessor has completed and flushed before touching global memory.  The
+// step is ~350 back-to-back launches, many of them a few microseconds long, so launch latency is a visible share of it.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_entry() { pdl_trigger(); pdl_wait(); }
+extern int g_use_pdl;      // TGAN_NO_PDL=1 disables the attribute (plain stream order)
+template <typename... KArgs, typename... Args>
+inline cudaError_t pdl_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 template <typename T> __device__ __forceinline__ float ldf(const T* p, int64_t i);
 template <> __device__ __forceinline__ float ldf<float>(const float* p, int64_t i) { return p[i]; }
 template <> __device__ __forceinline__ float ldf<bf16>(const bf16* p, int64_t i) { return __bfloat162float(p[i]); }

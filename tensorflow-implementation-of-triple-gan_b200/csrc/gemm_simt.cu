@@ -12,6 +12,7 @@ template <bool TA, bool TB>
 __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A,
                                                     int lda, const float* __restrict__ B, int ldb, float beta,
                                                     float* __restrict__ C, int ldc, int kper, float* __restrict__ ws) {
+  pdl_entry();
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
   const int tid = threadIdx.x;
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, float a
 
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, int M, int N, float alpha, float beta,
                                      float* __restrict__ C, int ldc) {
+  pdl_entry();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)M * N) return;
   float s = 0.f;
@@ -82,6 +84,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, i
 template <typename T>
 __global__ void im2col_kernel(const T* __restrict__ x, int N, int H, int W, int C, int ldx, int kh, int kw, int sh,
                               int sw, int pt, int pl, int Ho, int Wo, float* __restrict__ col, int64_t total) {
+  pdl_entry();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   int c = (int)(i % C);
@@ -105,6 +108,7 @@ template <typename T>
 __global__ void __launch_bounds__(128) im2col_bf16_kernel(const T* __restrict__ x, int N, int H, int W, int C, int ldx,
                                                           int kh, int kw, int sh, int sw, int pt, int pl, int Ho, int Wo,
                                                           bf16* __restrict__ col, int ldc, int64_t rows) {
+  pdl_entry();
   extern __shared__ uint32_t im2col_sm[];
   const int pitch = ldc / 2 + 1;                       // 32-bit words per row, odd (ldc % 8 == 0)
   bf16* srow = reinterpret_cast<bf16*>(im2col_sm + (size_t)threadIdx.x * pitch);
@@ -139,6 +143,7 @@ template <typename T>
 __global__ void col2im_kernel(const float* __restrict__ col, int N, int H, int W, int C, int kh, int kw, int sh,
                               int sw, int pt, int pl, int Ho, int Wo, T* __restrict__ x, int Cx, int ldx,
                               int64_t total) {
+  pdl_entry();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   int c = (int)(i % Cx);
@@ -179,7 +184,7 @@ extern "C" int tgan_sgemm(int transA, int transB, int M, int N, int K, float alp
   dim3 grid(ceil_div(N, BN), ceil_div(M, BM), splits);
   cudaStream_t st = (cudaStream_t)stream;
   float* w = splits > 1 ? ws : nullptr;
-#define L(TA, TB) sgemm_kernel<TA, TB><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, kper, w)
+#define L(TA, TB) pdl_launch(sgemm_kernel<TA, TB>, grid, 256, 0, (cudaStream_t)(st), M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, kper, w)
   if (!transA && !transB) L(false, false);
   else if (!transA && transB) L(false, true);
   else if (transA && !transB) L(true, false);
@@ -188,7 +193,7 @@ extern "C" int tgan_sgemm(int transA, int transB, int M, int N, int K, float alp
   TGAN_LAUNCHED();
   if (splits > 1) {
     int64_t tot = (int64_t)M * N;
-    splitk_reduce_kernel<<<ceil_div(tot, 256), 256, 0, st>>>(ws, splits, M, N, alpha, beta, C, ldc);
+    pdl_launch(splitk_reduce_kernel, ceil_div(tot, 256), 256, 0, (cudaStream_t)(st), ws, splits, M, N, alpha, beta, C, ldc);
     TGAN_LAUNCHED();
   }
   return 0;
@@ -199,8 +204,7 @@ extern "C" int tgan_im2col(const void* x, int xdt, int N, int H, int W, int C, i
   TGAN_CHECK_ARG(x && col, "im2col: null pointer");
   int64_t total = (int64_t)N * Ho * Wo * kh * kw * C;
   TGAN_CHECK_ARG(total > 0, "im2col: empty");
-  TGAN_DISPATCH_1(xdt, T, (im2col_kernel<T><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
-                              (const T*)x, N, H, W, C, ldx, kh, kw, sh, sw, pt, pl, Ho, Wo, col, total)));
+  TGAN_DISPATCH_1(xdt, T, (pdl_launch(im2col_kernel<T>, ceil_div(total, 256), 256, 0, (cudaStream_t)((cudaStream_t)stream), (const T*)x, N, H, W, C, ldx, kh, kw, sh, sw, pt, pl, Ho, Wo, col, total)));
   TGAN_LAUNCHED();
   return 0;
 }
@@ -217,8 +221,7 @@ extern "C" int tgan_im2col_bf16(const void* x, int xdt, int N, int H, int W, int
       cudaFuncSetAttribute(im2col_bf16_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024);
       attr = true;
     }
-    im2col_bf16_kernel<T><<<ceil_div(rows, 128), 128, smem, (cudaStream_t)stream>>>(
-        (const T*)x, N, H, W, C, ldx, kh, kw, sh, sw, pt, pl, Ho, Wo, (bf16*)col, ldc, rows);
+    pdl_launch(im2col_bf16_kernel<T>, ceil_div(rows, 128), 128, smem, (cudaStream_t)((cudaStream_t)stream), (const T*)x, N, H, W, C, ldx, kh, kw, sh, sw, pt, pl, Ho, Wo, (bf16*)col, ldc, rows);
   });
   TGAN_LAUNCHED();
   return 0;
@@ -230,8 +233,7 @@ extern "C" int tgan_col2im(const float* col, int N, int H, int W, int C, int kh,
   TGAN_CHECK_ARG(Cx <= C && Cx <= ldx, "col2im: bad channel slice");
   int64_t total = (int64_t)N * H * W * Cx;
   TGAN_CHECK_ARG(total > 0, "col2im: empty");
-  TGAN_DISPATCH_1(xdt, T, (col2im_kernel<T><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
-                              col, N, H, W, C, kh, kw, sh, sw, pt, pl, Ho, Wo, (T*)x, Cx, ldx, total)));
+  TGAN_DISPATCH_1(xdt, T, (pdl_launch(col2im_kernel<T>, ceil_div(total, 256), 256, 0, (cudaStream_t)((cudaStream_t)stream), col, N, H, W, C, kh, kw, sh, sw, pt, pl, Ho, Wo, (T*)x, Cx, ldx, total)));
   TGAN_LAUNCHED();
   return 0;
 }

@@ -200,6 +200,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
              const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
              const __grid_constant__ CUtensorMap tmO2, const __grid_constant__ CUtensorMap tmO3,
              const __grid_constant__ IgParams p) {
+  pdl_trigger();      // the wait sits after the prologue (barriers, TMEM allocation, descriptor prefetch)
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by OFFSET (pointer arithmetic on the __shared__ array keeps the address space, so the epilogue's
   // staging stores compile to STS instead of generic stores)
@@ -232,6 +233,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
 
   const int tiles_per_cls = p.pp_tiles * p.ct_tiles;
@@ -525,6 +527,7 @@ struct WgParams {
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorMap tmX,
              const __grid_constant__ WgParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by OFFSET (pointer arithmetic on the __shared__ array keeps the address space, so the epilogue's
   // staging stores compile to STS instead of generic stores)
@@ -563,6 +566,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ C
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -674,6 +678,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ C
 // dw[i] = beta*dw[i] + sum_splits ws[s][i]  (i over [T][Cin][Cout], same layout in and out -> fully coalesced)
 __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int64_t tot, int64_t tot_store,
                                     float* __restrict__ dw, float beta) {
+  pdl_entry();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot_store; i += (int64_t)gridDim.x * blockDim.x) {
     float s = 0.f;
     for (int z = 0; z < splits; ++z) s += ws[z * tot + i];
@@ -685,6 +690,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, in
 __global__ void pack_weight_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int T, int Nr, int K,
                                    int Kpad, int64_t st, int64_t sn, int64_t sk, const int* __restrict__ taps,
                                    int64_t total) {
+  pdl_entry();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int k = (int)(i % Kpad);
@@ -817,7 +823,7 @@ extern "C" int tgan_igemm_bf16(const tgan_igemm_args* a, void* stream) {
   p.d_ct.set(p.ct_tiles); p.d_tpc.set(p.pp_tiles * p.ct_tiles);
   const int total = p.pp_tiles * p.ct_tiles * p.ncls;
   const int grid = total < 148 ? total : 148;
-  igemm_kernel<<<grid, IG_THREADS, smem_bytes, (cudaStream_t)stream>>>(tmX, tmW, tmXh, tmO[0], tmO[1], tmO[2], tmO[3], p);
+  pdl_launch(igemm_kernel, grid, IG_THREADS, smem_bytes, (cudaStream_t)((cudaStream_t)stream), tmX, tmW, tmXh, tmO[0], tmO[1], tmO[2], tmO[3], p);
   TGAN_LAUNCHED();
   return 0;
 }
@@ -928,14 +934,14 @@ extern "C" int tgan_wgrad_bf16(const tgan_wgrad_args* a, void* stream) {
   const size_t stage_bytes = wg_stage_bytes(p);
   const size_t smem_bytes = 1024 + p.stages * stage_bytes + 256;
   const int grid = p.co_tiles * p.ci_tiles * p.tap_groups * p.splits;
-  wgrad_kernel<<<grid, WG_THREADS, smem_bytes, (cudaStream_t)stream>>>(tmDz, tmX, p);
+  pdl_launch(wgrad_kernel, grid, WG_THREADS, smem_bytes, (cudaStream_t)((cudaStream_t)stream), tmDz, tmX, p);
   TGAN_LAUNCHED();
   const int64_t tot = (int64_t)a->T * a->Cout * a->Cin;
   TGAN_CHECK_ARG(a->cin_store == 0 || (a->T == 1 && a->cin_store <= a->Cin), "wgrad: cin_store needs T == 1");
   const int64_t tot_store = a->cin_store > 0 ? (int64_t)a->cin_store * a->Cout : tot;
   int rg = ceil_div(tot_store, 256);
   if (rg > 148 * 8) rg = 148 * 8;
-  wgrad_reduce_kernel<<<rg, 256, 0, (cudaStream_t)stream>>>(a->ws, p.splits, tot, tot_store, a->dw, a->beta);
+  pdl_launch(wgrad_reduce_kernel, rg, 256, 0, (cudaStream_t)((cudaStream_t)stream), a->ws, p.splits, tot, tot_store, a->dw, a->beta);
   TGAN_LAUNCHED();
   return 0;
 }
@@ -944,7 +950,7 @@ extern "C" int tgan_pack_weight_bf16(const float* src, void* dst, int T, int Nro
                                      int64_t sn, int64_t sk, const int* taps_dev, void* stream) {
   TGAN_CHECK_ARG(src && dst && T >= 1 && Nrows >= 1 && K >= 1 && Kpad >= K && Kpad % 8 == 0, "pack_weight: bad args");
   const int64_t total = (int64_t)T * Nrows * Kpad;
-  pack_weight_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, T, Nrows, K, Kpad, st, sn,
+  pdl_launch(pack_weight_kernel, ceil_div(total, 256), 256, 0, (cudaStream_t)((cudaStream_t)stream), src, (bf16*)dst, T, Nrows, K, Kpad, st, sn,
                                                                             sk, taps_dev, total);
   TGAN_LAUNCHED();
   return 0;

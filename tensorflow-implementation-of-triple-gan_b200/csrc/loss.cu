@@ -27,6 +27,7 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 
 __global__ void __launch_bounds__(LT) loss_d_kernel(const float* dr, int nr, const float* df, int nf, const float* du,
                                                     int nu, float* loss, float* g_dr, float* g_df, float* g_du) {
+  pdl_entry();
   __shared__ float sm[32];
   float a = 0.f, b = 0.f, c = 0.f;
   for (int i = threadIdx.x; i < nr; i += LT) { float x = dr[i]; a += sig_ce(x, 1.f); if (g_dr) g_dr[i] = (sigmoidf_(x) - 1.f) / nr; }
@@ -37,6 +38,7 @@ __global__ void __launch_bounds__(LT) loss_d_kernel(const float* dr, int nr, con
 }
 
 __global__ void __launch_bounds__(LT) loss_g_kernel(const float* df, int nf, float* loss, float* g_df) {
+  pdl_entry();
   __shared__ float sm[32];
   float a = 0.f;
   for (int i = threadIdx.x; i < nf; i += LT) { float x = df[i]; a += sig_ce(x, 1.f); if (g_df) g_df[i] = 0.5f * (sigmoidf_(x) - 1.f) / nf; }
@@ -61,6 +63,7 @@ loss_c_kernel(const float* __restrict__ c_real, const float* __restrict__ y_l_c,
               int n_unl, const float* __restrict__ c_fake, const float* __restrict__ y_g, int n_fake, int K,
               const float* __restrict__ lambdas, float* loss, float* g_real, float* g_unl, float* g_rep,
               float* g_fake) {
+  pdl_entry();
   __shared__ float sm[32];
   __shared__ float q[MAXK];
   const float lambda_1 = lambdas[0], lambda_2 = lambdas[1];
@@ -142,13 +145,13 @@ using namespace tgan;
 extern "C" int tgan_loss_d(const float* dr, int nr, const float* df, int nf, const float* du, int nu, float* loss,
                            float* g_dr, float* g_df, float* g_du, void* stream) {
   TGAN_CHECK_ARG(dr && df && du && loss && nr > 0 && nf > 0 && nu > 0, "loss_d: bad args");
-  loss_d_kernel<<<1, LT, 0, (cudaStream_t)stream>>>(dr, nr, df, nf, du, nu, loss, g_dr, g_df, g_du);
+  pdl_launch(loss_d_kernel, 1, LT, 0, (cudaStream_t)((cudaStream_t)stream), dr, nr, df, nf, du, nu, loss, g_dr, g_df, g_du);
   TGAN_LAUNCHED();
   return 0;
 }
 extern "C" int tgan_loss_g(const float* df, int nf, float* loss, float* g_df, void* stream) {
   TGAN_CHECK_ARG(df && loss && nf > 0, "loss_g: bad args");
-  loss_g_kernel<<<1, LT, 0, (cudaStream_t)stream>>>(df, nf, loss, g_df);
+  pdl_launch(loss_g_kernel, 1, LT, 0, (cudaStream_t)((cudaStream_t)stream), df, nf, loss, g_df);
   TGAN_LAUNCHED();
   return 0;
 }
@@ -158,7 +161,7 @@ extern "C" int tgan_loss_c(const float* c_real, const float* y_l_c, int n_real, 
                            float* g_fake, void* stream) {
   TGAN_CHECK_ARG(c_real && y_l_c && c_unl && d_unl_logits && c_fake && y_g && lambdas && loss, "loss_c: null pointer");
   TGAN_CHECK_ARG(K > 0 && K <= MAXK && n_real > 0 && n_unl > 0 && n_fake > 0, "loss_c: bad sizes (K <= %d)", MAXK);
-  loss_c_kernel<<<1, LT, 0, (cudaStream_t)stream>>>(c_real, y_l_c, n_real, c_unl, c_rep, d_unl_logits, n_unl, c_fake,
+  pdl_launch(loss_c_kernel, 1, LT, 0, (cudaStream_t)((cudaStream_t)stream), c_real, y_l_c, n_real, c_unl, c_rep, d_unl_logits, n_unl, c_fake,
                                                     y_g, n_fake, K, lambdas, loss, g_real, g_unl, g_rep, g_fake);
   TGAN_LAUNCHED();
   return 0;

@@ -31,6 +31,7 @@ constexpr int WN_SPLITS = 16;      // row ranges per tensor (CTAs along blockIdx
 
 __global__ void __launch_bounds__(256) wn_fwd_part_kernel(const tgan_wn_desc* __restrict__ descs, float* __restrict__ part,
                                                           int max_co) {
+  pdl_entry();
   const tgan_wn_desc d = descs[blockIdx.y];
   const int c0 = blockIdx.x * 32;
   if (c0 >= d.Co) return;
@@ -48,6 +49,7 @@ __global__ void __launch_bounds__(256) wn_fwd_part_kernel(const tgan_wn_desc* __
   if (ty == 0 && co < d.Co) part[((int64_t)blockIdx.y * WN_SPLITS + blockIdx.z) * max_co + co] = s;
 }
 __global__ void wn_fwd_final_kernel(const tgan_wn_desc* __restrict__ descs, const float* __restrict__ part, int max_co) {
+  pdl_entry();
   const tgan_wn_desc d = descs[blockIdx.y];
   const int co = blockIdx.x * blockDim.x + threadIdx.x;
   if (co >= d.Co) return;
@@ -63,6 +65,7 @@ __global__ void wn_fwd_final_kernel(const tgan_wn_desc* __restrict__ descs, cons
 // WN_SPLITS CTAs: (1) partial dots per row range, (2) fold the partials in a fixed order and apply over the same range.
 __global__ void __launch_bounds__(256) wn_bwd_dot_kernel(const tgan_wn_desc* __restrict__ descs, float* __restrict__ part,
                                                          int max_co) {
+  pdl_entry();
   const tgan_wn_desc d = descs[blockIdx.y];
   const int c0 = blockIdx.x * 32;
   if (c0 >= d.Co) return;
@@ -82,6 +85,7 @@ __global__ void __launch_bounds__(256) wn_bwd_dot_kernel(const tgan_wn_desc* __r
 
 __global__ void __launch_bounds__(256) wn_bwd_apply_kernel(const tgan_wn_desc* __restrict__ descs,
                                                            const float* __restrict__ part, int max_co) {
+  pdl_entry();
   const tgan_wn_desc d = descs[blockIdx.y];
   const int c0 = blockIdx.x * 32;
   if (c0 >= d.Co) return;
@@ -104,6 +108,7 @@ __global__ void __launch_bounds__(256) wn_bwd_apply_kernel(const tgan_wn_desc* _
 // source strides is 1 in every layout the step uses; when it is the n stride the tile is transposed through shared
 // memory so that both the fp32 reads and the bf16 writes are coalesced.
 __global__ void __launch_bounds__(256) pack_multi_kernel(const tgan_pack_desc* __restrict__ descs) {
+  pdl_entry();
   const tgan_pack_desc d = descs[blockIdx.y];
   __shared__ float sm[32][33];
   const int nbk = (d.Kpad + 31) / 32, nbn = (d.Nr + 31) / 32;
@@ -162,9 +167,9 @@ extern "C" int tgan_sizeof_pack_desc(void) { return (int)sizeof(tgan_pack_desc);
 
 extern "C" int tgan_weightnorm_fwd_multi(const tgan_wn_desc* descs_dev, int n, int max_co, float* ws, void* stream) {
   TGAN_CHECK_ARG(descs_dev && ws && n > 0 && max_co > 0, "weightnorm_fwd_multi: bad args");
-  wn_fwd_part_kernel<<<dim3(ceil_div(max_co, 32), n, WN_SPLITS), 256, 0, (cudaStream_t)stream>>>(descs_dev, ws, max_co);
+  pdl_launch(wn_fwd_part_kernel, dim3(ceil_div(max_co, 32), n, WN_SPLITS), 256, 0, (cudaStream_t)((cudaStream_t)stream), descs_dev, ws, max_co);
   TGAN_LAUNCHED();
-  wn_fwd_final_kernel<<<dim3(ceil_div(max_co, 128), n), 128, 0, (cudaStream_t)stream>>>(descs_dev, ws, max_co);
+  pdl_launch(wn_fwd_final_kernel, dim3(ceil_div(max_co, 128), n), 128, 0, (cudaStream_t)((cudaStream_t)stream), descs_dev, ws, max_co);
   TGAN_LAUNCHED();
   return 0;
 }
@@ -172,15 +177,15 @@ extern "C" int64_t tgan_weightnorm_bwd_multi_ws_floats(int n, int max_co) { retu
 extern "C" int tgan_weightnorm_bwd_multi(const tgan_wn_desc* descs_dev, int n, int max_co, float* ws, void* stream) {
   TGAN_CHECK_ARG(descs_dev && ws && n > 0 && max_co > 0, "weightnorm_bwd_multi: bad args");
   dim3 grid(ceil_div(max_co, 32), n, WN_SPLITS);
-  wn_bwd_dot_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(descs_dev, ws, max_co);
+  pdl_launch(wn_bwd_dot_kernel, grid, 256, 0, (cudaStream_t)((cudaStream_t)stream), descs_dev, ws, max_co);
   TGAN_LAUNCHED();
-  wn_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(descs_dev, ws, max_co);
+  pdl_launch(wn_bwd_apply_kernel, grid, 256, 0, (cudaStream_t)((cudaStream_t)stream), descs_dev, ws, max_co);
   TGAN_LAUNCHED();
   return 0;
 }
 extern "C" int tgan_pack_weight_multi(const tgan_pack_desc* descs_dev, int n, void* stream) {
   TGAN_CHECK_ARG(descs_dev && n > 0, "pack_weight_multi: bad args");
-  pack_multi_kernel<<<dim3(148 * 4, n), 256, 0, (cudaStream_t)stream>>>(descs_dev);
+  pdl_launch(pack_multi_kernel, dim3(148 * 4, n), 256, 0, (cudaStream_t)((cudaStream_t)stream), descs_dev);
   TGAN_LAUNCHED();
   return 0;
 }

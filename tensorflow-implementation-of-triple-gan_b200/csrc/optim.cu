@@ -26,6 +26,7 @@ struct DotF {
 
 __global__ void wn_finalize_kernel(const float* ss, const float* g, int Co, int eps_mode, float* inv_norm,
                                    float* scale) {
+  pdl_entry();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= Co) return;
   float s = ss[c];
@@ -36,12 +37,14 @@ __global__ void wn_finalize_kernel(const float* ss, const float* g, int Co, int 
 // W[a,co,b] = V[a,co,b] * scale[co]
 __global__ void wn_scale_kernel(const float* __restrict__ V, const float* __restrict__ scale, float* __restrict__ W,
                                 int64_t n, int Co, int B) {
+  pdl_entry();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     W[i] = V[i] * scale[(i / B) % Co];
 }
 // generic (B > 1) sum of squares / dot: one CTA per output channel
 __global__ void wn_reduce_generic_kernel(const float* __restrict__ a, const float* __restrict__ b, int A, int Co, int B,
                                          float* __restrict__ out) {
+  pdl_entry();
   __shared__ float sm[32];
   int co = blockIdx.x;
   float s = 0.f;
@@ -59,6 +62,7 @@ __global__ void wn_reduce_generic_kernel(const float* __restrict__ a, const floa
   }
 }
 __global__ void wn_bwd_dg_kernel(const float* dot, const float* inv_norm, float* dg, int Co, float beta) {
+  pdl_entry();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < Co) dg[c] = (beta != 0.f ? beta * dg[c] : 0.f) + dot[c] * inv_norm[c];
 }
@@ -67,6 +71,7 @@ __global__ void wn_bwd_dv_kernel(const float* __restrict__ V, const float* __res
                                  const float* __restrict__ inv_norm, const float* __restrict__ dW,
                                  const float* __restrict__ dot, float* __restrict__ dV, int64_t n, int Co, int B,
                                  float beta) {
+  pdl_entry();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)((i / B) % Co);
     float inv = inv_norm[c];
@@ -78,6 +83,7 @@ __global__ void wn_bwd_dv_kernel(const float* __restrict__ V, const float* __res
 __global__ void adam_kernel(float* __restrict__ theta, float* __restrict__ m, float* __restrict__ v,
                             const float* __restrict__ grad, int64_t n, const float* __restrict__ state, float beta1,
                             float beta2, float eps, float gscale, float* __restrict__ ema, float ema_decay) {
+  pdl_entry();
   const float lr = state[0], b1p = state[1], b2p = state[2];
   const float a = lr * sqrtf(1.f - b2p) / (1.f - b1p);
   int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -115,10 +121,12 @@ __global__ void adam_kernel(float* __restrict__ theta, float* __restrict__ m, fl
   }
 }
 __global__ void adam_advance_kernel(float* state, float beta1, float beta2) {
+  pdl_entry();
   state[1] *= beta1;
   state[2] *= beta2;
 }
-__global__ void counter_advance_kernel(uint64_t* c, uint64_t inc) { *c += inc; }
+__global__ void counter_advance_kernel(uint64_t* c, uint64_t inc) {
+  pdl_entry(); *c += inc; }
 
 static inline int grid_for(int64_t n, int block = 256) {
   int64_t g = (n + block - 1) / block;
@@ -141,14 +149,14 @@ extern "C" int tgan_weightnorm_fwd(const float* V, const float* g, float* W, flo
     int rc = run_colreduce<1>(f1, f4, Co % 4 == 0, A, Co, ss, nullptr, 0.f, ws, st);
     if (rc) return rc;
   } else {
-    wn_reduce_generic_kernel<<<Co, 256, 0, st>>>(V, nullptr, A, Co, B, ss);
+    pdl_launch(wn_reduce_generic_kernel, Co, 256, 0, (cudaStream_t)(st), V, nullptr, A, Co, B, ss);
     TGAN_LAUNCHED();
   }
-  wn_finalize_kernel<<<ceil_div(Co, 128), 128, 0, st>>>(ss, g, Co, eps_mode, inv_norm, scale);
+  pdl_launch(wn_finalize_kernel, ceil_div(Co, 128), 128, 0, (cudaStream_t)(st), ss, g, Co, eps_mode, inv_norm, scale);
   TGAN_LAUNCHED();
   if (W) {
     int64_t n = (int64_t)A * Co * B;
-    wn_scale_kernel<<<grid_for(n), 256, 0, st>>>(V, scale, W, n, Co, B);
+    pdl_launch(wn_scale_kernel, grid_for(n), 256, 0, (cudaStream_t)(st), V, scale, W, n, Co, B);
     TGAN_LAUNCHED();
   }
   return 0;
@@ -165,13 +173,13 @@ extern "C" int tgan_weightnorm_bwd(const float* V, const float* g, const float* 
     int rc = run_colreduce<1>(f1, f4, Co % 4 == 0, A, Co, dot, nullptr, 0.f, ws, st);
     if (rc) return rc;
   } else {
-    wn_reduce_generic_kernel<<<Co, 256, 0, st>>>(dW, V, A, Co, B, dot);
+    pdl_launch(wn_reduce_generic_kernel, Co, 256, 0, (cudaStream_t)(st), dW, V, A, Co, B, dot);
     TGAN_LAUNCHED();
   }
-  wn_bwd_dg_kernel<<<ceil_div(Co, 128), 128, 0, st>>>(dot, inv_norm, dg, Co, beta);
+  pdl_launch(wn_bwd_dg_kernel, ceil_div(Co, 128), 128, 0, (cudaStream_t)(st), dot, inv_norm, dg, Co, beta);
   TGAN_LAUNCHED();
   int64_t n = (int64_t)A * Co * B;
-  wn_bwd_dv_kernel<<<grid_for(n), 256, 0, st>>>(V, g, inv_norm, dW, dot, dV, n, Co, B, beta);
+  pdl_launch(wn_bwd_dv_kernel, grid_for(n), 256, 0, (cudaStream_t)(st), V, g, inv_norm, dW, dot, dV, n, Co, B, beta);
   TGAN_LAUNCHED();
   return 0;
 }
@@ -183,20 +191,20 @@ extern "C" int tgan_adam(float* theta, float* m, float* v, const float* grad, in
   TGAN_CHECK_ARG(((uintptr_t)theta & 15) == 0 && ((uintptr_t)m & 15) == 0 && ((uintptr_t)v & 15) == 0 &&
                      ((uintptr_t)grad & 15) == 0 && (!ema || ((uintptr_t)ema & 15) == 0),
                  "adam: buffers must be 16-byte aligned");
-  adam_kernel<<<grid_for((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(theta, m, v, grad, n, state, beta1, beta2, eps,
+  pdl_launch(adam_kernel, grid_for((n + 3) / 4), 256, 0, (cudaStream_t)((cudaStream_t)stream), theta, m, v, grad, n, state, beta1, beta2, eps,
                                                                        grad_scale, ema, ema_decay);
   TGAN_LAUNCHED();
   return 0;
 }
 extern "C" int tgan_adam_advance(float* state, float beta1, float beta2, void* stream) {
   TGAN_CHECK_ARG(state, "adam_advance: null state");
-  adam_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, beta1, beta2);
+  pdl_launch(adam_advance_kernel, 1, 1, 0, (cudaStream_t)((cudaStream_t)stream), state, beta1, beta2);
   TGAN_LAUNCHED();
   return 0;
 }
 extern "C" int tgan_counter_advance(uint64_t* counter, uint64_t inc, void* stream) {
   TGAN_CHECK_ARG(counter, "counter_advance: null counter");
-  counter_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, inc);
+  pdl_launch(counter_advance_kernel, 1, 1, 0, (cudaStream_t)((cudaStream_t)stream), counter, inc);
   TGAN_LAUNCHED();
   return 0;
 }

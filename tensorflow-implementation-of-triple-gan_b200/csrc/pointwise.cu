@@ -90,6 +90,7 @@ struct BnBwdStatsF {
 __global__ void bn_finalize_kernel(const float* sum, const float* sumsq, float rows, int C, const float* gamma,
                                    const float* beta, float eps, float decay, float* mm, float* mv, float* mean,
                                    float* rstd, float* scale, float* shift) {
+  pdl_entry();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float mu = sum[c] / rows;
@@ -103,6 +104,7 @@ __global__ void bn_finalize_kernel(const float* sum, const float* sumsq, float r
 }
 __global__ void bn_eval_kernel(const float* gamma, const float* beta, const float* mm, const float* mv, float eps,
                                int C, float* scale, float* shift) {
+  pdl_entry();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float sc = gamma[c] * rsqrtf(mv[c] + eps);
@@ -115,6 +117,7 @@ __global__ void bn_eval_kernel(const float* gamma, const float* beta, const floa
 template <typename TX, typename TY, int VEC, int ACT>
 __global__ void affine_act_kernel(const TX* __restrict__ x, TY* __restrict__ y, int64_t nvec, int C,
                                   const float* __restrict__ scale, const float* __restrict__ shift, float alpha) {
+  pdl_entry();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t e = i * VEC;
     int c = (int)(e % C);
@@ -137,6 +140,7 @@ template <typename TX, typename TY, int VEC, int ACT>
 __global__ void mobn_apply_kernel(const TX* __restrict__ x, TY* __restrict__ y, int64_t nvec, int C,
                                   const float* __restrict__ sum, float inv_rows, const float* __restrict__ b,
                                   float* __restrict__ pop_mean, float decay, int train, float alpha) {
+  pdl_entry();
   if (train && pop_mean && blockIdx.x == 0) {
     for (int c = threadIdx.x; c < C; c += blockDim.x)
       pop_mean[c] = pop_mean[c] * decay + sum[c] * inv_rows * (1.f - decay);
@@ -180,6 +184,7 @@ template <int ACT>
 __global__ void mobn_apply_seg_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int64_t nvec, int C,
                                       const float* __restrict__ sums, Segs sg, const float* __restrict__ b,
                                       float* __restrict__ pop_mean, float decay, int train, float alpha) {
+  pdl_entry();
   if (train && pop_mean && blockIdx.x == 0) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       float pm = pop_mean[c];
@@ -215,6 +220,7 @@ template <int ACT>
 __global__ void __launch_bounds__(256) act_bwd_seg_v8_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y,
                                                              bf16* __restrict__ du, int64_t rows, int C, Segs sg,
                                                              float alpha, float* __restrict__ partials) {
+  pdl_entry();
   extern __shared__ float abs_sm[];              // [row lanes][4][C]; every thread owns its (lane, segment, 8 channels) slots
   const int cg = C / 8, rl = 256 / cg;           // channel groups per row, row lanes per CTA
   const int tc = threadIdx.x % cg, tr = threadIdx.x / cg;
@@ -270,6 +276,7 @@ __global__ void __launch_bounds__(256) act_bwd_seg_v8_kernel(const bf16* __restr
 // 256 threads = 32 channels x 8 part lanes; fixed summation order -> deterministic
 __global__ void __launch_bounds__(256) act_bwd_seg_fold_kernel(const float* __restrict__ partials, int nparts, int C,
                                                                float* __restrict__ colsums, float* __restrict__ grad_acc) {
+  pdl_entry();
   __shared__ double sm[8][4][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, c = blockIdx.x * 32 + tx;
   double t[4] = {0.0, 0.0, 0.0, 0.0};
@@ -297,6 +304,7 @@ __global__ void __launch_bounds__(256) act_bwd_seg_fold_kernel(const float* __re
 // dz = du - colsums[seg] / rows_seg  (bf16, C % 8 == 0), in place allowed
 __global__ void sub_mean_seg_kernel(const bf16* __restrict__ du, bf16* __restrict__ dz, int64_t nvec, int C,
                                     const float* __restrict__ colsums, Segs sg) {
+  pdl_entry();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t e = i * 8;
     const int64_t r = e / C;
@@ -317,6 +325,7 @@ __global__ void sub_mean_seg_kernel(const bf16* __restrict__ du, bf16* __restric
 template <typename TA, typename TB, int VEC>
 __global__ void sub_mean_kernel(const TA* __restrict__ du, TB* __restrict__ dz, int64_t nvec, int C,
                                 const float* __restrict__ colsum, float inv_rows) {
+  pdl_entry();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t e = i * VEC;
     int c = (int)(e % C);
@@ -336,6 +345,7 @@ __global__ void bn_bwd_apply_kernel(const TDY* __restrict__ dy, const TX* __rest
                                     int64_t n, int C, const float* __restrict__ mean, const float* __restrict__ rstd,
                                     const float* __restrict__ gamma, const float* __restrict__ s1,
                                     const float* __restrict__ s2, float inv_rows) {
+  pdl_entry();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % C);
     float xh = (ldf<TX>(x, i) - mean[c]) * rstd[c];
@@ -344,6 +354,7 @@ __global__ void bn_bwd_apply_kernel(const TDY* __restrict__ dy, const TX* __rest
   }
 }
 __global__ void add_to_kernel(float* dst, const float* src, int n, float beta) {
+  pdl_entry();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = (beta != 0.f ? beta * dst[i] : 0.f) + src[i];
 }
@@ -361,6 +372,7 @@ template <typename TX, typename TY>
 __global__ void add_noise_kernel(const TX* __restrict__ x, TY* __restrict__ y, int64_t n, float std,
                                  const float* __restrict__ noise, uint64_t seed, uint64_t stream_id,
                                  const uint64_t* __restrict__ counter) {
+  pdl_entry();
   int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 elements
   int64_t e = q * 4;
   if (e >= n) return;
@@ -383,6 +395,7 @@ template <typename TX, typename TY>
 __global__ void dropout_kernel(const TX* __restrict__ x, TY* __restrict__ y, uint8_t* __restrict__ mask, int64_t n,
                                float rate, float scale, int gen, uint64_t seed, uint64_t stream_id,
                                const uint64_t* __restrict__ counter) {
+  pdl_entry();
   int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t e = q * 4;
   if (e >= n) return;
@@ -408,6 +421,7 @@ __global__ void dropout_kernel(const TX* __restrict__ x, TY* __restrict__ y, uin
 template <typename T>
 __global__ void maxpool2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint8_t* __restrict__ idx, int N,
                                     int H, int W, int C, int64_t total) {
+  pdl_entry();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   int c = (int)(i % C);
@@ -428,6 +442,7 @@ __global__ void maxpool2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, 
 template <typename T>
 __global__ void maxpool2_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ idx, T* __restrict__ dx,
                                     int N, int H, int W, int C, int64_t total) {
+  pdl_entry();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   int c = (int)(i % C);
@@ -453,6 +468,7 @@ __global__ void maxpool2_dropout_fwd_kernel(const bf16* __restrict__ x, bf16* __
                                             int H, int W, int C, int64_t nvec, float rate, float scale,
                                             const uint8_t* __restrict__ mask, uint64_t seed, uint64_t stream_id,
                                             const uint64_t* __restrict__ counter) {
+  pdl_entry();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nvec) return;
   const int cv = C / 8, Wo = W / 2, Ho = H / 2;
@@ -499,6 +515,7 @@ __global__ void maxpool2_dropout_fwd_kernel(const bf16* __restrict__ x, bf16* __
 }
 __global__ void maxpool2_dropout_bwd_kernel(const bf16* __restrict__ dy, const uint8_t* __restrict__ code,
                                             bf16* __restrict__ dx, int H, int W, int C, int64_t nvec, float scale) {
+  pdl_entry();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nvec) return;
   const int cv = C / 8, Wo = W / 2, Ho = H / 2;
@@ -527,6 +544,7 @@ __global__ void maxpool2_dropout_bwd_kernel(const bf16* __restrict__ dy, const u
 template <typename TX, typename TY>
 __global__ void global_pool_fwd_kernel(const TX* __restrict__ x, TY* __restrict__ y, uint8_t* __restrict__ idx,
                                        int N, int HW, int C, int mode) {
+  pdl_entry();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * C) return;
   int c = i % C, n = i / C;
@@ -545,6 +563,7 @@ __global__ void global_pool_fwd_kernel(const TX* __restrict__ x, TY* __restrict_
 template <typename TDY, typename TDX>
 __global__ void global_pool_bwd_kernel(const TDY* __restrict__ dy, const uint8_t* __restrict__ idx,
                                        TDX* __restrict__ dx, int N, int HW, int C, int mode, int64_t total) {
+  pdl_entry();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   int c = (int)(i % C);
@@ -560,6 +579,7 @@ template <typename TX, typename TO>
 __global__ void concat_label_kernel(const TX* __restrict__ x, int64_t rows, int C, int ldx,
                                     const float* __restrict__ lab, int K, int rps, TO* __restrict__ out, int ldo,
                                     int64_t total) {
+  pdl_entry();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   int j = (int)(i % ldo);
@@ -574,6 +594,7 @@ __global__ void concat_label_kernel(const TX* __restrict__ x, int64_t rows, int 
 template <typename TO>
 __global__ void fill_label_kernel(const float* __restrict__ lab, int K, int rps, TO* __restrict__ out, int C, int ldo,
                                   int64_t total) {
+  pdl_entry();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int w = ldo - C;
@@ -584,6 +605,7 @@ __global__ void fill_label_kernel(const float* __restrict__ lab, int K, int rps,
 template <typename TS, typename TD>
 __global__ void copy_channels_kernel(const TS* __restrict__ src, int lds, TD* __restrict__ dst, int ldd, int C,
                                      int64_t total) {
+  pdl_entry();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   int j = (int)(i % C);
@@ -592,16 +614,19 @@ __global__ void copy_channels_kernel(const TS* __restrict__ src, int lds, TD* __
 }
 template <typename T>
 __global__ void accumulate_kernel(T* __restrict__ y, const T* __restrict__ x, int64_t n) {
+  pdl_entry();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     stf<T>(y, i, ldf<T>(y, i) + ldf<T>(x, i));
 }
 __global__ void fill_kernel(float* p, float v, int64_t n) {
+  pdl_entry();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     p[i] = v;
 }
 
 __global__ void argmax_onehot_kernel(const float* __restrict__ logits, int N, int K, int64_t* __restrict__ idx,
                                      float* __restrict__ onehot) {
+  pdl_entry();
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const float* p = logits + (int64_t)n * K;
@@ -653,8 +678,8 @@ extern "C" int tgan_mobn_apply(const void* x, int xdt, void* y, int ydt, int64_t
   const float inv = 1.0f / (float)rows;
   DISPATCH_2(xdt, TX, ydt, TY, {
     TGAN_DISPATCH_ACT(act, A, {
-      if (v) mobn_apply_kernel<TX, TY, 4, A><<<grid_for(n / 4), 256, 0, st>>>((const TX*)x, (TY*)y, n / 4, C, sum, inv, b, pop_mean, decay, train, alpha);
-      else mobn_apply_kernel<TX, TY, 1, A><<<grid_for(n), 256, 0, st>>>((const TX*)x, (TY*)y, n, C, sum, inv, b, pop_mean, decay, train, alpha);
+      if (v) pdl_launch(mobn_apply_kernel<TX, TY, 4, A>, grid_for(n / 4), 256, 0, (cudaStream_t)(st), (const TX*)x, (TY*)y, n / 4, C, sum, inv, b, pop_mean, decay, train, alpha);
+      else pdl_launch(mobn_apply_kernel<TX, TY, 1, A>, grid_for(n), 256, 0, (cudaStream_t)(st), (const TX*)x, (TY*)y, n, C, sum, inv, b, pop_mean, decay, train, alpha);
     });
   });
   TGAN_LAUNCHED();
@@ -686,8 +711,7 @@ extern "C" int tgan_mobn_apply_seg(const void* x, void* y, int64_t rows, int C, 
   if (make_segs(sg, rows, nseg, r0, r1, r2)) return 1;
   const int64_t nvec = rows * C / 8;
   cudaStream_t st = (cudaStream_t)stream;
-  TGAN_DISPATCH_ACT(act, A, (mobn_apply_seg_kernel<A><<<grid_for(nvec), 256, 0, st>>>(
-                                (const bf16*)x, (bf16*)y, nvec, C, sums, sg, b, pop_mean, decay, train, alpha)));
+  TGAN_DISPATCH_ACT(act, A, (pdl_launch(mobn_apply_seg_kernel<A>, grid_for(nvec), 256, 0, (cudaStream_t)(st), (const bf16*)x, (bf16*)y, nvec, C, sums, sg, b, pop_mean, decay, train, alpha)));
   TGAN_LAUNCHED();
   return 0;
 }
@@ -704,10 +728,9 @@ extern "C" int tgan_act_bwd_seg(const void* dy, int dydt, const void* y, int ydt
     const int nparts = TGAN_ACT_BWD_SEG_PARTS;    // 3 CTAs per SM; ws holds nparts * 4 * C floats
     const size_t smem = (size_t)(2048 / C) * 4 * C * sizeof(float);      // 32 KB
     cudaStream_t st = (cudaStream_t)stream;
-    TGAN_DISPATCH_ACT(act, A, (act_bwd_seg_v8_kernel<A><<<nparts, 256, smem, st>>>(
-                                  (const bf16*)dy, (const bf16*)y, (bf16*)du, rows, C, sg, alpha, ws)));
+    TGAN_DISPATCH_ACT(act, A, (pdl_launch(act_bwd_seg_v8_kernel<A>, nparts, 256, smem, (cudaStream_t)(st), (const bf16*)dy, (const bf16*)y, (bf16*)du, rows, C, sg, alpha, ws)));
     TGAN_LAUNCHED();
-    act_bwd_seg_fold_kernel<<<ceil_div(C, 32), 256, 0, st>>>(ws, nparts, C, colsums, grad_acc);
+    pdl_launch(act_bwd_seg_fold_kernel, ceil_div(C, 32), 256, 0, (cudaStream_t)(st), ws, nparts, C, colsums, grad_acc);
     TGAN_LAUNCHED();
     return 0;
   }
@@ -728,7 +751,7 @@ extern "C" int tgan_sub_channel_mean_seg(const void* du, void* dz, int64_t rows,
   Segs sg;
   if (make_segs(sg, rows, nseg, r0, r1, r2)) return 1;
   const int64_t nvec = rows * C / 8;
-  sub_mean_seg_kernel<<<grid_for(nvec), 256, 0, (cudaStream_t)stream>>>((const bf16*)du, (bf16*)dz, nvec, C, colsums, sg);
+  pdl_launch(sub_mean_seg_kernel, grid_for(nvec), 256, 0, (cudaStream_t)((cudaStream_t)stream), (const bf16*)du, (bf16*)dz, nvec, C, colsums, sg);
   TGAN_LAUNCHED();
   return 0;
 }
@@ -737,7 +760,7 @@ extern "C" int tgan_bn_finalize(const float* sum, const float* sumsq, int64_t ro
                                 const float* beta, float eps, float decay, float* moving_mean, float* moving_var,
                                 float* mean, float* rstd, float* scale, float* shift, void* stream) {
   TGAN_CHECK_ARG(sum && sumsq && gamma && beta && mean && rstd && scale && shift, "bn_finalize: bad args");
-  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(sum, sumsq, (float)rows, C, gamma, beta, eps,
+  pdl_launch(bn_finalize_kernel, ceil_div(C, 128), 128, 0, (cudaStream_t)((cudaStream_t)stream), sum, sumsq, (float)rows, C, gamma, beta, eps,
                                                                          decay, moving_mean, moving_var, mean, rstd,
                                                                          scale, shift);
   TGAN_LAUNCHED();
@@ -746,7 +769,7 @@ extern "C" int tgan_bn_finalize(const float* sum, const float* sumsq, int64_t ro
 extern "C" int tgan_bn_eval_affine(const float* gamma, const float* beta, const float* moving_mean,
                                    const float* moving_var, float eps, int C, float* scale, float* shift,
                                    void* stream) {
-  bn_eval_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(gamma, beta, moving_mean, moving_var, eps, C,
+  pdl_launch(bn_eval_kernel, ceil_div(C, 128), 128, 0, (cudaStream_t)((cudaStream_t)stream), gamma, beta, moving_mean, moving_var, eps, C,
                                                                      scale, shift);
   TGAN_LAUNCHED();
   return 0;
@@ -760,8 +783,8 @@ extern "C" int tgan_affine_act(const void* x, int xdt, void* y, int ydt, int64_t
   cudaStream_t st = (cudaStream_t)stream;
   DISPATCH_2(xdt, TX, ydt, TY, {
     TGAN_DISPATCH_ACT(act, A, {
-      if (v) affine_act_kernel<TX, TY, 4, A><<<grid_for(n / 4), 256, 0, st>>>((const TX*)x, (TY*)y, n / 4, C, scale, shift, alpha);
-      else affine_act_kernel<TX, TY, 1, A><<<grid_for(n), 256, 0, st>>>((const TX*)x, (TY*)y, n, C, scale, shift, alpha);
+      if (v) pdl_launch(affine_act_kernel<TX, TY, 4, A>, grid_for(n / 4), 256, 0, (cudaStream_t)(st), (const TX*)x, (TY*)y, n / 4, C, scale, shift, alpha);
+      else pdl_launch(affine_act_kernel<TX, TY, 1, A>, grid_for(n), 256, 0, (cudaStream_t)(st), (const TX*)x, (TY*)y, n, C, scale, shift, alpha);
     });
   });
   TGAN_LAUNCHED();
@@ -795,8 +818,8 @@ extern "C" int tgan_sub_channel_mean(const void* du, int dudt, void* dz, int dzd
   cudaStream_t st = (cudaStream_t)stream;
   float inv = 1.0f / (float)rows;
   DISPATCH_2(dudt, TA, dzdt, TB, {
-    if (v) sub_mean_kernel<TA, TB, 4><<<grid_for(n / 4), 256, 0, st>>>((const TA*)du, (TB*)dz, n / 4, C, colsum, inv);
-    else sub_mean_kernel<TA, TB, 1><<<grid_for(n), 256, 0, st>>>((const TA*)du, (TB*)dz, n, C, colsum, inv);
+    if (v) pdl_launch(sub_mean_kernel<TA, TB, 4>, grid_for(n / 4), 256, 0, (cudaStream_t)(st), (const TA*)du, (TB*)dz, n / 4, C, colsum, inv);
+    else pdl_launch(sub_mean_kernel<TA, TB, 1>, grid_for(n), 256, 0, (cudaStream_t)(st), (const TA*)du, (TB*)dz, n, C, colsum, inv);
   });
   TGAN_LAUNCHED();
   return 0;
@@ -818,12 +841,12 @@ extern "C" int tgan_bn_bwd(const void* dy, int dydt, const void* x, int xdt, voi
   });
   int64_t n = rows * C;
   TGAN_DISPATCH_1(dydt, TDY, TGAN_DISPATCH_1(xdt, TX, TGAN_DISPATCH_1(dxdt, TDX, {
-    bn_bwd_apply_kernel<TDY, TX, TDX><<<grid_for(n), 256, 0, st>>>((const TDY*)dy, (const TX*)x, (TDX*)dx, n, C, mean,
+    pdl_launch(bn_bwd_apply_kernel<TDY, TX, TDX>, grid_for(n), 256, 0, (cudaStream_t)(st), (const TDY*)dy, (const TX*)x, (TDX*)dx, n, C, mean,
                                                                    rstd, gamma, s1, s2, 1.0f / (float)rows);
   })));
   TGAN_LAUNCHED();
-  if (dbeta) { add_to_kernel<<<ceil_div(C, 128), 128, 0, st>>>(dbeta, s1, C, beta_acc); TGAN_LAUNCHED(); }
-  if (dgamma) { add_to_kernel<<<ceil_div(C, 128), 128, 0, st>>>(dgamma, s2, C, beta_acc); TGAN_LAUNCHED(); }
+  if (dbeta) { pdl_launch(add_to_kernel, ceil_div(C, 128), 128, 0, (cudaStream_t)(st), dbeta, s1, C, beta_acc); TGAN_LAUNCHED(); }
+  if (dgamma) { pdl_launch(add_to_kernel, ceil_div(C, 128), 128, 0, (cudaStream_t)(st), dgamma, s2, C, beta_acc); TGAN_LAUNCHED(); }
   return 0;
 }
 
@@ -831,8 +854,7 @@ extern "C" int tgan_add_noise(const void* x, int xdt, void* y, int ydt, int64_t 
                               uint64_t seed, uint64_t stream_id, const uint64_t* counter, void* stream) {
   TGAN_CHECK_ARG(x && y && n > 0, "add_noise: bad args");
   int64_t q = (n + 3) / 4;
-  DISPATCH_2(xdt, TX, ydt, TY, (add_noise_kernel<TX, TY><<<ceil_div(q, 256), 256, 0, (cudaStream_t)stream>>>(
-                                   (const TX*)x, (TY*)y, n, std, noise, seed, stream_id, counter)));
+  DISPATCH_2(xdt, TX, ydt, TY, (pdl_launch(add_noise_kernel<TX, TY>, ceil_div(q, 256), 256, 0, (cudaStream_t)((cudaStream_t)stream), (const TX*)x, (TY*)y, n, std, noise, seed, stream_id, counter)));
   TGAN_LAUNCHED();
   return 0;
 }
@@ -841,8 +863,7 @@ extern "C" int tgan_dropout(const void* x, int xdt, void* y, int ydt, uint8_t* m
                             uint64_t seed, uint64_t stream_id, const uint64_t* counter, void* stream) {
   TGAN_CHECK_ARG(x && y && mask && n > 0 && rate >= 0.f && rate < 1.f, "dropout: bad args");
   int64_t q = (n + 3) / 4;
-  DISPATCH_2(xdt, TX, ydt, TY, (dropout_kernel<TX, TY><<<ceil_div(q, 256), 256, 0, (cudaStream_t)stream>>>(
-                                   (const TX*)x, (TY*)y, mask, n, rate, 1.0f / (1.0f - rate), gen, seed, stream_id,
+  DISPATCH_2(xdt, TX, ydt, TY, (pdl_launch(dropout_kernel<TX, TY>, ceil_div(q, 256), 256, 0, (cudaStream_t)((cudaStream_t)stream), (const TX*)x, (TY*)y, mask, n, rate, 1.0f / (1.0f - rate), gen, seed, stream_id,
                                    counter)));
   TGAN_LAUNCHED();
   return 0;
@@ -852,8 +873,7 @@ extern "C" int tgan_maxpool2_fwd(const void* x, int dt, void* y, uint8_t* idx, i
                                  void* stream) {
   TGAN_CHECK_ARG(x && y && idx && H % 2 == 0 && W % 2 == 0, "maxpool2_fwd: bad args (even extents only)");
   int64_t total = (int64_t)N * (H / 2) * (W / 2) * C;
-  TGAN_DISPATCH_1(dt, T, (maxpool2_fwd_kernel<T><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
-                             (const T*)x, (T*)y, idx, N, H, W, C, total)));
+  TGAN_DISPATCH_1(dt, T, (pdl_launch(maxpool2_fwd_kernel<T>, ceil_div(total, 256), 256, 0, (cudaStream_t)((cudaStream_t)stream), (const T*)x, (T*)y, idx, N, H, W, C, total)));
   TGAN_LAUNCHED();
   return 0;
 }
@@ -861,8 +881,7 @@ extern "C" int tgan_maxpool2_bwd(const void* dy, int dt, const uint8_t* idx, voi
                                  void* stream) {
   TGAN_CHECK_ARG(dy && dx && idx && H % 2 == 0 && W % 2 == 0, "maxpool2_bwd: bad args");
   int64_t total = (int64_t)N * (H / 2) * (W / 2) * C;
-  TGAN_DISPATCH_1(dt, T, (maxpool2_bwd_kernel<T><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
-                             (const T*)dy, idx, (T*)dx, N, H, W, C, total)));
+  TGAN_DISPATCH_1(dt, T, (pdl_launch(maxpool2_bwd_kernel<T>, ceil_div(total, 256), 256, 0, (cudaStream_t)((cudaStream_t)stream), (const T*)dy, idx, (T*)dx, N, H, W, C, total)));
   TGAN_LAUNCHED();
   return 0;
 }
@@ -874,8 +893,7 @@ extern "C" int tgan_maxpool2_dropout_fwd(const void* x, void* y, uint8_t* code, 
                      aligned16(y) && ((uintptr_t)code & 7) == 0,
                  "maxpool2_dropout_fwd: bf16, even extents, C %% 8 == 0, aligned buffers");
   const int64_t nvec = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
-  maxpool2_dropout_fwd_kernel<<<ceil_div(nvec, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)x, (bf16*)y, code, H, W, C, nvec, rate, 1.0f / (1.0f - rate), mask, seed, stream_id, counter);
+  pdl_launch(maxpool2_dropout_fwd_kernel, ceil_div(nvec, 256), 256, 0, (cudaStream_t)((cudaStream_t)stream), (const bf16*)x, (bf16*)y, code, H, W, C, nvec, rate, 1.0f / (1.0f - rate), mask, seed, stream_id, counter);
   TGAN_LAUNCHED();
   return 0;
 }
@@ -884,8 +902,7 @@ extern "C" int tgan_maxpool2_dropout_bwd(const void* dy, const uint8_t* code, vo
   TGAN_CHECK_ARG(dy && dx && code && H % 2 == 0 && W % 2 == 0 && C % 8 == 0 && aligned16(dy) && aligned16(dx),
                  "maxpool2_dropout_bwd: bad args");
   const int64_t nvec = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
-  maxpool2_dropout_bwd_kernel<<<ceil_div(nvec, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)dy, code, (bf16*)dx, H, W, C, nvec, 1.0f / (1.0f - rate));
+  pdl_launch(maxpool2_dropout_bwd_kernel, ceil_div(nvec, 256), 256, 0, (cudaStream_t)((cudaStream_t)stream), (const bf16*)dy, code, (bf16*)dx, H, W, C, nvec, 1.0f / (1.0f - rate));
   TGAN_LAUNCHED();
   return 0;
 }
@@ -894,8 +911,7 @@ extern "C" int tgan_global_pool_fwd(const void* x, int xdt, void* y, int ydt, ui
                                     int mode, void* stream) {
   TGAN_CHECK_ARG(x && y && HW > 0 && HW <= 256, "global_pool_fwd: bad args");
   TGAN_CHECK_ARG(mode == 1 || idx, "global_pool_fwd: max mode needs idx");
-  DISPATCH_2(xdt, TX, ydt, TY, (global_pool_fwd_kernel<TX, TY><<<ceil_div((int64_t)N * C, 128), 128, 0,
-                                                                 (cudaStream_t)stream>>>((const TX*)x, (TY*)y, idx, N,
+  DISPATCH_2(xdt, TX, ydt, TY, (pdl_launch(global_pool_fwd_kernel<TX, TY>, ceil_div((int64_t)N * C, 128), 128, 0, (cudaStream_t)((cudaStream_t)stream), (const TX*)x, (TY*)y, idx, N,
                                                                                          HW, C, mode)));
   TGAN_LAUNCHED();
   return 0;
@@ -904,9 +920,7 @@ extern "C" int tgan_global_pool_bwd(const void* dy, int dydt, const uint8_t* idx
                                     int C, int mode, void* stream) {
   TGAN_CHECK_ARG(dy && dx, "global_pool_bwd: bad args");
   int64_t total = (int64_t)N * HW * C;
-  DISPATCH_2(dydt, TDY, dxdt, TDX, (global_pool_bwd_kernel<TDY, TDX><<<ceil_div(total, 256), 256, 0,
-                                                                     (cudaStream_t)stream>>>(
-                                       (const TDY*)dy, idx, (TDX*)dx, N, HW, C, mode, total)));
+  DISPATCH_2(dydt, TDY, dxdt, TDX, (pdl_launch(global_pool_bwd_kernel<TDY, TDX>, ceil_div(total, 256), 256, 0, (cudaStream_t)((cudaStream_t)stream), (const TDY*)dy, idx, (TDX*)dx, N, HW, C, mode, total)));
   TGAN_LAUNCHED();
   return 0;
 }
@@ -915,8 +929,7 @@ extern "C" int tgan_concat_label(const void* x, int xdt, int64_t rows, int C, in
                                  int rows_per_sample, void* out, int odt, int ldo, void* stream) {
   TGAN_CHECK_ARG(x && lab && out && ldo >= C + K && rows_per_sample > 0, "concat_label: bad args");
   int64_t total = rows * ldo;
-  DISPATCH_2(xdt, TX, odt, TO, (concat_label_kernel<TX, TO><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
-                                   (const TX*)x, rows, C, ldx, lab, K, rows_per_sample, (TO*)out, ldo, total)));
+  DISPATCH_2(xdt, TX, odt, TO, (pdl_launch(concat_label_kernel<TX, TO>, ceil_div(total, 256), 256, 0, (cudaStream_t)((cudaStream_t)stream), (const TX*)x, rows, C, ldx, lab, K, rows_per_sample, (TO*)out, ldo, total)));
   TGAN_LAUNCHED();
   return 0;
 }
@@ -924,8 +937,7 @@ extern "C" int tgan_fill_label(const float* lab, int K, int rows_per_sample, voi
                                int ldo, void* stream) {
   TGAN_CHECK_ARG(lab && out && ldo >= C + K && rows_per_sample > 0 && rows > 0, "fill_label: bad args");
   int64_t total = rows * (ldo - C);
-  TGAN_DISPATCH_1(odt, TO, (fill_label_kernel<TO><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
-                               lab, K, rows_per_sample, (TO*)out, C, ldo, total)));
+  TGAN_DISPATCH_1(odt, TO, (pdl_launch(fill_label_kernel<TO>, ceil_div(total, 256), 256, 0, (cudaStream_t)((cudaStream_t)stream), lab, K, rows_per_sample, (TO*)out, C, ldo, total)));
   TGAN_LAUNCHED();
   return 0;
 }
@@ -933,26 +945,25 @@ extern "C" int tgan_copy_channels(const void* src, int sdt, int lds, void* dst, 
                                   void* stream) {
   TGAN_CHECK_ARG(src && dst && lds >= C && ldd >= C, "copy_channels: bad args");
   int64_t total = rows * C;
-  DISPATCH_2(sdt, TS, ddt, TD, (copy_channels_kernel<TS, TD><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
-                                   (const TS*)src, lds, (TD*)dst, ldd, C, total)));
+  DISPATCH_2(sdt, TS, ddt, TD, (pdl_launch(copy_channels_kernel<TS, TD>, ceil_div(total, 256), 256, 0, (cudaStream_t)((cudaStream_t)stream), (const TS*)src, lds, (TD*)dst, ldd, C, total)));
   TGAN_LAUNCHED();
   return 0;
 }
 extern "C" int tgan_accumulate(void* y, const void* x, int dt, int64_t n, void* stream) {
   TGAN_CHECK_ARG(y && x && n > 0, "accumulate: bad args");
-  TGAN_DISPATCH_1(dt, T, (accumulate_kernel<T><<<grid_for(n), 256, 0, (cudaStream_t)stream>>>((T*)y, (const T*)x, n)));
+  TGAN_DISPATCH_1(dt, T, (pdl_launch(accumulate_kernel<T>, grid_for(n), 256, 0, (cudaStream_t)((cudaStream_t)stream), (T*)y, (const T*)x, n)));
   TGAN_LAUNCHED();
   return 0;
 }
 extern "C" int tgan_fill_f32(float* p, float v, int64_t n, void* stream) {
   TGAN_CHECK_ARG(p && n > 0, "fill: bad args");
-  fill_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(p, v, n);
+  pdl_launch(fill_kernel, grid_for(n), 256, 0, (cudaStream_t)((cudaStream_t)stream), p, v, n);
   TGAN_LAUNCHED();
   return 0;
 }
 extern "C" int tgan_argmax_onehot(const float* logits, int N, int K, int64_t* idx, float* onehot, void* stream) {
   TGAN_CHECK_ARG(logits && N > 0 && K > 0, "argmax_onehot: bad args");
-  argmax_onehot_kernel<<<ceil_div(N, 128), 128, 0, (cudaStream_t)stream>>>(logits, N, K, idx, onehot);
+  pdl_launch(argmax_onehot_kernel, ceil_div(N, 128), 128, 0, (cudaStream_t)((cudaStream_t)stream), logits, N, K, idx, onehot);
   TGAN_LAUNCHED();
   return 0;
 }
