@@ -11,11 +11,14 @@
 
 namespace tgan {
 
-__device__ unsigned int g_colreduce_ticket[1024];   // zero at load; the last CTA of every launch resets its slot
+// Ticket counters of the "last CTA folds" protocol, one set of 1024 per WORKSPACE: launches that may run concurrently (on
+// different streams) use different workspaces, hence different counters.  Zero at load; the last CTA resets its slot.
+constexpr int COLREDUCE_WS_SLOTS = 8;
+__device__ unsigned int g_colreduce_ticket[COLREDUCE_WS_SLOTS][1024];
 
 template <int NACC, int VEC, typename F>
 __global__ void __launch_bounds__(256) colreduce_kernel(F f, int64_t rows, int C, double* __restrict__ partials,
-                                                        float* o0, float* o1, float beta, float* acc0, int segmode) {
+                                                        float* o0, float* o1, float beta, float* acc0, int segmode, int slot) {
   pdl_entry();
   constexpr int CL = VEC == 4 ? 8 : 32, RL = 256 / CL;
   __shared__ double sm[RL][NACC][33];
@@ -53,7 +56,7 @@ __global__ void __launch_bounds__(256) colreduce_kernel(F f, int64_t rows, int C
   }
   __threadfence();
   __syncthreads();
-  if (t == 0) is_last = (atomicAdd(&g_colreduce_ticket[blockIdx.x], 1u) == gridDim.y - 1);
+  if (t == 0) is_last = (atomicAdd(&g_colreduce_ticket[slot][blockIdx.x], 1u) == gridDim.y - 1);
   __syncthreads();
   if (!is_last) return;
   __threadfence();
@@ -86,7 +89,21 @@ __global__ void __launch_bounds__(256) colreduce_kernel(F f, int64_t rows, int C
     }
     if (segmode && acc0) acc0[c] = (float)((double)acc0[c] + tot);
   }
-  if (t == 0) g_colreduce_ticket[blockIdx.x] = 0;
+  if (t == 0) g_colreduce_ticket[slot][blockIdx.x] = 0;
+}
+
+// workspace pointer -> ticket slot (first come, first served; the step uses two workspaces: main and side stream)
+static inline int colreduce_slot(const void* ws) {
+  static const void* seen[COLREDUCE_WS_SLOTS] = {nullptr};
+  static int next = 0;
+  for (int i = 0; i < COLREDUCE_WS_SLOTS; ++i)
+    if (seen[i] == ws) return i;
+  // a new workspace takes the oldest slot: its previous owner belongs to a context that was torn down (the counters
+  // are left at zero by every launch)
+  const int i = next;
+  next = (next + 1) % COLREDUCE_WS_SLOTS;
+  seen[i] = ws;
+  return i;
 }
 
 static inline int pick_parts(int64_t rows, int C, int vec) {
@@ -106,11 +123,12 @@ static int run_colreduce(F1 f1, F4 f4, bool vec_ok, int64_t rows, int C, float* 
                          cudaStream_t st, float* acc0 = nullptr, int segmode = 0) {
   if (ceil_div(C, 32) > 1024) { set_error("colreduce: more than 32768 channels"); return 1; }
   int vec = vec_ok ? 4 : 1;
+  const int slot = colreduce_slot(ws);
   int parts = pick_parts(rows, C, vec);
   dim3 grid(ceil_div(C, 32), parts);
   double* wsd = reinterpret_cast<double*>(ws);       // fp64 partials: the first 4*MAX_PARTS*C floats of ws
-  if (vec_ok) pdl_launch(colreduce_kernel<NACC, 4, F4>, grid, 256, 0, (cudaStream_t)(st), f4, rows, C, wsd, o0, o1, beta, acc0, segmode);
-  else pdl_launch(colreduce_kernel<NACC, 1, F1>, grid, 256, 0, (cudaStream_t)(st), f1, rows, C, wsd, o0, o1, beta, acc0, segmode);
+  if (vec_ok) pdl_launch(colreduce_kernel<NACC, 4, F4>, grid, 256, 0, (cudaStream_t)(st), f4, rows, C, wsd, o0, o1, beta, acc0, segmode, slot);
+  else pdl_launch(colreduce_kernel<NACC, 1, F1>, grid, 256, 0, (cudaStream_t)(st), f1, rows, C, wsd, o0, o1, beta, acc0, segmode, slot);
   TGAN_LAUNCHED();
   return 0;
 }

@@ -35,6 +35,9 @@ class Context:
         self.store = None
         self.rng = None
         self._ws = None
+        self._ws_side = None
+        self.side = None            # second stream: independent small-kernel chains run beside the big GEMMs
+        self.on_side = False
         self.ws_floats = 64 * 1024 * 1024
         self._arena = None          # zero-initialised fp32 scratch for epilogue-accumulated statistics
         self.arena_floats = 256 * 1024
@@ -51,9 +54,20 @@ class Context:
         return self._arena
 
     def ws(self):
+        """scratch workspace of the CURRENT stream (kernels on the side stream must not share partial sums / ticket
+        counters with kernels on the main stream)"""
+        if self.on_side:
+            if self._ws_side is None:
+                self._ws_side = torch.empty(self.ws_floats // 4, dtype=torch.float32, device=self.device)
+            return self._ws_side
         if self._ws is None:
             self._ws = torch.empty(self.ws_floats, dtype=torch.float32, device=self.device)
         return self._ws
+
+    def side_stream(self):
+        if self.side is None:
+            self.side = torch.cuda.Stream(device=self.device)
+        return self.side
 
 
 ctx = Context()
@@ -71,6 +85,9 @@ def init(device='cuda:0', math='fp32', seed=1234):
     torch.cuda.set_device(ctx.device)
     ctx.math = math
     ctx._ws = None
+    ctx._ws_side = None
+    ctx.side = None
+    ctx.on_side = False
     ctx._arena = None
     ctx.rng = PhiloxSource(seed)
     return ctx

@@ -53,6 +53,37 @@ def arena_take(n):
     return a[o:o + n]
 
 
+class side_stream:
+    """`with ops.side_stream(): ...` enqueues the enclosed launches on the context's second stream, ordered after
+    everything already enqueued on the current stream (fork); `ops.join_side()` makes the current stream wait for them.
+    Under CUDA-graph capture the two become parallel branches of the graph.  Used for work that is independent of what
+    the main stream does meanwhile: the generator forward beside the classifier forward of phase D, filter gradients
+    beside input gradients of small layers."""
+
+    def __enter__(self):
+        main = torch.cuda.current_stream()
+        side = ctx.side_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        side.wait_event(ev)
+        self._cm = torch.cuda.stream(side)
+        self._cm.__enter__()
+        ctx.on_side = True
+        return self
+
+    def __exit__(self, *a):
+        ctx.on_side = False
+        self._cm.__exit__(*a)
+
+
+def join_side():
+    if ctx.side is None:
+        return
+    ev = torch.cuda.Event()
+    ev.record(ctx.side)
+    torch.cuda.current_stream().wait_event(ev)
+
+
 class TagList:
     """RNG tags of several network calls grouped into one batch: [(tag, samples), ...].  `tags + '/noise'` appends
     the suffix to every tag, so builder code written for one call works unchanged on a grouped batch."""

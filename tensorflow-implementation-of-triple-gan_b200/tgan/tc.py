@@ -14,6 +14,7 @@ as a list of taps (dy, dx) over shifted, optionally strided windows of an NHWC b
 
 Skinny layers (Cout < 16: RGB output, logits, D head) stay on the fp32 SIMT path.
 """
+import contextlib
 import ctypes
 
 import torch
@@ -170,6 +171,16 @@ def conv_fwd(x, w, g, colsum=None, segs=None, bias=None, act=0, ldo=None):
     return z
 
 
+def _ops():
+    from . import ops
+    return ops
+
+
+def _small(rows, ch):
+    """fewer 256-pixel x 128-channel tiles than SMs: the launch cannot fill the GPU on its own"""
+    return not ctx.on_side and rows * ch < 148 * 256 * 128
+
+
 def _grad_target(x, C):
     """-> (Var that receives the input gradient, number of leading channels it covers)"""
     src = x.aux.get('concat_src') if x.aux else None
@@ -184,16 +195,21 @@ def conv_bwd(x, w, g, dz):
     C, Cout, kh, kw, s, pt, pl = g['C'], g['Cout'], g['kh'], g['kw'], g['s'], g['pt'], g['pl']
     rows = g['N'] * g['Ho'] * g['Wo']
     dzb, _ = _bf16_padded(dz, rows, Cout, Cout)
-    if w.requires_grad and _small_cin(g):
-        col, K, Kc = g.get('_col') or _im2col(x, g)
-        # dW[(tap, ci), co] = col^T dz: a plain GEMM whose [Kc][Cout] result starts with the K rows of the HWIO gradient
-        _wgrad(dzb, 1, 1, rows, Cout, Cout, col, 1, rows, Kc, Kc, [(0, 0)], 1, w.grad_target(), cin_store=K)
-    elif w.requires_grad:
-        xd, ld = g.get('_x') or _bf16_padded(x.data, x.rows, C, x.ld)
-        taps = [(r - pt, c - pl) for r in range(kh) for c in range(kw)]
-        # the kernel writes [t][ci][co] == HWIO
-        _wgrad(dzb, gf['N'], gf['Ho'], gf['Wo'], Cout, Cout, xd, gf['H'], gf['W'], C, ld, taps, s, w.grad_target())
     tgt, Cg = _grad_target(x, C)
+    # small layers (fewer tiles than SMs): the filter gradient runs on the side stream beside the input gradient
+    par = w.requires_grad and tgt.requires_grad and _small(rows, max(C, Cout))
+    if w.requires_grad:
+        dw = w.grad_target()
+        with (_ops().side_stream() if par else contextlib.nullcontext()):
+            if _small_cin(g):
+                col, K, Kc = g.get('_col') or _im2col(x, g)
+                # dW[(tap, ci), co] = col^T dz: a plain GEMM whose [Kc][Cout] result starts with the K rows of the HWIO gradient
+                _wgrad(dzb, 1, 1, rows, Cout, Cout, col, 1, rows, Kc, Kc, [(0, 0)], 1, dw, cin_store=K)
+            else:
+                xd, ld = g.get('_x') or _bf16_padded(x.data, x.rows, C, x.ld)
+                taps = [(r - pt, c - pl) for r in range(kh) for c in range(kw)]
+                # the kernel writes [t][ci][co] == HWIO
+                _wgrad(dzb, gf['N'], gf['Ho'], gf['Wo'], Cout, Cout, xd, gf['H'], gf['W'], C, ld, taps, s, dw)
     if tgt.requires_grad:
         # a label-concatenated input only needs the gradient of its first Cg channels: it goes to the concat's source
         dxt = _new(tuple(x.shape[:-1]) + (Cg,), tgt.data.dtype if tgt.data.dtype == torch.bfloat16 else torch.float32)
@@ -228,6 +244,8 @@ def conv_bwd(x, w, g, dz):
         if staged:
             _lib.call('tgan_copy_channels', dx.data_ptr(), BF16, Cs, dxt.data_ptr(), dt_code(dxt), Cg, x.rows, Cg, _st())
         add_grad(tgt, dxt if dxt.dtype == tgt.data.dtype else dxt.to(tgt.data.dtype))
+    if par:
+        _ops().join_side()
     g.pop('_x', None)
     g.pop('_col', None)
 
@@ -311,16 +329,21 @@ def deconv_bwd(x, w, g, dy):
     Cin, Cout, kh, kw, pt, pl = g['Cin'], g['Cout'], g['kh'], g['kw'], g['pt'], g['pl']
     dyb, _ = _bf16_padded(dy, g['N'] * g['Ho'] * g['Wo'], Cout, Cout)
     taps = [(r - pt, c - pl) for r in range(kh) for c in range(kw)]
-    if w.requires_grad:
-        xd, ld = g.get('_x') or _bf16_padded(x.data, x.rows, Cin, x.ld)
-        # roles exchanged: M side = x channels (ci), N side = strided dy window (co); the kernel's
-        # [t][N-side][M-side] output is then exactly the filter layout [kh,kw,Cout,Cin]
-        _wgrad(xd, g['N'], g['h'], g['w'], Cin, ld, dyb, g['Ho'], g['Wo'], Cout, Cout, taps, 2, w.grad_target())
     tgt, Cg = _grad_target(x, Cin)
+    par = w.requires_grad and tgt.requires_grad and _small(g['N'] * g['Ho'] * g['Wo'], max(Cin, Cout))
+    if w.requires_grad:
+        dw = w.grad_target()
+        with (_ops().side_stream() if par else contextlib.nullcontext()):
+            xd, ld = g.get('_x') or _bf16_padded(x.data, x.rows, Cin, x.ld)
+            # roles exchanged: M side = x channels (ci), N side = strided dy window (co); the kernel's
+            # [t][N-side][M-side] output is then exactly the filter layout [kh,kw,Cout,Cin]
+            _wgrad(xd, g['N'], g['h'], g['w'], Cin, ld, dyb, g['Ho'], g['Wo'], Cout, Cout, taps, 2, dw)
     if tgt.requires_grad:
         wp, Kpad = _pack(w, ('ddgrad', Cg), kh * kw, Cg, Cout, Cout * Cin, 1, Cin)
         dx = _new(tuple(x.shape[:-1]) + (Cg,), torch.bfloat16)
         _igemm(dyb, g['N'], g['Ho'], g['Wo'], Cout, Cout, wp, Kpad, taps, Cg, g['h'], g['w'], dx, g['h'], g['w'], Cg,
                s=2)
         add_grad(tgt, dx if dx.dtype == tgt.data.dtype else dx.to(tgt.data.dtype))
+    if par:
+        _ops().join_side()
     g.pop('_x', None)

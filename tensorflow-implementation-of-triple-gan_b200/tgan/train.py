@@ -175,6 +175,12 @@ class Train(Train_base):
         TL = ops.TagList
         # ---- phase D: sess.run([d_solver, d_loss]) (:267) ----
         ops.arena_reset()
+        # the generator forward (a chain of small kernels) runs on the side stream beside the classifier forward
+        for p in self.g_vars:                # record G(z, y) once, on its own tape, for phase G's backward
+            p.requires_grad = True
+        with ops.side_stream(), recording() as tape_g:
+            G = m.good_generator(v['z_g'], v['y_g'], reuse=True, tag='D/G')
+            G.data
         with no_grad():
             if grouped_c:
                 lg, _ = m.classifier(pre(ops.group_batch([v['x_u_d'], v['x_u_c']])), train, reuse=True,
@@ -187,10 +193,7 @@ class Train(Train_base):
                 c_unl, _ = m.classifier(pre(v['x_u_c']), train, reuse=True, tag='D/C_unl')
                 idx_d, oh_d = ops.argmax_onehot(c_unl_d, K)
                 idx_u, oh_u = ops.argmax_onehot(c_unl, K)
-        for p in self.g_vars:                # record G(z, y) once, on its own tape, for phase G's backward
-            p.requires_grad = True
-        with recording() as tape_g:
-            G = m.good_generator(v['z_g'], v['y_g'], reuse=True, tag='D/G')
+        ops.join_side()
         G_const = ops.Var(G.data, G.shape)   # phase D sees the generated images as constants (var_list = d_vars)
         fb = self._begin('discriminator', self.d_vars)
         with recording():
