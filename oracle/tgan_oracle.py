@@ -723,13 +723,15 @@ class OracleTrainer:
         gs = torch.autograd.grad(loss, [self.P[n] for n in names], allow_unused=True)
         return {n: (g if g is not None else torch.zeros_like(self.P[n])) for n, g in zip(names, gs)}
 
-    def step(self, batch, rng, lambda_1, lambda_2=0.0, lr=None, cla_lr=None, train=True, update=True):
+    def step(self, batch, rng, lambda_1, lambda_2=0.0, lr=None, cla_lr=None, train=True, update=True, phases='DGC'):
         cfg, m = self.cfg, self.model
         lr = cfg.LEARNING_RATE if lr is None else lr
         cla_lr = cfg.CLA_LEARNINIG_RATE if cla_lr is None else cla_lr
         b = {k: torch.as_tensor(v).to(self.dtype) for k, v in batch.items()}
         cif = cfg.DATA_NAME == 'cifar10'
         pre = m.zca_apply if cif else (lambda t: t)
+        if phases == 'C':      # PRE_TRAIN iteration (Train_goodGAN.py:182-224): only sess.run([c_solver, c_loss])
+            return self._phase_c(b, rng, lambda_1, lambda_2, cla_lr, train, update)
         # ---- phase D (Train_goodGAN.py:267) ----
         with torch.no_grad():
             c_unl_d, _ = m.classifier(pre(b['x_u_d']), train, rng, 'D/C_unl_d')
@@ -753,6 +755,14 @@ class OracleTrainer:
         gg = self._grads(g_loss, self.g_vars)
         if update:
             self.opt_g.apply(self.P, gg, lr)
+        _, _, c_loss_v = self._phase_c(b, rng, lambda_1, lambda_2, cla_lr, train, update)
+        self.last_grads = {'D': gd, 'G': gg, 'C': self.last_grads['C']}
+        return float(d_loss.detach()), float(g_loss.detach()), c_loss_v
+
+    def _phase_c(self, b, rng, lambda_1, lambda_2, cla_lr, train, update):
+        cfg, m = self.cfg, self.model
+        cif = cfg.DATA_NAME == 'cifar10'
+        pre = m.zca_apply if cif else (lambda t: t)
         # ---- phase C (:275) ----
         c_real, _ = m.classifier(pre(b['x_l_c']), train, rng, 'C/C_real')
         c_unl, _ = m.classifier(pre(b['x_u_c']), train, rng, 'C/C_unl')
@@ -771,5 +781,12 @@ class OracleTrainer:
             with torch.no_grad():       # ema.apply(c_vars) after c_solver_ (:101-103)
                 for k in self.c_vars:
                     self.ema[k] -= (self.ema[k] - self.P[k]) * (1 - 0.9999)
-        self.last_grads = {'D': gd, 'G': gg, 'C': gc}
-        return float(d_loss.detach()), float(g_loss.detach()), float(c_loss.detach())
+        self.last_grads = dict(self.last_grads, C=gc)
+        return None, None, float(c_loss.detach())
+
+    def evaluate(self, x, rng):
+        """validation forward of Train_goodGAN.py:296-351: classifier logits with train=False"""
+        m = self.model
+        pre = m.zca_apply if self.cfg.DATA_NAME == 'cifar10' else (lambda t: t)
+        with torch.no_grad():
+            return m.classifier(pre(torch.as_tensor(x).to(self.dtype)), False, rng, 'V/C_real')[0]

@@ -156,7 +156,7 @@ class Train(Train_base):
             return m._whitener().apply
         return lambda t: t
 
-    def _step_impl(self, train=True):
+    def _step_impl(self, train=True, phases='DGC'):
         """The three phases with TF's per-`sess.run` pruning, scheduled for the GPU:
 
         * calls of the same network inside a phase are GROUPED into one batch (ops.group_batch): per-sample work
@@ -173,47 +173,51 @@ class Train(Train_base):
         grouped_c = cif                      # mean-only-BN classifier: segment-aware ops
         nLD, nUD, nUC, nG, nLC = (c.BATCH_SIZE_L_D, c.BATCH_SIZE_U_D, c.BATCH_SIZE_U_C, c.BATCH_SIZE_G, c.BATCH_SIZE_L_C)
         TL = ops.TagList
-        # ---- phase D: sess.run([d_solver, d_loss]) (:267) ----
-        ops.arena_reset()
-        # the generator forward (a chain of small kernels) runs on the side stream beside the classifier forward
-        for p in self.g_vars:                # record G(z, y) once, on its own tape, for phase G's backward
-            p.requires_grad = True
-        with ops.side_stream(), recording() as tape_g:
-            G = m.good_generator(v['z_g'], v['y_g'], reuse=True, tag='D/G')
-            G.data
-        with no_grad():
-            if grouped_c:
-                lg, _ = m.classifier(pre(ops.group_batch([v['x_u_d'], v['x_u_c']])), train, reuse=True,
-                                     tag=TL([('D/C_unl_d', nUD), ('D/C_unl', nUC)]))
-                idx, oh = ops.argmax_onehot(lg, K)
-                idx_d, idx_u = ops.Var(idx.data[:nUD], (nUD,)), ops.Var(idx.data[nUD:], (nUC,))
-                oh_d, oh_u = ops.Var(oh.data[:nUD], (nUD, K)), ops.Var(oh.data[nUD:], (nUC, K))
-            else:
-                c_unl_d, _ = m.classifier(pre(v['x_u_d']), train, reuse=True, tag='D/C_unl_d')
-                c_unl, _ = m.classifier(pre(v['x_u_c']), train, reuse=True, tag='D/C_unl')
-                idx_d, oh_d = ops.argmax_onehot(c_unl_d, K)
-                idx_u, oh_u = ops.argmax_onehot(c_unl, K)
-        ops.join_side()
-        G_const = ops.Var(G.data, G.shape)   # phase D sees the generated images as constants (var_list = d_vars)
-        fb = self._begin('discriminator', self.d_vars)
-        with recording():
-            X = ops.group_batch([v['x_l_d'], v['x_u_d'], G_const, v['x_u_c']])
-            Y = ops.group_batch([v['y_l_d'], oh_d, v['y_g'], oh_u])
-            X.aux = None                     # D is per-sample: one plain batch of 250
-            _, dl = m.discriminator(X, Y, reuse=True, tag=TL([('D/D_real', nLD + nUD), ('D/D_fake', nG), ('D/D_unl', nUC)]))
-            d_loss = ops.loss_d_grouped(dl, nLD + nUD, nG, nUC)
-            ops.backward(d_loss)
-        self._apply(fb, self.d_optimizer, group='discriminator')
-        self.aux = dict(idx_unl_d=idx_d, idx_unl=idx_u, G_phaseD=G, d_logits=dl)
-        # ---- phase G: sess.run([g_solver, g_loss]) (:270) ----
-        fb = self._begin('good_generator', self.g_vars)
-        with recording() as tape_d:
-            _, df = m.discriminator(G, v['y_g'], reuse=True, tag='G/D_fake')
-            g_loss = ops.loss_g(df)
-            g_loss.seed()
-            tape_d.backward()                # d g_loss / d G through D1 (dgrad only)
-        tape_g.backward()                    # ... and through the generator recorded in phase D
-        self._apply(fb, self.g_optimizer, group='good_generator')
+        d_loss = g_loss = None
+        if phases == 'C':
+            self.aux = {}
+        if 'D' in phases or 'G' in phases:
+            # ---- phase D: sess.run([d_solver, d_loss]) (:267) ----
+            ops.arena_reset()
+            # the generator forward (a chain of small kernels) runs on the side stream beside the classifier forward
+            for p in self.g_vars:                # record G(z, y) once, on its own tape, for phase G's backward
+                p.requires_grad = True
+            with ops.side_stream(), recording() as tape_g:
+                G = m.good_generator(v['z_g'], v['y_g'], reuse=True, tag='D/G')
+                G.data
+            with no_grad():
+                if grouped_c:
+                    lg, _ = m.classifier(pre(ops.group_batch([v['x_u_d'], v['x_u_c']])), train, reuse=True,
+                                         tag=TL([('D/C_unl_d', nUD), ('D/C_unl', nUC)]))
+                    idx, oh = ops.argmax_onehot(lg, K)
+                    idx_d, idx_u = ops.Var(idx.data[:nUD], (nUD,)), ops.Var(idx.data[nUD:], (nUC,))
+                    oh_d, oh_u = ops.Var(oh.data[:nUD], (nUD, K)), ops.Var(oh.data[nUD:], (nUC, K))
+                else:
+                    c_unl_d, _ = m.classifier(pre(v['x_u_d']), train, reuse=True, tag='D/C_unl_d')
+                    c_unl, _ = m.classifier(pre(v['x_u_c']), train, reuse=True, tag='D/C_unl')
+                    idx_d, oh_d = ops.argmax_onehot(c_unl_d, K)
+                    idx_u, oh_u = ops.argmax_onehot(c_unl, K)
+            ops.join_side()
+            G_const = ops.Var(G.data, G.shape)   # phase D sees the generated images as constants (var_list = d_vars)
+            fb = self._begin('discriminator', self.d_vars)
+            with recording():
+                X = ops.group_batch([v['x_l_d'], v['x_u_d'], G_const, v['x_u_c']])
+                Y = ops.group_batch([v['y_l_d'], oh_d, v['y_g'], oh_u])
+                X.aux = None                     # D is per-sample: one plain batch of 250
+                _, dl = m.discriminator(X, Y, reuse=True, tag=TL([('D/D_real', nLD + nUD), ('D/D_fake', nG), ('D/D_unl', nUC)]))
+                d_loss = ops.loss_d_grouped(dl, nLD + nUD, nG, nUC)
+                ops.backward(d_loss)
+            self._apply(fb, self.d_optimizer, group='discriminator')
+            self.aux = dict(idx_unl_d=idx_d, idx_unl=idx_u, G_phaseD=G, d_logits=dl)
+            # ---- phase G: sess.run([g_solver, g_loss]) (:270) ----
+            fb = self._begin('good_generator', self.g_vars)
+            with recording() as tape_d:
+                _, df = m.discriminator(G, v['y_g'], reuse=True, tag='G/D_fake')
+                g_loss = ops.loss_g(df)
+                g_loss.seed()
+                tape_d.backward()                # d g_loss / d G through D1 (dgrad only)
+            tape_g.backward()                    # ... and through the generator recorded in phase D
+            self._apply(fb, self.g_optimizer, group='good_generator')
         # ---- phase C: sess.run([c_solver, c_loss]) (:275) ----
         fb = self._begin('classifier', self.c_vars)
         with no_grad():
@@ -245,8 +249,9 @@ class Train(Train_base):
         if not ctx.rng.injected:
             _lib.call('tgan_counter_advance', ctx.rng.counter().data_ptr(), 1, ops._st())
         for i, l in enumerate((d_loss, g_loss, c_loss)):
-            _lib.call('tgan_copy_channels', l.value.data_ptr(), 0, 1, self.loss_buf.data_ptr() + 4 * i, 0, 1, 1, 1,
-                      ops._st())
+            if l is not None:
+                _lib.call('tgan_copy_channels', l.value.data_ptr(), 0, 1, self.loss_buf.data_ptr() + 4 * i, 0, 1, 1, 1,
+                          ops._st())
         return d_loss, g_loss, c_loss
 
     def load_batch(self, batch):
@@ -257,18 +262,19 @@ class Train(Train_base):
                 t = torch.from_numpy(t)
             self.inputs[k].copy_(t.reshape(self.inputs[k].shape), non_blocking=True)
 
-    def step(self, batch=None, lambda_1=None, lambda_2=0.0, lr=None, cla_lr=None, train=True):
+    def step(self, batch=None, lambda_1=None, lambda_2=0.0, lr=None, cla_lr=None, train=True, phases='DGC'):
         """One training iteration (Train_goodGAN.py:249-276).  Returns the device tensor
-        [d_loss, g_loss, c_loss] (values before each phase's update); no host synchronisation."""
+        [d_loss, g_loss, c_loss] (values before each phase's update); no host synchronisation.
+        phases='C' is the PRE_TRAIN iteration (:182-224): only `sess.run([c_solver, c_loss])`."""
         ctx.store = self.store
         if batch is not None:
             self.load_batch(batch)
         lam1 = self.config.FAKE_G_LAMBDA if lambda_1 is None else lambda_1
         self._set_scalars(lam1, lambda_2, lr, cla_lr)
-        if self.graph is not None:
+        if self.graph is not None and phases == 'DGC':
             self.graph.replay()
         else:
-            self._step_impl(train)
+            self._step_impl(train, phases)
         return self.loss_buf
 
     def capture(self, warmup=3):
@@ -291,7 +297,40 @@ class Train(Train_base):
         self.graph = g
         return g
 
-    # ------------------------------------------------------------------ epoch driver (next) -------
+    # ------------------------------------------------------------------ evaluation --
+    def evaluate(self, x, y, reset=True):
+        """Validation pass of Train_goodGAN.py:296-351 with the metric of :428-447: the classifier with train=False
+        (mean-only BN / BN use their population statistics, dropout is off, the Gaussian input-noise layer stays active as
+        in the reference graph), streaming accuracy of argmax(C(x)) against argmax(y).  x, y: numpy / tensors of one
+        validation batch.  Returns (streaming accuracy, predictions as an int64 device tensor)."""
+        ctx.store = self.store
+        if reset or not hasattr(self, '_acc'):
+            self._acc = [0, 0]                  # tf.metrics.accuracy's (total, count) local variables
+        tx = torch.as_tensor(np.asarray(x, np.float32)).to(ctx.device)
+        ty = torch.as_tensor(np.asarray(y, np.float32)).to(ctx.device)
+        with no_grad():
+            logits, _ = self.model.classifier(self._pre()(ops.Var(tx, tuple(tx.shape))), False, reuse=True, tag='V/C_real')
+            idx, _ = ops.argmax_onehot(logits, self.config.NUM_CLASSES)
+        self._acc[0] += int((idx.data == ty.argmax(dim=1)).sum().item())
+        self._acc[1] += int(tx.shape[0])
+        self.aux_val = dict(logits=logits)
+        return self._acc[0] / max(1, self._acc[1]), idx.data
+
+    # ------------------------------------------------------------------ epoch driver (SURVEY §8f rank 1) --
+    def train_epoch(self, batches, epoch, start_epoch=0):
+        """One epoch of Train_goodGAN.py:160-276: the lambda / learning-rate schedule of :165-177, the classifier-only
+        PRE_TRAIN iterations for the first 30 epochs when config.PRE_TRAIN is set (:182-224), the full D -> G -> C
+        iteration otherwise.  `batches` yields dicts with the 8 step inputs; returns the mean (d, g, c) losses."""
+        lam1, lam2, lr, cla_lr = self.schedule(epoch, start_epoch)
+        pre = bool(getattr(self.config, 'PRE_TRAIN', False)) and (start_epoch + epoch <= 30)
+        tot, n = torch.zeros(3, dtype=torch.float64), 0
+        for b in batches:
+            out = self.step(b, lambda_1=lam1, lambda_2=lam2, lr=lr, cla_lr=cla_lr, phases='C' if pre else 'DGC')
+            tot += out.detach().double().cpu()
+            n += 1
+        return (tot / max(n, 1)).tolist()
+
+    # ------------------------------------------------------------------ schedules ------------------
     def schedule(self, epoch, start_epoch=0):
         """lambda_1 / lambda_2 / lr schedule of Train_goodGAN.py:165-177 for (1-based) `epoch`."""
         c = self.config

@@ -158,3 +158,65 @@ def test_graph_capture_matches_eager():
         outs.append(np.stack(losses))
     # capture itself executes nothing, so step k of the replay run == step k of the eager run
     assert np.allclose(outs[0], outs[1], rtol=1e-5, atol=1e-6), (outs[0], outs[1])
+
+
+def test_pretrain_iteration_phase_c_only():
+    """PRE_TRAIN (Train_goodGAN.py:182-224): only sess.run([c_solver, c_loss]) -- classifier updated, D and G untouched."""
+    import tgan
+    from tgan import core
+    P, S = O.init_params('cifar10', seed=5)
+    zca = O.make_zca(3)
+    orc = O.OracleTrainer('cifar10', P, S, zca, dtype=torch.float64, scale=10)
+    tgan.init('cuda:0', math='fp32')
+    tr = tgan.make_trainer('cifar10', scale=10, init=(P, S), zca=zca)
+    before = {p.name: tnp(p.data).copy() for g in ('discriminator', 'good_generator') for p in tr.store.flat[g]['params']}
+    rng = O.TagRNG(7)
+    core.ctx.rng = core.InjectedSource(rng)
+    batch = O.make_batch(orc.cfg, seed=8)
+    ref = orc.step(batch, rng, 0.3, 0.5, phases='C')
+    o32 = O.OracleTrainer('cifar10', P, S, zca, dtype=torch.float32, scale=10)      # float32 noise floor of the oracle itself
+    o32.step(batch, rng, 0.3, 0.5, phases='C')
+    got = tr.step(batch, lambda_1=0.3, lambda_2=0.5, phases='C').cpu().numpy()
+    assert abs(got[2] - ref[2]) < 2e-5 * max(1.0, abs(ref[2]))
+    fb = tr.store.flat['classifier']
+    scale = max(float(orc.last_grads['C'][p.name].abs().max()) for p in fb['params'])
+    for p, o in zip(fb['params'], fb['offsets']):
+        g = tnp(fb['grad'][o:o + p.size]).reshape(p.shape)
+        r = orc.last_grads['C'][p.name].numpy()
+        den = max(np.abs(r).max(), 1e-3 * scale)
+        floor = float(np.abs(o32.last_grads['C'][p.name].detach().double().numpy() - r).max() / den)
+        # the stated tolerance, or 8x the float32 noise floor the oracle itself shows (weight-norm gradients cancel heavily)
+        assert np.abs(g - r).max() / den < max(2e-4, 8 * floor), (p.name, floor)
+    for name, val in before.items():
+        assert np.array_equal(tnp(tr.store.vars[name].data), val), name + ' changed in a classifier-only iteration'
+
+
+@pytest.mark.parametrize('math,tol', [('fp32', 2e-5), ('bf16', 5e-2)])
+def test_evaluate_matches_oracle(math, tol):
+    """validation pass (Train_goodGAN.py:296-351, metric :428-447): train=False logits and streaming accuracy"""
+    import tgan
+    from tgan import core
+    P, S = O.init_params('cifar10', seed=5)
+    for k in S:                                    # non-trivial population statistics
+        S[k] = S[k] + 0.05 * np.random.default_rng(1).standard_normal(S[k].shape).astype(np.float32)
+    zca = O.make_zca(3)
+    orc = O.OracleTrainer('cifar10', P, S, zca, dtype=torch.float64, scale=10)
+    tgan.init('cuda:0', math=math)
+    tr = tgan.make_trainer('cifar10', scale=10, init=(P, S), zca=zca)
+    rs = np.random.default_rng(3)
+    tot = cnt = 0
+    for i in range(2):
+        x = rs.uniform(-1, 1, (16, 32, 32, 3)).astype(np.float32)
+        y = np.eye(10, dtype=np.float32)[rs.integers(0, 10, 16)]
+        rng = O.TagRNG(20 + i)
+        core.ctx.rng = core.InjectedSource(rng)
+        ref = orc.evaluate(x, rng).numpy()
+        acc, pred = tr.evaluate(x, y, reset=(i == 0))
+        got = tr.aux_val['logits'].numpy()
+        assert relerr(got, ref) < tol
+        top2 = np.sort(ref, axis=1)
+        sure = (top2[:, -1] - top2[:, -2]) > 10 * tol * np.abs(ref).max()
+        assert np.array_equal(pred.cpu().numpy()[sure], ref.argmax(1)[sure])
+        tot += int((pred.cpu().numpy() == y.argmax(1)).sum())
+        cnt += 16
+        assert abs(acc - tot / cnt) < 1e-12

@@ -110,3 +110,30 @@ def test_no_gpu_means_loud_failure():
         pytest.skip('GPU present')
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         tgan.init('cuda:0')
+
+
+def test_train_epoch_uses_schedule_and_pretrain_phase():
+    """Train.train_epoch (Train_goodGAN.py:160-276): lambda / lr schedule per epoch, classifier-only iterations while
+    PRE_TRAIN and epoch <= 30 -- checked on the host with the step stubbed out (no GPU)."""
+    import torch
+    import tgan
+    tr = tgan.make_trainer('cifar10', build_only=True)
+    calls = []
+
+    def fake_step(batch, **kw):
+        calls.append(kw)
+        return torch.tensor([1.0, 2.0, 3.0])
+    tr.step = fake_step
+    tr.config.PRE_TRAIN = True
+    out = tr.train_epoch([{}, {}], epoch=5)
+    assert out == [1.0, 2.0, 3.0] and len(calls) == 2 and all(c['phases'] == 'C' for c in calls)
+    assert calls[0]['lambda_1'] == 0.0 and calls[0]['lambda_2'] == 0
+    calls.clear()
+    tr.train_epoch([{}], epoch=31)
+    assert calls[0]['phases'] == 'DGC'
+    calls.clear()
+    tr.config.PRE_TRAIN = False
+    tr.train_epoch([{}], epoch=301)
+    c = tr.config
+    assert calls[0]['lambda_1'] == c.FAKE_G_LAMBDA and calls[0]['lambda_2'] == 0.5
+    assert abs(calls[0]['lr'] - c.LEARNING_RATE * 0.995 ** 2) < 1e-12 and abs(calls[0]['cla_lr'] - c.CLA_LEARNINIG_RATE * 0.99 ** 2) < 1e-12

@@ -1,6 +1,9 @@
 """warm per-kernel timings of the eager CIFAR-10 step via torch.profiler (CUPTI): aggregated by kernel name and a
 chronological list (name, grid, us) of one step -> gpurun_out/prof_step_{agg,seq}.txt"""
-import sys, collections
+import sys, collections, os
+# per-kernel attribution needs plain stream order: with programmatic dependent launch a kernel starts (and is timed)
+# while its predecessor is still running, waiting at griddepcontrol.wait
+os.environ.setdefault('TGAN_NO_PDL', '1')
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tensorflow-implementation-of-triple-gan_b200')
 import torch, tgan
 from tgan import synthetic
