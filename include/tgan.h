@@ -254,6 +254,19 @@ int tgan_maxpool2_dropout_fwd(const void* x, void* y, uint8_t* code, int N, int 
                               void* stream);
 int tgan_maxpool2_dropout_bwd(const void* dy, const uint8_t* code, void* dx, int N, int H, int W, int C, float rate,
                               void* stream);
+/* mean-only BN apply + nonlinearity + 2x2 max pool + dropout in one pass (conv1_3 / conv2_3 of the classifier,
+ * Good_GAN_cifar10.py:118-124, 137-143); the full-resolution activation is never materialised.  z: bf16 [N,H,W,C],
+ * segments in IMAGES (n0,n1,n2 = exclusive end images of segments 0..2), sums fp32 [nseg][C] as tgan_mobn_apply_seg.
+ * y / code as tgan_maxpool2_dropout_fwd.  bwd: du[N,H,W,C] = at the window winner keep * dy/(1-rate) * act'(y_winner),
+ * zero elsewhere; colsums[seg][c] = per-segment sums of du, grad_acc[c] += total (the bias gradient).
+ * ws: 4*TGAN_ACT_BWD_SEG_PARTS*C floats. */
+int tgan_mobn_pool_dropout_fwd(const void* z, void* y, uint8_t* code, int N, int H, int W, int C, int nseg, int64_t n0,
+                               int64_t n1, int64_t n2, const float* sums, const float* b, float* pop_mean, float decay,
+                               int train, int act, float alpha, float rate, const uint8_t* mask, uint64_t seed,
+                               uint64_t stream_id, const uint64_t* counter, void* stream);
+int tgan_mobn_pool_dropout_bwd(const void* dy, const void* y, const uint8_t* code, void* du, int N, int H, int W, int C,
+                               int nseg, int64_t n0, int64_t n1, int64_t n2, int act, float alpha, float rate,
+                               float* colsums, float* grad_acc, float* ws, void* stream);
 /* global pooling over H*W: mode 0 = max (max_pooling2d(6,1) 'avg_pool_0', Good_GAN_cifar10.py:163),
  * mode 1 = mean (average_pooling2d(8,1) :94; reduce_mean([1,2]) Good_GAN.py:157,243,295). */
 int tgan_global_pool_fwd(const void* x, int xdt, void* y, int ydt, uint8_t* idx, int N, int HW, int C,

@@ -273,15 +273,15 @@ __global__ void __launch_bounds__(256) act_bwd_seg_v8_kernel(const bf16* __restr
     partials[(size_t)blockIdx.x * 4 * C + i] = t;
   }
 }
-// 256 threads = 32 channels x 8 part lanes; fixed summation order -> deterministic
+// 256 threads = 8 channels x 32 part lanes (C/8 CTAs); fixed summation order -> deterministic
 __global__ void __launch_bounds__(256) act_bwd_seg_fold_kernel(const float* __restrict__ partials, int nparts, int C,
                                                                float* __restrict__ colsums, float* __restrict__ grad_acc) {
   pdl_entry();
-  __shared__ double sm[8][4][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, c = blockIdx.x * 32 + tx;
+  __shared__ double sm[32][4][9];
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3, c = blockIdx.x * 8 + tx;
   double t[4] = {0.0, 0.0, 0.0, 0.0};
   if (c < C)
-    for (int p = ty; p < nparts; p += 8)
+    for (int p = ty; p < nparts; p += 32)
 #pragma unroll
       for (int a = 0; a < 4; ++a) t[a] += (double)partials[((size_t)p * 4 + a) * C + c];
 #pragma unroll
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(256) act_bwd_seg_fold_kernel(const float* __re
     for (int a = 0; a < 4; ++a) {
       double u = 0.0;
 #pragma unroll
-      for (int l = 0; l < 8; ++l) u += sm[l][a][tx];
+      for (int l = 0; l < 32; ++l) u += sm[l][a][tx];
       colsums[a * C + c] = (float)u;
       tot += u;
     }
@@ -541,6 +541,149 @@ __global__ void maxpool2_dropout_bwd_kernel(const bf16* __restrict__ dy, const u
   st8(dx, p0, o[0]); st8(dx, p0 + C, o[1]); st8(dx, p0 + (int64_t)W * C, o[2]); st8(dx, p0 + (int64_t)W * C + C, o[3]);
 }
 
+// ---- mean-only BN apply + nonlinearity + 2x2 max pool + dropout in ONE pass (conv1_3 / conv2_3 of the classifier,
+// Good_GAN_cifar10.py:118-124, 137-143).  The full-resolution activation y is never written: the pool's gradient only
+// reaches the window winners, and the winner of y is the winner of its pre-activation (monotonic nonlinearity), so the
+// backward needs y at the winners only -- which is the pooled output itself.  bf16, C % 8 == 0, one thread = 8 channels
+// of one pooled pixel.  Same code byte and Philox stream as maxpool2_dropout_fwd_kernel.
+template <int ACT>
+__global__ void mobn_pool_dropout_fwd_kernel(const bf16* __restrict__ z, bf16* __restrict__ y, uint8_t* __restrict__ code,
+                                             int H, int W, int C, int64_t nvec, const float* __restrict__ sums, Segs sg,
+                                             int rows_per_img, const float* __restrict__ b, float* __restrict__ pop_mean,
+                                             float decay, int train, float alpha, float rate, float scale,
+                                             const uint8_t* __restrict__ mask, uint64_t seed, uint64_t stream_id,
+                                             const uint64_t* __restrict__ counter) {
+  pdl_entry();
+  if (train && pop_mean && blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float pm = pop_mean[c];
+      for (int s = 0; s < sg.n; ++s) pm = pm * decay + sums[s * C + c] * sg.inv_rows[s] * (1.f - decay);
+      pop_mean[c] = pm;
+    }
+  }
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nvec) return;
+  const int cv = C / 8, Wo = W / 2, Ho = H / 2;
+  const int c = (int)(i % cv) * 8;
+  int64_t t = i / cv;
+  const int wo = (int)(t % Wo); t /= Wo;
+  const int ho = (int)(t % Ho);
+  const int64_t n = t / Ho;
+  const int s = sg.of(n * rows_per_img);                    // segments are whole images
+  const int64_t p0 = ((n * H + 2 * ho) * W + 2 * wo) * C + c;
+  float a[4][8];
+  ld8(z, p0, a[0]); ld8(z, p0 + C, a[1]); ld8(z, p0 + (int64_t)W * C, a[2]); ld8(z, p0 + (int64_t)W * C + C, a[3]);
+  const float4* bp = reinterpret_cast<const float4*>(b + c);
+  const float4* mp = reinterpret_cast<const float4*>((train ? sums + (int64_t)s * C : pop_mean) + c);
+  const float msc = train ? sg.inv_rows[s] : 1.f;
+  const float4 b0 = bp[0], b1 = bp[1], m0 = mp[0], m1 = mp[1];
+  const float sh[8] = {b0.x - m0.x * msc, b0.y - m0.y * msc, b0.z - m0.z * msc, b0.w - m0.w * msc,
+                       b1.x - m1.x * msc, b1.y - m1.y * msc, b1.z - m1.z * msc, b1.w - m1.w * msc};
+  uint8_t keep[8];
+  const int64_t e = i * 8;
+  if (rate <= 0.f) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) keep[j] = 1;
+  } else if (mask) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) keep[j] = mask[e + j];
+  } else {
+    const uint64_t ctr = counter ? *counter : 0;
+    Philox ph(seed);
+    const uint4 r0 = ph((uint64_t)(e / 4), stream_id + (ctr << 20)), r1 = ph((uint64_t)(e / 4 + 1), stream_id + (ctr << 20));
+    const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) keep[j] = u32_to_unit(rr[j]) >= rate;
+  }
+  float o[8];
+  uint8_t cd[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    // the unfused path stores y in bf16 before pooling: round each candidate the same way
+    float q[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) q[k] = __bfloat162float(__float2bfloat16_rn(act_fwd_t<ACT>(a[k][j] + sh[j], alpha)));
+    float m = q[0]; int k = 0;
+    if (q[1] > m) { m = q[1]; k = 1; }
+    if (q[2] > m) { m = q[2]; k = 2; }
+    if (q[3] > m) { m = q[3]; k = 3; }
+    o[j] = keep[j] ? m * scale : 0.f;
+    cd[j] = (uint8_t)(k | (keep[j] << 2));
+  }
+  st8(y, e, o);
+  uint2 cw;
+  cw.x = cd[0] | (cd[1] << 8) | (cd[2] << 16) | ((uint32_t)cd[3] << 24);
+  cw.y = cd[4] | (cd[5] << 8) | (cd[6] << 16) | ((uint32_t)cd[7] << 24);
+  *reinterpret_cast<uint2*>(code + e) = cw;
+}
+
+// backward of the fused pass: du (full resolution) = winner ? keep * dy/(1-rate) * act'(y_winner) : 0, with per-segment
+// column sums of du (partials per CTA, folded by act_bwd_seg_fold_kernel).  y_winner = pooled output * (1-rate) where kept.
+// 256 threads = (C/8 channel groups) x (2048/C pooled-pixel lanes); contiguous pooled-pixel ranges per CTA.
+template <int ACT>
+__global__ void __launch_bounds__(256) mobn_pool_dropout_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ yp,
+                                                                    const uint8_t* __restrict__ code, bf16* __restrict__ du,
+                                                                    int H, int W, int C, int64_t prow_total, Segs sg,
+                                                                    int rows_per_img, float alpha, float scale,
+                                                                    float* __restrict__ partials) {
+  pdl_entry();
+  extern __shared__ float abs_sm[];              // [lanes][4][C]
+  const int cg = C / 8, rl = 256 / cg;
+  const int tc = threadIdx.x % cg, tr = threadIdx.x / cg;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) abs_sm[((size_t)tr * 4 + a) * C + tc * 8 + j] = 0.f;
+  const int Wo = W / 2, Ho = H / 2;
+  const int64_t per = ((prow_total + gridDim.x - 1) / gridDim.x + rl - 1) / rl * rl;
+  const int64_t rbeg = (int64_t)blockIdx.x * per, rend = rbeg + per < prow_total ? rbeg + per : prow_total;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  int cur = -1;
+  const float inv_scale = 1.f / scale;
+  for (int64_t r = rbeg + tr; r < rend; r += rl) {          // r = pooled pixel index (n, ho, wo)
+    const int wo = (int)(r % Wo);
+    const int ho = (int)((r / Wo) % Ho);
+    const int64_t n = r / ((int64_t)Wo * Ho);
+    const int s = sg.of(n * rows_per_img);
+    if (s != cur) {
+      if (cur >= 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { abs_sm[((size_t)tr * 4 + cur) * C + tc * 8 + j] += acc[j]; acc[j] = 0.f; }
+      }
+      cur = s;
+    }
+    const int64_t e = r * C + tc * 8;
+    float d[8], yv[8];
+    ld8(dy, e, d); ld8(yp, e, yv);
+    const uint2 cw = *reinterpret_cast<const uint2*>(code + e);
+    const uint32_t cws[2] = {cw.x, cw.y};
+    float o[4][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t cd = (cws[j >> 2] >> (8 * (j & 3))) & 0xff;
+      const float g = (cd & 4) ? d[j] * scale * act_grad_from_y_t<ACT>(yv[j] * inv_scale, alpha) : 0.f;
+      const float gq = __bfloat162float(__float2bfloat16_rn(g));      // du is stored in bf16: sum what is stored
+      const int k = cd & 3;
+      o[0][j] = k == 0 ? gq : 0.f; o[1][j] = k == 1 ? gq : 0.f; o[2][j] = k == 2 ? gq : 0.f; o[3][j] = k == 3 ? gq : 0.f;
+      acc[j] += gq;
+    }
+    const int64_t p0 = ((n * H + 2 * ho) * W + 2 * wo) * C + tc * 8;
+    st8(du, p0, o[0]); st8(du, p0 + C, o[1]); st8(du, p0 + (int64_t)W * C, o[2]); st8(du, p0 + (int64_t)W * C + C, o[3]);
+  }
+  if (cur >= 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) abs_sm[((size_t)tr * 4 + cur) * C + tc * 8 + j] += acc[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * C; i += 256) {
+    float t = 0.f;
+    for (int l = 0; l < rl; ++l) t += abs_sm[(size_t)l * 4 * C + i];
+    partials[(size_t)blockIdx.x * 4 * C + i] = t;
+  }
+}
+
 template <typename TX, typename TY>
 __global__ void global_pool_fwd_kernel(const TX* __restrict__ x, TY* __restrict__ y, uint8_t* __restrict__ idx,
                                        int N, int HW, int C, int mode) {
@@ -730,7 +873,7 @@ extern "C" int tgan_act_bwd_seg(const void* dy, int dydt, const void* y, int ydt
     cudaStream_t st = (cudaStream_t)stream;
     TGAN_DISPATCH_ACT(act, A, (pdl_launch(act_bwd_seg_v8_kernel<A>, nparts, 256, smem, (cudaStream_t)(st), (const bf16*)dy, (const bf16*)y, (bf16*)du, rows, C, sg, alpha, ws)));
     TGAN_LAUNCHED();
-    pdl_launch(act_bwd_seg_fold_kernel, ceil_div(C, 32), 256, 0, (cudaStream_t)(st), ws, nparts, C, colsums, grad_acc);
+    pdl_launch(act_bwd_seg_fold_kernel, ceil_div(C, 8), 256, 0, (cudaStream_t)(st), ws, nparts, C, colsums, grad_acc);
     TGAN_LAUNCHED();
     return 0;
   }
@@ -903,6 +1046,51 @@ extern "C" int tgan_maxpool2_dropout_bwd(const void* dy, const uint8_t* code, vo
                  "maxpool2_dropout_bwd: bad args");
   const int64_t nvec = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
   pdl_launch(maxpool2_dropout_bwd_kernel, ceil_div(nvec, 256), 256, 0, (cudaStream_t)((cudaStream_t)stream), (const bf16*)dy, code, (bf16*)dx, H, W, C, nvec, 1.0f / (1.0f - rate));
+  TGAN_LAUNCHED();
+  return 0;
+}
+
+extern "C" int tgan_mobn_pool_dropout_fwd(const void* z, void* y, uint8_t* code, int N, int H, int W, int C, int nseg,
+                                          int64_t n0, int64_t n1, int64_t n2, const float* sums, const float* b,
+                                          float* pop_mean, float decay, int train, int act, float alpha, float rate,
+                                          const uint8_t* mask, uint64_t seed, uint64_t stream_id, const uint64_t* counter,
+                                          void* stream) {
+  TGAN_CHECK_ARG(z && y && code && b && H % 2 == 0 && W % 2 == 0 && C % 8 == 0 && rate >= 0.f && rate < 1.f &&
+                     aligned16(z) && aligned16(y) && aligned16(b) && ((uintptr_t)code & 7) == 0,
+                 "mobn_pool_dropout_fwd: bf16, even extents, C %% 8 == 0, aligned buffers");
+  TGAN_CHECK_ARG(train ? (sums != nullptr && aligned16(sums)) : (pop_mean != nullptr && aligned16(pop_mean)),
+                 "mobn_pool_dropout_fwd: needs sums (train) or pop_mean (test)");
+  TGAN_CHECK_ARG(act == TGAN_ACT_NONE || act == TGAN_ACT_RELU || act == TGAN_ACT_LRELU || act == TGAN_ACT_TANH ||
+                     act == TGAN_ACT_SIGMOID || act == TGAN_ACT_SOFTPLUS, "mobn_pool_dropout_fwd: monotonic activations only");
+  const int rpi = H * W;
+  Segs sg;      // segment boundaries are given in images; Segs works on full-resolution rows
+  if (make_segs(sg, (int64_t)N * rpi, nseg, n0 * rpi, n1 * rpi, n2 * rpi)) return 1;
+  const int64_t nvec = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  TGAN_DISPATCH_ACT(act, A, (pdl_launch(mobn_pool_dropout_fwd_kernel<A>, ceil_div(nvec, 256), 256, 0, st, (const bf16*)z,
+                                        (bf16*)y, code, H, W, C, nvec, sums, sg, rpi, b, pop_mean, decay, train, alpha, rate,
+                                        1.0f / (1.0f - rate), mask, seed, stream_id, counter)));
+  TGAN_LAUNCHED();
+  return 0;
+}
+extern "C" int tgan_mobn_pool_dropout_bwd(const void* dy, const void* y, const uint8_t* code, void* du, int N, int H, int W,
+                                          int C, int nseg, int64_t n0, int64_t n1, int64_t n2, int act, float alpha,
+                                          float rate, float* colsums, float* grad_acc, float* ws, void* stream) {
+  TGAN_CHECK_ARG(dy && y && code && du && colsums && ws && H % 2 == 0 && W % 2 == 0 && C % 8 == 0 && 2048 % C == 0 &&
+                     C >= 64 && aligned16(dy) && aligned16(y) && aligned16(du),
+                 "mobn_pool_dropout_bwd: bf16, even extents, C in {64,128,256,512,1024,2048}, aligned buffers");
+  const int rpi = H * W;
+  Segs sg;
+  if (make_segs(sg, (int64_t)N * rpi, nseg, n0 * rpi, n1 * rpi, n2 * rpi)) return 1;
+  const int nparts = TGAN_ACT_BWD_SEG_PARTS;
+  const size_t smem = (size_t)(2048 / C) * 4 * C * sizeof(float);
+  const int64_t prows = (int64_t)N * (H / 2) * (W / 2);
+  cudaStream_t st = (cudaStream_t)stream;
+  TGAN_DISPATCH_ACT(act, A, (pdl_launch(mobn_pool_dropout_bwd_kernel<A>, nparts, 256, smem, st, (const bf16*)dy,
+                                        (const bf16*)y, code, (bf16*)du, H, W, C, prows, sg, rpi, alpha, 1.0f / (1.0f - rate),
+                                        ws)));
+  TGAN_LAUNCHED();
+  pdl_launch(act_bwd_seg_fold_kernel, ceil_div(C, 8), 256, 0, st, ws, nparts, C, colsums, grad_acc);
   TGAN_LAUNCHED();
   return 0;
 }

@@ -298,6 +298,15 @@ def _deferred(v):
     return v._data is None and isinstance(v._lazy, Deferred)
 
 
+class MobnDeferred:
+    """a mean-only-BN apply waiting to learn whether a 2x2 max pool (+ dropout) follows: if so the three run as one pass
+    and the full-resolution activation is never written (ops.mobn_act / ops.max_pool2)"""
+    __slots__ = ('run_plain', 'run_pooled')
+
+    def __init__(self, run_plain, run_pooled):
+        self.run_plain, self.run_pooled = run_plain, run_pooled
+
+
 class PoolDeferred:
     """a 2x2 max pool waiting to learn whether a dropout follows (the classifier's max_pool -> dropout pairs run as one
     kernel forward and one backward)"""
@@ -534,6 +543,9 @@ def lazy_bias(z, b):
 
 
 def _materialize(v, out_ld=None):
+    if isinstance(v._lazy, MobnDeferred):
+        v._lazy.run_plain()
+        return
     if isinstance(v._lazy, PoolDeferred):
         v._lazy.run(0.0, None)
         return
@@ -586,9 +598,10 @@ def mobn_act(z, b, pop_mean, train, act='none', alpha=0.2, decay=0.9):
     zd = z.data
     ez = zd.element_size()
     cs_all = z.aux.get('colsum') if z.aux else None      # [nseg, C] accumulated by the tcgen05 GEMM epilogue
-    y = _new(z.shape, _out_dtype(C))
-    ey = y.element_size()
-    fused = zd.dtype == torch.bfloat16 and y.dtype == torch.bfloat16 and C % 8 == 0 and len(segs) <= 4
+    ydt = _out_dtype(C)
+    fused = zd.dtype == torch.bfloat16 and ydt == torch.bfloat16 and C % 8 == 0 and len(segs) <= 4
+    tape = ctx.tape
+    out = _prop(Var(None, z.shape, requires_grad=rg), z)
 
     def seg_stats():
         s_all = _new((len(segs), C), torch.float32)
@@ -597,50 +610,94 @@ def mobn_act(z, b, pop_mean, train, act='none', alpha=0.2, decay=0.9):
                       None, 0.0, _p(ctx.ws()), _st())
         return s_all
 
-    if fused:       # one launch for the whole grouped batch, nonlinearity included
-        sums = (cs_all if cs_all is not None else seg_stats()) if train else None
-        _lib.call('tgan_mobn_apply_seg', _p(zd), _p(y), rows, C, len(segs), ends[0], ends[1], ends[2], _p(sums),
-                  _p(b.data), _p(pop_mean.data), decay, 1 if train else 0, a, alpha, _st())
-    else:
-        for i, (b0, nr) in enumerate(bounds):
-            s = None
-            if train:
-                if cs_all is not None:
-                    s = cs_all[i * C:(i + 1) * C]
-                else:
-                    s = _new((C,), torch.float32)
-                    _lib.call('tgan_channel_stats', zd.data_ptr() + b0 * C * ez, dt_code(zd), nr, C, _p(s), None, 0.0,
-                              _p(ctx.ws()), _st())
-            _lib.call('tgan_mobn_apply', zd.data_ptr() + b0 * C * ez, dt_code(zd), y.data_ptr() + b0 * C * ey, dt_code(y),
-                      nr, C, _p(s), _p(b.data), _p(pop_mean.data), decay, 1 if train else 0, a, alpha, _st())
-    out = _prop(Var(y, z.shape, requires_grad=rg), z)
-    if rg:
-        def bwd():
-            if out.grad is None:
-                return
-            dy = out.grad
-            du = _new(z.shape, zd.dtype)
-            ed, eu = dy.element_size(), du.element_size()
-            if fused:
-                cs = _new((4, C), torch.float32)
-                _lib.call('tgan_act_bwd_seg', _p(dy), dt_code(dy), _p(y), dt_code(y), _p(du), dt_code(du), rows, C,
-                          len(segs), ends[0], ends[1], ends[2], a, alpha, _p(cs),
-                          _p(b.grad) if b.requires_grad else None, _p(ctx.ws()), _st())
-                if z.requires_grad and train:
-                    _lib.call('tgan_sub_channel_mean_seg', _p(du), _p(du), rows, C, len(segs), ends[0], ends[1], ends[2],
-                              _p(cs), _st())
-            else:
-                for b0, nr in bounds:
-                    cs = _new((C,), torch.float32)
-                    _lib.call('tgan_act_bwd', dy.data_ptr() + b0 * C * ed, dt_code(dy), y.data_ptr() + b0 * C * ey,
-                              dt_code(y), du.data_ptr() + b0 * C * eu, dt_code(du), nr, C, a, alpha, _p(cs),
+    def run_plain():
+        y = _new(z.shape, ydt)
+        ey = y.element_size()
+        if fused:       # one launch for the whole grouped batch, nonlinearity included
+            sums = (cs_all if cs_all is not None else seg_stats()) if train else None
+            _lib.call('tgan_mobn_apply_seg', _p(zd), _p(y), rows, C, len(segs), ends[0], ends[1], ends[2], _p(sums),
+                      _p(b.data), _p(pop_mean.data), decay, 1 if train else 0, a, alpha, _st())
+        else:
+            for i, (b0, nr) in enumerate(bounds):
+                s = None
+                if train:
+                    if cs_all is not None:
+                        s = cs_all[i * C:(i + 1) * C]
+                    else:
+                        s = _new((C,), torch.float32)
+                        _lib.call('tgan_channel_stats', zd.data_ptr() + b0 * C * ez, dt_code(zd), nr, C, _p(s), None, 0.0,
+                                  _p(ctx.ws()), _st())
+                _lib.call('tgan_mobn_apply', zd.data_ptr() + b0 * C * ez, dt_code(zd), y.data_ptr() + b0 * C * ey, dt_code(y),
+                          nr, C, _p(s), _p(b.data), _p(pop_mean.data), decay, 1 if train else 0, a, alpha, _st())
+        out._data, out._lazy = y, None
+        if out.requires_grad and tape is not None:
+            def bwd():
+                if out.grad is None:
+                    return
+                dy = out.grad
+                du = _new(z.shape, zd.dtype)
+                ed, eu = dy.element_size(), du.element_size()
+                if fused:
+                    cs = _new((4, C), torch.float32)
+                    _lib.call('tgan_act_bwd_seg', _p(dy), dt_code(dy), _p(y), dt_code(y), _p(du), dt_code(du), rows, C,
+                              len(segs), ends[0], ends[1], ends[2], a, alpha, _p(cs),
                               _p(b.grad) if b.requires_grad else None, _p(ctx.ws()), _st())
                     if z.requires_grad and train:
-                        _lib.call('tgan_sub_channel_mean', du.data_ptr() + b0 * C * eu, dt_code(du),
-                                  du.data_ptr() + b0 * C * eu, dt_code(du), nr, C, _p(cs), _st())
-            if z.requires_grad:
-                add_grad(z, du)
-        ctx.tape.nodes.append(bwd)
+                        _lib.call('tgan_sub_channel_mean_seg', _p(du), _p(du), rows, C, len(segs), ends[0], ends[1], ends[2],
+                                  _p(cs), _st())
+                else:
+                    for b0, nr in bounds:
+                        cs = _new((C,), torch.float32)
+                        _lib.call('tgan_act_bwd', dy.data_ptr() + b0 * C * ed, dt_code(dy), y.data_ptr() + b0 * C * ey,
+                                  dt_code(y), du.data_ptr() + b0 * C * eu, dt_code(du), nr, C, a, alpha, _p(cs),
+                                  _p(b.grad) if b.requires_grad else None, _p(ctx.ws()), _st())
+                        if z.requires_grad and train:
+                            _lib.call('tgan_sub_channel_mean', du.data_ptr() + b0 * C * eu, dt_code(du),
+                                      du.data_ptr() + b0 * C * eu, dt_code(du), nr, C, _p(cs), _st())
+                if z.requires_grad:
+                    add_grad(z, du)
+            tape.nodes.append(bwd)
+
+    poolable = (fused and len(z.shape) == 4 and z.shape[1] % 2 == 0 and z.shape[2] % 2 == 0 and C >= 64 and 2048 % C == 0
+                and z.ld == C)
+    if not poolable:
+        run_plain()
+        return out
+
+    def run_pooled(pout, rate, tag):
+        """mean-only BN + nonlinearity + 2x2 max pool (+ dropout) in one pass; `out` (full resolution) is never written"""
+        N, H, W = z.shape[0], z.shape[1], z.shape[2]
+        iends = [sum(segs[:i + 1]) for i in range(len(segs) - 1)] + [0, 0, 0]       # segment ends in images
+        y, code = _new(pout.shape, torch.bfloat16), _new(pout.shape, torch.uint8)
+        sums = (cs_all if cs_all is not None else seg_stats()) if train else None
+        rng = ctx.rng
+        mask, seed, sid, ctr = None, 0, 0, None
+        if rate > 0 and rng.injected:
+            mask = _rng_mask(tag, pout.shape, rate)
+        elif rate > 0:
+            seed, sid, ctr = rng.seed, rng.stream_id(str(tag)), rng.counter()
+        _lib.call('tgan_mobn_pool_dropout_fwd', _p(zd), _p(y), _p(code), N, H, W, C, len(segs), iends[0], iends[1], iends[2],
+                  _p(sums), _p(b.data), _p(pop_mean.data), decay, 1 if train else 0, a, alpha, float(rate), _p(mask), seed,
+                  sid, _p(ctr), _st())
+        pout._data, pout._lazy = y, None
+        out._lazy = None                 # consumed: the full-resolution activation does not exist
+        if pout.requires_grad and tape is not None:
+            def bwd():
+                if pout.grad is None:
+                    return
+                du = _new(z.shape, torch.bfloat16)
+                cs = _new((4, C), torch.float32)
+                _lib.call('tgan_mobn_pool_dropout_bwd', _p(_cast(pout.grad, torch.bfloat16)), _p(y), _p(code), _p(du), N, H, W,
+                          C, len(segs), iends[0], iends[1], iends[2], a, alpha, float(rate), _p(cs),
+                          _p(b.grad) if b.requires_grad else None, _p(ctx.ws()), _st())
+                if z.requires_grad:
+                    if train:
+                        _lib.call('tgan_sub_channel_mean_seg', _p(du), _p(du), rows, C, len(segs), ends[0], ends[1], ends[2],
+                                  _p(cs), _st())
+                    add_grad(z, du)
+            tape.nodes.append(bwd)
+
+    out._lazy = MobnDeferred(run_plain, run_pooled)
     return out
 
 
@@ -752,6 +809,11 @@ def max_pool2(x):
     rg = _on() and x.requires_grad
     if ctx.building:
         return Var(None, oshape, requires_grad=rg)
+    if x._data is None and isinstance(x._lazy, MobnDeferred):
+        out = _prop(Var(None, oshape, requires_grad=rg), x)
+        fuse = x._lazy.run_pooled
+        out._lazy = PoolDeferred(lambda rate, tag: fuse(out, rate, tag))
+        return out
     xd = x.data
     if ctx.math == 'bf16' and xd.dtype == torch.bfloat16 and C % 8 == 0 and x.ld == C:
         out = _prop(Var(None, oshape, requires_grad=rg), x)

@@ -42,3 +42,20 @@ def test_only_sm100a_code_is_embedded():
     out = subprocess.run(['cuobjdump', '-lelf', _lib._SO], capture_output=True, text=True).stdout
     archs = {l.split('.')[-2] for l in out.splitlines() if 'sm_' in l}
     assert archs == {'sm_100a'}, out
+
+
+def test_every_kernel_has_the_pdl_entry():
+    """all launches carry the programmatic-stream-serialization attribute (common.cuh: pdl_launch), so a kernel that did
+    not wait on its predecessor (pdl_entry / pdl_trigger + pdl_wait) would race with it"""
+    import glob
+    import re
+    csrc = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tensorflow-implementation-of-triple-gan_b200', 'csrc')
+    n = 0
+    for f in sorted(glob.glob(os.path.join(csrc, '*.cu')) + glob.glob(os.path.join(csrc, '*.cuh'))):
+        src = open(f).read()
+        assert '<<<' not in src, f + ': raw launch (use pdl_launch)'
+        for m in re.finditer(r'__global__', src):
+            body = src[src.index('{', src.index(')', m.end())):][:400]
+            assert 'pdl_entry();' in body or 'pdl_trigger();' in body, (f, src[m.start():m.start() + 120])
+            n += 1
+    assert n >= 45

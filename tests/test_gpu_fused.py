@@ -207,3 +207,57 @@ def test_row_halo_equals_per_tap(c):
         assert relerr(a, b_) < 4e-3
     yt = O.conv2d_tf(T(x), T(w), 1, 'SAME')
     assert relerr(res[0][0], yt.numpy()) < 6e-3
+
+
+@pytest.mark.parametrize('geom', [dict(H=16, C=64, Cout=128, segs=[3, 2, 4], rate=0.5), dict(H=32, C=32, Cout=64, segs=[4], rate=0.5),
+                                  dict(H=8, C=64, Cout=256, segs=[2, 3], rate=0.0)])
+def test_mobn_pool_dropout_one_pass(geom):
+    """conv -> mean-only BN + leaky ReLU -> 2x2 max pool -> dropout (Good_GAN_cifar10.py:118-124): the last three run as ONE
+    kernel that never writes the full-resolution activation; backward through the pooled output only."""
+    from tgan import core, ops
+    rng = np.random.default_rng(21)
+    segs, H, C, Cout, rate = geom['segs'], geom['H'], geom['C'], geom['Cout'], geom['rate']
+    N = sum(segs)
+    x = bf(rng.standard_normal((N, H, H, C)))
+    w = bf(rng.standard_normal((3, 3, C, Cout)) * 0.1)
+    b = rng.standard_normal(Cout) * 0.1
+    pm = rng.standard_normal(Cout) * 0.1
+    oshape = (N, H // 2, H // 2, Cout)
+    gy = bf(rng.standard_normal(oshape))
+    src = O.TagRNG(9)
+    core.ctx.rng = core.InjectedSource(src)
+    xt, wt, bt = T(x, True), T(w, True), T(b, True)
+    S = {'pm': T(pm)}
+    ys, o = [], 0
+    for n in segs:
+        z = O.conv2d_tf(xt[o:o + n], wt, 1, 'SAME')
+        m = z.mean(dim=(0, 1, 2))
+        zr = T(bf(z.detach().numpy())) + (z - z.detach())
+        S['pm'] = S['pm'] * 0.9 + m.detach() * 0.1
+        y = O.lrelu_cifar(zr - m + bt)
+        ys.append(T(bf(y.detach().numpy())) + (y - y.detach()))          # y is rounded to bf16 before the pool
+        o += n
+    pooled = O.max_pool_tf(torch.cat(ys, 0), 2, 2)
+    yt = O.dropout_tf(pooled, src.keep_mask('t/drop', oshape, rate), rate) if rate > 0 else pooled
+    yt.backward(T(gy))
+    pw, pb, ppm = param(w), param(b), param(pm, False)
+    with core.recording():
+        parts, o = [], 0
+        for n in segs:
+            parts.append(ops.Var(dev(x[o:o + n]), (n, H, H, C)))
+            o += n
+        xg = ops.group_batch(parts)
+        xg.requires_grad = True
+        z = ops.conv2d(xg, ops.PlainWeight(pw), 3, 3, 1, 'SAME', colsum=True)
+        act = ops.mobn_act(z, pb, ppm, True, 'lrelu', 0.2)
+        assert act._data is None, 'the mean-only-BN apply waits for its consumer'
+        pl = ops.max_pool2(act)
+        out = ops.dropout(pl, rate, 't/drop', True) if rate > 0 else pl
+        fwd = tnp(out.data)
+        assert act._data is None, 'the full-resolution activation must not have been materialised'
+        run_bwd(out, gy)
+    assert relerr(fwd, yt.detach().numpy()) < 1e-2
+    assert relerr(tnp(ppm.data), S['pm'].numpy()) < 2e-3
+    assert relerr(tnp(pb.grad), bt.grad.numpy()) < 2.5e-2
+    assert relerr(tnp(pw.grad), wt.grad.numpy()) < 1e-2
+    assert relerr(tnp(xg.grad), xt.grad.numpy()) < 1e-2
