@@ -277,6 +277,15 @@ int tgan_global_pool_bwd(const void* dy, int dydt, const uint8_t* idx, void* dx,
  * out[r, 0:C] = x[r, 0:C]; out[r, C:C+K] = lab[r / rows_per_sample, 0:K]; out[r, C+K:ldo] = 0. */
 int tgan_concat_label(const void* x, int xdt, int64_t rows, int C, int ldx, const float* lab, int K,
                       int rows_per_sample, void* out, int odt, int ldo, void* stream);
+/* dropout / per-channel affine (batch-norm apply) written straight into a label-concatenated tensor: y[r, 0:C] =
+ * dropout(x)[r] resp. x*scale + shift, y[r, C:C+K] = lab[r / rows_per_sample], y[r, C+K:ldy] = 0 -- the
+ * `dropout -> _conv_cond_concat` (Good_GAN_cifar10.py:73-75, 83-85) and `batch_norm -> _conv_cond_concat` (:43-51) pairs
+ * as one pass.  Dropout arguments and Philox stream as tgan_dropout (mask is [rows, C], dense). */
+int tgan_dropout_concat(const void* x, int xdt, void* y, int ydt, int ldy, uint8_t* mask, int64_t rows, int C, float rate,
+                        int gen, uint64_t seed, uint64_t stream_id, const uint64_t* counter, const float* lab, int K,
+                        int rows_per_sample, void* stream);
+int tgan_affine_concat(const void* x, int xdt, void* y, int ydt, int ldy, int64_t rows, int C, const float* scale,
+                       const float* shift, const float* lab, int K, int rows_per_sample, void* stream);
 /* label planes only: out[r, C + j] = j < K ? lab[r / rows_per_sample, j] : 0 for j in [0, ldo - C) -- used when the
  * producing GEMM epilogue already wrote channels [0, C) of the concatenated tensor in place */
 int tgan_fill_label(const float* lab, int K, int rows_per_sample, void* out, int odt, int64_t rows, int C, int ldo,

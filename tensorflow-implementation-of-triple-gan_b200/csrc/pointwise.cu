@@ -732,6 +732,62 @@ __global__ void concat_label_kernel(const TX* __restrict__ x, int64_t rows, int 
   else if (j < C + K) v = lab[(r / rps) * K + (j - C)];
   stf<TO>(out, i, v);
 }
+// Dropout / per-channel affine written straight into a label-concatenated tensor (row stride ldy, label planes and zero pad
+// filled by the same launch): `dropout -> _conv_cond_concat` of the discriminator (Good_GAN_cifar10.py:73-75, 83-85) and
+// `batch_norm -> _conv_cond_concat` of the generator (:43-46, 49-51) as one pass instead of two.  The first `ngroups`
+// threads own 4 consecutive x elements (the Philox grouping of dropout_kernel), the rest own one label / pad element.
+template <typename TX, typename TY>
+__global__ void dropout_concat_kernel(const TX* __restrict__ x, TY* __restrict__ y, uint8_t* __restrict__ mask, int64_t n,
+                                      int C, int ldy, float rate, float scale, int gen, uint64_t seed, uint64_t stream_id,
+                                      const uint64_t* __restrict__ counter, const float* __restrict__ lab, int K, int rps,
+                                      int64_t ngroups, int64_t total) {
+  pdl_entry();
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  if (i < ngroups) {
+    const int64_t e = i * 4;
+    uint8_t k[4];
+    if (gen) {
+      uint64_t ctr = counter ? *counter : 0;
+      uint4 r = Philox(seed)((uint64_t)i, stream_id + (ctr << 20));
+      k[0] = u32_to_unit(r.x) >= rate; k[1] = u32_to_unit(r.y) >= rate;
+      k[2] = u32_to_unit(r.z) >= rate; k[3] = u32_to_unit(r.w) >= rate;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) k[j] = (e + j < n) ? mask[e + j] : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (e + j < n) {
+        if (gen) mask[e + j] = k[j];
+        const int64_t r = (e + j) / C;
+        const int c = (int)((e + j) - r * C);
+        stf<TY>(y, r * ldy + c, k[j] ? ldf<TX>(x, e + j) * scale : 0.f);
+      }
+    }
+  } else {
+    const int w = ldy - C;
+    const int64_t t = i - ngroups;
+    const int j = (int)(t % w);
+    const int64_t r = t / w;
+    stf<TY>(y, r * ldy + C + j, j < K ? lab[(r / rps) * K + j] : 0.f);
+  }
+}
+template <typename TX, typename TY>
+__global__ void affine_concat_kernel(const TX* __restrict__ x, TY* __restrict__ y, int C, int ldy,
+                                     const float* __restrict__ scale, const float* __restrict__ shift,
+                                     const float* __restrict__ lab, int K, int rps, int64_t total) {
+  pdl_entry();
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int j = (int)(i % ldy);
+  const int64_t r = i / ldy;
+  float v = 0.f;
+  if (j < C) v = ldf<TX>(x, r * C + j) * (scale ? scale[j] : 1.f) + (shift ? shift[j] : 0.f);
+  else if (j < C + K) v = lab[(r / rps) * K + (j - C)];
+  stf<TY>(y, i, v);
+}
+
 // out[r, C + j] = j < K ? lab[(r / rps) * K + j] : 0 for j in [0, ldo - C): the label planes (+ zero pad) of a tensor whose
 // first C channels were written in place by the producing GEMM epilogue
 template <typename TO>
@@ -1118,6 +1174,27 @@ extern "C" int tgan_concat_label(const void* x, int xdt, int64_t rows, int C, in
   TGAN_CHECK_ARG(x && lab && out && ldo >= C + K && rows_per_sample > 0, "concat_label: bad args");
   int64_t total = rows * ldo;
   DISPATCH_2(xdt, TX, odt, TO, (pdl_launch(concat_label_kernel<TX, TO>, ceil_div(total, 256), 256, 0, (cudaStream_t)((cudaStream_t)stream), (const TX*)x, rows, C, ldx, lab, K, rows_per_sample, (TO*)out, ldo, total)));
+  TGAN_LAUNCHED();
+  return 0;
+}
+extern "C" int tgan_dropout_concat(const void* x, int xdt, void* y, int ydt, int ldy, uint8_t* mask, int64_t rows, int C,
+                                   float rate, int gen, uint64_t seed, uint64_t stream_id, const uint64_t* counter,
+                                   const float* lab, int K, int rows_per_sample, void* stream) {
+  TGAN_CHECK_ARG(x && y && mask && lab && rows > 0 && ldy >= C + K && rate >= 0.f && rate < 1.f && rows_per_sample > 0,
+                 "dropout_concat: bad args");
+  const int64_t n = rows * C, ngroups = (n + 3) / 4, total = ngroups + rows * (ldy - C);
+  DISPATCH_2(xdt, TX, ydt, TY, (pdl_launch(dropout_concat_kernel<TX, TY>, ceil_div(total, 256), 256, 0, (cudaStream_t)stream,
+                                           (const TX*)x, (TY*)y, mask, n, C, ldy, rate, 1.0f / (1.0f - rate), gen, seed,
+                                           stream_id, counter, lab, K, rows_per_sample, ngroups, total)));
+  TGAN_LAUNCHED();
+  return 0;
+}
+extern "C" int tgan_affine_concat(const void* x, int xdt, void* y, int ydt, int ldy, int64_t rows, int C, const float* scale,
+                                  const float* shift, const float* lab, int K, int rows_per_sample, void* stream) {
+  TGAN_CHECK_ARG(x && y && lab && rows > 0 && ldy >= C + K && rows_per_sample > 0, "affine_concat: bad args");
+  const int64_t total = rows * ldy;
+  DISPATCH_2(xdt, TX, ydt, TY, (pdl_launch(affine_concat_kernel<TX, TY>, ceil_div(total, 256), 256, 0, (cudaStream_t)stream,
+                                           (const TX*)x, (TY*)y, C, ldy, scale, shift, lab, K, rows_per_sample, total)));
   TGAN_LAUNCHED();
   return 0;
 }

@@ -298,6 +298,16 @@ def _deferred(v):
     return v._data is None and isinstance(v._lazy, Deferred)
 
 
+class ConcatDeferred:
+    """an elementwise producer (dropout, batch-norm apply) waiting to learn whether a label concat follows: if so it writes
+    straight into the concatenated tensor and fills the label planes in the same launch.  run(ld, lab, K, rps); ld = None
+    materialises the plain tensor."""
+    __slots__ = ('run',)
+
+    def __init__(self, run):
+        self.run = run
+
+
 class MobnDeferred:
     """a mean-only-BN apply waiting to learn whether a 2x2 max pool (+ dropout) follows: if so the three run as one pass
     and the full-resolution activation is never written (ops.mobn_act / ops.max_pool2)"""
@@ -543,6 +553,9 @@ def lazy_bias(z, b):
 
 
 def _materialize(v, out_ld=None):
+    if isinstance(v._lazy, ConcatDeferred):
+        v._lazy.run(None, None, 0, 0)
+        return
     if isinstance(v._lazy, MobnDeferred):
         v._lazy.run_plain()
         return
@@ -718,8 +731,22 @@ def batch_norm(x, gamma, beta, mm, mv, train, eps=1e-5, decay=0.9):
     else:
         _lib.call('tgan_bn_eval_affine', _p(gamma.data), _p(beta.data), _p(mm.data), _p(mv.data), eps, C, _p(scale),
                   _p(shift), _st())
-    y = _affine_act(xd, rows, C, scale, shift, 0, 0.0, _out_dtype(C))
-    out = Var(y, x.shape, requires_grad=rg)
+    out = Var(None, x.shape, requires_grad=rg)
+
+    def run(ld, lab, K, rps):
+        if ld is None:
+            out._data = _affine_act(xd, rows, C, scale, shift, 0, 0.0, _out_dtype(C))
+        else:       # normalise straight into the label-concatenated tensor
+            y = _new(tuple(out.shape[:-1]) + (ld,))
+            _lib.call('tgan_affine_concat', _p(xd), dt_code(xd), _p(y), dt_code(y), ld, rows, C, _p(scale), _p(shift),
+                      _p(lab), K, rps, _st())
+            out._data, out.ld = y, ld
+        out._lazy = None
+
+    if ctx.math == 'bf16' and _out_dtype(C) == torch.bfloat16 and x.ld == C:
+        out._lazy = ConcatDeferred(run)
+    else:
+        run(None, None, 0, 0)
     if rg:
         def bwd():
             if out.grad is None:
@@ -780,16 +807,29 @@ def dropout(x, rate, tag, training=True):
         return x
     xd = x.data
     n = xd.numel()
-    y = _new(x.shape)
+    assert x.ld == x.C, 'dropout of a channel-padded tensor'
     rng = ctx.rng
-    if rng.injected:
-        mask = _rng_mask(tag, x.shape, rate)
-        _lib.call('tgan_dropout', _p(xd), dt_code(xd), _p(y), dt_code(y), _p(mask), n, rate, 0, 0, 0, None, _st())
+    mask = _rng_mask(tag, x.shape, rate) if rng.injected else _new(x.shape, torch.uint8)
+    gen = 0 if rng.injected else 1
+    seed, sid, ctr = (0, 0, None) if rng.injected else (rng.seed, rng.stream_id(str(tag)), rng.counter())
+    out = _prop(Var(None, x.shape, requires_grad=rg), x)
+
+    def run(ld, lab, K, rps):
+        if ld is None:
+            y = _new(x.shape)
+            _lib.call('tgan_dropout', _p(xd), dt_code(xd), _p(y), dt_code(y), _p(mask), n, rate, gen, seed, sid, _p(ctr), _st())
+            out._data = y
+        else:       # drop straight into the label-concatenated tensor (modle_base.py:190-191 + :239-244)
+            y = _new(tuple(out.shape[:-1]) + (ld,))
+            _lib.call('tgan_dropout_concat', _p(xd), dt_code(xd), _p(y), dt_code(y), ld, _p(mask), x.rows, x.C, rate, gen,
+                      seed, sid, _p(ctr), _p(lab), K, rps, _st())
+            out._data, out.ld = y, ld
+        out._lazy = None
+
+    if ctx.math == 'bf16':
+        out._lazy = ConcatDeferred(run)
     else:
-        mask = _new(x.shape, torch.uint8)
-        _lib.call('tgan_dropout', _p(xd), dt_code(xd), _p(y), dt_code(y), _p(mask), n, rate, 1, rng.seed,
-                  rng.stream_id(str(tag)), _p(rng.counter()), _st())
-    out = _prop(Var(y, x.shape, requires_grad=rg), x)
+        run(None, None, 0, 0)
     if rg:
         def bwd():
             if out.grad is None:
@@ -897,7 +937,10 @@ def concat_label(x, y):
         return Var(None, oshape, ld=ld, requires_grad=rg)
     lab = y.data if isinstance(y, Var) else y
     assert lab.dtype == torch.float32
-    if _deferred(x) and ctx.math == 'bf16':
+    if x._data is None and isinstance(x._lazy, ConcatDeferred) and ctx.math == 'bf16':
+        x._lazy.run(ld, lab, K, rps)           # the producer writes the concatenated tensor itself, labels included
+        o = x.data
+    elif _deferred(x) and ctx.math == 'bf16':
         # the producing GEMM writes channels [0, C) straight into the concatenated buffer; only the label planes
         # (and the zero pad) are filled here
         _materialize(x, out_ld=ld)

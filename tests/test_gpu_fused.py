@@ -261,3 +261,52 @@ def test_mobn_pool_dropout_one_pass(geom):
     assert relerr(tnp(pb.grad), bt.grad.numpy()) < 2.5e-2
     assert relerr(tnp(pw.grad), wt.grad.numpy()) < 1e-2
     assert relerr(tnp(xg.grad), xt.grad.numpy()) < 1e-2
+
+
+def test_dropout_and_batchnorm_write_into_the_concat():
+    """`dropout -> _conv_cond_concat` (D) and `batch_norm -> _conv_cond_concat` (G) are one launch each: the producer writes
+    the label-concatenated tensor itself"""
+    from tgan import core, ops
+    rng = np.random.default_rng(31)
+    N, H, C, K = 6, 8, 64, 10
+    x = bf(rng.standard_normal((N, H, H, C)))
+    y = np.eye(K, dtype=np.float32)[rng.integers(0, K, N)]
+    yv = lambda: ops.Var(torch.tensor(y).cuda(), y.shape)
+    src = O.TagRNG(3)
+    core.ctx.rng = core.InjectedSource(src)
+    # dropout -> concat
+    xt = T(x, True)
+    ref = O.cond_concat(O.dropout_tf(xt, src.keep_mask('d', x.shape, 0.2), 0.2), T(y).view(N, 1, 1, K))
+    gy = rng.standard_normal(tuple(ref.shape))
+    ref.backward(T(gy))
+    with core.recording():
+        xv = ops.Var(dev(x), x.shape, requires_grad=True)
+        d = ops.dropout(xv, 0.2, 'd', True)
+        assert d._data is None
+        c = ops.concat_label(d, yv())
+        assert c.ld == 80 and d.ld == 80 and c.data.data_ptr() == d.data.data_ptr()
+        got = tnp(c.data)[..., :C + K]
+        assert np.abs(tnp(c.data)[..., C + K:]).max() == 0.0
+        run_bwd(c, gy)
+    assert relerr(got, bf(ref.detach().numpy())) < 1e-6
+    assert relerr(tnp(xv.grad), bf(xt.grad.numpy())) < 8e-3      # dy and dy*1.25 are each rounded to bf16
+    # batch norm -> concat
+    gam, bet = rng.standard_normal(C) * 0.1 + 1, rng.standard_normal(C) * 0.1
+    xt, gt, bt = T(x, True), T(gam, True), T(bet, True)
+    P = {'s/gamma': gt, 's/beta': bt}
+    S = {'s/moving_mean': T(np.zeros(C)), 's/moving_variance': T(np.ones(C))}
+    ref = O.cond_concat(O.bn_contrib(P, S, 's', xt, True), T(y).view(N, 1, 1, K))
+    ref.backward(T(gy))
+    pg, pb = param(gam), param(bet)
+    mm, mv = param(np.zeros(C), False), param(np.ones(C), False)
+    with core.recording():
+        xv = ops.Var(dev(x), x.shape, requires_grad=True)
+        h = ops.batch_norm(xv, pg, pb, mm, mv, True)
+        assert h._data is None
+        c = ops.concat_label(h, yv())
+        assert c.ld == 80 and c.data.data_ptr() == h.data.data_ptr()
+        got = tnp(c.data)[..., :C + K]
+        run_bwd(c, gy)
+    assert relerr(got, ref.detach().numpy()) < 6e-3
+    assert relerr(tnp(xv.grad), xt.grad.numpy()) < 1e-2
+    assert relerr(tnp(pg.grad), gt.grad.numpy()) < 1e-2 and relerr(tnp(pb.grad), bt.grad.numpy()) < 1e-2
