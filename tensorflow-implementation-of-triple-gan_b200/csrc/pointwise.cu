@@ -219,7 +219,7 @@ __global__ void mobn_apply_seg_kernel(const bf16* __restrict__ x, bf16* __restri
 template <int ACT>
 __global__ void __launch_bounds__(256) act_bwd_seg_v8_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y,
                                                              bf16* __restrict__ du, int64_t rows, int C, Segs sg,
-                                                             float alpha, float* __restrict__ partials) {
+                                                             float alpha, float* __restrict__ partials, int ldy) {
   pdl_entry();
   extern __shared__ float abs_sm[];              // [row lanes][4][C]; every thread owns its (lane, segment, 8 channels) slots
   const int cg = C / 8, rl = 256 / cg;           // channel groups per row, row lanes per CTA
@@ -239,8 +239,8 @@ __global__ void __launch_bounds__(256) act_bwd_seg_v8_kernel(const bf16* __restr
   for (int64_t r0 = rbeg + tr; r0 < rend; r0 += 2 * rl) {
     const int64_t r1 = r0 + rl;
     float a0[8], b0[8], a1[8], b1[8];
-    ld8(dy, r0 * C + tc * 8, a0); ld8(y, r0 * C + tc * 8, b0);
-    if (r1 < rend) { ld8(dy, r1 * C + tc * 8, a1); ld8(y, r1 * C + tc * 8, b1); }
+    ld8(dy, r0 * C + tc * 8, a0); ld8(y, r0 * ldy + tc * 8, b0);
+    if (r1 < rend) { ld8(dy, r1 * C + tc * 8, a1); ld8(y, r1 * ldy + tc * 8, b1); }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int64_t r = u ? r1 : r0;
@@ -275,7 +275,8 @@ __global__ void __launch_bounds__(256) act_bwd_seg_v8_kernel(const bf16* __restr
 }
 // 256 threads = 8 channels x 32 part lanes (C/8 CTAs); fixed summation order -> deterministic
 __global__ void __launch_bounds__(256) act_bwd_seg_fold_kernel(const float* __restrict__ partials, int nparts, int C,
-                                                               float* __restrict__ colsums, float* __restrict__ grad_acc) {
+                                                               float* __restrict__ colsums, float* __restrict__ grad_acc,
+                                                               int nseg_out) {
   pdl_entry();
   __shared__ double sm[32][4][9];
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3, c = blockIdx.x * 8 + tx;
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(256) act_bwd_seg_fold_kernel(const float* __re
       double u = 0.0;
 #pragma unroll
       for (int l = 0; l < 32; ++l) u += sm[l][a][tx];
-      colsums[a * C + c] = (float)u;
+      if (a < nseg_out) colsums[a * C + c] = (float)u;
       tot += u;
     }
     if (grad_acc) grad_acc[c] = (float)((double)grad_acc[c] + tot);
@@ -801,6 +802,21 @@ __global__ void fill_label_kernel(const float* __restrict__ lab, int K, int rps,
   const int64_t r = i / w;
   stf<TO>(out, r * ldo + C + j, j < K ? lab[(r / rps) * K + j] : 0.f);
 }
+// bf16, C % 8 == 0 and ldo % 8 == 0: one thread = one 16-byte chunk of a row's label / pad tail
+__global__ void fill_label_v8_kernel(const float* __restrict__ lab, int K, int rps, bf16* __restrict__ out, int C, int ldo,
+                                     int64_t total) {
+  pdl_entry();
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cw = (ldo - C) / 8;
+  const int j0 = (int)(i % cw) * 8;
+  const int64_t r = i / cw;
+  const float* l = lab + (r / rps) * K;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = (j0 + j < K) ? l[j0 + j] : 0.f;
+  st8(out, r * ldo + C + j0, v);
+}
 template <typename TS, typename TD>
 __global__ void copy_channels_kernel(const TS* __restrict__ src, int lds, TD* __restrict__ dst, int ldd, int C,
                                      int64_t total) {
@@ -927,9 +943,9 @@ extern "C" int tgan_act_bwd_seg(const void* dy, int dydt, const void* y, int ydt
     const int nparts = TGAN_ACT_BWD_SEG_PARTS;    // 3 CTAs per SM; ws holds nparts * 4 * C floats
     const size_t smem = (size_t)(2048 / C) * 4 * C * sizeof(float);      // 32 KB
     cudaStream_t st = (cudaStream_t)stream;
-    TGAN_DISPATCH_ACT(act, A, (pdl_launch(act_bwd_seg_v8_kernel<A>, nparts, 256, smem, (cudaStream_t)(st), (const bf16*)dy, (const bf16*)y, (bf16*)du, rows, C, sg, alpha, ws)));
+    TGAN_DISPATCH_ACT(act, A, (pdl_launch(act_bwd_seg_v8_kernel<A>, nparts, 256, smem, (cudaStream_t)(st), (const bf16*)dy, (const bf16*)y, (bf16*)du, rows, C, sg, alpha, ws, C)));
     TGAN_LAUNCHED();
-    pdl_launch(act_bwd_seg_fold_kernel, ceil_div(C, 8), 256, 0, (cudaStream_t)(st), ws, nparts, C, colsums, grad_acc);
+    pdl_launch(act_bwd_seg_fold_kernel, ceil_div(C, 8), 256, 0, (cudaStream_t)(st), ws, nparts, C, colsums, grad_acc, 4);
     TGAN_LAUNCHED();
     return 0;
   }
@@ -1146,7 +1162,7 @@ extern "C" int tgan_mobn_pool_dropout_bwd(const void* dy, const void* y, const u
                                         (const bf16*)y, code, (bf16*)du, H, W, C, prows, sg, rpi, alpha, 1.0f / (1.0f - rate),
                                         ws)));
   TGAN_LAUNCHED();
-  pdl_launch(act_bwd_seg_fold_kernel, ceil_div(C, 8), 256, 0, st, ws, nparts, C, colsums, grad_acc);
+  pdl_launch(act_bwd_seg_fold_kernel, ceil_div(C, 8), 256, 0, st, ws, nparts, C, colsums, grad_acc, 4);
   TGAN_LAUNCHED();
   return 0;
 }
@@ -1201,6 +1217,13 @@ extern "C" int tgan_affine_concat(const void* x, int xdt, void* y, int ydt, int 
 extern "C" int tgan_fill_label(const float* lab, int K, int rows_per_sample, void* out, int odt, int64_t rows, int C,
                                int ldo, void* stream) {
   TGAN_CHECK_ARG(lab && out && ldo >= C + K && rows_per_sample > 0 && rows > 0, "fill_label: bad args");
+  if (odt == TGAN_BF16 && C % 8 == 0 && ldo % 8 == 0 && aligned16(out)) {
+    const int64_t tv = rows * ((ldo - C) / 8);
+    pdl_launch(fill_label_v8_kernel, ceil_div(tv, 256), 256, 0, (cudaStream_t)stream, lab, K, rows_per_sample, (bf16*)out, C,
+               ldo, tv);
+    TGAN_LAUNCHED();
+    return 0;
+  }
   int64_t total = rows * (ldo - C);
   TGAN_DISPATCH_1(odt, TO, (pdl_launch(fill_label_kernel<TO>, ceil_div(total, 256), 256, 0, (cudaStream_t)((cudaStream_t)stream), lab, K, rows_per_sample, (TO*)out, C, ldo, total)));
   TGAN_LAUNCHED();
