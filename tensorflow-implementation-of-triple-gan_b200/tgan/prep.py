@@ -19,9 +19,22 @@ def _st():
     return torch.cuda.current_stream().cuda_stream
 
 
+def to_device_table(host):
+    """small host table -> device, legal under CUDA-graph capture (the first step of a trainer may itself be captured):
+    staged through PINNED memory that stays alive with the device tensor, so the copy is a replayable memcpy node"""
+    pinned = host.contiguous().pin_memory()
+    dev = torch.empty(pinned.shape, dtype=pinned.dtype, device=ctx.device)
+    dev.copy_(pinned, non_blocking=True)
+    _keep_alive.append((pinned, dev))
+    return dev
+
+
+_keep_alive = []
+
+
 def _table(descs):
     raw = b''.join(bytes(d) for d in descs)
-    return torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(ctx.device)
+    return to_device_table(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
 
 
 def _groups(kind):

@@ -57,7 +57,8 @@ _taps_dev = {}
 def _taps_tensor(taps):
     key = tuple(taps)
     if key not in _taps_dev:
-        _taps_dev[key] = torch.tensor(list(taps), dtype=torch.int32, device=ctx.device)
+        from .prep import to_device_table
+        _taps_dev[key] = to_device_table(torch.tensor(list(taps), dtype=torch.int32))
     return _taps_dev[key]
 
 
