@@ -85,7 +85,8 @@ typedef struct {
   int osy, osx, ooy, oox; /* output placement (stride / offset)                */
   int vh, vw;          /* number of valid grid rows/cols actually stored       */
   const float* bias;   /* optional fp32 [Nout] added before the store          */
-  float* colsum;       /* optional fp32 [nseg][Nout]: += per-channel sums of the stored values, per batch segment */
+  void* colsum;        /* optional int64 [nseg][Nout], Q24 fixed point (value * 2^24): += per-channel sums of the stored
+                          values, per batch segment.  Integer atomics: the result does not depend on the CTA order */
   int nseg;            /* 0/1 = whole batch; up to 4 segments of consecutive images (several network calls grouped
                           in one launch keep their own mean-only-BN statistics) */
   int seg_end[4];      /* exclusive image index where segment i ends (plain GEMM, N == 1 && gh == 1: pixel index) */
@@ -187,11 +188,12 @@ int tgan_mobn_apply(const void* x, int xdt, void* y, int ydt, int64_t rows, int 
  * batch mean.  nseg <= 4 segments of consecutive rows; r0,r1,r2 = exclusive end rows of segments 0..2 (the last
  * segment ends at `rows`; unused values ignored).  bf16 tensors, C % 8 == 0 (16-byte vector accesses).
  *   mobn_apply_seg: y = act(x - sums[seg]/rows_seg + b) (train) | act(x - pop_mean + b) (test); pop_mean is updated once
- *                   per segment in call order (nn.py:176-183).  sums: fp32 [nseg][C].
+ *                   per segment in call order (nn.py:176-183).  sums: [nseg][C], fp32 (sums_q24 = 0) or the int64 Q24
+ *                   fixed-point sums a tgan_igemm_bf16 epilogue accumulated (sums_q24 = 1).
  *   act_bwd_seg:    du = dy * act'(y); colsums[seg][c] = sum_{rows in seg} du; grad_acc[c] += sum over all rows (db).
  *   sub_channel_mean_seg: dz = du - colsums[seg]/rows_seg (the mean-subtraction's gradient, nn.py:179). */
 int tgan_mobn_apply_seg(const void* x, void* y, int64_t rows, int C, int nseg, int64_t r0, int64_t r1, int64_t r2,
-                        const float* sums, const float* b, float* pop_mean, float decay, int train, int act,
+                        const void* sums, int sums_q24, const float* b, float* pop_mean, float decay, int train, int act,
                         float alpha, void* stream);
 int tgan_act_bwd_seg(const void* dy, int dydt, const void* y, int ydt, void* du, int dudt, int64_t rows, int C,
                      int nseg, int64_t r0, int64_t r1, int64_t r2, int act, float alpha, float* colsums,
@@ -261,8 +263,8 @@ int tgan_maxpool2_dropout_bwd(const void* dy, const uint8_t* code, void* dx, int
  * zero elsewhere; colsums[seg][c] = per-segment sums of du, grad_acc[c] += total (the bias gradient).
  * ws: 4*TGAN_ACT_BWD_SEG_PARTS*C floats. */
 int tgan_mobn_pool_dropout_fwd(const void* z, void* y, uint8_t* code, int N, int H, int W, int C, int nseg, int64_t n0,
-                               int64_t n1, int64_t n2, const float* sums, const float* b, float* pop_mean, float decay,
-                               int train, int act, float alpha, float rate, const uint8_t* mask, uint64_t seed,
+                               int64_t n1, int64_t n2, const void* sums, int sums_q24, const float* b, float* pop_mean,
+                               float decay, int train, int act, float alpha, float rate, const uint8_t* mask, uint64_t seed,
                                uint64_t stream_id, const uint64_t* counter, void* stream);
 int tgan_mobn_pool_dropout_bwd(const void* dy, const void* y, const uint8_t* code, void* du, int N, int H, int W, int C,
                                int nseg, int64_t n0, int64_t n1, int64_t n2, int act, float alpha, float rate,

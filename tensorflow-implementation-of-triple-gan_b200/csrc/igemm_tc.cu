@@ -105,7 +105,7 @@ struct IgParams {
   void* out;
   int odt, OH, OW, ldo, osy, osx, ooy, oox, vh, vw, Nout;
   const float* bias;
-  float* colsum;
+  long long* colsum;   // Q24 fixed point: integer atomics are order-independent, so the statistics are bit-reproducible
   int nseg, seg_end[4], segflat;   // segflat: plain GEMM (one row of pixels) -> segments are pixel ranges
   int act;
   float alpha;
@@ -493,7 +493,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       if (p.colsum && cvalid) {
 #pragma unroll
         for (int gg = 0; gg < 4; ++gg)
-          if (gg < p.nseg && csum[gg] != 0.f) atomicAdd(&p.colsum[gg * p.Nout + co], csum[gg]);
+          if (gg < p.nseg && csum[gg] != 0.f)
+            atomicAdd(reinterpret_cast<unsigned long long*>(&p.colsum[gg * p.Nout + co]),
+                      (unsigned long long)__float2ll_rn(csum[gg] * 16777216.f));
       }
       tc_fence_before();
       __syncwarp();
@@ -744,7 +746,7 @@ extern "C" int tgan_igemm_bf16(const tgan_igemm_args* a, void* stream) {
   TGAN_CHECK_ARG(p.nseg <= 4, "igemm: at most 4 batch segments");
   for (int i = 0; i < 4; ++i) p.seg_end[i] = (a->nseg > 1 && i < a->nseg - 1) ? a->seg_end[i] : 0x7fffffff;
   p.segflat = (a->nseg > 1 && a->N == 1 && a->gh == 1) ? 1 : 0;
-  p.bias = a->bias; p.colsum = a->colsum; p.act = a->act; p.alpha = a->alpha == 0.f ? 1.f : a->alpha;
+  p.bias = a->bias; p.colsum = reinterpret_cast<long long*>(a->colsum); p.act = a->act; p.alpha = a->alpha == 0.f ? 1.f : a->alpha;
   const size_t smem_bytes = 1024 + (size_t)IG_STAGES * IG_STAGE_BYTES + IG_OUT_STAGE_BYTES + 256;
   p.tstore = (a->odt == TGAN_BF16 && a->ldo % 8 == 0 && ((uintptr_t)a->out & 15) == 0) ? 1 : 0;
   { const char* e = getenv("TGAN_IGEMM_NO_TSTORE"); if (e && atoi(e)) p.tstore = 0; }

@@ -162,6 +162,12 @@ __global__ void mobn_apply_kernel(const TX* __restrict__ x, TY* __restrict__ y, 
   }
 }
 
+// per-segment channel sum: fp32, or the Q24 fixed-point value accumulated by the GEMM epilogue's integer atomics
+__device__ __forceinline__ float seg_sum(const void* sums, int q24, int64_t i) {
+  return q24 ? (float)((double)reinterpret_cast<const long long*>(sums)[i] * (1.0 / 16777216.0))
+             : reinterpret_cast<const float*>(sums)[i];
+}
+
 // 8 bf16 per thread (16-byte accesses)
 __device__ __forceinline__ void ld8(const bf16* p, int64_t i, float (&v)[8]) {
   uint4 t = *reinterpret_cast<const uint4*>(p + i);
@@ -182,13 +188,13 @@ __device__ __forceinline__ void st8(bf16* p, int64_t i, const float (&v)[8]) {
 // pop_mean is updated once per segment IN CALL ORDER (the reference runs the calls one after the other).
 template <int ACT>
 __global__ void mobn_apply_seg_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int64_t nvec, int C,
-                                      const float* __restrict__ sums, Segs sg, const float* __restrict__ b,
+                                      const void* __restrict__ sums, int q24, Segs sg, const float* __restrict__ b,
                                       float* __restrict__ pop_mean, float decay, int train, float alpha) {
   pdl_entry();
   if (train && pop_mean && blockIdx.x == 0) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       float pm = pop_mean[c];
-      for (int s = 0; s < sg.n; ++s) pm = pm * decay + sums[s * C + c] * sg.inv_rows[s] * (1.f - decay);
+      for (int s = 0; s < sg.n; ++s) pm = pm * decay + seg_sum(sums, q24, (int64_t)s * C + c) * sg.inv_rows[s] * (1.f - decay);
       pop_mean[c] = pm;
     }
   }
@@ -200,11 +206,12 @@ __global__ void mobn_apply_seg_kernel(const bf16* __restrict__ x, bf16* __restri
     float v[8];
     ld8(x, e, v);
     const float4* bp = reinterpret_cast<const float4*>(b + c);
-    const float4* mp = reinterpret_cast<const float4*>((train ? sums + (int64_t)s * C : pop_mean) + c);
     const float sc = train ? sg.inv_rows[s] : 1.f;
-    float4 b0 = bp[0], b1 = bp[1], m0 = mp[0], m1 = mp[1];
+    float4 b0 = bp[0], b1 = bp[1];
     const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+    float mm[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mm[j] = train ? seg_sum(sums, q24, (int64_t)s * C + c + j) : pop_mean[c + j];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = act_fwd_t<ACT>(v[j] + bb[j] - mm[j] * sc, alpha);
     st8(y, e, v);
@@ -549,7 +556,7 @@ __global__ void maxpool2_dropout_bwd_kernel(const bf16* __restrict__ dy, const u
 // of one pooled pixel.  Same code byte and Philox stream as maxpool2_dropout_fwd_kernel.
 template <int ACT>
 __global__ void mobn_pool_dropout_fwd_kernel(const bf16* __restrict__ z, bf16* __restrict__ y, uint8_t* __restrict__ code,
-                                             int H, int W, int C, int64_t nvec, const float* __restrict__ sums, Segs sg,
+                                             int H, int W, int C, int64_t nvec, const void* __restrict__ sums, int q24, Segs sg,
                                              int rows_per_img, const float* __restrict__ b, float* __restrict__ pop_mean,
                                              float decay, int train, float alpha, float rate, float scale,
                                              const uint8_t* __restrict__ mask, uint64_t seed, uint64_t stream_id,
@@ -558,7 +565,7 @@ __global__ void mobn_pool_dropout_fwd_kernel(const bf16* __restrict__ z, bf16* _
   if (train && pop_mean && blockIdx.x == 0) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       float pm = pop_mean[c];
-      for (int s = 0; s < sg.n; ++s) pm = pm * decay + sums[s * C + c] * sg.inv_rows[s] * (1.f - decay);
+      for (int s = 0; s < sg.n; ++s) pm = pm * decay + seg_sum(sums, q24, (int64_t)s * C + c) * sg.inv_rows[s] * (1.f - decay);
       pop_mean[c] = pm;
     }
   }
@@ -575,11 +582,12 @@ __global__ void mobn_pool_dropout_fwd_kernel(const bf16* __restrict__ z, bf16* _
   float a[4][8];
   ld8(z, p0, a[0]); ld8(z, p0 + C, a[1]); ld8(z, p0 + (int64_t)W * C, a[2]); ld8(z, p0 + (int64_t)W * C + C, a[3]);
   const float4* bp = reinterpret_cast<const float4*>(b + c);
-  const float4* mp = reinterpret_cast<const float4*>((train ? sums + (int64_t)s * C : pop_mean) + c);
   const float msc = train ? sg.inv_rows[s] : 1.f;
-  const float4 b0 = bp[0], b1 = bp[1], m0 = mp[0], m1 = mp[1];
-  const float sh[8] = {b0.x - m0.x * msc, b0.y - m0.y * msc, b0.z - m0.z * msc, b0.w - m0.w * msc,
-                       b1.x - m1.x * msc, b1.y - m1.y * msc, b1.z - m1.z * msc, b1.w - m1.w * msc};
+  const float4 b0 = bp[0], b1 = bp[1];
+  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  float sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh[j] = bb[j] - (train ? seg_sum(sums, q24, (int64_t)s * C + c + j) : pop_mean[c + j]) * msc;
   uint8_t keep[8];
   const int64_t e = i * 8;
   if (rate <= 0.f) {
@@ -916,8 +924,8 @@ static int make_segs(Segs& sg, int64_t rows, int nseg, int64_t r0, int64_t r1, i
 }
 
 extern "C" int tgan_mobn_apply_seg(const void* x, void* y, int64_t rows, int C, int nseg, int64_t r0, int64_t r1,
-                                   int64_t r2, const float* sums, const float* b, float* pop_mean, float decay,
-                                   int train, int act, float alpha, void* stream) {
+                                   int64_t r2, const void* sums, int sums_q24, const float* b, float* pop_mean,
+                                   float decay, int train, int act, float alpha, void* stream) {
   TGAN_CHECK_ARG(x && y && b && rows > 0 && C > 0 && C % 8 == 0 && aligned16(x) && aligned16(y) && aligned16(b),
                  "mobn_apply_seg: bf16 tensors with C %% 8 == 0 and 16-byte alignment only");
   TGAN_CHECK_ARG(train ? (sums != nullptr && aligned16(sums)) : (pop_mean != nullptr && aligned16(pop_mean)),
@@ -926,7 +934,7 @@ extern "C" int tgan_mobn_apply_seg(const void* x, void* y, int64_t rows, int C, 
   if (make_segs(sg, rows, nseg, r0, r1, r2)) return 1;
   const int64_t nvec = rows * C / 8;
   cudaStream_t st = (cudaStream_t)stream;
-  TGAN_DISPATCH_ACT(act, A, (pdl_launch(mobn_apply_seg_kernel<A>, grid_for(nvec), 256, 0, (cudaStream_t)(st), (const bf16*)x, (bf16*)y, nvec, C, sums, sg, b, pop_mean, decay, train, alpha)));
+  TGAN_DISPATCH_ACT(act, A, (pdl_launch(mobn_apply_seg_kernel<A>, grid_for(nvec), 256, 0, (cudaStream_t)(st), (const bf16*)x, (bf16*)y, nvec, C, sums, sums_q24, sg, b, pop_mean, decay, train, alpha)));
   TGAN_LAUNCHED();
   return 0;
 }
@@ -1123,8 +1131,9 @@ extern "C" int tgan_maxpool2_dropout_bwd(const void* dy, const uint8_t* code, vo
 }
 
 extern "C" int tgan_mobn_pool_dropout_fwd(const void* z, void* y, uint8_t* code, int N, int H, int W, int C, int nseg,
-                                          int64_t n0, int64_t n1, int64_t n2, const float* sums, const float* b,
-                                          float* pop_mean, float decay, int train, int act, float alpha, float rate,
+                                          int64_t n0, int64_t n1, int64_t n2, const void* sums, int sums_q24,
+                                          const float* b, float* pop_mean, float decay, int train, int act, float alpha,
+                                          float rate,
                                           const uint8_t* mask, uint64_t seed, uint64_t stream_id, const uint64_t* counter,
                                           void* stream) {
   TGAN_CHECK_ARG(z && y && code && b && H % 2 == 0 && W % 2 == 0 && C % 8 == 0 && rate >= 0.f && rate < 1.f &&
@@ -1140,7 +1149,7 @@ extern "C" int tgan_mobn_pool_dropout_fwd(const void* z, void* y, uint8_t* code,
   const int64_t nvec = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
   cudaStream_t st = (cudaStream_t)stream;
   TGAN_DISPATCH_ACT(act, A, (pdl_launch(mobn_pool_dropout_fwd_kernel<A>, ceil_div(nvec, 256), 256, 0, st, (const bf16*)z,
-                                        (bf16*)y, code, H, W, C, nvec, sums, sg, rpi, b, pop_mean, decay, train, alpha, rate,
+                                        (bf16*)y, code, H, W, C, nvec, sums, sums_q24, sg, rpi, b, pop_mean, decay, train, alpha, rate,
                                         1.0f / (1.0f - rate), mask, seed, stream_id, counter)));
   TGAN_LAUNCHED();
   return 0;

@@ -382,7 +382,7 @@ def conv2d(x, w, kh, kw, stride=1, padding='SAME', colsum=False):
             ld = out_ld or Cout
             cs = None
             if colsum and (segs is None or len(segs) <= 4):
-                cs = arena_take(Cout * (len(segs) if segs else 1))
+                cs = arena_take(2 * Cout * (len(segs) if segs else 1))      # int64 Q24 entries (two floats each)
             z = tc.conv_fwd(x, w, geom, cs, segs if cs is not None else None, bias=None if b is None else b.data,
                             act=ACT[act], ldo=ld)
             out._data, out.ld, out._lazy = z.view(tuple(out.shape[:-1]) + (ld,)), ld, None
@@ -635,17 +635,15 @@ def mobn_act(z, b, pop_mean, train, act='none', alpha=0.2, decay=0.9):
         if fused:       # one launch for the whole grouped batch, nonlinearity included
             sums = (cs_all if cs_all is not None else seg_stats()) if train else None
             _lib.call('tgan_mobn_apply_seg', _p(zd), _p(y), rows, C, len(segs), ends[0], ends[1], ends[2], _p(sums),
-                      _p(b.data), _p(pop_mean.data), decay, 1 if train else 0, a, alpha, _st())
+                      1 if cs_all is not None else 0, _p(b.data), _p(pop_mean.data), decay, 1 if train else 0, a, alpha,
+                      _st())
         else:
             for i, (b0, nr) in enumerate(bounds):
                 s = None
-                if train:
-                    if cs_all is not None:
-                        s = cs_all[i * C:(i + 1) * C]
-                    else:
-                        s = _new((C,), torch.float32)
-                        _lib.call('tgan_channel_stats', zd.data_ptr() + b0 * C * ez, dt_code(zd), nr, C, _p(s), None, 0.0,
-                                  _p(ctx.ws()), _st())
+                if train:       # (the epilogue's fixed-point sums are only consumed by the fused kernels)
+                    s = _new((C,), torch.float32)
+                    _lib.call('tgan_channel_stats', zd.data_ptr() + b0 * C * ez, dt_code(zd), nr, C, _p(s), None, 0.0,
+                              _p(ctx.ws()), _st())
                 _lib.call('tgan_mobn_apply', zd.data_ptr() + b0 * C * ez, dt_code(zd), y.data_ptr() + b0 * C * ey, dt_code(y),
                           nr, C, _p(s), _p(b.data), _p(pop_mean.data), decay, 1 if train else 0, a, alpha, _st())
         out._data, out._lazy = y, None
@@ -696,8 +694,8 @@ def mobn_act(z, b, pop_mean, train, act='none', alpha=0.2, decay=0.9):
         elif rate > 0:
             seed, sid, ctr = rng.seed, rng.stream_id(str(tag)), rng.counter()
         _lib.call('tgan_mobn_pool_dropout_fwd', _p(zd), _p(y), _p(code), N, H, W, C, len(segs), iends[0], iends[1], iends[2],
-                  _p(sums), _p(b.data), _p(pop_mean.data), decay, 1 if train else 0, a, alpha, float(rate), _p(mask), seed,
-                  sid, _p(ctr), _st())
+                  _p(sums), 1 if cs_all is not None else 0, _p(b.data), _p(pop_mean.data), decay, 1 if train else 0, a, alpha,
+                  float(rate), _p(mask), seed, sid, _p(ctr), _st())
         pout._data, pout._lazy = y, None
         out._lazy = None                 # consumed: the full-resolution activation does not exist
         if pout.requires_grad and tape is not None:

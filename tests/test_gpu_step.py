@@ -220,3 +220,39 @@ def test_evaluate_matches_oracle(math, tol):
         tot += int((pred.cpu().numpy() == y.argmax(1)).sum())
         cnt += 16
         assert abs(acc - tot / cnt) < 1e-12
+
+
+@pytest.mark.parametrize('math', ['bf16', 'fp32'])
+def test_step_is_bit_reproducible(math):
+    """Same seeds -> bit-identical losses and parameters, whether the step runs eagerly, as a CUDA-graph replay, with or
+    without the second stream / programmatic dependent launch.  Every reduction has a fixed order (split-K partials and
+    column reductions are folded deterministically, the GEMM-epilogue statistics use integer fixed-point atomics), so any
+    difference would be a race between the streams or a kernel that started before its predecessor finished."""
+    import os
+    import tgan
+    P, S = O.init_params('cifar10', seed=5)
+
+    def run(graph, env):
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            tgan.init('cuda:0', math=math, seed=77)
+            tr = tgan.make_trainer('cifar10', scale=10, init=(P, S), zca=O.make_zca(3))
+            tr.load_batch(O.make_batch(O.OracleConfig('cifar10', 10), seed=9))
+            if graph:
+                tr.capture(warmup=0)
+            losses = np.stack([tr.step(lambda_1=0.3, lambda_2=0.5).cpu().numpy().copy() for _ in range(3)])
+            theta = {g: tr.store.flat[g]['theta'].cpu().numpy().copy() for g in ('discriminator', 'good_generator', 'classifier')}
+            return losses, theta
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+    ref = run(False, {})
+    for graph, env in ((False, {}), (True, {}), (False, {'TGAN_NO_SIDE': '1'})):
+        got = run(graph, env)
+        assert np.array_equal(ref[0], got[0]), (graph, env, ref[0], got[0])
+        for g in ref[1]:
+            assert np.array_equal(ref[1][g], got[1][g]), (graph, env, g)
