@@ -198,22 +198,24 @@ __global__ void mobn_apply_seg_kernel(const bf16* __restrict__ x, bf16* __restri
       pop_mean[c] = pm;
     }
   }
+  // per-block table shift[seg][c] = b - mean (the fixed-point -> float conversion is done once per block, not per element)
+  extern __shared__ float seg_shift[];
+  for (int i = threadIdx.x; i < sg.n * C; i += blockDim.x) {
+    const int s = i / C, c = i - s * C;
+    // (in training pop_mean is being rewritten by CTA 0, but it is not read here: sums is)
+    const float m = train ? seg_sum(sums, q24, i) * sg.inv_rows[s] : pop_mean[c];
+    seg_shift[i] = b[c] - m;
+  }
+  __syncthreads();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t e = i * 8;
     const int64_t r = e / C;
     const int c = (int)(e - r * C);
-    const int s = sg.of(r);
+    const float* sh = seg_shift + sg.of(r) * C + c;
     float v[8];
     ld8(x, e, v);
-    const float4* bp = reinterpret_cast<const float4*>(b + c);
-    const float sc = train ? sg.inv_rows[s] : 1.f;
-    float4 b0 = bp[0], b1 = bp[1];
-    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    float mm[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) mm[j] = train ? seg_sum(sums, q24, (int64_t)s * C + c + j) : pop_mean[c + j];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = act_fwd_t<ACT>(v[j] + bb[j] - mm[j] * sc, alpha);
+    for (int j = 0; j < 8; ++j) v[j] = act_fwd_t<ACT>(v[j] + sh[j], alpha);
     st8(y, e, v);
   }
 }
@@ -569,6 +571,13 @@ __global__ void mobn_pool_dropout_fwd_kernel(const bf16* __restrict__ z, bf16* _
       pop_mean[c] = pm;
     }
   }
+  extern __shared__ float seg_shift[];         // shift[seg][c] = b - mean, converted once per block
+  for (int k = threadIdx.x; k < sg.n * C; k += blockDim.x) {
+    const int s2 = k / C, c2 = k - s2 * C;
+    const float m = train ? seg_sum(sums, q24, k) * sg.inv_rows[s2] : pop_mean[c2];
+    seg_shift[k] = b[c2] - m;
+  }
+  __syncthreads();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nvec) return;
   const int cv = C / 8, Wo = W / 2, Ho = H / 2;
@@ -581,13 +590,7 @@ __global__ void mobn_pool_dropout_fwd_kernel(const bf16* __restrict__ z, bf16* _
   const int64_t p0 = ((n * H + 2 * ho) * W + 2 * wo) * C + c;
   float a[4][8];
   ld8(z, p0, a[0]); ld8(z, p0 + C, a[1]); ld8(z, p0 + (int64_t)W * C, a[2]); ld8(z, p0 + (int64_t)W * C + C, a[3]);
-  const float4* bp = reinterpret_cast<const float4*>(b + c);
-  const float msc = train ? sg.inv_rows[s] : 1.f;
-  const float4 b0 = bp[0], b1 = bp[1];
-  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-  float sh[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) sh[j] = bb[j] - (train ? seg_sum(sums, q24, (int64_t)s * C + c + j) : pop_mean[c + j]) * msc;
+  const float* sh = seg_shift + s * C + c;
   uint8_t keep[8];
   const int64_t e = i * 8;
   if (rate <= 0.f) {
@@ -934,7 +937,7 @@ extern "C" int tgan_mobn_apply_seg(const void* x, void* y, int64_t rows, int C, 
   if (make_segs(sg, rows, nseg, r0, r1, r2)) return 1;
   const int64_t nvec = rows * C / 8;
   cudaStream_t st = (cudaStream_t)stream;
-  TGAN_DISPATCH_ACT(act, A, (pdl_launch(mobn_apply_seg_kernel<A>, grid_for(nvec), 256, 0, (cudaStream_t)(st), (const bf16*)x, (bf16*)y, nvec, C, sums, sums_q24, sg, b, pop_mean, decay, train, alpha)));
+  TGAN_DISPATCH_ACT(act, A, (pdl_launch(mobn_apply_seg_kernel<A>, grid_for(nvec), 256, (size_t)nseg * C * sizeof(float), (cudaStream_t)(st), (const bf16*)x, (bf16*)y, nvec, C, sums, sums_q24, sg, b, pop_mean, decay, train, alpha)));
   TGAN_LAUNCHED();
   return 0;
 }
@@ -1148,7 +1151,7 @@ extern "C" int tgan_mobn_pool_dropout_fwd(const void* z, void* y, uint8_t* code,
   if (make_segs(sg, (int64_t)N * rpi, nseg, n0 * rpi, n1 * rpi, n2 * rpi)) return 1;
   const int64_t nvec = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
   cudaStream_t st = (cudaStream_t)stream;
-  TGAN_DISPATCH_ACT(act, A, (pdl_launch(mobn_pool_dropout_fwd_kernel<A>, ceil_div(nvec, 256), 256, 0, st, (const bf16*)z,
+  TGAN_DISPATCH_ACT(act, A, (pdl_launch(mobn_pool_dropout_fwd_kernel<A>, ceil_div(nvec, 256), 256, (size_t)nseg * C * sizeof(float), st, (const bf16*)z,
                                         (bf16*)y, code, H, W, C, nvec, sums, sums_q24, sg, rpi, b, pop_mean, decay, train, alpha, rate,
                                         1.0f / (1.0f - rate), mask, seed, stream_id, counter)));
   TGAN_LAUNCHED();
