@@ -331,6 +331,28 @@ int tgan_adam_advance(float* state, float beta1, float beta2, void* stream);
 /* Philox counter bump once per step: *counter += inc */
 int tgan_counter_advance(uint64_t* counter, uint64_t inc, void* stream);
 
+/* ---------------------------------------------------------------- data formats either side of the step --
+ * Device-side batch formation from a uint8 dataset resident in HBM (replaces the tf.data / TFRecord host path of
+ * Input_Pipeline/cifar10Dataset.py:42-85, svhnDataset.py:41-88, mnistDataset.py:42-90 for the step's inputs):
+ * out[i] = map(data[idx[i]]) with map = x/255*2-1 (mode 0; cifar10Dataset.py:60, svhnDataset.py:63) or x/255 (mode 1;
+ * mnistDataset.py:65), bit-identical to the float32 TF expression.  data: [n_total, elems] uint8, elems % 16 == 0;
+ * idx: device int64[n] (NULL = the first n images); indices are clamped to [0, n_total). */
+int tgan_gather_images_u8(const void* data, int64_t n_total, int64_t elems, const int64_t* idx, int n,
+                          float* out, int mode, void* stream);
+/* tf.one_hot(label[idx[i]], depth=K) (cifar10Dataset.py:62); labels: device int32[n_total] */
+int tgan_gather_onehot(const int32_t* labels, int64_t n_total, const int64_t* idx, int n, int K, float* out,
+                       void* stream);
+/* z ~ U(-1,1) [n, zdim] and y = one_hot(randint(0,K)) [n, K] (Train_goodGAN.py:232-237) from Philox(seed, stream_id,
+ * *counter); counter may be NULL (= 0). */
+int tgan_draw_latent(float* z, int n, int zdim, float* y, int K, uint64_t seed, const uint64_t* counter,
+                     uint64_t stream_id, void* stream);
+/* utils.py:199-231: merge(inverse_transform(images), [gh, gw]) -> grid [gh*H, gw*W, C]; inverse = 1 applies (x+1)/2 */
+int tgan_image_grid(const float* x, int n, int H, int W, int C, int gh, int gw, float* grid, int inverse,
+                    void* stream);
+/* CRC-32C (Castagnoli, reflected 0x82f63b78) of a HOST buffer, continuing from `crc` (0 to start): the checksum of the
+ * TF tensor-bundle files written by tf.train.Saver (Training/Saver.py:29-36). */
+uint64_t tgan_crc32c(uint64_t crc, const void* data, int64_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -316,6 +316,22 @@ class Train(Train_base):
         self.aux_val = dict(logits=logits)
         return self._acc[0] / max(1, self._acc[1]), idx.data
 
+    def sample(self, z, y, grid=True):
+        """The per-epoch sample of Train_goodGAN.py:353-364: `model.good_sampler(sample_z, sample_y)` (train=False) and,
+        with grid=True, utils.save_images' 8x8 manifold of the first 64 images in [0, 1] (device tensor; writing the
+        PNG is left to the caller).  z [n, Z_DIM], y [n, NUM_CLASSES]: numpy / tensors."""
+        from . import pipeline
+        ctx.store = self.store
+        tz = torch.as_tensor(np.asarray(z, np.float32)).to(ctx.device)
+        ty = torch.as_tensor(np.asarray(y, np.float32)).to(ctx.device)
+        with no_grad():
+            g = self.model.good_sampler(ops.Var(tz, tuple(tz.shape)), ops.Var(ty, tuple(ty.shape)))
+            img = ops.force(g).data.float().reshape([-1] + list(self.config.IMAGE_DIM)).contiguous()
+        if not grid:
+            return img
+        n = min(64, int(img.shape[0]))
+        return pipeline.image_grid(img[:n], pipeline.image_manifold_size(n))
+
     # ------------------------------------------------------------------ epoch driver (SURVEY §8f rank 1) --
     def train_epoch(self, batches, epoch, start_epoch=0):
         """One epoch of Train_goodGAN.py:160-276: the lambda / learning-rate schedule of :165-177, the classifier-only
