@@ -258,10 +258,40 @@ def main():
     f1.record()
     barrier()
     t_e2e = f0.elapsed_time(f1) * 1e-3
-    tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device='cuda')
+    # ---- leg 3: the same public step fed by the device-side input pipeline (tgan/pipeline.py): a uint8 dataset resident
+    # in HBM, each step's eight inputs formed by gather / pixel-map / draw kernels, loss D2H every step, no H2D ----
+    from tgan import pipeline
+    rs = np.random.default_rng(99 + rank)
+    shp = tuple(tr.config.IMAGE_DIM)
+    n_unl, n_lab = 20000, 4000
+    inp = pipeline.TripleGANInput(
+        tr.config,
+        pipeline.DeviceDataset(rs.integers(0, 256, (n_lab,) + shp, dtype=np.uint8), rs.integers(0, tr.config.NUM_CLASSES, n_lab),
+                               tr.config.NUM_CLASSES, wl),
+        pipeline.DeviceDataset(rs.integers(0, 256, (n_unl,) + shp, dtype=np.uint8), rs.integers(0, tr.config.NUM_CLASSES, n_unl),
+                               tr.config.NUM_CLASSES, wl), seed=1234 + rank)
+
+    def pipe_step():
+        try:
+            inp.next_into(tr.inputs)
+        except StopIteration:
+            inp.start_epoch()
+            inp.next_into(tr.inputs)
+        return tr.step(**lam).cpu()
+    for _ in range(2):
+        pipe_step()
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(args.steps):
+        pipe_step()
+    g1.record()
+    barrier()
+    t_pipe = g0.elapsed_time(g1) * 1e-3
+    tt = torch.tensor([t_dev, t_e2e, t_pipe], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_dev, t_e2e = float(tt[0]), float(tt[1])
+    t_dev, t_e2e, t_pipe = float(tt[0]), float(tt[1]), float(tt[2])
     if rank != 0:
         _finish(world, dist, torch)
         return
@@ -278,6 +308,9 @@ def main():
                    'l2': 'no explicit flush: one step streams > 1 GB of activations (>> 126 MB L2) between reuses'},
         'e2e': {'value': imgs / t_e2e, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 12,
                 'ms_per_step': t_e2e / args.steps * 1e3},
+        'e2e_device_pipeline': {'value': imgs / t_pipe, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 12,
+                                'ms_per_step': t_pipe / args.steps * 1e3,
+                                'dataset': 'synthetic uint8, %d unlabelled + %d labelled images resident in HBM per rank' % (n_unl, n_lab)},
         'gpu_launches': int(launches),
         'clocks': clocks,
         'step_tensor_frac': STEP_TFLOPS[wl] * 1e12 * world * args.steps / t_dev / (pk['bf16_sustained'] * 1e12 * world),

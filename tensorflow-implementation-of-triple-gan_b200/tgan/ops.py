@@ -48,7 +48,9 @@ def arena_take(n):
     a = ctx.arena()
     n4 = (n + 3) // 4 * 4
     if ctx.arena_off + n4 > a.numel():
-        arena_reset()
+        # a reset here would zero sums that kernels already in flight still accumulate into / read
+        raise RuntimeError('statistics arena exhausted (%d floats): raise Context.arena_floats or call ops.arena_reset() '
+                           'between passes' % a.numel())
     o = ctx.arena_off
     ctx.arena_off += n4
     return a[o:o + n]

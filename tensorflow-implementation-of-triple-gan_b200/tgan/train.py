@@ -308,6 +308,7 @@ class Train(Train_base):
             self._acc = [0, 0]                  # tf.metrics.accuracy's (total, count) local variables
         tx = torch.as_tensor(np.asarray(x, np.float32)).to(ctx.device)
         ty = torch.as_tensor(np.asarray(y, np.float32)).to(ctx.device)
+        ops.arena_reset()
         with no_grad():
             logits, _ = self.model.classifier(self._pre()(ops.Var(tx, tuple(tx.shape))), False, reuse=True, tag='V/C_real')
             idx, _ = ops.argmax_onehot(logits, self.config.NUM_CLASSES)
@@ -324,6 +325,7 @@ class Train(Train_base):
         ctx.store = self.store
         tz = torch.as_tensor(np.asarray(z, np.float32)).to(ctx.device)
         ty = torch.as_tensor(np.asarray(y, np.float32)).to(ctx.device)
+        ops.arena_reset()
         with no_grad():
             g = self.model.good_sampler(ops.Var(tz, tuple(tz.shape)), ops.Var(ty, tuple(ty.shape)))
             img = ops.force(g).data.float().reshape([-1] + list(self.config.IMAGE_DIM)).contiguous()
