@@ -163,14 +163,22 @@ __global__ void mobn_apply_kernel(const TX* __restrict__ x, TY* __restrict__ y, 
 }
 
 // per-segment channel sum: fp32, or the Q24 fixed-point value accumulated by the GEMM epilogue's integer atomics
+// Q24 -> float without fp64: integer part and 24-bit fraction are each exact in fp32 (|sum| < 2^24), one rounding in the fma
+__device__ __forceinline__ float q24_to_float(long long v) {
+  return __fmaf_rn((float)(int)(v & 0xffffff), 1.f / 16777216.f, (float)(int)(v >> 24));
+}
 __device__ __forceinline__ float seg_sum(const void* sums, int q24, int64_t i) {
-  return q24 ? (float)((double)reinterpret_cast<const long long*>(sums)[i] * (1.0 / 16777216.0))
-             : reinterpret_cast<const float*>(sums)[i];
+  return q24 ? q24_to_float(reinterpret_cast<const long long*>(sums)[i]) : reinterpret_cast<const float*>(sums)[i];
 }
 
 // 8 bf16 per thread (16-byte accesses)
 __device__ __forceinline__ void ld8(const bf16* p, int64_t i, float (&v)[8]) {
   uint4 t = *reinterpret_cast<const uint4*>(p + i);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { v[2 * j] = __low2float(h[j]); v[2 * j + 1] = __high2float(h[j]); }
+}
+__device__ __forceinline__ void unpack8(const uint4& t, float (&v)[8]) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
 #pragma unroll
   for (int j = 0; j < 4; ++j) { v[2 * j] = __low2float(h[j]); v[2 * j + 1] = __high2float(h[j]); }
@@ -198,6 +206,10 @@ __global__ void mobn_apply_seg_kernel(const bf16* __restrict__ x, bf16* __restri
       pop_mean[c] = pm;
     }
   }
+  // the first vector of x is requested before the table is built, so its HBM latency covers the table's L2 latency
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint4 cur = make_uint4(0, 0, 0, 0);
+  if (i0 < nvec) cur = *reinterpret_cast<const uint4*>(x + i0 * 8);
   // per-block table shift[seg][c] = b - mean (the fixed-point -> float conversion is done once per block, not per element)
   extern __shared__ float seg_shift[];
   for (int i = threadIdx.x; i < sg.n * C; i += blockDim.x) {
@@ -207,13 +219,15 @@ __global__ void mobn_apply_seg_kernel(const bf16* __restrict__ x, bf16* __restri
     seg_shift[i] = b[c] - m;
   }
   __syncthreads();
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = i0; i < nvec; i += stride) {
     const int64_t e = i * 8;
     const int64_t r = e / C;
     const int c = (int)(e - r * C);
     const float* sh = seg_shift + sg.of(r) * C + c;
     float v[8];
-    ld8(x, e, v);
+    unpack8(cur, v);
+    if (i + stride < nvec) cur = *reinterpret_cast<const uint4*>(x + (i + stride) * 8);     // next vector in flight
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = act_fwd_t<ACT>(v[j] + sh[j], alpha);
     st8(y, e, v);
@@ -571,13 +585,6 @@ __global__ void mobn_pool_dropout_fwd_kernel(const bf16* __restrict__ z, bf16* _
       pop_mean[c] = pm;
     }
   }
-  extern __shared__ float seg_shift[];         // shift[seg][c] = b - mean, converted once per block
-  for (int k = threadIdx.x; k < sg.n * C; k += blockDim.x) {
-    const int s2 = k / C, c2 = k - s2 * C;
-    const float m = train ? seg_sum(sums, q24, k) * sg.inv_rows[s2] : pop_mean[c2];
-    seg_shift[k] = b[c2] - m;
-  }
-  __syncthreads();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nvec) return;
   const int cv = C / 8, Wo = W / 2, Ho = H / 2;
@@ -590,7 +597,16 @@ __global__ void mobn_pool_dropout_fwd_kernel(const bf16* __restrict__ z, bf16* _
   const int64_t p0 = ((n * H + 2 * ho) * W + 2 * wo) * C + c;
   float a[4][8];
   ld8(z, p0, a[0]); ld8(z, p0 + C, a[1]); ld8(z, p0 + (int64_t)W * C, a[2]); ld8(z, p0 + (int64_t)W * C + C, a[3]);
-  const float* sh = seg_shift + s * C + c;
+  // shift = b - mean of this thread's (segment, 8 channels): requested after the z loads so the latencies overlap
+  float sh[8];
+  {
+    const float4* bp = reinterpret_cast<const float4*>(b + c);
+    const float4 b0 = bp[0], b1 = bp[1];
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const float msc = train ? sg.inv_rows[s] : 1.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sh[j] = bb[j] - (train ? seg_sum(sums, q24, (int64_t)s * C + c + j) : pop_mean[c + j]) * msc;
+  }
   uint8_t keep[8];
   const int64_t e = i * 8;
   if (rate <= 0.f) {
@@ -937,7 +953,7 @@ extern "C" int tgan_mobn_apply_seg(const void* x, void* y, int64_t rows, int C, 
   if (make_segs(sg, rows, nseg, r0, r1, r2)) return 1;
   const int64_t nvec = rows * C / 8;
   cudaStream_t st = (cudaStream_t)stream;
-  TGAN_DISPATCH_ACT(act, A, (pdl_launch(mobn_apply_seg_kernel<A>, grid_for(nvec), 256, (size_t)nseg * C * sizeof(float), (cudaStream_t)(st), (const bf16*)x, (bf16*)y, nvec, C, sums, sums_q24, sg, b, pop_mean, decay, train, alpha)));
+  TGAN_DISPATCH_ACT(act, A, (pdl_launch(mobn_apply_seg_kernel<A>, std::min(grid_for(nvec), 148 * 8), 256, (size_t)nseg * C * sizeof(float), (cudaStream_t)(st), (const bf16*)x, (bf16*)y, nvec, C, sums, sums_q24, sg, b, pop_mean, decay, train, alpha)));
   TGAN_LAUNCHED();
   return 0;
 }
@@ -1151,7 +1167,7 @@ extern "C" int tgan_mobn_pool_dropout_fwd(const void* z, void* y, uint8_t* code,
   if (make_segs(sg, (int64_t)N * rpi, nseg, n0 * rpi, n1 * rpi, n2 * rpi)) return 1;
   const int64_t nvec = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
   cudaStream_t st = (cudaStream_t)stream;
-  TGAN_DISPATCH_ACT(act, A, (pdl_launch(mobn_pool_dropout_fwd_kernel<A>, ceil_div(nvec, 256), 256, (size_t)nseg * C * sizeof(float), st, (const bf16*)z,
+  TGAN_DISPATCH_ACT(act, A, (pdl_launch(mobn_pool_dropout_fwd_kernel<A>, ceil_div(nvec, 256), 256, 0, st, (const bf16*)z,
                                         (bf16*)y, code, H, W, C, nvec, sums, sums_q24, sg, rpi, b, pop_mean, decay, train, alpha, rate,
                                         1.0f / (1.0f - rate), mask, seed, stream_id, counter)));
   TGAN_LAUNCHED();

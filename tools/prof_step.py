@@ -9,14 +9,15 @@ import torch, tgan
 from tgan import synthetic
 from torch.profiler import profile, ProfilerActivity
 tag = sys.argv[1] if len(sys.argv) > 1 else 'r1'
+wl = sys.argv[2] if len(sys.argv) > 2 else 'cifar10'
 tgan.init('cuda:0', math='bf16')
-tr = tgan.make_trainer('cifar10', zca=synthetic.make_zca(1234))
+tr = tgan.make_trainer(wl, zca=synthetic.make_zca(1234) if wl == 'cifar10' else None)
 tr.load_batch({k: torch.from_numpy(v) for k, v in synthetic.make_batch(tr.config, 1234).items()})
 for _ in range(3):
-    tr.step(lambda_1=0.3, lambda_2=0.5)
+    tr.step(lambda_1=tr.config.FAKE_G_LAMBDA, lambda_2=0.5)
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
-    tr.step(lambda_1=0.3, lambda_2=0.5)
+    tr.step(lambda_1=tr.config.FAKE_G_LAMBDA, lambda_2=0.5)
     torch.cuda.synchronize()
 evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 evs.sort(key=lambda e: e.time_range.start)
