@@ -139,6 +139,49 @@ __global__ void __launch_bounds__(128) im2col_bf16_kernel(const T* __restrict__ 
   }
 }
 
+// bf16 input whose pixels are 16-byte aligned (ldx % 8 == 0): work item = (tap, row); a pixel's channels arrive with 16-byte
+// loads (consecutive threads -> consecutive pixels), the row is assembled in shared memory as above.  256 threads.
+__global__ void __launch_bounds__(256) im2col_bf16_vec_kernel(const bf16* __restrict__ x, int N, int H, int W, int C, int ldx,
+                                                              int kh, int kw, int sh, int sw, int pt, int pl, int Ho, int Wo,
+                                                              bf16* __restrict__ col, int ldc, int64_t rows) {
+  pdl_entry();
+  extern __shared__ uint32_t im2col_sm[];
+  const int pitch = ldc / 2 + 1;
+  const int64_t row0 = (int64_t)blockIdx.x * 128;
+  const int nrows = (int)(rows - row0 < 128 ? rows - row0 : 128);
+  const int taps = kh * kw, K = taps * C, nv = (C + 7) / 8;
+  for (int item = threadIdx.x; item < taps * 128; item += 256) {
+    const int t = item >> 7, rl = item & 127;
+    if (rl >= nrows) continue;
+    const int64_t row = row0 + rl;
+    const int wo = (int)(row % Wo), ho = (int)((row / Wo) % Ho), n = (int)(row / ((int64_t)Wo * Ho));
+    const int r = t / kw, s2 = t - r * kw;
+    const int hi = ho * sh + r - pt, wi = wo * sw + s2 - pl;
+    const bool in = hi >= 0 && hi < H && wi >= 0 && wi < W;
+    bf16* dst = reinterpret_cast<bf16*>(im2col_sm + (size_t)rl * pitch) + t * C;
+    const uint4* px = reinterpret_cast<const uint4*>(x + ((int64_t)(n * H + hi) * W + wi) * ldx);
+    for (int v = 0; v < nv; ++v) {
+      uint4 q = make_uint4(0, 0, 0, 0);
+      if (in) q = px[v];
+      const bf16* e = reinterpret_cast<const bf16*>(&q);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (v * 8 + j < C) dst[v * 8 + j] = e[j];
+    }
+  }
+  for (int i = threadIdx.x; i < nrows * (ldc - K); i += 256) {                 // zero the K..ldc tail of every row
+    const int rl = i / (ldc - K), k = K + i - rl * (ldc - K);
+    reinterpret_cast<bf16*>(im2col_sm + (size_t)rl * pitch)[k] = __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+  const int cpr = ldc / 8;
+  for (int j = threadIdx.x; j < nrows * cpr; j += 256) {
+    const int rl = j / cpr, kk = (j - rl * cpr) * 4;
+    const uint32_t* sp = im2col_sm + (size_t)rl * pitch + kk;
+    *reinterpret_cast<uint4*>(col + (row0 + rl) * ldc + kk * 2) = make_uint4(sp[0], sp[1], sp[2], sp[3]);
+  }
+}
+
 template <typename T>
 __global__ void col2im_kernel(const float* __restrict__ col, int N, int H, int W, int C, int kh, int kw, int sh,
                               int sw, int pt, int pl, int Ho, int Wo, T* __restrict__ x, int Cx, int ldx,
@@ -215,6 +258,17 @@ extern "C" int tgan_im2col_bf16(const void* x, int xdt, int N, int H, int W, int
   const int64_t rows = (int64_t)N * Ho * Wo;
   TGAN_CHECK_ARG(rows > 0 && ldc <= 512 && ((uintptr_t)col & 15) == 0, "im2col_bf16: empty / ldc > 512 / unaligned col");
   const size_t smem = (size_t)128 * (ldc / 2 + 1) * 4;
+  if (xdt == TGAN_BF16 && ldx % 8 == 0 && (C + 7) / 8 * 8 <= ldx && ((uintptr_t)x & 15) == 0) {
+    static bool vattr = false;
+    if (!vattr && smem > 48 * 1024) {
+      cudaFuncSetAttribute(im2col_bf16_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024);
+      vattr = true;
+    }
+    pdl_launch(im2col_bf16_vec_kernel, ceil_div(rows, 128), 256, smem, (cudaStream_t)stream, (const bf16*)x, N, H, W, C, ldx, kh, kw, sh,
+               sw, pt, pl, Ho, Wo, (bf16*)col, ldc, rows);
+    TGAN_LAUNCHED();
+    return 0;
+  }
   TGAN_DISPATCH_1(xdt, T, {
     static bool attr = false;
     if (!attr && smem > 48 * 1024) {

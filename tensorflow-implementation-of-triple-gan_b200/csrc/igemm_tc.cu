@@ -688,6 +688,31 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, in
   }
 }
 
+// the same sum (same order per element) with 16-byte accesses and four partial slices in flight per thread
+__global__ void wgrad_reduce_v4_kernel(const float4* __restrict__ ws, int splits, int64_t tot4, int64_t tot_store4,
+                                       float4* __restrict__ dw, float beta) {
+  pdl_entry();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot_store4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    int z = 0;
+    for (; z + 4 <= splits; z += 4) {
+      const float4 a = ws[(int64_t)z * tot4 + i], b = ws[(int64_t)(z + 1) * tot4 + i], c = ws[(int64_t)(z + 2) * tot4 + i],
+                   d = ws[(int64_t)(z + 3) * tot4 + i];
+      s.x = ((s.x + a.x) + b.x) + c.x + d.x; s.y = ((s.y + a.y) + b.y) + c.y + d.y;
+      s.z = ((s.z + a.z) + b.z) + c.z + d.z; s.w = ((s.w + a.w) + b.w) + c.w + d.w;
+    }
+    for (; z < splits; ++z) {
+      const float4 a = ws[(int64_t)z * tot4 + i];
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+    }
+    if (beta != 0.f) {
+      const float4 o = dw[i];
+      s.x += beta * o.x; s.y += beta * o.y; s.z += beta * o.z; s.w += beta * o.w;
+    }
+    dw[i] = s;
+  }
+}
+
 // dst[t][n][k] (bf16, k < Kpad) = k < K ? src[tap(t)*st + n*sn + k*sk] : 0
 __global__ void pack_weight_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int T, int Nr, int K,
                                    int Kpad, int64_t st, int64_t sn, int64_t sk, const int* __restrict__ taps,
@@ -941,9 +966,16 @@ extern "C" int tgan_wgrad_bf16(const tgan_wgrad_args* a, void* stream) {
   const int64_t tot = (int64_t)a->T * a->Cout * a->Cin;
   TGAN_CHECK_ARG(a->cin_store == 0 || (a->T == 1 && a->cin_store <= a->Cin), "wgrad: cin_store needs T == 1");
   const int64_t tot_store = a->cin_store > 0 ? (int64_t)a->cin_store * a->Cout : tot;
-  int rg = ceil_div(tot_store, 256);
-  if (rg > 148 * 8) rg = 148 * 8;
-  pdl_launch(wgrad_reduce_kernel, rg, 256, 0, (cudaStream_t)((cudaStream_t)stream), a->ws, p.splits, tot, tot_store, a->dw, a->beta);
+  if (tot % 4 == 0 && tot_store % 4 == 0 && ((uintptr_t)a->ws & 15) == 0 && ((uintptr_t)a->dw & 15) == 0) {
+    int rg = ceil_div(tot_store / 4, 256);
+    if (rg > 148 * 8) rg = 148 * 8;
+    pdl_launch(wgrad_reduce_v4_kernel, rg, 256, 0, (cudaStream_t)stream, (const float4*)a->ws, p.splits, tot / 4, tot_store / 4,
+               (float4*)a->dw, a->beta);
+  } else {
+    int rg = ceil_div(tot_store, 256);
+    if (rg > 148 * 8) rg = 148 * 8;
+    pdl_launch(wgrad_reduce_kernel, rg, 256, 0, (cudaStream_t)stream, a->ws, p.splits, tot, tot_store, a->dw, a->beta);
+  }
   TGAN_LAUNCHED();
   return 0;
 }
