@@ -688,21 +688,38 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, in
   }
 }
 
-// the same sum (same order per element) with 16-byte accesses and four partial slices in flight per thread
-__global__ void wgrad_reduce_v4_kernel(const float4* __restrict__ ws, int splits, int64_t tot4, int64_t tot_store4,
-                                       float4* __restrict__ dw, float beta) {
+// 16-byte accesses, and the split range is cut into 4 groups summed by different threads (64 outputs x 4 groups per CTA,
+// folded through shared memory in a fixed order): the single-chain version is bound by load latency -- 49 dependent
+// rounds for the 128->128 layers -- not by bandwidth.  Deterministic (fixed association), not the same rounding as the
+// scalar kernel.
+__global__ void __launch_bounds__(256) wgrad_reduce_v4_kernel(const float4* __restrict__ ws, int splits, int64_t tot4,
+                                                              int64_t tot_store4, float4* __restrict__ dw, float beta) {
   pdl_entry();
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot_store4; i += (int64_t)gridDim.x * blockDim.x) {
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    int z = 0;
-    for (; z + 4 <= splits; z += 4) {
+  __shared__ float4 part[4][64];
+  const int tx = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const int64_t i = (int64_t)blockIdx.x * 64 + tx;
+  const int per = (splits + 3) / 4;
+  const int z0 = g * per, z1 = min(splits, z0 + per);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < tot_store4) {
+    int z = z0;
+    for (; z + 4 <= z1; z += 4) {
       const float4 a = ws[(int64_t)z * tot4 + i], b = ws[(int64_t)(z + 1) * tot4 + i], c = ws[(int64_t)(z + 2) * tot4 + i],
                    d = ws[(int64_t)(z + 3) * tot4 + i];
       s.x = ((s.x + a.x) + b.x) + c.x + d.x; s.y = ((s.y + a.y) + b.y) + c.y + d.y;
       s.z = ((s.z + a.z) + b.z) + c.z + d.z; s.w = ((s.w + a.w) + b.w) + c.w + d.w;
     }
-    for (; z < splits; ++z) {
+    for (; z < z1; ++z) {
       const float4 a = ws[(int64_t)z * tot4 + i];
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+    }
+  }
+  part[g][tx] = s;
+  __syncthreads();
+  if (g == 0 && i < tot_store4) {
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      const float4 a = part[k][tx];
       s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
     }
     if (beta != 0.f) {
@@ -967,8 +984,7 @@ extern "C" int tgan_wgrad_bf16(const tgan_wgrad_args* a, void* stream) {
   TGAN_CHECK_ARG(a->cin_store == 0 || (a->T == 1 && a->cin_store <= a->Cin), "wgrad: cin_store needs T == 1");
   const int64_t tot_store = a->cin_store > 0 ? (int64_t)a->cin_store * a->Cout : tot;
   if (tot % 4 == 0 && tot_store % 4 == 0 && ((uintptr_t)a->ws & 15) == 0 && ((uintptr_t)a->dw & 15) == 0) {
-    int rg = ceil_div(tot_store / 4, 256);
-    if (rg > 148 * 8) rg = 148 * 8;
+    const int rg = ceil_div(tot_store / 4, 64);
     pdl_launch(wgrad_reduce_v4_kernel, rg, 256, 0, (cudaStream_t)stream, (const float4*)a->ws, p.splits, tot / 4, tot_store / 4,
                (float4*)a->dw, a->beta);
   } else {
