@@ -46,42 +46,52 @@ __global__ void __launch_bounds__(LT) loss_g_kernel(const float* df, int nf, flo
   if (threadIdx.x == 0) *loss = 0.5f * a / nf;
 }
 
-// softmax of one row into registers; returns log-sum-exp
-__device__ __forceinline__ float row_softmax(const float* x, int K, float (&p)[MAXK], int& am) {
+// softmax of one row into registers; returns log-sum-exp and the max probability.  KT > 0 = compile-time class count: the
+// loops unroll and p[] stays in registers (with a runtime K every p[k] is a local-memory access).
+template <int KT>
+__device__ __forceinline__ float row_softmax(const float* x, int Krt, float (&p)[MAXK], int& am, float& pmax) {
+  const int K = KT > 0 ? KT : Krt;
   float m = x[0]; am = 0;
+#pragma unroll
   for (int k = 1; k < K; ++k) if (x[k] > m) { m = x[k]; am = k; }
   float s = 0.f;
+#pragma unroll
   for (int k = 0; k < K; ++k) { p[k] = expf(x[k] - m); s += p[k]; }
   float inv = 1.f / s;
+#pragma unroll
   for (int k = 0; k < K; ++k) p[k] *= inv;
+  pmax = inv;                       // p[am] = exp(0) * inv
   return m + logf(s);
 }
 
+template <int KT>
 __global__ void __launch_bounds__(LT)
 loss_c_kernel(const float* __restrict__ c_real, const float* __restrict__ y_l_c, int n_real,
               const float* __restrict__ c_unl, const float* __restrict__ c_rep, const float* __restrict__ d_unl,
-              int n_unl, const float* __restrict__ c_fake, const float* __restrict__ y_g, int n_fake, int K,
+              int n_unl, const float* __restrict__ c_fake, const float* __restrict__ y_g, int n_fake, int Krt,
               const float* __restrict__ lambdas, float* loss, float* g_real, float* g_unl, float* g_rep,
               float* g_fake) {
   pdl_entry();
+  const int K = KT > 0 ? KT : Krt;
   __shared__ float sm[32];
   __shared__ float q[MAXK];
   const float lambda_1 = lambdas[0], lambda_2 = lambdas[1];
   float p[MAXK];
   int am;
+  float pam;
   // ---- supervised CE on labelled and generated images (train_base.py:130-131) ----
   float l_real = 0.f, l_fake = 0.f;
   for (int n = threadIdx.x; n < n_real; n += LT) {
-    float lse = row_softmax(c_real + n * K, K, p, am);
+    float lse = row_softmax<KT>(c_real + n * K, K, p, am, pam);
     float ys = 0.f, l = 0.f;
-    for (int k = 0; k < K; ++k) { float y = y_l_c[n * K + k]; ys += y; l -= y * (c_real[n * K + k] - lse); }
+    _Pragma("unroll") for (int k = 0; k < K; ++k) { float y = y_l_c[n * K + k]; ys += y; l -= y * (c_real[n * K + k] - lse); }
     l_real += l;
     if (g_real) for (int k = 0; k < K; ++k) g_real[n * K + k] = (p[k] * ys - y_l_c[n * K + k]) / n_real;
   }
   for (int n = threadIdx.x; n < n_fake; n += LT) {
-    float lse = row_softmax(c_fake + n * K, K, p, am);
+    float lse = row_softmax<KT>(c_fake + n * K, K, p, am, pam);
     float ys = 0.f, l = 0.f;
-    for (int k = 0; k < K; ++k) { float y = y_g[n * K + k]; ys += y; l -= y * (c_fake[n * K + k] - lse); }
+    _Pragma("unroll") for (int k = 0; k < K; ++k) { float y = y_g[n * K + k]; ys += y; l -= y * (c_fake[n * K + k] - lse); }
     l_fake += l;
     if (g_fake) for (int k = 0; k < K; ++k) g_fake[n * K + k] = lambda_1 * (p[k] * ys - y_g[n * K + k]) / n_fake;
   }
@@ -91,24 +101,24 @@ loss_c_kernel(const float* __restrict__ c_real, const float* __restrict__ y_l_c,
   for (int k = 0; k < MAXK; ++k) qk[k] = 0.f;
   for (int n = threadIdx.x; n < n_unl; n += LT) {
     const float* x = c_unl + n * K;
-    float lse = row_softmax(x, K, p, am);
+    float lse = row_softmax<KT>(x, K, p, am, pam);
     float s = sig_ce(d_unl[n], 1.f);
-    l_unl += p[am] * s;
+    l_unl += pam * s;
     float px = 0.f;
-    for (int k = 0; k < K; ++k) { px += p[k] * x[k]; qk[k] += p[k]; }
+    _Pragma("unroll") for (int k = 0; k < K; ++k) { px += p[k] * x[k]; qk[k] += p[k]; }
     l_ent += lse - px;
     if (c_rep) for (int k = 0; k < K; ++k) { float d = x[k] - c_rep[n * K + k]; l_mse += d * d; }
   }
   l_real = block_sum(l_real, sm); l_fake = block_sum(l_fake, sm);
   l_unl = block_sum(l_unl, sm); l_ent = block_sum(l_ent, sm); l_mse = block_sum(l_mse, sm);
-  for (int k = 0; k < K; ++k) {
+  _Pragma("unroll") for (int k = 0; k < K; ++k) {
     float s = block_sum(qk[k], sm);
     if (threadIdx.x == 0) q[k] = s / n_unl;
   }
   __syncthreads();
   float l_bal = 0.f;
   float r[MAXK];
-  for (int k = 0; k < K; ++k) { r[k] = 1.f / (q[k] + 1e-12f); l_bal -= logf(q[k] + 1e-12f) / K; }
+  _Pragma("unroll") for (int k = 0; k < K; ++k) { r[k] = 1.f / (q[k] + 1e-12f); l_bal -= logf(q[k] + 1e-12f) / K; }
   if (threadIdx.x == 0) {
     float c_real_tot = l_real / n_real + 1e-6f * (l_ent / n_unl) + 1e-3f * l_bal;
     float v = 0.01f * 0.5f * (l_unl / n_unl) + c_real_tot + lambda_1 * (l_fake / n_fake);
@@ -119,12 +129,12 @@ loss_c_kernel(const float* __restrict__ c_real, const float* __restrict__ y_l_c,
   if (g_unl) {
     for (int n = threadIdx.x; n < n_unl; n += LT) {
       const float* x = c_unl + n * K;
-      row_softmax(x, K, p, am);
+      row_softmax<KT>(x, K, p, am, pam);
       float s = sig_ce(d_unl[n], 1.f);
       float px = 0.f, pr = 0.f;
-      for (int k = 0; k < K; ++k) { px += p[k] * x[k]; pr += p[k] * r[k]; }
-      for (int k = 0; k < K; ++k) {
-        float g = 0.005f * (s / n_unl) * p[am] * ((k == am ? 1.f : 0.f) - p[k]);
+      _Pragma("unroll") for (int k = 0; k < K; ++k) { px += p[k] * x[k]; pr += p[k] * r[k]; }
+      _Pragma("unroll") for (int k = 0; k < K; ++k) {
+        float g = 0.005f * (s / n_unl) * pam * ((k == am ? 1.f : 0.f) - p[k]);
         g += 1e-6f * (-p[k] * (x[k] - px) / n_unl);
         g += 1e-3f * (-(1.f / (K * (float)n_unl)) * p[k] * (r[k] - pr));
         if (c_rep) {
@@ -161,8 +171,12 @@ extern "C" int tgan_loss_c(const float* c_real, const float* y_l_c, int n_real, 
                            float* g_fake, void* stream) {
   TGAN_CHECK_ARG(c_real && y_l_c && c_unl && d_unl_logits && c_fake && y_g && lambdas && loss, "loss_c: null pointer");
   TGAN_CHECK_ARG(K > 0 && K <= MAXK && n_real > 0 && n_unl > 0 && n_fake > 0, "loss_c: bad sizes (K <= %d)", MAXK);
-  pdl_launch(loss_c_kernel, 1, LT, 0, (cudaStream_t)((cudaStream_t)stream), c_real, y_l_c, n_real, c_unl, c_rep, d_unl_logits, n_unl, c_fake,
-                                                    y_g, n_fake, K, lambdas, loss, g_real, g_unl, g_rep, g_fake);
+  if (K == 10)
+    pdl_launch(loss_c_kernel<10>, 1, LT, 0, (cudaStream_t)stream, c_real, y_l_c, n_real, c_unl, c_rep, d_unl_logits, n_unl, c_fake,
+               y_g, n_fake, K, lambdas, loss, g_real, g_unl, g_rep, g_fake);
+  else
+    pdl_launch(loss_c_kernel<0>, 1, LT, 0, (cudaStream_t)stream, c_real, y_l_c, n_real, c_unl, c_rep, d_unl_logits, n_unl, c_fake,
+               y_g, n_fake, K, lambdas, loss, g_real, g_unl, g_rep, g_fake);
   TGAN_LAUNCHED();
   return 0;
 }
