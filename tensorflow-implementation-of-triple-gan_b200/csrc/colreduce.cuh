@@ -7,6 +7,7 @@
 // gradients behind a batch norm are sums of large terms that cancel almost exactly (sum of BN input-gradients is 0),
 // so fp32 summation noise would otherwise depend on the fold order at the 1e-2 level.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 namespace tgan {
@@ -15,6 +16,11 @@ namespace tgan {
 // different streams) use different workspaces, hence different counters.  Zero at load; the last CTA resets its slot.
 constexpr int COLREDUCE_WS_SLOTS = 8;
 __device__ unsigned int g_colreduce_ticket[COLREDUCE_WS_SLOTS][1024];
+
+template <typename F, typename = void>
+struct has_split_load : std::false_type {};
+template <typename F>
+struct has_split_load<F, std::void_t<typename F::Regs>> : std::true_type {};
 
 template <int NACC, int VEC, typename F>
 __global__ void __launch_bounds__(256) colreduce_kernel(F f, int64_t rows, int C, double* __restrict__ partials,
@@ -31,7 +37,27 @@ __global__ void __launch_bounds__(256) colreduce_kernel(F f, int64_t rows, int C
 #pragma unroll
     for (int j = 0; j < VEC; ++j) acc[a][j] = 0.0;
   if (c0 < C) {
-    for (int64_t r = (int64_t)blockIdx.y * RL + ty; r < rows; r += (int64_t)gridDim.y * RL) {
+    const int64_t step = (int64_t)gridDim.y * RL;
+    int64_t r = (int64_t)blockIdx.y * RL + ty;
+    if constexpr (has_split_load<F>::value) {
+      // functors with a load / finish split: the loads of four rows are issued before the first result is stored (the
+      // one-row-at-a-time loop keeps only two 8-byte loads per thread in flight and runs at a third of the HBM rate)
+      for (; r + 3 * step < rows; r += 4 * step) {
+        typename F::Regs q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) f.load(r + u * step, c0, q[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float v[NACC][VEC];
+          f.finish(r + u * step, c0, q[u], v);
+#pragma unroll
+          for (int a = 0; a < NACC; ++a)
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) acc[a][j] += (double)v[a][j];
+        }
+      }
+    }
+    for (; r < rows; r += step) {
       float v[NACC][VEC];
       f(r, c0, v);
 #pragma unroll

@@ -25,17 +25,29 @@ struct StatsF {
 template <typename TDY, typename TY, typename TDU, int VEC, int ACT>
 struct ActBwdF {
   const TDY* dy; const TY* y; TDU* du; int C; float alpha; int ldy;      // y may live in a channel-padded buffer
-  __device__ void operator()(int64_t r, int c0, float (&v)[1][VEC]) const {
+  struct Regs { float a[VEC], b[VEC]; };     // load / finish split (colreduce_kernel keeps four rows in flight)
+  __device__ __forceinline__ void load(int64_t r, int c0, Regs& q) const {
     if constexpr (VEC == 4) {
-      float a[4], b[4], o[4];
-      ld4<TDY>(dy, r * C + c0, a); ld4<TY>(y, r * ldy + c0, b);
+      ld4<TDY>(dy, r * C + c0, q.a); ld4<TY>(y, r * ldy + c0, q.b);
+    } else {
+      q.a[0] = ldf<TDY>(dy, r * C + c0); q.b[0] = ldf<TY>(y, r * ldy + c0);
+    }
+  }
+  __device__ __forceinline__ void finish(int64_t r, int c0, const Regs& q, float (&v)[1][VEC]) const {
+    if constexpr (VEC == 4) {
+      float o[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { o[j] = a[j] * act_grad_from_y_t<ACT>(b[j], alpha); v[0][j] = o[j]; }
+      for (int j = 0; j < 4; ++j) { o[j] = q.a[j] * act_grad_from_y_t<ACT>(q.b[j], alpha); v[0][j] = o[j]; }
       st4<TDU>(du, r * C + c0, o);
     } else {
-      float o = ldf<TDY>(dy, r * C + c0) * act_grad_from_y_t<ACT>(ldf<TY>(y, r * ldy + c0), alpha);
+      float o = q.a[0] * act_grad_from_y_t<ACT>(q.b[0], alpha);
       v[0][0] = o; stf<TDU>(du, r * C + c0, o);
     }
+  }
+  __device__ void operator()(int64_t r, int c0, float (&v)[1][VEC]) const {
+    Regs q;
+    load(r, c0, q);
+    finish(r, c0, q, v);
   }
 };
 
