@@ -11,14 +11,19 @@ namespace tgan {
 template <typename T, int VEC>
 struct StatsF {
   const T* x; int C;
-  __device__ void operator()(int64_t r, int c0, float (&v)[2][VEC]) const {
-    if constexpr (VEC == 4) {
-      float t[4]; ld4<T>(x, r * C + c0, t);
+  struct Regs { float t[VEC]; };
+  __device__ __forceinline__ void load(int64_t r, int c0, Regs& q) const {
+    if constexpr (VEC == 4) ld4<T>(x, r * C + c0, q.t);
+    else q.t[0] = ldf<T>(x, r * C + c0);
+  }
+  __device__ __forceinline__ void finish(int64_t, int, const Regs& q, float (&v)[2][VEC]) const {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { v[0][j] = t[j]; v[1][j] = t[j] * t[j]; }
-    } else {
-      float t = ldf<T>(x, r * C + c0); v[0][0] = t; v[1][0] = t * t;
-    }
+    for (int j = 0; j < VEC; ++j) { v[0][j] = q.t[j]; v[1][j] = q.t[j] * q.t[j]; }
+  }
+  __device__ void operator()(int64_t r, int c0, float (&v)[2][VEC]) const {
+    Regs q;
+    load(r, c0, q);
+    finish(r, c0, q, v);
   }
 };
 
@@ -86,13 +91,25 @@ struct ActBwdSegF {
 template <typename TDY, typename TX, int VEC>
 struct BnBwdStatsF {
   const TDY* dy; const TX* x; const float* mean; const float* rstd; int C;
-  __device__ void operator()(int64_t r, int c0, float (&v)[2][VEC]) const {
+  struct Regs { float d[VEC], x[VEC]; };
+  __device__ __forceinline__ void load(int64_t r, int c0, Regs& q) const {
+    if constexpr (VEC == 4) {
+      ld4<TDY>(dy, r * C + c0, q.d); ld4<TX>(x, r * C + c0, q.x);
+    } else {
+      q.d[0] = ldf<TDY>(dy, r * C + c0); q.x[0] = ldf<TX>(x, r * C + c0);
+    }
+  }
+  __device__ __forceinline__ void finish(int64_t, int c0, const Regs& q, float (&v)[2][VEC]) const {
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-      float d = ldf<TDY>(dy, r * C + c0 + j);
-      float xh = (ldf<TX>(x, r * C + c0 + j) - mean[c0 + j]) * rstd[c0 + j];
-      v[0][j] = d; v[1][j] = d * xh;
+      const float xh = (q.x[j] - mean[c0 + j]) * rstd[c0 + j];
+      v[0][j] = q.d[j]; v[1][j] = q.d[j] * xh;
     }
+  }
+  __device__ void operator()(int64_t r, int c0, float (&v)[2][VEC]) const {
+    Regs q;
+    load(r, c0, q);
+    finish(r, c0, q, v);
   }
 };
 
@@ -1090,7 +1107,7 @@ extern "C" int tgan_bn_bwd(const void* dy, int dydt, const void* x, int xdt, voi
   DISPATCH_2(dydt, TDY, xdt, TX, {
     BnBwdStatsF<TDY, TX, 1> f1{(const TDY*)dy, (const TX*)x, mean, rstd, C};
     BnBwdStatsF<TDY, TX, 4> f4{(const TDY*)dy, (const TX*)x, mean, rstd, C};
-    int rc = run_colreduce<2>(f1, f4, C % 4 == 0, rows, C, s1, s2, 0.f, ws, st);
+    int rc = run_colreduce<2>(f1, f4, C % 4 == 0 && aligned16(dy) && aligned16(x), rows, C, s1, s2, 0.f, ws, st);
     if (rc) return rc;
   });
   int64_t n = rows * C;
