@@ -845,6 +845,35 @@ __global__ void affine_concat_kernel(const TX* __restrict__ x, TY* __restrict__ 
   stf<TY>(y, i, v);
 }
 
+// bf16 in and out, C % 8 == 0, ldy % 8 == 0: one thread = one 16-byte chunk of an output row
+__global__ void affine_concat_v8_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int C, int ldy,
+                                        const float* __restrict__ scale, const float* __restrict__ shift,
+                                        const float* __restrict__ lab, int K, int rps, int64_t nvec) {
+  pdl_entry();
+  const int cw = ldy / 8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cw;
+    const int j0 = (int)(i - r * cw) * 8;
+    float v[8];
+    if (j0 < C) {
+      ld8(x, r * C + j0, v);
+      if (scale) {
+        const float4 s0 = *reinterpret_cast<const float4*>(scale + j0), s1 = *reinterpret_cast<const float4*>(scale + j0 + 4);
+        v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w; v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
+      }
+      if (shift) {
+        const float4 s0 = *reinterpret_cast<const float4*>(shift + j0), s1 = *reinterpret_cast<const float4*>(shift + j0 + 4);
+        v[0] += s0.x; v[1] += s0.y; v[2] += s0.z; v[3] += s0.w; v[4] += s1.x; v[5] += s1.y; v[6] += s1.z; v[7] += s1.w;
+      }
+    } else {
+      const float* l = lab + (r / rps) * K;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (j0 - C + j < K) ? l[j0 - C + j] : 0.f;
+    }
+    st8(y, r * ldy + j0, v);
+  }
+}
+
 // out[r, C + j] = j < K ? lab[(r / rps) * K + j] : 0 for j in [0, ldo - C): the label planes (+ zero pad) of a tensor whose
 // first C channels were written in place by the producing GEMM epilogue
 template <typename TO>
@@ -1266,6 +1295,13 @@ extern "C" int tgan_affine_concat(const void* x, int xdt, void* y, int ydt, int 
                                   const float* shift, const float* lab, int K, int rows_per_sample, void* stream) {
   TGAN_CHECK_ARG(x && y && lab && rows > 0 && ldy >= C + K && rows_per_sample > 0, "affine_concat: bad args");
   const int64_t total = rows * ldy;
+  if (xdt == TGAN_BF16 && ydt == TGAN_BF16 && C % 8 == 0 && ldy % 8 == 0 && aligned16(x) && aligned16(y) &&
+      (!scale || aligned16(scale)) && (!shift || aligned16(shift))) {
+    pdl_launch(affine_concat_v8_kernel, grid_for(total / 8), 256, 0, (cudaStream_t)stream, (const bf16*)x, (bf16*)y, C, ldy, scale, shift,
+               lab, K, rows_per_sample, total / 8);
+    TGAN_LAUNCHED();
+    return 0;
+  }
   DISPATCH_2(xdt, TX, ydt, TY, (pdl_launch(affine_concat_kernel<TX, TY>, ceil_div(total, 256), 256, 0, (cudaStream_t)stream,
                                            (const TX*)x, (TY*)y, C, ldy, scale, shift, lab, K, rows_per_sample, total)));
   TGAN_LAUNCHED();
