@@ -107,36 +107,16 @@ __global__ void __launch_bounds__(256) wn_bwd_apply_kernel(const tgan_wn_desc* _
 // dst[t][n][k] (bf16, k < Kpad) = k < K ? src[taps[t]*st + n*sn + k*sk] * scale : 0, in 32x32 (n, k) tiles.  One of the
 // source strides is 1 in every layout the step uses; when it is the n stride the tile is transposed through shared
 // memory so that both the fp32 reads and the bf16 writes are coalesced.
-// The tiles of all tensors form ONE work list walked by a fixed grid (a (148*4, n) grid of mostly empty CTAs cost more in
-// CTA scheduling than the copies themselves): every CTA builds the per-tensor tile prefix in shared memory.
-constexpr int PACK_MAX_DESCS = 128;
-__global__ void __launch_bounds__(256) pack_multi_kernel(const tgan_pack_desc* __restrict__ descs, int n) {
+__global__ void __launch_bounds__(256) pack_multi_kernel(const tgan_pack_desc* __restrict__ descs) {
   pdl_entry();
+  const tgan_pack_desc d = descs[blockIdx.y];
   __shared__ float sm[32][33];
-  __shared__ int pre[PACK_MAX_DESCS + 1];
-  if (threadIdx.x < n) {
-    const tgan_pack_desc* q = descs + threadIdx.x;
-    pre[threadIdx.x + 1] = q->T * ((q->Nr + 31) / 32) * ((q->Kpad + 31) / 32);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    pre[0] = 0;
-    for (int i = 0; i < n; ++i) pre[i + 1] += pre[i];
-  }
-  __syncthreads();
-  const int total = pre[n];
+  const int nbk = (d.Kpad + 31) / 32, nbn = (d.Nr + 31) / 32;
+  const int tiles = d.T * nbn * nbk;
+  bf16* dst = reinterpret_cast<bf16*>(d.dst);
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int g = blockIdx.x; g < total; g += gridDim.x) {
-    int lo = 0, hi = n - 1;                        // last tensor whose first tile is <= g
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (pre[mid] <= g) lo = mid; else hi = mid - 1;
-    }
-    const tgan_pack_desc d = descs[lo];
-    const int tile = g - pre[lo];
-    const int nbk = (d.Kpad + 31) / 32, nbn = (d.Nr + 31) / 32;
-    bf16* dst = reinterpret_cast<bf16*>(d.dst);
-    const bool transpose = d.sk != 1 && d.sn == 1;
+  const bool transpose = d.sk != 1 && d.sn == 1;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int kb = tile % nbk, nb = (tile / nbk) % nbn, t = tile / (nbk * nbn);
     const int64_t base = (int64_t)(d.taps ? d.taps[t] : t) * d.st;
     if (transpose) {
@@ -205,10 +185,7 @@ extern "C" int tgan_weightnorm_bwd_multi(const tgan_wn_desc* descs_dev, int n, i
 }
 extern "C" int tgan_pack_weight_multi(const tgan_pack_desc* descs_dev, int n, void* stream) {
   TGAN_CHECK_ARG(descs_dev && n > 0, "pack_weight_multi: bad args");
-  for (int i = 0; i < n; i += PACK_MAX_DESCS) {
-    const int m = n - i < PACK_MAX_DESCS ? n - i : PACK_MAX_DESCS;
-    pdl_launch(pack_multi_kernel, 148 * 8, 256, 0, (cudaStream_t)stream, descs_dev + i, m);
-    TGAN_LAUNCHED();
-  }
+  pdl_launch(pack_multi_kernel, dim3(148 * 4, n), 256, 0, (cudaStream_t)((cudaStream_t)stream), descs_dev);
+  TGAN_LAUNCHED();
   return 0;
 }

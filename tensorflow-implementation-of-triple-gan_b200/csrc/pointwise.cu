@@ -830,6 +830,50 @@ __global__ void dropout_concat_kernel(const TX* __restrict__ x, TY* __restrict__
     stf<TY>(y, r * ldy + C + j, j < K ? lab[(r / rps) * K + j] : 0.f);
   }
 }
+// narrow rows (the discriminator's input: 3 image channels + 10 label planes in a 16-channel bf16 row): one thread = one
+// output row, written with 16-byte stores; same Philox stream / element mapping as dropout_concat_kernel.
+template <typename TX>
+__global__ void dropout_concat_narrow_kernel(const TX* __restrict__ x, bf16* __restrict__ y, uint8_t* __restrict__ mask,
+                                             int64_t rows, int C, int ldy, float rate, float scale, int gen, uint64_t seed,
+                                             uint64_t stream_id, const uint64_t* __restrict__ counter,
+                                             const float* __restrict__ lab, int K, int rps) {
+  pdl_entry();
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const uint64_t ctr = (gen && counter) ? *counter : 0;
+  const int64_t e0 = r * C;
+  const float* l = lab + (r / rps) * K;
+  int64_t gcur = -1;
+  uint4 rnd = make_uint4(0, 0, 0, 0);
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    v[j] = 0.f;
+    if (j < C) {
+      const int64_t e = e0 + j;
+      uint8_t k;
+      if (gen) {
+        const int64_t g = e >> 2;
+        if (g != gcur) { rnd = Philox(seed)((uint64_t)g, stream_id + (ctr << 20)); gcur = g; }
+        const int q = (int)(e & 3);
+        const uint32_t w = q == 0 ? rnd.x : (q == 1 ? rnd.y : (q == 2 ? rnd.z : rnd.w));
+        k = u32_to_unit(w) >= rate;
+        mask[e] = k;
+      } else {
+        k = mask[e];
+      }
+      v[j] = k ? ldf<TX>(x, e) * scale : 0.f;
+    } else if (j - C < K && j < ldy) {
+      v[j] = l[j - C];
+    }
+  }
+  float lo[8], hi[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
+  st8(y, r * ldy, lo);
+  if (ldy > 8) st8(y, r * ldy + 8, hi);
+}
+
 template <typename TX, typename TY>
 __global__ void affine_concat_kernel(const TX* __restrict__ x, TY* __restrict__ y, int C, int ldy,
                                      const float* __restrict__ scale, const float* __restrict__ shift,
@@ -1285,6 +1329,13 @@ extern "C" int tgan_dropout_concat(const void* x, int xdt, void* y, int ydt, int
   TGAN_CHECK_ARG(x && y && mask && lab && rows > 0 && ldy >= C + K && rate >= 0.f && rate < 1.f && rows_per_sample > 0,
                  "dropout_concat: bad args");
   const int64_t n = rows * C, ngroups = (n + 3) / 4, total = ngroups + rows * (ldy - C);
+  if (ydt == TGAN_BF16 && (ldy == 8 || ldy == 16) && C <= 8 && aligned16(y)) {
+    TGAN_DISPATCH_1(xdt, TX, (pdl_launch(dropout_concat_narrow_kernel<TX>, ceil_div(rows, 256), 256, 0, (cudaStream_t)stream,
+                                         (const TX*)x, (bf16*)y, mask, rows, C, ldy, rate, 1.0f / (1.0f - rate), gen, seed, stream_id,
+                                         counter, lab, K, rows_per_sample)));
+    TGAN_LAUNCHED();
+    return 0;
+  }
   DISPATCH_2(xdt, TX, ydt, TY, (pdl_launch(dropout_concat_kernel<TX, TY>, ceil_div(total, 256), 256, 0, (cudaStream_t)stream,
                                            (const TX*)x, (TY*)y, mask, n, C, ldy, rate, 1.0f / (1.0f - rate), gen, seed,
                                            stream_id, counter, lab, K, rows_per_sample, ngroups, total)));
