@@ -6,7 +6,7 @@ surface (Model/nn.py, Model/modle_base.py, Model/Good_GAN*.py, Training/Train_go
     tr = tgan.make_trainer('cifar10')                 # builds the graph, initialises variables
     losses = tr.step(batch)                           # device tensor [d_loss, g_loss, c_loss]
 """
-from . import checkpoint, config, core, ddp, nn, ops, pipeline, synthetic  # noqa: F401
+from . import checkpoint, config, core, ddp, nn, ops, pipeline, synthetic, tfrecord  # noqa: F401
 from .checkpoint import Saver  # noqa: F401
 from .config import Config, make_config  # noqa: F401
 from .core import InjectedSource, PhiloxSource, building, ctx, init, no_grad, recording  # noqa: F401
