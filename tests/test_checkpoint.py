@@ -182,3 +182,15 @@ def test_saver_paths(tmp_path):
     assert (d, f, e) == (run, os.path.join(run, 'model_0020.ckpt'), 20)
     d, f, e = ck.Saver(str(tmp_path))._findfilename(dir_names=os.path.basename(run), epoch=10)
     assert (f, e) == (os.path.join(run, 'model_0010.ckpt'), 10)
+
+
+def test_reader_on_committed_fixture():
+    """tests/golden/fmt_ckpt.*: written by the independent encoder of oracle/gen_format_fixtures.py"""
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    want = np.load(os.path.join(g, 'fmt_expected.npz'))
+    r = ck.BundleReader(os.path.join(g, 'fmt_ckpt'))
+    assert r.keys() == ['Train/beta1_power', 'classifier/conv1_1/V', 'classifier/conv1_1/V/Adam_optimizer']
+    for k in r.keys():
+        a = r.get(k)
+        assert a.dtype == np.float32 and np.array_equal(a, want[k.replace('/', '.')]) and a.shape == want[k.replace('/', '.')].shape
+    assert r.get('Train/beta1_power').shape == () and r.num_shards == 1

@@ -100,3 +100,15 @@ def test_corruption_and_bad_files(tmp_path):
     open(p, 'wb').write(b'')
     with pytest.raises(ValueError, match='no records'):
         tr.load_image_records(p, 3)
+
+
+def test_reader_on_committed_fixture(tmp_path):
+    """tests/golden/fmt_records.tfrecords: written by the independent encoder of oracle/gen_format_fixtures.py; the product
+    writer reproduces the file byte for byte"""
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    want = np.load(os.path.join(g, 'fmt_expected.npz'))
+    im, lb = tr.load_image_records(os.path.join(g, 'fmt_records.tfrecords'), 3)
+    assert np.array_equal(im, want['images']) and np.array_equal(lb, want['labels'])
+    p = str(tmp_path / 'w.tfrecords')
+    tr.write_image_records(p, want['images'], want['labels'])
+    assert open(p, 'rb').read() == open(os.path.join(g, 'fmt_records.tfrecords'), 'rb').read()
