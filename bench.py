@@ -116,8 +116,8 @@ def run_reference(args, rank):
         'impl': 'reference', 'metric': 'CIFAR-10 Triple-GAN train images/sec', 'value': v, 'unit': 'images/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': t * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'CIFAR-10 32x32x3 Triple-GAN (Good_GAN_cifar10) training step, batch 100 per GPU',
-                   'sample': sample},
+        'config': {'workload': WORKLOADS['cifar10'], 'global_batch': IMAGES_PER_STEP * max(1, args.gpus),
+                   'parallelism': 'dp%d' % max(1, args.gpus), 'sample': sample},
         'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': os.cpu_count(), 'kind': 'port', 'sample': sample},
         'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
 
