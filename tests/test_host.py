@@ -137,3 +137,30 @@ def test_train_epoch_uses_schedule_and_pretrain_phase():
     c = tr.config
     assert calls[0]['lambda_1'] == c.FAKE_G_LAMBDA and calls[0]['lambda_2'] == 0.5
     assert abs(calls[0]['lr'] - c.LEARNING_RATE * 0.995 ** 2) < 1e-12 and abs(calls[0]['cla_lr'] - c.CLA_LEARNINIG_RATE * 0.99 ** 2) < 1e-12
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference's CPU path = the float32 oracle port, timed on the host cores): one JSON
+    line with the GPU arm's metric / unit / config plus impl, cpu_baseline and a zero-copy e2e block; other ranks print
+    nothing and exit 0."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RANK='0', WORLD_SIZE='1')
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1'],
+                         capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    j = json.loads(out.stdout.strip().splitlines()[-1])
+    assert j['impl'] == 'reference' and j['metric'] == 'CIFAR-10 Triple-GAN train images/sec' and j['unit'] == 'images/s'
+    assert j['higher_is_better'] is True and j['value'] > 0 and j['steps'] == 1
+    assert j['config']['workload'].startswith('CIFAR-10 32x32x3 Triple-GAN') and 'sample' in j['config']
+    assert j['cpu_baseline']['kind'] == 'port' and j['cpu_baseline']['cores'] == os.cpu_count()
+    assert j['cpu_baseline']['value'] == j['value']
+    assert j['e2e'] == {'value': j['value'], 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    env['RANK'] = '1'
+    env['WORLD_SIZE'] = '2'
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--gpus', '2', '--steps', '1',
+                          '--warmup', '1'], capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert out.returncode == 0 and out.stdout.strip() == ''
