@@ -84,42 +84,56 @@ class ClockSampler:
                     reasons=sorted(reasons), samples=len(sm))
 
 
-def cpu_step_time(scale, steps, warmup):
+LAMBDAS = {'cifar10': (0.3, 0.5), 'svhn': (0.03, 0.0), 'mnist': (0.1, 0.0)}     # FAKE_G_LAMBDA of each main; lambda_2 is cifar-only
+
+
+def cpu_step_time(workload, scale, steps, warmup):
     """the reference's CPU path: float32 torch-CPU restatement of the identical three-phase step (TensorFlow is
-    not installable in this image), all host threads."""
+    not installable in this image), all host threads.  -> (mean seconds per step, images per step, threads)"""
     import torch
     from oracle import tgan_oracle as O
     torch.set_num_threads(os.cpu_count())
-    P, S = O.init_params('cifar10', seed=1234)
-    tr = O.OracleTrainer('cifar10', P, S, O.make_zca(1234), dtype=torch.float32, scale=scale)
+    P, S = O.init_params(workload, seed=1234)
+    tr = O.OracleTrainer(workload, P, S, O.make_zca(1234) if workload == 'cifar10' else None, dtype=torch.float32, scale=scale)
     batch = O.make_batch(tr.cfg, seed=1234)
     rng = O.TagRNG(0)
+    l1, l2 = LAMBDAS[workload]
     for _ in range(warmup):
-        tr.step(batch, rng, 0.3, 0.5)
+        tr.step(batch, rng, l1, l2)
     ts = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        tr.step(batch, rng, 0.3, 0.5)
+        tr.step(batch, rng, l1, l2)
         ts.append(time.perf_counter() - t0)
-    return sum(ts) / len(ts), tr.cfg.BATCH_SIZE
+    return sum(ts) / len(ts), tr.cfg.BATCH_SIZE, torch.get_num_threads()
+
+
+def metric_name(wl):
+    return ('CIFAR-10' if wl == 'cifar10' else wl.upper()) + ' Triple-GAN train images/sec'
 
 
 def run_reference(args, rank):
+    """The reference arm: the reference's own CPU implementation of the path.  TensorFlow 1.x cannot be installed in
+    this image, so this is the oracle's float32 restatement of the same graph on all host threads, at
+    the FULL batch tuple of the workload (scale 1: the same 100 images per step the GPU arm processes per rank).
+    Under torchrun only rank 0 works; the other ranks exit."""
     if rank != 0:
         return
-    scale = 4                       # bounded sample: 25 images per step (G 25, L_C 12, U_C 12, L_D 5, U_D 20)
-    t, imgs = cpu_step_time(scale, args.steps, max(1, min(args.warmup, 2)))
+    wl = args.workload
+    t, imgs, threads = cpu_step_time(wl, 1, args.steps, max(1, min(args.warmup, 2)))
     v = imgs / t
-    sample = 'CIFAR-10 Triple-GAN step at 1/%d of the batch tuple (%d images/step), float32 torch-CPU restatement ' \
-             'of the TF graph (TensorFlow not installable here)' % (scale, imgs)
+    n = max(1, args.gpus)
+    sample = '%s: the full per-rank batch tuple (%d images/step), %d timed steps, float32 torch-CPU restatement of the ' \
+             'TF graph (TensorFlow not installable here), one process on %d host threads' % (WORKLOADS[wl], imgs, args.steps, threads)
+    if n > 1:
+        sample += '; the global batch of %d images is %d such steps on the same host cores, so images/s is unchanged' % (imgs * n, n)
     print(json.dumps({
-        'impl': 'reference', 'metric': 'CIFAR-10 Triple-GAN train images/sec', 'value': v, 'unit': 'images/s',
-        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': t * 1e3,
+        'impl': 'reference', 'metric': metric_name(wl), 'value': v, 'unit': 'images/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': t * 1e3 * n,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOADS['cifar10'], 'global_batch': IMAGES_PER_STEP * max(1, args.gpus),
-                   'parallelism': 'dp%d' % max(1, args.gpus), 'sample': sample},
-        'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': os.cpu_count(), 'kind': 'port', 'sample': sample},
-        'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+        'config': {'workload': WORKLOADS[wl], 'global_batch': IMAGES_PER_STEP * n, 'parallelism': 'dp%d' % n},
+        'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': threads, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}), flush=True)
 
 
 def dominant_kernel_roofline(torch, tgan, pk):
@@ -193,6 +207,10 @@ def main():
     if args.impl == 'reference':
         run_reference(args, rank)
         return
+    dbg = {k: v for k, v in os.environ.items() if k.startswith('TGAN_')}
+    if 'TGAN_IGEMM_DBG' in dbg:
+        raise SystemExit('bench.py: TGAN_IGEMM_DBG is set -- refusing to time a kernel with debug switches (they exist only '
+                         'in builds made with -DTGAN_DEBUG_SWITCHES)')
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -215,11 +233,13 @@ def main():
         try:
             tr.capture(warmup=3)
             graph = True
-        except Exception as e:            # e.g. NCCL capture unsupported: run the same launches eagerly
+        except Exception as e:
+            if world > 1:                 # a silent eager fallback on some ranks would desynchronise the collectives
+                raise
             tr.graph = None
             torch.cuda.synchronize()
-            if rank == 0:
-                print('graph capture failed (%s); running eager' % str(e)[:200], file=sys.stderr)
+            print('graph capture failed (%s); running the same launches eagerly (config.cuda_graph = false)'
+                  % str(e)[:200], file=sys.stderr)
 
     def barrier():
         torch.cuda.synchronize()
@@ -299,12 +319,12 @@ def main():
     imgs = IMAGES_PER_STEP * world * args.steps
     value = imgs / t_dev
     out = {
-        'metric': ('CIFAR-10' if wl == 'cifar10' else wl.upper()) + ' Triple-GAN train images/sec', 'value': value, 'unit': 'images/s', 'n_gpus': world,
+        'metric': metric_name(wl), 'value': value, 'unit': 'images/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': t_dev / args.steps * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16' if args.math == 'bf16' else 'f32', 'data': 'synthetic',
         'config': {'workload': WORKLOADS[wl],
                    'global_batch': IMAGES_PER_STEP * world, 'parallelism': 'dp%d' % world,
-                   'cuda_graph': graph,
+                   'cuda_graph': graph, 'debug_env': dbg,
                    'l2': 'no explicit flush: one step streams > 1 GB of activations (>> 126 MB L2) between reuses'},
         'e2e': {'value': imgs / t_e2e, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 12,
                 'ms_per_step': t_e2e / args.steps * 1e3},
@@ -318,11 +338,11 @@ def main():
     }
     if args.math == 'bf16':
         out['roofline'] = dominant_kernel_roofline(torch, tgan, pk)
-    if world == 1 and not args.no_cpu_baseline and wl == 'cifar10':
-        t, n = cpu_step_time(4, 2, 1)
-        out['cpu_baseline'] = {'value': n / t, 'unit': 'images/s', 'cores': os.cpu_count(), 'kind': 'port',
-                               'sample': 'CIFAR-10 step at 1/4 of the batch tuple (%d images/step), 2 timed steps, '
-                                         'float32 torch-CPU restatement of the TF graph' % n}
+    if world == 1 and not args.no_cpu_baseline:
+        t, n, threads = cpu_step_time(wl, 1, 4, 1)
+        out['cpu_baseline'] = {'value': n / t, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
+                               'sample': '%s step at the full batch tuple (%d images/step), 4 timed steps after 1 warm-up, '
+                                         'float32 torch-CPU restatement of the TF graph' % (wl, n)}
     print(json.dumps(out), flush=True)
     _finish(world, dist, torch)
 

@@ -203,10 +203,11 @@ int tgan_sub_channel_mean_seg(const void* du, void* dz, int64_t rows, int C, int
 
 /* tf.contrib.layers.batch_norm training statistics (modle_base.py:229-237):
  *   mean, rstd = rsqrt(var_biased + eps); scale = gamma*rstd; shift = beta - mean*scale;
- *   moving_mean/variance <- decay-EMA (variance uses the unbiased estimate). */
+ *   moving_mean/variance <- decay-EMA; unbiased_moving_var = 1: the variance fed to the EMA is the unbiased estimate
+ *   (contrib's fused path), 0: the biased tf.nn.moments variance (nn.batch_norm_impl, nn.py:207-214). */
 int tgan_bn_finalize(const float* sum, const float* sumsq, int64_t rows, int C, const float* gamma,
-                     const float* beta, float eps, float decay, float* moving_mean, float* moving_var,
-                     float* mean, float* rstd, float* scale, float* shift, void* stream);
+                     const float* beta, float eps, float decay, int unbiased_moving_var, float* moving_mean,
+                     float* moving_var, float* mean, float* rstd, float* scale, float* shift, void* stream);
 int tgan_bn_eval_affine(const float* gamma, const float* beta, const float* moving_mean,
                         const float* moving_var, float eps, int C, float* scale, float* shift, void* stream);
 

@@ -95,13 +95,14 @@ def max_pool(x, k, s, padding):
 
 
 def argmax_onehot(logits, depth):
-    """tf.argmax(axis=1) -> int64, lowest index wins ties; tf.one_hot(depth)."""
+    """tf.argmax(axis=1) -> int64 + tf.one_hot(depth), as Eigen's ArgMaxTupleReducer computes it: accumulator
+    (0, -FLT_MAX), replaced only by a strictly greater element -> lowest index wins ties, NaN never wins."""
     idx = np.zeros(logits.shape[0], dtype=np.int64)
     for n in range(logits.shape[0]):
-        best = 0
-        for k in range(1, logits.shape[1]):
-            if logits[n, k] > logits[n, best]:
-                best = k
+        best, m = 0, np.float32(-3.4028234663852886e38)
+        for k in range(logits.shape[1]):
+            if logits[n, k] > m:
+                best, m = k, logits[n, k]
         idx[n] = best
     oh = np.zeros((logits.shape[0], depth), dtype=np.float32)
     oh[np.arange(logits.shape[0]), idx] = 1.0

@@ -178,9 +178,17 @@ def softmax_ce(logits, labels):
 
 
 def argmax_onehot(logits, depth=10):
-    """tf.argmax(axis=1) (first max wins) + tf.one_hot (Good_GAN_cifar10.py:232,259)."""
-    idx = torch.argmax(logits.detach(), dim=1)
-    # torch.argmax returns the first maximal index on CPU; asserted in tests vs the numpy loop.
+    """tf.argmax(axis=1) + tf.one_hot (Good_GAN_cifar10.py:232,237,259,270).
+
+    tf.argmax reduces with Eigen's ArgMaxTupleReducer (TF 1.12-1.15): the accumulator starts at
+    (index 0, NumTraits<float>::lowest() = -FLT_MAX) and an element replaces it only if it is strictly GREATER.
+    Consequences restated here: the lowest index wins ties; a NaN never wins (NaN > x is false) and never blocks
+    a later number; a row of only NaN / -inf / -FLT_MAX yields index 0.  torch.argmax would return the NaN's
+    index, so NaN and -inf are mapped to -FLT_MAX first (torch.argmax on CPU returns the first maximal index;
+    checked against the loop restatement oracle/tf_semantics_np.py in tests/test_oracle.py)."""
+    lo = float(torch.finfo(torch.float32).min)
+    x = torch.nan_to_num(logits.detach().double(), nan=lo, neginf=lo).clamp_(min=lo)
+    idx = torch.argmax(x, dim=1)
     return idx, F.one_hot(idx, depth).to(logits.dtype)
 
 
@@ -287,6 +295,67 @@ def WN_deconv2d(P, scope, x, stride=2):
             + b.view(1, 1, 1, -1)
     y = conv2d_transpose_tf(x, l2_normalize(V, (0, 1, 3)), stride, 'SAME')
     return g.view(1, 1, 1, -1) * y + b.view(1, 1, 1, -1)
+
+
+def batch_norm_impl(P, S, scope, x, train, conv=True, decay=0.9):
+    """nn.batch_norm_impl (nn.py:192-217): tf.nn.batch_normalization with eps 1e-3, own scale / beta; the
+    population statistics follow the BIASED batch variance of tf.nn.moments (:207-214)."""
+    n = scope + '/BatchNormalization'
+    scale, beta = P[n + '/scale'], P[n + '/beta']
+    if train:
+        axes = (0, 1, 2) if conv else (0,)
+        mu = x.mean(dim=axes)
+        var = ((x - mu) ** 2).mean(dim=axes)
+        S[n + '/pop_mean'] = S[n + '/pop_mean'] * decay + mu.detach() * (1 - decay)
+        S[n + '/pop_var'] = S[n + '/pop_var'] * decay + var.detach() * (1 - decay)
+    else:
+        mu, var = S[n + '/pop_mean'], S[n + '/pop_var']
+    return qc((x - mu) * torch.rsqrt(var + 0.001) * scale + beta)
+
+
+def _salimans_init(z, axes, init_scale, eps, nonlin):
+    """the data-dependent branch shared by nn.dense / conv2d / deconv2d (nn.py:229-238, 264-274, 306-316):
+    x_init = init_scale / sqrt(var + eps) * (x_init - mean), then the nonlinearity."""
+    m = z.mean(dim=axes)
+    v = ((z - m) ** 2).mean(dim=axes)
+    y = (init_scale / torch.sqrt(v + eps)) * (z - m)
+    return qc(nonlin(y) if nonlin is not None else y)
+
+
+def salimans_dense(P, scope, x, nonlin=None, init=False, init_scale=1.0):
+    """nn.dense (nn.py:220-252).  init=True: x @ l2_normalize(V,[0]), data-normalised (eps 1e-10); else
+    (x @ V) * g / sqrt(sum V^2) + b (no epsilon)."""
+    V, g, b = P[scope + '/V'], P[scope + '/g'], P[scope + '/b']
+    if init:
+        return _salimans_init(matmul_tf(x, l2_normalize(V, (0,))), (0,), init_scale, 1e-10, nonlin)
+    sc = g / torch.sqrt((V * V).sum(dim=0))
+    y = (matmul_tf(x, V * sc.view(1, -1)) if _QUANT else sc.view(1, -1) * (x @ V)) + b.view(1, -1)
+    return qc(nonlin(y) if nonlin is not None else y)
+
+
+def salimans_conv2d(P, scope, x, stride=1, pad='SAME', nonlin=None, init=False, init_scale=1.0):
+    """nn.conv2d (nn.py:255-289)."""
+    V, g, b = P[scope + '/V'], P[scope + '/g'], P[scope + '/b']
+    if init:
+        return _salimans_init(conv2d_tf(x, l2_normalize(V, (0, 1, 2)), stride, pad), (0, 1, 2), init_scale, 1e-8, nonlin)
+    y = conv2d_tf(x, g.view(1, 1, 1, -1) * l2_normalize(V, (0, 1, 2)), stride, pad) + b
+    return qc(nonlin(y) if nonlin is not None else y)
+
+
+def salimans_deconv2d(P, scope, x, stride=1, nonlin=None, init=False, init_scale=1.0):
+    """nn.deconv2d, pad='SAME' (nn.py:292-332); V is [kh,kw,Cout,Cin], normalised over axes [0,1,3]."""
+    V, g, b = P[scope + '/V'], P[scope + '/g'], P[scope + '/b']
+    if init:
+        return _salimans_init(conv2d_transpose_tf(x, l2_normalize(V, (0, 1, 3)), stride, 'SAME'), (0, 1, 2), init_scale,
+                              1e-8, nonlin)
+    y = conv2d_transpose_tf(x, g.view(1, 1, -1, 1) * l2_normalize(V, (0, 1, 3)), stride, 'SAME') + b
+    return qc(nonlin(y) if nonlin is not None else y)
+
+
+def salimans_nin(P, scope, x, **kw):
+    """nn.nin (nn.py:335-340): reshape -> dense -> reshape."""
+    s = x.shape
+    return salimans_dense(P, scope, x.reshape(-1, s[-1]), **kw).reshape(s[0], s[1], s[2], -1)
 
 
 # --------------------------------------------------------------------------------------
@@ -719,25 +788,49 @@ class OracleTrainer:
         self.last_grads = {}
         self.last_aux = {}
 
+    def _pseudo(self, key, logits):
+        idx, oh = argmax_onehot(logits)
+        forced = getattr(self, '_labels', {}).get(key)
+        if forced is not None:
+            idx = torch.as_tensor(np.asarray(forced), dtype=torch.int64)
+            oh = F.one_hot(idx, logits.shape[1]).to(logits.dtype)
+        return idx, oh
+
     def _grads(self, loss, names):
         gs = torch.autograd.grad(loss, [self.P[n] for n in names], allow_unused=True)
         return {n: (g if g is not None else torch.zeros_like(self.P[n])) for n, g in zip(names, gs)}
 
-    def step(self, batch, rng, lambda_1, lambda_2=0.0, lr=None, cla_lr=None, train=True, update=True, phases='DGC'):
+    def step(self, batch, rng, lambda_1, lambda_2=0.0, lr=None, cla_lr=None, train=True, update=True, phases='DGC',
+             labels=None):
+        """labels (optional): {'idx_unl_d', 'idx_unl', 'idx_unl_c'} int arrays that REPLACE the three pseudo-label
+        argmaxes (Good_GAN_cifar10.py:232,237 in phase D, :232 again in phase C).  Used by the reduced-precision
+        parity tests: the run under test supplies its own labels so gradients are compared on identical discrete
+        routing; the labels themselves are checked separately wherever the top-2 margin exceeds the noise."""
         cfg, m = self.cfg, self.model
+        self._labels = labels or {}
         lr = cfg.LEARNING_RATE if lr is None else lr
         cla_lr = cfg.CLA_LEARNINIG_RATE if cla_lr is None else cla_lr
         b = {k: torch.as_tensor(v).to(self.dtype) for k, v in batch.items()}
         cif = cfg.DATA_NAME == 'cifar10'
         pre = m.zca_apply if cif else (lambda t: t)
         if phases == 'C':      # PRE_TRAIN iteration (Train_goodGAN.py:182-224): only sess.run([c_solver, c_loss])
+            self._labels = labels or {}
             return self._phase_c(b, rng, lambda_1, lambda_2, cla_lr, train, update)
-        # ---- phase D (Train_goodGAN.py:267) ----
+        d_loss, gd = self.phase_d(b, rng, lr, train, update)
+        g_loss, gg = self.phase_g(b, rng, lr, update)
+        _, _, c_loss_v = self._phase_c(b, rng, lambda_1, lambda_2, cla_lr, train, update)
+        self.last_grads = {'D': gd, 'G': gg, 'C': self.last_grads['C']}
+        return d_loss, g_loss, c_loss_v
+
+    def phase_d(self, b, rng, lr, train=True, update=True):
+        """sess.run([d_solver, d_loss]) (Train_goodGAN.py:267) -> (d_loss, {name: grad}); b: dict of tensors"""
+        m = self.model
+        pre = m.zca_apply if self.cfg.DATA_NAME == 'cifar10' else (lambda t: t)
         with torch.no_grad():
             c_unl_d, _ = m.classifier(pre(b['x_u_d']), train, rng, 'D/C_unl_d')
             c_unl, _ = m.classifier(pre(b['x_u_c']), train, rng, 'D/C_unl')
-            idx_d, oh_d = argmax_onehot(c_unl_d)
-            idx_u, oh_u = argmax_onehot(c_unl)
+            idx_d, oh_d = self._pseudo('idx_unl_d', c_unl_d)
+            idx_u, oh_u = self._pseudo('idx_unl', c_unl)
             G = m.good_generator(b['z_g'], b['y_g'], rng, 'D/G')
         X_P, Y_P = torch.cat([b['x_l_d'], b['x_u_d']], 0), torch.cat([b['y_l_d'], oh_d], 0)
         _, dr = m.discriminator(X_P, Y_P, rng, 'D/D_real')
@@ -748,16 +841,28 @@ class OracleTrainer:
         self.last_aux['D'] = dict(idx_unl_d=idx_d, idx_unl=idx_u, G=G, c_unl_d=c_unl_d, c_unl=c_unl, logits=(dr.detach(), df.detach(), du.detach()))
         if update:
             self.opt_d.apply(self.P, gd, lr)
-        # ---- phase G (:270) ----
+        return float(d_loss.detach()), gd
+
+    def phase_g(self, b, rng, lr, update=True):
+        """sess.run([g_solver, g_loss]) (Train_goodGAN.py:270)"""
+        m = self.model
         G = m.good_generator(b['z_g'], b['y_g'], rng, 'G/G')
         _, df = m.discriminator(G, b['y_g'], rng, 'G/D_fake')
         g_loss = g_loss_fn(df)
         gg = self._grads(g_loss, self.g_vars)
         if update:
             self.opt_g.apply(self.P, gg, lr)
-        _, _, c_loss_v = self._phase_c(b, rng, lambda_1, lambda_2, cla_lr, train, update)
-        self.last_grads = {'D': gd, 'G': gg, 'C': self.last_grads['C']}
-        return float(d_loss.detach()), float(g_loss.detach()), c_loss_v
+        return float(g_loss.detach()), gg
+
+    def apply_c(self, gc, cla_lr):
+        """c_solver: Adam on c_vars, then ema.apply(c_vars) (Train_goodGAN.py:101-103)"""
+        self.opt_c.apply(self.P, gc, cla_lr)
+        with torch.no_grad():
+            for k in self.c_vars:
+                self.ema[k] -= (self.ema[k] - self.P[k]) * (1 - 0.9999)
+
+    def tensors(self, batch):
+        return {k: torch.as_tensor(v).to(self.dtype) for k, v in batch.items()}
 
     def _phase_c(self, b, rng, lambda_1, lambda_2, cla_lr, train, update):
         cfg, m = self.cfg, self.model
@@ -769,18 +874,15 @@ class OracleTrainer:
         c_rep = m.classifier(pre(b['x_u_c']), train, rng, 'C/C_unl_rep')[0] if cif else None
         with torch.no_grad():
             G = m.good_generator(b['z_g'], b['y_g'], rng, 'C/G')
-            _, oh_u = argmax_onehot(c_unl)
+            idx_c, oh_u = self._pseudo('idx_unl_c', c_unl)
             _, du = m.discriminator(b['x_u_c'], oh_u, rng, 'C/D_unl')
         c_fake, _ = m.classifier(pre(G), train, rng, 'C/C_fake')
         c_loss = c_loss_fn(c_real, c_unl, c_fake, du, b['y_l_c'], b['y_g'], lambda_1, c_rep, lambda_2)
         gc = self._grads(c_loss, self.c_vars)
         self.last_aux['C'] = dict(logits=(c_real.detach(), c_unl.detach(), c_fake.detach(),
-                                          None if c_rep is None else c_rep.detach()), d_unl=du)
+                                          None if c_rep is None else c_rep.detach()), d_unl=du, idx_unl_c=idx_c)
         if update:
-            self.opt_c.apply(self.P, gc, cla_lr)
-            with torch.no_grad():       # ema.apply(c_vars) after c_solver_ (:101-103)
-                for k in self.c_vars:
-                    self.ema[k] -= (self.ema[k] - self.P[k]) * (1 - 0.9999)
+            self.apply_c(gc, cla_lr)
         self.last_grads = dict(self.last_grads, C=gc)
         return None, None, float(c_loss.detach())
 

@@ -19,6 +19,14 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 
+// Floor-measurement switches (skip loads / stores / the epilogue) exist only in builds made with
+// -DTGAN_DEBUG_SWITCHES; in the release library the branches are compiled out and TGAN_IGEMM_DBG is never read.
+#ifdef TGAN_DEBUG_SWITCHES
+#define TGAN_DBG(bit) (p.dbg & (bit))
+#else
+#define TGAN_DBG(bit) 0
+#endif
+
 namespace tgan {
 
 // ------------------------------------------------------------------------------------------------
@@ -255,16 +263,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         for (int c = 0; c < 3; ++c) {
           mbar_wait(&emptyA[sa], pa ^ 1);
           if (elect_one()) {
-            mbar_arrive_expect_tx(&fullA[sa], (p.dbg & 1) ? 0u : a_bytes);
-            if (!(p.dbg & 1)) tma_load_4d(smem + (size_t)sa * HALO_A_SLOT_BYTES, &tmXh, &fullA[sa], kc * 64, p.dx[c], y0, ng);
+            mbar_arrive_expect_tx(&fullA[sa], TGAN_DBG(1) ? 0u : a_bytes);
+            if (!TGAN_DBG(1)) tma_load_4d(smem + (size_t)sa * HALO_A_SLOT_BYTES, &tmXh, &fullA[sa], kc * 64, p.dx[c], y0, ng);
           }
           __syncwarp();
           if (++sa == HALO_A_SLOTS) { sa = 0; pa ^= 1; }
           for (int r = 0; r < 3; ++r) {
             mbar_wait(&emptyW[sw], pw ^ 1);
             if (elect_one()) {
-              mbar_arrive_expect_tx(&fullW[sw], (p.dbg & 2) ? 0u : (uint32_t)W_STAGE_BYTES);
-              if (!(p.dbg & 2)) tma_load_3d(wring + (size_t)sw * W_STAGE_BYTES, &tmW, &fullW[sw], kc * 64, ct * 128, r * 3 + c);
+              mbar_arrive_expect_tx(&fullW[sw], TGAN_DBG(2) ? 0u : (uint32_t)W_STAGE_BYTES);
+              if (!TGAN_DBG(2)) tma_load_3d(wring + (size_t)sw * W_STAGE_BYTES, &tmW, &fullW[sw], kc * 64, ct * 128, r * 3 + c);
             }
             __syncwarp();
             if (++sw == HALO_W_SLOTS) { sw = 0; pw ^= 1; }
@@ -334,14 +342,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       for (int t = tap0; t < tap1; ++t) {
         const int ddx = p.dx[t], ddy = p.dy[t];
         for (int kc = 0; kc < p.kchunks; ++kc) {
-          if (p.dbg & 16) continue;
+          if (TGAN_DBG(16)) continue;
           mbar_wait(&empty[stage], phase ^ 1);
           if (elect_one()) {
             uint8_t* s = smem + (size_t)stage * IG_STAGE_BYTES;
-            mbar_arrive_expect_tx(&full[stage], ((p.dbg & 2) ? 0u : (uint32_t)W_STAGE_BYTES) +
-                                                    ((p.dbg & 1) ? 0u : (uint32_t)p.nbox * P_TILE_BYTES));
-            if (!(p.dbg & 2)) tma_load_3d(s, &tmW, &full[stage], kc * 64, ct * 128, t);
-            if (!(p.dbg & 1)) {
+            mbar_arrive_expect_tx(&full[stage], (TGAN_DBG(2) ? 0u : (uint32_t)W_STAGE_BYTES) +
+                                                    (TGAN_DBG(1) ? 0u : (uint32_t)p.nbox * P_TILE_BYTES));
+            if (!TGAN_DBG(2)) tma_load_3d(s, &tmW, &full[stage], kc * 64, ct * 128, t);
+            if (!TGAN_DBG(1)) {
               tma_load_4d(s + W_STAGE_BYTES, &tmX, &full[stage], kc * 64, x0[0] + ddx, y0[0] + ddy, n0[0]);
               if (p.nbox == 2)
                 tma_load_4d(s + W_STAGE_BYTES + P_TILE_BYTES, &tmX, &full[stage], kc * 64, x0[1] + ddx, y0[1] + ddy, n0[1]);
@@ -365,7 +373,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * IG_NPIX);
       int kc = 0;
       for (int ks = 0; ks < ksteps; ++ks) {
-        if (!(p.dbg & 16)) mbar_wait(&full[stage], phase);
+        if (!TGAN_DBG(16)) mbar_wait(&full[stage], phase);
         tc_fence_after();
         const uint32_t a_lo = s_base + (uint32_t)stage * (IG_STAGE_BYTES >> 4);
         const uint32_t b_lo = a_lo + (W_STAGE_BYTES >> 4);
@@ -412,7 +420,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       tc_fence_after();
       for (int h = 0; h < p.nbox; ++h) {
         const int mt = p.nbox * pp + h;
-        if (mt >= p.m_tiles || (p.dbg & 8)) break;
+        if (mt >= p.m_tiles || TGAN_DBG(8)) break;
         int t2, tx, ty, ng;
         p.d_tiles_x.divmod(mt, t2, tx);
         p.d_tiles_y.divmod(t2, ng, ty);
@@ -472,7 +480,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             bf16* srow = reinterpret_cast<bf16*>(ostage) + (size_t)pbase * 128 + (q * 32 + lane);
 #pragma unroll
             for (int j = 0; j < 32; ++j) srow[j * 128] = __float2bfloat16_rn(v[j]);
-          } else if (!(p.dbg & 4)) {
+          } else if (!TGAN_DBG(4)) {
             float tmp[32], cs2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int j = 0; j < 32; ++j) tmp[j] = v[j];
@@ -484,7 +492,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         if (p.tstore) {
           fence_proxy_async();
           named_bar_sync(1, 256);
-          if (warp == 2 && lane == 0 && !(p.dbg & 4)) {
+          if (warp == 2 && lane == 0 && !TGAN_DBG(4)) {
             tma_store_4d(tmO, ostage, ct * 128, tx * p.tw, ty * p.th, ng * p.nb);
             bulk_commit();
           }
@@ -783,7 +791,11 @@ extern "C" int tgan_igemm_bf16(const tgan_igemm_args* a, void* stream) {
   p.out = a->out; p.odt = a->odt; p.OH = a->OH; p.OW = a->OW; p.ldo = a->ldo;
   p.osy = a->osy > 0 ? a->osy : 1; p.osx = a->osx > 0 ? a->osx : 1; p.ooy = a->ooy; p.oox = a->oox;
   p.vh = a->vh > 0 ? a->vh : a->gh; p.vw = a->vw > 0 ? a->vw : a->gw; p.Nout = a->Nout;
+#ifdef TGAN_DEBUG_SWITCHES
   { const char* e = getenv("TGAN_IGEMM_DBG"); p.dbg = e ? atoi(e) : 0; }
+#else
+  p.dbg = 0;
+#endif
   p.nseg = a->nseg > 1 ? a->nseg : 1;
   TGAN_CHECK_ARG(p.nseg <= 4, "igemm: at most 4 batch segments");
   for (int i = 0; i < 4; ++i) p.seg_end[i] = (a->nseg > 1 && i < a->nseg - 1) ? a->seg_end[i] : 0x7fffffff;

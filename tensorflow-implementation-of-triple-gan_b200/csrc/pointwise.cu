@@ -117,8 +117,8 @@ struct BnBwdStatsF {
 // finalize kernels (tiny, one thread per channel)
 // ------------------------------------------------------------------------------------------------
 __global__ void bn_finalize_kernel(const float* sum, const float* sumsq, float rows, int C, const float* gamma,
-                                   const float* beta, float eps, float decay, float* mm, float* mv, float* mean,
-                                   float* rstd, float* scale, float* shift) {
+                                   const float* beta, float eps, float decay, int unbiased, float* mm, float* mv,
+                                   float* mean, float* rstd, float* scale, float* shift) {
   pdl_entry();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -129,7 +129,9 @@ __global__ void bn_finalize_kernel(const float* sum, const float* sumsq, float r
   float sc = gamma[c] * rs;
   scale[c] = sc; shift[c] = beta[c] - mu * sc;
   if (mm) mm[c] = mm[c] * decay + mu * (1.f - decay);
-  if (mv) mv[c] = mv[c] * decay + var * (rows / fmaxf(rows - 1.f, 1.f)) * (1.f - decay);
+  // tf.contrib batch_norm (fused path) feeds the UNBIASED variance to the moving average; nn.batch_norm_impl
+  // (nn.py:207-214) feeds tf.nn.moments' biased one
+  if (mv) mv[c] = mv[c] * decay + var * (unbiased ? rows / fmaxf(rows - 1.f, 1.f) : 1.f) * (1.f - decay);
 }
 __global__ void bn_eval_kernel(const float* gamma, const float* beta, const float* mm, const float* mv, float eps,
                                int C, float* scale, float* shift) {
@@ -974,13 +976,14 @@ __global__ void argmax_onehot_kernel(const float* __restrict__ logits, int N, in
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const float* p = logits + (int64_t)n * K;
+  // tf.argmax = Eigen's ArgMaxTupleReducer: the accumulator starts at (0, -FLT_MAX) and is replaced only by a
+  // strictly GREATER element -> the lowest index wins ties, a NaN never wins and never blocks a later number,
+  // rows holding only NaN / -inf give index 0.
   int best = 0;
-  float m = p[0];
-  // strict '>' keeps the lowest index on ties; a NaN candidate never replaces a number, and a NaN
-  // incumbent is replaced by the first number that follows (NaN > x is false, so handle it explicitly).
-  for (int k = 1; k < K; ++k) {
+  float m = -3.402823466e+38f;
+  for (int k = 0; k < K; ++k) {
     float v = p[k];
-    if (v > m || (m != m && v == v)) { m = v; best = k; }
+    if (v > m) { m = v; best = k; }
   }
   if (idx) idx[n] = best;
   if (onehot)
@@ -1101,11 +1104,11 @@ extern "C" int tgan_sub_channel_mean_seg(const void* du, void* dz, int64_t rows,
 }
 
 extern "C" int tgan_bn_finalize(const float* sum, const float* sumsq, int64_t rows, int C, const float* gamma,
-                                const float* beta, float eps, float decay, float* moving_mean, float* moving_var,
-                                float* mean, float* rstd, float* scale, float* shift, void* stream) {
+                                const float* beta, float eps, float decay, int unbiased_moving_var, float* moving_mean,
+                                float* moving_var, float* mean, float* rstd, float* scale, float* shift, void* stream) {
   TGAN_CHECK_ARG(sum && sumsq && gamma && beta && mean && rstd && scale && shift, "bn_finalize: bad args");
   pdl_launch(bn_finalize_kernel, ceil_div(C, 128), 128, 0, (cudaStream_t)((cudaStream_t)stream), sum, sumsq, (float)rows, C, gamma, beta, eps,
-                                                                         decay, moving_mean, moving_var, mean, rstd,
+                                                                         decay, unbiased_moving_var, moving_mean, moving_var, mean, rstd,
                                                                          scale, shift);
   TGAN_LAUNCHED();
   return 0;

@@ -114,4 +114,8 @@ def make_config(data_name, scale=1, **over):
         setattr(cfg, k, getattr(cfg, k) // scale)
     for k, v in over.items():
         setattr(cfg, k, v)
+    # _main_training_svhn / _main_training_cifar10 (Train_goodGAN.py:537-538, 614-615): with fewer than 1000 labels
+    # the first 30 epochs train the classifier alone; the mnist main has the rule commented out (:692-693)
+    if data_name in ('svhn', 'cifar10') and cfg.NUM_LABEL < 1000 and 'PRE_TRAIN' not in over:
+        cfg.PRE_TRAIN = True
     return cfg

@@ -87,7 +87,8 @@ def batch_norm_impl(x, is_conv_out=True, deterministic=False, decay=0.9, name='B
         beta = get_variable('beta', [C], zeros_initializer(), trainable=True)
         pop_mean = get_variable('pop_mean', [C], zeros_initializer(), trainable=False)
         pop_var = get_variable('pop_var', [C], ones_initializer(), trainable=False)
-        return ops.batch_norm(x, scale, beta, pop_mean, pop_var, not deterministic, eps=0.001, decay=decay)
+        return ops.batch_norm(x, scale, beta, pop_mean, pop_var, not deterministic, eps=0.001, decay=decay,
+                              unbiased=False)
 
 
 # ---- Salimans & Kingma weight-normalised layers (nn.py:220-340) ----

@@ -720,8 +720,9 @@ def mobn_act(z, b, pop_mean, train, act='none', alpha=0.2, decay=0.9):
     return out
 
 
-def batch_norm(x, gamma, beta, mm, mv, train, eps=1e-5, decay=0.9):
-    """tf.contrib.layers.batch_norm(scale=True, updates_collections=None) (modle_base.py:229-237)."""
+def batch_norm(x, gamma, beta, mm, mv, train, eps=1e-5, decay=0.9, unbiased=True):
+    """tf.contrib.layers.batch_norm(scale=True, updates_collections=None) (modle_base.py:229-237); unbiased=False:
+    the moving variance follows the biased batch variance (nn.batch_norm_impl, nn.py:207-214)."""
     C, rows = x.C, x.rows
     rg = _on() and (x.requires_grad or gamma.requires_grad or beta.requires_grad)
     if ctx.building:
@@ -733,7 +734,7 @@ def batch_norm(x, gamma, beta, mm, mv, train, eps=1e-5, decay=0.9):
         s, ss = _new((C,), torch.float32), _new((C,), torch.float32)
         _lib.call('tgan_channel_stats', _p(xd), dt_code(xd), rows, C, _p(s), _p(ss), 0.0, _p(ctx.ws()), _st())
         _lib.call('tgan_bn_finalize', _p(s), _p(ss), rows, C, _p(gamma.data), _p(beta.data), eps, decay,
-                  None if mm is None else _p(mm.data), None if mv is None else _p(mv.data), _p(mean), _p(rstd), _p(scale), _p(shift), _st())
+                  1 if unbiased else 0, None if mm is None else _p(mm.data), None if mv is None else _p(mv.data), _p(mean), _p(rstd), _p(scale), _p(shift), _st())
     else:
         _lib.call('tgan_bn_eval_affine', _p(gamma.data), _p(beta.data), _p(mm.data), _p(mv.data), eps, C, _p(scale),
                   _p(shift), _st())

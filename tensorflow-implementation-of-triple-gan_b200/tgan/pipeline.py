@@ -64,49 +64,54 @@ class DeviceDataset:
 class TripleGANInput:
     """The step's inputs, formed on the device.  One instance per rank; `seed` should differ per rank (ddp.rank_seed)."""
 
-    def __init__(self, config, labelled, unlabelled, seed=1234):
+    def __init__(self, config, labelled, unlabelled, seed=1234, train_size=None):
         self.c, self.lab, self.unl = config, labelled, unlabelled
         self.seed = int(seed)
         self.gen = torch.Generator(device=labelled.images.device)
         self.gen.manual_seed(self.seed)
         self.counter = torch.zeros(1, dtype=torch.int64, device=labelled.images.device)   # Philox step counter for z / y_g
-        self._perm_l = self._perm_u = None
-        self._cl = self._cu = 0
+        # TRAIN_SIZE = number of unlabelled images (Train_goodGAN.py:523, 599, 677)
+        self.train_size = int(unlabelled.n if train_size is None else train_size)
+        # three independently shuffled, endlessly repeating streams (the reference builds separate tf.data pipelines
+        # for x_l_c, x_l_d and x_u, each shuffle -> repeat(-1) -> batch)
+        self._streams = {}
+        self._step = 0
         self.start_epoch()
 
     def _perm(self, n):
         return torch.randperm(n, device=self.lab.images.device, generator=self.gen)
 
     def start_epoch(self):
-        """init_op_train (Train_goodGAN.py:180): restart the unlabelled stream with a fresh shuffle."""
-        self._perm_u, self._cu = self._perm(self.unl.n), 0
-        if self._perm_l is None:
-            self._perm_l, self._cl = self._perm(self.lab.n), 0
+        """init_op_train (Train_goodGAN.py:180): re-initialise the iterators -> every stream restarts with a fresh shuffle."""
+        self._streams = {k: [self._perm(n), 0] for k, n in (('l_c', self.lab.n), ('l_d', self.lab.n), ('u', self.unl.n))}
+        self._step = 0
 
     def steps_per_epoch(self):
-        c = self.c
-        return self.unl.n // (c.BATCH_SIZE_U_D + c.BATCH_SIZE_U_C)
+        """int(TRAIN_SIZE / BATCH_SIZE) iterations (Train_goodGAN.py:230); the streams repeat, so the 130 unlabelled
+        images a CIFAR-10 iteration consumes wrap around within the epoch."""
+        return int(self.train_size / self.c.BATCH_SIZE)
 
-    def _take_l(self, n):
-        if n > self.lab.n:
-            raise ValueError('labelled set smaller than one batch')
-        if self._cl + n > self.lab.n:                    # repeat(-1): reshuffle and carry on
-            self._perm_l, self._cl = self._perm(self.lab.n), 0
-        idx = self._perm_l[self._cl:self._cl + n]
-        self._cl += n
+    def _take(self, key, n, total):
+        if n > total:
+            raise ValueError('dataset smaller than one batch')
+        st = self._streams[key]
+        if st[1] + n > total:                            # repeat(-1): reshuffle and carry on
+            st[0], st[1] = self._perm(total), 0
+        idx = st[0][st[1]:st[1] + n]
+        st[1] += n
         return idx
 
     def next_into(self, inputs):
         """Fill the eight step inputs (train.INPUT_NAMES) in place.  Raises StopIteration at the end of the epoch
-        (tf.errors.OutOfRangeError of the unlabelled iterator)."""
+        after int(TRAIN_SIZE / BATCH_SIZE) iterations (the range of Train_goodGAN.py:230)."""
         c = self.c
         nu = c.BATCH_SIZE_U_D + c.BATCH_SIZE_U_C
-        if self._cu + nu > self.unl.n:
+        if self._step >= self.steps_per_epoch():
             raise StopIteration
-        iu = self._perm_u[self._cu:self._cu + nu]
-        self._cu += nu
-        self.lab.gather(self._take_l(c.BATCH_SIZE_L_C), inputs['x_l_c'], inputs['y_l_c'])
-        self.lab.gather(self._take_l(c.BATCH_SIZE_L_D), inputs['x_l_d'], inputs['y_l_d'])
+        self._step += 1
+        iu = self._take('u', nu, self.unl.n)
+        self.lab.gather(self._take('l_c', c.BATCH_SIZE_L_C, self.lab.n), inputs['x_l_c'], inputs['y_l_c'])
+        self.lab.gather(self._take('l_d', c.BATCH_SIZE_L_D, self.lab.n), inputs['x_l_d'], inputs['y_l_d'])
         self.unl.gather(iu[:c.BATCH_SIZE_U_D], inputs['x_u_d'])                         # x_u[:U_D]        (:255)
         self.unl.gather(iu[c.BATCH_SIZE_U_D:], inputs['x_u_c'])                         # x_u[U_D:U_D+U_C] (:256)
         _lib.call('tgan_draw_latent', inputs['z_g'].data_ptr(), c.BATCH_SIZE_G, c.Z_DIM, inputs['y_g'].data_ptr(),
@@ -116,7 +121,7 @@ class TripleGANInput:
 
     def epoch(self, inputs):
         """Iterator for Train.train_epoch: yields None after filling `inputs` in place (Train.step(None) then runs on
-        the static buffers)."""
+        the static buffers): int(TRAIN_SIZE / BATCH_SIZE) iterations."""
         self.start_epoch()
         while True:
             try:

@@ -89,7 +89,6 @@ class Train(Train_base):
         self.g_optimizer = self._Adam_optimizer(lr=c.LEARNING_RATE, beta1=c.BETA1)
         self.c_optimizer = self._Adam_optimizer(lr=c.CLA_LEARNINIG_RATE, beta1=0.5)
         self.ema = ExponentialMovingAverage(decay=0.9999)
-        self.ema.bind(self.store.flat['classifier'])
         self.lambdas = torch.zeros(2, dtype=torch.float32, device=ctx.device)
         self._lam = (None, None)
         self.inputs = {k: torch.zeros(tuple(v), dtype=torch.float32, device=ctx.device)
@@ -106,6 +105,8 @@ class Train(Train_base):
             self.model._whitener()._upload()
         self.world = ddp.world_size()
         ddp.broadcast_params(self.store, 0, self.pg)
+        # the EMA shadow starts from the parameters every rank actually trains with (rank 0's after the broadcast)
+        self.ema.bind(self.store.flat['classifier'])
         return self
 
     def load_state(self, P=None, S=None, adam=None):
@@ -176,6 +177,7 @@ class Train(Train_base):
         d_loss = g_loss = None
         if phases == 'C':
             self.aux = {}
+            _lib.call('tgan_fill_f32', self.loss_buf.data_ptr(), 0.0, 2, ops._st())      # no d / g loss in a PRE_TRAIN iteration
         if 'D' in phases or 'G' in phases:
             # ---- phase D: sess.run([d_solver, d_loss]) (:267) ----
             ops.arena_reset()
@@ -230,7 +232,7 @@ class Train(Train_base):
                                      tag=TL([('C/C_real', nLC), ('C/C_unl', nUC), ('C/C_unl_rep', nUC), ('C/C_fake', nG)]))
                 c_unl_v = ops.Var(lg.data[nLC:nLC + nUC], (nUC, K))
                 with no_grad():
-                    _, oh_u = ops.argmax_onehot(c_unl_v, K)
+                    idx_c, oh_u = ops.argmax_onehot(c_unl_v, K)
                     _, du = m.discriminator(v['x_u_c'], oh_u, reuse=True, tag='C/D_unl')
                 c_loss = ops.loss_c_grouped(lg, segs, True, v['y_l_c'], du, v['y_g'], self.lambdas)
                 self.aux['c_logits'] = lg
@@ -239,11 +241,12 @@ class Train(Train_base):
                 c_unl, _ = m.classifier(pre(v['x_u_c']), train, reuse=True, tag='C/C_unl')
                 c_rep = m.classifier(pre(v['x_u_c']), train, reuse=True, tag='C/C_unl_rep')[0] if cif else None
                 with no_grad():
-                    _, oh_u = ops.argmax_onehot(c_unl, K)
+                    idx_c, oh_u = ops.argmax_onehot(c_unl, K)
                     _, du = m.discriminator(v['x_u_c'], oh_u, reuse=True, tag='C/D_unl')
                 c_fake, _ = m.classifier(pre(G), train, reuse=True, tag='C/C_fake')
                 c_loss = ops.loss_c(c_real, v['y_l_c'], c_unl, c_rep, du, c_fake, v['y_g'], self.lambdas)
                 self.aux['c_logits'] = (c_real, c_unl, c_fake, c_rep)
+            self.aux['idx_unl_c'] = idx_c
             ops.backward(c_loss)
         self._apply(fb, self.c_optimizer, self.ema, group='classifier')
         if not ctx.rng.injected:
@@ -277,11 +280,29 @@ class Train(Train_base):
             self._step_impl(train, phases)
         return self.loss_buf
 
+    def _snapshot(self):
+        """every tensor a training step mutates: parameters, Adam slots, population / moving statistics, the optimisers'
+        {lr, beta1^t, beta2^t} accumulators, the EMA shadow, the Philox step counter, the loss buffer"""
+        ts = [fb[k] for fb in self.store.flat.values() for k in ('theta', 'm', 'v') if k in fb]
+        ts += [o._state() for o in (self.d_optimizer, self.g_optimizer, self.c_optimizer)]
+        ts += [self.ema.shadow, self.loss_buf]
+        if not ctx.rng.injected:
+            ts.append(ctx.rng.counter())
+        return ts
+
     def capture(self, warmup=3):
         """Capture the whole three-phase step into one CUDA graph (the step is a few hundred small
-        launches, SURVEY.md §7 'Launch-bound regime').  Inputs are read from the static buffers."""
+        launches, SURVEY.md §7 'Launch-bound regime').  Inputs are read from the static buffers.
+
+        The `warmup` eager steps exist only to create every lazily allocated buffer and cache before the capture;
+        they are REAL training steps, so everything they mutate (parameters, Adam slots and beta powers, pop_mean /
+        BN moving statistics, EMA shadow, RNG counter) is saved before and restored after: capture() leaves the
+        training state -- a fresh initialisation or a restored checkpoint -- bitwise unchanged, whatever the static input
+        buffers hold at that moment (zeros before the first load_batch)."""
         assert not ctx.rng.injected, 'graph capture needs the in-kernel Philox RNG'
         ctx.store = self.store
+        live = self._snapshot()
+        saved = [t.clone() for t in live]
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -289,6 +310,11 @@ class Train(Train_base):
                 self._step_impl(True)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        if warmup:
+            for t, c in zip(live, saved):
+                t.copy_(c)
+            self.store.bump()                    # cached weight-norm scales / packed operands belong to the warm-up weights
+            torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         n0 = _lib.load().tgan_launch_count()
         with torch.cuda.graph(g):
@@ -341,12 +367,13 @@ class Train(Train_base):
         iteration otherwise.  `batches` yields dicts with the 8 step inputs; returns the mean (d, g, c) losses."""
         lam1, lam2, lr, cla_lr = self.schedule(epoch, start_epoch)
         pre = bool(getattr(self.config, 'PRE_TRAIN', False)) and (start_epoch + epoch <= 30)
-        tot, n = torch.zeros(3, dtype=torch.float64), 0
+        tot, n = None, 0
         for b in batches:
             out = self.step(b, lambda_1=lam1, lambda_2=lam2, lr=lr, cla_lr=cla_lr, phases='C' if pre else 'DGC')
-            tot += out.detach().double().cpu()
+            # epoch bookkeeping, accumulated where the losses live: no host synchronisation inside the epoch
+            tot = out.detach().double() if tot is None else tot + out.detach().double()
             n += 1
-        return (tot / max(n, 1)).tolist()
+        return [0.0, 0.0, 0.0] if tot is None else (tot.cpu() / n).tolist()
 
     # ------------------------------------------------------------------ schedules ------------------
     def schedule(self, epoch, start_epoch=0):

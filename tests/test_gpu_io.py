@@ -164,17 +164,23 @@ def test_input_stream_epoch_semantics():
             seen_l.append(np.concatenate([lc, ld]))
             zs.append(bufs['z_g'].cpu().numpy().copy())
             ys.append(bufs['y_g'].cpu().numpy().copy())
-        assert n == inp.steps_per_epoch() == Mu // 130
+        # the reference's epoch: int(TRAIN_SIZE / BATCH_SIZE) iterations (Train_goodGAN.py:230), TRAIN_SIZE = the
+        # number of unlabelled images; each iteration takes 130 of them, so the repeating stream wraps
+        assert n == inp.steps_per_epoch() == Mu // 100
         return np.concatenate(seen_u), np.concatenate(seen_l), np.stack(zs), np.stack(ys)
     su, sl, z, y = run(11)
-    assert len(np.unique(su)) == len(su) and su.max() < Mu                     # no repeats inside the epoch
-    assert sl.max() < Ml and len(np.unique(sl[:130])) > 100                    # labelled stream: shuffled, repeating
-    assert len(sl) == 7 * 70 and len(np.unique(sl)) >= Ml - 3
+    first = su[:7 * 130]                                                       # one pass over the shuffled stream
+    assert len(np.unique(first)) == len(first) and su.max() < Mu               # no repeats before the wrap-around
+    assert len(su) == 10 * 130 and len(np.unique(su)) > 900                    # ... then it reshuffles and repeats
+    lc = sl.reshape(10, 70)[:, :50].reshape(-1)
+    ld = sl.reshape(10, 70)[:, 50:].reshape(-1)
+    assert sl.max() < Ml and len(np.unique(lc[:100])) == 100 and len(np.unique(ld[:120])) == 120    # separate shuffled streams
+    assert not np.array_equal(lc[:20], ld[:20]) and len(np.unique(sl)) >= Ml - 3
     assert z.min() >= -1 and z.max() < 1 and abs(z.mean()) < 0.02 and abs(z.std() - 3 ** -0.5) < 0.02
     assert not np.array_equal(z[0], z[1])
     assert np.array_equal(y.sum(-1), np.ones(y.shape[:2])) and set(np.unique(y)) == {0.0, 1.0}
     h = y.reshape(-1, 10).sum(0)
-    assert h.min() > 35 and h.max() < 110                                      # 700 draws over 10 classes
+    assert h.min() > 55 and h.max() < 150                                      # 1000 draws over 10 classes
     su2, sl2, z2, y2 = run(11)
     assert np.array_equal(su, su2) and np.array_equal(sl, sl2) and np.array_equal(z, z2) and np.array_equal(y, y2)
     su3, _, z3, _ = run(12)
@@ -214,7 +220,7 @@ def test_epoch_from_device_pipeline_and_sample():
                                   pipeline.DeviceDataset(iu, lu, 10, 'cifar10'), seed=3)
     tr.capture()
     d, g, c = tr.train_epoch(inp.epoch(tr.inputs), epoch=1)
-    assert all(np.isfinite(v) for v in (d, g, c)) and inp.steps_per_epoch() == 3
+    assert all(np.isfinite(v) for v in (d, g, c)) and inp.steps_per_epoch() == 4
     ids = _ids(tr.inputs['x_u_c'])
     assert ids.max() < 400 and len(np.unique(ids)) == 50                  # the graph's static buffers hold the last batch
     rng = np.random.default_rng(0)

@@ -289,12 +289,23 @@ def test_argmax_onehot_bit_exact():
     lg[4, :] = 0.25                               # all equal -> 0
     lg[5, 9] = np.inf
     lg[6, 0] = -np.inf
+    # NaN rows: Eigen's ArgMaxTupleReducer starts at (0, -FLT_MAX) and takes strictly greater
+    # elements only, so a NaN never wins and never blocks a later number; all-NaN / all -inf rows give index 0
+    lg[7, 0] = np.nan
+    lg[8, 5] = np.nan
+    lg[9, :] = np.nan
+    lg[10, :] = -np.inf
+    lg[11, :4] = np.nan
+    lg[11, 4:] = -np.inf
+    lg[12, :] = np.nan
+    lg[12, 7] = -1e30
     idx_ref, oh_ref = tfnp.argmax_onehot(lg, 10)
+    assert idx_ref[7] != 0 and idx_ref[9] == 0 and idx_ref[10] == 0 and idx_ref[11] == 0 and idx_ref[12] == 7
     idx, oh = ops.argmax_onehot(var(lg), 10)
     assert idx.data.dtype == torch.int64
     assert np.array_equal(idx.data.cpu().numpy(), idx_ref)
     assert np.array_equal(oh.data.cpu().numpy(), oh_ref)
-    assert np.array_equal(idx_ref, torch.argmax(torch.from_numpy(lg), 1).numpy())
+    assert np.array_equal(idx_ref, O.argmax_onehot(torch.from_numpy(lg))[0].numpy())
 
 
 @pytest.mark.parametrize('rep', [True, False])

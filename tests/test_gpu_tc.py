@@ -48,7 +48,20 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize('c', CASES)
+# the heavy classifier layers at the sizes the benchmark runs them (Train_goodGAN.py:566-572): one call of batch
+# 100 (G) and the grouped phase-C batch of 250 (50 + 50 + 50 + 100): multi-wave persistent tile schedule, TMEM
+# double-buffer phase flips, 49-way split-K filter gradients
+FULL = [
+    dict(N=100, H=32, W=32, Cin=128, Cout=128, k=3, s=1, pad='SAME'),   # conv1_2 / conv1_3
+    dict(N=250, H=32, W=32, Cin=128, Cout=128, k=3, s=1, pad='SAME'),
+    dict(N=100, H=16, W=16, Cin=256, Cout=256, k=3, s=1, pad='SAME'),   # conv2_2 / conv2_3
+    dict(N=250, H=16, W=16, Cin=256, Cout=256, k=3, s=1, pad='SAME'),
+    dict(N=250, H=8, W=8, Cin=256, Cout=512, k=3, s=1, pad='VALID'),    # conv3
+    dict(N=250, H=16, W=16, Cin=128, Cout=256, k=3, s=1, pad='SAME'),   # conv2_1
+]
+
+
+@pytest.mark.parametrize('c', CASES + FULL)
 def test_tc_conv_fwd_bwd(c):
     from tgan import core, ops, tc
     rng = np.random.default_rng(1)

@@ -155,8 +155,12 @@ def test_bench_reference_arm_contract():
     j = json.loads(out.stdout.strip().splitlines()[-1])
     assert j['impl'] == 'reference' and j['metric'] == 'CIFAR-10 Triple-GAN train images/sec' and j['unit'] == 'images/s'
     assert j['higher_is_better'] is True and j['value'] > 0 and j['steps'] == 1
-    assert j['config']['workload'].startswith('CIFAR-10 32x32x3 Triple-GAN') and 'sample' in j['config']
-    assert j['cpu_baseline']['kind'] == 'port' and j['cpu_baseline']['cores'] == os.cpu_count()
+    # the same config block as the GPU arm: the FULL batch tuple (100 images per step), not a reduced sample
+    assert j['config'] == {'workload': j['config']['workload'], 'global_batch': 100, 'parallelism': 'dp1'}
+    assert j['config']['workload'].startswith('CIFAR-10 32x32x3 Triple-GAN')
+    assert abs(j['value'] - 100.0 / (j['ms_per_step'] * 1e-3)) < 1e-6 * j['value']
+    assert j['cpu_baseline']['kind'] == 'port' and 1 <= j['cpu_baseline']['cores'] <= os.cpu_count()
+    assert '100 images/step' in j['cpu_baseline']['sample']
     assert j['cpu_baseline']['value'] == j['value']
     assert j['e2e'] == {'value': j['value'], 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     env['RANK'] = '1'
@@ -164,3 +168,22 @@ def test_bench_reference_arm_contract():
     out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--gpus', '2', '--steps', '1',
                           '--warmup', '1'], capture_output=True, text=True, timeout=600, env=env, cwd=root)
     assert out.returncode == 0 and out.stdout.strip() == ''
+    # BASELINE.json configs[0]: the MNIST step on the reference's CPU path
+    env = dict(os.environ, RANK='0', WORLD_SIZE='1')
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--workload', 'mnist',
+                          '--steps', '1', '--warmup', '1'], capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    j = json.loads(out.stdout.strip().splitlines()[-1])
+    assert j['metric'] == 'MNIST Triple-GAN train images/sec' and j['config']['workload'].startswith('MNIST 28x28x1')
+    assert j['value'] > 0 and j['config']['global_batch'] == 100
+
+
+def test_pre_train_rule_of_the_dataset_mains():
+    """Train_goodGAN.py:537-538, 614-615: PRE_TRAIN (classifier-only iterations for the first 30 epochs) switches on
+    when NUM_LABEL < 1000 in the svhn and cifar10 mains; the mnist main has the rule commented out (:692-693)."""
+    from tgan.config import make_config
+    assert make_config('svhn').NUM_LABEL == 500 and make_config('svhn').PRE_TRAIN is True
+    assert make_config('cifar10').NUM_LABEL == 4000 and make_config('cifar10').PRE_TRAIN is False
+    assert make_config('cifar10', NUM_LABEL=500).PRE_TRAIN is True
+    assert make_config('mnist').NUM_LABEL == 100 and make_config('mnist').PRE_TRAIN is False
+    assert make_config('svhn', PRE_TRAIN=False).PRE_TRAIN is False
