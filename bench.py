@@ -136,27 +136,30 @@ def run_reference(args, rank):
         'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}), flush=True)
 
 
-def dominant_kernel_roofline(torch, tgan, pk):
-    """conv1_2 / conv1_3 forward at batch 100 (128 -> 128 channels, 32x32, 3x3): the implicit-GEMM tcgen05 kernel
-    (igemm_kernel) whose fprop / dgrad instances carry ~2/3 of the step's FLOPs.  16 launches over a ring of 8
-    distinct inputs (8 x 26 MB > the 126 MB L2, so no launch finds its input cached) are captured in one CUDA graph;
-    CUDA events on the launching stream bracket the replay, so no host launch overhead is in the number."""
-    from tgan import core, ops
-    core.ctx.store = core.VariableStore()
-    N, H, C, R = 100, 32, 128, 16
-    xs = [ops.Var(torch.randn(N, H, H, C, device='cuda').to(torch.bfloat16), (N, H, H, C)) for _ in range(8)]
+def _time_conv(torch, ops, core, N, segs, colsum, R, ring):
+    """R launches of the conv 128 -> 128 @32x32 forward over a ring of `ring` distinct inputs (ring x input bytes > the
+    126 MB L2, so no launch finds its input cached), captured in one CUDA graph; CUDA events on the launching stream
+    bracket the replay, so no host launch overhead is in the number.  -> seconds per launch"""
+    H, C = 32, 128
+    xs = []
+    for _ in range(ring):
+        v = ops.Var(torch.randn(N, H, H, C, device='cuda').to(torch.bfloat16), (N, H, H, C))
+        if segs:
+            v.aux = {'segs': list(segs)}
+        xs.append(v)
     p = core.Param('w', (3, 3, C, C), True, None)
     p.data = torch.randn(3, 3, C, C, device='cuda') * 0.03
     w = ops.PlainWeight(p)
-    flops = 2.0 * N * H * H * 9 * C * C
     st = torch.cuda.Stream()
     with torch.cuda.stream(st):
         for i in range(3):
-            ops.conv2d(xs[i], w, 3, 3, 1, 'SAME').data      # .data launches the (deferred) contraction
+            ops.arena_reset()
+            ops.conv2d(xs[i % ring], w, 3, 3, 1, 'SAME', colsum=colsum).data      # .data launches a deferred contraction
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
-        keep = [ops.conv2d(xs[i % 8], w, 3, 3, 1, 'SAME').data for i in range(R)]
+        ops.arena_reset()
+        keep = [ops.conv2d(xs[i % ring], w, 3, 3, 1, 'SAME', colsum=colsum).data for i in range(R)]
     g.replay()
     torch.cuda.synchronize()
     ts = []
@@ -167,16 +170,35 @@ def dominant_kernel_roofline(torch, tgan, pk):
         e1.record()
         e1.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e-3 / R)
-    t = sorted(ts)[len(ts) // 2]
-    del keep
-    achieved = flops / t / 1e12
+    del keep, xs
+    return sorted(ts)[len(ts) // 2]
+
+
+def dominant_kernel_roofline(torch, tgan, pk):
+    """The dominant kernel of the step is igemm_kernel on the classifier's 3x3 convolutions.  Its heaviest launches in
+    the timed step are the phase-C passes over the GROUPED batch of 250 (C(x_l) 50 + C(x_u) 50 + C(x_u) 50 + C(G(z)) 100,
+    Good_GAN_cifar10.py:228-240 as one pass with four mean-only-BN segments): conv1_2 / conv1_3, 128 -> 128 channels at
+    32x32, with the per-segment channel sums of the mean-only batch norm accumulated in the epilogue.  That launch is
+    measured here exactly as the step issues it; the single-call shape (batch 100, no statistics) is reported beside it."""
+    from tgan import core, ops
+    core.ctx.store = core.VariableStore()
+    C, H = 128, 32
+    t250 = _time_conv(torch, ops, core, 250, (50, 50, 50, 100), True, 12, 4)
+    t100 = _time_conv(torch, ops, core, 100, None, False, 16, 8)
+    f250, f100 = 2.0 * 250 * H * H * 9 * C * C, 2.0 * 100 * H * H * 9 * C * C
+    achieved = f250 / t250 / 1e12
     traffic = None
     pj = os.path.join(ROOT, 'profiles', 'dominant_kernel.json')
     if os.path.exists(pj):
-        traffic = json.load(open(pj)).get('dram_bytes_per_launch')
-    return {'bound': 'tensor', 'kernel': 'igemm_kernel (conv 128->128 @32x32, batch 100, fprop)', 'achieved': achieved,
-            'peak': pk['bf16'], 'unit': 'TFLOP/s', 'frac': achieved / pk['bf16'], 'peak_source': pk['src'] + ' burst bf16',
-            'traffic': traffic, 'flops_per_launch': flops, 'us_per_launch': t * 1e6}
+        traffic = json.load(open(pj)).get('dram_bytes_per_launch_b250')
+    return {'bound': 'tensor',
+            'kernel': 'igemm_kernel (conv 128->128 @32x32 fprop, grouped phase-C batch 250 with 4-segment channel sums: '
+                      'the launch the timed step issues for conv1_2 / conv1_3)',
+            'achieved': achieved, 'peak': pk['bf16'], 'unit': 'TFLOP/s', 'frac': achieved / pk['bf16'],
+            'peak_source': pk['src'] + ' burst bf16 (kernel timed alone)', 'frac_of_sustained': achieved / pk['bf16_sustained'],
+            'traffic': traffic, 'flops_per_launch': f250, 'us_per_launch': t250 * 1e6,
+            'single_call_batch100': {'achieved': f100 / t100 / 1e12, 'frac': f100 / t100 / 1e12 / pk['bf16'],
+                                     'flops_per_launch': f100, 'us_per_launch': t100 * 1e6}}
 
 
 def _finish(world, dist, torch):
@@ -266,15 +288,20 @@ def main():
     if graph:
         launches = tr.launches_per_step * args.steps
     clocks = sampler.stop()
-    # ---- leg 2: end to end through the public API: pinned host batch -> H2D -> step -> loss D2H, every step ----
+    # ---- leg 2: end to end through the public API (Train.host_feed): every step uploads ITS OWN pinned host batch
+    # (H2D on the copy stream, overlapped with the previous step) and the loss triple comes back D2H every step (read one
+    # step late); both are inside the timed region ----
+    feed = tr.host_feed()
+    feed.prime(batch)
     for _ in range(2):
-        tr.step(batch, **lam).cpu()
+        feed.step(batch, **lam)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     last = None
     for _ in range(args.steps):
-        last = tr.step(batch, **lam).cpu()
+        last = feed.step(batch, **lam)
+    last = feed.drain()
     f1.record()
     barrier()
     t_e2e = f0.elapsed_time(f1) * 1e-3

@@ -296,6 +296,11 @@ int tgan_fill_label(const float* lab, int K, int rows_per_sample, void* out, int
 /* strided channel slice / cast: dst[r, 0:C] = src[r, 0:C] */
 int tgan_copy_channels(const void* src, int sdt, int lds, void* dst, int ddt, int ldd, int64_t rows, int C,
                        void* stream);
+/* dst = concat(src[0], ..., src[n-1]) (n <= 8), each source contiguous with counts[i] elements of dtype dts[i]
+ * (fp32 / bf16), converted to ddt: the grouped batch of several calls of one network (Good_GAN_cifar10.py:228-240 /
+ * :264-270 run as one pass) formed by ONE launch */
+int tgan_gather_rows(const void* const* srcs, const int* dts, const int64_t* counts, int n, void* dst, int ddt,
+                     void* stream);
 /* y (+)= x elementwise (gradient accumulation), fp32 or bf16 */
 int tgan_accumulate(void* y, const void* x, int dt, int64_t n, void* stream);
 int tgan_fill_f32(float* p, float v, int64_t n, void* stream);

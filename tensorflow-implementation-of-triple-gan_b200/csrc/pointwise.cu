@@ -958,6 +958,26 @@ __global__ void copy_channels_kernel(const TS* __restrict__ src, int lds, TD* __
   int64_t r = i / C;
   stf<TD>(dst, r * ldd + j, ldf<TS>(src, r * lds + j));
 }
+// Concatenation of up to 8 contiguous sources (fp32 or bf16 each) into one destination: the grouped batch of several
+// network calls (ops.group_batch) in ONE launch instead of one copy per source.
+struct GatherSrcs {
+  const void* src[8];
+  int64_t end[8];      // exclusive prefix ends, in elements
+  int dt[8];
+  int n;
+};
+template <typename TD>
+__global__ void gather_rows_kernel(const __grid_constant__ GatherSrcs g, TD* __restrict__ dst, int64_t total) {
+  pdl_entry();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int k = 0;
+    while (k + 1 < g.n && i >= g.end[k]) ++k;
+    const int64_t j = i - (k ? g.end[k - 1] : 0);
+    const float v = g.dt[k] == TGAN_BF16 ? __bfloat162float(reinterpret_cast<const bf16*>(g.src[k])[j])
+                                         : reinterpret_cast<const float*>(g.src[k])[j];
+    stf<TD>(dst, i, v);
+  }
+}
 template <typename T>
 __global__ void accumulate_kernel(T* __restrict__ y, const T* __restrict__ x, int64_t n) {
   pdl_entry();
@@ -1381,6 +1401,22 @@ extern "C" int tgan_copy_channels(const void* src, int sdt, int lds, void* dst, 
   TGAN_CHECK_ARG(src && dst && lds >= C && ldd >= C, "copy_channels: bad args");
   int64_t total = rows * C;
   DISPATCH_2(sdt, TS, ddt, TD, (pdl_launch(copy_channels_kernel<TS, TD>, ceil_div(total, 256), 256, 0, (cudaStream_t)((cudaStream_t)stream), (const TS*)src, lds, (TD*)dst, ldd, C, total)));
+  TGAN_LAUNCHED();
+  return 0;
+}
+extern "C" int tgan_gather_rows(const void* const* srcs, const int* dts, const int64_t* counts, int n, void* dst, int ddt,
+                                void* stream) {
+  TGAN_CHECK_ARG(srcs && dts && counts && dst && n >= 1 && n <= 8, "gather_rows: 1..8 sources");
+  GatherSrcs g;
+  memset(&g, 0, sizeof(g));
+  int64_t tot = 0;
+  for (int i = 0; i < n; ++i) {
+    TGAN_CHECK_ARG(srcs[i] && counts[i] > 0 && (dts[i] == TGAN_F32 || dts[i] == TGAN_BF16), "gather_rows: bad source %d", i);
+    tot += counts[i];
+    g.src[i] = srcs[i]; g.end[i] = tot; g.dt[i] = dts[i];
+  }
+  g.n = n;
+  TGAN_DISPATCH_1(ddt, TD, (pdl_launch(gather_rows_kernel<TD>, grid_for(tot), 256, 0, (cudaStream_t)stream, g, (TD*)dst, tot)));
   TGAN_LAUNCHED();
   return 0;
 }

@@ -127,13 +127,18 @@ def group_batch(vs, tags=None):
         out = Var(None, shape)
     else:
         t = torch.empty(shape, dtype=vs[0].data.dtype, device=ctx.device)
-        per, o, es = int(np.prod(shape[1:])), 0, t.element_size()
+        per = int(np.prod(shape[1:]))
         for v in vs:      # same elements per sample in any view ([N,28,28,1] vs [N,784]); dtype converted on the fly
             assert v.ld == v.C and int(np.prod(v.shape[1:])) == per
-            n = v.shape[0] * per
-            _lib.call('tgan_copy_channels', _p(v.data), dt_code(v.data), n, t.data_ptr() + o * per * es, dt_code(t), n,
-                      1, n, _st())
-            o += v.shape[0]
+        o = 0
+        for i in range(0, len(vs), 8):      # ONE launch per 8 sources
+            part = vs[i:i + 8]
+            n = len(part)
+            srcs = (ctypes.c_void_p * n)(*[_p(v.data) for v in part])
+            dts = (ctypes.c_int * n)(*[dt_code(v.data) for v in part])
+            cnt = (ctypes.c_int64 * n)(*[v.shape[0] * per for v in part])
+            _lib.call('tgan_gather_rows', srcs, dts, cnt, n, t.data_ptr() + o * t.element_size(), dt_code(t), _st())
+            o += sum(v.shape[0] * per for v in part)
         out = Var(t, shape)
     out.aux = {'segs': [v.shape[0] for v in vs]}
     return out
@@ -1070,21 +1075,21 @@ def loss_d(dr, df, du):
     return Loss(val, list(zip((dr, df, du), g)))
 
 
-def loss_g(df):
-    """train_base.py:128."""
+def loss_g(df, out=None):
+    """train_base.py:128.  out: optional fp32 [1] device view that receives the scalar."""
     if ctx.building:
         return Loss(None, [])
-    val, g = _new((1,), torch.float32), _new(df.shape, torch.float32)
+    val, g = (out if out is not None else _new((1,), torch.float32)), _new(df.shape, torch.float32)
     _lib.call('tgan_loss_g', _p(_f32logits(df)), df.rows, _p(val), _p(g), _st())
     return Loss(val, [(df, g)])
 
 
-def loss_c(c_real, y_l_c, c_unl, c_rep, d_unl_logits, c_fake, y_g, lambdas):
+def loss_c(c_real, y_l_c, c_unl, c_rep, d_unl_logits, c_fake, y_g, lambdas, out=None):
     """train_base.py:130-152.  lambdas: device fp32 [2] = {lambda_1, lambda_2}."""
     if ctx.building:
         return Loss(None, [])
     K = c_real.shape[1]
-    val = _new((1,), torch.float32)
+    val = out if out is not None else _new((1,), torch.float32)
     g_real, g_unl, g_fake = (_new(v.shape, torch.float32) for v in (c_real, c_unl, c_fake))
     g_rep = _new(c_rep.shape, torch.float32) if c_rep is not None else None
     _lib.call('tgan_loss_c', _p(_f32logits(c_real)), _p(y_l_c.data), c_real.rows, _p(_f32logits(c_unl)),
@@ -1094,18 +1099,18 @@ def loss_c(c_real, y_l_c, c_unl, c_rep, d_unl_logits, c_fake, y_g, lambdas):
     return Loss(val, [(c_real, g_real), (c_unl, g_unl), (c_rep, g_rep), (c_fake, g_fake)])
 
 
-def loss_d_grouped(logits, nr, nf, nu):
+def loss_d_grouped(logits, nr, nf, nu, out=None):
     """d_loss on one grouped D pass: rows [0,nr) real, [nr,nr+nf) fake, [nr+nf, ...) unlabelled (train_base.py:123-126)"""
     if ctx.building:
         return Loss(None, [])
     x = _f32logits(logits)
-    val, g = _new((1,), torch.float32), _new(logits.shape, torch.float32)
+    val, g = (out if out is not None else _new((1,), torch.float32)), _new(logits.shape, torch.float32)
     _lib.call('tgan_loss_d', x.data_ptr(), nr, x.data_ptr() + 4 * nr, nf, x.data_ptr() + 4 * (nr + nf), nu, _p(val),
               g.data_ptr(), g.data_ptr() + 4 * nr, g.data_ptr() + 4 * (nr + nf), _st())
     return Loss(val, [(logits, g)])
 
 
-def loss_c_grouped(logits, segs, has_rep, y_l_c, d_unl_logits, y_g, lambdas):
+def loss_c_grouped(logits, segs, has_rep, y_l_c, d_unl_logits, y_g, lambdas, out=None):
     """c_loss on one grouped C pass with rows ordered [real | unl | (rep) | fake] (train_base.py:130-152)"""
     if ctx.building:
         return Loss(None, [])
@@ -1114,7 +1119,7 @@ def loss_c_grouped(logits, segs, has_rep, y_l_c, d_unl_logits, y_g, lambdas):
     offs = [0]
     for n in segs:
         offs.append(offs[-1] + n)
-    val, g = _new((1,), torch.float32), _new(logits.shape, torch.float32)
+    val, g = (out if out is not None else _new((1,), torch.float32)), _new(logits.shape, torch.float32)
     at = lambda t, i: t.data_ptr() + 4 * K * offs[i]
     i_fake = 3 if has_rep else 2
     _lib.call('tgan_loss_c', at(x, 0), _p(y_l_c.data), segs[0], at(x, 1), at(x, 2) if has_rep else None,

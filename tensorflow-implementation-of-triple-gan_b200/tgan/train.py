@@ -40,6 +40,76 @@ class ExponentialMovingAverage:
         return self.shadow[o:o + param.size].view(param.shape)
 
 
+class HostFeed:
+    """Double-buffered host -> device input feed for Train.step (the reference feeds numpy batches through feed_dict on
+    every sess.run, Train_goodGAN.py:249-276).  `step(next_batch)` runs one iteration on the batch uploaded by the
+    PREVIOUS call while `next_batch` travels to the device on a copy stream, and returns the losses of the previous
+    iteration (their device-to-host copy finished long ago), so neither the H2D copy nor the loss read-back stalls the
+    GPU.  Usage:
+        feed = tr.host_feed(); feed.prime(batch0)
+        for b in batches[1:]: losses_prev = feed.step(b, lambda_1=..., lambda_2=...)
+        last = feed.drain()
+    """
+
+    def __init__(self, trainer):
+        self.tr = trainer
+        n = trainer.input_flat.numel()
+        self.staging = [torch.empty(n, dtype=torch.float32, device=ctx.device) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream()
+        self.uploaded = [torch.cuda.Event(), torch.cuda.Event()]      # staging[i] holds a complete batch
+        self.consumed = [torch.cuda.Event(), torch.cuda.Event()]      # the step has copied staging[i] away
+        self.loss_host = torch.zeros((2, 3), dtype=torch.float32).pin_memory()
+        self.loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.cur, self.k, self.primed = 0, 0, False
+        for e in self.consumed:
+            e.record()
+
+    def _upload(self, batch, slot):
+        tr = self.tr
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.consumed[slot])
+            for name in INPUT_NAMES:
+                t = batch[name]
+                if isinstance(t, np.ndarray):
+                    t = torch.from_numpy(t)
+                o = tr.input_offsets[name]
+                self.staging[slot][o:o + t.numel()].copy_(t.reshape(-1), non_blocking=True)
+            self.uploaded[slot].record(self.copy_stream)
+
+    def prime(self, batch):
+        self._upload(batch, self.cur)
+        self.primed = True
+
+    def step(self, next_batch=None, **kw):
+        """one iteration on the batch uploaded last; uploads `next_batch` meanwhile.  Returns the PREVIOUS iteration's
+        [d_loss, g_loss, c_loss] as a host tensor (None on the first call)."""
+        assert self.primed, 'HostFeed.prime(batch) first'
+        tr, cur = self.tr, self.cur
+        st = torch.cuda.current_stream()
+        st.wait_event(self.uploaded[cur])
+        tr.input_flat.copy_(self.staging[cur], non_blocking=True)      # one 2.5 MB device-to-device copy
+        self.consumed[cur].record(st)
+        if next_batch is not None:
+            self._upload(next_batch, 1 - cur)
+        out = tr.step(**kw)
+        slot = self.k & 1
+        prev = None
+        if self.k > 0:
+            self.loss_ready[1 - slot].synchronize()
+            prev = self.loss_host[1 - slot].clone()
+        self.loss_host[slot].copy_(out, non_blocking=True)
+        self.loss_ready[slot].record(st)
+        self.cur, self.k = 1 - cur, self.k + 1
+        self.primed = next_batch is not None
+        return prev
+
+    def drain(self):
+        """losses of the last iteration (synchronises)"""
+        slot = (self.k - 1) & 1
+        self.loss_ready[slot].synchronize()
+        return self.loss_host[slot].clone()
+
+
 class Train(Train_base):
     def __init__(self, config, log_dir=None, save_dir=None, **kwargs):
         super(Train, self).__init__()
@@ -91,8 +161,16 @@ class Train(Train_base):
         self.ema = ExponentialMovingAverage(decay=0.9999)
         self.lambdas = torch.zeros(2, dtype=torch.float32, device=ctx.device)
         self._lam = (None, None)
-        self.inputs = {k: torch.zeros(tuple(v), dtype=torch.float32, device=ctx.device)
-                       for k, v in self.input_shapes().items()}
+        # the eight step inputs are views of ONE flat buffer (16-byte aligned each): a double-buffered host feed moves a
+        # whole batch with one device-to-device copy (HostFeed)
+        shp = self.input_shapes()
+        offs, tot = {}, 0
+        for k in INPUT_NAMES:
+            offs[k] = tot
+            tot += (int(np.prod(shp[k])) + 3) // 4 * 4
+        self.input_flat = torch.zeros(tot, dtype=torch.float32, device=ctx.device)
+        self.input_offsets = offs
+        self.inputs = {k: self.input_flat[offs[k]:offs[k] + int(np.prod(shp[k]))].view(tuple(shp[k])) for k in INPUT_NAMES}
         # everything a CUDA-graph replay must NOT re-initialise is created here, outside any capture
         for o in (self.d_optimizer, self.g_optimizer, self.c_optimizer):
             o._state()
@@ -207,7 +285,7 @@ class Train(Train_base):
                 Y = ops.group_batch([v['y_l_d'], oh_d, v['y_g'], oh_u])
                 X.aux = None                     # D is per-sample: one plain batch of 250
                 _, dl = m.discriminator(X, Y, reuse=True, tag=TL([('D/D_real', nLD + nUD), ('D/D_fake', nG), ('D/D_unl', nUC)]))
-                d_loss = ops.loss_d_grouped(dl, nLD + nUD, nG, nUC)
+                d_loss = ops.loss_d_grouped(dl, nLD + nUD, nG, nUC, out=self.loss_buf[0:1])
                 ops.backward(d_loss)
             self._apply(fb, self.d_optimizer, group='discriminator')
             self.aux = dict(idx_unl_d=idx_d, idx_unl=idx_u, G_phaseD=G, d_logits=dl)
@@ -215,7 +293,7 @@ class Train(Train_base):
             fb = self._begin('good_generator', self.g_vars)
             with recording() as tape_d:
                 _, df = m.discriminator(G, v['y_g'], reuse=True, tag='G/D_fake')
-                g_loss = ops.loss_g(df)
+                g_loss = ops.loss_g(df, out=self.loss_buf[1:2])
                 g_loss.seed()
                 tape_d.backward()                # d g_loss / d G through D1 (dgrad only)
             tape_g.backward()                    # ... and through the generator recorded in phase D
@@ -234,7 +312,7 @@ class Train(Train_base):
                 with no_grad():
                     idx_c, oh_u = ops.argmax_onehot(c_unl_v, K)
                     _, du = m.discriminator(v['x_u_c'], oh_u, reuse=True, tag='C/D_unl')
-                c_loss = ops.loss_c_grouped(lg, segs, True, v['y_l_c'], du, v['y_g'], self.lambdas)
+                c_loss = ops.loss_c_grouped(lg, segs, True, v['y_l_c'], du, v['y_g'], self.lambdas, out=self.loss_buf[2:3])
                 self.aux['c_logits'] = lg
             else:
                 c_real, _ = m.classifier(pre(v['x_l_c']), train, reuse=True, tag='C/C_real')
@@ -244,18 +322,15 @@ class Train(Train_base):
                     idx_c, oh_u = ops.argmax_onehot(c_unl, K)
                     _, du = m.discriminator(v['x_u_c'], oh_u, reuse=True, tag='C/D_unl')
                 c_fake, _ = m.classifier(pre(G), train, reuse=True, tag='C/C_fake')
-                c_loss = ops.loss_c(c_real, v['y_l_c'], c_unl, c_rep, du, c_fake, v['y_g'], self.lambdas)
+                c_loss = ops.loss_c(c_real, v['y_l_c'], c_unl, c_rep, du, c_fake, v['y_g'], self.lambdas,
+                                    out=self.loss_buf[2:3])
                 self.aux['c_logits'] = (c_real, c_unl, c_fake, c_rep)
             self.aux['idx_unl_c'] = idx_c
             ops.backward(c_loss)
         self._apply(fb, self.c_optimizer, self.ema, group='classifier')
         if not ctx.rng.injected:
             _lib.call('tgan_counter_advance', ctx.rng.counter().data_ptr(), 1, ops._st())
-        for i, l in enumerate((d_loss, g_loss, c_loss)):
-            if l is not None:
-                _lib.call('tgan_copy_channels', l.value.data_ptr(), 0, 1, self.loss_buf.data_ptr() + 4 * i, 0, 1, 1, 1,
-                          ops._st())
-        return d_loss, g_loss, c_loss
+        return d_loss, g_loss, c_loss      # the three loss kernels wrote their scalars straight into self.loss_buf
 
     def load_batch(self, batch):
         """Copy one step's inputs (numpy / CPU / device tensors) into the static device buffers."""
@@ -289,6 +364,11 @@ class Train(Train_base):
         if not ctx.rng.injected:
             ts.append(ctx.rng.counter())
         return ts
+
+    def host_feed(self):
+        """-> HostFeed: the step driven from HOST batches without stalling the GPU (upload of batch k+1 overlaps step k,
+        losses are read one step late)."""
+        return HostFeed(self)
 
     def capture(self, warmup=3):
         """Capture the whole three-phase step into one CUDA graph (the step is a few hundred small

@@ -230,3 +230,32 @@ def test_epoch_from_device_pipeline_and_sample():
     assert tuple(grid.shape) == (256, 256, 3)
     gn = grid.cpu().numpy()
     assert np.isfinite(gn).all() and gn.min() >= 0 and gn.max() <= 1
+
+
+@pytest.mark.parametrize('graph', [False, True])
+def test_host_feed_matches_direct_steps(graph):
+    """Train.host_feed(): the double-buffered host feed (upload of batch k+1 overlapped with step k, losses read one step
+    late) gives bit-identical losses and parameters to loading each batch and stepping directly."""
+    cfg = O.OracleConfig('cifar10', 10)
+    batches = [O.make_batch(cfg, seed=20 + i) for i in range(4)]
+    pinned = [{k: torch.from_numpy(v).pin_memory() for k, v in b.items()} for b in batches]
+    tr = _trainer('bf16', 5)
+    if graph:
+        tr.capture()
+    direct = [tr.step(b, lambda_1=0.3, lambda_2=0.5).cpu().numpy().copy() for b in batches]
+    theta = {g: tr.store.flat[g]['theta'].cpu().numpy().copy() for g in tr.store.GROUPS}
+    tr2 = _trainer('bf16', 5)
+    if graph:
+        tr2.capture()
+    feed = tr2.host_feed()
+    feed.prime(pinned[0])
+    got = []
+    for i in range(4):
+        prev = feed.step(pinned[i + 1] if i + 1 < 4 else None, lambda_1=0.3, lambda_2=0.5)
+        assert (prev is None) == (i == 0)
+        if prev is not None:
+            got.append(prev.numpy().copy())
+    got.append(feed.drain().numpy().copy())
+    assert np.array_equal(np.stack(direct), np.stack(got)), (direct, got)
+    for g in theta:
+        assert np.array_equal(theta[g], tr2.store.flat[g]['theta'].cpu().numpy()), g

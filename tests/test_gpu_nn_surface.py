@@ -85,8 +85,9 @@ def test_batch_norm_impl(shape, train, math):
     tf_, tg = TOL[math]
     assert relerr(fwd, yt.detach().numpy()) < tf_
     assert relerr(tnp(xv.grad), xt.grad.numpy()) < tg
-    assert relerr(tnp(ps.grad), P[n + '/scale'].grad.numpy()) < tg
-    assert relerr(tnp(pb.grad), P[n + '/beta'].grad.numpy()) < tg
+    if train:      # (deterministic=True is the test-time graph: nothing differentiates scale / beta through it)
+        assert relerr(tnp(ps.grad), P[n + '/scale'].grad.numpy()) < tg
+        assert relerr(tnp(pb.grad), P[n + '/beta'].grad.numpy()) < tg
     # population statistics: decay-0.9 EMA of the batch mean and of the BIASED batch variance (nn.py:207-214)
     assert relerr(tnp(ppm.data), S[n + '/pop_mean'].numpy()) < 1e-4
     assert relerr(tnp(ppv.data), S[n + '/pop_var'].numpy()) < 1e-4
