@@ -97,8 +97,42 @@ typedef struct {
                           of dy/dx/wp (sum = T) and writes at output offset (cls_ooy[c], cls_oox[c]) instead of (ooy, oox);
                           list the classes with the most taps first */
   int cls_T[4], cls_ooy[4], cls_oox[4];
+  /* ---- mean-only batch norm fused into the contraction (nn.py:147-187, :504-518 without a pass of its own).  All four
+   * need an output whose pixels are LINEAR in memory per launch tile (full-width row blocks of one image, or a flat
+   * GEMM) and the TMA-store epilogue (bf16 output, ldo % 8 == 0); the entry point rejects other geometries. ---- */
+  int bias_seg;        /* 1: bias is fp32 [nseg][Nout] -- segment s adds bias[s][:] (= b - mean_s, the mean known before
+                          the launch from tgan_mobn_mean_from_sums) */
+  void* clsum;         /* optional int64 Q24 [nseg][9][Nout]: += sums of the STORED values by border class, index
+                          3 * (row first / interior / last) + (column first / interior / last) of a cls_h x cls_w image */
+  int cls_h, cls_w;    /* powers of two; cls_w in {16, 32} */
+  void* mask_out;      /* optional uint32 [ceil(pixels / 32)][Nout]: bit j of word (i, c) = stored value of pixel
+                          32 i + j, channel c, is > 0 (which side of the leaky ReLU it is on) */
+  const void* mask_in; /* optional, same layout: the stored value is multiplied by 1 (bit set) or mask_alpha -- the
+                          input gradient passes through the PRODUCER's leaky ReLU inside this launch's epilogue */
+  float mask_alpha;
 } tgan_igemm_args;
 int tgan_igemm_bf16(const tgan_igemm_args* a, void* stream);
+
+/* The batch mean of a convolution output is a linear function of border-aware sums of its INPUT:
+ *   mean_s[co] = sum_{t, ci} W[t][co][ci] * S_s[t][ci] / count_s,
+ *   S_s[t = (r, c)][ci] = sum of class sums over the row classes tap row r reads x the column classes tap column c reads
+ * (a 3x3 / stride 1 / SAME tap at row offset -1 never reads the last input row, +1 never the first; kh = kw = 1: all).
+ * clsum: int64 Q24 [nseg][9][Cin] written by the producer (tgan_igemm_bf16.clsum, tgan_class_sums, the pooling kernel);
+ * wp: the packed bf16 fprop weights the contraction itself reads (so the mean matches its arithmetic), element
+ * (t, co, ci) at wp[t * w_tap_stride + co * w_co_stride + ci]: [T][Cout][Kpad] -> (Cout*Kpad, Kpad); the im2col form
+ * [Cout][T*Cin padded] -> (Cin, Kpad).  T = 9 (3x3 SAME, taps row-major) or 1.  count[s] = output pixels of segment s.
+ * Writes shift[s][co] = b[co] - mean_s[co] (the per-segment bias of the fused epilogue) and, in call order,
+ * pop_mean = pop_mean*decay + mean_s*(1-decay) (nn.py:181). */
+int tgan_mobn_mean_from_sums(const void* clsum, int nseg, const int64_t* count, const void* wp, int T, int Cout, int Cin,
+                             int64_t w_tap_stride, int64_t w_co_stride, const float* b, float* pop_mean, float decay,
+                             float* shift, void* stream);
+/* border-class sums (same layout as tgan_igemm_bf16.clsum) of a small-channel fp32 / bf16 tensor [N, H, W, C] (C <= 16),
+ * of its values rounded to bf16 (what the tensor-core path reads): the classifier's 3-channel input */
+int tgan_class_sums(const void* x, int xdt, int N, int H, int W, int C, int ld, int nseg, const int* seg_end_images,
+                    void* clsum, void* stream);
+/* int64 Q24 per-segment channel sums [nseg][C] (tgan_igemm_bf16.colsum) -> fp32 colsums[4][C] (unused segments 0) and
+ * grad_acc[c] += sum over segments (the bias gradient of a mean-only-BN layer); grad_acc may be NULL */
+int tgan_seg_sums_finalize(const void* q24, int nseg, int C, float* colsums, float* grad_acc, void* stream);
 
 /* wgrad on tensor cores: dW[t][ci][co] (+)= sum_{n,oy,ox} dz[n,oy,ox,co] * x[n, oy + dy[t], ox + dx[t], ci]
  * (pixel dimension is the GEMM K; both operands are MN-major UMMA operands loaded by TMA).
@@ -262,11 +296,12 @@ int tgan_maxpool2_dropout_bwd(const void* dy, const uint8_t* code, void* dx, int
  * segments in IMAGES (n0,n1,n2 = exclusive end images of segments 0..2), sums fp32 [nseg][C] as tgan_mobn_apply_seg.
  * y / code as tgan_maxpool2_dropout_fwd.  bwd: du[N,H,W,C] = at the window winner keep * dy/(1-rate) * act'(y_winner),
  * zero elsewhere; colsums[seg][c] = per-segment sums of du, grad_acc[c] += total (the bias gradient).
- * ws: 4*TGAN_ACT_BWD_SEG_PARTS*C floats. */
+ * ws: 4*TGAN_ACT_BWD_SEG_PARTS*C floats.  clsum (optional, training): int64 Q24 [nseg][9][C] += border-class sums of the
+ * pooled output (layout of tgan_igemm_bf16.clsum) for the next convolution's fused mean-only BN. */
 int tgan_mobn_pool_dropout_fwd(const void* z, void* y, uint8_t* code, int N, int H, int W, int C, int nseg, int64_t n0,
                                int64_t n1, int64_t n2, const void* sums, int sums_q24, const float* b, float* pop_mean,
                                float decay, int train, int act, float alpha, float rate, const uint8_t* mask, uint64_t seed,
-                               uint64_t stream_id, const uint64_t* counter, void* stream);
+                               uint64_t stream_id, const uint64_t* counter, void* clsum, void* stream);
 int tgan_mobn_pool_dropout_bwd(const void* dy, const void* y, const uint8_t* code, void* du, int N, int H, int W, int C,
                                int nseg, int64_t n0, int64_t n1, int64_t n2, int act, float alpha, float rate,
                                float* colsums, float* grad_acc, float* ws, void* stream);

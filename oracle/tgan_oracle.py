@@ -67,8 +67,29 @@ class quantized:
         _QUANT = self._old
 
 
+class _RoundBoth(torch.autograd.Function):
+    """bf16 rounding of an ACTIVATION: the value in forward and, in backward, the gradient that flows back through the
+    same tensor -- the tensor-core path stores activation gradients (dy, du = dy*act', dz = du - mean) in bf16 exactly
+    where it stores the activations."""
+
+    @staticmethod
+    def forward(ctx, t):
+        return t.to(torch.bfloat16).to(t.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
 def q(t):
-    """round to bf16 (straight-through gradient) when the bf16 restatement is active"""
+    """round an activation to bf16 (and its gradient on the way back) when the bf16 restatement is active"""
+    if not _QUANT:
+        return t
+    return _RoundBoth.apply(t)
+
+
+def qw(t):
+    """round a weight operand to bf16; its gradient stays fp32 (filter gradients accumulate in fp32 / TMEM)"""
     if not _QUANT:
         return t
     return t + (t.detach().to(torch.bfloat16).to(t.dtype) - t.detach())
@@ -95,19 +116,20 @@ def same_pad(n, k, s):
     return out, tot // 2, tot - tot // 2
 
 
-def conv2d_tf(x, w, stride=1, padding='SAME'):
-    """tf.nn.conv2d on NHWC x, HWIO w (nn.py:504, modle_base.py:102,161)."""
+def conv2d_tf(x, w, stride=1, padding='SAME', round_out=True):
+    """tf.nn.conv2d on NHWC x, HWIO w (nn.py:504, modle_base.py:102,161).  round_out=False (bf16 restatement only): the
+    result stays in the fp32 accumulator because the consuming epilogue is fused into the contraction."""
     kh, kw = w.shape[0], w.shape[1]
     tc = _tc(w.shape[3])
     if tc:
-        x, w = q(x), q(w)
+        x, w = q(x), qw(w)
     xc = x.permute(0, 3, 1, 2)
     if padding.upper() == 'SAME':
         _, pt, pb = same_pad(x.shape[1], kh, stride)
         _, pl, pr = same_pad(x.shape[2], kw, stride)
         xc = F.pad(xc, (pl, pr, pt, pb))
     y = F.conv2d(xc, w.permute(3, 2, 0, 1), stride=stride)
-    return q(y.permute(0, 2, 3, 1)) if tc else y.permute(0, 2, 3, 1)
+    return q(y.permute(0, 2, 3, 1)) if (tc and round_out) else y.permute(0, 2, 3, 1)
 
 
 def conv2d_transpose_tf(x, w, stride=2, padding='SAME'):
@@ -117,7 +139,7 @@ def conv2d_transpose_tf(x, w, stride=2, padding='SAME'):
     kh, kw = w.shape[0], w.shape[1]
     tc = _tc(w.shape[2])
     if tc:
-        x, w = q(x), q(w)
+        x, w = q(x), qw(w)
     y = F.conv_transpose2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), stride=stride)
     if padding.upper() == 'SAME':
         Ho, Wo = x.shape[1] * stride, x.shape[2] * stride
@@ -132,7 +154,7 @@ def conv2d_transpose_tf(x, w, stride=2, padding='SAME'):
 def matmul_tf(x, w):
     """tf.matmul / tf.layers.dense contraction (nn.py:553; modle_base.py:40,67)"""
     if _tc(w.shape[1]):
-        return q(q(x) @ q(w))
+        return q(q(x) @ qw(w))
     return x @ w
 
 
@@ -207,12 +229,13 @@ def mean_only_bn(x, pop_mean_key, b, S, train, conv, decay=0.9):
     return x - S[pop_mean_key] + b
 
 
-def conv2d_WN(P, S, scope, x, pad, train, nonlin=lrelu_cifar, stride=1):
+def conv2d_WN(P, S, scope, x, pad, train, nonlin=lrelu_cifar, stride=1, fused=False):
     """nn.conv2d_WN with use_weight_normalization + use_mean_only_batch_normalization,
-    init=False branch (nn.py:501-518)."""
+    init=False branch (nn.py:501-518).  fused (bf16 restatement): `- mean + b` and the nonlinearity run in the
+    contraction's epilogue on the fp32 accumulator, so the convolution output itself is never rounded."""
     V, g, b = P[scope + '/V'], P[scope + '/g'], P[scope + '/b']
     W = g.view(1, 1, 1, -1) * l2_normalize(V, (0, 1, 2))
-    x = conv2d_tf(x, W, stride, pad)
+    x = conv2d_tf(x, W, stride, pad, round_out=not fused)
     x = mean_only_bn(x, scope + '/meanOnlyBatchNormalization/pop_mean', b, S, train, True)
     return qc(nonlin(x) if nonlin is not None else x)
 
@@ -620,13 +643,16 @@ class OracleModel:
         if name == 'cifar10':    # Good_GAN_cifar10.py:101-174
             x = inp.reshape(-1, 32, 32, 3)
             x = q(x + 0.15 * rng.normal(tag + '/noise', x.shape).to(x.dtype))
+            # training-mode layers whose mean-only BN + leaky ReLU the tensor-core path fuses into the GEMM epilogue
+            # (tgan/ops.py conv2d_mobn): no max pool behind them, 16 / 32 pixel wide
+            fz = lambda n: train and n in ('conv1_1', 'conv1_2', 'conv2_1', 'conv2_2')
             for n in ['conv1_1', 'conv1_2', 'conv1_3']:
-                x = self._cap(tag + '/' + n, conv2d_WN(P, S, 'classifier/' + n, x, 'SAME', train))
+                x = self._cap(tag + '/' + n, conv2d_WN(P, S, 'classifier/' + n, x, 'SAME', train, fused=fz(n)))
             x = max_pool_tf(x, 2, 2)
             if train:
                 x = dropout_tf(x, rng.keep_mask(tag + '/drop1', x.shape, 0.5), 0.5)
             for n in ['conv2_1', 'conv2_2', 'conv2_3']:
-                x = self._cap(tag + '/' + n, conv2d_WN(P, S, 'classifier/' + n, x, 'SAME', train))
+                x = self._cap(tag + '/' + n, conv2d_WN(P, S, 'classifier/' + n, x, 'SAME', train, fused=fz(n)))
             x = max_pool_tf(x, 2, 2)
             if train:
                 x = dropout_tf(x, rng.keep_mask(tag + '/drop2', x.shape, 0.5), 0.5)

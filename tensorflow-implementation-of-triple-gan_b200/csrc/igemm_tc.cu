@@ -123,6 +123,15 @@ struct IgParams {
   int ncls, cT[4], ctap0[4], cooy[4], coox[4];
   int halo, halo_rows, halo_dy0;   // row-halo mode: box rows (2*th + 2), smallest dy
   int nbox;                        // 128-pixel boxes per tile: 2 (UMMA N = 256), or 1 when that leaves SMs without a tile
+  // ---- fused mean-only batch norm (nn.py:147-187 without its own pass over the activation) ----
+  int bias_seg;                    // bias is [nseg][Nout]: b - mean of the tile's batch segment (the mean is known BEFORE the
+                                   // launch: a linear function of border-aware input sums, tgan_mobn_mean_from_sums)
+  long long* clsum;                // Q24 [nseg][9][Nout]: sums of the STORED (bf16-rounded) values by border class
+                                   // (row first / interior / last) x (column first / interior / last) -> the next layer's mean
+  int cls_lw, cls_lh;              // log2 of the image width / height the classes refer to (pixels are linear in the output)
+  uint32_t* mask_out;              // [pixels / 32][Nout]: bit j = (stored value of pixel 32*i + j) > 0 (lrelu side)
+  const uint32_t* mask_in;         // input gradient: multiply by 1 (bit set) or mask_alpha (lrelu') before the store
+  float mask_alpha;
   int dbg;   // experiments only (TGAN_IGEMM_DBG): 1 skip activation loads, 2 skip weight loads, 4 skip stores,
              // 8 skip the epilogue body, 16 skip the smem-ring handshakes
 };
@@ -200,6 +209,26 @@ __device__ __forceinline__ void ig_sum_chunk(const IgParams& p, const float (&v)
     const int sg = p.segflat ? sga : (n >= p.seg_end[0]) + (n >= p.seg_end[1]) + (n >= p.seg_end[2]);
     csum[0] += sg == 0 ? s : 0.f; csum[1] += sg == 1 ? s : 0.f;
     csum[2] += sg == 2 ? s : 0.f; csum[3] += sg == 3 ? s : 0.f;
+  }
+}
+
+// Border-class sums of one chunk of 32 consecutive (linear) pixels starting at p0, image width W = 1 << LW in {16, 32}:
+// a[rc * 3 + cc], rc / cc = 0 first, 1 interior, 2 last row / column.  p0 is warp-uniform (lanes differ in the channel),
+// so the row-class branches do not diverge.  vr: the values as stored (bf16-rounded).
+template <int LW>
+__device__ __forceinline__ void ig_cls_chunk(const float (&vr)[32], int p0, int lh, int valid, float (&a)[9]) {
+  constexpr int W = 1 << LW;
+#pragma unroll
+  for (int k = 0; k < 32 / W; ++k) {
+    if (k * W >= valid) break;
+    float tot = 0.f;
+#pragma unroll
+    for (int j = 0; j < W; ++j) tot += vr[k * W + j];
+    const float fi = vr[k * W], la = vr[k * W + W - 1], mid = tot - fi - la;
+    const int y = ((p0 >> LW) + k) & ((1 << lh) - 1);
+    if (y == 0) { a[0] += fi; a[1] += mid; a[2] += la; }
+    else if (y == (1 << lh) - 1) { a[6] += fi; a[7] += mid; a[8] += la; }
+    else { a[3] += fi; a[4] += mid; a[5] += la; }
   }
 }
 
@@ -414,8 +443,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       const CUtensorMap* tmO = cls == 0 ? &tmO0 : cls == 1 ? &tmO1 : cls == 2 ? &tmO2 : &tmO3;
       const int co = ct * 128 + q * 32 + lane;
       const bool cvalid = co < p.Nout;
-      const float bias = (p.bias && cvalid) ? p.bias[co] : 0.f;
+      float bias = (p.bias && cvalid && !p.bias_seg) ? p.bias[co] : 0.f;
       float csum[4] = {0.f, 0.f, 0.f, 0.f};
+      float bsum[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};      // border-class sums of this tile
+      int tile_seg = 0;
       mbar_wait(&tfull[acc], accphase);
       tc_fence_after();
       for (int h = 0; h < p.nbox; ++h) {
@@ -427,6 +458,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         if (p.tstore) {           // the previous box's store must have finished reading the staging buffer
           if (warp == 2 && lane == 0) bulk_wait_read0();
           named_bar_sync(1, 256);
+        }
+        // linear index of the box's first pixel (host guarantees full-width tiles of one image, or one flat row, whenever
+        // masks / class sums / per-segment biases are requested) and the batch segment the box belongs to
+        const int box_p0 = ((ng * p.nb) * p.OH + ty * p.th) * p.OW + tx * p.tw;
+        if (p.bias_seg || p.clsum) {
+          const int key = p.segflat ? box_p0 : ng * p.nb;
+          tile_seg = (key >= p.seg_end[0]) + (key >= p.seg_end[1]) + (key >= p.seg_end[2]);
+          if (p.bias_seg) bias = cvalid ? p.bias[tile_seg * p.Nout + co] : 0.f;
         }
 #pragma unroll 1
         for (int cc = 0; cc < 2; ++cc) {
@@ -466,9 +505,32 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = tmp[j];
           }
+          if (p.mask_in && cvalid) {      // input gradient through the producer's leaky ReLU: du = dy * lrelu'(y)
+            const uint32_t mw = p.mask_in[(size_t)((box_p0 + pbase) >> 5) * p.Nout + co];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= ((mw >> j) & 1u) ? 1.f : p.mask_alpha;
+          }
           if (p.tstore) {
             // ---- staged path: [pixel][channel] rows in shared memory, one bulk-tensor store per 128-pixel box.  The
             // store needs no geometry (TMA clips at the valid extents); 32 lanes write 32 consecutive channels = 64 B.
+            if (p.mask_out || p.clsum) {
+              const int p0 = box_p0 + pbase;
+              const int total_px = p.segflat ? p.vw : p.N * p.OH * p.OW;
+              const int valid = total_px - p0;           // pixels of this chunk inside the tensor (flat GEMM tail)
+              if (p.mask_out && cvalid && valid > 0) {
+                uint32_t mw = 0u;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) mw |= (v[j] > 0.f ? 1u : 0u) << j;
+                p.mask_out[(size_t)(p0 >> 5) * p.Nout + co] = mw;
+              }
+              if (p.clsum && valid > 0) {
+                float vr[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) vr[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+                if (p.cls_lw == 5) ig_cls_chunk<5>(vr, p0, p.cls_lh, valid, bsum);
+                else ig_cls_chunk<4>(vr, p0, p.cls_lh, valid, bsum);
+              }
+            }
             if (p.colsum) {
               switch (p.ltw) {
                 case 2: ig_sum_chunk<4>(p, v, pbase, tx, ty, ng, csum); break;
@@ -504,6 +566,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
           if (gg < p.nseg && csum[gg] != 0.f)
             atomicAdd(reinterpret_cast<unsigned long long*>(&p.colsum[gg * p.Nout + co]),
                       (unsigned long long)__float2ll_rn(csum[gg] * 16777216.f));
+      }
+      if (p.clsum && cvalid) {        // a tile lies inside one batch segment (one image, or 256 pixels of one flat image)
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+          if (bsum[k] != 0.f)
+            atomicAdd(reinterpret_cast<unsigned long long*>(&p.clsum[((size_t)tile_seg * 9 + k) * p.Nout + co]),
+                      (unsigned long long)__float2ll_rn(bsum[k] * 16777216.f));
       }
       tc_fence_before();
       __syncwarp();
@@ -804,6 +873,29 @@ extern "C" int tgan_igemm_bf16(const tgan_igemm_args* a, void* stream) {
   const size_t smem_bytes = 1024 + (size_t)IG_STAGES * IG_STAGE_BYTES + IG_OUT_STAGE_BYTES + 256;
   p.tstore = (a->odt == TGAN_BF16 && a->ldo % 8 == 0 && ((uintptr_t)a->out & 15) == 0) ? 1 : 0;
   { const char* e = getenv("TGAN_IGEMM_NO_TSTORE"); if (e && atoi(e)) p.tstore = 0; }
+
+  p.bias_seg = a->bias_seg ? 1 : 0;
+  p.clsum = reinterpret_cast<long long*>(a->clsum);
+  p.mask_out = reinterpret_cast<uint32_t*>(a->mask_out);
+  p.mask_in = reinterpret_cast<const uint32_t*>(a->mask_in);
+  p.mask_alpha = a->mask_alpha;
+  const bool fused = p.bias_seg || p.clsum || p.mask_out || p.mask_in;
+  if (fused) {
+    TGAN_CHECK_ARG(p.nb == 1 && (p.tiles_x == 1 || a->gh == 1) && a->ncls <= 1 && p.osy == 1 && p.osx == 1 && p.ooy == 0 &&
+                       p.oox == 0 && p.vh == a->gh && p.vw == a->gw && a->OH == a->gh && a->OW == a->gw,
+                   "igemm: fused mean-only-BN epilogue needs linear output pixels (full-width tiles of one image or a flat GEMM)");
+    TGAN_CHECK_ARG(!p.bias_seg || a->bias, "igemm: bias_seg without bias");
+    TGAN_CHECK_ARG((!p.clsum && !p.mask_out) || p.tstore, "igemm: class sums / masks need the bf16 TMA-store epilogue");
+    if (p.clsum) {
+      TGAN_CHECK_ARG((a->cls_w == 16 || a->cls_w == 32) && a->cls_h >= 2 && (a->cls_h & (a->cls_h - 1)) == 0,
+                     "igemm: class sums need cls_w in {16, 32} and a power-of-two cls_h");
+      p.cls_lw = a->cls_w == 32 ? 5 : 4;
+      p.cls_lh = 0; while ((1 << p.cls_lh) < a->cls_h) ++p.cls_lh;
+    }
+    if (p.segflat)
+      for (int i = 0; i + 1 < a->nseg; ++i)
+        TGAN_CHECK_ARG(a->seg_end[i] % 256 == 0, "igemm: flat segments must end on multiples of 256 pixels for the fused epilogue");
+  }
 
   p.ncls = a->ncls > 1 ? a->ncls : 1;
   if (a->ncls > 1) {

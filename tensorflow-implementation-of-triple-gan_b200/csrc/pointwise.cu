@@ -607,7 +607,7 @@ __global__ void mobn_pool_dropout_fwd_kernel(const bf16* __restrict__ z, bf16* _
                                              int rows_per_img, const float* __restrict__ b, float* __restrict__ pop_mean,
                                              float decay, int train, float alpha, float rate, float scale,
                                              const uint8_t* __restrict__ mask, uint64_t seed, uint64_t stream_id,
-                                             const uint64_t* __restrict__ counter) {
+                                             const uint64_t* __restrict__ counter, long long* __restrict__ clsum) {
   pdl_entry();
   if (train && pop_mean && blockIdx.x == 0) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -615,6 +615,14 @@ __global__ void mobn_pool_dropout_fwd_kernel(const bf16* __restrict__ z, bf16* _
       for (int s = 0; s < sg.n; ++s) pm = pm * decay + seg_sum(sums, q24, (int64_t)s * C + c) * sg.inv_rows[s] * (1.f - decay);
       pop_mean[c] = pm;
     }
+  }
+  // optional border-class sums of the pooled output (Q24 integers in shared memory, then one global atomic per touched
+  // (class, channel)): the next convolution's batch mean is a linear function of them (csrc/mobn_fused.cu).  The host
+  // guarantees that a CTA's 256 threads lie inside one image (hence one batch segment).
+  extern __shared__ unsigned long long pool_cls[];      // [9][C]
+  if (clsum) {
+    for (int k = threadIdx.x; k < 9 * C; k += blockDim.x) pool_cls[k] = 0ull;
+    __syncthreads();
   }
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nvec) return;
@@ -674,6 +682,18 @@ __global__ void mobn_pool_dropout_fwd_kernel(const bf16* __restrict__ z, bf16* _
   cw.x = cd[0] | (cd[1] << 8) | (cd[2] << 16) | ((uint32_t)cd[3] << 24);
   cw.y = cd[4] | (cd[5] << 8) | (cd[6] << 16) | ((uint32_t)cd[7] << 24);
   *reinterpret_cast<uint2*>(code + e) = cw;
+  if (clsum) {
+    const int k = (ho == 0 ? 0 : ho == Ho - 1 ? 2 : 1) * 3 + (wo == 0 ? 0 : wo == Wo - 1 ? 2 : 1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float vr = __bfloat162float(__float2bfloat16_rn(o[j]));      // the value as stored
+      if (vr != 0.f) atomicAdd(&pool_cls[k * C + c + j], (unsigned long long)__float2ll_rn(vr * 16777216.f));
+    }
+    __syncthreads();      // (every thread of the CTA is alive here: nvec is a multiple of the CTA size when clsum is set)
+    for (int q = threadIdx.x; q < 9 * C; q += blockDim.x)
+      if (pool_cls[q] != 0ull)
+        atomicAdd(reinterpret_cast<unsigned long long*>(&clsum[(int64_t)s * 9 * C + q]), pool_cls[q]);
+  }
 }
 
 // backward of the fused pass: du (full resolution) = winner ? keep * dy/(1-rate) * act'(y_winner) : 0, with per-segment
@@ -1279,7 +1299,7 @@ extern "C" int tgan_mobn_pool_dropout_fwd(const void* z, void* y, uint8_t* code,
                                           const float* b, float* pop_mean, float decay, int train, int act, float alpha,
                                           float rate,
                                           const uint8_t* mask, uint64_t seed, uint64_t stream_id, const uint64_t* counter,
-                                          void* stream) {
+                                          void* clsum, void* stream) {
   TGAN_CHECK_ARG(z && y && code && b && H % 2 == 0 && W % 2 == 0 && C % 8 == 0 && rate >= 0.f && rate < 1.f &&
                      aligned16(z) && aligned16(y) && aligned16(b) && ((uintptr_t)code & 7) == 0,
                  "mobn_pool_dropout_fwd: bf16, even extents, C %% 8 == 0, aligned buffers");
@@ -1292,9 +1312,12 @@ extern "C" int tgan_mobn_pool_dropout_fwd(const void* z, void* y, uint8_t* code,
   if (make_segs(sg, (int64_t)N * rpi, nseg, n0 * rpi, n1 * rpi, n2 * rpi)) return 1;
   const int64_t nvec = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
   cudaStream_t st = (cudaStream_t)stream;
-  TGAN_DISPATCH_ACT(act, A, (pdl_launch(mobn_pool_dropout_fwd_kernel<A>, ceil_div(nvec, 256), 256, 0, st, (const bf16*)z,
+  TGAN_CHECK_ARG(!clsum || ((int64_t)(H / 2) * (W / 2) * (C / 8)) % 256 == 0,
+                 "mobn_pool_dropout_fwd: class sums need whole CTAs per image ((H/2)*(W/2)*(C/8) %% 256 == 0)");
+  const size_t smem = clsum ? (size_t)9 * C * sizeof(unsigned long long) : 0;
+  TGAN_DISPATCH_ACT(act, A, (pdl_launch(mobn_pool_dropout_fwd_kernel<A>, ceil_div(nvec, 256), 256, smem, st, (const bf16*)z,
                                         (bf16*)y, code, H, W, C, nvec, sums, sums_q24, sg, rpi, b, pop_mean, decay, train, alpha, rate,
-                                        1.0f / (1.0f - rate), mask, seed, stream_id, counter)));
+                                        1.0f / (1.0f - rate), mask, seed, stream_id, counter, (long long*)clsum)));
   TGAN_LAUNCHED();
   return 0;
 }

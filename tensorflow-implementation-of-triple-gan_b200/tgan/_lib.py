@@ -52,7 +52,9 @@ class TganIgemmArgs(ctypes.Structure):
                 ('vw', ctypes.c_int), ('bias', ctypes.c_void_p), ('colsum', ctypes.c_void_p), ('nseg', ctypes.c_int), ('seg_end', ctypes.c_int * 4),
                 ('act', ctypes.c_int),
                 ('alpha', ctypes.c_float), ('ncls', ctypes.c_int), ('cls_T', ctypes.c_int * 4),
-                ('cls_ooy', ctypes.c_int * 4), ('cls_oox', ctypes.c_int * 4)]
+                ('cls_ooy', ctypes.c_int * 4), ('cls_oox', ctypes.c_int * 4),
+                ('bias_seg', ctypes.c_int), ('clsum', ctypes.c_void_p), ('cls_h', ctypes.c_int), ('cls_w', ctypes.c_int),
+                ('mask_out', ctypes.c_void_p), ('mask_in', ctypes.c_void_p), ('mask_alpha', ctypes.c_float)]
 
 
 class TganWgradArgs(ctypes.Structure):

@@ -231,6 +231,9 @@ def no_grad():
 def add_grad(v, g):
     """Accumulate gradient tensor g into Var v."""
     from . import ops
+    if v.grad is not None and v.aux and v.aux.get('du_ready') and not getattr(g, '_tgan_du', False):
+        # (a consumer already delivered dy * lrelu'(y) for this tensor; a plain dy must not be mixed into it)
+        raise RuntimeError('add_grad: a plain gradient meets a leaky-ReLU-fused one on the same tensor')
     if v.grad is None:
         v.grad = g
     else:

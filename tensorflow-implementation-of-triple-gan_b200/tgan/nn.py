@@ -234,13 +234,14 @@ def conv2d_WN(x, num_filters, filter_size=[3, 3], pad='SAME', stride=[1, 1], non
                 z = ops.conv2d(x, ops.WNWeight(V, _tmp_param(np.ones(num_filters)), A, num_filters, 1, 1), kh, kw,
                                stride[0], pad)
                 return _data_init(z, init_scale, 1e-08, nonlinearity)
-            z = ops.conv2d(x, ops.WNWeight(V, g, A, num_filters, 1, 1), kh, kw, stride[0], pad,
-                           colsum=bool(use_mean_only_batch_normalization))
             if use_mean_only_batch_normalization:
                 fa = _fused(nonlinearity)
-                if fa is not None:
-                    return ops.mobn_act(z, b, pop_mean, not deterministic, fa[0], fa[1])
+                if fa is not None:      # conv + mean-only BN + nonlinearity as one unit (ops.conv2d_mobn)
+                    return ops.conv2d_mobn(x, ops.WNWeight(V, g, A, num_filters, 1, 1), kh, kw, stride[0], pad, b, pop_mean,
+                                           not deterministic, fa[0], fa[1])
+                z = ops.conv2d(x, ops.WNWeight(V, g, A, num_filters, 1, 1), kh, kw, stride[0], pad, colsum=True)
                 return nonlinearity(ops.mobn_act(z, b, pop_mean, not deterministic))
+            z = ops.conv2d(x, ops.WNWeight(V, g, A, num_filters, 1, 1), kh, kw, stride[0], pad)
             return _finish(z, b, nonlinearity)
         z = ops.conv2d(x, ops.PlainWeight(V), kh, kw, stride[0], pad)
         if use_batch_normalization:

@@ -694,6 +694,10 @@ def mobn_act(z, b, pop_mean, train, act='none', alpha=0.2, decay=0.9):
         iends = [sum(segs[:i + 1]) for i in range(len(segs) - 1)] + [0, 0, 0]       # segment ends in images
         y, code = _new(pout.shape, torch.bfloat16), _new(pout.shape, torch.uint8)
         sums = (cs_all if cs_all is not None else seg_stats()) if train else None
+        # border-class sums of the pooled output: the next convolution's fused mean-only BN reads them (conv2d_mobn)
+        clo = None
+        if train and ((H // 2) * (W // 2) * (C // 8)) % 256 == 0 and not os.environ.get('TGAN_NO_MOBN_FUSION'):
+            clo = arena_take(2 * 9 * C * len(segs))
         rng = ctx.rng
         mask, seed, sid, ctr = None, 0, 0, None
         if rate > 0 and rng.injected:
@@ -702,8 +706,10 @@ def mobn_act(z, b, pop_mean, train, act='none', alpha=0.2, decay=0.9):
             seed, sid, ctr = rng.seed, rng.stream_id(str(tag)), rng.counter()
         _lib.call('tgan_mobn_pool_dropout_fwd', _p(zd), _p(y), _p(code), N, H, W, C, len(segs), iends[0], iends[1], iends[2],
                   _p(sums), 1 if cs_all is not None else 0, _p(b.data), _p(pop_mean.data), decay, 1 if train else 0, a, alpha,
-                  float(rate), _p(mask), seed, sid, _p(ctr), _st())
+                  float(rate), _p(mask), seed, sid, _p(ctr), _p(clo), _st())
         pout._data, pout._lazy = y, None
+        if clo is not None:
+            pout.aux = dict(pout.aux or {}, cls=clo)
         out._lazy = None                 # consumed: the full-resolution activation does not exist
         if pout.requires_grad and tape is not None:
             def bwd():
@@ -719,6 +725,105 @@ def mobn_act(z, b, pop_mean, train, act='none', alpha=0.2, decay=0.9):
                         _lib.call('tgan_sub_channel_mean_seg', _p(du), _p(du), rows, C, len(segs), ends[0], ends[1], ends[2],
                                   _p(cs), _st())
                     add_grad(z, du)
+            tape.nodes.append(bwd)
+
+    out._lazy = MobnDeferred(run_plain, run_pooled)
+    return out
+
+
+def conv2d_mobn(x, w, kh, kw, stride, padding, b, pop_mean, train, act='none', alpha=0.2, decay=0.9):
+    """tf.nn.conv2d + mean_only_batch_norm_impl + nonlinearity of nn.conv2d_WN (nn.py:504-518) as ONE unit.
+
+    Tensor-core mode, training, 3x3 / stride 1 / SAME + leaky ReLU on 16- or 32-pixel-wide images (conv1_1, conv1_2,
+    conv2_1, conv2_2 of the CIFAR-10 classifier): the batch mean of the convolution output is a linear function of
+    border-class sums of its INPUT, which the producer of x emitted (GEMM epilogue / pooling kernel / tgan_class_sums);
+    tgan_mobn_mean_from_sums turns them into the per-segment bias b - mean BEFORE the contraction runs, whose epilogue
+    then applies `- mean + b`, the leaky ReLU, the bf16 store, the class sums for the NEXT layer and a 1-bit-per-element
+    mask of the leaky-ReLU side.  No separate pass over the activation in forward; in backward the consumer's
+    input-gradient epilogue applies lrelu' through the mask and accumulates the per-segment sums of du
+    (tc.conv_bwd), so the activation-backward pass disappears as well.  When a 2x2 max pool follows (conv1_3, conv2_3)
+    the one-pass pooled apply of mobn_act is used instead.  Everything else takes conv2d(colsum) + mobn_act."""
+    def legacy():
+        return mobn_act(conv2d(x, w, kh, kw, stride, padding, colsum=True), b, pop_mean, train, act, alpha, decay)
+
+    if (ctx.building or ctx.math != 'bf16' or not train or act != 'lrelu' or abs(alpha - 0.2) > 1e-12 or kh != 3 or kw != 3
+            or stride != 1 or padding.upper() != 'SAME' or len(x.shape) != 4 or os.environ.get('TGAN_NO_MOBN_FUSION')):
+        return legacy()
+    N, H, W = x.shape[0], x.shape[1], x.shape[2]
+    C, Cout = x.C, w.key.shape[-1]
+    segs = _segs(x) or [N]
+    if not (W in (16, 32) and H >= 2 and H & (H - 1) == 0 and (H * W) % 256 == 0 and len(segs) <= 4 and Cout >= 64
+            and 2048 % Cout == 0 and x.ld == C and (C <= 16 or C % 8 == 0)):
+        return legacy()
+    nseg = len(segs)
+    rows, rps = N * H * W, H * W
+    rg = _on() and (x.requires_grad or w.requires_grad or b.requires_grad)
+    out = _prop(Var(None, (N, H, W, Cout), requires_grad=rg), x)
+    tape = ctx.tape
+    geom = dict(N=N, H=H, W=W, C=C, kh=3, kw=3, s=1, pt=1, pl=1, Ho=H, Wo=W, Cout=Cout)
+    ends_img = [sum(segs[:i + 1]) for i in range(nseg - 1)] + [0, 0, 0]
+    ends = [e * rps for e in ends_img]
+
+    def forward_to(y):
+        """`out` stands for y (the two-kernel path computed it): share the tensor, route the gradient"""
+        out._data, out.ld, out._lazy = y.data, y.ld, None
+        out.aux = dict(y.aux or {}, **{k: v for k, v in (out.aux or {}).items() if k == 'segs'})
+        if out.requires_grad and tape is not None and y.requires_grad:
+            def bwd():
+                if out.grad is not None:
+                    add_grad(y, out.grad)
+            tape.nodes.append(bwd)
+
+    def run_pooled(pout, rate, tag):
+        y = legacy()      # (the eligibility test above implies mobn_act's own pooled form exists for this geometry)
+        assert y._data is None and isinstance(y._lazy, MobnDeferred)
+        y._lazy.run_pooled(pout, rate, tag)
+        out._lazy = None
+
+    def run_plain():
+        from . import tc
+        xd = x.data                                   # materialises the producer; its class sums are in x.aux now
+        cls = (x.aux or {}).get('cls')
+        if cls is None and C <= 16:                   # the network input: sums by a small kernel of its own
+            cls = arena_take(2 * 9 * C * nseg)
+            se = (ctypes.c_int * 3)(*ends_img[:3])
+            _lib.call('tgan_class_sums', _p(xd), dt_code(xd), N, H, W, C, x.ld, nseg, se, _p(cls), _st())
+        if cls is None or not tc.conv_eligible(geom, x):
+            forward_to(legacy())
+            return
+        wp, Kpad, w_ts, w_cs = tc.fprop_operand(w, geom)
+        shift = _new((4 * Cout,), torch.float32)
+        cnt = (ctypes.c_int64 * nseg)(*[n * rps for n in segs])
+        _lib.call('tgan_mobn_mean_from_sums', _p(cls), nseg, cnt, _p(wp), 9, Cout, C, w_ts, w_cs, _p(b.data),
+                  _p(pop_mean.data), decay, _p(shift), _st())
+        clo = arena_take(2 * 9 * Cout * nseg)
+        need_mask = out.requires_grad and tape is not None
+        mask = _new((rows // 32, Cout), torch.int32) if need_mask else None
+        y = tc.conv_fwd(x, w, geom, None, segs, bias=shift, act=ACT['lrelu'],
+                        fused=dict(bias_seg=True, clsum=clo, cls_hw=(H, W), mask_out=mask))
+        out._data, out.ld, out._lazy = y.view(N, H, W, Cout), Cout, None
+        out.aux = dict(out.aux or {}, cls=clo)
+        if need_mask:
+            out.aux.update(mask=mask, mask_alpha=alpha)
+
+            def bwd():
+                if out.grad is None:
+                    return
+                cs = _new((4, Cout), torch.float32)
+                if out.aux.get('du_ready'):           # the consumer's input-gradient epilogue already applied lrelu'
+                    du = out.grad
+                    _lib.call('tgan_seg_sums_finalize', _p(out.aux['du_q24']), nseg, Cout, _p(cs),
+                              _p(b.grad) if b.requires_grad else None, _st())
+                else:
+                    dy = _cast(out.grad, torch.bfloat16)
+                    du = _new(out.shape, torch.bfloat16)
+                    _lib.call('tgan_act_bwd_seg', _p(dy), BF16, _p(y), BF16, _p(du), BF16, rows, Cout, nseg, ends[0],
+                              ends[1], ends[2], ACT['lrelu'], alpha, _p(cs), _p(b.grad) if b.requires_grad else None,
+                              _p(ctx.ws()), _st())
+                if x.requires_grad or w.requires_grad:
+                    _lib.call('tgan_sub_channel_mean_seg', _p(du), _p(du), rows, Cout, nseg, ends[0], ends[1], ends[2], _p(cs),
+                              _st())
+                    tc.conv_bwd(x, w, geom, du)
             tape.nodes.append(bwd)
 
     out._lazy = MobnDeferred(run_plain, run_pooled)

@@ -70,7 +70,7 @@ def _pack(w, key, T, Nrows, K, st, sn, sk, taps=None):
 
 
 def _igemm(x, N, H, W, C, ldx, wp, Kpad, taps, Nout, gh, gw, out, OH, OW, ldo, s=1, os_=1, oo=(0, 0), vh=0, vw=0,
-           colsum=None, segs=None, bias=None, act=0, classes=None):
+           colsum=None, segs=None, bias=None, act=0, classes=None, fused=None):
     a = _lib.TganIgemmArgs()
     a.x, a.N, a.H, a.W, a.C, a.ldx = x.data_ptr(), N, H, W, C, ldx
     a.wp, a.T, a.Nout, a.Kpad = wp.data_ptr(), len(taps), Nout, Kpad
@@ -90,6 +90,14 @@ def _igemm(x, N, H, W, C, ldx, wp, Kpad, taps, Nout, gh, gw, out, OH, OW, ldo, s
         for i, n in enumerate(segs[:-1]):
             e += n
             a.seg_end[i] = e
+    if fused:      # mean-only BN fused into the epilogue (csrc/mobn_fused.cu): per-segment bias, class sums, lrelu masks
+        a.bias_seg = 1 if fused.get('bias_seg') else 0
+        if fused.get('clsum') is not None:
+            a.clsum, a.cls_h, a.cls_w = fused['clsum'].data_ptr(), fused['cls_hw'][0], fused['cls_hw'][1]
+        if fused.get('mask_out') is not None:
+            a.mask_out = fused['mask_out'].data_ptr()
+        if fused.get('mask_in') is not None:
+            a.mask_in, a.mask_alpha = fused['mask_in'].data_ptr(), fused.get('mask_alpha', 0.2)
     _lib.call('tgan_igemm_bf16', ctypes.byref(a), _st())
 
 
@@ -141,7 +149,17 @@ def _im2col(x, g):
     return col, K, Kc
 
 
-def conv_fwd(x, w, g, colsum=None, segs=None, bias=None, act=0, ldo=None):
+def fprop_operand(w, g):
+    """-> (packed bf16 fprop weights, Kpad, tap stride, channel stride) of the operand conv_fwd reads"""
+    C, Cout, kh, kw = g['C'], g['Cout'], g['kh'], g['kw']
+    if _small_cin(g):
+        wp, Kpad = _pack(w, 'fprop_col', 1, Cout, kh * kw * C, 0, 1, Cout)
+        return wp, Kpad, C, Kpad
+    wp, Kpad = _pack(w, 'fprop', kh * kw, Cout, C, C * Cout, 1, Cout)
+    return wp, Kpad, Cout * Kpad, Kpad
+
+
+def conv_fwd(x, w, g, colsum=None, segs=None, bias=None, act=0, ldo=None, fused=None):
     """-> bf16 [rows, ldo] with act(conv + bias) in channels [0, Cout) (ldo > Cout: the rest is left untouched)"""
     gf = _flat(g)
     C, Cout, kh, kw = g['C'], g['Cout'], g['kh'], g['kw']
@@ -156,7 +174,7 @@ def conv_fwd(x, w, g, colsum=None, segs=None, bias=None, act=0, ldo=None):
         if segs:
             segs = [n * (rows // sum(segs)) for n in segs]
         _igemm(col, 1, 1, rows, K, Kc, wp, Kpad, [(0, 0)], Cout, 1, rows, z, 1, rows, ldo, colsum=colsum, segs=segs,
-               bias=bias, act=act)
+               bias=bias, act=act, fused=fused)
         return z
     xd, ld = _bf16_padded(x.data, x.rows, C, x.ld)
     g['_x'] = (xd, ld)
@@ -168,7 +186,7 @@ def conv_fwd(x, w, g, colsum=None, segs=None, bias=None, act=0, ldo=None):
         rps = (g['N'] * g['Ho'] * g['Wo']) // sum(segs)
         segs = [n * rps for n in segs]
     _igemm(xd, gf['N'], gf['H'], gf['W'], C, ld, wp, Kpad, taps, Cout, gf['Ho'], gf['Wo'], z, gf['Ho'], gf['Wo'], ldo,
-           s=g['s'], colsum=colsum, segs=segs, bias=bias, act=act)
+           s=g['s'], colsum=colsum, segs=segs, bias=bias, act=act, fused=fused)
     return z
 
 
@@ -223,8 +241,20 @@ def conv_bwd(x, w, g, dz):
         if s == 1:
             wp, Kpad = _pack(w, ('dgrad', Cg), kh * kw, Cg, Cout, C * Cout, Cout, 1)
             taps = [(pt - r, pl - c) for r in range(kh) for c in range(kw)]
-            _igemm(dzb, gf['N'], gf['Ho'], gf['Wo'], Cout, Cout, wp, Kpad, taps, Cg, gf['H'], gf['W'], dx, gf['H'],
-                   gf['W'], Cs if staged else Cg)
+            # the producer of x was a fused mean-only-BN layer: its leaky-ReLU derivative (1-bit mask written by its forward
+            # epilogue) and the per-segment sums of du = dy * lrelu'(y) are applied / accumulated in THIS epilogue
+            mk = tgt.aux.get('mask') if (tgt.aux and tgt is x and gf is g and not staged and kh * kw == 9) else None
+            if mk is not None and (tgt.grad is None or tgt.aux.get('du_ready')):
+                sg = tgt.aux.get('segs') or [g['N']]
+                if tgt.aux.get('du_q24') is None:
+                    tgt.aux['du_q24'] = _ops().arena_take(2 * Cg * len(sg))
+                tgt.aux['du_ready'] = True
+                dx._tgan_du = True
+                _igemm(dzb, g['N'], g['Ho'], g['Wo'], Cout, Cout, wp, Kpad, taps, Cg, g['H'], g['W'], dx, g['H'], g['W'], Cg,
+                       colsum=tgt.aux['du_q24'], segs=sg, fused=dict(mask_in=mk, mask_alpha=tgt.aux.get('mask_alpha', 0.2)))
+            else:
+                _igemm(dzb, gf['N'], gf['Ho'], gf['Wo'], Cout, Cout, wp, Kpad, taps, Cg, gf['H'], gf['W'], dx, gf['H'],
+                       gf['W'], Cs if staged else Cg)
         else:
             # input-gradient of a stride-2 conv = transposed conv: its output-parity classes, heaviest first, in ONE launch
             cl = []

@@ -310,3 +310,107 @@ def test_dropout_and_batchnorm_write_into_the_concat():
     assert relerr(got, ref.detach().numpy()) < 6e-3
     assert relerr(tnp(xv.grad), xt.grad.numpy()) < 1e-2
     assert relerr(tnp(pg.grad), gt.grad.numpy()) < 1e-2 and relerr(tnp(pb.grad), bt.grad.numpy()) < 1e-2
+
+
+def _wn_layer_params(rng, name, cin, cout):
+    return {name + '/V': rng.standard_normal((3, 3, cin, cout)) * 0.05, name + '/g': rng.uniform(0.7, 1.3, cout),
+            name + '/b': rng.standard_normal(cout) * 0.1}, {name + '/meanOnlyBatchNormalization/pop_mean': rng.standard_normal(cout) * 0.1}
+
+
+@pytest.mark.parametrize('segs', [[2, 1, 3], [4]])
+@pytest.mark.parametrize('fusion', [True, False])
+def test_mobn_fused_into_gemm_epilogue_chain(segs, fusion):
+    """The CIFAR-10 classifier's head chain conv1_1 -> conv1_2 -> conv1_3 -> max pool -> dropout -> conv2_1 -> conv2_2
+    (nn.conv2d_WN, Good_GAN_cifar10.py:106-131) on a grouped batch, training mode: with mean-only batch norm FUSED
+    into the GEMM epilogues (batch mean from border-class input sums, lrelu mask, input-gradient epilogue applying
+    lrelu') and with the two-kernel path (TGAN_NO_MOBN_FUSION) -- both against the float64 oracle with the same bf16
+    rounding points, forward value, pop_mean of every layer and every parameter gradient."""
+    from tgan import core, nn, ops
+    old = os.environ.pop('TGAN_NO_MOBN_FUSION', None)
+    if not fusion:
+        os.environ['TGAN_NO_MOBN_FUSION'] = '1'
+    try:
+        rng = np.random.default_rng(21)
+        N = sum(segs)
+        chans = [('conv1_1', 3, 128), ('conv1_2', 128, 128), ('conv1_3', 128, 128), ('conv2_1', 128, 256), ('conv2_2', 256, 256)]
+        Pn, Sn = {}, {}
+        for n, ci, co in chans:
+            p_, s_ = _wn_layer_params(rng, 'classifier/' + n, ci, co)
+            Pn.update(p_)
+            Sn.update(s_)
+        x = bf(rng.standard_normal((N, 32, 32, 3)))
+        keep = (rng.uniform(size=(N, 16, 16, 128)) >= 0.5).astype(np.uint8)
+        R = bf(rng.standard_normal((N, 16, 16, 256)))
+        fused = lambda n: fusion and n in ('conv1_1', 'conv1_2', 'conv2_1', 'conv2_2')
+
+        def oracle_net(P, S, xt):
+            outs, o = [], 0
+            for ns in segs:                      # one call per segment, in call order (pop_mean chain)
+                h = xt[o:o + ns]
+                for n in ('conv1_1', 'conv1_2', 'conv1_3'):
+                    h = O.conv2d_WN(P, S, 'classifier/' + n, h, 'SAME', True, fused=fused(n))
+                h = O.dropout_tf(O.max_pool_tf(h, 2, 2), torch.tensor(keep[o:o + ns]), 0.5)
+                for n in ('conv2_1', 'conv2_2'):
+                    h = O.conv2d_WN(P, S, 'classifier/' + n, h, 'SAME', True, fused=fused(n))
+                outs.append(h)
+                o += ns
+            return torch.cat(outs, 0)
+        P = {k: T(v, True) for k, v in Pn.items()}
+        S = {k: T(v) for k, v in Sn.items()}
+        with O.quantized():
+            yt = oracle_net(P, S, T(x))
+            (yt * T(R)).sum().backward()
+        # CUDA
+        store = core.ctx.store
+        prm = {}
+        for k, v in list(Pn.items()) + list(Sn.items()):
+            parts = k.split('/')
+            import contextlib
+            with contextlib.ExitStack() as st:
+                for s_ in parts[:-1]:
+                    st.enter_context(core.variable_scope(s_))
+                p = core.get_variable(parts[-1], list(np.shape(v)), core.constant_initializer(0.0), trainable=k in Pn)
+            p.data = torch.from_numpy(np.asarray(v, np.float32).copy()).cuda()
+            p.grad = torch.zeros_like(p.data)
+            p.requires_grad = k in Pn
+            prm[k] = p
+        store.bump()
+        store.reuse[0] = True
+
+        class FixedMask:
+            injected = True
+
+            def keep_mask(self, tag, shape, rate):
+                return torch.from_numpy(keep).cuda()
+        core.ctx.rng = FixedMask()
+        lrelu = nn.leaky_relu
+        kw = dict(init=False, use_weight_normalization=True, use_mean_only_batch_normalization=True, deterministic=False)
+        ops.arena_reset()
+        with core.recording(), core.variable_scope('classifier', reuse=True):
+            xv = ops.Var(dev(x), x.shape)
+            if len(segs) > 1:
+                xv.aux = {'segs': list(segs)}
+            h = xv
+            for n, _, co in chans[:3]:
+                h = nn.conv2d_WN(h, num_filters=co, name=n, nonlinearity=lrelu, **kw)
+            h = ops.dropout(ops.max_pool2(h), 0.5, 'T/drop1')
+            for n, _, co in chans[3:]:
+                h = nn.conv2d_WN(h, num_filters=co, name=n, nonlinearity=lrelu, **kw)
+            fwd = tnp(h.data)
+            if fusion:
+                assert h.aux.get('mask') is not None and h.aux.get('cls') is not None      # proves the fused route ran
+            run_bwd(h, R)
+        assert relerr(fwd, yt.detach().numpy()) < 2e-2
+        for k in Sn:
+            assert relerr(tnp(prm[k].data), S[k].numpy()) < 5e-3, k
+        gscale = max(float(P[k].grad.abs().max()) for k in Pn)
+        for k in Pn:
+            ref = P[k].grad.numpy()
+            den = max(np.abs(ref).max(), 1e-2 * gscale)
+            e = np.abs(tnp(prm[k].grad) - ref).max() / den
+            print(fusion, segs, k, '%.3e' % e)
+            assert e < 6e-2, (k, e)
+    finally:
+        os.environ.pop('TGAN_NO_MOBN_FUSION', None)
+        if old is not None:
+            os.environ['TGAN_NO_MOBN_FUSION'] = old

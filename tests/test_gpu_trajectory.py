@@ -2,7 +2,8 @@
 Training/Train_goodGAN.py:230-278 from identical weights, inputs, noise and dropout masks, lambda_1 in {0, 0.3},
 lambda_2 in {0, 0.5}, in both math modes, against the float64 oracle.
 
-What can be asserted.  Step 0 is an exact single-step comparison (2e-5 fp32 / 2e-2 bf16).  From step 1 on the
+What can be asserted.  Step 0 is an exact single-step comparison (2e-5 fp32 / 2e-2 bf16, or 4x the error the
+oracle itself shows at that precision: c_loss in float32 carries ~5e-5).  From step 1 on the
 trajectories of ANY two arithmetics decorrelate: Adam's early updates are sign-like, so rounding noise on
 barely-resolved gradient elements moves weights by +-lr, and the reference's own float32 arithmetic leaves its
 float64 trajectory by 1e-2 ... 1e-1 within a few iterations (measured below, not assumed).  The band is therefore
@@ -86,8 +87,10 @@ def test_loss_trajectory_20_steps(math):
     for lam in LAMBDAS:
         ref0 = orc[('f64', lam)][0]
         e0 = np.abs(dev_c[lam][0]) / np.maximum(1.0, np.abs(ref0))
+        f0 = np.abs(dev_o[lam][0]) / np.maximum(1.0, np.abs(ref0))      # the oracle's own error at this precision
         rep['%s step0 rel.err' % (lam,)] = e0.tolist()
-        assert (e0 < STEP0_TOL[math]).all(), (lam, mine[lam][0], ref0)
+        rep['%s step0 oracle floor' % (lam,)] = f0.tolist()
+        assert (e0 < np.maximum(STEP0_TOL[math], 4 * f0)).all(), (lam, mine[lam][0], ref0, f0)
         assert np.isfinite(mine[lam]).all()
     rms = lambda d: np.sqrt(np.mean(np.concatenate([d[lam][1:] for lam in LAMBDAS]) ** 2, axis=0))
     mx = lambda d: np.max(np.abs(np.concatenate([d[lam][1:] for lam in LAMBDAS])), axis=0)
