@@ -336,6 +336,9 @@ int tgan_copy_channels(const void* src, int sdt, int lds, void* dst, int ddt, in
  * :264-270 run as one pass) formed by ONE launch */
 int tgan_gather_rows(const void* const* srcs, const int* dts, const int64_t* counts, int n, void* dst, int ddt,
                      void* stream);
+/* y[i] = sum_p x[p][i] over `parts` contiguous bf16 slices of n elements (n % 8 == 0): folds the split-K partial outputs
+ * of a contraction whose tap groups ran as output classes of one tgan_igemm_bf16 launch */
+int tgan_sum_slices_bf16(const void* x, void* y, int64_t n, int parts, void* stream);
 /* y (+)= x elementwise (gradient accumulation), fp32 or bf16 */
 int tgan_accumulate(void* y, const void* x, int dt, int64_t n, void* stream);
 int tgan_fill_f32(float* p, float v, int64_t n, void* stream);

@@ -998,6 +998,21 @@ __global__ void gather_rows_kernel(const __grid_constant__ GatherSrcs g, TD* __r
     stf<TD>(dst, i, v);
   }
 }
+// y = sum of `parts` bf16 slices laid out back to back ([parts][n]): the split-K partial outputs of one contraction
+// (tap groups run as output classes of ONE igemm launch, tgan/tc.py), 16-byte accesses, fp32 sum in a fixed order
+__global__ void sum_slices_bf16_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int64_t nvec, int parts) {
+  pdl_entry();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int p = 0; p < parts; ++p) {
+      float v[8];
+      ld8(x, ((int64_t)p * nvec + i) * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+    st8(y, i * 8, acc);
+  }
+}
 template <typename T>
 __global__ void accumulate_kernel(T* __restrict__ y, const T* __restrict__ x, int64_t n) {
   pdl_entry();
@@ -1440,6 +1455,12 @@ extern "C" int tgan_gather_rows(const void* const* srcs, const int* dts, const i
   }
   g.n = n;
   TGAN_DISPATCH_1(ddt, TD, (pdl_launch(gather_rows_kernel<TD>, grid_for(tot), 256, 0, (cudaStream_t)stream, g, (TD*)dst, tot)));
+  TGAN_LAUNCHED();
+  return 0;
+}
+extern "C" int tgan_sum_slices_bf16(const void* x, void* y, int64_t n, int parts, void* stream) {
+  TGAN_CHECK_ARG(x && y && n > 0 && n % 8 == 0 && parts >= 1 && aligned16(x) && aligned16(y), "sum_slices_bf16: bad args");
+  pdl_launch(sum_slices_bf16_kernel, grid_for(n / 8), 256, 0, (cudaStream_t)stream, (const bf16*)x, (bf16*)y, n / 8, parts);
   TGAN_LAUNCHED();
   return 0;
 }

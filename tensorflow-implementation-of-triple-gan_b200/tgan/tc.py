@@ -372,8 +372,21 @@ def deconv_bwd(x, w, g, dy):
     if tgt.requires_grad:
         wp, Kpad = _pack(w, ('ddgrad', Cg), kh * kw, Cg, Cout, Cout * Cin, 1, Cin)
         dx = _new(tuple(x.shape[:-1]) + (Cg,), torch.bfloat16)
-        _igemm(dyb, g['N'], g['Ho'], g['Wo'], Cout, Cout, wp, Kpad, taps, Cg, g['h'], g['w'], dx, g['h'], g['w'], Cg,
-               s=2)
+        # few output tiles (4x4 / 8x8 images) x many taps (25): one CTA per tile would stream the whole 1.6 MB filter
+        # through a single SM.  Split K: the tap list is cut into up to 4 groups that run as OUTPUT CLASSES of the same
+        # launch, each writing its own bf16 partial slice (class offset = slice index * N * h rows), then one fold.
+        tiles = -(-(g['N'] * g['h'] * g['w']) // 256) * -(-Cg // 128)
+        parts = max(1, min(4, 148 // max(tiles, 1), len(taps) // 4))
+        if parts > 1 and Cg % 8 == 0 and (g['N'] * g['h'] * g['w'] * Cg) % 8 == 0:
+            per = -(-len(taps) // parts)
+            cl = [(min(per, len(taps) - i * per), i * g['N'] * g['h'], 0) for i in range(parts)]
+            part = _new((parts,) + tuple(x.shape[:-1]) + (Cg,), torch.bfloat16)
+            _igemm(dyb, g['N'], g['Ho'], g['Wo'], Cout, Cout, wp, Kpad, taps, Cg, g['h'], g['w'], part, g['h'], g['w'], Cg,
+                   s=2, classes=cl)
+            _lib.call('tgan_sum_slices_bf16', part.data_ptr(), dx.data_ptr(), dx.numel(), parts, _st())
+        else:
+            _igemm(dyb, g['N'], g['Ho'], g['Wo'], Cout, Cout, wp, Kpad, taps, Cg, g['h'], g['w'], dx, g['h'], g['w'], Cg,
+                   s=2)
         add_grad(tgt, dx if dx.dtype == tgt.data.dtype else dx.to(tgt.data.dtype))
     if par:
         _ops().join_side()
