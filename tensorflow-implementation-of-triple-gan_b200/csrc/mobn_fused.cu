@@ -18,7 +18,8 @@ namespace tgan {
 
 __device__ __forceinline__ float q24f(const long long* p, int64_t i) { return (float)((double)p[i] * (1.0 / 16777216.0)); }
 
-// one warp per output channel: mean over every segment, pop_mean chain in call order, shift[s][co] = b - mean
+// S_s[t][ci] (tap sums from the nine class sums) is staged in shared memory once per CTA; then one warp per output
+// channel reduces over (t, ci) for every segment, updates pop_mean in call order and writes shift[s][co] = b - mean.
 struct InvCount { float v[4]; };
 
 __global__ void __launch_bounds__(256) mobn_mean_kernel(const long long* __restrict__ clsum, int nseg, const InvCount inv_count,
@@ -26,24 +27,31 @@ __global__ void __launch_bounds__(256) mobn_mean_kernel(const long long* __restr
                                                         int64_t w_cs, const float* __restrict__ b, float* __restrict__ pop_mean,
                                                         float decay, float* __restrict__ shift) {
   pdl_entry();
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= Cout) return;
-  const int co = warp;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int t = 0; t < T; ++t) {
-    // 3x3 / stride 1 / SAME, taps row-major: tap row r reads input rows [r-1, H-2+r] -> r = 0 skips the last row class,
-    // r = 2 the first; same for columns.  T == 1 (1x1 / dense): everything.
+  extern __shared__ float S[];      // [nseg][T][Cin]
+  const int K = T * Cin;
+  for (int i = threadIdx.x; i < nseg * K; i += blockDim.x) {
+    const int s = i / K, k = i - s * K, t = k / Cin, ci = k - t * Cin;
+    // 3x3 / stride 1 / SAME, taps row-major: tap row r reads input rows [r-1, H-2+r] -> r = 0 never reads the LAST row
+    // class, r = 2 never the first; same for columns.  T == 1 (1x1 / dense): everything.
     const int r = T == 9 ? t / 3 : 1, c = T == 9 ? t % 3 : 1;
     const int rc0 = r == 2 ? 1 : 0, rc1 = r == 0 ? 1 : 2, cc0 = c == 2 ? 1 : 0, cc1 = c == 0 ? 1 : 2;
+    long long a = 0;
+    for (int rc = rc0; rc <= rc1; ++rc)
+      for (int cc = cc0; cc <= cc1; ++cc) a += clsum[((int64_t)s * 9 + rc * 3 + cc) * Cin + ci];
+    S[i] = (float)((double)a * (1.0 / 16777216.0));
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int co = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (co >= Cout) return;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int t = 0; t < T; ++t) {
     const bf16* wrow = wp + (int64_t)t * w_ts + (int64_t)co * w_cs;
     for (int ci = lane; ci < Cin; ci += 32) {
       const float w = __bfloat162float(wrow[ci]);
-      for (int s = 0; s < nseg; ++s) {
-        float S = 0.f;
-        for (int rc = rc0; rc <= rc1; ++rc)
-          for (int cc = cc0; cc <= cc1; ++cc) S += q24f(clsum, ((int64_t)s * 9 + rc * 3 + cc) * Cin + ci);
-        acc[s] += w * S;
-      }
+#pragma unroll
+      for (int s = 0; s < 4; ++s)
+        if (s < nseg) acc[s] += w * S[s * K + t * Cin + ci];
     }
   }
 #pragma unroll
@@ -61,24 +69,43 @@ __global__ void __launch_bounds__(256) mobn_mean_kernel(const long long* __restr
   }
 }
 
-struct ClsSegs { int end[4]; int n; float inv_count[4]; };
+struct ClsSegs { int end[4]; int n; };
 
-// border-class sums of a small-channel tensor (the classifier's 3-channel input): one CTA per image
+// border-class sums of a small-channel tensor (the classifier's 3-channel input), one CTA per image.  Interior pixels
+// (88 % of a 32x32 image) accumulate in registers and meet in a warp shuffle; border pixels and the per-warp interior
+// totals go through Q24 integer atomics in shared memory, so the result does not depend on the order of the adds.
 __global__ void __launch_bounds__(256) class_sums_kernel(const void* __restrict__ x, int xdt, int H, int W, int C, int ld,
                                                          ClsSegs sg, long long* __restrict__ clsum) {
   pdl_entry();
-  __shared__ unsigned long long part[9 * 16];      // Q24 integers: the sums do not depend on the order of the atomics
+  __shared__ unsigned long long part[9 * 16];
   for (int i = threadIdx.x; i < 9 * 16; i += blockDim.x) part[i] = 0ull;
   __syncthreads();
   const int n = blockIdx.x;
   const int s = (n >= sg.end[0]) + (n >= sg.end[1]) + (n >= sg.end[2]);
-  for (int i = threadIdx.x; i < H * W * C; i += blockDim.x) {
-    const int c = i % C, px = i / C, xx = px % W, yy = px / W;
-    const int64_t off = ((int64_t)n * H * W + px) * ld + c;
-    float v = xdt == TGAN_BF16 ? __bfloat162float(reinterpret_cast<const bf16*>(x)[off]) : reinterpret_cast<const float*>(x)[off];
-    v = __bfloat162float(__float2bfloat16_rn(v));      // the contraction reads the bf16-rounded value
-    const int rc = yy == 0 ? 0 : yy == H - 1 ? 2 : 1, cc = xx == 0 ? 0 : xx == W - 1 ? 2 : 1;
-    atomicAdd(&part[(rc * 3 + cc) * 16 + c], (unsigned long long)__float2ll_rn(v * 16777216.f));
+  float mid[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) mid[c] = 0.f;
+  for (int px = threadIdx.x; px < H * W; px += blockDim.x) {
+    const int xx = px % W, yy = px / W;
+    const int k = (yy == 0 ? 0 : yy == H - 1 ? 2 : 1) * 3 + (xx == 0 ? 0 : xx == W - 1 ? 2 : 1);
+    const int64_t off = ((int64_t)n * H * W + px) * ld;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      if (c >= C) break;
+      float v = xdt == TGAN_BF16 ? __bfloat162float(reinterpret_cast<const bf16*>(x)[off + c])
+                                 : reinterpret_cast<const float*>(x)[off + c];
+      v = __bfloat162float(__float2bfloat16_rn(v));      // the contraction reads the bf16-rounded value
+      if (k == 4) mid[c] += v;
+      else atomicAdd(&part[k * 16 + c], (unsigned long long)__float2ll_rn(v * 16777216.f));
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    if (c >= C) break;
+    float v = mid[c];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&part[4 * 16 + c], (unsigned long long)__float2ll_rn(v * 16777216.f));
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 9 * 16; i += blockDim.x) {
@@ -115,7 +142,9 @@ extern "C" int tgan_mobn_mean_from_sums(const void* clsum, int nseg, const int64
                      w_co_stride >= 1, "mobn_mean_from_sums: bad args");
   InvCount ic;      // by value in the kernel arguments: nothing to stage, CUDA-graph capturable
   for (int s = 0; s < 4; ++s) ic.v[s] = s < nseg ? (float)(1.0 / (double)count[s]) : 0.f;
-  pdl_launch(mobn_mean_kernel, ceil_div(Cout * 32, 256), 256, 0, (cudaStream_t)stream, (const long long*)clsum, nseg, ic,
+  const size_t smem = (size_t)nseg * T * Cin * sizeof(float);
+  TGAN_CHECK_ARG(smem <= 48 * 1024, "mobn_mean_from_sums: T * Cin * nseg too large (%d x %d x %d)", T, Cin, nseg);
+  pdl_launch(mobn_mean_kernel, ceil_div(Cout, 8), 256, smem, (cudaStream_t)stream, (const long long*)clsum, nseg, ic,
              (const bf16*)wp, T, Cout, Cin, w_tap_stride, w_co_stride, b, pop_mean, decay, shift);
   TGAN_LAUNCHED();
   return 0;

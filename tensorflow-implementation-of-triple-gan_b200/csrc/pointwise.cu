@@ -616,14 +616,11 @@ __global__ void mobn_pool_dropout_fwd_kernel(const bf16* __restrict__ z, bf16* _
       pop_mean[c] = pm;
     }
   }
-  // optional border-class sums of the pooled output (Q24 integers in shared memory, then one global atomic per touched
-  // (class, channel)): the next convolution's batch mean is a linear function of them (csrc/mobn_fused.cu).  The host
-  // guarantees that a CTA's 256 threads lie inside one image (hence one batch segment).
-  extern __shared__ unsigned long long pool_cls[];      // [9][C]
-  if (clsum) {
-    for (int k = threadIdx.x; k < 9 * C; k += blockDim.x) pool_cls[k] = 0ull;
-    __syncthreads();
-  }
+  // optional border-class sums of the pooled output: the next convolution's batch mean is a linear function of them
+  // (csrc/mobn_fused.cu).  The CTA's 256 / (C/8) pooled pixels are staged in shared memory; thread c then walks them in a
+  // fixed order into ITS column of a [9][C] table (no atomics inside the CTA) and the non-zero entries leave as Q24
+  // integer atomics.  The host guarantees whole CTAs per image (hence one batch segment per CTA).
+  extern __shared__ float pool_sm[];      // [256 * 8] staged outputs, then [9][C] class table
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nvec) return;
   const int cv = C / 8, Wo = W / 2, Ho = H / 2;
@@ -683,16 +680,28 @@ __global__ void mobn_pool_dropout_fwd_kernel(const bf16* __restrict__ z, bf16* _
   cw.y = cd[4] | (cd[5] << 8) | (cd[6] << 16) | ((uint32_t)cd[7] << 24);
   *reinterpret_cast<uint2*>(code + e) = cw;
   if (clsum) {
-    const int k = (ho == 0 ? 0 : ho == Ho - 1 ? 2 : 1) * 3 + (wo == 0 ? 0 : wo == Wo - 1 ? 2 : 1);
+    float* stage = pool_sm;                      // [pixels of this CTA][C]
+    float* tab = pool_sm + 256 * 8;              // [9][C]
+    const int px_cta = 256 / cv;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float vr = __bfloat162float(__float2bfloat16_rn(o[j]));      // the value as stored
-      if (vr != 0.f) atomicAdd(&pool_cls[k * C + c + j], (unsigned long long)__float2ll_rn(vr * 16777216.f));
-    }
+    for (int j = 0; j < 8; ++j) stage[(threadIdx.x / cv) * C + c + j] = __bfloat162float(__float2bfloat16_rn(o[j]));
+    for (int q = threadIdx.x; q < 9 * C; q += blockDim.x) tab[q] = 0.f;
     __syncthreads();      // (every thread of the CTA is alive here: nvec is a multiple of the CTA size when clsum is set)
-    for (int q = threadIdx.x; q < 9 * C; q += blockDim.x)
-      if (pool_cls[q] != 0ull)
-        atomicAdd(reinterpret_cast<unsigned long long*>(&clsum[(int64_t)s * 9 * C + q]), pool_cls[q]);
+    const int64_t t0 = ((int64_t)blockIdx.x * blockDim.x) / cv;      // first pooled pixel of the CTA (linear over n, ho, wo)
+    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+      for (int q = 0; q < px_cta; ++q) {
+        const int64_t tt = t0 + q;
+        const int w2 = (int)(tt % Wo), h2 = (int)((tt / Wo) % Ho);
+        const int k = (h2 == 0 ? 0 : h2 == Ho - 1 ? 2 : 1) * 3 + (w2 == 0 ? 0 : w2 == Wo - 1 ? 2 : 1);
+        tab[k * C + ch] += stage[q * C + ch];
+      }
+      for (int k = 0; k < 9; ++k) {
+        const float v = tab[k * C + ch];
+        if (v != 0.f)
+          atomicAdd(reinterpret_cast<unsigned long long*>(&clsum[((int64_t)s * 9 + k) * C + ch]),
+                    (unsigned long long)__float2ll_rn(v * 16777216.f));
+      }
+    }
   }
 }
 
@@ -1329,7 +1338,7 @@ extern "C" int tgan_mobn_pool_dropout_fwd(const void* z, void* y, uint8_t* code,
   cudaStream_t st = (cudaStream_t)stream;
   TGAN_CHECK_ARG(!clsum || ((int64_t)(H / 2) * (W / 2) * (C / 8)) % 256 == 0,
                  "mobn_pool_dropout_fwd: class sums need whole CTAs per image ((H/2)*(W/2)*(C/8) %% 256 == 0)");
-  const size_t smem = clsum ? (size_t)9 * C * sizeof(unsigned long long) : 0;
+  const size_t smem = clsum ? (size_t)(256 * 8 + 9 * C) * sizeof(float) : 0;
   TGAN_DISPATCH_ACT(act, A, (pdl_launch(mobn_pool_dropout_fwd_kernel<A>, ceil_div(nvec, 256), 256, smem, st, (const bf16*)z,
                                         (bf16*)y, code, H, W, C, nvec, sums, sums_q24, sg, rpi, b, pop_mean, decay, train, alpha, rate,
                                         1.0f / (1.0f - rate), mask, seed, stream_id, counter, (long long*)clsum)));

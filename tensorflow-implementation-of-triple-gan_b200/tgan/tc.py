@@ -132,10 +132,14 @@ def _flat(g):
     return g
 
 
+import os
+SMALL_CIN_MAX = int(os.environ.get('TGAN_SMALL_CIN_MAX', '16'))
+
+
 def _small_cin(g):
     """few input channels (conv1_1: 3, D's first conv: 13): per-tap TMA boxes would move 6-26 useful bytes per 128-byte
     shared-memory row, so the taps are gathered once into a bf16 im2col matrix and the conv runs as one plain GEMM"""
-    return g['kh'] * g['kw'] > 1 and g['C'] <= 16
+    return g['kh'] * g['kw'] > 1 and g['C'] <= SMALL_CIN_MAX
 
 
 def _im2col(x, g):

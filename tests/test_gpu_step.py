@@ -6,6 +6,7 @@ fp32 mode (CUDA-core GEMMs): 2e-4 relative-to-max vs the float64 oracle -- measu
 oracle's own float32 run vs float64 is ~1e-5 on these nets; the margin covers summation-order effects.
 """
 import contextlib
+import os
 
 import numpy as np
 import pytest
@@ -161,7 +162,8 @@ def _run(data_name, math, steps, scale, tol_loss, tol_grad, lambdas=(0.3, 0.5), 
     REPORT[key] = {k: (v if isinstance(v, int) else float('%.3e' % v)) for k, v in worst.items()}
     print(key, REPORT[key])
     _dump_report()
-    assert not bad, bad[:12]
+    if not os.environ.get('TGAN_PARITY_RECORD'):      # (record-only runs collect the numbers the bounds are set from)
+        assert not bad, bad[:12]
     return worst
 
 
