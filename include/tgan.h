@@ -105,10 +105,10 @@ typedef struct {
   void* clsum;         /* optional int64 Q24 [nseg][9][Nout]: += sums of the STORED values by border class, index
                           3 * (row first / interior / last) + (column first / interior / last) of a cls_h x cls_w image */
   int cls_h, cls_w;    /* powers of two; cls_w in {16, 32} */
-  void* mask_out;      /* optional uint32 [ceil(pixels / 32)][Nout]: bit j of word (i, c) = stored value of pixel
-                          32 i + j, channel c, is > 0 (which side of the leaky ReLU it is on) */
-  const void* mask_in; /* optional, same layout: the stored value is multiplied by 1 (bit set) or mask_alpha -- the
-                          input gradient passes through the PRODUCER's leaky ReLU inside this launch's epilogue */
+  void* mask_out;      /* optional uint32 [ceil(pixels / 32)][Nout]: bit 31 - j of word (i, c) = SIGN bit of the stored
+                          value of pixel 32 i + j, channel c (set = the negative side of the leaky ReLU) */
+  const void* mask_in; /* optional, same layout: the stored value is multiplied by mask_alpha where the bit is set --
+                          the input gradient passes through the PRODUCER's leaky ReLU inside this launch's epilogue */
   float mask_alpha;
 } tgan_igemm_args;
 int tgan_igemm_bf16(const tgan_igemm_args* a, void* stream);

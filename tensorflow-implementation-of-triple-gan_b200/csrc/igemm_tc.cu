@@ -506,9 +506,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             for (int j = 0; j < 32; ++j) v[j] = tmp[j];
           }
           if (p.mask_in && cvalid) {      // input gradient through the producer's leaky ReLU: du = dy * lrelu'(y)
+            // bit 31 - j of the word = sign bit of the producer's stored value j (set = negative side = slope alpha)
             const uint32_t mw = p.mask_in[(size_t)((box_p0 + pbase) >> 5) * p.Nout + co];
+            const float sl = p.mask_alpha;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= ((mw >> j) & 1u) ? 1.f : p.mask_alpha;
+            for (int j = 0; j < 32; ++j)
+              if (mw & (0x80000000u >> j)) v[j] *= sl;
           }
           if (p.tstore) {
             // ---- staged path: [pixel][channel] rows in shared memory, one bulk-tensor store per 128-pixel box.  The
@@ -518,9 +521,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
               const int total_px = p.segflat ? p.vw : p.N * p.OH * p.OW;
               const int valid = total_px - p0;           // pixels of this chunk inside the tensor (flat GEMM tail)
               if (p.mask_out && cvalid && valid > 0) {
+                // one funnel shift per element moves its SIGN bit into the word: bit 31 - j = (value j is negative)
                 uint32_t mw = 0u;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) mw |= (v[j] > 0.f ? 1u : 0u) << j;
+                for (int j = 0; j < 32; ++j) mw = __funnelshift_l(__float_as_uint(v[j]), mw, 1);
                 p.mask_out[(size_t)(p0 >> 5) * p.Nout + co] = mw;
               }
               if (p.clsum && valid > 0) {

@@ -687,11 +687,11 @@ __global__ void mobn_pool_dropout_fwd_kernel(const bf16* __restrict__ z, bf16* _
     for (int j = 0; j < 8; ++j) stage[(threadIdx.x / cv) * C + c + j] = __bfloat162float(__float2bfloat16_rn(o[j]));
     for (int q = threadIdx.x; q < 9 * C; q += blockDim.x) tab[q] = 0.f;
     __syncthreads();      // (every thread of the CTA is alive here: nvec is a multiple of the CTA size when clsum is set)
-    const int64_t t0 = ((int64_t)blockIdx.x * blockDim.x) / cv;      // first pooled pixel of the CTA (linear over n, ho, wo)
+    // (the CTA's pixels lie inside one image: the class only needs the pixel index within the image, 32-bit arithmetic)
+    const int t0 = (int)((((int64_t)blockIdx.x * blockDim.x) / cv) % ((int64_t)Ho * Wo));
     for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
       for (int q = 0; q < px_cta; ++q) {
-        const int64_t tt = t0 + q;
-        const int w2 = (int)(tt % Wo), h2 = (int)((tt / Wo) % Ho);
+        const int tt = t0 + q, w2 = tt % Wo, h2 = tt / Wo;
         const int k = (h2 == 0 ? 0 : h2 == Ho - 1 ? 2 : 1) * 3 + (w2 == 0 ? 0 : w2 == Wo - 1 ? 2 : 1);
         tab[k * C + ch] += stage[q * C + ch];
       }

@@ -696,7 +696,8 @@ def mobn_act(z, b, pop_mean, train, act='none', alpha=0.2, decay=0.9):
         sums = (cs_all if cs_all is not None else seg_stats()) if train else None
         # border-class sums of the pooled output: the next convolution's fused mean-only BN reads them (conv2d_mobn)
         clo = None
-        if train and ((H // 2) * (W // 2) * (C // 8)) % 256 == 0 and not os.environ.get('TGAN_NO_MOBN_FUSION'):
+        if (train and ((H // 2) * (W // 2) * (C // 8)) % 256 == 0 and W // 2 in (16, 32) and (H // 2) & (H // 2 - 1) == 0
+                and not os.environ.get('TGAN_NO_MOBN_FUSION')):      # (only where a fusable convolution can follow)
             clo = arena_take(2 * 9 * C * len(segs))
         rng = ctx.rng
         mask, seed, sid, ctr = None, 0, 0, None
@@ -782,6 +783,8 @@ def conv2d_mobn(x, w, kh, kw, stride, padding, b, pop_mean, train, act='none', a
 
     def run_plain():
         from . import tc
+        if x._data is None:      # tell a still-pending producer that THIS consumer reads its border-class sums
+            x.aux = dict(x.aux or {}, want_cls=True)
         xd = x.data                                   # materialises the producer; its class sums are in x.aux now
         cls = (x.aux or {}).get('cls')
         if cls is None and C <= 16:                   # the network input: sums by a small kernel of its own
@@ -796,13 +799,16 @@ def conv2d_mobn(x, w, kh, kw, stride, padding, b, pop_mean, train, act='none', a
         cnt = (ctypes.c_int64 * nseg)(*[n * rps for n in segs])
         _lib.call('tgan_mobn_mean_from_sums', _p(cls), nseg, cnt, _p(wp), 9, Cout, C, w_ts, w_cs, _p(b.data),
                   _p(pop_mean.data), decay, _p(shift), _st())
-        clo = arena_take(2 * 9 * Cout * nseg)
+        # class sums of the output only when the consumer asked for them (a fused layer behind this one); a consumer that
+        # pools (conv1_3, conv2_3) does not, and the heavy layers' epilogues stay lean
+        clo = arena_take(2 * 9 * Cout * nseg) if (out.aux or {}).get('want_cls') else None
         need_mask = out.requires_grad and tape is not None
         mask = _new((rows // 32, Cout), torch.int32) if need_mask else None
         y = tc.conv_fwd(x, w, geom, None, segs, bias=shift, act=ACT['lrelu'],
                         fused=dict(bias_seg=True, clsum=clo, cls_hw=(H, W), mask_out=mask))
         out._data, out.ld, out._lazy = y.view(N, H, W, Cout), Cout, None
-        out.aux = dict(out.aux or {}, cls=clo)
+        if clo is not None:
+            out.aux = dict(out.aux or {}, cls=clo)
         if need_mask:
             out.aux.update(mask=mask, mask_alpha=alpha)
 

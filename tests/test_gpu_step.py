@@ -90,15 +90,18 @@ def _run(data_name, math, steps, scale, tol_loss, tol_grad, lambdas=(0.3, 0.5), 
         # CUDA run's pseudo-labels (identical discrete routing -> gradients comparable tensor by tensor)
         with (O.quantized() if math == 'bf16' else contextlib.nullcontext()):
             ref32 = o32.step(batch, rng, lambdas[0], lambdas[1], labels=labels if math == 'bf16' else None)
-        # pseudo-labels: bit-exact wherever the oracle's top-2 logit margin exceeds the single-step noise
-        # (every step starts from identical state, so the same margin holds on all steps)
+        # pseudo-labels: bit-exact wherever the oracle's top-2 logit margin exceeds the single-step noise -- margin0, or
+        # 4x the logit error the ORACLE ITSELF shows at the precision under test (a 10-way batch-norm output on 5 samples
+        # amplifies bf16 rounding; every step starts from identical state, so the same margin holds on all steps)
         for key, lk, ph in (('idx_unl_d', 'c_unl_d', 'D'), ('idx_unl', 'c_unl', 'D'), ('idx_unl_c', None, 'C')):
             lg = orc.last_aux['D'][lk] if lk else orc.last_aux['C']['logits'][1]
+            lq = o32.last_aux['D'][lk] if lk else o32.last_aux['C']['logits'][1]
+            lfl = float((lq.double() - lg).abs().max())
             top2 = torch.topk(lg, 2, dim=1).values
-            sure = ((top2[:, 0] - top2[:, 1]) > margin0).numpy()
+            sure = ((top2[:, 0] - top2[:, 1]) > max(margin0, 4 * lfl)).numpy()
             mine, theirs = labels[key], orc.last_aux[ph][key].numpy()
             assert mine.dtype == np.int64
-            assert np.array_equal(mine[sure], theirs[sure]), (step, key, mine, theirs)
+            assert np.array_equal(mine[sure], theirs[sure]), (step, key, mine, theirs, lfl)
             worst['labels_checked'] = worst.get('labels_checked', 0) + int(sure.sum())
             worst['labels_total'] = worst.get('labels_total', 0) + int(sure.size)
         for i, nm in enumerate('dgc'):
