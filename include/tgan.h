@@ -126,8 +126,9 @@ int tgan_igemm_bf16(const tgan_igemm_args* a, void* stream);
 int tgan_mobn_mean_from_sums(const void* clsum, int nseg, const int64_t* count, const void* wp, int T, int Cout, int Cin,
                              int64_t w_tap_stride, int64_t w_co_stride, const float* b, float* pop_mean, float decay,
                              float* shift, void* stream);
-/* border-class sums (same layout as tgan_igemm_bf16.clsum) of a small-channel fp32 / bf16 tensor [N, H, W, C] (C <= 16),
- * of its values rounded to bf16 (what the tensor-core path reads): the classifier's 3-channel input */
+/* border-class sums (same layout as tgan_igemm_bf16.clsum) of [N, H, W, C]: a small-channel fp32 / bf16 tensor (C <= 16,
+ * values rounded to bf16 as the tensor-core path reads them: the classifier's 3-channel input) or a contiguous bf16
+ * activation with C % 8 == 0 (the pooled + dropped tensor in front of conv2_1) */
 int tgan_class_sums(const void* x, int xdt, int N, int H, int W, int C, int ld, int nseg, const int* seg_end_images,
                     void* clsum, void* stream);
 /* int64 Q24 per-segment channel sums [nseg][C] (tgan_igemm_bf16.colsum) -> fp32 colsums[4][C] (unused segments 0) and

@@ -18,45 +18,58 @@ namespace tgan {
 
 __device__ __forceinline__ float q24f(const long long* p, int64_t i) { return (float)((double)p[i] * (1.0 / 16777216.0)); }
 
-// S_s[t][ci] (tap sums from the nine class sums) is staged in shared memory once per CTA; then one warp per output
-// channel reduces over (t, ci) for every segment, updates pop_mean in call order and writes shift[s][co] = b - mean.
+// One warp per output channel.  A lane owns the input channels ci = lane, lane + 32, ...: per (segment, ci) it loads
+// the nine class sums, forms the nine tap sums in registers (a tap at row offset -1 never reads the LAST input row, +1
+// never the first; same for columns) and multiplies them with the nine tap weights -- every load of an iteration is
+// independent of the others, so the kernel is not bound by one memory latency per multiply.  The warp then reduces,
+// updates pop_mean in call order and writes shift[s][co] = b - mean_s.
 struct InvCount { float v[4]; };
+struct ClsSegs { int end[4]; int n; };
+typedef ClsSegs ClsSegsFwd;
 
 __global__ void __launch_bounds__(128) mobn_mean_kernel(const long long* __restrict__ clsum, int nseg, const InvCount inv_count,
                                                         const bf16* __restrict__ wp, int T, int Cout, int Cin, int64_t w_ts,
                                                         int64_t w_cs, const float* __restrict__ b, float* __restrict__ pop_mean,
                                                         float decay, float* __restrict__ shift) {
   pdl_entry();
-  extern __shared__ float S[];      // [nseg][T][Cin]
-  const int K = T * Cin;
-  for (int i = threadIdx.x; i < nseg * K; i += blockDim.x) {
-    const int s = i / K, k = i - s * K, t = k / Cin, ci = k - t * Cin;
-    // 3x3 / stride 1 / SAME, taps row-major: tap row r reads input rows [r-1, H-2+r] -> r = 0 never reads the LAST row
-    // class, r = 2 never the first; same for columns.  T == 1 (1x1 / dense): everything.
-    const int r = T == 9 ? t / 3 : 1, c = T == 9 ? t % 3 : 1;
-    const int rc0 = r == 2 ? 1 : 0, rc1 = r == 0 ? 1 : 2, cc0 = c == 2 ? 1 : 0, cc1 = c == 0 ? 1 : 2;
-    long long a = 0;
-    for (int rc = rc0; rc <= rc1; ++rc)
-      for (int cc = cc0; cc <= cc1; ++cc) a += clsum[((int64_t)s * 9 + rc * 3 + cc) * Cin + ci];
-    S[i] = (float)((double)a * (1.0 / 16777216.0));
-  }
-  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int co = blockIdx.x * (blockDim.x >> 5) + warp;
   if (co >= Cout) return;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  // all taps of one channel slice are requested together (nine independent loads in flight per lane) -- a single
-  // dependent load per iteration made this kernel latency bound (18 us for 2304 weights per output channel)
   for (int ci = lane; ci < Cin; ci += 32) {
     float w[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) w[t] = t < T ? __bfloat162float(wp[(int64_t)t * w_ts + (int64_t)co * w_cs + ci]) : 0.f;
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      if (t >= T) break;
+    for (int s = 0; s < 4; ++s) {
+      if (s >= nseg) break;
+      long long a[9];
 #pragma unroll
-      for (int s = 0; s < 4; ++s)
-        if (s < nseg) acc[s] += w[t] * S[s * K + t * Cin + ci];
+      for (int k = 0; k < 9; ++k) a[k] = clsum[((int64_t)s * 9 + k) * Cin + ci];
+      if (T == 9) {
+        // rows: R[r][cc], r = 0 -> classes {first, interior}, 1 -> all, 2 -> {interior, last}
+        long long R[3][3];
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+          R[0][cc] = a[cc] + a[3 + cc];
+          R[2][cc] = a[3 + cc] + a[6 + cc];
+          R[1][cc] = R[0][cc] + a[6 + cc];
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const long long c0 = R[r][0] + R[r][1], c2 = R[r][1] + R[r][2], c1 = c0 + R[r][2];
+          sum += w[r * 3 + 0] * (float)((double)c0 * (1.0 / 16777216.0));
+          sum += w[r * 3 + 1] * (float)((double)c1 * (1.0 / 16777216.0));
+          sum += w[r * 3 + 2] * (float)((double)c2 * (1.0 / 16777216.0));
+        }
+        acc[s] += sum;
+      } else {
+        long long tot = 0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) tot += a[k];
+        acc[s] += w[0] * (float)((double)tot * (1.0 / 16777216.0));
+      }
     }
   }
 #pragma unroll
@@ -74,8 +87,10 @@ __global__ void __launch_bounds__(128) mobn_mean_kernel(const long long* __restr
   }
 }
 
-struct ClsSegs { int end[4]; int n; };
-
+// Border-class sums of a wide bf16 tensor [N, H, W, C] (C % 8 == 0): one CTA per image, thread = (8 channels, one image
+// row).  A thread folds its row into (first / interior / last column) x 8 channels in registers; the rows then meet in
+// shared memory in a FIXED order (first row, interior rows top to bottom, last row), so the per-image sums are bit
+// reproducible, and leave as Q24 integer atomics (one per class and channel and image).
 // border-class sums of a small-channel tensor (the classifier's 3-channel input), one CTA per image.  Interior pixels
 // (88 % of a 32x32 image) accumulate in registers and meet in a warp shuffle; border pixels and the per-warp interior
 // totals go through Q24 integer atomics in shared memory, so the result does not depend on the order of the adds.
@@ -120,6 +135,60 @@ __global__ void __launch_bounds__(256) class_sums_kernel(const void* __restrict_
   }
 }
 
+__global__ void __launch_bounds__(1024) class_sums_wide_kernel(const bf16* __restrict__ x, int H, int W, int C, ClsSegs sg,
+                                                               long long* __restrict__ clsum) {
+  pdl_entry();
+  extern __shared__ float rows_sm[];      // [H][3][C]
+  const int cv = C / 8, n = blockIdx.x;
+  const int s = (n >= sg.end[0]) + (n >= sg.end[1]) + (n >= sg.end[2]);
+  for (int i = threadIdx.x; i < cv * H; i += blockDim.x) {
+    const int cg = i % cv, y = i / cv;
+    const bf16* row = x + (((int64_t)n * H + y) * W) * C + cg * 8;
+    float fi[8], mid[8], la[8], v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mid[j] = 0.f;
+    {
+      const uint4 u = *reinterpret_cast<const uint4*>(row);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { fi[2 * j] = __low2float(h[j]); fi[2 * j + 1] = __high2float(h[j]); }
+    }
+    {
+      const uint4 u = *reinterpret_cast<const uint4*>(row + (int64_t)(W - 1) * C);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { la[2 * j] = __low2float(h[j]); la[2 * j + 1] = __high2float(h[j]); }
+    }
+    for (int xx = 1; xx < W - 1; ++xx) {
+      const uint4 u = *reinterpret_cast<const uint4*>(row + (int64_t)xx * C);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { v[2 * j] = __low2float(h[j]); v[2 * j + 1] = __high2float(h[j]); }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mid[j] += v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      rows_sm[((size_t)y * 3 + 0) * C + cg * 8 + j] = fi[j];
+      rows_sm[((size_t)y * 3 + 1) * C + cg * 8 + j] = mid[j];
+      rows_sm[((size_t)y * 3 + 2) * C + cg * 8 + j] = la[j];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) {      // i = cc * C + channel
+    const float first = rows_sm[i], last = rows_sm[(size_t)(H - 1) * 3 * C + i];
+    float inner = 0.f;
+    for (int y = 1; y < H - 1; ++y) inner += rows_sm[(size_t)y * 3 * C + i];
+    const int cc = i / C, ch = i - cc * C;
+    const float val[3] = {first, inner, last};
+#pragma unroll
+    for (int rc = 0; rc < 3; ++rc)
+      if (val[rc] != 0.f)
+        atomicAdd(reinterpret_cast<unsigned long long*>(&clsum[((int64_t)s * 9 + rc * 3 + cc) * C + ch]),
+                  (unsigned long long)__float2ll_rn(val[rc] * 16777216.f));
+  }
+}
+
 // Backward bookkeeping of a fused layer: the consumer's input-gradient epilogue left per-segment channel sums of
 // du = dy * lrelu'(y) in Q24; this turns them into the fp32 sums the mean-subtraction reads and adds db = sum_s.
 __global__ void seg_sums_finalize_kernel(const long long* __restrict__ q, int nseg, int C, float* __restrict__ colsums,
@@ -157,11 +226,25 @@ extern "C" int tgan_mobn_mean_from_sums(const void* clsum, int nseg, const int64
 
 extern "C" int tgan_class_sums(const void* x, int xdt, int N, int H, int W, int C, int ld, int nseg,
                                const int* seg_end_images, void* clsum, void* stream) {
-  TGAN_CHECK_ARG(x && clsum && N > 0 && H > 1 && W > 1 && C >= 1 && C <= 16 && ld >= C && nseg >= 1 && nseg <= 4,
-                 "class_sums: bad args (C <= 16)");
+  TGAN_CHECK_ARG(x && clsum && N > 0 && H > 2 && W > 2 && C >= 1 && ld >= C && nseg >= 1 && nseg <= 4, "class_sums: bad args");
   ClsSegs sg;
   for (int i = 0; i < 4; ++i) sg.end[i] = (nseg > 1 && i < nseg - 1 && seg_end_images) ? seg_end_images[i] : 0x7fffffff;
   sg.n = nseg;
+  if (C > 16) {      // wide bf16 activation (the pooled tensor in front of conv2_1)
+    const size_t smem = (size_t)H * 3 * C * sizeof(float);
+    TGAN_CHECK_ARG(xdt == TGAN_BF16 && C % 8 == 0 && ld == C && ((uintptr_t)x & 15) == 0 && smem <= 96 * 1024,
+                   "class_sums: wide tensors must be contiguous bf16 with C %% 8 == 0 and H * C <= 8192");
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(class_sums_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      attr_set = true;
+    }
+    int threads = (C / 8) * H;
+    threads = threads > 1024 ? 1024 : (threads + 31) / 32 * 32;
+    pdl_launch(class_sums_wide_kernel, N, threads, smem, (cudaStream_t)stream, (const bf16*)x, H, W, C, sg, (long long*)clsum);
+    TGAN_LAUNCHED();
+    return 0;
+  }
   pdl_launch(class_sums_kernel, N, 256, 0, (cudaStream_t)stream, x, xdt, H, W, C, ld, sg, (long long*)clsum);
   TGAN_LAUNCHED();
   return 0;

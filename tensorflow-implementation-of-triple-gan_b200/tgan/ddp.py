@@ -54,3 +54,63 @@ def broadcast_params(store, src=0, group=None):
     if world_size() > 1:
         for fb in store.flat.values():
             dist.broadcast(fb['theta'], src=src, group=group)
+
+
+class BucketedAllReduce:
+    """Two gradient buckets for the classifier (the network whose backward pass is long enough to hide a collective).
+
+    The flat gradient buffer is ordered by variable creation, i.e. by layer; the backward pass produces it back to
+    front.  Bucket A = the tail [split:] (conv2_2 ... output_dense: 81 % of the 12.5 MB) is complete as soon as the
+    first filter gradient of an EARLIER layer is requested; at that moment the weight-norm backward of bucket A runs and
+    its all-reduce starts on a communication stream, overlapped with the remaining backward work (conv2_1 ... conv1_1,
+    ~0.4 ms).  Bucket B = the head [:split] is reduced when the pass ends; Adam waits for both.  Sums are identical to
+    the single all-reduce (same elements, same reduction), only the timing changes."""
+
+    def __init__(self, store, group, first_param_of_tail, pg=None):
+        fb = store.flat[group]
+        self.fb, self.pg, self.group = fb, pg, group
+        self.split = None
+        for p, o in zip(fb['params'], fb['offsets']):
+            if p.name == first_param_of_tail:
+                self.split = o
+        if self.split is None:
+            raise KeyError(first_param_of_tail)
+        self.stream = None
+        self.done_evt = None
+        self.flushed = None
+
+    def install(self):
+        from .prep import WNGroup
+        grp = WNGroup.of(self.group)
+        grp.bucket_hook = self._hook
+        return self
+
+    def _hook(self, grp, entry, tape):
+        if world_size() <= 1 or self.flushed is tape or entry['off'] is None or entry['off'] >= self.split:
+            return
+        # first filter gradient of a head layer: every tail layer's dW, bias gradient and g / V inputs are final
+        self.flushed = tape
+        grp.flush_bucket(lambda x: x['off'] is not None and x['off'] >= self.split)
+        if self.stream is None:
+            self.stream = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        self.stream.wait_event(ready)
+        with torch.cuda.stream(self.stream):
+            dist.all_reduce(self.fb['grad'][self.split:], op=dist.ReduceOp.SUM, group=self.pg)
+            self.done_evt = torch.cuda.Event()
+            self.done_evt.record(self.stream)
+
+    def finish(self, tape_done=True):
+        """all-reduce what is left and make the current stream wait for the early bucket; -> 1 / world"""
+        w = world_size()
+        if w <= 1:
+            return 1.0
+        if self.flushed is not None and self.done_evt is not None:
+            dist.all_reduce(self.fb['grad'][:self.split], op=dist.ReduceOp.SUM, group=self.pg)
+            torch.cuda.current_stream().wait_event(self.done_evt)
+        else:
+            dist.all_reduce(self.fb['grad'], op=dist.ReduceOp.SUM, group=self.pg)
+        self.flushed, self.done_evt = None, None
+        return 1.0 / w

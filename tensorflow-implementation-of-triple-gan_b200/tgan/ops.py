@@ -696,7 +696,7 @@ def mobn_act(z, b, pop_mean, train, act='none', alpha=0.2, decay=0.9):
         sums = (cs_all if cs_all is not None else seg_stats()) if train else None
         # border-class sums of the pooled output: the next convolution's fused mean-only BN reads them (conv2d_mobn)
         clo = None
-        if (train and ((H // 2) * (W // 2) * (C // 8)) % 256 == 0 and W // 2 in (16, 32) and (H // 2) & (H // 2 - 1) == 0
+        if (train and W // 2 in (16, 32) and (H // 2) & (H // 2 - 1) == 0 and (H // 2) * C <= 8192
                 and not os.environ.get('TGAN_NO_MOBN_FUSION')):      # (only where a fusable convolution can follow)
             clo = arena_take(2 * 9 * C * len(segs))
         rng = ctx.rng
@@ -707,9 +707,11 @@ def mobn_act(z, b, pop_mean, train, act='none', alpha=0.2, decay=0.9):
             seed, sid, ctr = rng.seed, rng.stream_id(str(tag)), rng.counter()
         _lib.call('tgan_mobn_pool_dropout_fwd', _p(zd), _p(y), _p(code), N, H, W, C, len(segs), iends[0], iends[1], iends[2],
                   _p(sums), 1 if cs_all is not None else 0, _p(b.data), _p(pop_mean.data), decay, 1 if train else 0, a, alpha,
-                  float(rate), _p(mask), seed, sid, _p(ctr), _p(clo), _st())
+                  float(rate), _p(mask), seed, sid, _p(ctr), None, _st())
         pout._data, pout._lazy = y, None
-        if clo is not None:
+        if clo is not None:      # one pass over the (L2-resident) pooled tensor: one CTA per image, fixed summation order
+            se = (ctypes.c_int * 3)(*iends[:3])
+            _lib.call('tgan_class_sums', _p(y), BF16, N, H // 2, W // 2, C, C, len(segs), se, _p(clo), _st())
             pout.aux = dict(pout.aux or {}, cls=clo)
         out._lazy = None                 # consumed: the full-resolution activation does not exist
         if pout.requires_grad and tape is not None:
@@ -810,7 +812,7 @@ def conv2d_mobn(x, w, kh, kw, stride, padding, b, pop_mean, train, act='none', a
         if clo is not None:
             out.aux = dict(out.aux or {}, cls=clo)
         if need_mask:
-            out.aux.update(mask=mask, mask_alpha=alpha)
+            out.aux = dict(out.aux or {}, mask=mask, mask_alpha=alpha)
 
             def bwd():
                 if out.grad is None:

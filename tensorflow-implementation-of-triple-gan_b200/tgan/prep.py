@@ -74,7 +74,7 @@ class WNGroup:
             dW = self.dWflat[off:off + n] if off is not None else torch.zeros(n, dtype=torch.float32, device=ctx.device)
             e = dict(w=w, inv=torch.empty(w.Co, dtype=torch.float32, device=ctx.device),
                      scale=torch.empty(w.Co, dtype=torch.float32, device=ctx.device), dW=dW.view(w.V.shape),
-                     flat=off is not None)
+                     flat=off is not None, off=off)
             self.entries[w.V] = e
             self.table = None
             if self.version == ctx.store.group_version(self.group):      # the group was prepared without this tensor
@@ -123,20 +123,37 @@ class WNGroup:
                 if not x['flat']:
                     _lib.call('tgan_fill_f32', x['dW'].data_ptr(), 0.0, x['dW'].numel(), _st())
             me = self
+            self.done = set()
 
             def post():
-                # every tensor registered by now (tensors that join during the pass start from zeroed accumulators)
-                live = [x for x in me.entries.values() if x['w'].V.grad is not None and x['w'].g.grad is not None]
-                key = tuple(id(x['w'].V) for x in live)
-                tbl = me.bwd_tables.get(key)
-                if tbl is None:
-                    tbl = me.bwd_tables[key] = (_table([me._desc(x) for x in live]), len(live),
-                                                max(x['w'].Co for x in live))
-                assert _lib.load().tgan_weightnorm_bwd_multi_ws_floats(tbl[1], tbl[2]) <= ctx.ws().numel()
-                _lib.call('tgan_weightnorm_bwd_multi', tbl[0].data_ptr(), tbl[1], tbl[2], ctx.ws().data_ptr(), _st())
+                # every tensor registered by now (tensors that join during the pass start from zeroed accumulators),
+                # minus the ones an early gradient bucket already converted (flush_bucket)
+                me._run_bwd([x for x in me.entries.values() if id(x) not in me.done])
                 me.bwd_tape = None
             tape.post.append(post)
+        hook = getattr(self, 'bucket_hook', None)
+        if hook is not None:
+            hook(self, e, tape)
         return e['dW']
+
+    def _run_bwd(self, entries):
+        """dV / dg of `entries` from their accumulated dW: one multi-tensor launch"""
+        live = [x for x in entries if x['w'].V.grad is not None and x['w'].g.grad is not None]
+        if not live:
+            return
+        key = tuple(id(x['w'].V) for x in live)
+        tbl = self.bwd_tables.get(key)
+        if tbl is None:
+            tbl = self.bwd_tables[key] = (_table([self._desc(x) for x in live]), len(live), max(x['w'].Co for x in live))
+        assert _lib.load().tgan_weightnorm_bwd_multi_ws_floats(tbl[1], tbl[2]) <= ctx.ws().numel()
+        _lib.call('tgan_weightnorm_bwd_multi', tbl[0].data_ptr(), tbl[1], tbl[2], ctx.ws().data_ptr(), _st())
+
+    def flush_bucket(self, pred):
+        """convert the dW of the entries selected by pred NOW (their filter gradients are complete): the data-parallel
+        step all-reduces that part of the flat gradient buffer while the rest of the backward pass still runs"""
+        sel = [x for x in self.entries.values() if id(x) not in self.done and pred(x)]
+        self._run_bwd(sel)
+        self.done.update(id(x) for x in sel)
 
 
 class PackGroup:

@@ -225,7 +225,14 @@ class Train(Train_base):
         return fb
 
     def _apply(self, fb, opt, ema=None, group=None):
-        scale = ddp.allreduce_grads(fb['grad'], self.pg)      # NCCL sum over NVLink; 1/world folded into Adam
+        if group == 'classifier' and self.world > 1 and ctx.math == 'bf16' and self.config.DATA_NAME == 'cifar10' \
+                and hasattr(self.model, '_whitener'):
+            # the classifier's gradient travels in two buckets; the tail one was started behind its own backward pass
+            if getattr(self, '_c_buckets', None) is None:
+                self._c_buckets = ddp.BucketedAllReduce(self.store, 'classifier', 'classifier/conv2_2/V', self.pg).install()
+            scale = self._c_buckets.finish()
+        else:
+            scale = ddp.allreduce_grads(fb['grad'], self.pg)      # NCCL sum over NVLink; 1/world folded into Adam
         opt.apply_flat(fb, scale, ema.shadow if ema is not None else None, ema.decay if ema is not None else 0.0)
         self.store.bump(group)
 
