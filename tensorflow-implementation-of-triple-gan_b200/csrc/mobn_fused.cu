@@ -32,11 +32,13 @@ __global__ void __launch_bounds__(128) mobn_mean_kernel(const long long* __restr
                                                         int64_t w_cs, const float* __restrict__ b, float* __restrict__ pop_mean,
                                                         float decay, float* __restrict__ shift) {
   pdl_entry();
+  // one CTA (4 warps) per output channel: the 128 threads split the input channels, so even Cin = 256 is two
+  // iterations per thread and Cout CTAs keep every SM busy
+  __shared__ float red[4][4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int co = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (co >= Cout) return;
+  const int co = blockIdx.x;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int ci = lane; ci < Cin; ci += 32) {
+  for (int ci = threadIdx.x; ci < Cin; ci += 128) {
     float w[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) w[t] = t < T ? __bfloat162float(wp[(int64_t)t * w_ts + (int64_t)co * w_cs + ci]) : 0.f;
@@ -73,13 +75,16 @@ __global__ void __launch_bounds__(128) mobn_mean_kernel(const long long* __restr
     }
   }
 #pragma unroll
-  for (int s = 0; s < 4; ++s)
+  for (int s = 0; s < 4; ++s) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) acc[s] += __shfl_xor_sync(0xffffffffu, acc[s], o);
-  if (lane == 0) {
+    if (lane == 0) red[warp][s] = acc[s];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
     float pm = pop_mean ? pop_mean[co] : 0.f;
     for (int s = 0; s < nseg; ++s) {
-      const float m = acc[s] * inv_count.v[s];
+      const float m = (((red[0][s] + red[1][s]) + red[2][s]) + red[3][s]) * inv_count.v[s];
       shift[s * Cout + co] = b[co] - m;
       pm = pm * decay + m * (1.f - decay);      // one update per call, in call order (nn.py:181)
     }
@@ -216,9 +221,7 @@ extern "C" int tgan_mobn_mean_from_sums(const void* clsum, int nseg, const int64
                      w_co_stride >= 1, "mobn_mean_from_sums: bad args");
   InvCount ic;      // by value in the kernel arguments: nothing to stage, CUDA-graph capturable
   for (int s = 0; s < 4; ++s) ic.v[s] = s < nseg ? (float)(1.0 / (double)count[s]) : 0.f;
-  const size_t smem = (size_t)nseg * T * Cin * sizeof(float);
-  TGAN_CHECK_ARG(smem <= 48 * 1024, "mobn_mean_from_sums: T * Cin * nseg too large (%d x %d x %d)", T, Cin, nseg);
-  pdl_launch(mobn_mean_kernel, ceil_div(Cout, 4), 128, smem, (cudaStream_t)stream, (const long long*)clsum, nseg, ic,
+  pdl_launch(mobn_mean_kernel, Cout, 128, 0, (cudaStream_t)stream, (const long long*)clsum, nseg, ic,
              (const bf16*)wp, T, Cout, Cin, w_tap_stride, w_co_stride, b, pop_mean, decay, shift);
   TGAN_LAUNCHED();
   return 0;
