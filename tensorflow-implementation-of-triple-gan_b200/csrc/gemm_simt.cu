@@ -213,6 +213,70 @@ __global__ void col2im_kernel(const float* __restrict__ col, int N, int H, int W
 
 }  // namespace tgan
 
+namespace tgan {
+
+// Skinny outputs (N <= 16: the discriminator head 138 -> 1, the classifier logits 128 -> 10; SURVEY 2.2 'warp-reduce
+// GEMV for N in {1, 10}'): a 64x64-tile SIMT GEMM leaves 63 of 64 columns idle and took 11-19 us per call.
+// C[m, :] = A[m, :] * B (+ beta * C): one warp per row, lanes stride K, N accumulators per lane, shuffle reduction.
+template <int NMAX>
+__global__ void __launch_bounds__(256) skinny_nn_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
+                                                        const float* __restrict__ B, int ldb, float beta,
+                                                        float* __restrict__ C, int ldc) {
+  pdl_entry();
+  const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (m >= M) return;
+  float acc[NMAX];
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n) acc[n] = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float a = A[(int64_t)m * lda + k];
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n)
+      if (n < N) acc[n] += a * B[(int64_t)k * ldb + n];
+  }
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n)
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
+  if (lane == 0)
+    for (int n = 0; n < N; ++n) C[(int64_t)m * ldc + n] = acc[n] + (beta != 0.f ? beta * C[(int64_t)m * ldc + n] : 0.f);
+}
+
+// C[i, :] = beta * C[i, :] + sum_r A[r, i] * B[r, :]  (the filter gradient of a skinny layer: A = layer input [rows, M],
+// B = dlogits [rows, N]).  Thread (i, part): the row range is cut into PARTS fixed slices summed in a fixed order.
+template <int NMAX>
+__global__ void __launch_bounds__(256) skinny_tn_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
+                                                        const float* __restrict__ B, int ldb, float beta,
+                                                        float* __restrict__ C, int ldc) {
+  pdl_entry();
+  constexpr int PARTS = 8;
+  __shared__ float red[PARTS][32][NMAX];
+  const int il = threadIdx.x & 31, part = threadIdx.x >> 5, i = blockIdx.x * 32 + il;
+  float acc[NMAX];
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n) acc[n] = 0.f;
+  const int per = (K + PARTS - 1) / PARTS, r0 = part * per, r1 = min(K, r0 + per);
+  if (i < M)
+    for (int r = r0; r < r1; ++r) {
+      const float a = A[(int64_t)r * lda + i];
+#pragma unroll
+      for (int n = 0; n < NMAX; ++n)
+        if (n < N) acc[n] += a * B[(int64_t)r * ldb + n];
+    }
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n) red[part][il][n] = acc[n];
+  __syncthreads();
+  if (part == 0 && i < M)
+    for (int n = 0; n < N; ++n) {
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < PARTS; ++q) s += red[q][il][n];
+      C[(int64_t)i * ldc + n] = s + (beta != 0.f ? beta * C[(int64_t)i * ldc + n] : 0.f);
+    }
+}
+
+}  // namespace tgan
+
 using namespace tgan;
 
 extern "C" int tgan_sgemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
@@ -220,6 +284,13 @@ extern "C" int tgan_sgemm(int transA, int transB, int M, int N, int K, float alp
                           void* stream) {
   TGAN_CHECK_ARG(M > 0 && N > 0 && K > 0, "sgemm: empty problem %d %d %d", M, N, K);
   TGAN_CHECK_ARG(A && B && C, "sgemm: null pointer");
+  if (N <= 16 && alpha == 1.f && !transB) {      // skinny outputs: dedicated kernels (fixed summation order, no split-K)
+    cudaStream_t sst = (cudaStream_t)stream;
+    if (!transA) pdl_launch(skinny_nn_kernel<16>, ceil_div((int64_t)M * 32, 256), 256, 0, sst, M, N, K, A, lda, B, ldb, beta, C, ldc);
+    else pdl_launch(skinny_tn_kernel<16>, ceil_div(M, 32), 256, 0, sst, M, N, K, A, lda, B, ldb, beta, C, ldc);
+    TGAN_LAUNCHED();
+    return 0;
+  }
   if (splits < 1) splits = 1;
   TGAN_CHECK_ARG(splits == 1 || ws, "sgemm: split-K needs a workspace");
   int kper = ((ceil_div(K, splits) + BK - 1) / BK) * BK;

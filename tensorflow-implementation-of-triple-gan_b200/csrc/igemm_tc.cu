@@ -668,12 +668,12 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ C
             tma_load_4d(s + 2 * dz_box + (size_t)bb * x_box, &tmX, &full[stage], cit * p.BNc + bb * 64, ox0 + p.dx[t0],
                         oy0 + p.dy0, n0);
         } else {
-          mbar_arrive_expect_tx(&full[stage], (uint32_t)(2 + nt * nbB) * WG_BOX_BYTES);   // exact: last group may be short
+          mbar_arrive_expect_tx(&full[stage], (uint32_t)(2 + nt * nbB) * dz_box);   // exact: last group may be short
           tma_load_4d(s, &tmDz, &full[stage], cot * 128, ox0, oy0, n0);
-          tma_load_4d(s + WG_BOX_BYTES, &tmDz, &full[stage], cot * 128 + 64, ox0, oy0, n0);
+          tma_load_4d(s + dz_box, &tmDz, &full[stage], cot * 128 + 64, ox0, oy0, n0);
           for (int j = 0; j < nt; ++j)
             for (int bb = 0; bb < nbB; ++bb)
-              tma_load_4d(s + (size_t)(2 + j * nbB + bb) * WG_BOX_BYTES, &tmX, &full[stage], cit * p.BNc + bb * 64,
+              tma_load_4d(s + (size_t)(2 + j * nbB + bb) * dz_box, &tmX, &full[stage], cit * p.BNc + bb * 64,
                           ox0 * p.sx + p.dx[t0 + j], oy0 * p.sy + p.dy[t0 + j], n0);
         }
       }
@@ -684,7 +684,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ C
     const int span = max(1, 256 / p.BNc);
     const uint32_t idesc = umma_idesc_bf16(128, span * p.BNc, 1, 1);
     // MN-major SWIZZLE_128B: LBO = distance between 64-channel boxes, SBO = 8 pixel rows = 1024 B
-    const uint64_t desc_hi = ((uint64_t)(WG_BOX_BYTES >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+    // (non-halo: the dz box and every x box hold kp pixel rows of 128 B; kp = 32, or gh*gw*bn for small odd grids)
+    const uint64_t desc_hi = ((uint64_t)(dz_box >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
     const uint32_t s_base = smem_u32(smem) >> 4;
     int stage = 0; uint32_t phase = 0;
     for (int pt = pt0; pt < pt1; ++pt) {
@@ -712,12 +713,13 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ C
         // MMA spans `span` taps: N = span*BNc <= 256 (an MMA costs the same ~82 ns for any N <= 256)
         for (int j = 0; j < nt; j += span) {
           const int sp = min(span, nt - j);
-          const uint32_t b_lo = s + (uint32_t)(2 + j * nbB) * (WG_BOX_BYTES >> 4);
+          const uint32_t b_lo = s + (uint32_t)(2 + j * nbB) * (dz_box >> 4);
           const uint32_t d = tmem_base + (uint32_t)(j * p.BNc);
           const uint32_t id = sp == span ? idesc : umma_idesc_bf16(128, sp * p.BNc, 1, 1);
           // a K step of 16 pixels = 2 row groups = +2048 B = +128 in the (>>4) start-address field
-          umma_bf16(d, desc_hi | (uint64_t)(s + 0), desc_hi | (uint64_t)(b_lo + 0), id, pt > pt0 ? 1u : 0u);
-          umma_bf16(d, desc_hi | (uint64_t)(s + 128), desc_hi | (uint64_t)(b_lo + 128), id, 1u);
+          for (int ks = 0; ks < p.kp / 16; ++ks)
+            umma_bf16(d, desc_hi | (uint64_t)(s + (uint32_t)ks * 128u), desc_hi | (uint64_t)(b_lo + (uint32_t)ks * 128u), id,
+                      (pt > pt0 || ks > 0) ? 1u : 0u);
         }
         umma_commit(&empty[stage]);
         if (pt == pt1 - 1) umma_commit(done);
@@ -1006,6 +1008,18 @@ static int wgrad_plan(const tgan_wgrad_args* a, WgParams& p) {
   } else {
     pick_tile(a->gh, a->gw, p.bh, p.bw, p.bn, WG_KP);
     p.kp = WG_KP; p.xrows = WG_KP;
+    // small grids that are not powers of two (conv3: 6x6 VALID outputs): power-of-two pixel tiles would carry 44 % padding
+    // through the tensor pipe.  Take the exact grid of bn images as one K tile when that is a multiple of 16 pixels.
+    const bool pow2 = (a->gh & (a->gh - 1)) == 0 && (a->gw & (a->gw - 1)) == 0;
+    if (!pow2 && a->gh <= 16 && a->gw <= 16 && !getenv("TGAN_WGRAD_NO_EXACT")) {
+      for (int bn = 1; bn <= 8; ++bn) {
+        const int kp = a->gh * a->gw * bn;
+        if (kp % 16 == 0 && kp <= 256 && kp >= 64) {
+          p.bh = a->gh; p.bw = a->gw; p.bn = bn; p.kp = kp; p.xrows = kp;
+          break;
+        }
+      }
+    }
   }
   if (p.bw * sx > 256 || p.bh * sy > 256) { set_error("wgrad: strided box too large"); return 1; }
   p.ptiles_y = ceil_div(a->gh, p.bh); p.ptiles_x = ceil_div(a->gw, p.bw);
@@ -1022,8 +1036,8 @@ static int wgrad_plan(const tgan_wgrad_args* a, WgParams& p) {
     p.tg = 512 / p.BNc;
     if (p.tg > a->T) p.tg = a->T;
     p.tg = ceil_div(a->T, ceil_div(a->T, p.tg));     // balanced tap groups (T=9, max 4 -> 3+3+3)
-    // smem: stages * (2 + tg*BNc/64) boxes of 4 KB
-    while (p.tg > 1 && (size_t)2 * (2 + p.tg * (p.BNc / 64)) * WG_BOX_BYTES > 200 * 1024) --p.tg;
+    // smem: stages * (2 + tg*BNc/64) boxes of kp * 128 B, at least two stages
+    while (p.tg > 1 && (size_t)2 * (2 + p.tg * (p.BNc / 64)) * p.kp * 128 > 200 * 1024) --p.tg;
     p.tap_groups = ceil_div(a->T, p.tg);
   }
   const int base = p.co_tiles * p.ci_tiles * p.tap_groups;

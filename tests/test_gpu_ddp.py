@@ -41,13 +41,13 @@ def _launch(tmp, math):
     return [np.load(os.path.join(str(tmp), 'rank%d.npz' % k)) for k in range(2)]
 
 
-def _oracle_dp_first_step():
+def _oracle_dp_first_step(dtype=torch.float64):
     """one data-parallel iteration restated on the oracle: per phase, the gradients of the two shards at the SAME
     parameters are averaged and applied once"""
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     from ddp_worker import shard_inputs
     P, S = O.init_params('cifar10', seed=5)               # rank 0's initial values
-    orc = O.OracleTrainer('cifar10', P, S, O.make_zca(3), dtype=torch.float64, scale=SCALE)
+    orc = O.OracleTrainer('cifar10', P, S, O.make_zca(3), dtype=dtype, scale=SCALE)
     shards = [shard_inputs(orc.cfg, r, 0) for r in range(2)]
     lr, cla_lr = orc.cfg.LEARNING_RATE, orc.cfg.CLA_LEARNINIG_RATE
     avg = lambda gs: {n: (gs[0][n] + gs[1][n]) / 2 for n in gs[0]}
@@ -73,6 +73,8 @@ def _oracle_dp_first_step():
 def test_two_rank_step_equals_shard_averaged_oracle(tmp_path):
     ranks = _launch(tmp_path, 'fp32')
     orc, losses, grads = _oracle_dp_first_step()
+    # the same restatement in float32: the arithmetic's own noise floor on these (heavily cancelling) gradients
+    _, _, grads32 = _oracle_dp_first_step(torch.float32)
     for r in range(2):
         got = ranks[r]['loss0']
         assert np.allclose(got, losses[r], rtol=2e-5, atol=2e-5), (r, got, losses[r])
@@ -83,10 +85,12 @@ def test_two_rank_step_equals_shard_averaged_oracle(tmp_path):
         for n in names:
             ref = grads[n].numpy()
             den = max(np.abs(ref).max(), 1e-3 * scale[ph])
+            floor = np.abs(grads32[n].double().numpy() - ref).max() / den
             for r in range(2):
                 e = np.abs(ranks[r]['grad:' + n] / 2.0 - ref).max() / den      # the buffer holds the SUM; Adam applies 1/world
                 worst = max(worst, e)
-                assert e < 5e-4, (n, r, e)
+                # the single-GPU bound of tests/test_gpu_step.py: 2e-4, or 8x the float32 floor of the oracle itself
+                assert e < max(2e-4, 8 * floor), (n, r, e, floor)
             # one averaged Adam update per network: |theta - oracle| is a small fraction of the step lr
             lr = orc.cfg.CLA_LEARNINIG_RATE if ph == 'C' else orc.cfg.LEARNING_RATE
             resolved = np.abs(ref) > 1e-3 * scale[ph]
