@@ -371,6 +371,20 @@ int tgan_loss_c(const float* c_real, const float* y_l_c, int n_real, const float
 int tgan_adam(float* theta, float* m, float* v, const float* grad, int64_t n, const float* state,
               float beta1, float beta2, float eps, float grad_scale, float* ema, float ema_decay,
               void* stream);
+/* ---------------------------------------------------------------- data-parallel update over peer memory ----
+ * NEW (the reference is single-GPU): reduce-scatter -> Adam on the owned shard -> all-gather of the parameters as one
+ * kernel over NVLink peer memory (csrc/dp_fused.cu).  grad_ptrs / theta_ptrs / flag_ptrs: HOST arrays of `world` device
+ * addresses (uint64), entry p = rank p's buffer (symmetric allocations, identical layout on every rank).
+ *   tgan_dp_barrier : every rank arrives, nobody leaves before all did; slot 0 / 1 = two independent barriers; flags:
+ *                     int [2][8] per rank, zero-initialised; epoch: LOCAL int [2] zero-initialised (device counters)
+ *   tgan_dp_adam    : rank r sums elements [r*per, (r+1)*per) of all gradient buffers in rank order, divides by world,
+ *                     applies tgan_adam's update with its local m / v slice and writes the new parameters into EVERY
+ *                     rank's theta buffer.  Call between tgan_dp_barrier(slot 0) and tgan_dp_barrier(slot 1).
+ *   tgan_ema        : shadow -= (shadow - theta) * (1 - decay) over the gathered parameters (Train_goodGAN.py:101-103) */
+int tgan_dp_barrier(const uint64_t* flag_ptrs, int rank, int world, int slot, int* epoch, void* stream);
+int tgan_dp_adam(const uint64_t* grad_ptrs, const uint64_t* theta_ptrs, float* m, float* v, int64_t n, int rank, int world,
+                 const float* state, float beta1, float beta2, float eps, void* stream);
+int tgan_ema(float* ema, const float* theta, int64_t n, float decay, void* stream);
 /* beta1_power *= beta1, beta2_power *= beta2 (TF's _finish) */
 int tgan_adam_advance(float* state, float beta1, float beta2, void* stream);
 /* Philox counter bump once per step: *counter += inc */

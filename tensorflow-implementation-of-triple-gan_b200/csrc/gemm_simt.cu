@@ -245,11 +245,11 @@ __global__ void __launch_bounds__(256) skinny_nn_kernel(int M, int N, int K, con
 // C[i, :] = beta * C[i, :] + sum_r A[r, i] * B[r, :]  (the filter gradient of a skinny layer: A = layer input [rows, M],
 // B = dlogits [rows, N]).  Thread (i, part): the row range is cut into PARTS fixed slices summed in a fixed order.
 template <int NMAX>
-__global__ void __launch_bounds__(256) skinny_tn_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
+__global__ void __launch_bounds__(512) skinny_tn_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
                                                         const float* __restrict__ B, int ldb, float beta,
                                                         float* __restrict__ C, int ldc) {
   pdl_entry();
-  constexpr int PARTS = 8;
+  constexpr int PARTS = 16;      // 512 threads: 32 output rows x 16 slices of the reduction axis
   __shared__ float red[PARTS][32][NMAX];
   const int il = threadIdx.x & 31, part = threadIdx.x >> 5, i = blockIdx.x * 32 + il;
   float acc[NMAX];
@@ -257,7 +257,8 @@ __global__ void __launch_bounds__(256) skinny_tn_kernel(int M, int N, int K, con
   for (int n = 0; n < NMAX; ++n) acc[n] = 0.f;
   const int per = (K + PARTS - 1) / PARTS, r0 = part * per, r1 = min(K, r0 + per);
   if (i < M)
-    for (int r = r0; r < r1; ++r) {
+#pragma unroll 4
+    for (int r = r0; r < r1; ++r) {      // (independent loads: four rows in flight per thread)
       const float a = A[(int64_t)r * lda + i];
 #pragma unroll
       for (int n = 0; n < NMAX; ++n)
@@ -287,7 +288,7 @@ extern "C" int tgan_sgemm(int transA, int transB, int M, int N, int K, float alp
   if (N <= 16 && alpha == 1.f && !transB) {      // skinny outputs: dedicated kernels (fixed summation order, no split-K)
     cudaStream_t sst = (cudaStream_t)stream;
     if (!transA) pdl_launch(skinny_nn_kernel<16>, ceil_div((int64_t)M * 32, 256), 256, 0, sst, M, N, K, A, lda, B, ldb, beta, C, ldc);
-    else pdl_launch(skinny_tn_kernel<16>, ceil_div(M, 32), 256, 0, sst, M, N, K, A, lda, B, ldb, beta, C, ldc);
+    else pdl_launch(skinny_tn_kernel<16>, ceil_div(M, 32), 512, 0, sst, M, N, K, A, lda, B, ldb, beta, C, ldc);
     TGAN_LAUNCHED();
     return 0;
   }

@@ -343,6 +343,8 @@ def _opt_of(trainer, grp):
 def state_dict(trainer):
     """Everything `tf.train.Saver()` would save for the reference's graph, as {TF variable name: ndarray}."""
     st = trainer.store
+    if getattr(trainer, 'fused_dp', None) is not None:      # Adam slots are sharded across the ranks: make them whole
+        trainer.fused_dp.gather_slots(st)
     out = {n: st.vars[n].data.detach().cpu().numpy().copy() for n in st.order}
     for grp, fb in st.flat.items():
         if 'm' not in fb:

@@ -350,10 +350,20 @@ class VariableStore:
             host = np.zeros(tot, np.float32)
             for p, o in zip(ps, offs):
                 host[o:o + p.size] = p.init_value.reshape(-1)
-            theta = torch.from_numpy(host).to(device)
+            # data-parallel runs place parameters and gradients in symmetric (peer-addressable) memory: ddp.FusedUpdate
+            alloc = self.alloc if (getattr(self, 'alloc', None) is not None and grp != '_state') else None
+            if alloc is not None:
+                theta = alloc(tot)
+                theta.copy_(torch.from_numpy(host))
+            else:
+                theta = torch.from_numpy(host).to(device)
             fb = dict(theta=theta, params=ps, offsets=offs, n=tot)
             if grp != '_state':
-                fb['grad'] = torch.zeros_like(theta)
+                if alloc is not None:
+                    fb['grad'] = alloc(tot)
+                    fb['grad'].zero_()
+                else:
+                    fb['grad'] = torch.zeros_like(theta)
                 fb['m'] = torch.zeros_like(theta)
                 fb['v'] = torch.zeros_like(theta)
             for p, o in zip(ps, offs):

@@ -114,3 +114,77 @@ class BucketedAllReduce:
             dist.all_reduce(self.fb['grad'], op=dist.ReduceOp.SUM, group=self.pg)
         self.flushed, self.done_evt = None, None
         return 1.0 / w
+
+
+def symmetric_allocator(device):
+    """-> alloc(n) returning fp32 tensors in symmetric memory (every rank allocates the same sizes in the same order), or
+    None when this is a single-process run / symmetric memory is unavailable (the NCCL all-reduce path is used then)."""
+    if world_size() <= 1 or os.environ.get('TGAN_DP_NCCL'):
+        return None
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+        if hasattr(symm_mem, 'enable_symm_mem_for_group'):
+            symm_mem.enable_symm_mem_for_group(dist.group.WORLD.group_name)
+        probe = symm_mem.empty(16, dtype=torch.float32, device=device)
+        symm_mem.rendezvous(probe, dist.group.WORLD)
+    except Exception as e:      # no peer access / old runtime: say so once, keep NCCL
+        if dist.get_rank() == 0:
+            print('tgan.ddp: symmetric memory unavailable (%s); gradients travel through ncclAllReduce' % str(e)[:200])
+        return None
+    return lambda n: symm_mem.empty(int(n), dtype=torch.float32, device=device)
+
+
+class FusedUpdate:
+    """reduce-scatter -> Adam on the owned shard -> all-gather of the parameters in ONE kernel over NVLink peer memory
+    (csrc/dp_fused.cu) instead of ncclAllReduce + Adam.  Needs the store's theta / grad buffers in symmetric memory
+    (VariableStore.alloc = ddp.symmetric_allocator(...) before finalize).  Adam's m / v slots are SHARDED: rank r keeps
+    the slice [r*per, (r+1)*per) current; `gather_slots` makes them whole again (checkpoints)."""
+
+    def __init__(self, store, device, pg=None):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm_mem
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        grp = dist.group.WORLD if pg is None else pg
+        self.flags = symm_mem.empty(16, dtype=torch.int32, device=device)
+        self.flags.zero_()
+        self.epoch = torch.zeros(2, dtype=torch.int32, device=device)
+        arr = lambda ptrs: (ctypes.c_uint64 * len(ptrs))(*[int(x) for x in ptrs])
+        self.flag_ptrs = arr(symm_mem.rendezvous(self.flags, grp).buffer_ptrs)
+        self.ptrs = {}
+        for name, fb in store.flat.items():
+            if 'grad' not in fb:
+                continue
+            g = symm_mem.rendezvous(fb['grad'], grp).buffer_ptrs
+            t = symm_mem.rendezvous(fb['theta'], grp).buffer_ptrs
+            self.ptrs[name] = (arr(g), arr(t))
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    def shard(self, n):
+        per = ((n // 4 + self.world - 1) // self.world) * 4
+        return per
+
+    def apply(self, name, fb, opt, ema=None, ema_decay=0.9999):
+        from . import _lib
+        st = torch.cuda.current_stream().cuda_stream
+        g, t = self.ptrs[name]
+        state = opt._state()
+        _lib.call('tgan_dp_barrier', self.flag_ptrs, self.rank, self.world, 0, self.epoch.data_ptr(), st)
+        _lib.call('tgan_dp_adam', g, t, fb['m'].data_ptr(), fb['v'].data_ptr(), fb['n'], self.rank, self.world,
+                  state.data_ptr(), opt.beta1, opt.beta2, opt.eps, st)
+        _lib.call('tgan_dp_barrier', self.flag_ptrs, self.rank, self.world, 1, self.epoch.data_ptr(), st)
+        if ema is not None:
+            _lib.call('tgan_ema', ema.data_ptr(), fb['theta'].data_ptr(), fb['n'], ema_decay, st)
+        _lib.call('tgan_adam_advance', state.data_ptr(), opt.beta1, opt.beta2, st)
+
+    def gather_slots(self, store):
+        """make every rank's m / v complete (each rank only keeps its own shard current)"""
+        for name, fb in store.flat.items():
+            if 'm' not in fb:
+                continue
+            per = self.shard(fb['n'])
+            for r in range(self.world):
+                lo, hi = r * per, min(fb['n'], (r + 1) * per)
+                if hi > lo:
+                    dist.broadcast(fb['m'][lo:hi], src=r)
+                    dist.broadcast(fb['v'][lo:hi], src=r)

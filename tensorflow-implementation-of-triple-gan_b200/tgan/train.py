@@ -153,6 +153,8 @@ class Train(Train_base):
             raise RuntimeError('call _build_train_graph(Model) first')
         if init is not None:
             self.store.load_numpy(*init)
+        # data parallel: parameters / gradients in peer-addressable memory for the fused update (ddp.FusedUpdate)
+        self.store.alloc = ddp.symmetric_allocator(ctx.device) if ctx.device.type == 'cuda' else None
         self.store.finalize(ctx.device)
         c = self.config
         self.d_optimizer = self._Adam_optimizer(lr=c.LEARNING_RATE, beta1=c.BETA1)
@@ -183,6 +185,7 @@ class Train(Train_base):
             self.model._whitener()._upload()
         self.world = ddp.world_size()
         ddp.broadcast_params(self.store, 0, self.pg)
+        self.fused_dp = ddp.FusedUpdate(self.store, ctx.device, self.pg) if self.store.alloc is not None else None
         # the EMA shadow starts from the parameters every rank actually trains with (rank 0's after the broadcast)
         self.ema.bind(self.store.flat['classifier'])
         return self
@@ -225,6 +228,11 @@ class Train(Train_base):
         return fb
 
     def _apply(self, fb, opt, ema=None, group=None):
+        if getattr(self, 'fused_dp', None) is not None:
+            # reduce-scatter -> Adam on the owned shard -> all-gather of the parameters, one kernel over NVLink peer memory
+            self.fused_dp.apply(group, fb, opt, ema.shadow if ema is not None else None, ema.decay if ema is not None else 0.0)
+            self.store.bump(group)
+            return
         if group == 'classifier' and self.world > 1 and ctx.math == 'bf16' and self.config.DATA_NAME == 'cifar10' \
                 and hasattr(self.model, '_whitener'):
             # the classifier's gradient travels in two buckets; the tail one was started behind its own backward pass

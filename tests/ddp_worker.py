@@ -40,6 +40,7 @@ def main():
     for grp in tr.store.GROUPS:
         res['theta:' + grp] = tr.store.flat[grp]['theta'].cpu().numpy().copy()
     res['ema'] = tr.ema.shadow.cpu().numpy().copy()
+    res['fused'] = np.array(1 if getattr(tr, 'fused_dp', None) is not None else 0)
     np.savez(os.path.join(out_dir, 'rank%d.npz' % rank), **res)
     torch.cuda.synchronize()
     torch.distributed.barrier()
