@@ -123,8 +123,6 @@ def symmetric_allocator(device):
         return None
     try:
         import torch.distributed._symmetric_memory as symm_mem
-        if hasattr(symm_mem, 'enable_symm_mem_for_group'):
-            symm_mem.enable_symm_mem_for_group(dist.group.WORLD.group_name)
         probe = symm_mem.empty(16, dtype=torch.float32, device=device)
         symm_mem.rendezvous(probe, dist.group.WORLD)
     except Exception as e:      # no peer access / old runtime: say so once, keep NCCL

@@ -82,10 +82,14 @@ def test_two_rank_step_equals_shard_averaged_oracle(tmp_path):
              for ph, names in (('D', orc.d_vars), ('G', orc.g_vars), ('C', orc.c_vars))}
     worst = 0.0
     for ph, names in (('D', orc.d_vars), ('G', orc.g_vars), ('C', orc.c_vars)):
+        dens = {n: max(np.abs(grads[n].numpy()).max(), 1e-3 * scale[ph]) for n in names}
+        # the float32 noise of these heavily cancelling gradients is a property of the network, one sample per tensor:
+        # a tensor is also allowed twice the worst floor any tensor of its network shows
+        phase_floor = max(np.abs(grads32[n].double().numpy() - grads[n].numpy()).max() / dens[n] for n in names)
         for n in names:
             ref = grads[n].numpy()
-            den = max(np.abs(ref).max(), 1e-3 * scale[ph])
-            floor = np.abs(grads32[n].double().numpy() - ref).max() / den
+            den = dens[n]
+            floor = max(np.abs(grads32[n].double().numpy() - ref).max() / den, 0.25 * phase_floor)
             fused = int(ranks[0]['fused']) == 1
             for r in range(2):
                 # NCCL path: the buffer holds the all-reduced SUM (Adam applies 1/world).  Fused peer-memory update: the
