@@ -352,7 +352,8 @@ def main():
         'config': {'workload': WORKLOADS[wl],
                    'global_batch': IMAGES_PER_STEP * world, 'parallelism': 'dp%d' % world,
                    'cuda_graph': graph, 'debug_env': dbg,
-                   'dp_update': ('n/a (1 GPU)' if world == 1 else 'fused reduce-scatter + Adam + all-gather kernel over NVLink peer memory'
+                   'dp_update': ('n/a (1 GPU)' if world == 1 else ('fused reduce-scatter + Adam + all-gather kernel over NVLink peer memory'
+                                  + (' (NVSwitch multimem.ld_reduce / multimem.st)' if tr.fused_dp.multimem else ' (peer loads / stores)'))
                                  if getattr(tr, 'fused_dp', None) is not None else 'ncclAllReduce + Adam'),
                    'l2': 'no explicit flush: one step streams > 1 GB of activations (>> 126 MB L2) between reuses'},
         'e2e': {'value': imgs / t_e2e, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 12,

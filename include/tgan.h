@@ -380,10 +380,13 @@ int tgan_adam(float* theta, float* m, float* v, const float* grad, int64_t n, co
  *   tgan_dp_adam    : rank r sums elements [r*per, (r+1)*per) of all gradient buffers in rank order, divides by world,
  *                     applies tgan_adam's update with its local m / v slice and writes the new parameters into EVERY
  *                     rank's theta buffer.  Call between tgan_dp_barrier(slot 0) and tgan_dp_barrier(slot 1).
+ *                     mc_grad / mc_theta (optional, both or neither): NVSwitch MULTICAST addresses of the same buffers;
+ *                     then the sum is one multimem.ld_reduce (added inside the switch) and the broadcast one multimem.st.
  *   tgan_ema        : shadow -= (shadow - theta) * (1 - decay) over the gathered parameters (Train_goodGAN.py:101-103) */
 int tgan_dp_barrier(const uint64_t* flag_ptrs, int rank, int world, int slot, int* epoch, void* stream);
-int tgan_dp_adam(const uint64_t* grad_ptrs, const uint64_t* theta_ptrs, float* m, float* v, int64_t n, int rank, int world,
-                 const float* state, float beta1, float beta2, float eps, void* stream);
+int tgan_dp_adam(const uint64_t* grad_ptrs, const uint64_t* theta_ptrs, const float* mc_grad, float* mc_theta, float* m,
+                 float* v, int64_t n, int rank, int world, const float* state, float beta1, float beta2, float eps,
+                 void* stream);
 int tgan_ema(float* ema, const float* theta, int64_t n, float decay, void* stream);
 /* beta1_power *= beta1, beta2_power *= beta2 (TF's _finish) */
 int tgan_adam_advance(float* state, float beta1, float beta2, void* stream);

@@ -41,6 +41,18 @@ __device__ __forceinline__ void st_peer_f4(float* p, float4 v) {
   asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// NVSwitch multicast (NVLS): ONE load returns the sum of the same address on every GPU (the switch adds), ONE store
+// reaches every GPU -- the owner of a shard moves 1/W of the bytes the peer-pointer version moves.
+__device__ __forceinline__ float4 ld_reduce_mc_f4(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_mc_f4(float* mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // flags: int [2 slots][8 ranks] per rank (symmetric); epoch: int [2] local counters
 __global__ void dp_barrier_kernel(DpPeers flags, int rank, int world, int slot, int* __restrict__ epoch) {
   pdl_entry();
@@ -66,7 +78,8 @@ __global__ void dp_barrier_kernel(DpPeers flags, int rank, int world, int slot, 
 }
 
 // one launch per network: rank r owns elements [r * per, min(n, (r + 1) * per))
-__global__ void __launch_bounds__(256) dp_adam_kernel(DpPeers grads, DpPeers thetas, float* __restrict__ m, float* __restrict__ v,
+__global__ void __launch_bounds__(256) dp_adam_kernel(DpPeers grads, DpPeers thetas, const float* __restrict__ mc_grad,
+                                                      float* __restrict__ mc_theta, float* __restrict__ m, float* __restrict__ v,
                                                       int64_t n, int64_t per, int rank, int world,
                                                       const float* __restrict__ state, float beta1, float beta2, float eps) {
   pdl_entry();
@@ -78,11 +91,15 @@ __global__ void __launch_bounds__(256) dp_adam_kernel(DpPeers grads, DpPeers the
   // (lo, hi and n are multiples of 4: the flat buffers pad every tensor to 4 elements)
   for (int64_t i = lo + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < hi; i += (int64_t)gridDim.x * blockDim.x * 4) {
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mc_grad) {
+      g = ld_reduce_mc_f4(mc_grad + i);      // summed inside the switch; every shard is reduced exactly once, by its owner
+    } else {
 #pragma unroll
-    for (int p = 0; p < 8; ++p) {      // fixed order: every shard is summed exactly once, by its owner
-      if (p >= world) break;
-      const float4 t = ld_peer_f4(reinterpret_cast<const float*>(grads.ptr[p]) + i);
-      g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+      for (int p = 0; p < 8; ++p) {      // fixed order
+        if (p >= world) break;
+        const float4 t = ld_peer_f4(reinterpret_cast<const float*>(grads.ptr[p]) + i);
+        g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+      }
     }
     const float4 t = *reinterpret_cast<const float4*>(th_local + i);
     const float4 mm = *reinterpret_cast<const float4*>(m + i), vv = *reinterpret_cast<const float4*>(v + i);
@@ -97,10 +114,14 @@ __global__ void __launch_bounds__(256) dp_adam_kernel(DpPeers grads, DpPeers the
     *reinterpret_cast<float4*>(m + i) = make_float4(ma[0], ma[1], ma[2], ma[3]);
     *reinterpret_cast<float4*>(v + i) = make_float4(va[0], va[1], va[2], va[3]);
     const float4 nt = make_float4(tt[0], tt[1], tt[2], tt[3]);
+    if (mc_theta) {
+      st_mc_f4(mc_theta + i, nt);
+    } else {
 #pragma unroll
-    for (int p = 0; p < 8; ++p) {
-      if (p >= world) break;
-      st_peer_f4(reinterpret_cast<float*>(thetas.ptr[p]) + i, nt);
+      for (int p = 0; p < 8; ++p) {
+        if (p >= world) break;
+        st_peer_f4(reinterpret_cast<float*>(thetas.ptr[p]) + i, nt);
+      }
     }
   }
 }
@@ -131,8 +152,9 @@ extern "C" int tgan_dp_barrier(const uint64_t* flag_ptrs, int rank, int world, i
   return 0;
 }
 
-extern "C" int tgan_dp_adam(const uint64_t* grad_ptrs, const uint64_t* theta_ptrs, float* m, float* v, int64_t n, int rank,
-                            int world, const float* state, float beta1, float beta2, float eps, void* stream) {
+extern "C" int tgan_dp_adam(const uint64_t* grad_ptrs, const uint64_t* theta_ptrs, const float* mc_grad, float* mc_theta, float* m,
+                            float* v, int64_t n, int rank, int world, const float* state, float beta1, float beta2, float eps,
+                            void* stream) {
   TGAN_CHECK_ARG(grad_ptrs && theta_ptrs && m && v && state && n > 0 && n % 4 == 0 && world >= 2 && world <= 8 && rank >= 0 &&
                      rank < world, "dp_adam: bad args (n %% 4 == 0, 2 <= world <= 8)");
   DpPeers g, t;
@@ -146,7 +168,8 @@ extern "C" int tgan_dp_adam(const uint64_t* grad_ptrs, const uint64_t* theta_ptr
   int grid = (int)((per / 4 + 255) / 256);
   if (grid > 148 * 4) grid = 148 * 4;
   if (grid < 1) grid = 1;
-  pdl_launch(dp_adam_kernel, grid, 256, 0, (cudaStream_t)stream, g, t, m, v, n, per, rank, world, state, beta1, beta2, eps);
+  pdl_launch(dp_adam_kernel, grid, 256, 0, (cudaStream_t)stream, g, t, mc_grad, mc_theta, m, v, n, per, rank, world, state, beta1,
+             beta2, eps);
   TGAN_LAUNCHED();
   return 0;
 }

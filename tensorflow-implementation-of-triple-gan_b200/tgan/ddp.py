@@ -152,9 +152,15 @@ class FusedUpdate:
         for name, fb in store.flat.items():
             if 'grad' not in fb:
                 continue
-            g = symm_mem.rendezvous(fb['grad'], grp).buffer_ptrs
-            t = symm_mem.rendezvous(fb['theta'], grp).buffer_ptrs
-            self.ptrs[name] = (arr(g), arr(t))
+            hg, ht = symm_mem.rendezvous(fb['grad'], grp), symm_mem.rendezvous(fb['theta'], grp)
+            mcg = mct = None
+            try:      # NVSwitch multicast addresses (NVLS) when the fabric has them
+                if not os.environ.get('TGAN_DP_NO_MULTIMEM') and int(hg.multicast_ptr) and int(ht.multicast_ptr):
+                    mcg, mct = int(hg.multicast_ptr), int(ht.multicast_ptr)
+            except Exception:
+                mcg = mct = None
+            self.ptrs[name] = (arr(hg.buffer_ptrs), arr(ht.buffer_ptrs), mcg, mct)
+        self.multimem = all(p[2] is not None for p in self.ptrs.values())
         torch.cuda.synchronize()
         dist.barrier()
 
@@ -165,10 +171,10 @@ class FusedUpdate:
     def apply(self, name, fb, opt, ema=None, ema_decay=0.9999):
         from . import _lib
         st = torch.cuda.current_stream().cuda_stream
-        g, t = self.ptrs[name]
+        g, t, mcg, mct = self.ptrs[name]
         state = opt._state()
         _lib.call('tgan_dp_barrier', self.flag_ptrs, self.rank, self.world, 0, self.epoch.data_ptr(), st)
-        _lib.call('tgan_dp_adam', g, t, fb['m'].data_ptr(), fb['v'].data_ptr(), fb['n'], self.rank, self.world,
+        _lib.call('tgan_dp_adam', g, t, mcg, mct, fb['m'].data_ptr(), fb['v'].data_ptr(), fb['n'], self.rank, self.world,
                   state.data_ptr(), opt.beta1, opt.beta2, opt.eps, st)
         _lib.call('tgan_dp_barrier', self.flag_ptrs, self.rank, self.world, 1, self.epoch.data_ptr(), st)
         if ema is not None:
