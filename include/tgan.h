@@ -158,6 +158,13 @@ int64_t tgan_wgrad_workspace_bytes(const tgan_wgrad_args* a);
 int tgan_sizeof_igemm_args(void);
 int tgan_sizeof_wgrad_args(void);
 
+/* The generator's last layer (Good_GAN_cifar10.py:56): 5x5 / stride 2 / SAME transposed convolution with <= 8 output
+ * channels on a 16x16 input, bias and optional tanh fused: y[N,32,32,Cout] fp32 = act(conv2d_transpose(x, w) + bias).
+ * x: bf16 [N,16,16,ldx] (first Cin <= 144 channels), w: fp32 [5,5,Cout,Cin] (the TF filter as it is).  Pixels are the MMA
+ * rows (mma.sync m16n8k16), one CTA per image: replaces a 128-lane tcgen05 launch that used 3 lanes. */
+int tgan_deconv5s2_skinny(const void* x, int N, int ldx, int Cin, const float* w, const float* bias, int Cout, float* y,
+                          int act, void* stream);
+
 /* weight preparation for the tcgen05 path: fp32 weights (any TF layout, addressed by strides) ->
  * bf16 K-major [T][Nrows][Kpad]:  dst[t][n][k] = k < K ? src[taps[t]*st + n*sn + k*sk] : 0
  * (taps_dev = NULL -> identity).  fprop HWIO: Nrows=Cout,K=Cin,sn=1,sk=Cout; dgrad HWIO: Nrows=Cin,K=Cout,

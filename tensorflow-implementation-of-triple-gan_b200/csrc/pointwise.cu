@@ -623,9 +623,11 @@ __global__ void mobn_pool_dropout_fwd_kernel(const bf16* __restrict__ z, bf16* _
   extern __shared__ float pool_sm[];      // [256 * 8] staged outputs, then [9][C] class table
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nvec) return;
-  const int cv = C / 8, Wo = W / 2, Ho = H / 2;
-  const int c = (int)(i % cv) * 8;
-  int64_t t = i / cv;
+  // 32-bit index arithmetic (the host checks nvec < 2^31): 64-bit divisions were a third of this kernel's instructions
+  const unsigned cv = C / 8, Wo = W / 2, Ho = H / 2;
+  const unsigned iu = (unsigned)i;
+  const int c = (int)(iu % cv) * 8;
+  unsigned t = iu / cv;
   const int wo = (int)(t % Wo); t /= Wo;
   const int ho = (int)(t % Ho);
   const int64_t n = t / Ho;
@@ -731,9 +733,11 @@ __global__ void __launch_bounds__(256) mobn_pool_dropout_bwd_kernel(const bf16* 
   int cur = -1;
   const float inv_scale = 1.f / scale;
   for (int64_t r = rbeg + tr; r < rend; r += rl) {          // r = pooled pixel index (n, ho, wo)
-    const int wo = (int)(r % Wo);
-    const int ho = (int)((r / Wo) % Ho);
-    const int64_t n = r / ((int64_t)Wo * Ho);
+    const unsigned ru = (unsigned)r, q = ru / (unsigned)Wo;   // 32-bit arithmetic (host checks the pixel count < 2^31)
+    const int wo = (int)(ru - q * (unsigned)Wo);
+    const unsigned nn = q / (unsigned)Ho;
+    const int ho = (int)(q - nn * (unsigned)Ho);
+    const int64_t n = nn;
     const int s = sg.of(n * rows_per_img);
     if (s != cur) {
       if (cur >= 0) {
@@ -1335,6 +1339,7 @@ extern "C" int tgan_mobn_pool_dropout_fwd(const void* z, void* y, uint8_t* code,
   Segs sg;      // segment boundaries are given in images; Segs works on full-resolution rows
   if (make_segs(sg, (int64_t)N * rpi, nseg, n0 * rpi, n1 * rpi, n2 * rpi)) return 1;
   const int64_t nvec = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
+  TGAN_CHECK_ARG(nvec < (1ll << 31), "mobn_pool_dropout_fwd: more than 2^31 output vectors");
   cudaStream_t st = (cudaStream_t)stream;
   TGAN_CHECK_ARG(!clsum || ((int64_t)(H / 2) * (W / 2) * (C / 8)) % 256 == 0,
                  "mobn_pool_dropout_fwd: class sums need whole CTAs per image ((H/2)*(W/2)*(C/8) %% 256 == 0)");
@@ -1357,6 +1362,7 @@ extern "C" int tgan_mobn_pool_dropout_bwd(const void* dy, const void* y, const u
   const int nparts = TGAN_ACT_BWD_SEG_PARTS;
   const size_t smem = (size_t)(2048 / C) * 4 * C * sizeof(float);
   const int64_t prows = (int64_t)N * (H / 2) * (W / 2);
+  TGAN_CHECK_ARG(prows < (1ll << 31), "mobn_pool_dropout_bwd: more than 2^31 pooled pixels");
   cudaStream_t st = (cudaStream_t)stream;
   TGAN_DISPATCH_ACT(act, A, (pdl_launch(mobn_pool_dropout_bwd_kernel<A>, nparts, 256, smem, st, (const bf16*)dy,
                                         (const bf16*)y, code, (bf16*)du, H, W, C, prows, sg, rpi, alpha, 1.0f / (1.0f - rate),

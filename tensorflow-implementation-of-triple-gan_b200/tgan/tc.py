@@ -317,6 +317,13 @@ def deconv_fwd(x, w, g, bias=None, act=0, ldo=None):
     xd, ld = _bf16_padded(x.data, x.rows, Cin, x.ld)
     g['_x'] = (xd, ld)
     skinny = _skinny(g)
+    if (skinny and g['h'] == 16 and g['w'] == 16 and g['kh'] == 5 and g['kw'] == 5 and g['s'] == 2 and Cin <= 144 and act in (0, 3)
+            and getattr(w, 'scale', 1) is None and not os.environ.get('TGAN_NO_SKINNY_DECONV')):
+        # the generator's RGB layer: pixels on the MMA rows, one CTA per image (csrc/deconv_skinny.cu)
+        yf = _new((g['N'], g['Ho'], g['Wo'], Cout), torch.float32)
+        _lib.call('tgan_deconv5s2_skinny', xd.data_ptr(), g['N'], ld, Cin, w.value().data_ptr(),
+                  None if bias is None else bias.data_ptr(), Cout, yf.data_ptr(), act, _st())
+        return yf
     ldo = 8 if skinny else (ldo or Cout)
     y = _new((g['N'], g['Ho'], g['Wo'], ldo), torch.bfloat16)
     cl = sorted(_parity_classes(g), key=lambda c: -len(c[2]))      # heaviest class first, all in ONE launch
