@@ -304,12 +304,11 @@ int tgan_maxpool2_dropout_bwd(const void* dy, const uint8_t* code, void* dx, int
  * segments in IMAGES (n0,n1,n2 = exclusive end images of segments 0..2), sums fp32 [nseg][C] as tgan_mobn_apply_seg.
  * y / code as tgan_maxpool2_dropout_fwd.  bwd: du[N,H,W,C] = at the window winner keep * dy/(1-rate) * act'(y_winner),
  * zero elsewhere; colsums[seg][c] = per-segment sums of du, grad_acc[c] += total (the bias gradient).
- * ws: 4*TGAN_ACT_BWD_SEG_PARTS*C floats.  clsum (optional, training): int64 Q24 [nseg][9][C] += border-class sums of the
- * pooled output (layout of tgan_igemm_bf16.clsum) for the next convolution's fused mean-only BN. */
+ * ws: 4*TGAN_ACT_BWD_SEG_PARTS*C floats. */
 int tgan_mobn_pool_dropout_fwd(const void* z, void* y, uint8_t* code, int N, int H, int W, int C, int nseg, int64_t n0,
                                int64_t n1, int64_t n2, const void* sums, int sums_q24, const float* b, float* pop_mean,
                                float decay, int train, int act, float alpha, float rate, const uint8_t* mask, uint64_t seed,
-                               uint64_t stream_id, const uint64_t* counter, void* clsum, void* stream);
+                               uint64_t stream_id, const uint64_t* counter, void* stream);
 int tgan_mobn_pool_dropout_bwd(const void* dy, const void* y, const uint8_t* code, void* du, int N, int H, int W, int C,
                                int nseg, int64_t n0, int64_t n1, int64_t n2, int act, float alpha, float rate,
                                float* colsums, float* grad_acc, float* ws, void* stream);

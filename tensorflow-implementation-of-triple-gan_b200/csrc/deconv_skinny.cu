@@ -43,7 +43,8 @@ __global__ void __launch_bounds__(256, 1) deconv5s2_skinny_kernel(const bf16* __
   bf16* xs = reinterpret_cast<bf16*>(ds_smem);                        // [18][18][DS_PIX]
   bf16* ws = xs + 18 * 18 * DS_PIX;                                   // [25][144][8]
   const int n = blockIdx.x, tid = threadIdx.x;
-  // ---- stage: zero everything (halo, channel padding), then the image and the filter
+  // ---- stage: zero everything (halo, channel padding), then the image (cp.async: every 16-byte piece in flight at once)
+  // and the filter (eight independent loads per thread and round; one load per round made this phase latency bound)
   {
     uint4* z = reinterpret_cast<uint4*>(ds_smem);
     const int nz = (18 * 18 * DS_PIX + 25 * 144 * 8) * 2 / 16;
@@ -51,21 +52,36 @@ __global__ void __launch_bounds__(256, 1) deconv5s2_skinny_kernel(const bf16* __
   }
   __syncthreads();
   {
-    const int vpp = (Cin + 7) / 8;                                    // 16-byte vectors per pixel that hold real channels
+    const int vfull = Cin / 8, vpp = (Cin + 7) / 8;                   // whole / all 16-byte vectors per pixel with real channels
     const bf16* xi = x + (int64_t)n * 256 * ldx;
-    for (int i = tid; i < 256 * vpp; i += 256) {
-      const int px = i / vpp, v = i - px * vpp;
+    for (int i = tid; i < 256 * vfull; i += 256) {
+      const int px = i / vfull, v = i - px * vfull;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(xs + ((px / 16 + 1) * 18 + (px % 16 + 1)) * DS_PIX + v * 8);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(xi + (int64_t)px * ldx + v * 8) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (vpp > vfull && tid < 256) {                                   // the last, partial vector of every pixel
+      const int px = tid, v = vfull;
       uint4 u = *reinterpret_cast<const uint4*>(xi + (int64_t)px * ldx + v * 8);
-      if (v * 8 + 8 > Cin) {                                          // channels beyond Cin (the zero pad of the concat buffer)
-        bf16* e = reinterpret_cast<bf16*>(&u);
-        for (int j = 0; j < 8; ++j) if (v * 8 + j >= Cin) e[j] = __float2bfloat16_rn(0.f);
-      }
+      bf16* e = reinterpret_cast<bf16*>(&u);
+      for (int j = 0; j < 8; ++j) if (v * 8 + j >= Cin) e[j] = __float2bfloat16_rn(0.f);
       *reinterpret_cast<uint4*>(xs + ((px / 16 + 1) * 18 + (px % 16 + 1)) * DS_PIX + v * 8) = u;
     }
-    for (int i = tid; i < 25 * Cout * Cin; i += 256) {                // w[t][co][ci] -> ws[t][ci][co]
-      const int ci = i % Cin, co = (i / Cin) % Cout, t = i / (Cin * Cout);
-      ws[(t * 144 + ci) * 8 + co] = __float2bfloat16_rn(w[i]);
+    const int total = 25 * Cout * Cin;                                // w[t][co][ci] -> ws[t][ci][co]
+    for (int base = 0; base < total; base += 256 * 8) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const int i = base + k * 256 + tid; v[k] = i < total ? __ldg(w + i) : 0.f; }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = base + k * 256 + tid;
+        if (i < total) {
+          const int ci = i % Cin, co = (i / Cin) % Cout, t = i / (Cin * Cout);
+          ws[(t * 144 + ci) * 8 + co] = __float2bfloat16_rn(v[k]);
+        }
+      }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
   }
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31;
@@ -75,35 +91,37 @@ __global__ void __launch_bounds__(256, 1) deconv5s2_skinny_kernel(const bf16* __
   if (bias) { b0 = 2 * q < Cout ? bias[2 * q] : 0.f; b1 = 2 * q + 1 < Cout ? bias[2 * q + 1] : 0.f; }
   for (int oy = warp; oy < 32; oy += 8) {
     const int py = oy & 1;
-#pragma unroll 1
-    for (int px = 0; px < 2; ++px) {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int r = (py + 1) & 1; r < 5; r += 2) {
-        const int iy = (oy + 1 - r) / 2;                              // exact: the numerator is even; -1 <= iy <= 16
-        for (int c = (px + 1) & 1; c < 5; c += 2) {
-          const int ix0 = (px + 1 - c) / 2;                           // input column of output column ox = px (may be -1)
-          // A: rows = 16 consecutive input pixels of row iy starting at ix0, cols = 16 channels of the K step
-          const bf16* arow = xs + ((iy + 1) * 18 + (ix0 + 1) + (lane & 7) + 8 * ((lane >> 3) & 1)) * DS_PIX + 8 * (lane >> 4);
-          const bf16* brow = ws + ((r * 5 + c) * 144 + (lane & 15)) * 8;
-          for (int ks = 0; ks < ksteps; ++ks) {
-            uint32_t a[4], b[2];
-            ldsm_x4(a, arow + ks * 16);
-            ldsm_x2_trans(b, brow + ks * 16 * 8);
-            mma_bf16_16816(acc, a, b);
-          }
+    // both column parities of the row advance together: two independent accumulator chains hide the MMA latency
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    for (int r = (py + 1) & 1; r < 5; r += 2) {
+      const int iy = (oy + 1 - r) / 2;                                // exact: the numerator is even; -1 <= iy <= 16
+      const bf16* xrow = xs + ((iy + 1) * 18 + (lane & 7) + 8 * ((lane >> 3) & 1)) * DS_PIX + 8 * (lane >> 4);
+      const bf16* wrow = ws + (r * 5 * 144 + (lane & 15)) * 8;
+      // px = 0 uses column taps c = 1, 3 (ix0 = 0, -1); px = 1 uses c = 0, 2, 4 (ix0 = 1, 0, -1)
+      for (int ks = 0; ks < ksteps; ++ks) {
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {                                 // consecutive MMAs alternate between the two chains
+          const int px = (c & 1) ^ 1;                                 // parity of the output columns tap c reaches
+          const int ix0 = (px + 1 - c) / 2;                           // input column of the first such output column
+          uint32_t a[4], b[2];
+          ldsm_x4(a, xrow + (ix0 + 1) * DS_PIX + ks * 16);
+          ldsm_x2_trans(b, wrow + (c * 144 + ks * 16) * 8);
+          mma_bf16_16816(acc[px], a, b);
         }
       }
-      // C fragment: rows g and g + 8 (output columns px + 2g, px + 2(g + 8)), channels 2q, 2q + 1
+    }
+    // C fragment: rows g and g + 8 (output columns px + 2g, px + 2(g + 8)), channels 2q, 2q + 1
+#pragma unroll
+    for (int px = 0; px < 2; ++px)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int ox = px + 2 * (g + 8 * h);
-        float v0 = acc[2 * h] + b0, v1 = acc[2 * h + 1] + b1;
+        float v0 = acc[px][2 * h] + b0, v1 = acc[px][2 * h + 1] + b1;
         if (act == TGAN_ACT_TANH) { v0 = tanhf(v0); v1 = tanhf(v1); }
         float* o = y + (((int64_t)n * 32 + oy) * 32 + ox) * Cout;
         if (2 * q < Cout) o[2 * q] = v0;
         if (2 * q + 1 < Cout) o[2 * q + 1] = v1;
       }
-    }
   }
 }
 

@@ -607,7 +607,7 @@ __global__ void mobn_pool_dropout_fwd_kernel(const bf16* __restrict__ z, bf16* _
                                              int rows_per_img, const float* __restrict__ b, float* __restrict__ pop_mean,
                                              float decay, int train, float alpha, float rate, float scale,
                                              const uint8_t* __restrict__ mask, uint64_t seed, uint64_t stream_id,
-                                             const uint64_t* __restrict__ counter, long long* __restrict__ clsum) {
+                                             const uint64_t* __restrict__ counter) {
   pdl_entry();
   if (train && pop_mean && blockIdx.x == 0) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -616,11 +616,6 @@ __global__ void mobn_pool_dropout_fwd_kernel(const bf16* __restrict__ z, bf16* _
       pop_mean[c] = pm;
     }
   }
-  // optional border-class sums of the pooled output: the next convolution's batch mean is a linear function of them
-  // (csrc/mobn_fused.cu).  The CTA's 256 / (C/8) pooled pixels are staged in shared memory; thread c then walks them in a
-  // fixed order into ITS column of a [9][C] table (no atomics inside the CTA) and the non-zero entries leave as Q24
-  // integer atomics.  The host guarantees whole CTAs per image (hence one batch segment per CTA).
-  extern __shared__ float pool_sm[];      // [256 * 8] staged outputs, then [9][C] class table
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nvec) return;
   // 32-bit index arithmetic (the host checks nvec < 2^31): 64-bit divisions were a third of this kernel's instructions
@@ -681,30 +676,6 @@ __global__ void mobn_pool_dropout_fwd_kernel(const bf16* __restrict__ z, bf16* _
   cw.x = cd[0] | (cd[1] << 8) | (cd[2] << 16) | ((uint32_t)cd[3] << 24);
   cw.y = cd[4] | (cd[5] << 8) | (cd[6] << 16) | ((uint32_t)cd[7] << 24);
   *reinterpret_cast<uint2*>(code + e) = cw;
-  if (clsum) {
-    float* stage = pool_sm;                      // [pixels of this CTA][C]
-    float* tab = pool_sm + 256 * 8;              // [9][C]
-    const int px_cta = 256 / cv;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) stage[(threadIdx.x / cv) * C + c + j] = __bfloat162float(__float2bfloat16_rn(o[j]));
-    for (int q = threadIdx.x; q < 9 * C; q += blockDim.x) tab[q] = 0.f;
-    __syncthreads();      // (every thread of the CTA is alive here: nvec is a multiple of the CTA size when clsum is set)
-    // (the CTA's pixels lie inside one image: the class only needs the pixel index within the image, 32-bit arithmetic)
-    const int t0 = (int)((((int64_t)blockIdx.x * blockDim.x) / cv) % ((int64_t)Ho * Wo));
-    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
-      for (int q = 0; q < px_cta; ++q) {
-        const int tt = t0 + q, w2 = tt % Wo, h2 = tt / Wo;
-        const int k = (h2 == 0 ? 0 : h2 == Ho - 1 ? 2 : 1) * 3 + (w2 == 0 ? 0 : w2 == Wo - 1 ? 2 : 1);
-        tab[k * C + ch] += stage[q * C + ch];
-      }
-      for (int k = 0; k < 9; ++k) {
-        const float v = tab[k * C + ch];
-        if (v != 0.f)
-          atomicAdd(reinterpret_cast<unsigned long long*>(&clsum[((int64_t)s * 9 + k) * C + ch]),
-                    (unsigned long long)__float2ll_rn(v * 16777216.f));
-      }
-    }
-  }
 }
 
 // backward of the fused pass: du (full resolution) = winner ? keep * dy/(1-rate) * act'(y_winner) : 0, with per-segment
@@ -1327,7 +1298,7 @@ extern "C" int tgan_mobn_pool_dropout_fwd(const void* z, void* y, uint8_t* code,
                                           const float* b, float* pop_mean, float decay, int train, int act, float alpha,
                                           float rate,
                                           const uint8_t* mask, uint64_t seed, uint64_t stream_id, const uint64_t* counter,
-                                          void* clsum, void* stream) {
+                                          void* stream) {
   TGAN_CHECK_ARG(z && y && code && b && H % 2 == 0 && W % 2 == 0 && C % 8 == 0 && rate >= 0.f && rate < 1.f &&
                      aligned16(z) && aligned16(y) && aligned16(b) && ((uintptr_t)code & 7) == 0,
                  "mobn_pool_dropout_fwd: bf16, even extents, C %% 8 == 0, aligned buffers");
@@ -1341,12 +1312,9 @@ extern "C" int tgan_mobn_pool_dropout_fwd(const void* z, void* y, uint8_t* code,
   const int64_t nvec = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
   TGAN_CHECK_ARG(nvec < (1ll << 31), "mobn_pool_dropout_fwd: more than 2^31 output vectors");
   cudaStream_t st = (cudaStream_t)stream;
-  TGAN_CHECK_ARG(!clsum || ((int64_t)(H / 2) * (W / 2) * (C / 8)) % 256 == 0,
-                 "mobn_pool_dropout_fwd: class sums need whole CTAs per image ((H/2)*(W/2)*(C/8) %% 256 == 0)");
-  const size_t smem = clsum ? (size_t)(256 * 8 + 9 * C) * sizeof(float) : 0;
-  TGAN_DISPATCH_ACT(act, A, (pdl_launch(mobn_pool_dropout_fwd_kernel<A>, ceil_div(nvec, 256), 256, smem, st, (const bf16*)z,
+  TGAN_DISPATCH_ACT(act, A, (pdl_launch(mobn_pool_dropout_fwd_kernel<A>, ceil_div(nvec, 256), 256, 0, st, (const bf16*)z,
                                         (bf16*)y, code, H, W, C, nvec, sums, sums_q24, sg, rpi, b, pop_mean, decay, train, alpha, rate,
-                                        1.0f / (1.0f - rate), mask, seed, stream_id, counter, (long long*)clsum)));
+                                        1.0f / (1.0f - rate), mask, seed, stream_id, counter)));
   TGAN_LAUNCHED();
   return 0;
 }

@@ -707,7 +707,7 @@ def mobn_act(z, b, pop_mean, train, act='none', alpha=0.2, decay=0.9):
             seed, sid, ctr = rng.seed, rng.stream_id(str(tag)), rng.counter()
         _lib.call('tgan_mobn_pool_dropout_fwd', _p(zd), _p(y), _p(code), N, H, W, C, len(segs), iends[0], iends[1], iends[2],
                   _p(sums), 1 if cs_all is not None else 0, _p(b.data), _p(pop_mean.data), decay, 1 if train else 0, a, alpha,
-                  float(rate), _p(mask), seed, sid, _p(ctr), None, _st())
+                  float(rate), _p(mask), seed, sid, _p(ctr), _st())
         pout._data, pout._lazy = y, None
         if clo is not None:      # one pass over the (L2-resident) pooled tensor: one CTA per image, fixed summation order
             se = (ctypes.c_int * 3)(*iends[:3])

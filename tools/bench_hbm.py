@@ -99,7 +99,7 @@ for H, C in ((32, 128), (16, 256)):
         ctr = torch.zeros(1, dtype=torch.int64, device='cuda')
         t = timed(lambda i: _lib.call('tgan_mobn_pool_dropout_fwd', p(xs[i % k]), p(po[i % k]), p(code[i % k]), N, H, H, C, 4,
                                       iends[0], iends[1], iends[2], p(sums), 0, p(b), p(pm), 0.9, 1, 2, 0.2, 0.5, None, 7, 3,
-                                      p(ctr), None, st()), reps)
+                                      p(ctr), st()), reps)
         row('mobn_pool_dropout_fwd (BN+lrelu+pool+drop) ' + tag, N, nb + nb // 4 + nb // 8, t)
         t = timed(lambda i: _lib.call('tgan_mobn_pool_dropout_bwd', p(po[i % k]), p(po[(i + 1) % k]), p(code[i % k]), p(dus[i % k]),
                                       N, H, H, C, 4, iends[0], iends[1], iends[2], 2, 0.2, 0.5, p(cs), p(gb), p(ws), st()), reps)
