@@ -107,27 +107,48 @@ __global__ void __launch_bounds__(256) wn_bwd_apply_kernel(const tgan_wn_desc* _
 // dst[t][n][k] (bf16, k < Kpad) = k < K ? src[taps[t]*st + n*sn + k*sk] * scale : 0, in 32x32 (n, k) tiles.  One of the
 // source strides is 1 in every layout the step uses; when it is the n stride the tile is transposed through shared
 // memory so that both the fp32 reads and the bf16 writes are coalesced.
-__global__ void __launch_bounds__(256) pack_multi_kernel(const tgan_pack_desc* __restrict__ descs) {
+// One wave of persistent CTAs over a FLAT list of 32x32 tiles of all tensors (the descriptor table and the running tile
+// counts are staged in shared memory once per CTA).  The first version launched 592 CTAs per tensor: ~12,000 CTAs per
+// network, most of which read their descriptor and left -- ten waves of latency for 6 us of memory traffic.
+constexpr int PACK_MAX_DESCS = 64;
+__global__ void __launch_bounds__(256) pack_multi_kernel(const tgan_pack_desc* __restrict__ descs, int n0, int n) {
   pdl_entry();
-  const tgan_pack_desc d = descs[blockIdx.y];
+  __shared__ tgan_pack_desc ds[PACK_MAX_DESCS];
+  __shared__ int first[PACK_MAX_DESCS + 1];      // first flat tile of every tensor
   __shared__ float sm[32][33];
-  const int nbk = (d.Kpad + 31) / 32, nbn = (d.Nr + 31) / 32;
-  const int tiles = d.T * nbn * nbk;
-  bf16* dst = reinterpret_cast<bf16*>(d.dst);
+  for (int i = threadIdx.x; i < n * (int)(sizeof(tgan_pack_desc) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(ds)[i] = reinterpret_cast<const uint32_t*>(descs + n0)[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int i = 0; i < n; ++i) {
+      first[i] = acc;
+      acc += ds[i].T * ((ds[i].Nr + 31) / 32) * ((ds[i].Kpad + 31) / 32);
+    }
+    first[n] = acc;
+  }
+  __syncthreads();
+  const int total = first[n];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const bool transpose = d.sk != 1 && d.sn == 1;
-  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+  int di = 0;
+  for (int ft = blockIdx.x; ft < total; ft += gridDim.x) {
+    while (ft >= first[di + 1]) ++di;            // flat tiles are visited in increasing order
+    const tgan_pack_desc& d = ds[di];
+    const int tile = ft - first[di];
+    const int nbk = (d.Kpad + 31) / 32, nbn = (d.Nr + 31) / 32;
+    bf16* dst = reinterpret_cast<bf16*>(d.dst);
+    const bool transpose = d.sk != 1 && d.sn == 1;
     const int kb = tile % nbk, nb = (tile / nbk) % nbn, t = tile / (nbk * nbn);
     const int64_t base = (int64_t)(d.taps ? d.taps[t] : t) * d.st;
     if (transpose) {
-      const int n = nb * 32 + tx;
+      const int n_ = nb * 32 + tx;
 #pragma unroll
       for (int j = ty; j < 32; j += 8) {
         const int k = kb * 32 + j;
         float v = 0.f;
-        if (k < d.K && n < d.Nr) {
-          v = d.src[base + n + k * d.sk];
-          if (d.scale_on == 1) v *= d.scale[n];
+        if (k < d.K && n_ < d.Nr) {
+          v = d.src[base + n_ + k * d.sk];
+          if (d.scale_on == 1) v *= d.scale[n_];
           else if (d.scale_on == 2) v *= d.scale[k];
         }
         sm[j][tx] = v;
@@ -144,15 +165,15 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const tgan_pack_desc* _
       const int k = kb * 32 + tx;
 #pragma unroll
       for (int j = ty; j < 32; j += 8) {
-        const int n = nb * 32 + j;
-        if (n >= d.Nr || k >= d.Kpad) continue;
+        const int n_ = nb * 32 + j;
+        if (n_ >= d.Nr || k >= d.Kpad) continue;
         float v = 0.f;
         if (k < d.K) {
-          v = d.src[base + n * d.sn + k * d.sk];
-          if (d.scale_on == 1) v *= d.scale[n];
+          v = d.src[base + n_ * d.sn + k * d.sk];
+          if (d.scale_on == 1) v *= d.scale[n_];
           else if (d.scale_on == 2) v *= d.scale[k];
         }
-        dst[((int64_t)t * d.Nr + n) * d.Kpad + k] = __float2bfloat16_rn(v);
+        dst[((int64_t)t * d.Nr + n_) * d.Kpad + k] = __float2bfloat16_rn(v);
       }
     }
   }
@@ -185,7 +206,10 @@ extern "C" int tgan_weightnorm_bwd_multi(const tgan_wn_desc* descs_dev, int n, i
 }
 extern "C" int tgan_pack_weight_multi(const tgan_pack_desc* descs_dev, int n, void* stream) {
   TGAN_CHECK_ARG(descs_dev && n > 0, "pack_weight_multi: bad args");
-  pdl_launch(pack_multi_kernel, dim3(148 * 4, n), 256, 0, (cudaStream_t)((cudaStream_t)stream), descs_dev);
-  TGAN_LAUNCHED();
+  for (int n0 = 0; n0 < n; n0 += PACK_MAX_DESCS) {      // (a network has 10-40 packed operands: one launch)
+    const int cnt = n - n0 < PACK_MAX_DESCS ? n - n0 : PACK_MAX_DESCS;
+    pdl_launch(pack_multi_kernel, 148 * 8, 256, 0, (cudaStream_t)stream, descs_dev, n0, cnt);
+    TGAN_LAUNCHED();
+  }
   return 0;
 }
