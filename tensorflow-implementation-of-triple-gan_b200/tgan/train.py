@@ -418,6 +418,19 @@ class Train(Train_base):
         self.graph = g
         return g
 
+    def close(self):
+        """Orderly shutdown: drop the captured graph (it may hold collective / peer-memory launches) BEFORE the process
+        group goes away, wait for the device, then leave the group.  Safe to call more than once."""
+        self.graph = None
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        self.fused_dp = None
+        self._c_buckets = None
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.barrier()
+            dist.destroy_process_group()
+
     # ------------------------------------------------------------------ evaluation (SURVEY §8f rank 2) --
     def evaluate(self, x, y, reset=True):
         """Validation pass of Train_goodGAN.py:296-351 with the metric of :428-447: the classifier with train=False

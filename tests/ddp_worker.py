@@ -42,9 +42,7 @@ def main():
     res['ema'] = tr.ema.shadow.cpu().numpy().copy()
     res['fused'] = np.array(1 if getattr(tr, 'fused_dp', None) is not None else 0)
     np.savez(os.path.join(out_dir, 'rank%d.npz' % rank), **res)
-    torch.cuda.synchronize()
-    torch.distributed.barrier()
-    torch.distributed.destroy_process_group()
+    tr.close()              # orderly: graph, device, process group
 
 
 if __name__ == '__main__':
