@@ -201,8 +201,10 @@ class Tape:
         made current for the duration, so it can be differentiated outside the `recording()` block that built it."""
         old, ctx.tape = ctx.tape, self
         try:
+            from . import ops
             for fn in reversed(self.nodes):
                 fn()
+            ops.join_side_if_pending()      # filter gradients parked on the side stream (ops.defer_join)
             for fn in self.post:
                 fn()
         finally:

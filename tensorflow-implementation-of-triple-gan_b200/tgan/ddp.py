@@ -89,6 +89,8 @@ class BucketedAllReduce:
         if world_size() <= 1 or self.flushed is tape or entry['off'] is None or entry['off'] >= self.split:
             return
         # first filter gradient of a head layer: every tail layer's dW, bias gradient and g / V inputs are final
+        from . import ops
+        ops.join_side_if_pending()      # (small tail layers computed theirs on the side stream)
         self.flushed = tape
         grp.flush_bucket(lambda x: x['off'] is not None and x['off'] >= self.split)
         if self.stream is None:

@@ -85,11 +85,30 @@ class side_stream:
 
 
 def join_side():
+    ctx.side_keep, ctx.side_dirty = [], False
     if ctx.side is None:
         return
     ev = torch.cuda.Event()
     ev.record(ctx.side)
     torch.cuda.current_stream().wait_event(ev)
+
+
+def defer_join(keep):
+    """A filter gradient was enqueued on the side stream; nothing on the main stream needs its result (dW) before the
+    backward pass ends, so the join is postponed to Tape.backward's tail (the side stream's filter gradients then
+    overlap the whole chain of input gradients instead of one layer each).  `keep`: every tensor the side-stream
+    kernels still read -- held alive until the join so the caching allocator cannot hand their memory to the main
+    stream meanwhile."""
+    if os.environ.get('TGAN_EAGER_JOIN'):
+        join_side()
+        return
+    ctx.side_keep = getattr(ctx, 'side_keep', []) + [keep]
+    ctx.side_dirty = True
+
+
+def join_side_if_pending():
+    if getattr(ctx, 'side_dirty', False):
+        join_side()
 
 
 class TagList:

@@ -279,8 +279,8 @@ def conv_bwd(x, w, g, dz):
         if staged:
             _lib.call('tgan_copy_channels', dx.data_ptr(), BF16, Cs, dxt.data_ptr(), dt_code(dxt), Cg, x.rows, Cg, _st())
         add_grad(tgt, dxt if dxt.dtype == tgt.data.dtype else dxt.to(tgt.data.dtype))
-    if par:
-        _ops().join_side()
+    if par:      # the side stream still reads these; the join waits until the backward pass ends (ops.defer_join)
+        _ops().defer_join([dzb, dz, g.get('_x'), g.get('_col'), x.data])
     g.pop('_x', None)
     g.pop('_col', None)
 
@@ -400,5 +400,5 @@ def deconv_bwd(x, w, g, dy):
                    s=2)
         add_grad(tgt, dx if dx.dtype == tgt.data.dtype else dx.to(tgt.data.dtype))
     if par:
-        _ops().join_side()
+        _ops().defer_join([dyb, dy, g.get('_x'), x.data])
     g.pop('_x', None)
