@@ -81,9 +81,16 @@ constexpr int IG_OUT_STAGE_BYTES = 128 * 256;   // epilogue staging: 128 pixels 
 // row-shifted views of it (UMMA descriptor start address + dy * width * 128 B) -- 3 activation loads per K chunk instead
 // of 9.  Shared memory: HALO_A_SLOTS activation slots + HALO_W_SLOTS weight slots (one per tap) replace the 4-stage ring.
 constexpr int HALO_A_SLOT_BYTES = 40 * 1024;    // (8 + 2) rows x 32 pixels x 128 B is the largest box (32x32 images)
-constexpr int HALO_A_SLOTS = 3;
-constexpr int HALO_W_SLOTS = 4;
-static_assert(HALO_A_SLOTS * HALO_A_SLOT_BYTES + HALO_W_SLOTS * W_STAGE_BYTES <= IG_STAGES * IG_STAGE_BYTES, "halo rings fit");
+#ifndef TGAN_HALO_A_SLOTS
+#define TGAN_HALO_A_SLOTS 2
+#define TGAN_HALO_W_SLOTS 4
+#endif
+constexpr int HALO_A_SLOTS = TGAN_HALO_A_SLOTS;
+constexpr int HALO_W_SLOTS = TGAN_HALO_W_SLOTS;
+// Two activation slots keep the MMAs fed (three measured no faster); the 48 KB that frees inside the ring region hold a
+// SECOND epilogue staging buffer in row-halo mode, so the shared-memory writes of box h+1 overlap the TMA store of box h.
+constexpr int HALO_OSTAGE2_OFFSET = HALO_A_SLOTS * HALO_A_SLOT_BYTES + HALO_W_SLOTS * W_STAGE_BYTES;
+static_assert(HALO_OSTAGE2_OFFSET + IG_OUT_STAGE_BYTES <= IG_STAGES * IG_STAGE_BYTES, "halo rings + second staging buffer fit");
 
 // Orientation: D[co, pixel] = W[co, k] * X[pixel, k]^T.  The OUTPUT CHANNELS are the UMMA M dimension (TMEM lanes) and
 // 256 PIXELS are the UMMA N dimension: measured on B200, one cta_group::1 tcgen05.mma (M=128, K=16, smem operands)
@@ -435,6 +442,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     const int q = warp & 3;                    // TMEM lane quadrant this warp may access
     const int g = (warp - 2) >> 2;             // which 64 pixels of each 128-pixel box
     const bool plain = p.alpha == 1.f && p.bias == nullptr;
+#ifdef TGAN_SINGLE_OSTAGE
+    const bool two_stage = false;
+#else
+    const bool two_stage = p.halo != 0;
+#endif
+    // (offset arithmetic on the shared-memory base keeps the address space: the staging stores stay STS)
+    constexpr int OSTAGE_B_DELTA = HALO_OSTAGE2_OFFSET - IG_STAGES * IG_STAGE_BYTES;
+    int obuf = 0;
     int acc = 0; uint32_t accphase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int cls, tin, ct, pp;
@@ -455,8 +470,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         int t2, tx, ty, ng;
         p.d_tiles_x.divmod(mt, t2, tx);
         p.d_tiles_y.divmod(t2, ng, ty);
-        if (p.tstore) {           // the previous box's store must have finished reading the staging buffer
-          if (warp == 2 && lane == 0) bulk_wait_read0();
+        uint8_t* const ost = ostage + (obuf ? OSTAGE_B_DELTA : 0);
+        if (p.tstore) {           // the store that last used THIS staging buffer must have finished reading it
+          if (warp == 2 && lane == 0) { if (two_stage) bulk_wait_read1(); else bulk_wait_read0(); }
           named_bar_sync(1, 256);
         }
         // linear index of the box's first pixel (host guarantees full-width tiles of one image, or one flat row, whenever
@@ -543,7 +559,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                 default: ig_sum_chunk<32>(p, v, pbase, tx, ty, ng, csum); break;
               }
             }
-            bf16* srow = reinterpret_cast<bf16*>(ostage) + (size_t)pbase * 128 + (q * 32 + lane);
+            bf16* srow = reinterpret_cast<bf16*>(ost) + (size_t)pbase * 128 + (q * 32 + lane);
 #pragma unroll
             for (int j = 0; j < 32; ++j) srow[j * 128] = __float2bfloat16_rn(v[j]);
           } else if (!TGAN_DBG(4)) {
@@ -559,9 +575,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
           fence_proxy_async();
           named_bar_sync(1, 256);
           if (warp == 2 && lane == 0 && !TGAN_DBG(4)) {
-            tma_store_4d(tmO, ostage, ct * 128, tx * p.tw, ty * p.th, ng * p.nb);
+            tma_store_4d(tmO, ost, ct * 128, tx * p.tw, ty * p.th, ng * p.nb);
             bulk_commit();
           }
+          if (two_stage) obuf ^= 1;
         }
       }
       if (p.colsum && cvalid) {

@@ -9,7 +9,7 @@ import re
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _HEADER = os.path.normpath(os.path.join(_PKG, '..', '..', 'include', 'tgan.h'))
-_SO = os.path.join(_PKG, 'libtgan.so')
+_SO = os.environ.get('TGAN_LIBTGAN') or os.path.join(_PKG, 'libtgan.so')      # (override: kernel-variant experiments)
 
 _CT = {'int': ctypes.c_int, 'float': ctypes.c_float, 'int64_t': ctypes.c_int64, 'uint64_t': ctypes.c_uint64,
        'void': None}
