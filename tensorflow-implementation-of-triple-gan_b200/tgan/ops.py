@@ -863,7 +863,10 @@ def batch_norm(x, gamma, beta, mm, mv, train, eps=1e-5, decay=0.9, unbiased=True
     C, rows = x.C, x.rows
     rg = _on() and (x.requires_grad or gamma.requires_grad or beta.requires_grad)
     if ctx.building:
-        return Var(None, x.shape, requires_grad=rg)
+        return _prop(Var(None, x.shape, requires_grad=rg), x)
+    segs = _segs(x)
+    if train and segs and len(segs) > 1:
+        return _batch_norm_segments(x, gamma, beta, mm, mv, eps, decay, unbiased, segs, rg)
     xd = x.data
     scale, shift = _new((C,), torch.float32), _new((C,), torch.float32)
     mean, rstd = _new((C,), torch.float32), _new((C,), torch.float32)
@@ -875,7 +878,7 @@ def batch_norm(x, gamma, beta, mm, mv, train, eps=1e-5, decay=0.9, unbiased=True
     else:
         _lib.call('tgan_bn_eval_affine', _p(gamma.data), _p(beta.data), _p(mm.data), _p(mv.data), eps, C, _p(scale),
                   _p(shift), _st())
-    out = Var(None, x.shape, requires_grad=rg)
+    out = _prop(Var(None, x.shape, requires_grad=rg), x)
 
     def run(ld, lab, K, rps):
         if ld is None:
@@ -904,6 +907,51 @@ def batch_norm(x, gamma, beta, mm, mv, train, eps=1e-5, decay=0.9, unbiased=True
             _lib.call('tgan_bn_bwd', _p(dy), dt_code(dy), _p(xd), dt_code(xd), _p(dx), dt_code(dx), rows, C, _p(mean),
                       _p(rstd), _p(gamma.data), _p(gamma.grad) if gamma.requires_grad else None,
                       _p(beta.grad) if beta.requires_grad else None, 1.0, _p(ctx.ws()), _st())
+            if x.requires_grad:
+                add_grad(x, dx)
+        ctx.tape.nodes.append(bwd)
+    return out
+
+
+def _batch_norm_segments(x, gamma, beta, mm, mv, eps, decay, unbiased, segs, rg):
+    """Training-mode batch norm of a GROUPED batch (ops.group_batch): every network call keeps its own batch statistics
+    (the rows of a call are contiguous), the moving statistics are updated once per call in call order -- what the
+    separate calls of the reference graph compute -- while the convolutions around it run once on the whole group."""
+    C, rows = x.C, x.rows
+    assert x.ld == C, 'segmented batch norm of a channel-padded tensor'
+    xd = x.data
+    ex = xd.element_size()
+    rps = rows // sum(segs)
+    y = _new(x.shape, _out_dtype(C))
+    ey = y.element_size()
+    stats, r0 = [], 0
+    for n in segs:
+        nr = n * rps
+        scale, shift = _new((C,), torch.float32), _new((C,), torch.float32)
+        mean, rstd = _new((C,), torch.float32), _new((C,), torch.float32)
+        s, ss = _new((C,), torch.float32), _new((C,), torch.float32)
+        xp = xd.data_ptr() + r0 * C * ex
+        _lib.call('tgan_channel_stats', xp, dt_code(xd), nr, C, _p(s), _p(ss), 0.0, _p(ctx.ws()), _st())
+        _lib.call('tgan_bn_finalize', _p(s), _p(ss), nr, C, _p(gamma.data), _p(beta.data), eps, decay, 1 if unbiased else 0,
+                  None if mm is None else _p(mm.data), None if mv is None else _p(mv.data), _p(mean), _p(rstd), _p(scale),
+                  _p(shift), _st())
+        _lib.call('tgan_affine_act', xp, dt_code(xd), y.data_ptr() + r0 * C * ey, dt_code(y), nr, C, _p(scale), _p(shift), 0, 0.0,
+                  _st())
+        stats.append((r0, nr, mean, rstd))
+        r0 += nr
+    out = _prop(Var(y, x.shape, requires_grad=rg), x)
+    if rg:
+        def bwd():
+            if out.grad is None:
+                return
+            dy = out.grad
+            ed = dy.element_size()
+            dx = _new(x.shape, xd.dtype)
+            for b0, nr, mean, rstd in stats:
+                _lib.call('tgan_bn_bwd', dy.data_ptr() + b0 * C * ed, dt_code(dy), xd.data_ptr() + b0 * C * ex, dt_code(xd),
+                          dx.data_ptr() + b0 * C * ex, dt_code(dx), nr, C, _p(mean), _p(rstd), _p(gamma.data),
+                          _p(gamma.grad) if gamma.requires_grad else None, _p(beta.grad) if beta.requires_grad else None,
+                          1.0, _p(ctx.ws()), _st())
             if x.requires_grad:
                 add_grad(x, dx)
         ctx.tape.nodes.append(bwd)

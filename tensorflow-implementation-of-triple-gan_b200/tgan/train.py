@@ -11,6 +11,8 @@ Data parallelism (new; the reference is single-GPU): one process per GPU, each r
 per-rank batch tuple, the flat fp32 gradient buffer of the phase's network is all-reduced (NCCL, sum)
 and 1/world is folded into the fused Adam kernel.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -264,7 +266,8 @@ class Train(Train_base):
         v = {k: ops.Var(t, tuple(t.shape)) for k, t in self.inputs.items()}
         pre, K = self._pre(), c.NUM_CLASSES
         cif = c.DATA_NAME == 'cifar10' and hasattr(m, '_whitener')
-        grouped_c = cif                      # mean-only-BN classifier: segment-aware ops
+        # grouped classifier passes: segment-aware mean-only BN (cifar10) / per-segment tf.contrib batch norm (Good_GAN)
+        grouped_c = not os.environ.get('TGAN_NO_GROUPING')
         nLD, nUD, nUC, nG, nLC = (c.BATCH_SIZE_L_D, c.BATCH_SIZE_U_D, c.BATCH_SIZE_U_C, c.BATCH_SIZE_G, c.BATCH_SIZE_L_C)
         TL = ops.TagList
         d_loss = g_loss = None
@@ -319,15 +322,21 @@ class Train(Train_base):
             G = m.good_generator(v['z_g'], v['y_g'], reuse=True, tag='C/G')
         with recording():
             if grouped_c:
-                segs = [nLC, nUC, nUC, nG]
-                xs = ops.group_batch([v['x_l_c'], v['x_u_c'], v['x_u_c'], ops.Var(G.data, G.shape)])
-                lg, _ = m.classifier(pre(xs), train, reuse=True,
-                                     tag=TL([('C/C_real', nLC), ('C/C_unl', nUC), ('C/C_unl_rep', nUC), ('C/C_fake', nG)]))
+                Gv = ops.Var(G.data, G.shape)      # (group_batch takes any per-sample view: [N,784] beside [N,28,28,1])
+                if cif:      # Good_GAN_cifar10.forward_pass: a second stochastic pass over x_u_c (:233)
+                    segs = [nLC, nUC, nUC, nG]
+                    xs = ops.group_batch([v['x_l_c'], v['x_u_c'], v['x_u_c'], Gv])
+                    tags = TL([('C/C_real', nLC), ('C/C_unl', nUC), ('C/C_unl_rep', nUC), ('C/C_fake', nG)])
+                else:
+                    segs = [nLC, nUC, nG]
+                    xs = ops.group_batch([v['x_l_c'], v['x_u_c'], Gv])
+                    tags = TL([('C/C_real', nLC), ('C/C_unl', nUC), ('C/C_fake', nG)])
+                lg, _ = m.classifier(pre(xs), train, reuse=True, tag=tags)
                 c_unl_v = ops.Var(lg.data[nLC:nLC + nUC], (nUC, K))
                 with no_grad():
                     idx_c, oh_u = ops.argmax_onehot(c_unl_v, K)
                     _, du = m.discriminator(v['x_u_c'], oh_u, reuse=True, tag='C/D_unl')
-                c_loss = ops.loss_c_grouped(lg, segs, True, v['y_l_c'], du, v['y_g'], self.lambdas, out=self.loss_buf[2:3])
+                c_loss = ops.loss_c_grouped(lg, segs, cif, v['y_l_c'], du, v['y_g'], self.lambdas, out=self.loss_buf[2:3])
                 self.aux['c_logits'] = lg
             else:
                 c_real, _ = m.classifier(pre(v['x_l_c']), train, reuse=True, tag='C/C_real')
