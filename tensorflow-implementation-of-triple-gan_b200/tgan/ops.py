@@ -579,7 +579,7 @@ def lazy_bias(z, b):
         z._lazy.b = b
         z.requires_grad = z.requires_grad or (_on() and b.requires_grad)
         return z
-    v = Var(None, z.shape, requires_grad=_on() and (z.requires_grad or b.requires_grad))
+    v = _prop(Var(None, z.shape, requires_grad=_on() and (z.requires_grad or b.requires_grad)), z)
     v._lazy = (z, b)
     return v
 
