@@ -118,6 +118,12 @@ class BucketedAllReduce:
         return 1.0 / w
 
 
+def shard_len(n, world):
+    """length of one rank's shard of a flat buffer of n elements (n % 4 == 0): a multiple of 4 elements (16-byte vectors),
+    the same formula as tgan_dp_adam (csrc/dp_fused.cu); rank r owns [r * len, min(n, (r + 1) * len))"""
+    return ((n // 4 + world - 1) // world) * 4
+
+
 def symmetric_allocator(device):
     """-> alloc(n) returning fp32 tensors in symmetric memory (every rank allocates the same sizes in the same order), or
     None when this is a single-process run / symmetric memory is unavailable (the NCCL all-reduce path is used then)."""
@@ -167,8 +173,7 @@ class FusedUpdate:
         dist.barrier()
 
     def shard(self, n):
-        per = ((n // 4 + self.world - 1) // self.world) * 4
-        return per
+        return shard_len(n, self.world)
 
     def apply(self, name, fb, opt, ema=None, ema_decay=0.9999):
         from . import _lib

@@ -60,3 +60,24 @@ def test_two_rank_gradient_allreduce_and_broadcast():
         assert out['discriminator'][3] >= 327467 and out['good_generator'][3] >= 5129201
     assert np.array_equal(res[0][2], res[1][2])                # parameters broadcast from rank 0
     assert res[0][3] != res[1][3]                              # per-rank input streams differ
+
+
+def test_shard_partition_of_the_fused_update():
+    """ddp.shard_len (the host mirror of tgan_dp_adam's partition): the shards of every rank are 16-byte aligned, disjoint
+    and cover the flat buffer exactly, for the three networks' sizes and every world size the kernel accepts."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path[:0] = [root, os.path.join(root, 'tensorflow-implementation-of-triple-gan_b200')]
+    from tgan import ddp
+    for n in (327468, 5129204, 3121812, 4, 8, 64):
+        assert n % 4 == 0
+        for world in range(2, 9):
+            per = ddp.shard_len(n, world)
+            assert per % 4 == 0 and per * world >= n and per * (world - 1) < n + 4 * world
+            covered = 0
+            for r in range(world):
+                lo, hi = r * per, min(n, (r + 1) * per)
+                if hi > lo:
+                    assert lo == covered and lo % 4 == 0
+                    covered = hi
+            assert covered == n
