@@ -243,6 +243,34 @@ int tgan_act_bwd_seg(const void* dy, int dydt, const void* y, int ydt, void* du,
 int tgan_sub_channel_mean_seg(const void* du, void* dz, int64_t rows, int C, int nseg, int64_t r0, int64_t r1,
                               int64_t r2, const float* colsums, void* stream);
 
+/* The same layer on a SMALL fp32 tensor (the classifier's logits [rows, 10], Good_GAN_cifar10.py:166 through
+ * nn.py:147-187 / :517): every segment of the grouped batch in ONE single-CTA launch instead of two launches per segment.
+ * C <= 32, rows * C <= 2^20, nseg <= 4, r0..r2 as above.
+ *   mobn_small_fwd: per-segment column means in a fixed order; y = act(z - mean_seg + b) (train) | act(z - pop_mean + b);
+ *                   pop_mean <- decay*pop_mean + (1-decay)*mean_seg once per segment, in segment order.
+ *   mobn_small_bwd: du = dy * act'(y); grad_acc[c] += sum_rows du (may be NULL);
+ *                   dz = du - mean_seg(du) if subtract_mean else du (dz may be NULL: bias gradient only). */
+int tgan_mobn_small_fwd(const float* z, float* y, int64_t rows, int C, int nseg, int64_t r0, int64_t r1, int64_t r2,
+                        const float* b, float* pop_mean, float decay, int train, int act, float alpha, void* stream);
+int tgan_mobn_small_bwd(const float* dy, const float* y, float* dz, int64_t rows, int C, int nseg, int64_t r0, int64_t r1,
+                        int64_t r2, int act, float alpha, int subtract_mean, float* grad_acc, void* stream);
+
+/* Training-mode tf.contrib.layers.batch_norm (modle_base.py:229-237) of a GROUPED batch: rows [0, r0), [r0, r1), ... are
+ * the calls of one network (segments as in tgan_mobn_apply_seg, nseg <= 4); every call keeps its own batch statistics and
+ * updates the moving statistics once, in call order -- what the separate calls of the reference graph compute
+ * (Good_GAN.py:220-299 normalises after every convolution of the classifier).  Three launches per direction for all
+ * segments (partial sums -> fold / finalize -> apply), fp64 partials folded in a fixed order.
+ *   bn_fwd_seg: y = (x - mean_seg) * rstd_seg * gamma + beta; mean / rstd: [nseg][C] outputs kept for the backward.
+ *   bn_bwd_seg: dx = gamma * rstd_seg * (dy - s1_seg/n_seg - xhat * s2_seg/n_seg), s1 = sum dy, s2 = sum dy * xhat;
+ *               dbeta = beta_acc * dbeta + sum_seg s1, dgamma likewise with s2 (either may be NULL).
+ * ws: 520 * C floats, 16-byte aligned. */
+int tgan_bn_fwd_seg(const void* x, int xdt, void* y, int ydt, int64_t rows, int C, int nseg, int64_t r0, int64_t r1,
+                    int64_t r2, const float* gamma, const float* beta, float eps, float decay, int unbiased_moving_var,
+                    float* moving_mean, float* moving_var, float* mean, float* rstd, float* ws, void* stream);
+int tgan_bn_bwd_seg(const void* dy, int dydt, const void* x, int xdt, void* dx, int dxdt, int64_t rows, int C, int nseg,
+                    int64_t r0, int64_t r1, int64_t r2, const float* mean, const float* rstd, const float* gamma,
+                    float* dgamma, float* dbeta, float beta_acc, float* ws, void* stream);
+
 /* tf.contrib.layers.batch_norm training statistics (modle_base.py:229-237):
  *   mean, rstd = rsqrt(var_biased + eps); scale = gamma*rstd; shift = beta - mean*scale;
  *   moving_mean/variance <- decay-EMA; unbiased_moving_var = 1: the variance fed to the EMA is the unbiased estimate

@@ -107,75 +107,109 @@ __global__ void __launch_bounds__(256) wn_bwd_apply_kernel(const tgan_wn_desc* _
 // dst[t][n][k] (bf16, k < Kpad) = k < K ? src[taps[t]*st + n*sn + k*sk] * scale : 0, in 32x32 (n, k) tiles.  One of the
 // source strides is 1 in every layout the step uses; when it is the n stride the tile is transposed through shared
 // memory so that both the fp32 reads and the bf16 writes are coalesced.
-// One wave of persistent CTAs over a FLAT list of 32x32 tiles of all tensors (the descriptor table and the running tile
-// counts are staged in shared memory once per CTA).  The first version launched 592 CTAs per tensor: ~12,000 CTAs per
-// network, most of which read their descriptor and left -- ten waves of latency for 6 us of memory traffic.
+// One wave of persistent CTAs over a FLAT list of 32x32 tiles of all tensors.  The kernel is latency-bound (a network has
+// 0.3-10 M weights: 1-10 tiles per CTA), so everything that would sit in front of a tile's loads is hoisted into the CTA
+// prologue -- descriptor table, a parallel scan of the per-tensor tile counts, the tap tables -- and the tile loop
+// handles PACK_U tiles per iteration: all their global loads are issued before the first store.
+// (v1: 592 CTAs per tensor, ~12,000 CTAs per network.  v2: flat list, but a serial prefix sum by thread 0, a dependent
+// tap-table load and one tile per iteration: 9 / 22 / 30 us for D / C / G.)
 constexpr int PACK_MAX_DESCS = 64;
+constexpr int PACK_U = 2;
 __global__ void __launch_bounds__(256) pack_multi_kernel(const tgan_pack_desc* __restrict__ descs, int n0, int n) {
   pdl_entry();
   __shared__ tgan_pack_desc ds[PACK_MAX_DESCS];
   __shared__ int first[PACK_MAX_DESCS + 1];      // first flat tile of every tensor
-  __shared__ float sm[32][33];
+  __shared__ int wtot[2];
+  __shared__ unsigned char tap_sm[PACK_MAX_DESCS][32];
+  __shared__ float sm[PACK_U][32][33];
   for (int i = threadIdx.x; i < n * (int)(sizeof(tgan_pack_desc) / 4); i += blockDim.x)
     reinterpret_cast<uint32_t*>(ds)[i] = reinterpret_cast<const uint32_t*>(descs + n0)[i];
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int acc = 0;
-    for (int i = 0; i < n; ++i) {
-      first[i] = acc;
-      acc += ds[i].T * ((ds[i].Nr + 31) / 32) * ((ds[i].Kpad + 31) / 32);
+  int incl = 0;
+  if (threadIdx.x < PACK_MAX_DESCS) {      // two warps: inclusive scan of the tile counts
+    const int i = threadIdx.x, lane = i & 31;
+    int v = i < n ? ds[i].T * ((ds[i].Nr + 31) / 32) * ((ds[i].Kpad + 31) / 32) : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
     }
-    first[n] = acc;
+    if (lane == 31) wtot[i >> 5] = v;
+    incl = v;
+  }
+  for (int idx = threadIdx.x; idx < n * 32; idx += blockDim.x) {
+    const int i = idx >> 5, t = idx & 31;
+    tap_sm[i][t] = (unsigned char)((ds[i].taps && t < ds[i].T) ? ds[i].taps[t] : t);
+  }
+  __syncthreads();
+  if (threadIdx.x < PACK_MAX_DESCS) {
+    first[threadIdx.x + 1] = incl + (threadIdx.x >= 32 ? wtot[0] : 0);
+    if (threadIdx.x == 0) first[0] = 0;
   }
   __syncthreads();
   const int total = first[n];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   int di = 0;
-  for (int ft = blockIdx.x; ft < total; ft += gridDim.x) {
-    while (ft >= first[di + 1]) ++di;            // flat tiles are visited in increasing order
-    const tgan_pack_desc& d = ds[di];
-    const int tile = ft - first[di];
-    const int nbk = (d.Kpad + 31) / 32, nbn = (d.Nr + 31) / 32;
-    bf16* dst = reinterpret_cast<bf16*>(d.dst);
-    const bool transpose = d.sk != 1 && d.sn == 1;
-    const int kb = tile % nbk, nb = (tile / nbk) % nbn, t = tile / (nbk * nbn);
-    const int64_t base = (int64_t)(d.taps ? d.taps[t] : t) * d.st;
-    if (transpose) {
-      const int n_ = nb * 32 + tx;
+  for (int ft0 = blockIdx.x * PACK_U; ft0 < total; ft0 += gridDim.x * PACK_U) {
+    float v[PACK_U][4];
+    int dsel[PACK_U], kb_[PACK_U], nb_[PACK_U], t_[PACK_U];
+    // ---- phase 1: every global load of the PACK_U tiles ----
 #pragma unroll
-      for (int j = ty; j < 32; j += 8) {
-        const int k = kb * 32 + j;
-        float v = 0.f;
+    for (int u = 0; u < PACK_U; ++u) {
+      const int ft = ft0 + u;
+      dsel[u] = -1;
+      if (ft >= total) continue;
+      while (ft >= first[di + 1]) ++di;            // flat tiles are visited in increasing order
+      const tgan_pack_desc& d = ds[di];
+      const int tile = ft - first[di];
+      const int nbk = (d.Kpad + 31) / 32, nbn = (d.Nr + 31) / 32;
+      const int kb = tile % nbk, nb = (tile / nbk) % nbn, t = tile / (nbk * nbn);
+      dsel[u] = di; kb_[u] = kb; nb_[u] = nb; t_[u] = t;
+      const int tap = t < 32 ? (int)tap_sm[di][t] : (d.taps ? d.taps[t] : t);
+      const int64_t base = (int64_t)tap * d.st;
+      const bool transpose = d.sk != 1 && d.sn == 1;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = ty + 8 * jj;
+        // transposed tiles: lanes along n (the contiguous source axis), rows j along k; else lanes along k, rows along n
+        const int n_ = transpose ? nb * 32 + tx : nb * 32 + j;
+        const int k = transpose ? kb * 32 + j : kb * 32 + tx;
+        float x = 0.f;
         if (k < d.K && n_ < d.Nr) {
-          v = d.src[base + n_ + k * d.sk];
-          if (d.scale_on == 1) v *= d.scale[n_];
-          else if (d.scale_on == 2) v *= d.scale[k];
+          x = d.src[base + (int64_t)n_ * d.sn + (int64_t)k * d.sk];
+          if (d.scale_on == 1) x *= d.scale[n_];
+          else if (d.scale_on == 2) x *= d.scale[k];
         }
-        sm[j][tx] = v;
-      }
-      __syncthreads();
-      const int k = kb * 32 + tx;
-#pragma unroll
-      for (int j = ty; j < 32; j += 8) {
-        const int nn = nb * 32 + j;
-        if (nn < d.Nr && k < d.Kpad) dst[((int64_t)t * d.Nr + nn) * d.Kpad + k] = __float2bfloat16_rn(sm[tx][j]);
-      }
-      __syncthreads();
-    } else {
-      const int k = kb * 32 + tx;
-#pragma unroll
-      for (int j = ty; j < 32; j += 8) {
-        const int n_ = nb * 32 + j;
-        if (n_ >= d.Nr || k >= d.Kpad) continue;
-        float v = 0.f;
-        if (k < d.K) {
-          v = d.src[base + n_ * d.sn + k * d.sk];
-          if (d.scale_on == 1) v *= d.scale[n_];
-          else if (d.scale_on == 2) v *= d.scale[k];
-        }
-        dst[((int64_t)t * d.Nr + n_) * d.Kpad + k] = __float2bfloat16_rn(v);
+        v[u][jj] = x;
       }
     }
+    // ---- phase 2: transposed tiles go through shared memory ----
+#pragma unroll
+    for (int u = 0; u < PACK_U; ++u) {
+      if (dsel[u] < 0) continue;
+      const tgan_pack_desc& d = ds[dsel[u]];
+      if (d.sk != 1 && d.sn == 1) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) sm[u][ty + 8 * jj][tx] = v[u][jj];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < PACK_U; ++u) {
+      if (dsel[u] < 0) continue;
+      const tgan_pack_desc& d = ds[dsel[u]];
+      bf16* dst = reinterpret_cast<bf16*>(d.dst);
+      const bool transpose = d.sk != 1 && d.sn == 1;
+      const int k = kb_[u] * 32 + tx;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = ty + 8 * jj;
+        const int nn = nb_[u] * 32 + j;
+        if (nn < d.Nr && k < d.Kpad)
+          dst[((int64_t)t_[u] * d.Nr + nn) * d.Kpad + k] = __float2bfloat16_rn(transpose ? sm[u][tx][j] : v[u][jj]);
+      }
+    }
+    __syncthreads();
   }
 }
 

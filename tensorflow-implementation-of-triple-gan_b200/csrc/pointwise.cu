@@ -1035,6 +1035,92 @@ static inline int grid_for(int64_t n, int block = 256) {
   return (int)(g < cap ? (g > 0 ? g : 1) : cap);
 }
 
+// Mean-only batch norm of a SMALL fp32 tensor (the classifier's 10 logits, Good_GAN_cifar10.py:166; nn.py:147-187) for
+// all segments of a grouped batch in ONE single-CTA launch: per-segment column means (fixed summation order), pop_mean
+// updated once per segment in call order, apply + nonlinearity.  Replaces 2 launches per segment (8 for the grouped
+// phase-C batch) of a few microseconds each.  256 threads = 32 columns x 8 row lanes; C <= 32.
+struct SmallSegs { int n; int end[4]; };      // exclusive end row of every segment
+__global__ void __launch_bounds__(256) mobn_small_fwd_kernel(const float* __restrict__ z, float* __restrict__ y, int C, SmallSegs sg,
+                                                             const float* __restrict__ b, float* __restrict__ pop_mean,
+                                                             float decay, int train, int act, float alpha) {
+  pdl_entry();
+  __shared__ float part[8][33];
+  __shared__ float mean[4][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int s = 0, r0 = 0; s < sg.n; r0 = sg.end[s], ++s) {
+    const int r1 = sg.end[s];
+    if (train) {
+      float a = 0.f;
+      if (tx < C)
+        for (int r = r0 + ty; r < r1; r += 8) a += z[(int64_t)r * C + tx];
+      part[ty][tx] = a;
+      __syncthreads();
+      if (ty == 0 && tx < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int l = 0; l < 8; ++l) t += part[l][tx];
+        mean[s][tx] = t * (1.0f / (float)(r1 - r0));
+      }
+      __syncthreads();
+    } else if (ty == 0 && tx < C) {
+      mean[s][tx] = pop_mean[tx];
+    }
+  }
+  __syncthreads();
+  if (train && pop_mean && threadIdx.x < C) {
+    float pm = pop_mean[threadIdx.x];
+    for (int s = 0; s < sg.n; ++s) pm = pm * decay + mean[s][threadIdx.x] * (1.f - decay);
+    pop_mean[threadIdx.x] = pm;
+  }
+  const int total = sg.end[sg.n - 1] * C;
+  for (int i = threadIdx.x; i < total; i += 256) {
+    const int r = i / C, c = i - r * C;
+    const int s = (r >= sg.end[0]) + (sg.n > 2 && r >= sg.end[1]) + (sg.n > 3 && r >= sg.end[2]);
+    y[i] = act_fwd(z[i] + (b ? b[c] : 0.f) - mean[s][c], act, alpha);
+  }
+}
+
+// backward of the same: du = dy * act'(y); grad_acc[c] += sum over all rows of du (the bias gradient);
+// dz = du - mean_{rows of the segment}(du) when the batch mean was subtracted (training), else du.
+__global__ void __launch_bounds__(256) mobn_small_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                             float* __restrict__ dz, int C, SmallSegs sg, int act, float alpha,
+                                                             int subtract_mean, float* __restrict__ grad_acc) {
+  pdl_entry();
+  __shared__ float part[8][33];
+  __shared__ float mean[4][32];
+  __shared__ float tot[32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (threadIdx.x < 32) tot[threadIdx.x] = 0.f;
+  for (int s = 0, r0 = 0; s < sg.n; r0 = sg.end[s], ++s) {
+    const int r1 = sg.end[s];
+    float a = 0.f;
+    if (tx < C)
+      for (int r = r0 + ty; r < r1; r += 8) {
+        const int64_t i = (int64_t)r * C + tx;
+        a += dy[i] * act_grad_from_y(y[i], act, alpha);
+      }
+    part[ty][tx] = a;
+    __syncthreads();
+    if (ty == 0 && tx < C) {
+      float t = 0.f;
+#pragma unroll
+      for (int l = 0; l < 8; ++l) t += part[l][tx];
+      tot[tx] += t;
+      mean[s][tx] = subtract_mean ? t * (1.0f / (float)(r1 - r0)) : 0.f;
+    }
+    __syncthreads();
+  }
+  if (grad_acc && threadIdx.x < C) grad_acc[threadIdx.x] += tot[threadIdx.x];
+  if (dz) {
+    const int total = sg.end[sg.n - 1] * C;
+    for (int i = threadIdx.x; i < total; i += 256) {
+      const int r = i / C, c = i - r * C;
+      const int s = (r >= sg.end[0]) + (sg.n > 2 && r >= sg.end[1]) + (sg.n > 3 && r >= sg.end[2]);
+      dz[i] = dy[i] * act_grad_from_y(y[i], act, alpha) - mean[s][c];
+    }
+  }
+}
+
 }  // namespace tgan
 
 using namespace tgan;
@@ -1138,6 +1224,42 @@ extern "C" int tgan_sub_channel_mean_seg(const void* du, void* dz, int64_t rows,
   if (make_segs(sg, rows, nseg, r0, r1, r2)) return 1;
   const int64_t nvec = rows * C / 8;
   pdl_launch(sub_mean_seg_kernel, grid_for(nvec), 256, 0, (cudaStream_t)((cudaStream_t)stream), (const bf16*)du, (bf16*)dz, nvec, C, colsums, sg);
+  TGAN_LAUNCHED();
+  return 0;
+}
+
+static int make_small_segs(SmallSegs& sg, int64_t rows, int C, int nseg, int64_t r0, int64_t r1, int64_t r2) {
+  if (nseg < 1 || nseg > 4 || C < 1 || C > 32 || rows < 1 || rows * C > (1 << 20)) {
+    set_error("mobn_small: needs 1 <= nseg <= 4, C <= 32, rows * C <= 2^20 (got nseg %d, C %d, rows %lld)", nseg, C, (long long)rows);
+    return 1;
+  }
+  const int64_t e[4] = {r0, r1, r2, rows};
+  int64_t prev = 0;
+  sg.n = nseg;
+  for (int i = 0; i < 4; ++i) {
+    const int64_t end = i < nseg - 1 ? e[i] : rows;
+    if (i < nseg && end <= prev) { set_error("mobn_small: segment boundaries must be increasing and non-empty"); return 1; }
+    sg.end[i] = (int)end;
+    if (i < nseg) prev = end;
+  }
+  return 0;
+}
+extern "C" int tgan_mobn_small_fwd(const float* z, float* y, int64_t rows, int C, int nseg, int64_t r0, int64_t r1, int64_t r2,
+                                   const float* b, float* pop_mean, float decay, int train, int act, float alpha, void* stream) {
+  TGAN_CHECK_ARG(z && y && (train || pop_mean), "mobn_small_fwd: bad args (test mode needs pop_mean)");
+  SmallSegs sg;
+  if (make_small_segs(sg, rows, C, nseg, r0, r1, r2)) return 1;
+  pdl_launch(mobn_small_fwd_kernel, 1, 256, 0, (cudaStream_t)stream, z, y, C, sg, b, pop_mean, decay, train, act, alpha);
+  TGAN_LAUNCHED();
+  return 0;
+}
+extern "C" int tgan_mobn_small_bwd(const float* dy, const float* y, float* dz, int64_t rows, int C, int nseg, int64_t r0,
+                                   int64_t r1, int64_t r2, int act, float alpha, int subtract_mean, float* grad_acc,
+                                   void* stream) {
+  TGAN_CHECK_ARG(dy && y && (dz || grad_acc), "mobn_small_bwd: bad args");
+  SmallSegs sg;
+  if (make_small_segs(sg, rows, C, nseg, r0, r1, r2)) return 1;
+  pdl_launch(mobn_small_bwd_kernel, 1, 256, 0, (cudaStream_t)stream, dy, y, dz, C, sg, act, alpha, subtract_mean, grad_acc);
   TGAN_LAUNCHED();
   return 0;
 }

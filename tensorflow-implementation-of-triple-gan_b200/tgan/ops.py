@@ -645,6 +645,9 @@ def mobn_act(z, b, pop_mean, train, act='none', alpha=0.2, decay=0.9):
     cs_all = z.aux.get('colsum') if z.aux else None      # [nseg, C] accumulated by the tcgen05 GEMM epilogue
     ydt = _out_dtype(C)
     fused = zd.dtype == torch.bfloat16 and ydt == torch.bfloat16 and C % 8 == 0 and len(segs) <= 4
+    # the 10 logits: every segment in one single-CTA launch (tgan_mobn_small_*) instead of two launches per segment
+    small = (not fused and zd.dtype == torch.float32 and ydt == torch.float32 and C <= 32 and rows * C <= (1 << 16)
+             and len(segs) <= 4 and z.ld == C and not os.environ.get('TGAN_NO_SMALL_MOBN'))
     tape = ctx.tape
     out = _prop(Var(None, z.shape, requires_grad=rg), z)
 
@@ -663,6 +666,9 @@ def mobn_act(z, b, pop_mean, train, act='none', alpha=0.2, decay=0.9):
             _lib.call('tgan_mobn_apply_seg', _p(zd), _p(y), rows, C, len(segs), ends[0], ends[1], ends[2], _p(sums),
                       1 if cs_all is not None else 0, _p(b.data), _p(pop_mean.data), decay, 1 if train else 0, a, alpha,
                       _st())
+        elif small:
+            _lib.call('tgan_mobn_small_fwd', _p(zd), _p(y), rows, C, len(segs), ends[0], ends[1], ends[2], _p(b.data),
+                      _p(pop_mean.data), decay, 1 if train else 0, a, alpha, _st())
         else:
             for i, (b0, nr) in enumerate(bounds):
                 s = None
@@ -688,6 +694,10 @@ def mobn_act(z, b, pop_mean, train, act='none', alpha=0.2, decay=0.9):
                     if z.requires_grad and train:
                         _lib.call('tgan_sub_channel_mean_seg', _p(du), _p(du), rows, C, len(segs), ends[0], ends[1], ends[2],
                                   _p(cs), _st())
+                elif small and dy.dtype == torch.float32:
+                    _lib.call('tgan_mobn_small_bwd', _p(dy), _p(y), _p(du) if z.requires_grad else None, rows, C, len(segs),
+                              ends[0], ends[1], ends[2], a, alpha, 1 if train else 0,
+                              _p(b.grad) if b.requires_grad else None, _st())
                 else:
                     for b0, nr in bounds:
                         cs = _new((C,), torch.float32)
@@ -924,6 +934,28 @@ def _batch_norm_segments(x, gamma, beta, mm, mv, eps, decay, unbiased, segs, rg)
     rps = rows // sum(segs)
     y = _new(x.shape, _out_dtype(C))
     ey = y.element_size()
+    if len(segs) <= 4 and not os.environ.get('TGAN_NO_BN_SEG'):
+        # all segments in three launches per direction (csrc/bn_seg.cu) instead of 3 + 4 launches per segment
+        ends = [sum(segs[:i + 1]) * rps for i in range(len(segs) - 1)] + [0, 0, 0]
+        mean, rstd = _new((len(segs), C), torch.float32), _new((len(segs), C), torch.float32)
+        _lib.call('tgan_bn_fwd_seg', _p(xd), dt_code(xd), _p(y), dt_code(y), rows, C, len(segs), ends[0], ends[1], ends[2],
+                  _p(gamma.data), _p(beta.data), eps, decay, 1 if unbiased else 0, None if mm is None else _p(mm.data),
+                  None if mv is None else _p(mv.data), _p(mean), _p(rstd), _p(ctx.ws()), _st())
+        out = _prop(Var(y, x.shape, requires_grad=rg), x)
+        if rg:
+            def bwd_seg():
+                if out.grad is None:
+                    return
+                dy = out.grad
+                dx = _new(x.shape, xd.dtype)
+                _lib.call('tgan_bn_bwd_seg', _p(dy), dt_code(dy), _p(xd), dt_code(xd), _p(dx), dt_code(dx), rows, C, len(segs),
+                          ends[0], ends[1], ends[2], _p(mean), _p(rstd), _p(gamma.data),
+                          _p(gamma.grad) if gamma.requires_grad else None, _p(beta.grad) if beta.requires_grad else None,
+                          1.0, _p(ctx.ws()), _st())
+                if x.requires_grad:
+                    add_grad(x, dx)
+            ctx.tape.nodes.append(bwd_seg)
+        return out
     stats, r0 = [], 0
     for n in segs:
         nr = n * rps

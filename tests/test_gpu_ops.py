@@ -165,6 +165,40 @@ def test_mobn_act(train, shape):
     assert relerr(tnp(ppm.data), S['pm'].numpy()) < TOL
 
 
+@pytest.mark.parametrize('train', [True, False])
+@pytest.mark.parametrize('segs', [[7], [5, 3], [4, 9, 2], [50, 50, 50, 100]])
+@pytest.mark.parametrize('act', ['none', 'lrelu'])
+def test_mobn_small_segments(train, segs, act):
+    """the classifier's logits layer on a grouped batch (tgan_mobn_small_fwd / _bwd: every segment in one launch) against
+    the oracle applied call by call: outputs, dz, db and the pop_mean chain (one update per call, in call order)"""
+    from tgan import core, ops
+    rng = np.random.default_rng(14)
+    n, C = sum(segs), 10
+    z = rng.standard_normal((n, C)) + 0.5
+    b, pm = rng.standard_normal(C), rng.standard_normal(C)
+    gy = rng.standard_normal((n, C))
+    zt, bt = T(z, True), T(b, True)
+    S = {'pm': T(pm)}
+    ys, r0 = [], 0
+    for k in segs:
+        y = O.mean_only_bn(zt[r0:r0 + k], 'pm', bt, S, train, False)
+        ys.append(O.lrelu_cifar(y) if act == 'lrelu' else y)
+        r0 += k
+    yt = torch.cat(ys, 0)
+    yt.backward(T(gy))
+    pb, ppm = param(b), param(pm, False)
+    with core.recording():
+        zv = var(z, True)
+        zv.aux = {'segs': list(segs)}
+        out = ops.mobn_act(zv, pb, ppm, train, act, 0.2)
+        fwd = tnp(out.data)
+        run_bwd(out, gy)
+    assert relerr(fwd, yt.detach().numpy()) < TOL
+    assert relerr(tnp(zv.grad), zt.grad.numpy()) < TOL
+    assert relerr(tnp(pb.grad), bt.grad.numpy()) < TOL
+    assert relerr(tnp(ppm.data), S['pm'].numpy()) < TOL
+
+
 @pytest.mark.parametrize('shape', [(4, 6, 6, 8), (16, 12), (5, 4, 4, 3), (16, 8, 8, 128), (16, 32, 32, 128)])
 def test_batch_norm_train(shape):
     from tgan import core, ops
@@ -181,6 +215,45 @@ def test_batch_norm_train(shape):
     pg, pb, pmm, pmv = param(gm), param(bt_), param(np.zeros(C), False), param(np.ones(C), False)
     with core.recording():
         xv = var(x, True)
+        out = ops.batch_norm(xv, pg, pb, pmm, pmv, True)
+        fwd = tnp(out.data)
+        run_bwd(out, gy)
+    assert relerr(fwd, yt.detach().numpy()) < 5e-5
+    assert relerr(tnp(xv.grad), xt.grad.numpy()) < 2e-4
+    assert relerr(tnp(pg.grad), gt.grad.numpy()) < 5e-5
+    assert relerr(tnp(pb.grad), bt.grad.numpy()) < 5e-5
+    assert relerr(tnp(pmm.data), S['s/moving_mean'].numpy()) < 5e-5
+    assert relerr(tnp(pmv.data), S['s/moving_variance'].numpy()) < 5e-5
+
+
+@pytest.mark.parametrize('shape,segs', [((9, 8, 8, 16), [3, 2, 4]), ((20, 12), [5, 15]), ((9, 4, 4, 3), [4, 5]),
+                                        ((12, 16, 16, 64), [2, 3, 3, 4])])
+@pytest.mark.parametrize('seg_kernels', [True, False])
+def test_batch_norm_segments(shape, segs, seg_kernels, monkeypatch):
+    """training-mode contrib batch norm of a grouped batch (tgan_bn_fwd_seg / _bwd_seg: every call of the group in three
+    launches per direction; seg_kernels=False: the per-call launches) against the oracle applied call by call: outputs,
+    dx, dgamma, dbeta, and the moving statistics after one update per call in call order"""
+    from tgan import core, ops
+    if not seg_kernels:
+        monkeypatch.setenv('TGAN_NO_BN_SEG', '1')
+    rng = np.random.default_rng(15)
+    x = rng.standard_normal(shape) * 2 + 1
+    C = shape[-1]
+    gm, bt_ = rng.uniform(0.5, 1.5, C), rng.standard_normal(C)
+    xt, gt, bt = T(x, True), T(gm, True), T(bt_, True)
+    P = {'s/gamma': gt, 's/beta': bt}
+    S = {'s/moving_mean': T(np.zeros(C)), 's/moving_variance': T(np.ones(C))}
+    ys, r0 = [], 0
+    for k in segs:
+        ys.append(O.bn_contrib(P, S, 's', xt[r0:r0 + k], True))
+        r0 += k
+    yt = torch.cat(ys, 0)
+    gy = rng.standard_normal(shape)
+    yt.backward(T(gy))
+    pg, pb, pmm, pmv = param(gm), param(bt_), param(np.zeros(C), False), param(np.ones(C), False)
+    with core.recording():
+        xv = var(x, True)
+        xv.aux = {'segs': list(segs)}
         out = ops.batch_norm(xv, pg, pb, pmm, pmv, True)
         fwd = tnp(out.data)
         run_bwd(out, gy)

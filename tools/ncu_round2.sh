@@ -10,3 +10,7 @@ python tools/agg_launches.py gpurun_out/r2_launches.csv 40 > gpurun_out/r2_ncu_l
 ncu --set full --clock-control none --import-source on -k regex:igemm_kernel -s 4 -c 1 -o gpurun_out/r2_igemm250 -f \
     python tools/prof_conv250.py > gpurun_out/r2_ncu_full.log 2>&1
 ncu -i gpurun_out/r2_igemm250.ncu-rep --page raw --csv > gpurun_out/r2_igemm250_raw.csv 2>/dev/null
+#  3. --set full of the weight-packing launches (pack_multi_kernel: classifier, discriminator, generator) of one eager step
+ncu --set full --clock-control none --import-source on -k regex:pack_multi -c 4 -o gpurun_out/r2_pack_multi -f \
+    python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/r2_ncu_pack.log 2>&1
+ncu -i gpurun_out/r2_pack_multi.ncu-rep --page raw --csv > gpurun_out/r2_pack_multi_raw.csv 2>/dev/null
