@@ -11,11 +11,12 @@
 //
 // Partials are fp64 and folded in a fixed order (bit-reproducible; the backward sums cancel almost exactly, see
 // colreduce.cuh).  HBM-bound: forward reads x twice and writes y once, backward reads dy and x twice and writes dx.
+#include <type_traits>
 #include "common.cuh"
 
 namespace tgan {
 
-constexpr int BNS_MAX_PARTS = 32;
+constexpr int BNS_MAX_PARTS = 64;
 struct SegRows {
   int n;
   int64_t end[4];      // exclusive end row of every segment (end[n - 1] = rows)
@@ -23,55 +24,95 @@ struct SegRows {
   __device__ __forceinline__ int64_t begin(int s) const { return s ? end[s - 1] : 0; }
 };
 
-template <typename T>
+// VEC consecutive channels per thread: 8 (16-byte bf16 / 2 x 16-byte fp32 accesses) or 1
+template <typename T, int VEC> __device__ __forceinline__ void ldv(const T* p, int64_t i, float (&v)[VEC]) {
+  if constexpr (VEC == 1) {
+    v[0] = ldf<T>(p, i);
+  } else if constexpr (std::is_same<T, float>::value) {
+    const float4 a = *reinterpret_cast<const float4*>(p + i), b = *reinterpret_cast<const float4*>(p + i + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    const uint4 t = *reinterpret_cast<const uint4*>(p + i);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { v[2 * j] = __low2float(h[j]); v[2 * j + 1] = __high2float(h[j]); }
+  }
+}
+template <typename T, int VEC> __device__ __forceinline__ void stv(T* p, int64_t i, const float (&v)[VEC]) {
+  if constexpr (VEC == 1) {
+    stf<T>(p, i, v[0]);
+  } else if constexpr (std::is_same<T, float>::value) {
+    *reinterpret_cast<float4*>(p + i) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + i + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    uint4 t;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    *reinterpret_cast<uint4*>(p + i) = t;
+  }
+}
+
+template <typename T, int VEC>
 struct BnFwdSegF {
   const T* x; int C;
-  __device__ __forceinline__ void operator()(int64_t r, int c, int, float& a, float& b) const {
-    const float v = ldf<T>(x, r * C + c);
-    a = v; b = v * v;
+  __device__ __forceinline__ void operator()(int64_t r, int c, int, float (&a)[VEC], float (&b)[VEC]) const {
+    ldv<T, VEC>(x, r * C + c, a);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) b[j] = a[j] * a[j];
   }
 };
-template <typename TDY, typename TX>
+template <typename TDY, typename TX, int VEC>
 struct BnBwdSegF {
   const TDY* dy; const TX* x; const float* mean; const float* rstd; int C;
-  __device__ __forceinline__ void operator()(int64_t r, int c, int s, float& a, float& b) const {
-    const float d = ldf<TDY>(dy, r * C + c);
-    const float xh = (ldf<TX>(x, r * C + c) - mean[s * C + c]) * rstd[s * C + c];
-    a = d; b = d * xh;
+  __device__ __forceinline__ void operator()(int64_t r, int c, int s, float (&a)[VEC], float (&b)[VEC]) const {
+    float xv[VEC];
+    ldv<TDY, VEC>(dy, r * C + c, a);
+    ldv<TX, VEC>(x, r * C + c, xv);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) b[j] = a[j] * ((xv[j] - mean[s * C + c + j]) * rstd[s * C + c + j]);
   }
 };
 
-// grid (ceil(C / 32), parts, nseg); 256 threads = 32 channels x 8 row lanes; partials [seg][part][2][C] (fp64)
-template <typename F>
+// grid (ceil(C / CH), parts, nseg); 256 threads = CL channel lanes (VEC channels each) x RL row lanes, CH = CL * VEC
+// channels per CTA; partials [seg][part][2][C] (fp64).  Four rows per thread are in flight (64 B per thread with VEC = 8).
+template <typename F, int VEC>
 __global__ void __launch_bounds__(256) segreduce_kernel(F f, SegRows sg, int C, double* __restrict__ partials) {
   pdl_entry();
-  __shared__ double sm[8][2][33];
-  const int s = blockIdx.z, tx = threadIdx.x & 31, ty = threadIdx.x >> 5, c = blockIdx.x * 32 + tx;
-  const int64_t r1 = sg.end[s], step = (int64_t)gridDim.y * 8;
-  double a0 = 0.0, a1 = 0.0;
+  constexpr int CL = VEC == 8 ? 8 : 32, RL = 256 / CL, CH = CL * VEC;
+  __shared__ double sm[RL][2][CH + 1];
+  const int s = blockIdx.z, tx = threadIdx.x % CL, ty = threadIdx.x / CL, c = blockIdx.x * CH + tx * VEC;
+  const int64_t r1 = sg.end[s], step = (int64_t)gridDim.y * RL;
+  double a0[VEC], a1[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) { a0[j] = 0.0; a1[j] = 0.0; }
   if (c < C) {
-    int64_t r = sg.begin(s) + (int64_t)blockIdx.y * 8 + ty;
-    for (; r + 3 * step < r1; r += 4 * step) {      // four rows in flight
-      float u[4], v[4];
+    int64_t r = sg.begin(s) + (int64_t)blockIdx.y * RL + ty;
+    for (; r + 3 * step < r1; r += 4 * step) {
+      float u[4][VEC], v[4][VEC];
 #pragma unroll
       for (int k = 0; k < 4; ++k) f(r + k * step, c, s, u[k], v[k]);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { a0 += (double)u[k]; a1 += (double)v[k]; }
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { a0[j] += (double)u[k][j]; a1[j] += (double)v[k][j]; }
     }
     for (; r < r1; r += step) {
-      float u, v;
+      float u[VEC], v[VEC];
       f(r, c, s, u, v);
-      a0 += (double)u; a1 += (double)v;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) { a0[j] += (double)u[j]; a1[j] += (double)v[j]; }
     }
   }
-  sm[ty][0][tx] = a0; sm[ty][1][tx] = a1;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) { sm[ty][0][tx * VEC + j] = a0[j]; sm[ty][1][tx * VEC + j] = a1[j]; }
   __syncthreads();
-  if (threadIdx.x < 64) {
-    const int a = threadIdx.x >> 5, cc = threadIdx.x & 31, co = blockIdx.x * 32 + cc;
+  if (threadIdx.x < 2 * CH) {
+    const int a = threadIdx.x / CH, cc = threadIdx.x % CH, co = blockIdx.x * CH + cc;
     if (co < C) {
       double t = 0.0;
-#pragma unroll
-      for (int y = 0; y < 8; ++y) t += sm[y][a][cc];
+#pragma unroll 8
+      for (int y = 0; y < RL; ++y) t += sm[y][a][cc];
       partials[(((int64_t)s * gridDim.y + blockIdx.y) * 2 + a) * C + co] = t;
     }
   }
@@ -108,20 +149,23 @@ __global__ void bn_finalize_seg_kernel(const double* __restrict__ partials, int 
   if (mv) mv[c] = v_run;
 }
 
+// (32-bit index arithmetic: the host checks rows * C < 2^31; a 64-bit division per vector costs more than the math)
+struct SegRows32 {
+  int n; unsigned end[4]; float inv_rows[4];
+  __device__ __forceinline__ int of(unsigned r) const { return (r >= end[0]) + (n > 2 && r >= end[1]) + (n > 3 && r >= end[2]); }
+};
 template <typename TX, typename TY, int VEC>
-__global__ void bn_apply_seg_kernel(const TX* __restrict__ x, TY* __restrict__ y, int64_t nvec, int C, SegRows sg,
+__global__ void bn_apply_seg_kernel(const TX* __restrict__ x, TY* __restrict__ y, unsigned nvec, unsigned cv, int C, SegRows32 sg,
                                     const float* __restrict__ scale, const float* __restrict__ shift) {
   pdl_entry();
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t e = i * VEC, r = e / C;
-    const int c = (int)(e - r * C), s = sg.of(r);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) {
+    const unsigned r = i / cv, c = (i - r * cv) * VEC;
+    const int s = sg.of(r);
     float v[VEC];
-    if constexpr (VEC == 4) ld4<TX>(x, e, *reinterpret_cast<float(*)[4]>(v));
-    else v[0] = ldf<TX>(x, e);
+    ldv<TX, VEC>(x, (int64_t)i * VEC, v);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) v[j] = v[j] * scale[s * C + c + j] + shift[s * C + c + j];
-    if constexpr (VEC == 4) st4<TY>(y, e, *reinterpret_cast<float(*)[4]>(v));
-    else stf<TY>(y, e, v[0]);
+    stv<TY, VEC>(y, (int64_t)i * VEC, v);
   }
 }
 
@@ -145,29 +189,25 @@ __global__ void bn_bwd_fold_seg_kernel(const double* __restrict__ partials, int 
 }
 
 template <typename TDY, typename TX, typename TDX, int VEC>
-__global__ void bn_bwd_apply_seg_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, TDX* __restrict__ dx, int64_t nvec,
-                                        int C, SegRows sg, const float* __restrict__ mean, const float* __restrict__ rstd,
-                                        const float* __restrict__ gamma, const float* __restrict__ s1,
-                                        const float* __restrict__ s2) {
+__global__ void bn_bwd_apply_seg_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, TDX* __restrict__ dx, unsigned nvec,
+                                        unsigned cv, int C, SegRows32 sg, const float* __restrict__ mean,
+                                        const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                        const float* __restrict__ s1, const float* __restrict__ s2) {
   pdl_entry();
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t e = i * VEC, r = e / C;
-    const int c = (int)(e - r * C), s = sg.of(r);
-    const float inv_rows = 1.0f / (float)(sg.end[s] - sg.begin(s));
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) {
+    const unsigned r = i / cv, c = (i - r * cv) * VEC;
+    const int s = sg.of(r);
+    const float inv_rows = sg.inv_rows[s];
     float d[VEC], xv[VEC], o[VEC];
-    if constexpr (VEC == 4) {
-      ld4<TDY>(dy, e, *reinterpret_cast<float(*)[4]>(d)); ld4<TX>(x, e, *reinterpret_cast<float(*)[4]>(xv));
-    } else {
-      d[0] = ldf<TDY>(dy, e); xv[0] = ldf<TX>(x, e);
-    }
+    ldv<TDY, VEC>(dy, (int64_t)i * VEC, d);
+    ldv<TX, VEC>(x, (int64_t)i * VEC, xv);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       const int k = s * C + c + j;
       const float xh = (xv[j] - mean[k]) * rstd[k];
       o[j] = gamma[c + j] * rstd[k] * (d[j] - s1[k] * inv_rows - xh * s2[k] * inv_rows);
     }
-    if constexpr (VEC == 4) st4<TDX>(dx, e, *reinterpret_cast<float(*)[4]>(o));
-    else stf<TDX>(dx, e, o[0]);
+    stv<TDX, VEC>(dx, (int64_t)i * VEC, o);
   }
 }
 
@@ -185,10 +225,20 @@ static int make_seg_rows(SegRows& sg, int64_t rows, int nseg, int64_t r0, int64_
   }
   return 0;
 }
-static int pick_seg_parts(int64_t rows, int nseg, int C) {
-  const int xb = ceil_div(C, 32);
-  int64_t want = (148 * 4 + xb * nseg - 1) / (xb * nseg);      // ~4 CTAs per SM over the whole grid
-  const int64_t maxp = (rows / nseg + 15) / 16;                  // >= 2 rows per thread
+static int make_seg_rows32(SegRows32& s32, const SegRows& sg, int64_t rows, int C) {
+  if (rows * C >= ((int64_t)1 << 31)) { set_error("bn_seg: rows * C must be < 2^31"); return 1; }
+  s32.n = sg.n;
+  for (int i = 0; i < 4; ++i) {
+    s32.end[i] = (unsigned)sg.end[i];
+    s32.inv_rows[i] = i < sg.n ? 1.0f / (float)(sg.end[i] - (i ? sg.end[i - 1] : 0)) : 0.f;
+  }
+  return 0;
+}
+static int pick_seg_parts(int64_t rows, int nseg, int C, int vec) {
+  const int ch = vec == 8 ? 64 : 32, rl = vec == 8 ? 32 : 8;
+  const int xb = ceil_div(C, ch);
+  int64_t want = (148 * 6 + xb * nseg - 1) / (xb * nseg);      // ~6 CTAs per SM over the whole grid
+  const int64_t maxp = (rows / nseg + rl * 2 - 1) / (rl * 2);    // >= 2 rows per thread
   int64_t p = want < maxp ? want : maxp;
   if (p < 1) p = 1;
   if (p > BNS_MAX_PARTS) p = BNS_MAX_PARTS;
@@ -204,33 +254,40 @@ static inline int grid1d(int64_t n) {
 
 using namespace tgan;
 
+// ws layout (floats): [0, 1024 C) fp64 partials [nseg][parts <= 64][2][C]; [1024 C, 1032 C) two [4][C] fp32 tables
 extern "C" int tgan_bn_fwd_seg(const void* x, int xdt, void* y, int ydt, int64_t rows, int C, int nseg, int64_t r0, int64_t r1,
                                int64_t r2, const float* gamma, const float* beta, float eps, float decay,
                                int unbiased_moving_var, float* moving_mean, float* moving_var, float* mean, float* rstd,
                                float* ws, void* stream) {
   TGAN_CHECK_ARG(x && y && gamma && beta && mean && rstd && ws && rows > 0 && C > 0 && aligned16(ws), "bn_fwd_seg: bad args");
   SegRows sg;
-  if (make_seg_rows(sg, rows, nseg, r0, r1, r2)) return 1;
+  SegRows32 s32;
+  if (make_seg_rows(sg, rows, nseg, r0, r1, r2) || make_seg_rows32(s32, sg, rows, C)) return 1;
   cudaStream_t st = (cudaStream_t)stream;
-  const int parts = pick_seg_parts(rows, nseg, C);
-  double* partials = reinterpret_cast<double*>(ws);                    // [nseg][parts][2][C] fp64: <= 512 * C floats
-  float* scale = ws + (int64_t)4 * BNS_MAX_PARTS * 4 * C;              // [nseg][C], then shift [nseg][C]
+  const bool v8 = C % 8 == 0 && aligned16(x) && aligned16(y);
+  const int parts = pick_seg_parts(rows, nseg, C, v8 ? 8 : 1);
+  double* partials = reinterpret_cast<double*>(ws);
+  float* scale = ws + (int64_t)1024 * C;
   float* shift = scale + (int64_t)4 * C;
   TGAN_DISPATCH_1(xdt, TX, {
-    BnFwdSegF<TX> f{(const TX*)x, C};
-    pdl_launch(segreduce_kernel<BnFwdSegF<TX>>, dim3(ceil_div(C, 32), parts, nseg), 256, 0, st, f, sg, C, partials);
+    if (v8) {
+      BnFwdSegF<TX, 8> f{(const TX*)x, C};
+      pdl_launch(segreduce_kernel<BnFwdSegF<TX, 8>, 8>, dim3(ceil_div(C, 64), parts, nseg), 256, 0, st, f, sg, C, partials);
+    } else {
+      BnFwdSegF<TX, 1> f{(const TX*)x, C};
+      pdl_launch(segreduce_kernel<BnFwdSegF<TX, 1>, 1>, dim3(ceil_div(C, 32), parts, nseg), 256, 0, st, f, sg, C, partials);
+    }
   });
   TGAN_LAUNCHED();
   pdl_launch(bn_finalize_seg_kernel, ceil_div(C, 128), 128, 0, st, (const double*)partials, parts, sg, C, gamma, beta, eps, decay,
              unbiased_moving_var, moving_mean, moving_var, mean, rstd, scale, shift);
   TGAN_LAUNCHED();
   const int64_t n = rows * C;
-  const bool v4 = C % 4 == 0 && aligned16(x) && aligned16(y);
   TGAN_DISPATCH_1(xdt, TX, TGAN_DISPATCH_1(ydt, TY, {
-    if (v4) pdl_launch(bn_apply_seg_kernel<TX, TY, 4>, grid1d(n / 4), 256, 0, st, (const TX*)x, (TY*)y, n / 4, C, sg,
-                       (const float*)scale, (const float*)shift);
-    else pdl_launch(bn_apply_seg_kernel<TX, TY, 1>, grid1d(n), 256, 0, st, (const TX*)x, (TY*)y, n, C, sg, (const float*)scale,
-                    (const float*)shift);
+    if (v8) pdl_launch(bn_apply_seg_kernel<TX, TY, 8>, grid1d(n / 8), 256, 0, st, (const TX*)x, (TY*)y, (unsigned)(n / 8),
+                       (unsigned)(C / 8), C, s32, (const float*)scale, (const float*)shift);
+    else pdl_launch(bn_apply_seg_kernel<TX, TY, 1>, grid1d(n), 256, 0, st, (const TX*)x, (TY*)y, (unsigned)n, (unsigned)C, C, s32,
+                    (const float*)scale, (const float*)shift);
   }));
   TGAN_LAUNCHED();
   return 0;
@@ -241,27 +298,33 @@ extern "C" int tgan_bn_bwd_seg(const void* dy, int dydt, const void* x, int xdt,
                                const float* gamma, float* dgamma, float* dbeta, float beta_acc, float* ws, void* stream) {
   TGAN_CHECK_ARG(dy && x && dx && mean && rstd && gamma && ws && rows > 0 && C > 0 && aligned16(ws), "bn_bwd_seg: bad args");
   SegRows sg;
-  if (make_seg_rows(sg, rows, nseg, r0, r1, r2)) return 1;
+  SegRows32 s32;
+  if (make_seg_rows(sg, rows, nseg, r0, r1, r2) || make_seg_rows32(s32, sg, rows, C)) return 1;
   cudaStream_t st = (cudaStream_t)stream;
-  const int parts = pick_seg_parts(rows, nseg, C);
+  const bool v8 = C % 8 == 0 && aligned16(dy) && aligned16(x) && aligned16(dx);
+  const int parts = pick_seg_parts(rows, nseg, C, v8 ? 8 : 1);
   double* partials = reinterpret_cast<double*>(ws);
-  float* s1 = ws + (int64_t)4 * BNS_MAX_PARTS * 4 * C;
+  float* s1 = ws + (int64_t)1024 * C;
   float* s2 = s1 + (int64_t)4 * C;
   TGAN_DISPATCH_1(dydt, TDY, TGAN_DISPATCH_1(xdt, TX, {
-    BnBwdSegF<TDY, TX> f{(const TDY*)dy, (const TX*)x, mean, rstd, C};
-    pdl_launch(segreduce_kernel<BnBwdSegF<TDY, TX>>, dim3(ceil_div(C, 32), parts, nseg), 256, 0, st, f, sg, C, partials);
+    if (v8) {
+      BnBwdSegF<TDY, TX, 8> f{(const TDY*)dy, (const TX*)x, mean, rstd, C};
+      pdl_launch(segreduce_kernel<BnBwdSegF<TDY, TX, 8>, 8>, dim3(ceil_div(C, 64), parts, nseg), 256, 0, st, f, sg, C, partials);
+    } else {
+      BnBwdSegF<TDY, TX, 1> f{(const TDY*)dy, (const TX*)x, mean, rstd, C};
+      pdl_launch(segreduce_kernel<BnBwdSegF<TDY, TX, 1>, 1>, dim3(ceil_div(C, 32), parts, nseg), 256, 0, st, f, sg, C, partials);
+    }
   }));
   TGAN_LAUNCHED();
   pdl_launch(bn_bwd_fold_seg_kernel, ceil_div(C, 128), 128, 0, st, (const double*)partials, parts, nseg, C, s1, s2, dgamma, dbeta,
              beta_acc);
   TGAN_LAUNCHED();
   const int64_t n = rows * C;
-  const bool v4 = C % 4 == 0 && aligned16(dy) && aligned16(x) && aligned16(dx);
   TGAN_DISPATCH_1(dydt, TDY, TGAN_DISPATCH_1(xdt, TX, TGAN_DISPATCH_1(dxdt, TDX, {
-    if (v4) pdl_launch(bn_bwd_apply_seg_kernel<TDY, TX, TDX, 4>, grid1d(n / 4), 256, 0, st, (const TDY*)dy, (const TX*)x, (TDX*)dx,
-                       n / 4, C, sg, mean, rstd, gamma, (const float*)s1, (const float*)s2);
-    else pdl_launch(bn_bwd_apply_seg_kernel<TDY, TX, TDX, 1>, grid1d(n), 256, 0, st, (const TDY*)dy, (const TX*)x, (TDX*)dx, n, C, sg,
-                    mean, rstd, gamma, (const float*)s1, (const float*)s2);
+    if (v8) pdl_launch(bn_bwd_apply_seg_kernel<TDY, TX, TDX, 8>, grid1d(n / 8), 256, 0, st, (const TDY*)dy, (const TX*)x, (TDX*)dx,
+                       (unsigned)(n / 8), (unsigned)(C / 8), C, s32, mean, rstd, gamma, (const float*)s1, (const float*)s2);
+    else pdl_launch(bn_bwd_apply_seg_kernel<TDY, TX, TDX, 1>, grid1d(n), 256, 0, st, (const TDY*)dy, (const TX*)x, (TDX*)dx,
+                    (unsigned)n, (unsigned)C, C, s32, mean, rstd, gamma, (const float*)s1, (const float*)s2);
   })));
   TGAN_LAUNCHED();
   return 0;

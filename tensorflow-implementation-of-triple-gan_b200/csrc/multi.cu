@@ -238,11 +238,24 @@ extern "C" int tgan_weightnorm_bwd_multi(const tgan_wn_desc* descs_dev, int n, i
   TGAN_LAUNCHED();
   return 0;
 }
+// the tile loop is grid-strided over RESIDENT CTAs: a grid larger than one wave would run its surplus CTAs after the
+// first wave has finished all of its tiles
+static int pack_grid() {
+  static int grid = 0;
+  if (!grid) {
+    int per_sm = 0, dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pack_multi_kernel, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    grid = sms * per_sm;
+  }
+  return grid;
+}
 extern "C" int tgan_pack_weight_multi(const tgan_pack_desc* descs_dev, int n, void* stream) {
   TGAN_CHECK_ARG(descs_dev && n > 0, "pack_weight_multi: bad args");
   for (int n0 = 0; n0 < n; n0 += PACK_MAX_DESCS) {      // (a network has 10-40 packed operands: one launch)
     const int cnt = n - n0 < PACK_MAX_DESCS ? n - n0 : PACK_MAX_DESCS;
-    pdl_launch(pack_multi_kernel, 148 * 8, 256, 0, (cudaStream_t)stream, descs_dev, n0, cnt);
+    pdl_launch(pack_multi_kernel, pack_grid(), 256, 0, (cudaStream_t)stream, descs_dev, n0, cnt);
     TGAN_LAUNCHED();
   }
   return 0;

@@ -1039,32 +1039,49 @@ static inline int grid_for(int64_t n, int block = 256) {
 // all segments of a grouped batch in ONE single-CTA launch: per-segment column means (fixed summation order), pop_mean
 // updated once per segment in call order, apply + nonlinearity.  Replaces 2 launches per segment (8 for the grouped
 // phase-C batch) of a few microseconds each.  256 threads = 32 columns x 8 row lanes; C <= 32.
-struct SmallSegs { int n; int end[4]; };      // exclusive end row of every segment
+struct SmallSegs { int n; int end[4]; };      // exclusive end row of every segment (unused entries = rows)
+__device__ __forceinline__ int small_seg_of(const SmallSegs& sg, int r) { return (r >= sg.end[0]) + (r >= sg.end[1]) + (r >= sg.end[2]); }
+// ONE pass over the rows for all segments: thread (column tx, row lane ty) adds row r into the accumulator of r's segment
+// (four independent accumulators, selected without branches), so the loads of all segments are in flight together.
+template <typename Fn>
+__device__ __forceinline__ void small_seg_colsums(const SmallSegs& sg, int C, float (*part)[4][33], float (*out)[32], Fn val) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int rows = sg.end[sg.n - 1];
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+  if (tx < C)
+    for (int r = ty; r < rows; r += 8) {
+      const float v = val(r * C + tx);
+      const int s = small_seg_of(sg, r);
+      a[0] += s == 0 ? v : 0.f; a[1] += s == 1 ? v : 0.f; a[2] += s == 2 ? v : 0.f; a[3] += s == 3 ? v : 0.f;
+    }
+#pragma unroll
+  for (int s = 0; s < 4; ++s) part[ty][s][tx] = a[s];
+  __syncthreads();
+  if (threadIdx.x < 128) {      // 4 segments x 32 columns, fixed order over the 8 row lanes
+    const int s = threadIdx.x >> 5, c = threadIdx.x & 31;
+    float t = 0.f;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) t += part[l][s][c];
+    out[s][c] = t;
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(256) mobn_small_fwd_kernel(const float* __restrict__ z, float* __restrict__ y, int C, SmallSegs sg,
                                                              const float* __restrict__ b, float* __restrict__ pop_mean,
                                                              float decay, int train, int act, float alpha) {
   pdl_entry();
-  __shared__ float part[8][33];
+  __shared__ float part[8][4][33];
   __shared__ float mean[4][32];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int s = 0, r0 = 0; s < sg.n; r0 = sg.end[s], ++s) {
-    const int r1 = sg.end[s];
-    if (train) {
-      float a = 0.f;
-      if (tx < C)
-        for (int r = r0 + ty; r < r1; r += 8) a += z[(int64_t)r * C + tx];
-      part[ty][tx] = a;
-      __syncthreads();
-      if (ty == 0 && tx < C) {
-        float t = 0.f;
-#pragma unroll
-        for (int l = 0; l < 8; ++l) t += part[l][tx];
-        mean[s][tx] = t * (1.0f / (float)(r1 - r0));
-      }
-      __syncthreads();
-    } else if (ty == 0 && tx < C) {
-      mean[s][tx] = pop_mean[tx];
+  if (train) {
+    small_seg_colsums(sg, C, part, mean, [&](int i) { return z[i]; });
+    if (threadIdx.x < 128) {
+      const int s = threadIdx.x >> 5, c = threadIdx.x & 31;
+      const int n = s < sg.n ? sg.end[s] - (s ? sg.end[s - 1] : 0) : 1;
+      mean[s][c] *= 1.0f / (float)n;
     }
+  } else if (threadIdx.x < 128) {
+    mean[threadIdx.x >> 5][threadIdx.x & 31] = (int)(threadIdx.x & 31) < C ? pop_mean[threadIdx.x & 31] : 0.f;
   }
   __syncthreads();
   if (train && pop_mean && threadIdx.x < C) {
@@ -1075,8 +1092,7 @@ __global__ void __launch_bounds__(256) mobn_small_fwd_kernel(const float* __rest
   const int total = sg.end[sg.n - 1] * C;
   for (int i = threadIdx.x; i < total; i += 256) {
     const int r = i / C, c = i - r * C;
-    const int s = (r >= sg.end[0]) + (sg.n > 2 && r >= sg.end[1]) + (sg.n > 3 && r >= sg.end[2]);
-    y[i] = act_fwd(z[i] + (b ? b[c] : 0.f) - mean[s][c], act, alpha);
+    y[i] = act_fwd(z[i] + (b ? b[c] : 0.f) - mean[small_seg_of(sg, r)][c], act, alpha);
   }
 }
 
@@ -1086,37 +1102,21 @@ __global__ void __launch_bounds__(256) mobn_small_bwd_kernel(const float* __rest
                                                              float* __restrict__ dz, int C, SmallSegs sg, int act, float alpha,
                                                              int subtract_mean, float* __restrict__ grad_acc) {
   pdl_entry();
-  __shared__ float part[8][33];
-  __shared__ float mean[4][32];
-  __shared__ float tot[32];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  if (threadIdx.x < 32) tot[threadIdx.x] = 0.f;
-  for (int s = 0, r0 = 0; s < sg.n; r0 = sg.end[s], ++s) {
-    const int r1 = sg.end[s];
-    float a = 0.f;
-    if (tx < C)
-      for (int r = r0 + ty; r < r1; r += 8) {
-        const int64_t i = (int64_t)r * C + tx;
-        a += dy[i] * act_grad_from_y(y[i], act, alpha);
-      }
-    part[ty][tx] = a;
-    __syncthreads();
-    if (ty == 0 && tx < C) {
-      float t = 0.f;
-#pragma unroll
-      for (int l = 0; l < 8; ++l) t += part[l][tx];
-      tot[tx] += t;
-      mean[s][tx] = subtract_mean ? t * (1.0f / (float)(r1 - r0)) : 0.f;
-    }
-    __syncthreads();
+  __shared__ float part[8][4][33];
+  __shared__ float sums[4][32];
+  small_seg_colsums(sg, C, part, sums, [&](int i) { return dy[i] * act_grad_from_y(y[i], act, alpha); });
+  if (grad_acc && threadIdx.x < C) {
+    float t = 0.f;
+    for (int s = 0; s < sg.n; ++s) t += sums[s][threadIdx.x];
+    grad_acc[threadIdx.x] += t;
   }
-  if (grad_acc && threadIdx.x < C) grad_acc[threadIdx.x] += tot[threadIdx.x];
   if (dz) {
     const int total = sg.end[sg.n - 1] * C;
     for (int i = threadIdx.x; i < total; i += 256) {
       const int r = i / C, c = i - r * C;
-      const int s = (r >= sg.end[0]) + (sg.n > 2 && r >= sg.end[1]) + (sg.n > 3 && r >= sg.end[2]);
-      dz[i] = dy[i] * act_grad_from_y(y[i], act, alpha) - mean[s][c];
+      const int s = small_seg_of(sg, r);
+      const int n = sg.end[s] - (s ? sg.end[s - 1] : 0);
+      dz[i] = dy[i] * act_grad_from_y(y[i], act, alpha) - (subtract_mean ? sums[s][c] / (float)n : 0.f);
     }
   }
 }
