@@ -118,26 +118,48 @@ __global__ void __launch_bounds__(256) segreduce_kernel(F f, SegRows sg, int C, 
   }
 }
 
-// one thread per channel: fold the partials of every segment in order, finalize, update the moving statistics once per
-// segment in call order (tf.contrib batch_norm with updates_collections=None runs its update inside every call)
-__global__ void bn_finalize_seg_kernel(const double* __restrict__ partials, int parts, SegRows sg, int C,
+// Fold of the partials: 256 threads = 32 channels x 8 part lanes; lane l sums parts l, l + 8, ... of every (segment,
+// statistic), the eight lane sums are added in a fixed order.  out[seg * 2 + stat][channel] in shared memory.
+__device__ __forceinline__ void fold_partials(const double* __restrict__ partials, int parts, int nseg, int C, int c,
+                                              double (*lanes)[8][33], double (*out)[33]) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int q = 0; q < nseg * 2; ++q) {
+    double t = 0.0;
+    if (c < C)
+      for (int p = ty; p < parts; p += 8) t += partials[(((int64_t)(q >> 1) * parts + p) * 2 + (q & 1)) * C + c];
+    lanes[ty][q][tx] = t;
+  }
+  __syncthreads();
+  {
+    const int q = threadIdx.x >> 5;      // 8 warps = up to 4 segments x 2 statistics
+    if (q < nseg * 2) {
+      double t = 0.0;
+#pragma unroll
+      for (int l = 0; l < 8; ++l) t += lanes[l][q][tx];
+      out[q][tx] = t;
+    }
+  }
+  __syncthreads();
+}
+
+// finalize (mean, rstd, scale, shift per segment) and update the moving statistics once per segment in call order
+// (tf.contrib batch_norm with updates_collections=None runs its update inside every call).  grid ceil(C / 32) x 256 threads
+__global__ void __launch_bounds__(256) bn_finalize_seg_kernel(const double* __restrict__ partials, int parts, SegRows sg, int C,
                                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float decay,
                                        int unbiased, float* mm, float* mv, float* __restrict__ mean, float* __restrict__ rstd,
                                        float* __restrict__ scale, float* __restrict__ shift) {
   pdl_entry();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  __shared__ double lanes[8][8][33];
+  __shared__ double tot[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  fold_partials(partials, parts, sg.n, C, c, lanes, tot);
+  if (threadIdx.x >= 32 || c >= C) return;
   float m_run = mm ? mm[c] : 0.f, v_run = mv ? mv[c] : 0.f;
   for (int s = 0; s < sg.n; ++s) {
-    double s0 = 0.0, s1 = 0.0;
-    for (int p = 0; p < parts; ++p) {
-      s0 += partials[(((int64_t)s * parts + p) * 2 + 0) * C + c];
-      s1 += partials[(((int64_t)s * parts + p) * 2 + 1) * C + c];
-    }
     const float rows = (float)(sg.end[s] - sg.begin(s));
     // (the same fp32 arithmetic as bn_finalize_kernel on the fp32-rounded totals: the grouped and the per-call paths agree)
-    const float mu = (float)s0 / rows;
-    const float var = fmaxf((float)s1 / rows - mu * mu, 0.f);
+    const float mu = (float)tot[2 * s][threadIdx.x] / rows;
+    const float var = fmaxf((float)tot[2 * s + 1][threadIdx.x] / rows - mu * mu, 0.f);
     const float rs = rsqrtf(var + eps);
     mean[s * C + c] = mu; rstd[s * C + c] = rs;
     const float sc = gamma[c] * rs;
@@ -169,20 +191,20 @@ __global__ void bn_apply_seg_kernel(const TX* __restrict__ x, TY* __restrict__ y
   }
 }
 
-__global__ void bn_bwd_fold_seg_kernel(const double* __restrict__ partials, int parts, int nseg, int C, float* __restrict__ s1,
-                                       float* __restrict__ s2, float* dgamma, float* dbeta, float beta_acc) {
+__global__ void __launch_bounds__(256) bn_bwd_fold_seg_kernel(const double* __restrict__ partials, int parts, int nseg, int C,
+                                                              float* __restrict__ s1, float* __restrict__ s2, float* dgamma,
+                                                              float* dbeta, float beta_acc) {
   pdl_entry();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  __shared__ double lanes[8][8][33];
+  __shared__ double tot[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  fold_partials(partials, parts, nseg, C, c, lanes, tot);
+  if (threadIdx.x >= 32 || c >= C) return;
   double t1 = 0.0, t2 = 0.0;
   for (int s = 0; s < nseg; ++s) {
-    double a = 0.0, b = 0.0;
-    for (int p = 0; p < parts; ++p) {
-      a += partials[(((int64_t)s * parts + p) * 2 + 0) * C + c];
-      b += partials[(((int64_t)s * parts + p) * 2 + 1) * C + c];
-    }
-    s1[s * C + c] = (float)a; s2[s * C + c] = (float)b;
-    t1 += (double)(float)a; t2 += (double)(float)b;      // (per-call path: every call adds its fp32-rounded sums)
+    const float a = (float)tot[2 * s][threadIdx.x], b = (float)tot[2 * s + 1][threadIdx.x];
+    s1[s * C + c] = a; s2[s * C + c] = b;
+    t1 += (double)a; t2 += (double)b;      // (per-call path: every call adds its fp32-rounded sums)
   }
   if (dbeta) dbeta[c] = (float)((beta_acc != 0.f ? (double)beta_acc * dbeta[c] : 0.0) + t1);
   if (dgamma) dgamma[c] = (float)((beta_acc != 0.f ? (double)beta_acc * dgamma[c] : 0.0) + t2);
@@ -279,7 +301,7 @@ extern "C" int tgan_bn_fwd_seg(const void* x, int xdt, void* y, int ydt, int64_t
     }
   });
   TGAN_LAUNCHED();
-  pdl_launch(bn_finalize_seg_kernel, ceil_div(C, 128), 128, 0, st, (const double*)partials, parts, sg, C, gamma, beta, eps, decay,
+  pdl_launch(bn_finalize_seg_kernel, ceil_div(C, 32), 256, 0, st, (const double*)partials, parts, sg, C, gamma, beta, eps, decay,
              unbiased_moving_var, moving_mean, moving_var, mean, rstd, scale, shift);
   TGAN_LAUNCHED();
   const int64_t n = rows * C;
@@ -316,7 +338,7 @@ extern "C" int tgan_bn_bwd_seg(const void* dy, int dydt, const void* x, int xdt,
     }
   }));
   TGAN_LAUNCHED();
-  pdl_launch(bn_bwd_fold_seg_kernel, ceil_div(C, 128), 128, 0, st, (const double*)partials, parts, nseg, C, s1, s2, dgamma, dbeta,
+  pdl_launch(bn_bwd_fold_seg_kernel, ceil_div(C, 32), 256, 0, st, (const double*)partials, parts, nseg, C, s1, s2, dgamma, dbeta,
              beta_acc);
   TGAN_LAUNCHED();
   const int64_t n = rows * C;

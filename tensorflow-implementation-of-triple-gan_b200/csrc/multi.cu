@@ -150,45 +150,77 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const tgan_pack_desc* _
   const int total = first[n];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   int di = 0;
+  // ncu (profiles/r2_ncu_pack_multi_summary.txt): the first versions of this loop were INSTRUCTION-bound -- 84 instructions
+  // per element (64-bit index arithmetic on descriptor fields re-read from shared memory, per-element bounds checks).  Per
+  // tile everything is now reduced to one source pointer + stride and one destination pointer + stride per thread; only
+  // edge tiles (partial in n or k) take the checked path.
   for (int ft0 = blockIdx.x * PACK_U; ft0 < total; ft0 += gridDim.x * PACK_U) {
     float v[PACK_U][4];
-    int dsel[PACK_U], kb_[PACK_U], nb_[PACK_U], t_[PACK_U];
+    bf16* dptr[PACK_U];
+    int64_t dstep[PACK_U];
+    int mode[PACK_U];            // -1: no tile; bit 0: transposed; bit 1: edge tile (checked stores)
+    int nrem[PACK_U], krem[PACK_U];
     // ---- phase 1: every global load of the PACK_U tiles ----
 #pragma unroll
     for (int u = 0; u < PACK_U; ++u) {
       const int ft = ft0 + u;
-      dsel[u] = -1;
+      mode[u] = -1;
       if (ft >= total) continue;
       while (ft >= first[di + 1]) ++di;            // flat tiles are visited in increasing order
       const tgan_pack_desc& d = ds[di];
+      const int K = d.K, Nr = d.Nr, Kpad = d.Kpad, son = d.scale_on;
+      const int64_t sn = d.sn, sk = d.sk;
       const int tile = ft - first[di];
-      const int nbk = (d.Kpad + 31) / 32, nbn = (d.Nr + 31) / 32;
-      const int kb = tile % nbk, nb = (tile / nbk) % nbn, t = tile / (nbk * nbn);
-      dsel[u] = di; kb_[u] = kb; nb_[u] = nb; t_[u] = t;
+      const int nbk = (Kpad + 31) >> 5, nbn = (Nr + 31) >> 5;
+      const int kb = tile % nbk, r2 = tile / nbk, nb = r2 % nbn, t = r2 / nbn;
       const int tap = t < 32 ? (int)tap_sm[di][t] : (d.taps ? d.taps[t] : t);
-      const int64_t base = (int64_t)tap * d.st;
-      const bool transpose = d.sk != 1 && d.sn == 1;
+      const bool transpose = sk != 1 && sn == 1;
+      const bool edge = (nb * 32 + 32 > Nr) || (kb * 32 + 32 > K);
+      mode[u] = (transpose ? 1 : 0) | (edge ? 2 : 0);
+      // rows j = ty + 8 * jj of the tile; lanes tx along the source's contiguous axis
+      const int n0 = transpose ? nb * 32 + tx : nb * 32 + ty;      // first n of this thread
+      const int k0 = transpose ? kb * 32 + ty : kb * 32 + tx;      // first k of this thread
+      const float* sp = d.src + (int64_t)tap * d.st + (int64_t)n0 * sn + (int64_t)k0 * sk;
+      const int64_t sstep = 8 * (transpose ? sk : sn);
+      const float* scp = son == 0 ? nullptr : d.scale + ((son == 1) == transpose ? (transpose ? n0 : k0) : 0);
+      // scale index: son == 1 -> scale[n], son == 2 -> scale[k]; it is lane-constant when it follows the lane axis
+      const bool sc_lane = son != 0 && ((son == 1) == transpose);   // transposed: lanes along n; else lanes along k
+      float scl = 1.f;
+      if (!edge) {
+        if (sc_lane) scl = *scp;
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const int j = ty + 8 * jj;
-        // transposed tiles: lanes along n (the contiguous source axis), rows j along k; else lanes along k, rows along n
-        const int n_ = transpose ? nb * 32 + tx : nb * 32 + j;
-        const int k = transpose ? kb * 32 + j : kb * 32 + tx;
-        float x = 0.f;
-        if (k < d.K && n_ < d.Nr) {
-          x = d.src[base + (int64_t)n_ * d.sn + (int64_t)k * d.sk];
-          if (d.scale_on == 1) x *= d.scale[n_];
-          else if (d.scale_on == 2) x *= d.scale[k];
+        for (int jj = 0; jj < 4; ++jj) v[u][jj] = sp[jj * sstep];
+        if (son != 0 && !sc_lane) {
+          const float* sr = d.scale + (transpose ? k0 : n0);       // follows the row axis j
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) v[u][jj] *= sr[8 * jj];
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) v[u][jj] *= scl;
         }
-        v[u][jj] = x;
+      } else {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int n_ = transpose ? n0 : n0 + 8 * jj, k = transpose ? k0 + 8 * jj : k0;
+          float x = 0.f;
+          if (k < K && n_ < Nr) {
+            x = sp[jj * sstep];
+            if (son == 1) x *= d.scale[n_];
+            else if (son == 2) x *= d.scale[k];
+          }
+          v[u][jj] = x;
+        }
       }
+      // destination: rows nn = nb * 32 + ty + 8 * jj, lane k = kb * 32 + tx
+      dptr[u] = reinterpret_cast<bf16*>(d.dst) + ((int64_t)t * Nr + nb * 32 + ty) * Kpad + kb * 32 + tx;
+      dstep[u] = (int64_t)8 * Kpad;
+      nrem[u] = Nr - (nb * 32 + ty);          // row jj is inside iff 8 * jj < nrem
+      krem[u] = Kpad - (kb * 32 + tx);        // lane is inside iff krem > 0
     }
     // ---- phase 2: transposed tiles go through shared memory ----
 #pragma unroll
     for (int u = 0; u < PACK_U; ++u) {
-      if (dsel[u] < 0) continue;
-      const tgan_pack_desc& d = ds[dsel[u]];
-      if (d.sk != 1 && d.sn == 1) {
+      if (mode[u] >= 0 && (mode[u] & 1)) {
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) sm[u][ty + 8 * jj][tx] = v[u][jj];
       }
@@ -196,17 +228,18 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const tgan_pack_desc* _
     __syncthreads();
 #pragma unroll
     for (int u = 0; u < PACK_U; ++u) {
-      if (dsel[u] < 0) continue;
-      const tgan_pack_desc& d = ds[dsel[u]];
-      bf16* dst = reinterpret_cast<bf16*>(d.dst);
-      const bool transpose = d.sk != 1 && d.sn == 1;
-      const int k = kb_[u] * 32 + tx;
+      if (mode[u] < 0) continue;
+      if (mode[u] & 1) {
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const int j = ty + 8 * jj;
-        const int nn = nb_[u] * 32 + j;
-        if (nn < d.Nr && k < d.Kpad)
-          dst[((int64_t)t_[u] * d.Nr + nn) * d.Kpad + k] = __float2bfloat16_rn(transpose ? sm[u][tx][j] : v[u][jj]);
+        for (int jj = 0; jj < 4; ++jj) v[u][jj] = sm[u][tx][ty + 8 * jj];
+      }
+      if (!(mode[u] & 2)) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) dptr[u][jj * dstep[u]] = __float2bfloat16_rn(v[u][jj]);
+      } else if (krem[u] > 0) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          if (8 * jj < nrem[u]) dptr[u][jj * dstep[u]] = __float2bfloat16_rn(v[u][jj]);
       }
     }
     __syncthreads();

@@ -1049,7 +1049,8 @@ __device__ __forceinline__ void small_seg_colsums(const SmallSegs& sg, int C, fl
   const int rows = sg.end[sg.n - 1];
   float a[4] = {0.f, 0.f, 0.f, 0.f};
   if (tx < C)
-    for (int r = ty; r < rows; r += 8) {
+#pragma unroll 8
+    for (int r = ty; r < rows; r += 8) {      // (unrolled: the loads of eight rows are issued before the first add)
       const float v = val(r * C + tx);
       const int s = small_seg_of(sg, r);
       a[0] += s == 0 ? v : 0.f; a[1] += s == 1 ? v : 0.f; a[2] += s == 2 ? v : 0.f; a[3] += s == 3 ? v : 0.f;
