@@ -188,7 +188,7 @@ typedef struct {
 typedef struct {
   const float* src; void* dst; const float* scale; const int* taps;
   int64_t st, sn, sk;
-  int T, Nr, K, Kpad, scale_on, pad_;
+  int T, Nr, K, Kpad, scale_on, scale_mod;   /* scale_mod > 0: the scale index is taken modulo scale_mod (k = (tap, co) flattened) */
 } tgan_pack_desc;
 int tgan_weightnorm_fwd_multi(const tgan_wn_desc* descs_dev, int n, int max_co, float* ws, void* stream);
 int tgan_weightnorm_bwd_multi(const tgan_wn_desc* descs_dev, int n, int max_co, float* ws, void* stream);
@@ -263,7 +263,7 @@ int tgan_mobn_small_bwd(const float* dy, const float* y, float* dz, int64_t rows
  *   bn_fwd_seg: y = (x - mean_seg) * rstd_seg * gamma + beta; mean / rstd: [nseg][C] outputs kept for the backward.
  *   bn_bwd_seg: dx = gamma * rstd_seg * (dy - s1_seg/n_seg - xhat * s2_seg/n_seg), s1 = sum dy, s2 = sum dy * xhat;
  *               dbeta = beta_acc * dbeta + sum_seg s1, dgamma likewise with s2 (either may be NULL).
- * ws: 1032 * C floats, 16-byte aligned; rows * C < 2^31. */
+ * ws: 1036 * C floats, 16-byte aligned; rows * C < 2^31. */
 int tgan_bn_fwd_seg(const void* x, int xdt, void* y, int ydt, int64_t rows, int C, int nseg, int64_t r0, int64_t r1,
                     int64_t r2, const float* gamma, const float* beta, float eps, float decay, int unbiased_moving_var,
                     float* moving_mean, float* moving_var, float* mean, float* rstd, float* ws, void* stream);

@@ -56,6 +56,7 @@ template <typename T, int VEC> __device__ __forceinline__ void stv(T* p, int64_t
 template <typename T, int VEC>
 struct BnFwdSegF {
   const T* x; int C;
+  __device__ __forceinline__ void prepare(int, int) {}
   __device__ __forceinline__ void operator()(int64_t r, int c, int, float (&a)[VEC], float (&b)[VEC]) const {
     ldv<T, VEC>(x, r * C + c, a);
 #pragma unroll
@@ -65,20 +66,26 @@ struct BnFwdSegF {
 template <typename TDY, typename TX, int VEC>
 struct BnBwdSegF {
   const TDY* dy; const TX* x; const float* mean; const float* rstd; int C;
-  __device__ __forceinline__ void operator()(int64_t r, int c, int s, float (&a)[VEC], float (&b)[VEC]) const {
+  float m[VEC], rs[VEC];      // this thread's (segment, channels): loaded once by prepare()
+  __device__ __forceinline__ void prepare(int c, int s) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { m[j] = mean[s * C + c + j]; rs[j] = rstd[s * C + c + j]; }
+  }
+  __device__ __forceinline__ void operator()(int64_t r, int c, int, float (&a)[VEC], float (&b)[VEC]) const {
     float xv[VEC];
     ldv<TDY, VEC>(dy, r * C + c, a);
     ldv<TX, VEC>(x, r * C + c, xv);
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) b[j] = a[j] * ((xv[j] - mean[s * C + c + j]) * rstd[s * C + c + j]);
+    for (int j = 0; j < VEC; ++j) b[j] = a[j] * ((xv[j] - m[j]) * rs[j]);
   }
 };
 
 // grid (ceil(C / CH), parts, nseg); 256 threads = CL channel lanes (VEC channels each) x RL row lanes, CH = CL * VEC
 // channels per CTA; partials [seg][part][2][C] (fp64).  Four rows per thread are in flight (64 B per thread with VEC = 8).
 template <typename F, int VEC>
-__global__ void __launch_bounds__(256) segreduce_kernel(F f, SegRows sg, int C, double* __restrict__ partials) {
+__global__ void __launch_bounds__(256) segreduce_kernel(const F f_in, SegRows sg, int C, double* __restrict__ partials) {
   pdl_entry();
+  F f = f_in;
   constexpr int CL = VEC == 8 ? 8 : 32, RL = 256 / CL, CH = CL * VEC;
   __shared__ double sm[RL][2][CH + 1];
   const int s = blockIdx.z, tx = threadIdx.x % CL, ty = threadIdx.x / CL, c = blockIdx.x * CH + tx * VEC;
@@ -87,6 +94,7 @@ __global__ void __launch_bounds__(256) segreduce_kernel(F f, SegRows sg, int C, 
 #pragma unroll
   for (int j = 0; j < VEC; ++j) { a0[j] = 0.0; a1[j] = 0.0; }
   if (c < C) {
+    f.prepare(c, s);
     int64_t r = sg.begin(s) + (int64_t)blockIdx.y * RL + ty;
     for (; r + 3 * step < r1; r += 4 * step) {
       float u[4][VEC], v[4][VEC];
@@ -123,11 +131,17 @@ __global__ void __launch_bounds__(256) segreduce_kernel(F f, SegRows sg, int C, 
 __device__ __forceinline__ void fold_partials(const double* __restrict__ partials, int parts, int nseg, int C, int c,
                                               double (*lanes)[8][33], double (*out)[33]) {
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int q = 0; q < nseg * 2; ++q) {
-    double t = 0.0;
-    if (c < C)
-      for (int p = ty; p < parts; p += 8) t += partials[(((int64_t)(q >> 1) * parts + p) * 2 + (q & 1)) * C + c];
-    lanes[ty][q][tx] = t;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {      // (unrolled: the loads of all segments / statistics are independent)
+    if (q >= nseg * 2) break;
+    double t0 = 0.0, t1 = 0.0;
+    if (c < C) {
+      const double* pp = partials + ((int64_t)(q >> 1) * parts * 2 + (q & 1)) * C + c;
+      int p = ty;
+      for (; p + 8 < parts; p += 16) { t0 += pp[(int64_t)p * 2 * C]; t1 += pp[(int64_t)(p + 8) * 2 * C]; }
+      if (p < parts) t0 += pp[(int64_t)p * 2 * C];
+    }
+    lanes[ty][q][tx] = t0 + t1;
   }
   __syncthreads();
   {
@@ -176,24 +190,37 @@ struct SegRows32 {
   int n; unsigned end[4]; float inv_rows[4];
   __device__ __forceinline__ int of(unsigned r) const { return (r >= end[0]) + (n > 2 && r >= end[1]) + (n > 3 && r >= end[2]); }
 };
+// per-(segment, channel) coefficient vector: 16-byte loads when VEC == 8 (tables are 16-byte aligned, C % 8 == 0)
+template <int VEC> __device__ __forceinline__ void ldc(const float* __restrict__ t, int i, float (&v)[VEC]) {
+  if constexpr (VEC == 8) {
+    const float4 a = *reinterpret_cast<const float4*>(t + i), b = *reinterpret_cast<const float4*>(t + i + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    v[0] = t[i];
+  }
+}
 template <typename TX, typename TY, int VEC>
 __global__ void bn_apply_seg_kernel(const TX* __restrict__ x, TY* __restrict__ y, unsigned nvec, unsigned cv, int C, SegRows32 sg,
                                     const float* __restrict__ scale, const float* __restrict__ shift) {
   pdl_entry();
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) {
     const unsigned r = i / cv, c = (i - r * cv) * VEC;
-    const int s = sg.of(r);
-    float v[VEC];
+    const int k = sg.of(r) * C + (int)c;
+    float v[VEC], sc[VEC], sh[VEC];
     ldv<TX, VEC>(x, (int64_t)i * VEC, v);
+    ldc<VEC>(scale, k, sc); ldc<VEC>(shift, k, sh);
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) v[j] = v[j] * scale[s * C + c + j] + shift[s * C + c + j];
+    for (int j = 0; j < VEC; ++j) v[j] = v[j] * sc[j] + sh[j];
     stv<TY, VEC>(y, (int64_t)i * VEC, v);
   }
 }
 
-__global__ void __launch_bounds__(256) bn_bwd_fold_seg_kernel(const double* __restrict__ partials, int parts, int nseg, int C,
-                                                              float* __restrict__ s1, float* __restrict__ s2, float* dgamma,
+__global__ void __launch_bounds__(256) bn_bwd_fold_seg_kernel(const double* __restrict__ partials, int parts, SegRows sg, int C,
+                                                              const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                              const float* __restrict__ gamma, float* __restrict__ ca,
+                                                              float* __restrict__ cb, float* __restrict__ cc, float* dgamma,
                                                               float* dbeta, float beta_acc) {
+  const int nseg = sg.n;
   pdl_entry();
   __shared__ double lanes[8][8][33];
   __shared__ double tot[8][33];
@@ -203,8 +230,12 @@ __global__ void __launch_bounds__(256) bn_bwd_fold_seg_kernel(const double* __re
   double t1 = 0.0, t2 = 0.0;
   for (int s = 0; s < nseg; ++s) {
     const float a = (float)tot[2 * s][threadIdx.x], b = (float)tot[2 * s + 1][threadIdx.x];
-    s1[s * C + c] = a; s2[s * C + c] = b;
     t1 += (double)a; t2 += (double)b;      // (per-call path: every call adds its fp32-rounded sums)
+    // dx = g rs (dy - s1/n - xhat s2/n), xhat = (x - mu) rs   ==   ca * dy + cb * x + cc
+    const float inv_n = 1.0f / (float)(sg.end[s] - sg.begin(s));
+    const float g = gamma[c], rs = rstd[s * C + c], mu = mean[s * C + c];
+    const float ca_ = g * rs, cb_ = -g * rs * rs * b * inv_n;
+    ca[s * C + c] = ca_; cb[s * C + c] = cb_; cc[s * C + c] = -ca_ * a * inv_n - cb_ * mu;
   }
   if (dbeta) dbeta[c] = (float)((beta_acc != 0.f ? (double)beta_acc * dbeta[c] : 0.0) + t1);
   if (dgamma) dgamma[c] = (float)((beta_acc != 0.f ? (double)beta_acc * dgamma[c] : 0.0) + t2);
@@ -212,24 +243,19 @@ __global__ void __launch_bounds__(256) bn_bwd_fold_seg_kernel(const double* __re
 
 template <typename TDY, typename TX, typename TDX, int VEC>
 __global__ void bn_bwd_apply_seg_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, TDX* __restrict__ dx, unsigned nvec,
-                                        unsigned cv, int C, SegRows32 sg, const float* __restrict__ mean,
-                                        const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                        const float* __restrict__ s1, const float* __restrict__ s2) {
+                                        unsigned cv, int C, SegRows32 sg, const float* __restrict__ ca,
+                                        const float* __restrict__ cb, const float* __restrict__ cc) {
   pdl_entry();
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) {
     const unsigned r = i / cv, c = (i - r * cv) * VEC;
-    const int s = sg.of(r);
-    const float inv_rows = sg.inv_rows[s];
-    float d[VEC], xv[VEC], o[VEC];
+    const int k = sg.of(r) * C + (int)c;
+    float d[VEC], xv[VEC], a[VEC], b[VEC], e[VEC];
     ldv<TDY, VEC>(dy, (int64_t)i * VEC, d);
     ldv<TX, VEC>(x, (int64_t)i * VEC, xv);
+    ldc<VEC>(ca, k, a); ldc<VEC>(cb, k, b); ldc<VEC>(cc, k, e);
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      const int k = s * C + c + j;
-      const float xh = (xv[j] - mean[k]) * rstd[k];
-      o[j] = gamma[c + j] * rstd[k] * (d[j] - s1[k] * inv_rows - xh * s2[k] * inv_rows);
-    }
-    stv<TDX, VEC>(dx, (int64_t)i * VEC, o);
+    for (int j = 0; j < VEC; ++j) d[j] = a[j] * d[j] + (b[j] * xv[j] + e[j]);
+    stv<TDX, VEC>(dx, (int64_t)i * VEC, d);
   }
 }
 
@@ -276,7 +302,7 @@ static inline int grid1d(int64_t n) {
 
 using namespace tgan;
 
-// ws layout (floats): [0, 1024 C) fp64 partials [nseg][parts <= 64][2][C]; [1024 C, 1032 C) two [4][C] fp32 tables
+// ws layout (floats): [0, 1024 C) fp64 partials [nseg][parts <= 64][2][C]; [1024 C, 1036 C) up to three [4][C] fp32 tables
 extern "C" int tgan_bn_fwd_seg(const void* x, int xdt, void* y, int ydt, int64_t rows, int C, int nseg, int64_t r0, int64_t r1,
                                int64_t r2, const float* gamma, const float* beta, float eps, float decay,
                                int unbiased_moving_var, float* moving_mean, float* moving_var, float* mean, float* rstd,
@@ -326,8 +352,9 @@ extern "C" int tgan_bn_bwd_seg(const void* dy, int dydt, const void* x, int xdt,
   const bool v8 = C % 8 == 0 && aligned16(dy) && aligned16(x) && aligned16(dx);
   const int parts = pick_seg_parts(rows, nseg, C, v8 ? 8 : 1);
   double* partials = reinterpret_cast<double*>(ws);
-  float* s1 = ws + (int64_t)1024 * C;
-  float* s2 = s1 + (int64_t)4 * C;
+  float* ca = ws + (int64_t)1024 * C;       // three [4][C] coefficient tables
+  float* cb = ca + (int64_t)4 * C;
+  float* cc = cb + (int64_t)4 * C;
   TGAN_DISPATCH_1(dydt, TDY, TGAN_DISPATCH_1(xdt, TX, {
     if (v8) {
       BnBwdSegF<TDY, TX, 8> f{(const TDY*)dy, (const TX*)x, mean, rstd, C};
@@ -338,15 +365,15 @@ extern "C" int tgan_bn_bwd_seg(const void* dy, int dydt, const void* x, int xdt,
     }
   }));
   TGAN_LAUNCHED();
-  pdl_launch(bn_bwd_fold_seg_kernel, ceil_div(C, 32), 256, 0, st, (const double*)partials, parts, nseg, C, s1, s2, dgamma, dbeta,
-             beta_acc);
+  pdl_launch(bn_bwd_fold_seg_kernel, ceil_div(C, 32), 256, 0, st, (const double*)partials, parts, sg, C, mean, rstd, gamma, ca, cb, cc,
+             dgamma, dbeta, beta_acc);
   TGAN_LAUNCHED();
   const int64_t n = rows * C;
   TGAN_DISPATCH_1(dydt, TDY, TGAN_DISPATCH_1(xdt, TX, TGAN_DISPATCH_1(dxdt, TDX, {
     if (v8) pdl_launch(bn_bwd_apply_seg_kernel<TDY, TX, TDX, 8>, grid1d(n / 8), 256, 0, st, (const TDY*)dy, (const TX*)x, (TDX*)dx,
-                       (unsigned)(n / 8), (unsigned)(C / 8), C, s32, mean, rstd, gamma, (const float*)s1, (const float*)s2);
+                       (unsigned)(n / 8), (unsigned)(C / 8), C, s32, (const float*)ca, (const float*)cb, (const float*)cc);
     else pdl_launch(bn_bwd_apply_seg_kernel<TDY, TX, TDX, 1>, grid1d(n), 256, 0, st, (const TDY*)dy, (const TX*)x, (TDX*)dx,
-                    (unsigned)n, (unsigned)C, C, s32, mean, rstd, gamma, (const float*)s1, (const float*)s2);
+                    (unsigned)n, (unsigned)C, C, s32, (const float*)ca, (const float*)cb, (const float*)cc);
   })));
   TGAN_LAUNCHED();
   return 0;

@@ -40,11 +40,23 @@ __global__ void __launch_bounds__(256) wn_fwd_part_kernel(const tgan_wn_desc* __
   const int AB = d.A * d.B, per = (AB + WN_SPLITS - 1) / WN_SPLITS;
   const int e0 = blockIdx.z * per, e1 = min(AB, e0 + per);
   float s = 0.f;
-  if (co < d.Co)
-    for (int e = e0 + ty; e < e1; e += 8) {
-      const float v = d.V[wn_idx(e / d.B, co, e % d.B, d.Co, d.B)];
-      s += v * v;
+  if (co < d.Co) {
+    if (d.B == 1) {      // [A, Co]: conv HWIO / dense kernels -- no index division, four rows in flight
+      const float* vp = d.V + co;
+      const int64_t Co = d.Co;
+      int e = e0 + ty;
+      for (; e + 24 < e1; e += 32) {
+        const float v0 = vp[e * Co], v1 = vp[(e + 8) * Co], v2 = vp[(e + 16) * Co], v3 = vp[(e + 24) * Co];
+        s += v0 * v0; s += v1 * v1; s += v2 * v2; s += v3 * v3;
+      }
+      for (; e < e1; e += 8) { const float v = vp[e * Co]; s += v * v; }
+    } else {
+      for (int e = e0 + ty; e < e1; e += 8) {
+        const float v = d.V[wn_idx(e / d.B, co, e % d.B, d.Co, d.B)];
+        s += v * v;
+      }
     }
+  }
   s = fold8(sm, s, tx, ty);
   if (ty == 0 && co < d.Co) part[((int64_t)blockIdx.y * WN_SPLITS + blockIdx.z) * max_co + co] = s;
 }
@@ -74,11 +86,25 @@ __global__ void __launch_bounds__(256) wn_bwd_dot_kernel(const tgan_wn_desc* __r
   const int AB = d.A * d.B, per = (AB + WN_SPLITS - 1) / WN_SPLITS;
   const int e0 = blockIdx.z * per, e1 = min(AB, e0 + per);
   float s = 0.f;
-  if (co < d.Co)
-    for (int e = e0 + ty; e < e1; e += 8) {
-      const int64_t i = wn_idx(e / d.B, co, e % d.B, d.Co, d.B);
-      s += d.dW[i] * d.V[i];
+  if (co < d.Co) {
+    if (d.B == 1) {
+      const float* vp = d.V + co;
+      const float* wp = d.dW + co;
+      const int64_t Co = d.Co;
+      int e = e0 + ty;
+      for (; e + 24 < e1; e += 32) {
+        const float a0 = wp[e * Co], a1 = wp[(e + 8) * Co], a2 = wp[(e + 16) * Co], a3 = wp[(e + 24) * Co];
+        const float b0 = vp[e * Co], b1 = vp[(e + 8) * Co], b2 = vp[(e + 16) * Co], b3 = vp[(e + 24) * Co];
+        s += a0 * b0; s += a1 * b1; s += a2 * b2; s += a3 * b3;
+      }
+      for (; e < e1; e += 8) s += wp[e * Co] * vp[e * Co];
+    } else {
+      for (int e = e0 + ty; e < e1; e += 8) {
+        const int64_t i = wn_idx(e / d.B, co, e % d.B, d.Co, d.B);
+        s += d.dW[i] * d.V[i];
+      }
     }
+  }
   s = fold8(sm, s, tx, ty);
   if (ty == 0 && co < d.Co) part[((int64_t)blockIdx.y * WN_SPLITS + blockIdx.z) * max_co + co] = s;
 }
@@ -98,6 +124,25 @@ __global__ void __launch_bounds__(256) wn_bwd_apply_kernel(const tgan_wn_desc* _
   if (ty == 0 && blockIdx.z == 0) d.dg[co] += dot * inv;
   const int AB = d.A * d.B, per = (AB + WN_SPLITS - 1) / WN_SPLITS;
   const int e0 = blockIdx.z * per, e1 = min(AB, e0 + per);
+  if (d.B == 1) {
+    const int64_t Co = d.Co;
+    int e = e0 + ty;
+    for (; e + 24 < e1; e += 32) {
+      float w[4], v[4], o[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t i = (int64_t)(e + 8 * u) * Co + co;
+        w[u] = d.dW[i]; v[u] = d.V[i]; o[u] = d.dV[i];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) d.dV[(int64_t)(e + 8 * u) * Co + co] = o[u] + gi * (w[u] - v[u] * k);
+    }
+    for (; e < e1; e += 8) {
+      const int64_t i = (int64_t)e * Co + co;
+      d.dV[i] += gi * (d.dW[i] - d.V[i] * k);
+    }
+    return;
+  }
   for (int e = e0 + ty; e < e1; e += 8) {
     const int64_t i = wn_idx(e / d.B, co, e % d.B, d.Co, d.B);
     d.dV[i] += gi * (d.dW[i] - d.V[i] * k);
@@ -175,7 +220,8 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const tgan_pack_desc* _
       const int kb = tile % nbk, r2 = tile / nbk, nb = r2 % nbn, t = r2 / nbn;
       const int tap = t < 32 ? (int)tap_sm[di][t] : (d.taps ? d.taps[t] : t);
       const bool transpose = sk != 1 && sn == 1;
-      const bool edge = (nb * 32 + 32 > Nr) || (kb * 32 + 32 > K);
+      const int smod = d.scale_mod;               // (scale index modulo: only the checked path handles it)
+      const bool edge = (nb * 32 + 32 > Nr) || (kb * 32 + 32 > K) || smod > 0;
       mode[u] = (transpose ? 1 : 0) | (edge ? 2 : 0);
       // rows j = ty + 8 * jj of the tile; lanes tx along the source's contiguous axis
       const int n0 = transpose ? nb * 32 + tx : nb * 32 + ty;      // first n of this thread
@@ -205,8 +251,8 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const tgan_pack_desc* _
           float x = 0.f;
           if (k < K && n_ < Nr) {
             x = sp[jj * sstep];
-            if (son == 1) x *= d.scale[n_];
-            else if (son == 2) x *= d.scale[k];
+            if (son == 1) x *= d.scale[smod > 0 ? n_ % smod : n_];
+            else if (son == 2) x *= d.scale[smod > 0 ? k % smod : k];
           }
           v[u][jj] = x;
         }

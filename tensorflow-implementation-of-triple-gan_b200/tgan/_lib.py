@@ -77,7 +77,7 @@ class TganPackDesc(ctypes.Structure):
     _fields_ = [('src', ctypes.c_void_p), ('dst', ctypes.c_void_p), ('scale', ctypes.c_void_p), ('taps', ctypes.c_void_p),
                 ('st', ctypes.c_int64), ('sn', ctypes.c_int64), ('sk', ctypes.c_int64),
                 ('T', ctypes.c_int), ('Nr', ctypes.c_int), ('K', ctypes.c_int), ('Kpad', ctypes.c_int),
-                ('scale_on', ctypes.c_int), ('pad_', ctypes.c_int)]
+                ('scale_on', ctypes.c_int), ('scale_mod', ctypes.c_int)]
 
 
 _lib = None

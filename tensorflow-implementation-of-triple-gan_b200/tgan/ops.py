@@ -482,7 +482,8 @@ def conv2d_transpose(x, w, kh, kw, stride=2):
         return Var(None, oshape, requires_grad=rg)
     from . import tc
     geom = dict(N=N, h=h, w=wd, Cin=Cin, Cout=Cout, kh=kh, kw=kw, s=stride, pt=pt, pl=pl, Ho=Ho, Wo=Wo)
-    use_tc = ctx.math == 'bf16' and tc.deconv_eligible(geom, x) and not (tc._skinny(geom) and isinstance(w, WNWeight))
+    use_tc = ctx.math == 'bf16' and tc.deconv_eligible(geom, x) and not (
+        tc._skinny(geom) and isinstance(w, WNWeight) and os.environ.get('TGAN_NO_WN_SKINNY_TC'))
     rows, KK = N * h * wd, kh * kw * Cout
     if use_tc:
         tape = ctx.tape

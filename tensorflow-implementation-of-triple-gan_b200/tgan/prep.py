@@ -169,7 +169,7 @@ class PackGroup:
             g[group] = PackGroup(group)
         return g[group]
 
-    def get(self, w, key, T, Nrows, K, st, sn, sk, taps_dev):
+    def get(self, w, key, T, Nrows, K, st, sn, sk, taps_dev, scale_mod=0):
         from .ops import WNWeight
         ver = ctx.store.group_version(self.group)
         wn = isinstance(w, WNWeight)
@@ -187,6 +187,7 @@ class PackGroup:
                 d.scale = we['scale'].data_ptr()
                 assert (sn == w.B) != (sk == w.B), 'cannot tell which packed axis is the output channel'
                 d.scale_on = 1 if sn == w.B else 2
+                d.scale_mod = scale_mod      # k = (tap, co) flattened: the per-channel scale is scale[k % Co]
             e = self.entries[k] = (d, dst, Kpad, taps_dev)
             self.table = None
             if self.version == ver:        # the group was packed without this operand

@@ -62,11 +62,12 @@ def _taps_tensor(taps):
     return _taps_dev[key]
 
 
-def _pack(w, key, T, Nrows, K, st, sn, sk, taps=None):
+def _pack(w, key, T, Nrows, K, st, sn, sk, taps=None, scale_mod=0):
     """Packed bf16 K-major weights [T][Nrows][Kpad] for the current optimiser version.  All operands of a network are
     (re)packed by one multi-tensor launch when its version changes (prep.PackGroup)."""
     from .prep import PackGroup
-    return PackGroup.of(w.key.group).get(w, key, T, Nrows, K, st, sn, sk, None if taps is None else _taps_tensor(taps))
+    return PackGroup.of(w.key.group).get(w, key, T, Nrows, K, st, sn, sk, None if taps is None else _taps_tensor(taps),
+                                         scale_mod)
 
 
 def _igemm(x, N, H, W, C, ldx, wp, Kpad, taps, Nout, gh, gw, out, OH, OW, ldo, s=1, os_=1, oo=(0, 0), vh=0, vw=0,
@@ -357,7 +358,8 @@ def _deconv_bwd_skinny(x, w, g, dy):
         _wgrad(xd, 1, 1, rows_in, Cin, ld, col, 1, rows_in, Kc, Kc, [(0, 0)], 1, w.grad_target(), cin_store=K)
     tgt, Cg = _grad_target(x, Cin)
     if tgt.requires_grad:
-        wp, Kpad = _pack(w, ('ddgrad_col', Cg), 1, Cg, K, 0, 1, Cin)     # [ci][(r,c,co)]: k has stride Cin
+        # [ci][(r,c,co)]: k has stride Cin; a weight-normalised filter's per-channel scale is scale[k % Cout]
+        wp, Kpad = _pack(w, ('ddgrad_col', Cg), 1, Cg, K, 0, 1, Cin, scale_mod=Cout)
         dx = _new(tuple(x.shape[:-1]) + (Cg,), torch.bfloat16)
         _igemm(col, 1, 1, rows_in, K, Kc, wp, Kpad, [(0, 0)], Cg, 1, rows_in, dx, 1, rows_in, Cg)
         add_grad(tgt, dx if dx.dtype == tgt.data.dtype else dx.to(tgt.data.dtype))
