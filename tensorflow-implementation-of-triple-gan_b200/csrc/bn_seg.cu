@@ -131,17 +131,17 @@ __global__ void __launch_bounds__(256) segreduce_kernel(const F f_in, SegRows sg
 __device__ __forceinline__ void fold_partials(const double* __restrict__ partials, int parts, int nseg, int C, int c,
                                               double (*lanes)[8][33], double (*out)[33]) {
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  // constant trip counts (parts <= 64 = 8 lanes x 8 rounds, 8 (segment, statistic) pairs): fully unrolled, so the
+  // up to 64 loads of a thread are independent and in flight together (a runtime loop ran at one L2 latency per round)
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {      // (unrolled: the loads of all segments / statistics are independent)
-    if (q >= nseg * 2) break;
-    double t0 = 0.0, t1 = 0.0;
-    if (c < C) {
-      const double* pp = partials + ((int64_t)(q >> 1) * parts * 2 + (q & 1)) * C + c;
-      int p = ty;
-      for (; p + 8 < parts; p += 16) { t0 += pp[(int64_t)p * 2 * C]; t1 += pp[(int64_t)(p + 8) * 2 * C]; }
-      if (p < parts) t0 += pp[(int64_t)p * 2 * C];
+  for (int q = 0; q < 8; ++q) {
+    double v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int p = ty + 8 * i;
+      v[i] = (c < C && q < nseg * 2 && p < parts) ? partials[(((int64_t)(q >> 1) * parts + p) * 2 + (q & 1)) * C + c] : 0.0;
     }
-    lanes[ty][q][tx] = t0 + t1;
+    lanes[ty][q][tx] = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
   }
   __syncthreads();
   {

@@ -121,7 +121,10 @@ def _wgrad(dz, N, gh, gw, Cout, lddz, x, H, W, Cin, ldx, taps, s, dw, cin_store=
 
 
 def conv_eligible(g, x):
-    return g['Cout'] >= 16 and g['kh'] * g['kw'] <= 25 and g['s'] in (1, 2) and g['Cout'] % 8 == 0 and \
+    # dense layers (tf.matmul) of any width >= 64 run on the tensor cores: the MNIST networks are 250 / 500 wide
+    # (Good_GAN.py:93-124, :31-57); an output whose row pitch is not a multiple of 16 bytes is staged (conv_fwd)
+    dense = g['kh'] == 1 and g['kw'] == 1 and g['s'] == 1 and g['Cout'] >= 64 and not os.environ.get('TGAN_NO_ODD_DENSE_TC')
+    return g['Cout'] >= 16 and g['kh'] * g['kw'] <= 25 and g['s'] in (1, 2) and (g['Cout'] % 8 == 0 or dense) and \
         (g['s'] == 1 or (g['H'] % 2 == 0 and g['W'] % 2 == 0))
 
 
@@ -186,12 +189,20 @@ def conv_fwd(x, w, g, colsum=None, segs=None, bias=None, act=0, ldo=None, fused=
     wp, Kpad = _pack(w, 'fprop', kh * kw, Cout, C, C * Cout, 1, Cout)
     taps = [(r - g['pt'], c - g['pl']) for r in range(kh) for c in range(kw)]
     ldo = ldo or Cout
-    z = _new((g['N'] * g['Ho'] * g['Wo'], ldo), torch.bfloat16)
+    rows = g['N'] * g['Ho'] * g['Wo']
+    # TMA stores need a 16-byte row pitch: an odd width (250, 500: only ldo == Cout can be odd, concatenated outputs are
+    # padded by their consumer) goes through an 8-channel-aligned staging tensor and one compaction
+    lds = (ldo + 7) // 8 * 8
+    z = _new((rows, lds), torch.bfloat16)
     if segs and gf is not g:          # plain GEMM: segments become ranges of rows
-        rps = (g['N'] * g['Ho'] * g['Wo']) // sum(segs)
+        rps = rows // sum(segs)
         segs = [n * rps for n in segs]
-    _igemm(xd, gf['N'], gf['H'], gf['W'], C, ld, wp, Kpad, taps, Cout, gf['Ho'], gf['Wo'], z, gf['Ho'], gf['Wo'], ldo,
+    _igemm(xd, gf['N'], gf['H'], gf['W'], C, ld, wp, Kpad, taps, Cout, gf['Ho'], gf['Wo'], z, gf['Ho'], gf['Wo'], lds,
            s=g['s'], colsum=colsum, segs=segs, bias=bias, act=act, fused=fused)
+    if lds != ldo:
+        zc = _new((rows, ldo), torch.bfloat16)
+        _lib.call('tgan_copy_channels', z.data_ptr(), BF16, lds, zc.data_ptr(), BF16, ldo, rows, Cout, _st())
+        return zc
     return z
 
 
@@ -218,7 +229,7 @@ def conv_bwd(x, w, g, dz):
     gf = _flat(g)
     C, Cout, kh, kw, s, pt, pl = g['C'], g['Cout'], g['kh'], g['kw'], g['s'], g['pt'], g['pl']
     rows = g['N'] * g['Ho'] * g['Wo']
-    dzb, _ = _bf16_padded(dz, rows, Cout, Cout)
+    dzb, lddz = _bf16_padded(dz, rows, Cout, Cout)      # (lddz > Cout: odd-width dense layers)
     tgt, Cg = _grad_target(x, C)
     # small layers (fewer tiles than SMs): the filter gradient runs on the side stream beside the input gradient
     par = w.requires_grad and tgt.requires_grad and _small(rows, max(C, Cout))
@@ -228,12 +239,12 @@ def conv_bwd(x, w, g, dz):
             if _small_cin(g):
                 col, K, Kc = g.get('_col') or _im2col(x, g)
                 # dW[(tap, ci), co] = col^T dz: a plain GEMM whose [Kc][Cout] result starts with the K rows of the HWIO gradient
-                _wgrad(dzb, 1, 1, rows, Cout, Cout, col, 1, rows, Kc, Kc, [(0, 0)], 1, dw, cin_store=K)
+                _wgrad(dzb, 1, 1, rows, Cout, lddz, col, 1, rows, Kc, Kc, [(0, 0)], 1, dw, cin_store=K)
             else:
                 xd, ld = g.get('_x') or _bf16_padded(x.data, x.rows, C, x.ld)
                 taps = [(r - pt, c - pl) for r in range(kh) for c in range(kw)]
                 # the kernel writes [t][ci][co] == HWIO
-                _wgrad(dzb, gf['N'], gf['Ho'], gf['Wo'], Cout, Cout, xd, gf['H'], gf['W'], C, ld, taps, s, dw)
+                _wgrad(dzb, gf['N'], gf['Ho'], gf['Wo'], Cout, lddz, xd, gf['H'], gf['W'], C, ld, taps, s, dw)
     if tgt.requires_grad:
         # a label-concatenated input only needs the gradient of its first Cg channels: it goes to the concat's source
         dxt = _new(tuple(x.shape[:-1]) + (Cg,), tgt.data.dtype if tgt.data.dtype == torch.bfloat16 else torch.float32)
@@ -255,10 +266,10 @@ def conv_bwd(x, w, g, dz):
                     tgt.aux['du_q24'] = _ops().arena_take(2 * Cg * len(sg))
                 tgt.aux['du_ready'] = True
                 dx._tgan_du = True
-                _igemm(dzb, g['N'], g['Ho'], g['Wo'], Cout, Cout, wp, Kpad, taps, Cg, g['H'], g['W'], dx, g['H'], g['W'], Cg,
+                _igemm(dzb, g['N'], g['Ho'], g['Wo'], Cout, lddz, wp, Kpad, taps, Cg, g['H'], g['W'], dx, g['H'], g['W'], Cg,
                        colsum=tgt.aux['du_q24'], segs=sg, fused=dict(mask_in=mk, mask_alpha=tgt.aux.get('mask_alpha', 0.2)))
             else:
-                _igemm(dzb, gf['N'], gf['Ho'], gf['Wo'], Cout, Cout, wp, Kpad, taps, Cg, gf['H'], gf['W'], dx, gf['H'],
+                _igemm(dzb, gf['N'], gf['Ho'], gf['Wo'], Cout, lddz, wp, Kpad, taps, Cg, gf['H'], gf['W'], dx, gf['H'],
                        gf['W'], Cs if staged else Cg)
         else:
             # input-gradient of a stride-2 conv = transposed conv: its output-parity classes, heaviest first, in ONE launch
@@ -275,7 +286,7 @@ def conv_bwd(x, w, g, dz):
             sel = [i for c in cl for i in c[2]]
             taps = [t for c in cl for t in c[3]]
             wp, Kpad = _pack(w, ('dgrad2', Cg), len(sel), Cg, Cout, C * Cout, Cout, 1, sel)
-            _igemm(dzb, g['N'], g['Ho'], g['Wo'], Cout, Cout, wp, Kpad, taps, Cg, g['H'] // 2, g['W'] // 2, dx,
+            _igemm(dzb, g['N'], g['Ho'], g['Wo'], Cout, lddz, wp, Kpad, taps, Cg, g['H'] // 2, g['W'] // 2, dx,
                    g['H'], g['W'], Cs if staged else Cg, os_=2, classes=[(len(c[2]), c[0], c[1]) for c in cl])
         if staged:
             _lib.call('tgan_copy_channels', dx.data_ptr(), BF16, Cs, dxt.data_ptr(), dt_code(dxt), Cg, x.rows, Cg, _st())

@@ -45,6 +45,11 @@ CASES = [
     dict(N=16, H=6, W=6, Cin=512, Cout=256, k=1, s=1, pad='SAME'),    # NiN1
     dict(N=16, H=6, W=6, Cin=256, Cout=128, k=1, s=1, pad='SAME'),    # NiN2
     dict(N=16, H=1, W=1, Cin=110, Cout=8192, k=1, s=1, pad='SAME'),   # G fc 110 -> 8192 (32 N-tiles)
+    # the MNIST networks (Good_GAN.py:93-124, :31-57): widths that are not multiples of 8 on either side
+    dict(N=300, H=1, W=1, Cin=794, Cout=1000, k=1, s=1, pad='SAME'),
+    dict(N=300, H=1, W=1, Cin=1010, Cout=500, k=1, s=1, pad='SAME'),
+    dict(N=100, H=1, W=1, Cin=510, Cout=250, k=1, s=1, pad='SAME'),
+    dict(N=120, H=1, W=1, Cin=260, Cout=250, k=1, s=1, pad='SAME'),
 ]
 
 
