@@ -90,9 +90,11 @@ __global__ void __launch_bounds__(256) segreduce_kernel(const F f_in, SegRows sg
   __shared__ double sm[RL][2][CH + 1];
   const int s = blockIdx.z, tx = threadIdx.x % CL, ty = threadIdx.x / CL, c = blockIdx.x * CH + tx * VEC;
   const int64_t r1 = sg.end[s], step = (int64_t)gridDim.y * RL;
-  double a0[VEC], a1[VEC];
+  // per-thread sums (a few dozen rows) in fp32, everything across threads and CTAs in fp64: sixteen fp64 accumulators per
+  // thread cost 32 registers and the compiler then serialised the four row loads (84 registers, 1.8 TB/s in the backward)
+  float a0[VEC], a1[VEC];
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) { a0[j] = 0.0; a1[j] = 0.0; }
+  for (int j = 0; j < VEC; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
   if (c < C) {
     f.prepare(c, s);
     int64_t r = sg.begin(s) + (int64_t)blockIdx.y * RL + ty;
@@ -103,17 +105,17 @@ __global__ void __launch_bounds__(256) segreduce_kernel(const F f_in, SegRows sg
 #pragma unroll
       for (int k = 0; k < 4; ++k)
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) { a0[j] += (double)u[k][j]; a1[j] += (double)v[k][j]; }
+        for (int j = 0; j < VEC; ++j) { a0[j] += u[k][j]; a1[j] += v[k][j]; }
     }
     for (; r < r1; r += step) {
       float u[VEC], v[VEC];
       f(r, c, s, u, v);
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) { a0[j] += (double)u[j]; a1[j] += (double)v[j]; }
+      for (int j = 0; j < VEC; ++j) { a0[j] += u[j]; a1[j] += v[j]; }
     }
   }
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) { sm[ty][0][tx * VEC + j] = a0[j]; sm[ty][1][tx * VEC + j] = a1[j]; }
+  for (int j = 0; j < VEC; ++j) { sm[ty][0][tx * VEC + j] = (double)a0[j]; sm[ty][1][tx * VEC + j] = (double)a1[j]; }
   __syncthreads();
   if (threadIdx.x < 2 * CH) {
     const int a = threadIdx.x / CH, cc = threadIdx.x % CH, co = blockIdx.x * CH + cc;

@@ -21,6 +21,28 @@ __device__ float block_sum(float v, float* sm) {
   return s;
 }
 
+// N block sums behind ONE pair of barriers (loss_c needs 5 scalars + K class means: fifteen separate block_sum calls were
+// thirty barriers, most of the kernel's 10 us); same fixed order as block_sum
+template <int N>
+__device__ __forceinline__ void block_sum_n(float (&v)[N], float (*sm)[LT / 32]) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < N; ++k) v[k] = warp_sum(v[k]);
+  __syncthreads();
+  if (l == 0) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) sm[k][w] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < LT / 32; ++i) s += sm[k][i];
+    v[k] = s;
+  }
+}
+
 // tf.nn.sigmoid_cross_entropy_with_logits
 __device__ __forceinline__ float sig_ce(float x, float z) { return fmaxf(x, 0.f) - x * z + log1pf(expf(-fabsf(x))); }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
@@ -73,7 +95,7 @@ loss_c_kernel(const float* __restrict__ c_real, const float* __restrict__ y_l_c,
               float* g_fake) {
   pdl_entry();
   const int K = KT > 0 ? KT : Krt;
-  __shared__ float sm[32];
+  __shared__ float smn[5 + MAXK][LT / 32];
   __shared__ float q[MAXK];
   const float lambda_1 = lambdas[0], lambda_2 = lambdas[1];
   float p[MAXK];
@@ -109,11 +131,15 @@ loss_c_kernel(const float* __restrict__ c_real, const float* __restrict__ y_l_c,
     l_ent += lse - px;
     if (c_rep) for (int k = 0; k < K; ++k) { float d = x[k] - c_rep[n * K + k]; l_mse += d * d; }
   }
-  l_real = block_sum(l_real, sm); l_fake = block_sum(l_fake, sm);
-  l_unl = block_sum(l_unl, sm); l_ent = block_sum(l_ent, sm); l_mse = block_sum(l_mse, sm);
-  _Pragma("unroll") for (int k = 0; k < K; ++k) {
-    float s = block_sum(qk[k], sm);
-    if (threadIdx.x == 0) q[k] = s / n_unl;
+  {
+    float red[5 + MAXK];
+    red[0] = l_real; red[1] = l_fake; red[2] = l_unl; red[3] = l_ent; red[4] = l_mse;
+    _Pragma("unroll") for (int k = 0; k < MAXK; ++k) red[5 + k] = qk[k];
+    block_sum_n<5 + MAXK>(red, smn);
+    l_real = red[0]; l_fake = red[1]; l_unl = red[2]; l_ent = red[3]; l_mse = red[4];
+    if (threadIdx.x == 0) {
+      _Pragma("unroll") for (int k = 0; k < MAXK; ++k) if (k < K) q[k] = red[5 + k] / n_unl;
+    }
   }
   __syncthreads();
   float l_bal = 0.f;

@@ -99,45 +99,57 @@ __global__ void __launch_bounds__(128) mobn_mean_kernel(const long long* __restr
 // border-class sums of a small-channel tensor (the classifier's 3-channel input), one CTA per image.  Interior pixels
 // (88 % of a 32x32 image) accumulate in registers and meet in a warp shuffle; border pixels and the per-warp interior
 // totals go through Q24 integer atomics in shared memory, so the result does not depend on the order of the adds.
-__global__ void __launch_bounds__(256) class_sums_kernel(const void* __restrict__ x, int xdt, int H, int W, int C, int ld,
+constexpr int CLS_IMGS = 4;      // images per CTA: 4x fewer same-address global atomics at the end (they serialise)
+__global__ void __launch_bounds__(256) class_sums_kernel(const void* __restrict__ x, int xdt, int N, int H, int W, int C, int ld,
                                                          ClsSegs sg, long long* __restrict__ clsum) {
   pdl_entry();
   __shared__ unsigned long long part[9 * 16];
   for (int i = threadIdx.x; i < 9 * 16; i += blockDim.x) part[i] = 0ull;
   __syncthreads();
-  const int n = blockIdx.x;
-  const int s = (n >= sg.end[0]) + (n >= sg.end[1]) + (n >= sg.end[2]);
+  const int n0 = blockIdx.x * CLS_IMGS, n1 = min(N, n0 + CLS_IMGS);
+  int cur = (n0 >= sg.end[0]) + (n0 >= sg.end[1]) + (n0 >= sg.end[2]);
   float mid[16];
 #pragma unroll
   for (int c = 0; c < 16; ++c) mid[c] = 0.f;
-  for (int px = threadIdx.x; px < H * W; px += blockDim.x) {
-    const int xx = px % W, yy = px / W;
-    const int k = (yy == 0 ? 0 : yy == H - 1 ? 2 : 1) * 3 + (xx == 0 ? 0 : xx == W - 1 ? 2 : 1);
-    const int64_t off = ((int64_t)n * H * W + px) * ld;
+  // interior sums of the thread (registers) -> shared memory -> this segment's global Q24 sums; leaves part[] zeroed
+  auto flush = [&](int s) {
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
       if (c >= C) break;
-      float v = xdt == TGAN_BF16 ? __bfloat162float(reinterpret_cast<const bf16*>(x)[off + c])
-                                 : reinterpret_cast<const float*>(x)[off + c];
-      v = __bfloat162float(__float2bfloat16_rn(v));      // the contraction reads the bf16-rounded value
-      if (k == 4) mid[c] += v;
-      else atomicAdd(&part[k * 16 + c], (unsigned long long)__float2ll_rn(v * 16777216.f));
+      float v = mid[c];
+      mid[c] = 0.f;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&part[4 * 16 + c], (unsigned long long)__float2ll_rn(v * 16777216.f));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 9 * 16; i += blockDim.x) {
+      const int k = i / 16, c = i % 16;
+      if (c < C && part[i] != 0ull)
+        atomicAdd(reinterpret_cast<unsigned long long*>(&clsum[((int64_t)s * 9 + k) * C + c]), part[i]);
+      part[i] = 0ull;
+    }
+    __syncthreads();
+  };
+  for (int n = n0; n < n1; ++n) {
+    const int s = (n >= sg.end[0]) + (n >= sg.end[1]) + (n >= sg.end[2]);
+    if (s != cur) { flush(cur); cur = s; }      // (block-uniform)
+    for (int px = threadIdx.x; px < H * W; px += blockDim.x) {
+      const int xx = px % W, yy = px / W;
+      const int k = (yy == 0 ? 0 : yy == H - 1 ? 2 : 1) * 3 + (xx == 0 ? 0 : xx == W - 1 ? 2 : 1);
+      const int64_t off = ((int64_t)n * H * W + px) * ld;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        if (c >= C) break;
+        float v = xdt == TGAN_BF16 ? __bfloat162float(reinterpret_cast<const bf16*>(x)[off + c])
+                                   : reinterpret_cast<const float*>(x)[off + c];
+        v = __bfloat162float(__float2bfloat16_rn(v));      // the contraction reads the bf16-rounded value
+        if (k == 4) mid[c] += v;
+        else atomicAdd(&part[k * 16 + c], (unsigned long long)__float2ll_rn(v * 16777216.f));
+      }
     }
   }
-#pragma unroll
-  for (int c = 0; c < 16; ++c) {
-    if (c >= C) break;
-    float v = mid[c];
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&part[4 * 16 + c], (unsigned long long)__float2ll_rn(v * 16777216.f));
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 9 * 16; i += blockDim.x) {
-    const int k = i / 16, c = i % 16;
-    if (c < C && part[i] != 0ull)
-      atomicAdd(reinterpret_cast<unsigned long long*>(&clsum[((int64_t)s * 9 + k) * C + c]), part[i]);
-  }
+  flush(cur);
 }
 
 __global__ void __launch_bounds__(1024) class_sums_wide_kernel(const bf16* __restrict__ x, int H, int W, int C, ClsSegs sg,
@@ -248,7 +260,7 @@ extern "C" int tgan_class_sums(const void* x, int xdt, int N, int H, int W, int 
     TGAN_LAUNCHED();
     return 0;
   }
-  pdl_launch(class_sums_kernel, N, 256, 0, (cudaStream_t)stream, x, xdt, H, W, C, ld, sg, (long long*)clsum);
+  pdl_launch(class_sums_kernel, ceil_div(N, CLS_IMGS), 256, 0, (cudaStream_t)stream, x, xdt, N, H, W, C, ld, sg, (long long*)clsum);
   TGAN_LAUNCHED();
   return 0;
 }

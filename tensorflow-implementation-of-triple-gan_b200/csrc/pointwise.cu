@@ -781,6 +781,21 @@ __global__ void global_pool_bwd_kernel(const TDY* __restrict__ dy, const uint8_t
   stf<TDX>(dx, i, v);
 }
 
+// mean pooling, bf16, 8 channels per thread (D's average_pooling2d(8, 1), Good_GAN_cifar10.py:94): the scalar kernel
+// spends two 64-bit divisions on every element
+__global__ void global_pool_bwd_mean_v8_kernel(const bf16* __restrict__ dy, bf16* __restrict__ dx, unsigned HW, unsigned cv,
+                                               unsigned nvec, float inv) {
+  pdl_entry();
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nvec) return;
+  const unsigned t = i / cv, c8 = i - t * cv, n = t / HW;
+  float v[8];
+  ld8(dy, ((int64_t)n * cv + c8) * 8, v);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] *= inv;
+  st8(dx, (int64_t)i * 8, v);
+}
+
 template <typename TX, typename TO>
 __global__ void concat_label_kernel(const TX* __restrict__ x, int64_t rows, int C, int ldx,
                                     const float* __restrict__ lab, int K, int rps, TO* __restrict__ out, int ldo,
@@ -1091,7 +1106,8 @@ __global__ void __launch_bounds__(256) mobn_small_fwd_kernel(const float* __rest
     pop_mean[threadIdx.x] = pm;
   }
   const int total = sg.end[sg.n - 1] * C;
-  for (int i = threadIdx.x; i < total; i += 256) {
+#pragma unroll 4
+  for (int i = threadIdx.x; i < total; i += 256) {      // (unrolled: four loads in flight instead of one L2 latency per round)
     const int r = i / C, c = i - r * C;
     y[i] = act_fwd(z[i] + (b ? b[c] : 0.f) - mean[small_seg_of(sg, r)][c], act, alpha);
   }
@@ -1113,6 +1129,7 @@ __global__ void __launch_bounds__(256) mobn_small_bwd_kernel(const float* __rest
   }
   if (dz) {
     const int total = sg.end[sg.n - 1] * C;
+#pragma unroll 4
     for (int i = threadIdx.x; i < total; i += 256) {
       const int r = i / C, c = i - r * C;
       const int s = small_seg_of(sg, r);
@@ -1477,6 +1494,13 @@ extern "C" int tgan_global_pool_bwd(const void* dy, int dydt, const uint8_t* idx
                                     int C, int mode, void* stream) {
   TGAN_CHECK_ARG(dy && dx, "global_pool_bwd: bad args");
   int64_t total = (int64_t)N * HW * C;
+  if (mode != 0 && dydt == TGAN_BF16 && dxdt == TGAN_BF16 && C % 8 == 0 && aligned16(dy) && aligned16(dx) &&
+      total / 8 < ((int64_t)1 << 31)) {
+    pdl_launch(global_pool_bwd_mean_v8_kernel, ceil_div(total / 8, 256), 256, 0, (cudaStream_t)stream, (const bf16*)dy, (bf16*)dx,
+               (unsigned)HW, (unsigned)(C / 8), (unsigned)(total / 8), 1.0f / (float)HW);
+    TGAN_LAUNCHED();
+    return 0;
+  }
   DISPATCH_2(dydt, TDY, dxdt, TDX, (pdl_launch(global_pool_bwd_kernel<TDY, TDX>, ceil_div(total, 256), 256, 0, (cudaStream_t)((cudaStream_t)stream), (const TDY*)dy, idx, (TDX*)dx, N, HW, C, mode, total)));
   TGAN_LAUNCHED();
   return 0;
