@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(128) mobn_mean_kernel(const long long* __restr
 // border-class sums of a small-channel tensor (the classifier's 3-channel input), one CTA per image.  Interior pixels
 // (88 % of a 32x32 image) accumulate in registers and meet in a warp shuffle; border pixels and the per-warp interior
 // totals go through Q24 integer atomics in shared memory, so the result does not depend on the order of the adds.
-constexpr int CLS_IMGS = 4;      // images per CTA: 4x fewer same-address global atomics at the end (they serialise)
+constexpr int CLS_IMGS = 1;      // images per CTA (4 was measured 3x slower: 256 threads walk the images one after the other)
 __global__ void __launch_bounds__(256) class_sums_kernel(const void* __restrict__ x, int xdt, int N, int H, int W, int C, int ld,
                                                          ClsSegs sg, long long* __restrict__ clsum) {
   pdl_entry();

@@ -1063,13 +1063,27 @@ __device__ __forceinline__ void small_seg_colsums(const SmallSegs& sg, int C, fl
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int rows = sg.end[sg.n - 1];
   float a[4] = {0.f, 0.f, 0.f, 0.f};
-  if (tx < C)
-#pragma unroll 8
-    for (int r = ty; r < rows; r += 8) {      // (unrolled: the loads of eight rows are issued before the first add)
-      const float v = val(r * C + tx);
-      const int s = small_seg_of(sg, r);
+  if (tx < C) {
+    // eight rows per round with unpredicated loads (full rounds), then a checked tail: predicated loads with per-load
+    // address arithmetic were compiled to one load in flight per L2 round trip (5-14 us for a 10 KB tensor)
+    int r0 = ty;
+    for (; r0 + 56 < rows; r0 += 64) {
+      float v[8];
+      const int base = r0 * C + tx;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = val(base + 8 * k * C);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int s = small_seg_of(sg, r0 + 8 * k);
+        a[0] += s == 0 ? v[k] : 0.f; a[1] += s == 1 ? v[k] : 0.f; a[2] += s == 2 ? v[k] : 0.f; a[3] += s == 3 ? v[k] : 0.f;
+      }
+    }
+    for (; r0 < rows; r0 += 8) {
+      const float v = val(r0 * C + tx);
+      const int s = small_seg_of(sg, r0);
       a[0] += s == 0 ? v : 0.f; a[1] += s == 1 ? v : 0.f; a[2] += s == 2 ? v : 0.f; a[3] += s == 3 ? v : 0.f;
     }
+  }
 #pragma unroll
   for (int s = 0; s < 4; ++s) part[ty][s][tx] = a[s];
   __syncthreads();
@@ -1106,10 +1120,18 @@ __global__ void __launch_bounds__(256) mobn_small_fwd_kernel(const float* __rest
     pop_mean[threadIdx.x] = pm;
   }
   const int total = sg.end[sg.n - 1] * C;
-#pragma unroll 4
-  for (int i = threadIdx.x; i < total; i += 256) {      // (unrolled: four loads in flight instead of one L2 latency per round)
-    const int r = i / C, c = i - r * C;
-    y[i] = act_fwd(z[i] + (b ? b[c] : 0.f) - mean[small_seg_of(sg, r)][c], act, alpha);
+  for (int i0 = threadIdx.x; i0 < total; i0 += 1024) {      // four elements per round, loads first
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = i0 + 256 * k < total ? z[i0 + 256 * k] : 0.f;
+    asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + 256 * k;
+      if (i >= total) break;
+      const int r = i / C, c = i - r * C;
+      y[i] = act_fwd(v[k] + (b ? b[c] : 0.f) - mean[small_seg_of(sg, r)][c], act, alpha);
+    }
   }
 }
 
@@ -1129,12 +1151,23 @@ __global__ void __launch_bounds__(256) mobn_small_bwd_kernel(const float* __rest
   }
   if (dz) {
     const int total = sg.end[sg.n - 1] * C;
-#pragma unroll 4
-    for (int i = threadIdx.x; i < total; i += 256) {
-      const int r = i / C, c = i - r * C;
-      const int s = small_seg_of(sg, r);
-      const int n = sg.end[s] - (s ? sg.end[s - 1] : 0);
-      dz[i] = dy[i] * act_grad_from_y(y[i], act, alpha) - (subtract_mean ? sums[s][c] / (float)n : 0.f);
+    for (int i0 = threadIdx.x; i0 < total; i0 += 1024) {
+      float d[4], yy[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const bool ok = i0 + 256 * k < total;
+        d[k] = ok ? dy[i0 + 256 * k] : 0.f; yy[k] = ok ? y[i0 + 256 * k] : 0.f;
+      }
+      asm volatile("" : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]), "+f"(yy[0]), "+f"(yy[1]), "+f"(yy[2]), "+f"(yy[3]));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = i0 + 256 * k;
+        if (i >= total) break;
+        const int r = i / C, c = i - r * C;
+        const int s = small_seg_of(sg, r);
+        const int n = sg.end[s] - (s ? sg.end[s - 1] : 0);
+        dz[i] = d[k] * act_grad_from_y(yy[k], act, alpha) - (subtract_mean ? sums[s][c] / (float)n : 0.f);
+      }
     }
   }
 }

@@ -113,6 +113,35 @@ def test_tc_deconv_fwd_bwd(c):
     assert relerr(tnp(p.grad), wt.grad.numpy()) < 2e-3
 
 
+def test_tc_weightnorm_rgb_deconv():
+    """the Good_GAN generator's last layer (Good_GAN.py:57: `_WN_deconv2d`, 138 -> 3 channels, norm over axes [0, 1, 3]) on
+    the tensor-core path: the packed operands fold g / ||V|| per OUTPUT channel -- in the input-gradient operand the GEMM K
+    axis is (row, column, channel) flattened, so the scale index is taken modulo the channel count (tgan_pack_desc.scale_mod)"""
+    from tgan import core, ops
+    rng = np.random.default_rng(8)
+    N, Cin, Cout = 4, 138, 3
+    x = bf(rng.standard_normal((N, 16, 16, Cin)))
+    V = rng.standard_normal((5, 5, Cout, Cin)) * 0.05
+    g = rng.uniform(0.5, 1.5, Cout)
+    xt, Vt, gt = T(x, True), T(V, True), T(g, True)
+    W = gt.view(1, 1, -1, 1) * O.l2_normalize(Vt, (0, 1, 3))
+    Wq = W + (torch.tensor(bf(W.detach().numpy())) - W.detach())      # the MMA reads the bf16-rounded effective filter
+    yt = O.conv2d_transpose_tf(xt, Wq, 2)
+    gy = bf(rng.standard_normal(tuple(yt.shape)))
+    yt.backward(T(gy))
+    pV, pg = param(V), param(g)
+    core.ctx.store.bump()
+    with core.recording():
+        xv = ops.Var(torch.tensor(x, dtype=torch.float32).cuda().to(torch.bfloat16), x.shape, requires_grad=True)
+        out = ops.conv2d_transpose(xv, ops.WNWeight(pV, pg, 25, Cout, Cin, 1), 5, 5, 2)
+        fwd = tnp(out.data)
+        run_bwd(out, gy)
+    assert relerr(fwd, yt.detach().numpy()) < 6e-3
+    assert relerr(tnp(xv.grad), xt.grad.numpy()) < 6e-3
+    assert relerr(tnp(pV.grad), Vt.grad.numpy()) < 4e-3
+    assert relerr(tnp(pg.grad), gt.grad.numpy()) < 4e-3
+
+
 def test_tc_padded_concat_input():
     """label-concatenated activations (13/42/74/138/522 channels) are stored with a zero-padded pixel stride."""
     from tgan import core, ops
