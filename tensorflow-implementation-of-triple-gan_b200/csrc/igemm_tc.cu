@@ -183,6 +183,15 @@ __device__ __noinline__ void ig_slow_chunk(const IgParams& p, float* v, int pbas
   }
 }
 
+__device__ __noinline__ void ig_sum_boundary(const IgParams& p, const float* v, int n, int ox0, int lim, float* cs) {
+#pragma unroll 1
+  for (int jc = 0; jc < n; ++jc) {
+    const int ox = ox0 + jc;
+    const float xs = (jc < lim) ? v[jc] : 0.f;
+    cs[(ox >= p.seg_end[0]) + (ox >= p.seg_end[1]) + (ox >= p.seg_end[2])] += xs;
+  }
+}
+
 // Per-segment channel sums of one chunk of 32 tile pixels (TMA-store path: the store itself needs no geometry, the
 // statistics still must skip pixels outside the valid grid).  A run of TW pixels lies in one image row.
 template <int TW>
@@ -200,14 +209,13 @@ __device__ __forceinline__ void ig_sum_chunk(const IgParams& p, const float (&v)
     const int oxl = ox0 + TW - 1;
     const int sgb = (oxl >= p.seg_end[0]) + (oxl >= p.seg_end[1]) + (oxl >= p.seg_end[2]);
     if (p.segflat && sga != sgb) {      // a segment boundary falls inside this run of pixels: classify every pixel
+      // (rare: at most three runs per launch.  Out of line on a copy, so that the hot path stays short and v[] in registers)
+      float tmp[TW], cs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int jc = 0; jc < TW; ++jc) {
-        const int ox = ox0 + jc;
-        const float xs = (jc < lim) ? v[sgm * TW + jc] : 0.f;
-        const int sgj = (ox >= p.seg_end[0]) + (ox >= p.seg_end[1]) + (ox >= p.seg_end[2]);
-        csum[0] += sgj == 0 ? xs : 0.f; csum[1] += sgj == 1 ? xs : 0.f;
-        csum[2] += sgj == 2 ? xs : 0.f; csum[3] += sgj == 3 ? xs : 0.f;
-      }
+      for (int jc = 0; jc < TW; ++jc) tmp[jc] = v[sgm * TW + jc];
+      ig_sum_boundary(p, tmp, TW, ox0, lim, cs);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) csum[k] += cs[k];
       continue;
     }
     float s = 0.f;
@@ -239,6 +247,14 @@ __device__ __forceinline__ void ig_cls_chunk(const float (&vr)[32], int p0, int 
   }
 }
 
+// FUSED / RARE prune the epilogue at compile time.  ncu's source page of the all-in-one kernel (profiles/
+// r2_ncu_igemm250_source_summary.txt): one pass of the epilogue body executes ~290 instructions scattered over 85 KB of SASS
+// (every activation, the fused mean-only-BN stages, the direct-store path), and a third of the epilogue warps' stall
+// samples are instruction fetches (stall_no_inst).  The launches of the step fall into three groups:
+//   <false, false>  bf16 TMA-store output, activation none / leaky ReLU, optional channel sums   (most launches)
+//   <true,  false>  the same plus the fused mean-only-BN stages (per-segment bias, masks, class sums)
+//   <true,  true >  everything (tanh / sigmoid / relu / softplus, fp32 or narrow outputs through the direct store)
+template <bool FUSED, bool RARE>
 __global__ void __launch_bounds__(IG_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
              const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
@@ -471,14 +487,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         p.d_tiles_x.divmod(mt, t2, tx);
         p.d_tiles_y.divmod(t2, ng, ty);
         uint8_t* const ost = ostage + (obuf ? OSTAGE_B_DELTA : 0);
-        if (p.tstore) {           // the store that last used THIS staging buffer must have finished reading it
+        if (!RARE || p.tstore) {           // the store that last used THIS staging buffer must have finished reading it
           if (warp == 2 && lane == 0) { if (two_stage) bulk_wait_read1(); else bulk_wait_read0(); }
           named_bar_sync(1, 256);
         }
         // linear index of the box's first pixel (host guarantees full-width tiles of one image, or one flat row, whenever
         // masks / class sums / per-segment biases are requested) and the batch segment the box belongs to
         const int box_p0 = ((ng * p.nb) * p.OH + ty * p.th) * p.OW + tx * p.tw;
-        if (p.bias_seg || p.clsum) {
+        if (FUSED && (p.bias_seg || p.clsum)) {
           const int key = p.segflat ? box_p0 : ng * p.nb;
           tile_seg = (key >= p.seg_end[0]) + (key >= p.seg_end[1]) + (key >= p.seg_end[2]);
           if (p.bias_seg) bias = cvalid ? p.bias[tile_seg * p.Nout + co] : 0.f;
@@ -502,18 +518,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
           if (p.act == TGAN_ACT_LRELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
-          } else if (p.act == TGAN_ACT_RELU) {
+          } else if (RARE && p.act == TGAN_ACT_RELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          } else if (p.act == TGAN_ACT_TANH && p.tstore) {
+          } else if (RARE && p.act == TGAN_ACT_TANH && p.tstore) {
             // bf16 output: 1 - 2/(e^2x + 1) with the fast exponential (abs. error ~1e-7, far below the bf16 rounding);
             // fp32 outputs take the exact tanhf of the out-of-line path
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 1.f - __fdividef(2.f, __expf(2.f * v[j]) + 1.f);
-          } else if (p.act == TGAN_ACT_SIGMOID && p.tstore) {
+          } else if (RARE && p.act == TGAN_ACT_SIGMOID && p.tstore) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __fdividef(1.f, 1.f + __expf(-v[j]));
-          } else if (p.act != TGAN_ACT_NONE) {
+          } else if (RARE && p.act != TGAN_ACT_NONE) {
             float tmp[32];            // a separate copy: taking v's address would move v to local memory on the hot path too
 #pragma unroll
             for (int j = 0; j < 32; ++j) tmp[j] = v[j];
@@ -521,7 +537,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = tmp[j];
           }
-          if (p.mask_in && cvalid) {      // input gradient through the producer's leaky ReLU: du = dy * lrelu'(y)
+          if (FUSED && p.mask_in && cvalid) {      // input gradient through the producer's leaky ReLU: du = dy * lrelu'(y)
             // bit 31 - j of the word = sign bit of the producer's stored value j (set = negative side = slope alpha)
             const uint32_t mw = p.mask_in[(size_t)((box_p0 + pbase) >> 5) * p.Nout + co];
             const float sl = p.mask_alpha;
@@ -529,10 +545,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             for (int j = 0; j < 32; ++j)
               if (mw & (0x80000000u >> j)) v[j] *= sl;
           }
-          if (p.tstore) {
+          if (!RARE || p.tstore) {
             // ---- staged path: [pixel][channel] rows in shared memory, one bulk-tensor store per 128-pixel box.  The
             // store needs no geometry (TMA clips at the valid extents); 32 lanes write 32 consecutive channels = 64 B.
-            if (p.mask_out || p.clsum) {
+            if (FUSED && (p.mask_out || p.clsum)) {
               const int p0 = box_p0 + pbase;
               const int total_px = p.segflat ? p.vw : p.N * p.OH * p.OW;
               const int valid = total_px - p0;           // pixels of this chunk inside the tensor (flat GEMM tail)
@@ -562,7 +578,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             bf16* srow = reinterpret_cast<bf16*>(ost) + (size_t)pbase * 128 + (q * 32 + lane);
 #pragma unroll
             for (int j = 0; j < 32; ++j) srow[j * 128] = __float2bfloat16_rn(v[j]);
-          } else if (!TGAN_DBG(4)) {
+          } else if (RARE && !TGAN_DBG(4)) {
             float tmp[32], cs2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int j = 0; j < 32; ++j) tmp[j] = v[j];
@@ -571,7 +587,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             for (int j = 0; j < 4; ++j) csum[j] += cs2[j];
           }
         }
-        if (p.tstore) {
+        if (!RARE || p.tstore) {
           fence_proxy_async();
           named_bar_sync(1, 256);
           if (warp == 2 && lane == 0 && !TGAN_DBG(4)) {
@@ -588,7 +604,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             atomicAdd(reinterpret_cast<unsigned long long*>(&p.colsum[gg * p.Nout + co]),
                       (unsigned long long)__float2ll_rn(csum[gg] * 16777216.f));
       }
-      if (p.clsum && cvalid) {        // a tile lies inside one batch segment (one image, or 256 pixels of one flat image)
+      if (FUSED && p.clsum && cvalid) {        // a tile lies inside one batch segment (one image, or 256 pixels of one flat image)
 #pragma unroll
         for (int k = 0; k < 9; ++k)
           if (bsum[k] != 0.f)
@@ -600,7 +616,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       if (lane == 0) mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; accphase ^= 1; }
     }
-    if (p.tstore && warp == 2 && lane == 0) bulk_wait_read0();   // staging buffer must outlive the last store's read
+    if ((!RARE || p.tstore) && warp == 2 && lane == 0) bulk_wait_read0();   // staging buffer must outlive the last store's read
   }
   tc_fence_before();
   __syncthreads();
@@ -986,7 +1002,9 @@ extern "C" int tgan_igemm_bf16(const tgan_igemm_args* a, void* stream) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(igemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(igemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     TGAN_CHECK_ARG(e == cudaSuccess, "igemm: cannot set max dynamic smem: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -994,7 +1012,15 @@ extern "C" int tgan_igemm_bf16(const tgan_igemm_args* a, void* stream) {
   p.d_ct.set(p.ct_tiles); p.d_tpc.set(p.pp_tiles * p.ct_tiles);
   const int total = p.pp_tiles * p.ct_tiles * p.ncls;
   const int grid = total < 148 ? total : 148;
-  pdl_launch(igemm_kernel, grid, IG_THREADS, smem_bytes, (cudaStream_t)((cudaStream_t)stream), tmX, tmW, tmXh, tmO[0], tmO[1], tmO[2], tmO[3], p);
+  // epilogue variant (see igemm_kernel): the pruned instantiations are exact subsets of the full one
+  static const bool one_kernel = getenv("TGAN_IGEMM_ONE_KERNEL") != nullptr;
+  const bool common = p.tstore && (p.act == TGAN_ACT_NONE || p.act == TGAN_ACT_LRELU) && !one_kernel;
+  if (!common)
+    pdl_launch(igemm_kernel<true, true>, grid, IG_THREADS, smem_bytes, (cudaStream_t)stream, tmX, tmW, tmXh, tmO[0], tmO[1], tmO[2], tmO[3], p);
+  else if (fused)
+    pdl_launch(igemm_kernel<true, false>, grid, IG_THREADS, smem_bytes, (cudaStream_t)stream, tmX, tmW, tmXh, tmO[0], tmO[1], tmO[2], tmO[3], p);
+  else
+    pdl_launch(igemm_kernel<false, false>, grid, IG_THREADS, smem_bytes, (cudaStream_t)stream, tmX, tmW, tmXh, tmO[0], tmO[1], tmO[2], tmO[3], p);
   TGAN_LAUNCHED();
   return 0;
 }
