@@ -219,8 +219,13 @@ __device__ __forceinline__ void ig_sum_chunk(const IgParams& p, const float (&v)
       continue;
     }
     float s = 0.f;
+    if (lim >= TW) {            // the whole run is inside the image (warp-uniform: lanes differ in the channel only)
 #pragma unroll
-    for (int jc = 0; jc < TW; ++jc) s += (jc < lim) ? v[sgm * TW + jc] : 0.f;
+      for (int jc = 0; jc < TW; ++jc) s += v[sgm * TW + jc];
+    } else {
+#pragma unroll
+      for (int jc = 0; jc < TW; ++jc) s += (jc < lim) ? v[sgm * TW + jc] : 0.f;
+    }
     const int sg = p.segflat ? sga : (n >= p.seg_end[0]) + (n >= p.seg_end[1]) + (n >= p.seg_end[2]);
     csum[0] += sg == 0 ? s : 0.f; csum[1] += sg == 1 ? s : 0.f;
     csum[2] += sg == 2 ? s : 0.f; csum[3] += sg == 3 ? s : 0.f;
