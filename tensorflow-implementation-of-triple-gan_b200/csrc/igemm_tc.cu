@@ -256,10 +256,11 @@ __device__ __forceinline__ void ig_cls_chunk(const float (&vr)[32], int p0, int 
 // r2_ncu_igemm250_source_summary.txt): one pass of the epilogue body executes ~290 instructions scattered over 85 KB of SASS
 // (every activation, the fused mean-only-BN stages, the direct-store path), and a third of the epilogue warps' stall
 // samples are instruction fetches (stall_no_inst).  The launches of the step fall into three groups:
-//   <false, false>  bf16 TMA-store output, activation none / leaky ReLU, optional channel sums   (most launches)
-//   <true,  false>  the same plus the fused mean-only-BN stages (per-segment bias, masks, class sums)
-//   <true,  true >  everything (tanh / sigmoid / relu / softplus, fp32 or narrow outputs through the direct store)
-template <bool FUSED, bool RARE>
+//   <0, false>  bf16 TMA-store output, activation none / leaky ReLU / ReLU, optional channel sums   (most launches)
+//   <1, false>  + the forward stages of the fused mean-only BN (per-segment bias, sign masks out, border-class sums)
+//   <2, false>  + its backward stage (sign masks in: du = dy * lrelu'(y), with the per-segment channel sums of du)
+//   <3, true >  everything (tanh / sigmoid / softplus, fp32 or narrow outputs through the direct store)
+template <int FUSED, bool RARE>
 __global__ void __launch_bounds__(IG_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
              const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
@@ -499,7 +500,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         // linear index of the box's first pixel (host guarantees full-width tiles of one image, or one flat row, whenever
         // masks / class sums / per-segment biases are requested) and the batch segment the box belongs to
         const int box_p0 = ((ng * p.nb) * p.OH + ty * p.th) * p.OW + tx * p.tw;
-        if (FUSED && (p.bias_seg || p.clsum)) {
+        if ((FUSED & 1) && (p.bias_seg || p.clsum)) {
           const int key = p.segflat ? box_p0 : ng * p.nb;
           tile_seg = (key >= p.seg_end[0]) + (key >= p.seg_end[1]) + (key >= p.seg_end[2]);
           if (p.bias_seg) bias = cvalid ? p.bias[tile_seg * p.Nout + co] : 0.f;
@@ -523,7 +524,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
           if (p.act == TGAN_ACT_LRELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
-          } else if (RARE && p.act == TGAN_ACT_RELU) {
+          } else if (p.act == TGAN_ACT_RELU) {      // (one FMNMX per element: the generator's fc / transposed convs)
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
           } else if (RARE && p.act == TGAN_ACT_TANH && p.tstore) {
@@ -542,7 +543,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = tmp[j];
           }
-          if (FUSED && p.mask_in && cvalid) {      // input gradient through the producer's leaky ReLU: du = dy * lrelu'(y)
+          if ((FUSED & 2) && p.mask_in && cvalid) {      // input gradient through the producer's leaky ReLU: du = dy * lrelu'(y)
             // bit 31 - j of the word = sign bit of the producer's stored value j (set = negative side = slope alpha)
             const uint32_t mw = p.mask_in[(size_t)((box_p0 + pbase) >> 5) * p.Nout + co];
             const float sl = p.mask_alpha;
@@ -553,7 +554,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
           if (!RARE || p.tstore) {
             // ---- staged path: [pixel][channel] rows in shared memory, one bulk-tensor store per 128-pixel box.  The
             // store needs no geometry (TMA clips at the valid extents); 32 lanes write 32 consecutive channels = 64 B.
-            if (FUSED && (p.mask_out || p.clsum)) {
+            if ((FUSED & 1) && (p.mask_out || p.clsum)) {
               const int p0 = box_p0 + pbase;
               const int total_px = p.segflat ? p.vw : p.N * p.OH * p.OW;
               const int valid = total_px - p0;           // pixels of this chunk inside the tensor (flat GEMM tail)
@@ -609,7 +610,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             atomicAdd(reinterpret_cast<unsigned long long*>(&p.colsum[gg * p.Nout + co]),
                       (unsigned long long)__float2ll_rn(csum[gg] * 16777216.f));
       }
-      if (FUSED && p.clsum && cvalid) {        // a tile lies inside one batch segment (one image, or 256 pixels of one flat image)
+      if ((FUSED & 1) && p.clsum && cvalid) {        // a tile lies inside one batch segment (one image, or 256 pixels of one flat image)
 #pragma unroll
         for (int k = 0; k < 9; ++k)
           if (bsum[k] != 0.f)
@@ -1007,9 +1008,10 @@ extern "C" int tgan_igemm_bf16(const tgan_igemm_args* a, void* stream) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(igemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(igemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(igemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(igemm_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(igemm_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     TGAN_CHECK_ARG(e == cudaSuccess, "igemm: cannot set max dynamic smem: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -1019,13 +1021,14 @@ extern "C" int tgan_igemm_bf16(const tgan_igemm_args* a, void* stream) {
   const int grid = total < 148 ? total : 148;
   // epilogue variant (see igemm_kernel): the pruned instantiations are exact subsets of the full one
   static const bool one_kernel = getenv("TGAN_IGEMM_ONE_KERNEL") != nullptr;
-  const bool common = p.tstore && (p.act == TGAN_ACT_NONE || p.act == TGAN_ACT_LRELU) && !one_kernel;
-  if (!common)
-    pdl_launch(igemm_kernel<true, true>, grid, IG_THREADS, smem_bytes, (cudaStream_t)stream, tmX, tmW, tmXh, tmO[0], tmO[1], tmO[2], tmO[3], p);
-  else if (fused)
-    pdl_launch(igemm_kernel<true, false>, grid, IG_THREADS, smem_bytes, (cudaStream_t)stream, tmX, tmW, tmXh, tmO[0], tmO[1], tmO[2], tmO[3], p);
-  else
-    pdl_launch(igemm_kernel<false, false>, grid, IG_THREADS, smem_bytes, (cudaStream_t)stream, tmX, tmW, tmXh, tmO[0], tmO[1], tmO[2], tmO[3], p);
+  const bool common = p.tstore && (p.act == TGAN_ACT_NONE || p.act == TGAN_ACT_LRELU || p.act == TGAN_ACT_RELU) && !one_kernel;
+  const bool ffwd = p.bias_seg || p.clsum || p.mask_out, fbwd = p.mask_in != nullptr;
+#define TGAN_IG_LAUNCH(F, R) pdl_launch(igemm_kernel<F, R>, grid, IG_THREADS, smem_bytes, (cudaStream_t)stream, tmX, tmW, tmXh, tmO[0], tmO[1], tmO[2], tmO[3], p)
+  if (!common || (ffwd && fbwd)) TGAN_IG_LAUNCH(3, true);
+  else if (ffwd) TGAN_IG_LAUNCH(1, false);
+  else if (fbwd) TGAN_IG_LAUNCH(2, false);
+  else TGAN_IG_LAUNCH(0, false);
+#undef TGAN_IG_LAUNCH
   TGAN_LAUNCHED();
   return 0;
 }
