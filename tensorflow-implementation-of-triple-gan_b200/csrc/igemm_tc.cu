@@ -129,6 +129,8 @@ struct IgParams {
   // [ctap0[c], ctap0[c] + cT[c]) of dy/dx/the packed weights and writes at output offset (cooy[c], coox[c])
   int ncls, cT[4], ctap0[4], cooy[4], coox[4];
   int halo, halo_rows, halo_dy0;   // row-halo mode: box rows (2*th + 2), smallest dy
+  int nstages;                     // ring depth of the tap-by-tap mode: 4, or 3 for launches with <= 2 stages per tile --
+                                   // the fourth stage's 48 KB then hold the SECOND output staging buffer (as in row-halo mode)
   int nbox;                        // 128-pixel boxes per tile: 2 (UMMA N = 256), or 1 when that leaves SMs without a tile
   // ---- fused mean-only batch norm (nn.py:147-187 without its own pass over the activation) ----
   int bias_seg;                    // bias is [nseg][Nout]: b - mean of the tile's batch segment (the mean is known BEFORE the
@@ -414,7 +416,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             }
           }
           __syncwarp();
-          if (++stage == IG_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == p.nstages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -452,7 +454,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
           if (ks == ksteps - 1) umma_commit(&tfull[acc]); // accumulator complete -> epilogue
         }
         __syncwarp();
-        if (++stage == IG_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == p.nstages) { stage = 0; phase ^= 1; }
       }
       if (++acc == 2) { acc = 0; accphase ^= 1; }
     }
@@ -467,10 +469,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 #ifdef TGAN_SINGLE_OSTAGE
     const bool two_stage = false;
 #else
-    const bool two_stage = p.halo != 0;
+    const bool two_stage = p.halo != 0 || p.nstages == 3;
 #endif
     // (offset arithmetic on the shared-memory base keeps the address space: the staging stores stay STS)
-    constexpr int OSTAGE_B_DELTA = HALO_OSTAGE2_OFFSET - IG_STAGES * IG_STAGE_BYTES;
+    const int OSTAGE_B_DELTA = p.halo ? HALO_OSTAGE2_OFFSET - IG_STAGES * IG_STAGE_BYTES : -IG_STAGE_BYTES;
     int obuf = 0;
     int acc = 0; uint32_t accphase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -975,6 +977,13 @@ extern "C" int tgan_igemm_bf16(const tgan_igemm_args* a, void* stream) {
     }
   }
   { const char* e = getenv("TGAN_IGEMM_NO_HALO"); if (e && atoi(e)) p.halo = 0; }
+  // short K loops (conv1_1 / D's first conv through im2col, small dense layers: <= 2 ring stages per tile) are bound by the
+  // epilogue waiting for the previous box's TMA store to release the single staging buffer, not by load latency
+  {
+    int max_t = a->T;
+    if (a->ncls > 1) { max_t = 0; for (int c = 0; c < a->ncls; ++c) max_t = a->cls_T[c] > max_t ? a->cls_T[c] : max_t; }
+    p.nstages = (!p.halo && p.tstore && max_t * p.kchunks <= 2 && !getenv("TGAN_IGEMM_RING4")) ? 3 : IG_STAGES;
+  }
 
   CUtensorMap tmX, tmW, tmXh, tmO[4];
   {
