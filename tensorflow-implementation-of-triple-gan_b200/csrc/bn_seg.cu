@@ -9,8 +9,10 @@
 //   backward: partial sums (dy, dy * xhat)  ->  fold (s1, s2 per segment; dbeta += sum s1, dgamma += sum s2)  ->
 //             dx = gamma * rstd * (dy - s1/n - xhat * s2/n)
 //
-// Partials are fp64 and folded in a fixed order (bit-reproducible; the backward sums cancel almost exactly, see
-// colreduce.cuh).  HBM-bound: forward reads x twice and writes y once, backward reads dy and x twice and writes dx.
+// A thread sums its few dozen rows in fp32; everything across threads and CTAs is fp64 and folded in a fixed order
+// (bit-reproducible; the backward sums cancel almost exactly, see colreduce.cuh).  HBM-bound: forward reads x twice and
+// writes y once, backward reads dy and x twice and writes dx.  Measured on the Good_GAN classifier's largest layer
+// (52 MB bf16): statistics 4.0 TB/s forward, apply 5.5 TB/s, backward apply 3.1 TB/s.
 #include <type_traits>
 #include "common.cuh"
 
