@@ -568,9 +568,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                 p.mask_out[(size_t)(p0 >> 5) * p.Nout + co] = mw;
               }
               if (p.clsum && valid > 0) {
+                // the values as stored: rounded in PAIRS (F2FP.PACK_AB on the ALU pipe) and unpacked with a shift / a mask;
+                // element-wise F2F conversions go through the quarter-rate conversion unit (ncu: mio / short-scoreboard stalls
+                // in the conv1_1 launch, profiles/r2_ncu_conv11_wgrad_summary.txt)
                 float vr[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) vr[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+                for (int j = 0; j < 16; ++j) {
+                  const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                  const uint32_t u = *reinterpret_cast<const uint32_t*>(&h);
+                  vr[2 * j] = __uint_as_float(u << 16);
+                  vr[2 * j + 1] = __uint_as_float(u & 0xffff0000u);
+                }
                 if (p.cls_lw == 5) ig_cls_chunk<5>(vr, p0, p.cls_lh, valid, bsum);
                 else ig_cls_chunk<4>(vr, p0, p.cls_lh, valid, bsum);
               }

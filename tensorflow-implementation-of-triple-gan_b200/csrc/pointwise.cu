@@ -222,6 +222,14 @@ __device__ __forceinline__ void st8(bf16* p, int64_t i, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p + i) = t;
 }
 
+// bf16 round trip of two values: one F2FP.PACK_AB + a shift and a mask (same round-to-nearest-even as __float2bfloat16_rn)
+__device__ __forceinline__ void round_bf16_pair(float a, float b, float& ra, float& rb) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const uint32_t u = *reinterpret_cast<const uint32_t*>(&h);
+  ra = __uint_as_float(u << 16);
+  rb = __uint_as_float(u & 0xffff0000u);
+}
+
 // Segment-aware mean-only batch norm apply + nonlinearity, whole grouped batch in one launch (bf16, C % 8 == 0):
 //   y = act(z - mean_seg + b),  mean_seg = sums[seg] / rows_seg   (training)   |   mean = pop_mean (test)
 // pop_mean is updated once per segment IN CALL ORDER (the reference runs the calls one after the other).
@@ -663,7 +671,8 @@ __global__ void mobn_pool_dropout_fwd_kernel(const bf16* __restrict__ z, bf16* _
     // the unfused path stores y in bf16 before pooling: round each candidate the same way
     float q[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) q[k] = __bfloat162float(__float2bfloat16_rn(act_fwd_t<ACT>(a[k][j] + sh[j], alpha)));
+    for (int k = 0; k < 4; k += 2)      // rounded in pairs on the ALU pipe (element-wise F2F goes through the quarter-rate unit)
+      round_bf16_pair(act_fwd_t<ACT>(a[k][j] + sh[j], alpha), act_fwd_t<ACT>(a[k + 1][j] + sh[j], alpha), q[k], q[k + 1]);
     float m = q[0]; int k = 0;
     if (q[1] > m) { m = q[1]; k = 1; }
     if (q[2] > m) { m = q[2]; k = 2; }
@@ -722,12 +731,18 @@ __global__ void __launch_bounds__(256) mobn_pool_dropout_bwd_kernel(const bf16* 
     ld8(dy, e, d); ld8(yp, e, yv);
     const uint2 cw = *reinterpret_cast<const uint2*>(code + e);
     const uint32_t cws[2] = {cw.x, cw.y};
-    float o[4][8];
+    float o[4][8], gqv[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const uint32_t cd = (cws[j >> 2] >> (8 * (j & 3))) & 0xff;
-      const float g = (cd & 4) ? d[j] * scale * act_grad_from_y_t<ACT>(yv[j] * inv_scale, alpha) : 0.f;
-      const float gq = __bfloat162float(__float2bfloat16_rn(g));      // du is stored in bf16: sum what is stored
+      gqv[j] = (cd & 4) ? d[j] * scale * act_grad_from_y_t<ACT>(yv[j] * inv_scale, alpha) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) round_bf16_pair(gqv[j], gqv[j + 1], gqv[j], gqv[j + 1]);   // du is stored in bf16: sum what is stored
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t cd = (cws[j >> 2] >> (8 * (j & 3))) & 0xff;
+      const float gq = gqv[j];
       const int k = cd & 3;
       o[0][j] = k == 0 ? gq : 0.f; o[1][j] = k == 1 ? gq : 0.f; o[2][j] = k == 2 ? gq : 0.f; o[3][j] = k == 3 ? gq : 0.f;
       acc[j] += gq;
